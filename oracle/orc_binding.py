@@ -1,0 +1,163 @@
+"""ctypes binding of the CPU oracle (oracle/liborc.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs as the checker / reported baseline. The product package never imports it.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from pitt_object_table_segmentation_b200 import _abi as A
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liborc.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".h"))]
+    srcs.append(os.path.join(_HERE, "..", "include", "pitt_b200.h"))
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "liborc.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_mt19937_nth.restype = C.c_uint32
+    return _LIB
+
+
+def _f4(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    assert a.ndim == 2 and a.shape[1] == 4, a.shape
+    return a
+
+
+def _fp(a):
+    return a.ctypes.data_as(A.f32p) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(A.i32p) if a is not None else None
+
+
+def default_sac_params(model):
+    p = A.SacParams()
+    lib().orc_default_sac_params(int(model), C.byref(p))
+    return p
+
+
+def default_support_sac_params():
+    p = A.SacParams()
+    lib().orc_default_support_sac_params(C.byref(p))
+    return p
+
+
+def mt19937_nth(seed, nth):
+    return int(lib().orc_mt19937_nth(C.c_uint32(seed), int(nth)))
+
+
+def sac_segment(xyz4, nrm4, params):
+    xyz4 = _f4(xyz4)
+    nrm4 = _f4(nrm4) if nrm4 is not None else None
+    n = xyz4.shape[0]
+    inl = np.empty(max(n, 1), np.int32)
+    n_inl, n_co = C.c_int(0), C.c_int(0)
+    co = np.zeros(8, np.float32)
+    info = A.SacInfo()
+    keep = _hold_replay(params)
+    st = lib().orc_sac_segment(_fp(xyz4), _fp(nrm4), n, C.byref(params), _ip(inl), n, C.byref(n_inl), _fp(co),
+                               C.byref(n_co), C.byref(info))
+    del keep
+    assert st == 0, st
+    return {"inliers": inl[: n_inl.value].copy(), "coeffs": co[: n_co.value].copy(), "info": info}
+
+
+def _hold_replay(params):
+    return params.replay_samples  # the caller keeps the numpy array alive; nothing to do
+
+
+def sac_score(xyz4, nrm4, params, samples):
+    xyz4 = _f4(xyz4)
+    nrm4 = _f4(nrm4) if nrm4 is not None else None
+    samples = np.ascontiguousarray(samples, np.int32)
+    H = samples.shape[0]
+    counts = np.zeros(H, np.int32)
+    co = np.zeros((H, 8), np.float32)
+    valid = np.zeros(H, np.uint8)
+    st = lib().orc_sac_score(_fp(xyz4), _fp(nrm4), xyz4.shape[0], C.byref(params), _ip(samples), H, _ip(counts),
+                             _fp(co), valid.ctypes.data_as(C.POINTER(C.c_uint8)))
+    assert st == 0, st
+    return counts, co, valid
+
+
+def sac_select(xyz4, nrm4, params, coeffs):
+    xyz4 = _f4(xyz4)
+    nrm4 = _f4(nrm4) if nrm4 is not None else None
+    n = xyz4.shape[0]
+    co = np.zeros(8, np.float32)
+    co[: len(coeffs)] = coeffs
+    inl = np.empty(max(n, 1), np.int32)
+    n_inl = C.c_int(0)
+    st = lib().orc_sac_select(_fp(xyz4), _fp(nrm4), n, C.byref(params), _fp(co), _ip(inl), n, C.byref(n_inl))
+    assert st == 0, st
+    return inl[: n_inl.value].copy()
+
+
+def sac_refine(xyz4, nrm4, params, coeffs, inliers):
+    xyz4 = _f4(xyz4)
+    nrm4 = _f4(nrm4) if nrm4 is not None else None
+    co = np.zeros(8, np.float32)
+    co[: len(coeffs)] = coeffs
+    inliers = np.ascontiguousarray(inliers, np.int32)
+    out = np.zeros(8, np.float32)
+    info = A.SacInfo()
+    st = lib().orc_sac_refine(_fp(xyz4), _fp(nrm4), xyz4.shape[0], C.byref(params), _fp(co), _ip(inliers),
+                              len(inliers), _fp(out), C.byref(info))
+    assert st == 0, st
+    return out[: A.N_COEFFS[params.model]].copy(), info
+
+
+def pcl_sample_stream(xyz4, model, count):
+    xyz4 = _f4(xyz4)
+    S = A.SAMPLE_SIZE[model]
+    out = np.zeros((count, S), np.int32)
+    st = lib().orc_pcl_sample_stream(_fp(xyz4), xyz4.shape[0], int(model), int(count), _ip(out))
+    assert st == 0, st
+    return out
+
+
+def knn(xyz4, k):
+    xyz4 = _f4(xyz4)
+    n = xyz4.shape[0]
+    idx = np.zeros((n, k), np.int32)
+    sq = np.zeros((n, k), np.float32)
+    st = lib().orc_knn(_fp(xyz4), n, int(k), _ip(idx), _fp(sq))
+    assert st == 0, st
+    return idx, sq
+
+
+def estimate_normals(xyz4, k=50, viewpoint=(0.0, 0.0, 0.0)):
+    xyz4 = _f4(xyz4)
+    n = xyz4.shape[0]
+    out = np.zeros((n, 4), np.float32)
+    vp = (C.c_float * 3)(*viewpoint)
+    st = lib().orc_estimate_normals(_fp(xyz4), n, int(k), vp, _fp(out))
+    assert st == 0, st
+    return out
+
+
+def euclidean_clusters(xyz4, tolerance, min_size, max_size):
+    xyz4 = _f4(xyz4)
+    n = xyz4.shape[0]
+    labels = np.full(n, -1, np.int32)
+    nc = C.c_int(0)
+    st = lib().orc_euclidean_clusters(_fp(xyz4), n, C.c_double(tolerance), int(min_size), int(max_size), _ip(labels),
+                                      C.byref(nc))
+    assert st == 0, st
+    return labels, nc.value

@@ -1,0 +1,301 @@
+"""Python host mirror of the C ABI (include/pitt_b200.h) — thin ctypes calls into libpitt_b200.so.
+
+There is no CPU fallback: `Context()` raises when the CUDA library is missing or no B200 is visible.
+The classes below only marshal numpy arrays; every number is produced by the CUDA kernels in csrc/.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi as A
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpitt_b200.so")
+_LIB = None
+
+# every symbol declared in include/pitt_b200.h
+EXPORTED_SYMBOLS = [
+    "pitt_create", "pitt_create_on_stream", "pitt_destroy", "pitt_last_error", "pitt_version", "pitt_device_count",
+    "pitt_synchronize", "pitt_default_sac_params", "pitt_default_support_sac_params", "pitt_default_support_params",
+    "pitt_default_cluster_params", "pitt_default_frame_params", "pitt_stage_cloud", "pitt_stage_cloud_device",
+    "pitt_set_normals", "pitt_cloud_size", "pitt_cloud_has_normals", "pitt_cloud_device_points",
+    "pitt_cloud_device_normals", "pitt_release_cloud", "pitt_estimate_normals", "pitt_get_normals", "pitt_knn",
+    "pitt_sac_segment", "pitt_sac_score", "pitt_sac_score_device", "pitt_sac_select", "pitt_sac_refine",
+    "pitt_pcl_sample_stream", "pitt_euclidean_clusters", "pitt_find_supports", "pitt_cluster_service",
+    "pitt_primitive_service", "pitt_select_primitive", "pitt_segment_frame", "pitt_fp32_peak", "pitt_last_device_ms",
+    "pitt_kernel_launches",
+]
+
+
+class PittError(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen libpitt_b200.so (built in-tree by __graft_entry__.build()). Raises if it is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise PittError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    lib.pitt_create.restype = vp
+    lib.pitt_create.argtypes = [C.c_int, C.c_uint64]
+    lib.pitt_create_on_stream.restype = vp
+    lib.pitt_create_on_stream.argtypes = [C.c_int, C.c_uint64, vp]
+    lib.pitt_destroy.argtypes = [vp]
+    lib.pitt_last_error.restype = C.c_char_p
+    lib.pitt_last_error.argtypes = [vp]
+    lib.pitt_version.restype = C.c_char_p
+    lib.pitt_synchronize.argtypes = [vp]
+    lib.pitt_stage_cloud.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.pitt_stage_cloud_device.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
+    lib.pitt_set_normals.argtypes = [vp, vp, vp, C.c_int]
+    lib.pitt_cloud_size.argtypes = [vp]
+    lib.pitt_cloud_has_normals.argtypes = [vp]
+    lib.pitt_cloud_device_points.restype = vp
+    lib.pitt_cloud_device_points.argtypes = [vp]
+    lib.pitt_cloud_device_normals.restype = vp
+    lib.pitt_cloud_device_normals.argtypes = [vp]
+    lib.pitt_release_cloud.argtypes = [vp, vp]
+    lib.pitt_estimate_normals.argtypes = [vp, vp, C.c_int, A.f32p]
+    lib.pitt_get_normals.argtypes = [vp, vp, A.f32p]
+    lib.pitt_knn.argtypes = [vp, vp, C.c_int, A.i32p, A.f32p]
+    lib.pitt_sac_segment.argtypes = [vp, vp, C.POINTER(A.SacParams), A.i32p, C.c_int, C.POINTER(C.c_int), A.f32p,
+                                     C.POINTER(C.c_int), C.POINTER(A.SacInfo)]
+    lib.pitt_sac_score.argtypes = [vp, vp, C.POINTER(A.SacParams), A.i32p, C.c_int, A.i32p, A.f32p,
+                                   C.POINTER(C.c_uint8)]
+    lib.pitt_sac_score_device.argtypes = [vp, vp, C.POINTER(A.SacParams), vp, C.c_int, vp]
+    lib.pitt_sac_select.argtypes = [vp, vp, C.POINTER(A.SacParams), A.f32p, A.i32p, C.c_int, C.POINTER(C.c_int)]
+    lib.pitt_sac_refine.argtypes = [vp, vp, C.POINTER(A.SacParams), A.f32p, A.i32p, C.c_int, A.f32p,
+                                    C.POINTER(A.SacInfo)]
+    lib.pitt_pcl_sample_stream.argtypes = [vp, vp, C.c_int, C.c_int, A.i32p]
+    lib.pitt_euclidean_clusters.argtypes = [vp, vp, C.c_double, C.c_int, C.c_int, A.i32p, C.POINTER(C.c_int)]
+    lib.pitt_find_supports.argtypes = [vp, vp, C.POINTER(A.SupportParams), C.POINTER(A.SupportResult)]
+    lib.pitt_cluster_service.argtypes = [vp, vp, C.POINTER(A.ClusterParams), C.POINTER(A.ClustersResult)]
+    lib.pitt_primitive_service.argtypes = [vp, vp, C.POINTER(A.SacParams), C.POINTER(A.PrimitiveResult)]
+    lib.pitt_select_primitive.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_float]
+    lib.pitt_segment_frame.argtypes = [vp, vp, C.POINTER(A.FrameParams), C.POINTER(A.FrameResult)]
+    lib.pitt_fp32_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    lib.pitt_last_device_ms.restype = C.c_double
+    lib.pitt_last_device_ms.argtypes = [vp]
+    lib.pitt_kernel_launches.restype = C.c_int64
+    lib.pitt_kernel_launches.argtypes = [vp]
+    _LIB = lib
+    return lib
+
+
+def default_sac_params(model):
+    p = A.SacParams()
+    load_library().pitt_default_sac_params(int(model), C.byref(p))
+    return p
+
+
+def default_support_sac_params():
+    p = A.SacParams()
+    load_library().pitt_default_support_sac_params(C.byref(p))
+    return p
+
+
+def default_support_params():
+    p = A.SupportParams()
+    load_library().pitt_default_support_params(C.byref(p))
+    return p
+
+
+def default_cluster_params():
+    p = A.ClusterParams()
+    load_library().pitt_default_cluster_params(C.byref(p))
+    return p
+
+
+def default_frame_params():
+    p = A.FrameParams()
+    load_library().pitt_default_frame_params(C.byref(p))
+    return p
+
+
+def select_primitive(plane, sphere, cylinder, cone, priority=0.9):
+    return int(load_library().pitt_select_primitive(int(plane), int(sphere), int(cylinder), int(cone),
+                                                    C.c_float(priority)))
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Cloud:
+    """A cloud staged in HBM (pitt_cloud). Created through Context.stage()."""
+
+    def __init__(self, ctx, handle, n):
+        self.ctx, self.handle, self.n = ctx, handle, n
+
+    def release(self):
+        if self.handle:
+            self.ctx.lib.pitt_release_cloud(self.ctx.handle, self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:
+            pass
+
+    def set_normals(self, nrm):
+        nrm = _f32(nrm)
+        assert nrm.shape == (self.n, 4) or nrm.shape == (self.n, 8)
+        self.ctx._check(self.ctx.lib.pitt_set_normals(self.ctx.handle, self.handle, nrm.ctypes.data, nrm.shape[1] * 4))
+        return self
+
+    @property
+    def device_points(self):
+        return self.ctx.lib.pitt_cloud_device_points(self.handle)
+
+
+class Context:
+    """One CUDA stream on one B200 (pitt_ctx)."""
+
+    def __init__(self, device=0, seed=12345, stream=None):
+        self.lib = load_library()
+        if self.lib.pitt_device_count() <= 0:
+            raise PittError("no CUDA device visible: libpitt_b200 has no CPU fallback")
+        if stream is None:
+            self.handle = self.lib.pitt_create(int(device), int(seed))
+        else:
+            self.handle = self.lib.pitt_create_on_stream(int(device), int(seed), C.c_void_p(int(stream)))
+        if not self.handle:
+            raise PittError("pitt_create failed (no usable CUDA device)")
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.pitt_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, status, allow=()):
+        if status != A.PITT_OK and status not in allow:
+            raise PittError(f"status {status}: {self.lib.pitt_last_error(self.handle).decode()}")
+        return status
+
+    @property
+    def last_device_ms(self):
+        return float(self.lib.pitt_last_device_ms(self.handle))
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.pitt_kernel_launches(self.handle))
+
+    def synchronize(self):
+        self._check(self.lib.pitt_synchronize(self.handle))
+
+    # ---- staging
+    def stage(self, xyz, normals=None):
+        """xyz: (n,3) or (n,4) float32 host array (numpy) -> Cloud in HBM."""
+        xyz = _f32(xyz)
+        assert xyz.ndim == 2 and xyz.shape[1] in (3, 4), xyz.shape
+        h = C.c_void_p()
+        ptr = xyz.ctypes.data if xyz.shape[0] else None
+        self._check(self.lib.pitt_stage_cloud(self.handle, ptr, xyz.shape[1] * 4, xyz.shape[0], C.byref(h)))
+        c = Cloud(self, h, xyz.shape[0])
+        if normals is not None:
+            c.set_normals(normals)
+        return c
+
+    def stage_host_ptr(self, ptr, stride, n):
+        h = C.c_void_p()
+        self._check(self.lib.pitt_stage_cloud(self.handle, C.c_void_p(ptr), stride, n, C.byref(h)))
+        return Cloud(self, h, n)
+
+    def stage_device(self, d_ptr, n):
+        h = C.c_void_p()
+        self._check(self.lib.pitt_stage_cloud_device(self.handle, C.c_void_p(d_ptr), n, C.byref(h)))
+        return Cloud(self, h, n)
+
+    # ---- normals / kNN
+    def estimate_normals(self, cloud, k=50, viewpoint=(0.0, 0.0, 0.0)):
+        vp = (C.c_float * 3)(*viewpoint)
+        self._check(self.lib.pitt_estimate_normals(self.handle, cloud.handle, int(k), vp))
+        out = np.zeros((cloud.n, 4), np.float32)
+        self._check(self.lib.pitt_get_normals(self.handle, cloud.handle, out.ctypes.data_as(A.f32p)))
+        return out
+
+    def knn(self, cloud, k):
+        idx = np.zeros((cloud.n, k), np.int32)
+        sq = np.zeros((cloud.n, k), np.float32)
+        self._check(self.lib.pitt_knn(self.handle, cloud.handle, int(k), idx.ctypes.data_as(A.i32p),
+                                      sq.ctypes.data_as(A.f32p)))
+        return idx, sq
+
+    # ---- sample consensus
+    def sac_segment(self, cloud, params):
+        n = cloud.n
+        inl = np.empty(max(n, 1), np.int32)
+        n_inl, n_co = C.c_int(0), C.c_int(0)
+        co = np.zeros(8, np.float32)
+        info = A.SacInfo()
+        self._check(self.lib.pitt_sac_segment(self.handle, cloud.handle, C.byref(params), inl.ctypes.data_as(A.i32p), n,
+                                              C.byref(n_inl), co.ctypes.data_as(A.f32p), C.byref(n_co), C.byref(info)))
+        return {"inliers": inl[: n_inl.value].copy(), "coeffs": co[: n_co.value].copy(), "info": info}
+
+    def sac_score(self, cloud, params, samples):
+        samples = np.ascontiguousarray(samples, np.int32)
+        H = samples.shape[0]
+        counts = np.zeros(H, np.int32)
+        co = np.zeros((H, 8), np.float32)
+        valid = np.zeros(H, np.uint8)
+        self._check(self.lib.pitt_sac_score(self.handle, cloud.handle, C.byref(params), samples.ctypes.data_as(A.i32p),
+                                            H, counts.ctypes.data_as(A.i32p), co.ctypes.data_as(A.f32p),
+                                            valid.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return counts, co, valid
+
+    def sac_score_device(self, cloud, params, d_samples, H, d_counts):
+        self._check(self.lib.pitt_sac_score_device(self.handle, cloud.handle, C.byref(params), C.c_void_p(d_samples),
+                                                   int(H), C.c_void_p(d_counts)))
+
+    def sac_select(self, cloud, params, coeffs):
+        co = np.zeros(8, np.float32)
+        co[: len(coeffs)] = coeffs
+        inl = np.empty(max(cloud.n, 1), np.int32)
+        n_inl = C.c_int(0)
+        self._check(self.lib.pitt_sac_select(self.handle, cloud.handle, C.byref(params), co.ctypes.data_as(A.f32p),
+                                             inl.ctypes.data_as(A.i32p), cloud.n, C.byref(n_inl)))
+        return inl[: n_inl.value].copy()
+
+    def sac_refine(self, cloud, params, coeffs, inliers):
+        co = np.zeros(8, np.float32)
+        co[: len(coeffs)] = coeffs
+        inliers = np.ascontiguousarray(inliers, np.int32)
+        out = np.zeros(8, np.float32)
+        info = A.SacInfo()
+        self._check(self.lib.pitt_sac_refine(self.handle, cloud.handle, C.byref(params), co.ctypes.data_as(A.f32p),
+                                             inliers.ctypes.data_as(A.i32p), len(inliers),
+                                             out.ctypes.data_as(A.f32p), C.byref(info)))
+        return out[: A.N_COEFFS[params.model]].copy(), info
+
+    def pcl_sample_stream(self, cloud, model, count):
+        out = np.zeros((count, A.SAMPLE_SIZE[model]), np.int32)
+        self._check(self.lib.pitt_pcl_sample_stream(self.handle, cloud.handle, int(model), int(count),
+                                                    out.ctypes.data_as(A.i32p)))
+        return out
+
+    # ---- clustering
+    def euclidean_clusters(self, cloud, tolerance, min_size, max_size):
+        labels = np.full(cloud.n, -1, np.int32)
+        nc = C.c_int(0)
+        self._check(self.lib.pitt_euclidean_clusters(self.handle, cloud.handle, float(tolerance), int(min_size),
+                                                     int(max_size), labels.ctypes.data_as(A.i32p), C.byref(nc)))
+        return labels, nc.value
+
+    # ---- measurement
+    def fp32_peak(self, kind):
+        t = C.c_double(0)
+        self._check(self.lib.pitt_fp32_peak(self.handle, int(kind), C.byref(t)))
+        return t.value

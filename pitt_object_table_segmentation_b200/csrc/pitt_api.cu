@@ -1,0 +1,467 @@
+// pitt_api.cu — the C ABI declared in include/pitt_b200.h: lifecycle, staging (K0), defaults and
+// the seg.segment()-shaped entry points. Service-shaped entry points live in services.cu.
+#include <cfloat>
+#include <cmath>
+
+#include "pitt_common.cuh"
+#include "sac.cuh"
+
+using namespace pitt;
+
+namespace pitt {
+// K0: AoS records with arbitrary stride -> float4 {x,y,z,1}
+__global__ void pack_xyz_kernel(const unsigned char* __restrict__ src, int stride, int n, float4* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = reinterpret_cast<const float*>(src + (size_t)i * stride);
+  dst[i] = make_float4(p[0], p[1], p[2], 1.0f);
+}
+__global__ void pack_normals_kernel(const unsigned char* __restrict__ src, int stride, int curv_off, int n,
+                                    float4* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = reinterpret_cast<const float*>(src + (size_t)i * stride);
+  dst[i] = make_float4(p[0], p[1], p[2], p[curv_off]);
+}
+}  // namespace pitt
+
+extern "C" {
+
+const char* pitt_version(void) { return "pitt_b200 0.1 (sm_100a)"; }
+
+int pitt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+static pitt_ctx* create_impl(int device, uint64_t seed, void* stream, bool own) {
+  int n = pitt_device_count();
+  if (n <= 0 || device < 0 || device >= n) return nullptr;  // no CPU fallback
+  if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+  pitt_ctx* ctx = new pitt_ctx();
+  ctx->device = device;
+  ctx->seed = seed;
+  ctx->own_stream = own;
+  if (own) {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return nullptr; }
+  } else {
+    ctx->stream = (cudaStream_t)stream;
+  }
+  cudaEventCreate(&ctx->ev0);
+  cudaEventCreate(&ctx->ev1);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  return ctx;
+}
+
+pitt_ctx* pitt_create(int device, uint64_t seed) { return create_impl(device, seed, nullptr, true); }
+pitt_ctx* pitt_create_on_stream(int device, uint64_t seed, void* cuda_stream) {
+  return create_impl(device, seed, cuda_stream, false);
+}
+
+void pitt_destroy(pitt_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (void* p : ctx->d_overflow) cudaFree(p);
+  if (ctx->d_arena) cudaFree(ctx->d_arena);
+  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* pitt_last_error(const pitt_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context (no CUDA device?)"; }
+double pitt_last_device_ms(const pitt_ctx* ctx) { return ctx ? ctx->last_ms : 0.0; }
+int64_t pitt_kernel_launches(const pitt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int pitt_synchronize(pitt_ctx* ctx) {
+  if (!ctx) return PITT_ERR_CUDA;
+  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PITT_OK;
+}
+
+// ------------------------------------------------------------------ defaults
+void pitt_default_sac_params(int model, pitt_sac_params* p) {
+  memset(p, 0, sizeof(*p));
+  p->model = model;
+  p->max_iterations = 1000;
+  p->probability = 0.99;
+  p->radius_min = -DBL_MAX;
+  p->radius_max = DBL_MAX;
+  p->min_angle = -DBL_MAX;
+  p->max_angle = DBL_MAX;
+  p->optimize = 1;
+  p->sampler = PITT_SAMPLER_PCL_MT19937;
+  p->stop = PITT_STOP_PCL_ADAPTIVE;
+  const double deg = M_PI / 180.0;
+  (void)deg;
+  switch (model) {
+    case PITT_MODEL_PLANE:  // plane_segmentation_srv.cpp:19-24
+      p->normal_distance_weight = 0.001; p->distance_threshold = 0.007; p->eps_angle = 0.0;
+      p->min_angle = 0.0 / 180.0 * M_PI; p->max_angle = 10.0 / 180.0 * M_PI;
+      break;
+    case PITT_MODEL_SPHERE:  // sphere_segmentation_srv.cpp:19-26
+      p->normal_distance_weight = 0.001; p->distance_threshold = 0.007; p->eps_angle = 0.0;
+      p->radius_min = 0.005; p->radius_max = 0.500;
+      p->min_angle = 100.0 / 180.0 * M_PI; p->max_angle = 180.0 / 180.0 * M_PI;
+      break;
+    case PITT_MODEL_CYLINDER:  // cylinder_segmentation_srv.cpp:23-30
+      p->normal_distance_weight = 0.001; p->distance_threshold = 0.008; p->eps_angle = 0.0001;
+      p->radius_min = 0.005; p->radius_max = 0.500;
+      p->min_angle = 50.0 / 180.0 * M_PI; p->max_angle = 180.0 / 180.0 * M_PI;
+      break;
+    default:  // cone_segmentation_srv.cpp:24-31
+      p->normal_distance_weight = 0.0006; p->distance_threshold = 0.0055; p->eps_angle = 0.4;
+      p->radius_min = 0.001; p->radius_max = 0.500;
+      p->min_angle = 10.0 / 180.0 * M_PI; p->max_angle = 170.0 / 180.0 * M_PI;
+      break;
+  }
+}
+
+void pitt_default_support_sac_params(pitt_sac_params* p) {  // supports_segmentation_srv.cpp:35-37,89-111
+  pitt_default_sac_params(PITT_MODEL_PLANE, p);
+  p->distance_threshold = (double)0.02f;
+  p->normal_distance_weight = (double)0.9f;
+  p->max_iterations = 10;
+  p->min_angle = -DBL_MAX;
+  p->max_angle = DBL_MAX;
+}
+
+void pitt_default_support_params(pitt_support_params* p) {
+  memset(p, 0, sizeof(*p));
+  p->min_iterative_cloud_percentual_size = -1.0f;
+  p->min_iterative_plane_percentual_size = -1.0f;
+  p->variance_threshold_for_horizontal = -1.0f;
+  p->ransac_distance_point_in_shape_threshold = -1.0f;
+  p->ransac_model_normal_distance_weigth = -1.0f;
+  p->ransac_max_iteration_threshold = -1;
+  p->horizontal_axis_len = 1;  // {-1}: srvm::DEFAULT_SERVICE_VEC_PARAMETER_REQUEST
+  p->horizontal_axis[0] = -1.0f;
+  p->support_edge_remove_offset_len = 1;
+  p->support_edge_remove_offset[0] = -1.0f;
+  p->normals_k = 50;
+  p->compute_discarded_normals = 0;
+}
+
+void pitt_default_cluster_params(pitt_cluster_params* p) {  // cluster_segmentation_srv.cpp:32-35
+  p->tolerance = 0.03;
+  p->min_rate = 0.01;
+  p->max_rate = 0.99;
+  p->min_input_size = 30;
+  p->reserved = 0;
+}
+
+void pitt_default_frame_params(pitt_frame_params* p) {
+  memset(p, 0, sizeof(*p));
+  pitt_default_support_params(&p->support);
+  pitt_default_cluster_params(&p->cluster);
+  pitt_default_sac_params(PITT_MODEL_PLANE, &p->plane);
+  pitt_default_sac_params(PITT_MODEL_SPHERE, &p->sphere);
+  pitt_default_sac_params(PITT_MODEL_CYLINDER, &p->cylinder);
+  pitt_default_sac_params(PITT_MODEL_CONE, &p->cone);
+  p->normals_k = 50;
+  p->min_points = 30;
+  p->viewpoint[0] = p->viewpoint[1] = p->viewpoint[2] = 0.0f;
+  p->cone_over_cylinder_priority = 0.9f;
+}
+
+// ------------------------------------------------------------------ staging
+int pitt_stage_cloud(pitt_ctx* ctx, const void* xyz, int stride_bytes, int n, pitt_cloud** out) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!out || n < 0 || (n > 0 && !xyz) || stride_bytes < 12 || (stride_bytes & 3)) return fail(ctx, PITT_ERR_INVALID, "pitt_stage_cloud arguments");
+  cudaSetDevice(ctx->device);
+  CallTimer timer(ctx);
+  pitt_cloud* c = new pitt_cloud();
+  c->n = n;
+  if (n > 0) {
+    cudaError_t e = cudaMalloc((void**)&c->d_xyz, (size_t)n * sizeof(float4));
+    if (e != cudaSuccess) { delete c; return fail(ctx, PITT_ERR_CUDA, "cudaMalloc(cloud)", e); }
+    if (stride_bytes == 16) {
+      // pcl::PointXYZ / PointCloud2 point_step 16: already the HBM layout, one DMA
+      e = cudaMemcpyAsync(c->d_xyz, xyz, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream);
+      if (e != cudaSuccess) { cudaFree(c->d_xyz); delete c; return fail(ctx, PITT_ERR_CUDA, "cudaMemcpyAsync(H2D cloud)", e); }
+    } else {
+      unsigned char* d_raw = nullptr;
+      int s = arena_alloc(ctx, (size_t)n * stride_bytes, &d_raw);
+      if (s != PITT_OK) { cudaFree(c->d_xyz); delete c; return s; }
+      e = cudaMemcpyAsync(d_raw, xyz, (size_t)n * stride_bytes, cudaMemcpyHostToDevice, ctx->stream);
+      if (e != cudaSuccess) { cudaFree(c->d_xyz); delete c; return fail(ctx, PITT_ERR_CUDA, "cudaMemcpyAsync(H2D cloud)", e); }
+      pack_xyz_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_raw, stride_bytes, n, c->d_xyz);
+      ctx->launches++;
+    }
+    e = cudaStreamSynchronize(ctx->stream);  // the caller's buffer is only borrowed for the call
+    if (e != cudaSuccess) { cudaFree(c->d_xyz); delete c; return fail(ctx, PITT_ERR_CUDA, "stage sync", e); }
+  }
+  timer.finish();
+  *out = c;
+  return PITT_OK;
+}
+
+int pitt_stage_cloud_device(pitt_ctx* ctx, const void* d_xyz4, int n, pitt_cloud** out) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!out || n < 0 || (n > 0 && !d_xyz4)) return fail(ctx, PITT_ERR_INVALID, "pitt_stage_cloud_device arguments");
+  cudaSetDevice(ctx->device);
+  pitt_cloud* c = new pitt_cloud();
+  c->n = n;
+  if (n > 0) {
+    cudaError_t e = cudaMalloc((void**)&c->d_xyz, (size_t)n * sizeof(float4));
+    if (e != cudaSuccess) { delete c; return fail(ctx, PITT_ERR_CUDA, "cudaMalloc(cloud)", e); }
+    e = cudaMemcpyAsync(c->d_xyz, d_xyz4, (size_t)n * 16, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e != cudaSuccess) { cudaFree(c->d_xyz); delete c; return fail(ctx, PITT_ERR_CUDA, "cudaMemcpyAsync(D2D cloud)", e); }
+  }
+  *out = c;
+  return PITT_OK;
+}
+
+int pitt_set_normals(pitt_ctx* ctx, pitt_cloud* c, const void* normals, int stride_bytes) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!c || (c->n > 0 && !normals) || (stride_bytes != 16 && stride_bytes != 32)) return fail(ctx, PITT_ERR_INVALID, "pitt_set_normals arguments");
+  cudaSetDevice(ctx->device);
+  CallTimer timer(ctx);
+  if (c->n > 0) {
+    if (!c->d_nrm) PITT_CUDA(ctx, cudaMalloc((void**)&c->d_nrm, (size_t)c->n * sizeof(float4)));
+    if (stride_bytes == 16) {
+      PITT_CUDA(ctx, cudaMemcpyAsync(c->d_nrm, normals, (size_t)c->n * 16, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+      unsigned char* d_raw = nullptr;
+      PITT_TRY(arena_alloc(ctx, (size_t)c->n * stride_bytes, &d_raw));
+      PITT_CUDA(ctx, cudaMemcpyAsync(d_raw, normals, (size_t)c->n * stride_bytes, cudaMemcpyHostToDevice, ctx->stream));
+      pack_normals_kernel<<<cdiv(c->n, 256), 256, 0, ctx->stream>>>(d_raw, stride_bytes, 4, c->n, c->d_nrm);
+      ctx->launches++;
+    }
+    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  c->has_normals = true;
+  timer.finish();
+  return PITT_OK;
+}
+
+int pitt_cloud_size(const pitt_cloud* c) { return c ? c->n : 0; }
+int pitt_cloud_has_normals(const pitt_cloud* c) { return (c && c->has_normals) ? 1 : 0; }
+const void* pitt_cloud_device_points(const pitt_cloud* c) { return c ? c->d_xyz : nullptr; }
+const void* pitt_cloud_device_normals(const pitt_cloud* c) { return (c && c->has_normals) ? c->d_nrm : nullptr; }
+
+void pitt_release_cloud(pitt_ctx* ctx, pitt_cloud* c) {
+  if (!c) return;
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  if (c->d_xyz) cudaFree(c->d_xyz);
+  if (c->d_nrm) cudaFree(c->d_nrm);
+  delete c;
+}
+
+int pitt_get_normals(pitt_ctx* ctx, const pitt_cloud* c, float* out4) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!c || !out4) return fail(ctx, PITT_ERR_INVALID, "pitt_get_normals arguments");
+  if (!c->has_normals) return fail(ctx, PITT_ERR_STATE, "cloud has no normals");
+  cudaSetDevice(ctx->device);
+  if (c->n > 0) {
+    PITT_CUDA(ctx, cudaMemcpyAsync(out4, c->d_nrm, (size_t)c->n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return PITT_OK;
+}
+
+// ------------------------------------------------------------------ seg.segment()
+int pitt_sac_segment(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params* p, int32_t* inliers, int cap,
+                     int* n_inliers, float coeffs[8], int* n_coeffs, pitt_sac_info* info) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!c || !p || !n_inliers || !coeffs || !n_coeffs) return fail(ctx, PITT_ERR_INVALID, "pitt_sac_segment arguments");
+  cudaSetDevice(ctx->device);
+  CallTimer timer(ctx);
+  SacDeviceResult r;
+  *n_inliers = 0;
+  *n_coeffs = 0;
+  PITT_TRY(sac_segment_impl(ctx, c, *p, &r));
+  *n_inliers = r.n_inliers;
+  *n_coeffs = r.n_coeffs;
+  for (int i = 0; i < 8; ++i) coeffs[i] = r.coeffs[i];
+  int status = PITT_OK;
+  if (r.n_inliers > 0) {
+    if (!inliers || cap < r.n_inliers) {
+      status = fail(ctx, PITT_ERR_CAPACITY, "inlier buffer too small");
+    } else {
+      PITT_CUDA(ctx, cudaMemcpyAsync(inliers, r.d_inliers, (size_t)r.n_inliers * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  timer.finish();
+  if (info) {
+    *info = r.info;
+    info->device_ms = ctx->last_ms;
+  }
+  return status;
+}
+
+static int score_common(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params* p, const int* d_samples, int H,
+                        int* d_counts, float* d_coeffs8, uint8_t* d_flags) {
+  if ((p->model == PITT_MODEL_CYLINDER || p->model == PITT_MODEL_CONE) && !c->has_normals)
+    return fail(ctx, PITT_ERR_STATE, "cylinder/cone scoring needs normals on the cloud");
+  const Limits L = limits_for(*p);
+  const ScoreParams sp = score_params_for(*p, L);
+  HypRec* d_recs = nullptr;
+  PITT_TRY(arena_alloc(ctx, (size_t)H, &d_recs));
+  PITT_TRY(sac_estimate(ctx, c, p->model, d_samples, H, L, d_recs, d_coeffs8, d_flags));
+  PITT_TRY(sac_score(ctx, c, p->model, d_recs, H, sp, d_counts));
+  return PITT_OK;
+}
+
+int pitt_sac_score(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params* p, const int32_t* samples, int H,
+                   int32_t* counts, float* coeffs8, uint8_t* valid) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!c || !p || !samples || H < 0 || p->model < 0 || p->model > 3) return fail(ctx, PITT_ERR_INVALID, "pitt_sac_score arguments");
+  if (H == 0) return PITT_OK;
+  cudaSetDevice(ctx->device);
+  CallTimer timer(ctx);
+  const int S = p->model == PITT_MODEL_PLANE ? 3 : p->model == PITT_MODEL_SPHERE ? 4 : p->model == PITT_MODEL_CYLINDER ? 2 : 3;
+  for (size_t i = 0; i < (size_t)H * S; ++i)
+    if (samples[i] < 0 || samples[i] >= c->n) return fail(ctx, PITT_ERR_INVALID, "sample index out of range");
+  int* d_samples = nullptr;
+  int* d_counts = nullptr;
+  float* d_coeffs8 = nullptr;
+  uint8_t* d_flags = nullptr;
+  PITT_TRY(arena_alloc(ctx, (size_t)H * S, &d_samples));
+  PITT_TRY(arena_alloc(ctx, (size_t)H, &d_counts));
+  PITT_TRY(arena_alloc(ctx, (size_t)H * 8, &d_coeffs8));
+  PITT_TRY(arena_alloc(ctx, (size_t)H, &d_flags));
+  PITT_CUDA(ctx, cudaMemcpyAsync(d_samples, samples, (size_t)H * S * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  PITT_TRY(score_common(ctx, c, p, d_samples, H, d_counts, d_coeffs8, d_flags));
+  if (counts) PITT_CUDA(ctx, cudaMemcpyAsync(counts, d_counts, (size_t)H * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  if (coeffs8) PITT_CUDA(ctx, cudaMemcpyAsync(coeffs8, d_coeffs8, (size_t)H * 8 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  std::vector<uint8_t> flags;
+  if (valid) {
+    flags.resize(H);
+    PITT_CUDA(ctx, cudaMemcpyAsync(flags.data(), d_flags, (size_t)H, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (valid)
+    for (int h = 0; h < H; ++h) valid[h] = flags[h] & 1;
+  timer.finish();
+  return PITT_OK;
+}
+
+int pitt_sac_score_device(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params* p, const void* d_samples, int H,
+                          void* d_counts) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!c || !p || !d_samples || !d_counts || H <= 0 || p->model < 0 || p->model > 3) return fail(ctx, PITT_ERR_INVALID, "pitt_sac_score_device arguments");
+  cudaSetDevice(ctx->device);
+  // no CallTimer: nothing here synchronises; callers bracket with their own events
+  arena_reset(ctx);
+  uint8_t* d_flags = nullptr;
+  PITT_TRY(arena_alloc(ctx, (size_t)H, &d_flags));
+  return score_common(ctx, c, p, (const int*)d_samples, H, (int*)d_counts, nullptr, d_flags);
+}
+
+int pitt_sac_select(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params* p, const float* coeffs,
+                    int32_t* inliers, int cap, int* n_inliers) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!c || !p || !coeffs || !n_inliers) return fail(ctx, PITT_ERR_INVALID, "pitt_sac_select arguments");
+  if ((p->model == PITT_MODEL_CYLINDER || p->model == PITT_MODEL_CONE) && !c->has_normals)
+    return fail(ctx, PITT_ERR_STATE, "cylinder/cone selection needs normals on the cloud");
+  cudaSetDevice(ctx->device);
+  CallTimer timer(ctx);
+  const Limits L = limits_for(*p);
+  const ScoreParams sp = score_params_for(*p, L);
+  float* d_co = nullptr;
+  int* d_out = nullptr;
+  int* d_total = nullptr;
+  PITT_TRY(arena_alloc(ctx, 8, &d_co));
+  PITT_TRY(arena_alloc(ctx, (size_t)c->n + 1, &d_out));
+  PITT_TRY(arena_alloc(ctx, 1, &d_total));
+  float h_co[8] = {0};
+  const int NC = (p->model == PITT_MODEL_PLANE || p->model == PITT_MODEL_SPHERE) ? 4 : 7;
+  for (int i = 0; i < NC; ++i) h_co[i] = coeffs[i];
+  PITT_CUDA(ctx, cudaMemcpyAsync(d_co, h_co, sizeof(h_co), cudaMemcpyHostToDevice, ctx->stream));
+  PITT_TRY(sac_select(ctx, c, p->model, d_co, L, sp, d_out, d_total));
+  int total = 0;
+  PITT_CUDA(ctx, cudaMemcpyAsync(&total, d_total, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *n_inliers = total;
+  int status = PITT_OK;
+  if (total > 0) {
+    if (!inliers || cap < total) status = fail(ctx, PITT_ERR_CAPACITY, "inlier buffer too small");
+    else {
+      PITT_CUDA(ctx, cudaMemcpyAsync(inliers, d_out, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  timer.finish();
+  return status;
+}
+
+int pitt_sac_refine(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params* p, const float* coeffs,
+                    const int32_t* inliers, int n_inliers, float* refined, pitt_sac_info* info) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!c || !p || !coeffs || !refined || n_inliers < 0 || (n_inliers > 0 && !inliers)) return fail(ctx, PITT_ERR_INVALID, "pitt_sac_refine arguments");
+  cudaSetDevice(ctx->device);
+  CallTimer timer(ctx);
+  const Limits L = limits_for(*p);
+  const ScoreParams sp = score_params_for(*p, L);
+  const int NC = (p->model == PITT_MODEL_PLANE || p->model == PITT_MODEL_SPHERE) ? 4 : 7;
+  float* d_co = nullptr;
+  float* d_ref = nullptr;
+  int* d_idx = nullptr;
+  int* d_ints = nullptr;
+  PITT_TRY(arena_alloc(ctx, 8, &d_co));
+  PITT_TRY(arena_alloc(ctx, 8, &d_ref));
+  PITT_TRY(arena_alloc(ctx, (size_t)n_inliers + 1, &d_idx));
+  PITT_TRY(arena_alloc(ctx, 4, &d_ints));
+  float h_co[8] = {0};
+  for (int i = 0; i < NC; ++i) h_co[i] = coeffs[i];
+  int h_ints[4] = {n_inliers, 0, 0, 0};
+  PITT_CUDA(ctx, cudaMemcpyAsync(d_co, h_co, sizeof(h_co), cudaMemcpyHostToDevice, ctx->stream));
+  PITT_CUDA(ctx, cudaMemcpyAsync(d_ints, h_ints, sizeof(h_ints), cudaMemcpyHostToDevice, ctx->stream));
+  if (n_inliers > 0) PITT_CUDA(ctx, cudaMemcpyAsync(d_idx, inliers, (size_t)n_inliers * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  if (p->model == PITT_MODEL_PLANE) {
+    PITT_TRY(plane_refine(ctx, c, d_co, d_idx, d_ints, L, sp, d_ref, d_ints + 1));
+  } else {
+    PITT_TRY(lm_refine(ctx, c, p->model, d_co, d_idx, d_ints, n_inliers, d_ref, d_ints + 2));
+  }
+  float h_ref[8];
+  PITT_CUDA(ctx, cudaMemcpyAsync(h_ref, d_ref, sizeof(h_ref), cudaMemcpyDeviceToHost, ctx->stream));
+  PITT_CUDA(ctx, cudaMemcpyAsync(h_ints, d_ints, sizeof(h_ints), cudaMemcpyDeviceToHost, ctx->stream));
+  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < NC; ++i) refined[i] = h_ref[i];
+  timer.finish();
+  if (info) {
+    memset(info, 0, sizeof(*info));
+    info->lm_info = h_ints[2];
+    info->lm_nfev = h_ints[3];
+    info->device_ms = ctx->last_ms;
+  }
+  return PITT_OK;
+}
+
+int pitt_pcl_sample_stream(pitt_ctx* ctx, const pitt_cloud* c, int model, int count, int32_t* out) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!c || !out || count < 0 || model < 0 || model > 3) return fail(ctx, PITT_ERR_INVALID, "pitt_pcl_sample_stream arguments");
+  cudaSetDevice(ctx->device);
+  if (model == PITT_MODEL_PLANE) PITT_TRY(ensure_host_mirror(ctx, c));
+  PclSampleStream s(c->n, model, model == PITT_MODEL_PLANE ? c->h_xyz.data() : nullptr);
+  const int S = model == PITT_MODEL_PLANE ? 3 : model == PITT_MODEL_SPHERE ? 4 : model == PITT_MODEL_CYLINDER ? 2 : 3;
+  for (int h = 0; h < count; ++h)
+    if (!s.next(out + (size_t)h * S)) return fail(ctx, PITT_ERR_INVALID, "cloud smaller than the sample size");
+  return PITT_OK;
+}
+
+int pitt_fp32_peak(pitt_ctx* ctx, int kind, double* tflops) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!tflops || kind < 0 || kind > 2) return fail(ctx, PITT_ERR_INVALID, "pitt_fp32_peak arguments");
+  cudaSetDevice(ctx->device);
+  CallTimer timer(ctx);
+  int s = fp32_peak(ctx, kind, tflops);
+  timer.finish();
+  return s;
+}
+
+/* test hook (not in the public header): route plane scoring through the generic kernel */
+void pitt_debug_force_generic_plane(int on) { g_force_generic_plane = on; }
+
+}  // extern "C"

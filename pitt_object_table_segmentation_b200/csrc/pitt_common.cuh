@@ -1,0 +1,159 @@
+// pitt_common.cuh — context, cloud handle and launch helpers shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pitt_b200.h"
+
+#define PITT_SM_COUNT_DEFAULT 148
+
+struct pitt_ctx {
+  int device = 0;
+  uint64_t seed = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_count = PITT_SM_COUNT_DEFAULT;
+  std::string err;
+  double last_ms = 0.0;
+  int64_t launches = 0;
+  int timing_depth = 0;
+  // pinned host scratch (grow-only)
+  void* h_pin = nullptr;
+  size_t h_pin_bytes = 0;
+  // device scratch (grow-only arena, bump allocated per API call, reset at call entry)
+  char* d_arena = nullptr;
+  size_t d_arena_bytes = 0;
+  size_t d_arena_off = 0;
+  size_t d_call_total = 0;
+  std::vector<void*> d_overflow;  // blocks allocated when the arena was too small (freed at reset)
+};
+
+struct pitt_cloud {
+  int n = 0;
+  float4* d_xyz = nullptr;
+  float4* d_nrm = nullptr;
+  bool has_normals = false;
+  std::vector<float> h_xyz;  // lazy host mirror (n*4)
+  bool h_valid = false;
+};
+
+namespace pitt {
+
+inline int fail(pitt_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (ctx) {
+    ctx->err = what;
+    if (e != cudaSuccess) {
+      ctx->err += ": ";
+      ctx->err += cudaGetErrorString(e);
+    }
+  }
+  return code;
+}
+
+#define PITT_CUDA(ctx, call)                                                  \
+  do {                                                                        \
+    cudaError_t e__ = (call);                                                 \
+    if (e__ != cudaSuccess) return pitt::fail((ctx), PITT_ERR_CUDA, #call, e__); \
+  } while (0)
+
+#define PITT_TRY(expr)              \
+  do {                              \
+    int s__ = (expr);               \
+    if (s__ != PITT_OK) return s__; \
+  } while (0)
+
+// -------- device arena: one cudaMalloc that grows; bump pointer reset at the start of an API call.
+inline void arena_reset(pitt_ctx* ctx) {
+  // blocks that did not fit last time are released and the arena grown to last call's total
+  if (!ctx->d_overflow.empty() || ctx->d_call_total > ctx->d_arena_bytes) {
+    cudaStreamSynchronize(ctx->stream);
+    for (void* p : ctx->d_overflow) cudaFree(p);
+    ctx->d_overflow.clear();
+    if (ctx->d_call_total > ctx->d_arena_bytes) {
+      if (ctx->d_arena) cudaFree(ctx->d_arena);
+      ctx->d_arena = nullptr;
+      ctx->d_arena_bytes = 0;
+      size_t want = ctx->d_call_total + ctx->d_call_total / 4 + (1 << 20);
+      if (cudaMalloc((void**)&ctx->d_arena, want) == cudaSuccess) ctx->d_arena_bytes = want;
+      else cudaGetLastError();
+    }
+  }
+  ctx->d_arena_off = 0;
+  ctx->d_call_total = 0;
+}
+template <typename T>
+inline int arena_alloc(pitt_ctx* ctx, size_t count, T** out) {
+  size_t bytes = (count * sizeof(T) + 255) & ~(size_t)255;
+  if (bytes == 0) bytes = 256;
+  ctx->d_call_total += bytes;
+  if (ctx->d_arena_off + bytes <= ctx->d_arena_bytes) {
+    *out = (T*)(ctx->d_arena + ctx->d_arena_off);
+    ctx->d_arena_off += bytes;
+    return PITT_OK;
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) return fail(ctx, PITT_ERR_CUDA, "cudaMalloc(overflow)", e);
+  ctx->d_overflow.push_back(p);
+  *out = (T*)p;
+  return PITT_OK;
+}
+inline int pinned_reserve(pitt_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->h_pin_bytes) return PITT_OK;
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  ctx->h_pin = nullptr;
+  ctx->h_pin_bytes = 0;
+  size_t want = bytes + bytes / 4 + 4096;
+  cudaError_t e = cudaMallocHost(&ctx->h_pin, want);
+  if (e != cudaSuccess) return fail(ctx, PITT_ERR_CUDA, "cudaMallocHost", e);
+  ctx->h_pin_bytes = want;
+  return PITT_OK;
+}
+
+// RAII bracket for the per-call device timing (outermost API call only).
+struct CallTimer {
+  pitt_ctx* ctx;
+  bool outer;
+  explicit CallTimer(pitt_ctx* c) : ctx(c) {
+    outer = (ctx->timing_depth++ == 0);
+    if (outer) {
+      arena_reset(ctx);
+      cudaEventRecord(ctx->ev0, ctx->stream);
+    }
+  }
+  // call after the stream has been synchronised by the API function
+  void finish() {
+    if (outer) {
+      cudaEventRecord(ctx->ev1, ctx->stream);
+      cudaEventSynchronize(ctx->ev1);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+      ctx->last_ms = ms;
+    }
+  }
+  ~CallTimer() { ctx->timing_depth--; }
+};
+
+inline int ensure_host_mirror(pitt_ctx* ctx, const pitt_cloud* cc) {
+  pitt_cloud* c = const_cast<pitt_cloud*>(cc);
+  if (c->h_valid) return PITT_OK;
+  c->h_xyz.resize((size_t)c->n * 4);
+  if (c->n > 0) {
+    PITT_CUDA(ctx, cudaMemcpyAsync(c->h_xyz.data(), c->d_xyz, (size_t)c->n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  c->h_valid = true;
+  return PITT_OK;
+}
+
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace pitt

@@ -1,0 +1,996 @@
+// sac.cu — RANSAC on the device: hypothesis estimation (K2), inlier scoring (K3), winner
+// selection (K4), ordered inlier selection (K5) and plane least-squares refinement (K6).
+//
+// Replaces pcl::RandomSampleConsensus::computeModel + SACSegmentation::segment reached from
+// seg.segment() at supports_segmentation_srv.cpp:110, plane_segmentation_srv.cpp:67,
+// sphere…:73, cylinder…:126, cone…:127.
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <unordered_map>
+
+#include "pitt_common.cuh"
+#include "sac.cuh"
+#include "sac_device.cuh"
+
+namespace pitt {
+
+// =====================================================================================
+// K2: one thread per hypothesis: minimal sample -> coefficients, validity, scoring record
+// =====================================================================================
+template <int MODEL>
+__global__ void estimate_kernel(const float4* __restrict__ xyz, const float4* __restrict__ nrm,
+                                const int* __restrict__ samples, int H, Limits L, HypRec* __restrict__ recs,
+                                float* __restrict__ coeffs8, uint8_t* __restrict__ flags) {
+  int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  constexpr int S = (MODEL == PITT_MODEL_PLANE) ? 3 : (MODEL == PITT_MODEL_SPHERE) ? 4 : (MODEL == PITT_MODEL_CYLINDER) ? 2 : 3;
+  int s[4];
+#pragma unroll
+  for (int i = 0; i < S; ++i) s[i] = samples[(size_t)h * S + i];
+  float mc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) mc[i] = 0.0f;
+  bool ok;
+  if (MODEL == PITT_MODEL_PLANE) ok = estimate_plane(xyz, s, mc);
+  else if (MODEL == PITT_MODEL_SPHERE) ok = estimate_sphere(xyz, s, mc);
+  else if (MODEL == PITT_MODEL_CYLINDER) ok = estimate_cylinder(xyz, nrm, s, L, mc);
+  else ok = estimate_cone(xyz, nrm, s, L, mc);
+  bool valid = ok && model_valid<MODEL>(L, mc);
+  HypRec r;
+  make_rec<MODEL>(mc, valid, r);
+  recs[h] = r;
+  if (coeffs8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) coeffs8[(size_t)h * 8 + i] = ok ? mc[i] : 0.0f;
+  }
+  flags[h] = (ok ? 1 : 0) | (valid ? 2 : 0);
+}
+
+// coefficients (device, 8 floats) -> one scoring record (isModelValid applied)
+template <int MODEL>
+__global__ void prep_rec_kernel(const float* __restrict__ coeffs, Limits L, HypRec* __restrict__ rec) {
+  float mc[8];
+  for (int i = 0; i < 8; ++i) mc[i] = coeffs[i];
+  bool valid = model_valid<MODEL>(L, mc);
+  HypRec r;
+  make_rec<MODEL>(mc, valid, r);
+  *rec = r;
+}
+
+// =====================================================================================
+// K3 (generic): lanes = points, hypotheses broadcast from shared memory.
+// grid.x = point blocks, grid.y = hypothesis chunks. Each CTA keeps its chunk's counters in
+// shared memory over all of its point tiles and flushes them once with one RED per hypothesis.
+// =====================================================================================
+template <int MODEL, int P, int TPB>
+__global__ void __launch_bounds__(TPB)
+score_kernel(const float4* __restrict__ xyz, const float4* __restrict__ nrm, int n, const HypRec* __restrict__ recs,
+             int H, int hyp_chunk, int pts_per_cta, ScoreParams sp, int* __restrict__ counts) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  HypRec* s_rec = reinterpret_cast<HypRec*>(smem_raw);
+  int* s_cnt = reinterpret_cast<int*>(smem_raw + (size_t)hyp_chunk * sizeof(HypRec));
+  constexpr bool NEED_N = (MODEL == PITT_MODEL_CYLINDER || MODEL == PITT_MODEL_CONE);
+  const int h0 = blockIdx.y * hyp_chunk;
+  const int hc = min(hyp_chunk, H - h0);
+  // stage the hypothesis chunk (16 B per thread per step, coalesced)
+  {
+    const float4* src = reinterpret_cast<const float4*>(recs + h0);
+    float4* dst = reinterpret_cast<float4*>(s_rec);
+    for (int i = threadIdx.x; i < hc * 4; i += TPB) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < hc; i += TPB) s_cnt[i] = 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int p_begin = blockIdx.x * pts_per_cta;
+  const int p_end = min(n, p_begin + pts_per_cta);
+  for (int base = p_begin; base < p_end; base += TPB * P) {
+    f3 pt[P], nv[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      int i = base + p * TPB + threadIdx.x;
+      if (i < p_end) {
+        pt[p] = ld3(xyz, i);
+        if (NEED_N) nv[p] = ld3(nrm, i);
+        else nv[p] = mk3(0.f, 0.f, 0.f);
+      } else {
+        pt[p] = mk3(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+        nv[p] = pt[p];
+      }
+    }
+    for (int h = 0; h < hc; ++h) {
+      RecRegs<MODEL> r;
+      r.load(s_rec + h);
+      if (s_rec[h].v[0] != s_rec[h].v[0]) continue;  // invalid hypothesis (uniform branch)
+      int c = 0;
+#pragma unroll
+      for (int p = 0; p < P; ++p) c += r.inlier(pt[p], nv[p], sp) ? 1 : 0;
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (lane == 0 && c) atomicAdd(&s_cnt[h], c);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < hc; i += TPB) {
+    int c = s_cnt[i];
+    if (c) atomicAdd(&counts[h0 + i], c);
+  }
+}
+
+// =====================================================================================
+// K3p: plane scoring, lanes = hypotheses, points broadcast from shared memory, packed f32x2
+// arithmetic (FMUL2/FADD2 are IEEE round-to-nearest per element => same bits as scalar).
+// Each thread owns KH hypotheses (KH/2 register pairs) and its own counters: no reduction at all
+// until the final RED per hypothesis.
+// =====================================================================================
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  return ((unsigned long long)__float_as_uint(hi) << 32) | (unsigned long long)__float_as_uint(lo);
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false, which would
+// round a*x+c*z once instead of three times. The packed add is therefore issued as
+// fma(x, ONE, y) with ONE = 1.0f taken from a kernel argument: round(x*1 + y) == round(x + y)
+// bit for bit, and an FMA cannot be contracted any further.
+__device__ __forceinline__ unsigned long long fadd2_exact(unsigned long long a, unsigned long long b, unsigned long long one) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(one), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float lo32(unsigned long long v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
+__device__ __forceinline__ float hi32(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
+
+template <int KH, int TPB, int TILE>
+__global__ void __launch_bounds__(TPB)
+plane_score_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict__ recs, int H, int pts_per_cta,
+                   float thr_up, float one_rt, int* __restrict__ counts) {
+  __shared__ __align__(16) float4 s_pts[2][TILE];
+  const unsigned long long ONE = pack2(one_rt, one_rt);
+  constexpr int KP = KH / 2;
+  const int h_base = (blockIdx.y * TPB + threadIdx.x) * KH;
+  unsigned long long A[KP], B[KP], C[KP], D[KP];
+  int cnt[KH];
+#pragma unroll
+  for (int k = 0; k < KP; ++k) {
+    float4 r0 = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F), r1 = r0;
+    if (h_base + 2 * k < H) r0 = __ldg(reinterpret_cast<const float4*>(recs[h_base + 2 * k].v));
+    if (h_base + 2 * k + 1 < H) r1 = __ldg(reinterpret_cast<const float4*>(recs[h_base + 2 * k + 1].v));
+    A[k] = pack2(r0.x, r1.x); B[k] = pack2(r0.y, r1.y); C[k] = pack2(r0.z, r1.z); D[k] = pack2(r0.w, r1.w);
+    cnt[2 * k] = 0; cnt[2 * k + 1] = 0;
+  }
+  const int p_begin = blockIdx.x * pts_per_cta;
+  const int p_end = min(n, p_begin + pts_per_cta);
+  const int n_tiles = (p_end - p_begin + TILE - 1) / TILE;
+  // double-buffered tile staging with cp.async (LDGSTS)
+  auto stage = [&](int t, int buf) {
+    int base = p_begin + t * TILE;
+    for (int i = threadIdx.x; i < TILE; i += TPB) {
+      int gi = base + i;
+      if (gi < p_end) {
+        unsigned saddr = (unsigned)__cvta_generic_to_shared(&s_pts[buf][i]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(xyz + gi));
+      } else {
+        s_pts[buf][i] = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+      }
+    }
+    asm volatile("cp.async.commit_group;");
+  };
+  if (n_tiles > 0) stage(0, 0);
+  for (int t = 0; t < n_tiles; ++t) {
+    if (t + 1 < n_tiles) {
+      stage(t + 1, (t + 1) & 1);
+      asm volatile("cp.async.wait_group 1;");
+    } else {
+      asm volatile("cp.async.wait_group 0;");
+    }
+    __syncthreads();
+    const float4* tile = s_pts[t & 1];
+#pragma unroll 2
+    for (int i = 0; i < TILE; ++i) {
+      float4 p = tile[i];  // LDS.128 broadcast
+      unsigned long long X = pack2(p.x, p.x), Y = pack2(p.y, p.y), Z = pack2(p.z, p.z);
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        // (a*x + c*z) + (b*y + d), two hypotheses per instruction
+        unsigned long long s = fadd2_exact(fadd2_exact(mul2(A[k], X), mul2(C[k], Z), ONE),
+                                           fadd2_exact(mul2(B[k], Y), D[k], ONE), ONE);
+        cnt[2 * k] += (fabsf(lo32(s)) < thr_up) ? 1 : 0;
+        cnt[2 * k + 1] += (fabsf(hi32(s)) < thr_up) ? 1 : 0;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < KH; ++k)
+    if (h_base + k < H && cnt[k]) atomicAdd(&counts[h_base + k], cnt[k]);
+}
+
+// =====================================================================================
+// K4: earliest arg-max over the scored hypotheses (ALL_H stop rule)
+// =====================================================================================
+__global__ void winner_kernel(const int* __restrict__ counts, const uint8_t* __restrict__ flags, int H,
+                              const float* __restrict__ coeffs8, int* __restrict__ best /*[2]: idx,count*/,
+                              float* __restrict__ best_coeffs /*8*/) {
+  __shared__ int s_c[32], s_i[32];
+  int bc = INT_MIN, bi = INT_MAX;
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    if (!(flags[h] & 1)) continue;  // computeModelCoefficients failed: skipped by PCL
+    int c = counts[h];
+    if (c > bc || (c == bc && h < bi)) { bc = c; bi = h; }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    int oc = __shfl_down_sync(0xffffffffu, bc, o), oi = __shfl_down_sync(0xffffffffu, bi, o);
+    if (oc > bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
+  }
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { s_c[w] = bc; s_i[w] = bi; }
+  __syncthreads();
+  if (w == 0) {
+    int nw = blockDim.x >> 5;
+    bc = (l < nw) ? s_c[l] : INT_MIN;
+    bi = (l < nw) ? s_i[l] : INT_MAX;
+    for (int o = 16; o > 0; o >>= 1) {
+      int oc = __shfl_down_sync(0xffffffffu, bc, o), oi = __shfl_down_sync(0xffffffffu, bi, o);
+      if (oc > bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
+    }
+    if (l == 0) {
+      if (bi == INT_MAX) { best[0] = -1; best[1] = 0; }
+      else { best[0] = bi; best[1] = bc; }
+    }
+    __syncwarp();
+    int idx = __shfl_sync(0xffffffffu, (l == 0) ? ((bi == INT_MAX) ? -1 : bi) : 0, 0);
+    if (l < 8) best_coeffs[l] = (idx >= 0) ? coeffs8[(size_t)idx * 8 + l] : 0.0f;
+  }
+}
+
+// =====================================================================================
+// K5: selectWithinDistance — predicate + ordered (ascending index) stream compaction.
+// pass 1: per-block inlier counts; pass 2: exclusive scan of the block counts (one block);
+// pass 3: predicate again + ballot ranks -> indices. The predicate is evaluated twice instead of
+// materialising N flags.
+// =====================================================================================
+constexpr int SEL_TPB = 256;
+constexpr int SEL_PPT = 4;  // consecutive points per thread
+template <int MODEL>
+__device__ __forceinline__ unsigned select_mask(const float4* xyz, const float4* nrm, int n, const RecRegs<MODEL>& r,
+                                                const ScoreParams& sp, int first) {
+  constexpr bool NEED_N = (MODEL == PITT_MODEL_CYLINDER || MODEL == PITT_MODEL_CONE);
+  unsigned m = 0;
+#pragma unroll
+  for (int j = 0; j < SEL_PPT; ++j) {
+    int i = first + j;
+    if (i < n) {
+      f3 pt = ld3(xyz, i);
+      f3 nv = NEED_N ? ld3(nrm, i) : mk3(0.f, 0.f, 0.f);
+      if (r.inlier(pt, nv, sp)) m |= (1u << j);
+    }
+  }
+  return m;
+}
+template <int MODEL>
+__global__ void __launch_bounds__(SEL_TPB)
+select_count_kernel(const float4* __restrict__ xyz, const float4* __restrict__ nrm, int n, const HypRec* __restrict__ rec,
+                    ScoreParams sp, int* __restrict__ block_counts) {
+  __shared__ int s_w[SEL_TPB / 32];
+  RecRegs<MODEL> r;
+  r.load(rec);
+  int first = (blockIdx.x * SEL_TPB + threadIdx.x) * SEL_PPT;
+  int c = __popc(select_mask<MODEL>(xyz, nrm, n, r, sp, first));
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < SEL_TPB / 32; ++i) t += s_w[i];
+    block_counts[blockIdx.x] = t;
+  }
+}
+// exclusive scan of nb ints in place, total -> *total (single block, any nb)
+__global__ void scan_blocks_kernel(int* __restrict__ v, int nb, int* __restrict__ total) {
+  __shared__ int s_carry;
+  __shared__ int s_w[32];
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += blockDim.x) {
+    int i = base + threadIdx.x;
+    int x = (i < nb) ? v[i] : 0;
+    int incl = x;
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((threadIdx.x & 31) >= o) incl += y;
+    }
+    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      int nw = blockDim.x >> 5;
+      int wv = (threadIdx.x < nw) ? s_w[threadIdx.x] : 0;
+      int wi = wv;
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, wi, o);
+        if (threadIdx.x >= o) wi += y;
+      }
+      s_w[threadIdx.x] = wi - wv;  // exclusive warp offsets
+    }
+    __syncthreads();
+    int carry = s_carry;
+    int excl = carry + s_w[threadIdx.x >> 5] + incl - x;
+    if (i < nb) v[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry = excl + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = s_carry;
+}
+template <int MODEL>
+__global__ void __launch_bounds__(SEL_TPB)
+select_write_kernel(const float4* __restrict__ xyz, const float4* __restrict__ nrm, int n, const HypRec* __restrict__ rec,
+                    ScoreParams sp, const int* __restrict__ block_offsets, int* __restrict__ out) {
+  __shared__ int s_w[SEL_TPB / 32];
+  RecRegs<MODEL> r;
+  r.load(rec);
+  int first = (blockIdx.x * SEL_TPB + threadIdx.x) * SEL_PPT;
+  unsigned m = select_mask<MODEL>(xyz, nrm, n, r, sp, first);
+  int c = __popc(m);
+  int incl = c;
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((threadIdx.x & 31) >= o) incl += y;
+  }
+  if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  int woff = 0;
+  for (int i = 0; i < (threadIdx.x >> 5); ++i) woff += s_w[i];
+  int pos = block_offsets[blockIdx.x] + woff + incl - c;
+#pragma unroll
+  for (int j = 0; j < SEL_PPT; ++j)
+    if (m & (1u << j)) out[pos++] = first + j;
+}
+
+// =====================================================================================
+// K6: plane refinement = computeMeanAndCovarianceMatrix over the winner's inliers + eigen33.
+// The nine sums are accumulated in double by a fixed-shape tree (deterministic) and rounded once
+// to float — the oracle defines them as exact sums rounded once (oracle/orc_math.h DD).
+// =====================================================================================
+constexpr int REF_TPB = 256;
+constexpr int REF_BLOCKS = 296;
+__global__ void __launch_bounds__(REF_TPB)
+plane_sums_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict__ rec, const int* __restrict__ idx,
+                  const int* __restrict__ n_idx, ScoreParams sp, double* __restrict__ partial /*[blocks][10]*/) {
+  // two modes: idx != nullptr sums the listed points; otherwise the predicate of *rec decides
+  __shared__ double s_red[REF_TPB / 32][10];
+  RecRegs<PITT_MODEL_PLANE> r;
+  if (rec) r.load(rec);
+  double a[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) a[k] = 0.0;
+  int total = idx ? *n_idx : n;
+  for (int i = blockIdx.x * REF_TPB + threadIdx.x; i < total; i += gridDim.x * REF_TPB) {
+    int pi = idx ? idx[i] : i;
+    f3 p = ld3(xyz, pi);
+    bool in = idx ? true : r.inlier(p, p, sp);
+    if (in) {
+      double x = p.x, y = p.y, z = p.z;
+      a[0] += x * x; a[1] += x * y; a[2] += x * z; a[3] += y * y; a[4] += y * z; a[5] += z * z;
+      a[6] += x; a[7] += y; a[8] += z; a[9] += 1.0;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 10; ++k)
+    for (int o = 16; o > 0; o >>= 1) a[k] += __shfl_down_sync(0xffffffffu, a[k], o);
+  if ((threadIdx.x & 31) == 0)
+    for (int k = 0; k < 10; ++k) s_red[threadIdx.x >> 5][k] = a[k];
+  __syncthreads();
+  if (threadIdx.x < 10) {
+    double t = 0.0;
+    for (int w = 0; w < REF_TPB / 32; ++w) t += s_red[w][threadIdx.x];
+    partial[(size_t)blockIdx.x * 10 + threadIdx.x] = t;
+  }
+}
+__global__ void plane_refine_final_kernel(const double* __restrict__ partial, int blocks, const float* __restrict__ model,
+                                          float* __restrict__ refined, int* __restrict__ n_model_inliers) {
+  __shared__ double s[10];
+  if (threadIdx.x < 10) {
+    double t = 0.0;
+    for (int b = 0; b < blocks; ++b) t += partial[(size_t)b * 10 + threadIdx.x];
+    s[threadIdx.x] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int cnt = (int)s[9];
+    *n_model_inliers = cnt;
+    if (cnt < 4) {
+      for (int i = 0; i < 8; ++i) refined[i] = model[i];
+    } else {
+      float accu[9], cov[9], cen[3], ev, evec[3];
+      for (int i = 0; i < 9; ++i) accu[i] = (float)s[i];
+      cov_from_accu(accu, (float)cnt, cov, cen);
+      eigen33(cov, ev, evec);
+      f3 o = mk3(evec[0], evec[1], evec[2]);
+      refined[0] = o.x; refined[1] = o.y; refined[2] = o.z;
+      refined[3] = -dot0(o, mk3(cen[0], cen[1], cen[2]));
+      for (int i = 4; i < 8; ++i) refined[i] = 0.0f;
+    }
+  }
+}
+
+// =====================================================================================
+// FP32 pipe micro-benchmarks (roofline denominators of K3)
+// =====================================================================================
+template <int KIND>
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float seed, float one_rt) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = seed + (float)(threadIdx.x + i) * 1e-3f;
+  const float m = 1.0000001f, c = 1e-7f;
+  if (KIND == 2) {
+    unsigned long long v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = pack2(a[2 * i], a[2 * i + 1]);
+    unsigned long long M = pack2(m, m), Cc = pack2(c, c), ONE = pack2(one_rt, one_rt);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fadd2_exact(mul2(v[i], M), Cc, ONE);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a[2 * i] = lo32(v[i]); a[2 * i + 1] = hi32(v[i]); }
+  } else {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (KIND == 0) a[i] = __fmaf_rn(a[i], m, c);
+        else a[i] = __fadd_rn(__fmul_rn(a[i], m), c);
+      }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// =====================================================================================
+// host side
+// =====================================================================================
+static inline int sample_size(int model) {
+  return model == PITT_MODEL_PLANE ? 3 : model == PITT_MODEL_SPHERE ? 4 : model == PITT_MODEL_CYLINDER ? 2 : 3;
+}
+static inline int coeff_count(int model) { return (model == PITT_MODEL_PLANE || model == PITT_MODEL_SPHERE) ? 4 : 7; }
+
+Limits limits_for(const pitt_sac_params& p) {
+  Limits L;
+  L.radius_min = -DBL_MAX; L.radius_max = DBL_MAX; L.min_angle = -DBL_MAX; L.max_angle = DBL_MAX;
+  L.eps_angle = 0.0; L.w = 0.0; L.ax = L.ay = L.az = 0.0f;
+  const bool fwd_radius = (p.radius_min != -DBL_MAX) && (p.radius_max != DBL_MAX);
+  const bool has_axis = (p.axis[0] != 0.0f || p.axis[1] != 0.0f || p.axis[2] != 0.0f);
+  if (p.model == PITT_MODEL_SPHERE) {
+    if (fwd_radius) { L.radius_min = p.radius_min; L.radius_max = p.radius_max; }
+  } else if (p.model == PITT_MODEL_CYLINDER || p.model == PITT_MODEL_CONE) {
+    if (p.model == PITT_MODEL_CYLINDER && fwd_radius) { L.radius_min = p.radius_min; L.radius_max = p.radius_max; }
+    L.w = p.normal_distance_weight;
+    if (has_axis) { L.ax = p.axis[0]; L.ay = p.axis[1]; L.az = p.axis[2]; }
+    if (p.eps_angle != 0.0) L.eps_angle = p.eps_angle;
+    if (p.model == PITT_MODEL_CONE && p.min_angle != -DBL_MAX && p.max_angle != DBL_MAX) {
+      L.min_angle = p.min_angle; L.max_angle = p.max_angle;
+    }
+  }
+  return L;
+}
+
+ScoreParams score_params_for(const pitt_sac_params& p, const Limits& L) {
+  ScoreParams sp;
+  sp.thr = p.distance_threshold;
+  float t = (float)p.distance_threshold;
+  if ((double)t < p.distance_threshold) t = nextafterf(t, INFINITY);
+  sp.thr_up = t;
+  sp.w = L.w;
+  // |FP32 score - exact score| bound: acosf near |cos|=1 loses up to ~1e-3 rad (times w), the
+  // euclidean part a few ulps of the point-axis distance (clouds within ~8 m of the axis).
+  sp.band = (float)(2e-3 * fabs(L.w) + 2e-6);
+  return sp;
+}
+
+#define PITT_LAUNCH_CHECK(ctx, what)                                       \
+  do {                                                                     \
+    (ctx)->launches++;                                                     \
+    cudaError_t e__ = cudaGetLastError();                                  \
+    if (e__ != cudaSuccess) return fail((ctx), PITT_ERR_CUDA, what, e__);  \
+  } while (0)
+
+template <int MODEL>
+static int launch_estimate(pitt_ctx* ctx, const pitt_cloud* c, const int* d_samples, int H, const Limits& L,
+                           HypRec* d_recs, float* d_coeffs8, uint8_t* d_flags) {
+  estimate_kernel<MODEL><<<cdiv(H, 128), 128, 0, ctx->stream>>>(c->d_xyz, c->d_nrm, d_samples, H, L, d_recs, d_coeffs8, d_flags);
+  PITT_LAUNCH_CHECK(ctx, "estimate_kernel");
+  return PITT_OK;
+}
+
+int sac_estimate(pitt_ctx* ctx, const pitt_cloud* c, int model, const int* d_samples, int H, const Limits& L,
+                 HypRec* d_recs, float* d_coeffs8, uint8_t* d_flags) {
+  if (H <= 0) return PITT_OK;
+  switch (model) {
+    case PITT_MODEL_PLANE: return launch_estimate<PITT_MODEL_PLANE>(ctx, c, d_samples, H, L, d_recs, d_coeffs8, d_flags);
+    case PITT_MODEL_SPHERE: return launch_estimate<PITT_MODEL_SPHERE>(ctx, c, d_samples, H, L, d_recs, d_coeffs8, d_flags);
+    case PITT_MODEL_CYLINDER: return launch_estimate<PITT_MODEL_CYLINDER>(ctx, c, d_samples, H, L, d_recs, d_coeffs8, d_flags);
+    default: return launch_estimate<PITT_MODEL_CONE>(ctx, c, d_samples, H, L, d_recs, d_coeffs8, d_flags);
+  }
+}
+
+template <int MODEL, int P>
+static int launch_score_generic(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_recs, int H, const ScoreParams& sp,
+                                int* d_counts) {
+  constexpr int TPB = 256;
+  const int n = c->n;
+  int hyp_chunk = H < 512 ? H : 512;
+  int n_chunks = cdiv(H, hyp_chunk);
+  // point blocks: enough CTAs for ~4 waves, each covering a whole number of TPB*P tiles
+  const int tile = TPB * P;
+  int want_ctas = ctx->sm_count * 8;
+  int pblocks = want_ctas / n_chunks;
+  if (pblocks < 1) pblocks = 1;
+  int tiles = cdiv(n, tile);
+  if (pblocks > tiles) pblocks = tiles;
+  int pts_per_cta = cdiv(tiles, pblocks) * tile;
+  pblocks = cdiv(n, pts_per_cta);
+  size_t smem = (size_t)hyp_chunk * (sizeof(HypRec) + sizeof(int));
+  dim3 grid(pblocks, n_chunks);
+  score_kernel<MODEL, P, TPB><<<grid, TPB, smem, ctx->stream>>>(c->d_xyz, c->d_nrm, n, d_recs, H, hyp_chunk, pts_per_cta, sp, d_counts);
+  PITT_LAUNCH_CHECK(ctx, "score_kernel");
+  return PITT_OK;
+}
+
+static int launch_score_plane_packed(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_recs, int H, const ScoreParams& sp,
+                                     int* d_counts) {
+  constexpr int KH = 8, TPB = 128, TILE = 512;
+  const int n = c->n;
+  int hblocks = cdiv(H, KH * TPB);
+  int want_ctas = ctx->sm_count * 8;
+  int pblocks = want_ctas / hblocks;
+  if (pblocks < 1) pblocks = 1;
+  int tiles = cdiv(n, TILE);
+  if (pblocks > tiles) pblocks = tiles;
+  int pts_per_cta = cdiv(tiles, pblocks) * TILE;
+  pblocks = cdiv(n, pts_per_cta);
+  dim3 grid(pblocks, hblocks);
+  plane_score_kernel<KH, TPB, TILE><<<grid, TPB, 0, ctx->stream>>>(c->d_xyz, n, d_recs, H, pts_per_cta, sp.thr_up, 1.0f, d_counts);
+  PITT_LAUNCH_CHECK(ctx, "plane_score_kernel");
+  return PITT_OK;
+}
+
+int g_force_generic_plane = 0;  // test hook: 1 routes plane scoring through the generic kernel
+
+int sac_score(pitt_ctx* ctx, const pitt_cloud* c, int model, const HypRec* d_recs, int H, const ScoreParams& sp,
+              int* d_counts) {
+  if (H <= 0) return PITT_OK;
+  PITT_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (size_t)H * sizeof(int), ctx->stream));
+  if (c->n <= 0) return PITT_OK;
+  switch (model) {
+    case PITT_MODEL_PLANE:
+      if (H >= 256 && !g_force_generic_plane) return launch_score_plane_packed(ctx, c, d_recs, H, sp, d_counts);
+      return launch_score_generic<PITT_MODEL_PLANE, 8>(ctx, c, d_recs, H, sp, d_counts);
+    case PITT_MODEL_SPHERE: return launch_score_generic<PITT_MODEL_SPHERE, 8>(ctx, c, d_recs, H, sp, d_counts);
+    case PITT_MODEL_CYLINDER: return launch_score_generic<PITT_MODEL_CYLINDER, 2>(ctx, c, d_recs, H, sp, d_counts);
+    default: return launch_score_generic<PITT_MODEL_CONE, 2>(ctx, c, d_recs, H, sp, d_counts);
+  }
+}
+
+template <int MODEL>
+static int launch_select(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_rec, const ScoreParams& sp, int* d_out,
+                         int* d_total) {
+  const int n = c->n;
+  const int nb = cdiv(n, SEL_TPB * SEL_PPT);
+  int* d_bc = nullptr;
+  PITT_TRY(arena_alloc(ctx, (size_t)nb + 1, &d_bc));
+  select_count_kernel<MODEL><<<nb, SEL_TPB, 0, ctx->stream>>>(c->d_xyz, c->d_nrm, n, d_rec, sp, d_bc);
+  PITT_LAUNCH_CHECK(ctx, "select_count_kernel");
+  scan_blocks_kernel<<<1, 1024, 0, ctx->stream>>>(d_bc, nb, d_total);
+  PITT_LAUNCH_CHECK(ctx, "scan_blocks_kernel");
+  select_write_kernel<MODEL><<<nb, SEL_TPB, 0, ctx->stream>>>(c->d_xyz, c->d_nrm, n, d_rec, sp, d_bc, d_out);
+  PITT_LAUNCH_CHECK(ctx, "select_write_kernel");
+  return PITT_OK;
+}
+
+// d_coeffs: 8 floats on the device. Writes ascending inlier indices to d_out (capacity n) and
+// their number to d_total. isModelValid is applied (invalid model => 0 inliers).
+int sac_select(pitt_ctx* ctx, const pitt_cloud* c, int model, const float* d_coeffs, const Limits& L,
+               const ScoreParams& sp, int* d_out, int* d_total) {
+  if (c->n <= 0) {
+    PITT_CUDA(ctx, cudaMemsetAsync(d_total, 0, sizeof(int), ctx->stream));
+    return PITT_OK;
+  }
+  HypRec* d_rec = nullptr;
+  PITT_TRY(arena_alloc(ctx, 1, &d_rec));
+  switch (model) {
+    case PITT_MODEL_PLANE:
+      prep_rec_kernel<PITT_MODEL_PLANE><<<1, 1, 0, ctx->stream>>>(d_coeffs, L, d_rec);
+      PITT_LAUNCH_CHECK(ctx, "prep_rec_kernel");
+      return launch_select<PITT_MODEL_PLANE>(ctx, c, d_rec, sp, d_out, d_total);
+    case PITT_MODEL_SPHERE:
+      prep_rec_kernel<PITT_MODEL_SPHERE><<<1, 1, 0, ctx->stream>>>(d_coeffs, L, d_rec);
+      PITT_LAUNCH_CHECK(ctx, "prep_rec_kernel");
+      return launch_select<PITT_MODEL_SPHERE>(ctx, c, d_rec, sp, d_out, d_total);
+    case PITT_MODEL_CYLINDER:
+      prep_rec_kernel<PITT_MODEL_CYLINDER><<<1, 1, 0, ctx->stream>>>(d_coeffs, L, d_rec);
+      PITT_LAUNCH_CHECK(ctx, "prep_rec_kernel");
+      return launch_select<PITT_MODEL_CYLINDER>(ctx, c, d_rec, sp, d_out, d_total);
+    default:
+      prep_rec_kernel<PITT_MODEL_CONE><<<1, 1, 0, ctx->stream>>>(d_coeffs, L, d_rec);
+      PITT_LAUNCH_CHECK(ctx, "prep_rec_kernel");
+      return launch_select<PITT_MODEL_CONE>(ctx, c, d_rec, sp, d_out, d_total);
+  }
+}
+
+// Plane optimizeModelCoefficients. Either over an explicit inlier list (d_idx, d_n_idx) or, when
+// d_idx == nullptr, over the points satisfying the predicate of d_model (fused select + sums).
+int plane_refine(pitt_ctx* ctx, const pitt_cloud* c, const float* d_model, const int* d_idx, const int* d_n_idx,
+                 const Limits& L, const ScoreParams& sp, float* d_refined, int* d_n_model_inliers) {
+  double* d_partial = nullptr;
+  PITT_TRY(arena_alloc(ctx, (size_t)REF_BLOCKS * 10, &d_partial));
+  HypRec* d_rec = nullptr;
+  if (!d_idx) {
+    PITT_TRY(arena_alloc(ctx, 1, &d_rec));
+    prep_rec_kernel<PITT_MODEL_PLANE><<<1, 1, 0, ctx->stream>>>(d_model, L, d_rec);
+    PITT_LAUNCH_CHECK(ctx, "prep_rec_kernel");
+  }
+  plane_sums_kernel<<<REF_BLOCKS, REF_TPB, 0, ctx->stream>>>(c->d_xyz, c->n, d_rec, d_idx, d_n_idx, sp, d_partial);
+  PITT_LAUNCH_CHECK(ctx, "plane_sums_kernel");
+  plane_refine_final_kernel<<<1, 32, 0, ctx->stream>>>(d_partial, REF_BLOCKS, d_model, d_refined, d_n_model_inliers);
+  PITT_LAUNCH_CHECK(ctx, "plane_refine_final_kernel");
+  return PITT_OK;
+}
+
+int sac_winner(pitt_ctx* ctx, const int* d_counts, const uint8_t* d_flags, int H, const float* d_coeffs8, int* d_best,
+               float* d_best_coeffs) {
+  winner_kernel<<<1, 1024, 0, ctx->stream>>>(d_counts, d_flags, H, d_coeffs8, d_best, d_best_coeffs);
+  PITT_LAUNCH_CHECK(ctx, "winner_kernel");
+  return PITT_OK;
+}
+
+int fp32_peak(pitt_ctx* ctx, int kind, double* tflops) {
+  const int blocks = ctx->sm_count * 16, tpb = 256, iters = 4096;
+  float* d_out = nullptr;
+  PITT_TRY(arena_alloc(ctx, (size_t)blocks * tpb, &d_out));
+  cudaEvent_t e0, e1;
+  PITT_CUDA(ctx, cudaEventCreate(&e0));
+  PITT_CUDA(ctx, cudaEventCreate(&e1));
+  float best_ms = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0, ctx->stream);
+    if (kind == 0) fp32_peak_kernel<0><<<blocks, tpb, 0, ctx->stream>>>(d_out, iters, 1.0f, 1.0f);
+    else if (kind == 1) fp32_peak_kernel<1><<<blocks, tpb, 0, ctx->stream>>>(d_out, iters, 1.0f, 1.0f);
+    else fp32_peak_kernel<2><<<blocks, tpb, 0, ctx->stream>>>(d_out, iters, 1.0f, 1.0f);
+    ctx->launches++;
+    cudaEventRecord(e1, ctx->stream);
+    PITT_CUDA(ctx, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best_ms) best_ms = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  double flops = (double)blocks * tpb * (double)iters * 16.0 * 2.0;
+  *tflops = flops / (best_ms * 1e-3) / 1e12;
+  return PITT_OK;
+}
+
+// ------------------------------------------------------------------ PCL sample stream (host)
+// boost::mt19937(12345) + SampleConsensusModel::drawIndexSample, sparse partial Fisher-Yates.
+struct Mt19937 {
+  uint32_t s[624];
+  int idx;
+  explicit Mt19937(uint32_t seed) {
+    s[0] = seed;
+    for (int i = 1; i < 624; ++i) s[i] = 1812433253u * (s[i - 1] ^ (s[i - 1] >> 30)) + (uint32_t)i;
+    idx = 624;
+  }
+  uint32_t next() {
+    if (idx >= 624) {
+      for (int i = 0; i < 624; ++i) {
+        uint32_t y = (s[i] & 0x80000000u) | (s[(i + 1) % 624] & 0x7fffffffu);
+        s[i] = s[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+      }
+      idx = 0;
+    }
+    uint32_t y = s[idx++];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+  }
+};
+
+struct PclSampleStream::Impl {
+  Mt19937 mt{12345u};
+  std::unordered_map<int, int> moved;
+  int n = 0;
+  int get(int i) const {
+    auto it = moved.find(i);
+    return it == moved.end() ? i : it->second;
+  }
+  void draw(int S, int* out) {
+    for (int i = 0; i < S; ++i) {
+      uint32_t r = mt.next() >> 1;  // uniform_int<>(0, INT_MAX) over a 32-bit engine
+      int j = i + (int)(r % (uint32_t)(n - i));
+      int a = get(i), b = get(j);
+      moved[i] = b;
+      moved[j] = a;
+    }
+    for (int i = 0; i < S; ++i) out[i] = get(i);
+  }
+};
+PclSampleStream::PclSampleStream(int n, int model, const float* h_xyz4) : impl_(new Impl), model_(model), h_xyz_(h_xyz4) {
+  impl_->n = n;
+}
+PclSampleStream::~PclSampleStream() { delete impl_; }
+static bool plane_sample_good(const float* xyz, const int* s) {
+  float q[3];
+  for (int k = 0; k < 3; ++k) {
+    float a = xyz[4 * (size_t)s[1] + k] - xyz[4 * (size_t)s[0] + k];
+    float b = xyz[4 * (size_t)s[2] + k] - xyz[4 * (size_t)s[0] + k];
+    q[k] = a / b;
+  }
+  return (q[0] != q[1]) || (q[2] != q[1]);
+}
+bool PclSampleStream::next(int* out) {
+  const int S = sample_size(model_);
+  if (impl_->n < S) return false;
+  for (int iter = 0; iter < 1000; ++iter) {
+    impl_->draw(S, out);
+    // isSampleGood: only the plane model tests anything; without a host mirror the draw is
+    // speculative and the device's collinearity flag decides (see sac_segment_impl)
+    if (model_ != PITT_MODEL_PLANE || !h_xyz_ || plane_sample_good(h_xyz_, out)) return true;
+  }
+  return false;
+}
+
+// Philox-4x32-10 minimal sets drawn on the device (production sampler)
+__device__ __forceinline__ void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
+  uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+  uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+  uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+  c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+__global__ void philox_samples_kernel(int* __restrict__ samples, int H, int S, int n, uint64_t seed, uint32_t stream_id) {
+  int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  uint32_t c0 = (uint32_t)h, c1 = stream_id, c2 = 0x9E3779B9u, c3 = 0xBB67AE85u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c0, c1, c2, c3, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  uint32_t rnd[4] = {c0, c1, c2, c3};
+  int s[4];
+  for (int i = 0; i < S; ++i) {
+    // i-th draw without replacement: uniform in [0, n-i), then skip over earlier picks (kept sorted)
+    int v = (int)(((uint64_t)rnd[i] * (uint64_t)(n - i)) >> 32);
+    int sorted[4];
+    for (int j = 0; j < i; ++j) sorted[j] = s[j];
+    for (int a = 1; a < i; ++a)
+      for (int b = a; b > 0 && sorted[b - 1] > sorted[b]; --b) { int t = sorted[b]; sorted[b] = sorted[b - 1]; sorted[b - 1] = t; }
+    for (int j = 0; j < i; ++j)
+      if (v >= sorted[j]) ++v;
+    s[i] = v;
+  }
+  for (int i = 0; i < S; ++i) samples[(size_t)h * S + i] = s[i];
+}
+int sac_philox_samples(pitt_ctx* ctx, int* d_samples, int H, int S, int n, uint32_t stream_id) {
+  philox_samples_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(d_samples, H, S, n, ctx->seed, stream_id);
+  PITT_LAUNCH_CHECK(ctx, "philox_samples_kernel");
+  return PITT_OK;
+}
+
+// ------------------------------------------------------------------ RandomSampleConsensus::computeModel scan (host)
+struct RansacScan {
+  int iterations = 0, skipped = 0, pos = 0;
+  int best = -INT_MAX, best_pos = -1;
+  double k = 1.0;
+  bool done = false;
+};
+// Consumes hypotheses [scan.pos, H) of the stream; returns true when the loop has terminated.
+static bool ransac_scan(RansacScan& sc, const pitt_sac_params& p, int n, int S, const int* counts, const uint8_t* flags, int H) {
+  const double log_probability = log(1.0 - p.probability);
+  const double one_over_indices = 1.0 / (double)n;
+  const int max_skip = p.max_iterations * 10;
+  while ((double)sc.iterations < sc.k && sc.skipped < max_skip) {
+    if (sc.pos >= H) return false;  // need more samples
+    int h = sc.pos++;
+    if (!(flags[h] & 1)) { ++sc.skipped; continue; }
+    int cnt = counts[h];
+    if (cnt > sc.best) {
+      sc.best = cnt;
+      sc.best_pos = h;
+      double w = (double)cnt * one_over_indices;
+      double p_no = 1.0 - pow(w, (double)S);
+      p_no = std::max(DBL_EPSILON, p_no);
+      p_no = std::min(1.0 - DBL_EPSILON, p_no);
+      sc.k = log_probability / log(p_no);
+    }
+    ++sc.iterations;
+    if (sc.iterations > p.max_iterations) break;
+  }
+  sc.done = true;
+  return true;
+}
+
+int lm_refine(pitt_ctx* ctx, const pitt_cloud* c, int model, const float* d_model, const int* d_idx, const int* d_n_idx,
+              int n_idx_host, float* d_refined, int* d_lm_info /*[2]: status,nfev*/);
+
+// ------------------------------------------------------------------ seg.segment()
+int sac_segment_impl(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& p, SacDeviceResult* out) {
+  const int model = p.model;
+  const int S = sample_size(model);
+  const int n = c->n;
+  memset(&out->info, 0, sizeof(out->info));
+  out->info.best_hypothesis = -1;
+  out->n_inliers = 0;
+  out->n_coeffs = 0;
+  out->d_inliers = nullptr;
+  if (model < 0 || model > 3) return fail(ctx, PITT_ERR_INVALID, "bad model");
+  if ((model == PITT_MODEL_CYLINDER || model == PITT_MODEL_CONE) && !c->has_normals)
+    return fail(ctx, PITT_ERR_STATE, "cylinder/cone segmentation needs normals on the cloud");
+  if (n < S || p.max_iterations < 0) return PITT_OK;  // getSamples fails: "No solution found"
+  const Limits L = limits_for(p);
+  const ScoreParams sp = score_params_for(p, L);
+  const bool all_h = (p.stop == PITT_STOP_ALL_H);
+  const int H_first = all_h ? p.max_iterations : p.max_iterations + 1;
+  if (H_first <= 0) return PITT_OK;
+
+  // result block on the device: best[2], n_model, n_final, lm[2], model coeffs[8], refined[8]
+  int* d_ints = nullptr;
+  float* d_flt = nullptr;
+  PITT_TRY(arena_alloc(ctx, 8, &d_ints));
+  PITT_TRY(arena_alloc(ctx, 16, &d_flt));
+  PITT_CUDA(ctx, cudaMemsetAsync(d_ints, 0, 8 * sizeof(int), ctx->stream));
+  int* d_best = d_ints;         // [0]=idx [1]=count
+  int* d_n_model = d_ints + 2;
+  int* d_n_final = d_ints + 3;
+  int* d_lm = d_ints + 4;       // [4],[5]
+  float* d_model = d_flt;
+  float* d_refined = d_flt + 8;
+  int* d_inl = nullptr;
+  PITT_TRY(arena_alloc(ctx, (size_t)n, &d_inl));
+
+  PclSampleStream stream(n, model, (c->h_valid ? c->h_xyz.data() : nullptr));
+  RansacScan scan;
+  std::vector<int> h_samples;
+  int H_total = 0;
+  int batch = H_first;
+  int* d_samples = nullptr;
+  HypRec* d_recs = nullptr;
+  float* d_coeffs8 = nullptr;
+  uint8_t* d_flags = nullptr;
+  int* d_counts = nullptr;
+  std::vector<int> h_counts;
+  std::vector<uint8_t> h_flags;
+  int winner = -1, winner_count = 0;
+
+  for (int round = 0; round < 64; ++round) {
+    const int H = batch;
+    PITT_TRY(arena_alloc(ctx, (size_t)H * S, &d_samples));
+    PITT_TRY(arena_alloc(ctx, (size_t)H, &d_recs));
+    PITT_TRY(arena_alloc(ctx, (size_t)H * 8, &d_coeffs8));
+    PITT_TRY(arena_alloc(ctx, (size_t)H, &d_flags));
+    PITT_TRY(arena_alloc(ctx, (size_t)H, &d_counts));
+    int H_have = H;
+    if (p.sampler == PITT_SAMPLER_PHILOX) {
+      PITT_TRY(sac_philox_samples(ctx, d_samples, H, S, n, (uint32_t)(round + 1)));
+    } else {
+      h_samples.resize((size_t)H * S);
+      if (p.sampler == PITT_SAMPLER_REPLAY) {
+        if (!p.replay_samples) return fail(ctx, PITT_ERR_INVALID, "replay_samples is null");
+        H_have = std::min(H, p.replay_count - H_total);
+        if (H_have <= 0) break;
+        memcpy(h_samples.data(), p.replay_samples + (size_t)H_total * S, (size_t)H_have * S * sizeof(int));
+      } else {
+        H_have = 0;
+        for (int h = 0; h < H; ++h) {
+          if (!stream.next(h_samples.data() + (size_t)h * S)) break;
+          ++H_have;
+        }
+        if (H_have == 0) break;
+      }
+      PITT_TRY(pinned_reserve(ctx, (size_t)H * S * sizeof(int) + (size_t)H * 8));
+      memcpy(ctx->h_pin, h_samples.data(), (size_t)H_have * S * sizeof(int));
+      PITT_CUDA(ctx, cudaMemcpyAsync(d_samples, ctx->h_pin, (size_t)H_have * S * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    PITT_TRY(sac_estimate(ctx, c, model, d_samples, H_have, L, d_recs, d_coeffs8, d_flags));
+    PITT_TRY(sac_score(ctx, c, model, d_recs, H_have, sp, d_counts));
+    out->info.hypotheses += H_have;
+    if (all_h) {
+      PITT_TRY(sac_winner(ctx, d_counts, d_flags, H_have, d_coeffs8, d_best, d_model));
+      winner = -2;  // decided on the device
+      H_total += H_have;
+      break;
+    }
+    // PCL stop rule: scan counts in stream order on the host
+    h_counts.resize(H_total + H_have);
+    h_flags.resize(H_total + H_have);
+    PITT_CUDA(ctx, cudaMemcpyAsync(h_counts.data() + H_total, d_counts, (size_t)H_have * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PITT_CUDA(ctx, cudaMemcpyAsync(h_flags.data() + H_total, d_flags, (size_t)H_have, cudaMemcpyDeviceToHost, ctx->stream));
+    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (model == PITT_MODEL_PLANE && p.sampler == PITT_SAMPLER_PCL_MT19937 && !c->h_valid) {
+      // speculative draws: a collinear triple would have been redrawn by getSamples. Extremely
+      // rare; fetch the host mirror and restart with exact isSampleGood on the host.
+      bool bad = false;
+      for (int h = 0; h < H_have; ++h) bad |= !(h_flags[H_total + h] & 1);
+      if (bad) {
+        PITT_TRY(ensure_host_mirror(ctx, c));
+        return sac_segment_impl(ctx, c, p, out);
+      }
+    }
+    int base = H_total;
+    H_total += H_have;
+    bool done = ransac_scan(scan, p, n, S, h_counts.data(), h_flags.data(), H_total);
+    if (scan.best_pos >= base) {
+      // remember the coefficients of a winner found in this batch
+      PITT_CUDA(ctx, cudaMemcpyAsync(d_model, d_coeffs8 + (size_t)(scan.best_pos - base) * 8, 8 * sizeof(float),
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    if (done || H_have < H) break;
+    batch = std::max(64, std::min(p.max_iterations + 1, 4096));
+  }
+  if (!all_h) {
+    out->info.iterations = scan.iterations;
+    out->info.skipped = scan.skipped;
+    winner = scan.best_pos;
+    winner_count = scan.best_pos >= 0 ? scan.best : 0;
+    if (winner < 0) return PITT_OK;
+  }
+
+  const int NC = coeff_count(model);
+  // refinement + final inliers
+  if (model == PITT_MODEL_PLANE) {
+    if (p.optimize) {
+      PITT_TRY(plane_refine(ctx, c, d_model, nullptr, nullptr, L, sp, d_refined, d_n_model));
+      PITT_TRY(sac_select(ctx, c, model, d_refined, L, sp, d_inl, d_n_final));
+    } else {
+      PITT_TRY(sac_select(ctx, c, model, d_model, L, sp, d_inl, d_n_final));
+      PITT_CUDA(ctx, cudaMemcpyAsync(d_refined, d_model, 8 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+      PITT_CUDA(ctx, cudaMemcpyAsync(d_n_model, d_n_final, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  } else {
+    PITT_TRY(sac_select(ctx, c, model, d_model, L, sp, d_inl, d_n_model));
+    if (p.optimize) {
+      PITT_TRY(lm_refine(ctx, c, model, d_model, d_inl, d_n_model, -1, d_refined, d_lm));
+      PITT_TRY(sac_select(ctx, c, model, d_refined, L, sp, d_inl, d_n_final));
+    } else {
+      PITT_CUDA(ctx, cudaMemcpyAsync(d_refined, d_model, 8 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+      PITT_CUDA(ctx, cudaMemcpyAsync(d_n_final, d_n_model, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  }
+  // one small D2H for the scalars
+  PITT_TRY(pinned_reserve(ctx, 256));
+  int* h_ints = (int*)ctx->h_pin;
+  float* h_flt = (float*)((char*)ctx->h_pin + 64);
+  PITT_CUDA(ctx, cudaMemcpyAsync(h_ints, d_ints, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PITT_CUDA(ctx, cudaMemcpyAsync(h_flt, d_flt, 16 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (all_h) {
+    winner = h_ints[0];
+    winner_count = h_ints[1];
+    out->info.iterations = H_total;
+    if (winner < 0) return PITT_OK;
+  }
+  out->info.best_hypothesis = winner;
+  out->info.best_count = winner_count;
+  out->info.n_inliers_model = h_ints[2];
+  out->info.lm_info = h_ints[4];
+  out->info.lm_nfev = h_ints[5];
+  for (int i = 0; i < 8; ++i) out->info.model_coeffs[i] = i < NC ? h_flt[i] : 0.0f;
+  for (int i = 0; i < 8; ++i) out->coeffs[i] = i < NC ? h_flt[8 + i] : 0.0f;
+  out->n_coeffs = NC;
+  out->n_inliers = h_ints[3];
+  out->d_inliers = d_inl;
+  return PITT_OK;
+}
+
+}  // namespace pitt

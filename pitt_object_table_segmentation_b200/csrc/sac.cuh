@@ -1,0 +1,52 @@
+// sac.cuh — host-side interface of sac.cu / lm.cu used by the C ABI and the service layer.
+#pragma once
+#include "pitt_common.cuh"
+#include "sac_device.cuh"
+
+namespace pitt {
+
+struct SacDeviceResult {
+  pitt_sac_info info;
+  float coeffs[8];
+  int n_coeffs;
+  int n_inliers;
+  const int* d_inliers;  // device, ascending, valid until the next outermost API call (arena)
+};
+
+// pcl::SampleConsensusModel::getSamples replay (host). h_xyz4 may be null: draws are then
+// speculative for the plane model (no isSampleGood redraw).
+class PclSampleStream {
+ public:
+  PclSampleStream(int n, int model, const float* h_xyz4);
+  ~PclSampleStream();
+  bool next(int* out);
+
+ private:
+  struct Impl;
+  Impl* impl_;
+  int model_;
+  const float* h_xyz_;
+};
+
+Limits limits_for(const pitt_sac_params& p);
+ScoreParams score_params_for(const pitt_sac_params& p, const Limits& L);
+
+int sac_estimate(pitt_ctx* ctx, const pitt_cloud* c, int model, const int* d_samples, int H, const Limits& L,
+                 HypRec* d_recs, float* d_coeffs8, uint8_t* d_flags);
+int sac_score(pitt_ctx* ctx, const pitt_cloud* c, int model, const HypRec* d_recs, int H, const ScoreParams& sp,
+              int* d_counts);
+int sac_winner(pitt_ctx* ctx, const int* d_counts, const uint8_t* d_flags, int H, const float* d_coeffs8, int* d_best,
+               float* d_best_coeffs);
+int sac_select(pitt_ctx* ctx, const pitt_cloud* c, int model, const float* d_coeffs, const Limits& L,
+               const ScoreParams& sp, int* d_out, int* d_total);
+int plane_refine(pitt_ctx* ctx, const pitt_cloud* c, const float* d_model, const int* d_idx, const int* d_n_idx,
+                 const Limits& L, const ScoreParams& sp, float* d_refined, int* d_n_model_inliers);
+int lm_refine(pitt_ctx* ctx, const pitt_cloud* c, int model, const float* d_model, const int* d_idx, const int* d_n_idx,
+              int n_idx_host, float* d_refined, int* d_lm_info);
+int sac_philox_samples(pitt_ctx* ctx, int* d_samples, int H, int S, int n, uint32_t stream_id);
+int sac_segment_impl(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& p, SacDeviceResult* out);
+int fp32_peak(pitt_ctx* ctx, int kind, double* tflops);
+
+extern int g_force_generic_plane;
+
+}  // namespace pitt

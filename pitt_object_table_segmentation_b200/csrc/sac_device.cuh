@@ -1,0 +1,329 @@
+// sac_device.cuh — device side of the sample-consensus models (plane, sphere, cylinder, cone):
+// closed-form model estimation (K2) and the per-point inlier predicate (K3/K5).
+//
+// Replaces pcl::SampleConsensusModel{Plane,Sphere,Cylinder,Cone}::{computeModelCoefficients,
+// isModelValid,countWithinDistance,selectWithinDistance} reached from seg.segment() at
+// supports_segmentation_srv.cpp:110, plane…:67, sphere…:73, cylinder…:126, cone…:127
+// (SURVEY.md B.3-B.6). Operation order is the oracle's (oracle/orc_sac.h), written independently.
+#pragma once
+#include <float.h>
+
+#include "pitt_math.cuh"
+
+namespace pitt {
+
+// One scored hypothesis, 64 B, laid out for LDS.128 broadcasts.
+//  plane    v[0..3]  = a,b,c,d
+//  sphere   v[0..3]  = cx,cy,cz,r
+//  cylinder v[0..2]  = point on axis, v[4..6] = axis dir, v[3] = r, v[7] = pt.dir, v[8] = 1/dir.dir
+//  cone     v[0..2]  = apex, v[4..6] = axis dir, v[3] = opening angle, v[7] = apex.dir,
+//           v[8] = 1/dir.dir, v[9] = sin(angle), v[10] = cos(angle), v[12..13] = tan(angle) as double
+// An invalid hypothesis is all NaN: every comparison is false, so it scores 0.
+struct __align__(16) HypRec {
+  float v[16];
+};
+
+// model limits after SACSegmentation(FromNormals)::initSACModel forwarding
+struct Limits {
+  double radius_min, radius_max;
+  double min_angle, max_angle;
+  double eps_angle;
+  double w;  // normal_distance_weight of the model
+  float ax, ay, az;
+};
+
+struct ScoreParams {
+  double thr;    // distance threshold (double, as PCL compares)
+  float thr_up;  // smallest float >= thr:  (double)f < thr  <=>  f < thr_up
+  double w;      // normal distance weight
+  float band;    // FP32 fast path: |score - thr| <= band is re-evaluated exactly
+};
+
+__device__ __forceinline__ f3 ld3(const float4* p, int i) {
+  float4 v = __ldg(p + i);
+  return mk3(v.x, v.y, v.z);
+}
+
+// ------------------------------------------------------------------ computeModelCoefficients
+__device__ inline bool estimate_plane(const float4* xyz, const int* s, float* mc) {
+  f3 p0 = ld3(xyz, s[0]), p1 = ld3(xyz, s[1]), p2 = ld3(xyz, s[2]);
+  f3 d1 = p1 - p0, d2 = p2 - p0;
+  float qx = d1.x / d2.x, qy = d1.y / d2.y, qz = d1.z / d2.z;
+  if ((qx == qy) && (qz == qy)) return false;  // collinear
+  f3 v = cross0(d1, d2);
+  v = unit0(v);
+  mc[0] = v.x; mc[1] = v.y; mc[2] = v.z;
+  mc[3] = -dot0(v, p0);
+  return true;
+}
+
+__device__ __forceinline__ float det4h(const float (*m)[4], int j, int k, int mm, int nn) {
+  return (m[j][0] * m[k][1] - m[k][0] * m[j][1]) * (m[mm][2] * m[nn][3] - m[nn][2] * m[mm][3]);
+}
+__device__ __forceinline__ float det4(const float (*m)[4]) {
+  return det4h(m, 0, 1, 2, 3) - det4h(m, 0, 2, 1, 3) + det4h(m, 0, 3, 1, 2) + det4h(m, 1, 2, 0, 3) -
+         det4h(m, 1, 3, 0, 2) + det4h(m, 2, 3, 0, 1);
+}
+__device__ inline bool estimate_sphere(const float4* xyz, const int* s, float* mc) {
+  float t[4][4], x[4], y[4], z[4], sq[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f3 p = ld3(xyz, s[i]);
+    x[i] = p.x; y[i] = p.y; z[i] = p.z;
+    sq[i] = p.x * p.x + p.y * p.y + p.z * p.z;
+    t[i][0] = x[i]; t[i][1] = y[i]; t[i][2] = z[i]; t[i][3] = 1.0f;
+  }
+  float m11 = det4(t);
+  if (m11 == 0.0f) return false;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) t[i][0] = sq[i];
+  float m12 = det4(t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { t[i][1] = sq[i]; t[i][0] = x[i]; }
+  float m13 = det4(t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { t[i][2] = sq[i]; t[i][1] = y[i]; }
+  float m14 = det4(t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { t[i][0] = sq[i]; t[i][1] = x[i]; t[i][2] = y[i]; t[i][3] = z[i]; }
+  float m15 = det4(t);
+  mc[0] = 0.5f * m12 / m11;
+  mc[1] = 0.5f * m13 / m11;
+  mc[2] = 0.5f * m14 / m11;
+  mc[3] = sqrtf(mc[0] * mc[0] + mc[1] * mc[1] + mc[2] * mc[2] - m15 / m11);
+  return true;
+}
+
+__device__ inline bool estimate_cylinder(const float4* xyz, const float4* nrm, const int* s, const Limits& L, float* mc) {
+  const float eps = 1.1920928955078125e-07f;
+  f3 p1 = ld3(xyz, s[0]), p2 = ld3(xyz, s[1]);
+  if (fabsf(p1.x - p2.x) <= eps && fabsf(p1.y - p2.y) <= eps && fabsf(p1.z - p2.z) <= eps) return false;
+  f3 n1 = ld3(nrm, s[0]), n2 = ld3(nrm, s[1]);
+  f3 w = (n1 + p1) - p2;
+  float a = dot0(n1, n1), b = dot0(n1, n2), c = dot0(n2, n2), d = dot0(n1, w), e = dot0(n2, w);
+  float den = a * c - b * b;
+  float sc, tc;
+  if ((double)den < 1e-8) {
+    sc = 0.0f;
+    tc = (b > c ? d / b : e / c);
+  } else {
+    sc = (b * e - c * d) / den;
+    tc = (a * e - b * d) / den;
+  }
+  f3 line_pt = (p1 + n1) + sc * n1;
+  f3 line_dir = unit0((p2 + tc * n2) - line_pt);
+  mc[0] = line_pt.x; mc[1] = line_pt.y; mc[2] = line_pt.z;
+  mc[3] = line_dir.x; mc[4] = line_dir.y; mc[5] = line_dir.z;
+  mc[6] = (float)sqrt((double)sqr_pt_line(p1, line_pt, line_dir));
+  if ((double)mc[6] > L.radius_max || (double)mc[6] < L.radius_min) return false;
+  return true;
+}
+
+__device__ inline bool estimate_cone(const float4* xyz, const float4* nrm, const int* s, const Limits& L, float* mc) {
+  f3 p1 = ld3(xyz, s[0]), p2 = ld3(xyz, s[1]), p3 = ld3(xyz, s[2]);
+  f3 n1 = ld3(nrm, s[0]), n2 = ld3(nrm, s[1]), n3 = ld3(nrm, s[2]);
+  f3 o12 = cross0(n1, n2), o23 = cross0(n2, n3), o31 = cross0(n3, n1);
+  float den = dot0(n1, o23);
+  float d1 = dot0(p1, n1), d2 = dot0(p2, n2), d3 = dot0(p3, n3);
+  f3 apex = ((d1 * o23 + d2 * o31) + d3 * o12) / den;
+  f3 ap1 = p1 - apex, ap2 = p2 - apex, ap3 = p3 - apex;
+  f3 np1 = apex + ap1 / nrm0(ap1), np2 = apex + ap2 / nrm0(ap2), np3 = apex + ap3 / nrm0(ap3);
+  f3 axis = unit0(cross0(np2 - np1, np3 - np1));
+  ap1 = unit0(ap1); ap2 = unit0(ap2); ap3 = unit0(ap3);
+  float ang = ((acosf_d(dot0(ap1, axis)) + acosf_d(dot0(ap2, axis))) + acosf_d(dot0(ap3, axis))) / 3.0f;
+  mc[0] = apex.x; mc[1] = apex.y; mc[2] = apex.z;
+  mc[3] = axis.x; mc[4] = axis.y; mc[5] = axis.z;
+  mc[6] = ang;
+  if ((double)ang < L.min_angle) return false;
+  if ((double)ang > L.max_angle) return false;
+  return true;
+}
+
+// ------------------------------------------------------------------ isModelValid
+__device__ inline bool axis_angle_ok(const Limits& L, const float* mc) {
+  if (L.eps_angle > 0.0) {
+    double ad = fabs(angle3d(mk3(L.ax, L.ay, L.az), mk3(mc[3], mc[4], mc[5])));
+    double other = 3.14159265358979323846 - ad;
+    ad = (other < ad) ? other : ad;  // std::min semantics: NaN stays NaN and never rejects
+    if (ad > L.eps_angle) return false;
+  }
+  return true;
+}
+template <int MODEL>
+__device__ inline bool model_valid(const Limits& L, const float* mc) {
+  if (MODEL == PITT_MODEL_PLANE) return true;
+  if (MODEL == PITT_MODEL_SPHERE) {
+    if (L.radius_min != -DBL_MAX && (double)mc[3] < L.radius_min) return false;
+    if (L.radius_max != DBL_MAX && (double)mc[3] > L.radius_max) return false;
+    return true;
+  }
+  if (!axis_angle_ok(L, mc)) return false;
+  if (MODEL == PITT_MODEL_CYLINDER) {
+    if (L.radius_min != -DBL_MAX && (double)mc[6] < L.radius_min) return false;
+    if (L.radius_max != DBL_MAX && (double)mc[6] > L.radius_max) return false;
+    return true;
+  }
+  if ((double)mc[6] < L.min_angle) return false;
+  if ((double)mc[6] > L.max_angle) return false;
+  return true;
+}
+
+// coefficients (PCL order) -> scoring record with the per-hypothesis terms PCL hoists out of the loop
+template <int MODEL>
+__device__ inline void make_rec(const float* mc, bool ok, HypRec& r) {
+  if (!ok) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r.v[i] = CUDART_NAN_F;
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) r.v[i] = 0.0f;
+  if (MODEL == PITT_MODEL_PLANE || MODEL == PITT_MODEL_SPHERE) {
+    r.v[0] = mc[0]; r.v[1] = mc[1]; r.v[2] = mc[2]; r.v[3] = mc[3];
+  } else {
+    f3 p0 = mk3(mc[0], mc[1], mc[2]), dir = mk3(mc[3], mc[4], mc[5]);
+    r.v[0] = p0.x; r.v[1] = p0.y; r.v[2] = p0.z; r.v[3] = mc[6];
+    r.v[4] = dir.x; r.v[5] = dir.y; r.v[6] = dir.z;
+    r.v[7] = dot0(p0, dir);
+    r.v[8] = 1.0f / dot0(dir, dir);
+    if (MODEL == PITT_MODEL_CONE) {
+      r.v[9] = sinf_d(mc[6]);
+      r.v[10] = cosf_d(mc[6]);
+      double t = tan((double)mc[6]);
+      r.v[12] = __int_as_float(__double2loint(t));
+      r.v[13] = __int_as_float(__double2hiint(t));
+    }
+  }
+}
+
+// ------------------------------------------------------------------ inlier predicates
+// Registers-only view of a record for the scoring loops.
+template <int MODEL>
+struct RecRegs;
+
+template <>
+struct RecRegs<PITT_MODEL_PLANE> {
+  float a, b, c, d;
+  __device__ __forceinline__ void load(const HypRec* r) {
+    float4 q = *reinterpret_cast<const float4*>(r->v);
+    a = q.x; b = q.y; c = q.z; d = q.w;
+  }
+  // fabs(coeff.dot(Vector4f(x,y,z,1))) < thr   with Eigen's (p0+p2)+(p1+p3) order
+  __device__ __forceinline__ bool inlier(f3 p, f3, const ScoreParams& sp) const {
+    float s = (a * p.x + c * p.z) + (b * p.y + d);
+    return fabsf(s) < sp.thr_up;
+  }
+};
+
+template <>
+struct RecRegs<PITT_MODEL_SPHERE> {
+  float cx, cy, cz, r;
+  __device__ __forceinline__ void load(const HypRec* rec) {
+    float4 q = *reinterpret_cast<const float4*>(rec->v);
+    cx = q.x; cy = q.y; cz = q.z; r = q.w;
+  }
+  __device__ __forceinline__ bool inlier(f3 p, f3, const ScoreParams& sp) const {
+    float dx = p.x - cx, dy = p.y - cy, dz = p.z - cz;
+    float d = sqrtf(dx * dx + dy * dy + dz * dz) - r;
+    return fabsf(d) < sp.thr_up;
+  }
+};
+
+__device__ __forceinline__ bool weighted_inlier(double d_normal, double d_euclid, const ScoreParams& sp) {
+  double other = 3.14159265358979323846 - d_normal;
+  d_normal = (other < d_normal) ? other : d_normal;
+  return fabs(sp.w * d_normal + (1.0 - sp.w) * d_euclid) < sp.thr;
+}
+
+template <>
+struct RecRegs<PITT_MODEL_CYLINDER> {
+  f3 p0, dir;
+  float r, ptdotdir, dirdotdir;
+  __device__ __forceinline__ void load(const HypRec* rec) {
+    float4 q0 = *reinterpret_cast<const float4*>(rec->v);
+    float4 q1 = *reinterpret_cast<const float4*>(rec->v + 4);
+    float4 q2 = *reinterpret_cast<const float4*>(rec->v + 8);
+    p0 = mk3(q0.x, q0.y, q0.z); r = q0.w;
+    dir = mk3(q1.x, q1.y, q1.z); ptdotdir = q1.w;
+    dirdotdir = q2.x;
+  }
+  // exact PCL sequence (float geometry, double sqrt/acos/weighting)
+  __device__ __forceinline__ bool inlier_exact(f3 pt, f3 n, const ScoreParams& sp) const {
+    double d_euclid = fabs(sqrt((double)sqr_pt_line(pt, p0, dir)) - (double)r);
+    float k = (dot0(pt, dir) - ptdotdir) * dirdotdir;
+    f3 proj = p0 + k * dir;
+    f3 d = unit0(pt - proj);
+    double d_normal = fabs(angle3d(n, d));
+    return weighted_inlier(d_normal, d_euclid, sp);
+  }
+  // FP32 filter: same geometry with float sqrt/acos; only scores within sp.band of the threshold
+  // are re-evaluated with the exact sequence, so the predicate is identical to inlier_exact.
+  __device__ __forceinline__ bool inlier(f3 pt, f3 n, const ScoreParams& sp) const {
+    float sq = sqr_pt_line(pt, p0, dir);
+    float de = fabsf(sqrtf(sq) - r);
+    float k = (dot0(pt, dir) - ptdotdir) * dirdotdir;
+    f3 d = pt - (p0 + k * dir);
+    float cosang = dot0(n, d) * rsqrtf(sqn0(n) * sqn0(d));
+    cosang = fminf(1.0f, fmaxf(-1.0f, cosang));
+    float dn = acosf(cosang);
+    dn = fminf(dn, 3.14159265f - dn);
+    float wf = (float)sp.w;
+    float score = wf * dn + (1.0f - wf) * de;
+    float thr = (float)sp.thr;
+    if (fabsf(score - thr) <= sp.band) return inlier_exact(pt, n, sp);
+    return score < thr;  // NaN (point on the axis, zero normal, padding) is false on both paths
+  }
+};
+
+template <>
+struct RecRegs<PITT_MODEL_CONE> {
+  f3 apex, dir;
+  float angle, apexdotdir, dirdotdir, sin_a, cos_a;
+  double tan_a;
+  __device__ __forceinline__ void load(const HypRec* rec) {
+    float4 q0 = *reinterpret_cast<const float4*>(rec->v);
+    float4 q1 = *reinterpret_cast<const float4*>(rec->v + 4);
+    float4 q2 = *reinterpret_cast<const float4*>(rec->v + 8);
+    float4 q3 = *reinterpret_cast<const float4*>(rec->v + 12);
+    apex = mk3(q0.x, q0.y, q0.z); angle = q0.w;
+    dir = mk3(q1.x, q1.y, q1.z); apexdotdir = q1.w;
+    dirdotdir = q2.x; sin_a = q2.y; cos_a = q2.z;
+    tan_a = __hiloint2double(__float_as_int(q3.y), __float_as_int(q3.x));
+  }
+  __device__ __forceinline__ bool inlier_exact(f3 pt, f3 n, const ScoreParams& sp) const {
+    float k = (dot0(pt, dir) - apexdotdir) * dirdotdir;
+    f3 proj = apex + k * dir;
+    f3 pp = unit0(pt - proj);
+    f3 height = apex - proj;
+    double actual_r = tan_a * (double)nrm0(height);
+    height = unit0(height);
+    f3 cone_normal = sin_a * height + cos_a * pp;
+    double d_euclid = fabs(sqrt((double)sqr_pt_line(pt, apex, dir)) - actual_r);
+    double d_normal = fabs(angle3d(n, cone_normal));
+    return weighted_inlier(d_normal, d_euclid, sp);
+  }
+  __device__ __forceinline__ bool inlier(f3 pt, f3 n, const ScoreParams& sp) const {
+    float k = (dot0(pt, dir) - apexdotdir) * dirdotdir;
+    f3 proj = apex + k * dir;
+    f3 pp = pt - proj;
+    f3 height = apex - proj;
+    float hn = nrm0(height);
+    float ppn = nrm0(pp);
+    float actual_r = (float)tan_a * hn;
+    // cone normal = sin * unit(height) + cos * unit(pp)
+    float ih = 1.0f / hn, ip = 1.0f / ppn;
+    f3 cn = (sin_a * ih) * height + (cos_a * ip) * pp;
+    float de = fabsf(sqrtf(sqr_pt_line(pt, apex, dir)) - actual_r);
+    float cosang = dot0(n, cn) * rsqrtf(sqn0(n) * sqn0(cn));
+    cosang = fminf(1.0f, fmaxf(-1.0f, cosang));
+    float dn = acosf(cosang);
+    dn = fminf(dn, 3.14159265f - dn);
+    float wf = (float)sp.w;
+    float score = wf * dn + (1.0f - wf) * de;
+    float thr = (float)sp.thr;
+    if (fabsf(score - thr) <= sp.band) return inlier_exact(pt, n, sp);
+    return score < thr;  // NaN (point on the axis, zero normal, padding) is false on both paths
+  }
+};
+
+}  // namespace pitt

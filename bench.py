@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native segmentation hot path.
+
+Workload (BASELINE.json configs[1], "C2"): table-plane RANSAC on a 1 000 000-point synthetic cloud
+(70 % plane z=0 with sigma 2 mm, 30 % uniform outliers, seed 12345), 5000 hypotheses replayed from
+PCL's mt19937(12345) sample stream, threshold 0.02, stop rule ALL_H. A step = one seg.segment():
+model estimation, scoring of all H x N hypothesis-point pairs, earliest arg-max, least-squares
+refinement of the winner and final inlier selection.
+
+metric  = RANSAC hypothesis.point evaluations per second (whole job, all GPUs).
+value   = cloud resident in HBM, the step runs through pitt_sac_segment (count-only output).
+e2e     = same call with HOST buffers: pitt_stage_cloud from pinned memory (H2D of the cloud inside
+          the timed region) + pitt_sac_segment + the inlier list copied back to the host.
+N > 1   = weak scaling of the hypothesis split (config 5 pattern): every rank holds the cloud and
+          scores its own 5000 hypotheses of a N x 5000 stream, the counts are all-gathered with NCCL
+          and every rank takes the earliest arg-max; rank 0 refines/selects the winner.
+
+`--impl reference` times the CPU path (the oracle = the PCL restatement; the reference itself
+cannot be built here) on the host cores on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+N_POINTS = 1_000_000
+N_HYP = 5000
+FLOP_PER_EVAL = 6  # 3 mul + 3 add, unfused
+METRIC = "RANSAC hypothesis-point evals/s"
+UNIT = "evals/s"
+
+
+def make_workload(n_ranks):
+    from pitt_object_table_segmentation_b200 import scenes
+    xyz = scenes.plane_outlier_cloud(N_POINTS, seed=12345)
+    return xyz
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); power.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(xyz, samples, seconds_target=12.0, threads=None):
+    """The oracle (PCL restatement) scoring a bounded hypothesis sample of the same cloud on the host."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import orc_binding as O
+    threads = threads or (os.cpu_count() or 1)
+    p = O.default_support_sac_params()
+    # calibrate on 2 hypotheses per thread
+    t0 = time.perf_counter()
+    O.sac_score(xyz, None, p, samples[:2])
+    per_h = (time.perf_counter() - t0) / 2
+    h_total = int(max(threads, min(len(samples), seconds_target / per_h * threads)))
+    h_total -= h_total % threads
+    chunks = np.array_split(samples[:h_total], threads)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:  # ctypes releases the GIL inside the oracle
+        res = list(ex.map(lambda s: O.sac_score(xyz, None, p, s)[0], chunks))
+    dt = time.perf_counter() - t0
+    evals = float(h_total) * xyz.shape[0]
+    return {"value": evals / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{h_total} of {N_HYP} hypotheses x {xyz.shape[0]} points, oracle countWithinDistance, "
+                      f"{dt:.1f} s wall", "checksum": int(sum(int(r.sum()) for r in res))}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "liborc.so"], stdout=subprocess.DEVNULL)
+    from oracle import orc_binding as O
+    from pitt_object_table_segmentation_b200 import _abi as A
+    xyz = make_workload(1)
+    samples = O.pcl_sample_stream(xyz, A.MODEL_PLANE, N_HYP)
+    threads = os.cpu_count() or 1
+    per_step_target = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    last = None
+    for i in range(args.warmup + args.steps):
+        r = cpu_baseline(xyz, samples, seconds_target=per_step_target, threads=threads)
+        if i >= args.warmup:
+            vals.append(r["value"])
+        last = r
+    value = float(np.mean(vals))
+    evals_per_step = N_POINTS * N_HYP
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": evals_per_step / value * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: table-plane RANSAC, 1M-point cloud x 5000 hypotheses (bounded sample per step, "
+                               "ms_per_step extrapolated to the full 5e9 evaluations)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": last["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(3, args.warmup)
+
+    import torch
+    import torch.distributed as dist
+    import pitt_object_table_segmentation_b200 as pkg
+    from pitt_object_table_segmentation_b200 import _abi as A
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream()
+    ctx = pkg.Context(local_rank, seed=12345, stream=stream.cuda_stream)
+
+    xyz = make_workload(world)
+    n = xyz.shape[0]
+    host_pinned = torch.from_numpy(xyz).pin_memory()
+    cloud = ctx.stage_host_ptr(host_pinned.data_ptr(), 16, n)
+    samples_all = ctx.pcl_sample_stream(cloud, A.MODEL_PLANE, N_HYP * world)
+    samples = np.ascontiguousarray(samples_all[rank * N_HYP:(rank + 1) * N_HYP])
+
+    p = pkg.default_support_sac_params()
+    p.sampler, p.stop, p.max_iterations = A.SAMPLER_REPLAY, A.STOP_ALL_H, N_HYP
+    p.replay_samples = samples.ctypes.data_as(A.i32p)
+    p.replay_count = N_HYP
+
+    l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    d_samples = torch.from_numpy(samples).to(dev)
+    d_counts = torch.zeros(N_HYP, dtype=torch.int32, device=dev)
+    d_all = torch.zeros(N_HYP * world, dtype=torch.int32, device=dev)
+    d_best = torch.zeros(2, dtype=torch.int32, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        if world == 1:
+            return ctx.sac_segment_count_only(cloud, p)
+        # hypothesis split: local scoring, NCCL all-gather of the counts, earliest arg-max everywhere
+        ctx.sac_score_device(cloud, p, d_samples.data_ptr(), N_HYP, d_counts.data_ptr())
+        dist.all_gather_into_tensor(d_all, d_counts)
+        ctx.argmax_counts_device(d_all.data_ptr(), N_HYP * world, d_best.data_ptr())
+        return None
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        t_wall = time.perf_counter()
+        l0 = ctx.kernel_launches
+        for i in range(steps):
+            l2_flush.zero_()  # flush L2 between timed iterations (outside the event pair)
+            ev[i][0].record()
+            fn()
+            ev[i][1].record()
+        barrier()
+        wall = time.perf_counter() - t_wall
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        timed.launches = ctx.kernel_launches - l0
+        return float(t.item()) / steps, wall
+
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ms_step, wall = timed(step_resident, args.steps, args.warmup)
+    clk = clocks.stop()
+    launches = timed.launches
+    evals_step = float(n) * N_HYP * world
+    value = evals_step / (ms_step * 1e-3)
+
+    # ---- end-to-end arm: host buffers in, host buffers out, through the C ABI
+    inl_host = np.empty(n, np.int32)
+    n_inl, n_co = C.c_int(0), C.c_int(0)
+    co = np.zeros(8, np.float32)
+    handle = C.c_void_p()
+    d2h_bytes = [0]
+
+    def step_e2e():
+        st = ctx.lib.pitt_stage_cloud(ctx.handle, C.c_void_p(host_pinned.data_ptr()), 16, n, C.byref(handle))
+        assert st == 0, st
+        st = ctx.lib.pitt_sac_segment(ctx.handle, handle, C.byref(p), inl_host.ctypes.data_as(A.i32p), n,
+                                      C.byref(n_inl), co.ctypes.data_as(A.f32p), C.byref(n_co), None)
+        assert st == 0, st
+        ctx.lib.pitt_release_cloud(ctx.handle, handle)
+        d2h_bytes[0] = n_inl.value * 4 + 8 * 4 + 16 * 4
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_counts)
+
+    e2e_steps = max(3, min(args.steps, 10))
+    e2e_ms, _ = timed(step_e2e, e2e_steps, 2)
+    e2e_value = evals_step / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (plane_score_kernel): estimate + score bracketed by events
+    def kernel_only():
+        ctx.sac_score_device(cloud, p, d_samples.data_ptr(), N_HYP, d_counts.data_ptr())
+
+    k_ms, _ = timed(kernel_only, max(5, min(args.steps, 20)), 3)
+    peak_unfused = ctx.fp32_peak(1)
+    peak_ffma = ctx.fp32_peak(0)
+    achieved = float(n) * N_HYP * FLOP_PER_EVAL / (k_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_plane_score_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "fp32", "kernel": "plane_score_kernel", "achieved": achieved, "peak": peak_unfused,
+        "unit": "TFLOP/s", "frac": achieved / peak_unfused, "traffic": traffic,
+        "peak_source": "measured live: pitt_fp32_peak(kind=1) = unfused FMUL+FADD issue rate (bit-exact scoring "
+                       "cannot use FMA); MEASURED_PEAKS.json has no FP32 CUDA-core figure",
+        "peak_ffma_tflops": peak_ffma, "kernel_ms": k_ms, "algorithmic_flop_per_launch": float(n) * N_HYP * 6,
+        "algorithmic_bytes_per_launch": n * 16 + N_HYP * (64 + 4),
+    }
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C2: table-plane RANSAC only, 1M-point synthetic cloud x 5000 replayed "
+                                   "mt19937(12345) hypotheses per GPU, thr 0.02, ALL_H, refine + select",
+                       "points": n, "hypotheses_per_gpu": N_HYP, "l2": "flushed between timed iterations (256 MB write)",
+                       "parallelism": "hypothesis split + NCCL all-gather of counts" if world > 1 else "single GPU"},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": n * 16 + N_HYP * 12,
+                    "d2h_bytes_per_step": d2h_bytes[0]},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "wall_s_timed_region": wall,
+        }
+        if not args.no_cpu_baseline:
+            from oracle import orc_binding as O
+            line["cpu_baseline"] = cpu_baseline(xyz, samples, seconds_target=12.0)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -269,7 +269,7 @@ int pitt_knn(pitt_ctx* ctx, const pitt_cloud* cloud, int k, int32_t* out_idx, fl
 
 /* ------------------------------------------------------------------ a2,a9-a12: seg.segment() */
 int pitt_sac_segment(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_sac_params* params,
-                     int32_t* inliers, int inliers_cap, int* n_inliers,
+                     int32_t* inliers /* NULL: count only */, int inliers_cap, int* n_inliers,
                      float coeffs[8], int* n_coeffs, pitt_sac_info* info /* nullable */);
 
 /* Parity/bench hook below segment(): score a caller supplied sample table. For hypothesis h the
@@ -283,6 +283,9 @@ int pitt_sac_score(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_sac_params
  * the resident-input arm of bench.py and the multi-GPU hypothesis split (config 5). */
 int pitt_sac_score_device(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_sac_params* params,
                           const void* d_samples, int n_hypotheses, void* d_counts);
+/* Earliest arg-max over H device-resident int32 counts (e.g. all-gathered over NVLink from the
+ * ranks of a hypothesis split); d_best (device) receives {index, count}. */
+int pitt_argmax_counts_device(pitt_ctx* ctx, const void* d_counts, int n_hypotheses, void* d_best);
 /* selectWithinDistance for given coefficients (ascending indices). */
 int pitt_sac_select(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_sac_params* params,
                     const float* coeffs, int32_t* inliers, int inliers_cap, int* n_inliers);

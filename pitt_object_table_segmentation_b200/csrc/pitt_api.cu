@@ -284,8 +284,8 @@ int pitt_sac_segment(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params* 
   *n_coeffs = r.n_coeffs;
   for (int i = 0; i < 8; ++i) coeffs[i] = r.coeffs[i];
   int status = PITT_OK;
-  if (r.n_inliers > 0) {
-    if (!inliers || cap < r.n_inliers) {
+  if (r.n_inliers > 0 && inliers) {  // inliers == NULL: the caller only wants the count and the coefficients
+    if (cap < r.n_inliers) {
       status = fail(ctx, PITT_ERR_CAPACITY, "inlier buffer too small");
     } else {
       PITT_CUDA(ctx, cudaMemcpyAsync(inliers, r.d_inliers, (size_t)r.n_inliers * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -459,6 +459,21 @@ int pitt_fp32_peak(pitt_ctx* ctx, int kind, double* tflops) {
   int s = fp32_peak(ctx, kind, tflops);
   timer.finish();
   return s;
+}
+
+/* arg-max of gathered per-hypothesis counts (multi-GPU hypothesis split, config 5): d_counts are H
+ * int32 on the device, d_best receives {index, count}; ties keep the earliest hypothesis. */
+int pitt_argmax_counts_device(pitt_ctx* ctx, const void* d_counts, int H, void* d_best) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!d_counts || !d_best || H <= 0) return fail(ctx, PITT_ERR_INVALID, "pitt_argmax_counts_device arguments");
+  cudaSetDevice(ctx->device);
+  arena_reset(ctx);
+  uint8_t* d_flags = nullptr;
+  float* d_dummy = nullptr;
+  PITT_TRY(arena_alloc(ctx, (size_t)H, &d_flags));
+  PITT_TRY(arena_alloc(ctx, (size_t)H * 8 + 8, &d_dummy));
+  PITT_CUDA(ctx, cudaMemsetAsync(d_flags, 1, (size_t)H, ctx->stream));
+  return sac_winner(ctx, (const int*)d_counts, d_flags, H, d_dummy, (int*)d_best, d_dummy + (size_t)H * 8);
 }
 
 /* test hook (not in the public header): route plane scoring through the generic kernel */

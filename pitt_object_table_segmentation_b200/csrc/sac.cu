@@ -144,6 +144,10 @@ __device__ __forceinline__ unsigned long long fadd2_exact(unsigned long long a, 
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(one), "l"(b));
   return d;
 }
+// cnt += (a < b): FSETP + predicated IADD3 (two ALU-pipe instructions; NaN compares false)
+__device__ __forceinline__ void count_if_lt(int& cnt, float a, float b) {
+  asm("{\n\t.reg .pred p;\n\tsetp.lt.f32 p, %1, %2;\n\t@p add.s32 %0, %0, 1;\n\t}" : "+r"(cnt) : "f"(a), "f"(b));
+}
 __device__ __forceinline__ float lo32(unsigned long long v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
 __device__ __forceinline__ float hi32(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
 
@@ -192,17 +196,22 @@ plane_score_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restri
     }
     __syncthreads();
     const float4* tile = s_pts[t & 1];
-#pragma unroll 2
-    for (int i = 0; i < TILE; ++i) {
-      float4 p = tile[i];  // LDS.128 broadcast
-      unsigned long long X = pack2(p.x, p.x), Y = pack2(p.y, p.y), Z = pack2(p.z, p.z);
+    // two points per step (ILP): 6 packed FP32 instructions + 2x(FSETP, @p IADD3) per evaluation pair
+    for (int i = 0; i < TILE; i += 2) {
+      float4 p = tile[i], q = tile[i + 1];  // LDS.128 broadcasts
+      unsigned long long PX = pack2(p.x, p.x), PY = pack2(p.y, p.y), PZ = pack2(p.z, p.z);
+      unsigned long long QX = pack2(q.x, q.x), QY = pack2(q.y, q.y), QZ = pack2(q.z, q.z);
 #pragma unroll
       for (int k = 0; k < KP; ++k) {
         // (a*x + c*z) + (b*y + d), two hypotheses per instruction
-        unsigned long long s = fadd2_exact(fadd2_exact(mul2(A[k], X), mul2(C[k], Z), ONE),
-                                           fadd2_exact(mul2(B[k], Y), D[k], ONE), ONE);
-        cnt[2 * k] += (fabsf(lo32(s)) < thr_up) ? 1 : 0;
-        cnt[2 * k + 1] += (fabsf(hi32(s)) < thr_up) ? 1 : 0;
+        unsigned long long sp = fadd2_exact(fadd2_exact(mul2(A[k], PX), mul2(C[k], PZ), ONE),
+                                            fadd2_exact(mul2(B[k], PY), D[k], ONE), ONE);
+        unsigned long long sq = fadd2_exact(fadd2_exact(mul2(A[k], QX), mul2(C[k], QZ), ONE),
+                                            fadd2_exact(mul2(B[k], QY), D[k], ONE), ONE);
+        count_if_lt(cnt[2 * k], fabsf(lo32(sp)), thr_up);
+        count_if_lt(cnt[2 * k + 1], fabsf(hi32(sp)), thr_up);
+        count_if_lt(cnt[2 * k], fabsf(lo32(sq)), thr_up);
+        count_if_lt(cnt[2 * k + 1], fabsf(hi32(sq)), thr_up);
       }
     }
     __syncthreads();

@@ -1,0 +1,220 @@
+// knn.cu — exact k-nearest-neighbour search on the uniform grid and the normal estimator (K8).
+//
+// Replaces ne.compute() of PCManager::estimateNormal (reference: src/point_cloud_library/
+// pc_manager.cpp:68-78; pcl::NormalEstimation::computeFeature + KdTreeFLANN::nearestKSearch,
+// SURVEY.md B.7/B.8): k neighbours including the query, ordered by (squared distance, index);
+// float covariance accumulated in that order; eigen33; curvature; flip towards the viewpoint.
+#include <cmath>
+
+#include "grid.cuh"
+#include "pitt_math.cuh"
+
+namespace pitt {
+
+constexpr int KNN_KMAX = 64;
+
+__device__ __forceinline__ bool cand_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
+
+// max-heap on (d, i) in thread-local arrays
+__device__ __forceinline__ void heap_sift_down(float* hd, int* hi, int size, int pos) {
+  float d = hd[pos];
+  int i = hi[pos];
+  for (;;) {
+    int c = 2 * pos + 1;
+    if (c >= size) break;
+    if (c + 1 < size && cand_less(hd[c], hi[c], hd[c + 1], hi[c + 1])) ++c;
+    if (!cand_less(d, i, hd[c], hi[c])) break;
+    hd[pos] = hd[c];
+    hi[pos] = hi[c];
+    pos = c;
+  }
+  hd[pos] = d;
+  hi[pos] = i;
+}
+__device__ __forceinline__ void heap_sift_up(float* hd, int* hi, int pos) {
+  float d = hd[pos];
+  int i = hi[pos];
+  while (pos > 0) {
+    int p = (pos - 1) >> 1;
+    if (!cand_less(hd[p], hi[p], d, i)) break;
+    hd[pos] = hd[p];
+    hi[pos] = hi[p];
+    pos = p;
+  }
+  hd[pos] = d;
+  hi[pos] = i;
+}
+
+template <int MODE>  // 0: neighbour lists, 1: normals
+__global__ void __launch_bounds__(128)
+knn_kernel(GridDev g, const float4* __restrict__ xyz, int k, float vpx, float vpy, float vpz, int* __restrict__ out_idx,
+           float* __restrict__ out_sq, float4* __restrict__ out_nrm) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= g.n) return;
+  const float4 q = g.sorted[t];
+  const int qi = __float_as_int(q.w);
+  float hd[KNN_KMAX];
+  int hi[KNN_KMAX];
+  int size = 0;
+  const int want = min(k, g.n);
+  const int cx = grid_coord(q.x, g.mnx, g.inv_h, g.dx), cy = grid_coord(q.y, g.mny, g.inv_h, g.dy),
+            cz = grid_coord(q.z, g.mnz, g.inv_h, g.dz);
+  const int rmax = max(g.dx, max(g.dy, g.dz));
+  for (int r = 0; r <= rmax; ++r) {
+    const int z0 = max(cz - r, 0), z1 = min(cz + r, g.dz - 1);
+    const int y0 = max(cy - r, 0), y1 = min(cy + r, g.dy - 1);
+    const int x0 = max(cx - r, 0), x1 = min(cx + r, g.dx - 1);
+    for (int z = z0; z <= z1; ++z)
+      for (int y = y0; y <= y1; ++y) {
+        const bool face = (abs(z - cz) == r) || (abs(y - cy) == r);
+        const int step = face ? 1 : max(1, x1 - x0);  // interior rows: only the two end cells
+        for (int x = x0; x <= x1; x += step) {
+          if (!face && abs(x - cx) != r) continue;
+          const int cell = (z * g.dy + y) * g.dx + x;
+          const int b = g.cell_start[cell], e = g.cell_start[cell + 1];
+          for (int j = b; j < e; ++j) {
+            const float4 p = g.sorted[j];
+            const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
+            const float d = (ddx * ddx + ddy * ddy) + ddz * ddz;
+            const int pi = __float_as_int(p.w);
+            if (size < want) {
+              hd[size] = d;
+              hi[size] = pi;
+              heap_sift_up(hd, hi, size);
+              ++size;
+            } else if (cand_less(d, pi, hd[0], hi[0])) {
+              hd[0] = d;
+              hi[0] = pi;
+              heap_sift_down(hd, hi, size, 0);
+            }
+          }
+        }
+      }
+    if (size >= want) {
+      // every point outside the cube of r cells around the query cell is farther than `bound`
+      float bound = 3.0e38f;
+      if (cx - r > 0) bound = fminf(bound, q.x - (g.mnx + (float)(cx - r) * g.h));
+      if (cx + r < g.dx - 1) bound = fminf(bound, (g.mnx + (float)(cx + r + 1) * g.h) - q.x);
+      if (cy - r > 0) bound = fminf(bound, q.y - (g.mny + (float)(cy - r) * g.h));
+      if (cy + r < g.dy - 1) bound = fminf(bound, (g.mny + (float)(cy + r + 1) * g.h) - q.y);
+      if (cz - r > 0) bound = fminf(bound, q.z - (g.mnz + (float)(cz - r) * g.h));
+      if (cz + r < g.dz - 1) bound = fminf(bound, (g.mnz + (float)(cz + r + 1) * g.h) - q.z);
+      bound -= 2e-3f * g.h;  // float rounding of the cell assignment
+      if (bound > 0.0f && hd[0] < bound * bound) break;
+    }
+  }
+  // heap sort -> ascending (distance, index)
+  for (int s = size - 1; s > 0; --s) {
+    float d = hd[0];
+    int i = hi[0];
+    hd[0] = hd[s];
+    hi[0] = hi[s];
+    hd[s] = d;
+    hi[s] = i;
+    heap_sift_down(hd, hi, s, 0);
+  }
+  if (MODE == 0) {
+    for (int s = 0; s < k; ++s) {
+      out_idx[(size_t)qi * k + s] = s < size ? hi[s] : -1;
+      if (out_sq) out_sq[(size_t)qi * k + s] = s < size ? hd[s] : CUDART_INF_F;
+    }
+    return;
+  }
+  if (size < 3) return;  // stays NaN
+  // computeMeanAndCovarianceMatrix: float accumulators in neighbour order
+  float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int s = 0; s < size; ++s) {
+    const float4 p = __ldg(xyz + hi[s]);
+    accu[0] += p.x * p.x; accu[1] += p.x * p.y; accu[2] += p.x * p.z;
+    accu[3] += p.y * p.y; accu[4] += p.y * p.z; accu[5] += p.z * p.z;
+    accu[6] += p.x; accu[7] += p.y; accu[8] += p.z;
+  }
+  float cov[9], cen[3], ev, evec[3];
+  cov_from_accu(accu, (float)size, cov, cen);
+  eigen33(cov, ev, evec);
+  float nx = evec[0], ny = evec[1], nz = evec[2];
+  const float eig_sum = cov[0] + cov[4] + cov[8];
+  const float curv = (eig_sum != 0.0f) ? fabsf(ev / eig_sum) : 0.0f;
+  const float vx = vpx - q.x, vy = vpy - q.y, vz = vpz - q.z;
+  const float cos_theta = (vx * nx + vy * ny + vz * nz);
+  if (cos_theta < 0.0f) { nx = -nx; ny = -ny; nz = -nz; }
+  out_nrm[qi] = make_float4(nx, ny, nz, curv);
+}
+
+__global__ void fill_f4_kernel(float4* p, int n, float4 v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void fill_knn_kernel(int* idx, float* sq, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    idx[i] = -1;
+    if (sq) sq[i] = CUDART_INF_F;
+  }
+}
+
+int estimate_normals_impl(pitt_ctx* ctx, const float4* d_xyz, int n, int k, const float vp[3], float4* d_nrm) {
+  if (n <= 0) return PITT_OK;
+  if (k < 1 || k > KNN_KMAX) return fail(ctx, PITT_ERR_INVALID, "k must be in [1, 64]");
+  const float nan = nanf("");
+  fill_f4_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_nrm, n, make_float4(nan, nan, nan, nan));
+  ctx->launches++;
+  GridDev g;
+  PITT_TRY(grid_build(ctx, d_xyz, n, -1.0f, fmaxf(2.0f, (float)k / 4.0f), &g));
+  if (g.n <= 0) return PITT_OK;
+  knn_kernel<1><<<cdiv(g.n, 128), 128, 0, ctx->stream>>>(g, d_xyz, k, vp[0], vp[1], vp[2], nullptr, nullptr, d_nrm);
+  ctx->launches++;
+  PITT_CUDA(ctx, cudaGetLastError());
+  return PITT_OK;
+}
+
+}  // namespace pitt
+
+using namespace pitt;
+
+extern "C" {
+
+int pitt_estimate_normals(pitt_ctx* ctx, pitt_cloud* c, int k, const float viewpoint[3]) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!c || !viewpoint) return fail(ctx, PITT_ERR_INVALID, "pitt_estimate_normals arguments");
+  cudaSetDevice(ctx->device);
+  CallTimer timer(ctx);
+  if (c->n > 0) {
+    if (!c->d_nrm) PITT_CUDA(ctx, cudaMalloc((void**)&c->d_nrm, (size_t)c->n * sizeof(float4)));
+    PITT_TRY(estimate_normals_impl(ctx, c->d_xyz, c->n, k, viewpoint, c->d_nrm));
+    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  c->has_normals = true;
+  timer.finish();
+  return PITT_OK;
+}
+
+int pitt_knn(pitt_ctx* ctx, const pitt_cloud* c, int k, int32_t* out_idx, float* out_sqdist) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!c || !out_idx || k < 1 || k > KNN_KMAX) return fail(ctx, PITT_ERR_INVALID, "pitt_knn arguments (k in [1,64])");
+  cudaSetDevice(ctx->device);
+  CallTimer timer(ctx);
+  const int n = c->n;
+  if (n > 0) {
+    int* d_idx = nullptr;
+    float* d_sq = nullptr;
+    PITT_TRY(arena_alloc(ctx, (size_t)n * k, &d_idx));
+    PITT_TRY(arena_alloc(ctx, (size_t)n * k, &d_sq));
+    size_t tot = (size_t)n * k;
+    fill_knn_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, ctx->stream>>>(d_idx, d_sq, tot);
+    ctx->launches++;
+    GridDev g;
+    PITT_TRY(grid_build(ctx, c->d_xyz, n, -1.0f, fmaxf(2.0f, (float)k / 4.0f), &g));
+    if (g.n > 0) {
+      knn_kernel<0><<<cdiv(g.n, 128), 128, 0, ctx->stream>>>(g, c->d_xyz, k, 0.f, 0.f, 0.f, d_idx, d_sq, nullptr);
+      ctx->launches++;
+    }
+    PITT_CUDA(ctx, cudaMemcpyAsync(out_idx, d_idx, tot * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_sqdist) PITT_CUDA(ctx, cudaMemcpyAsync(out_sqdist, d_sq, tot * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  timer.finish();
+  return PITT_OK;
+}
+
+}  // extern "C"

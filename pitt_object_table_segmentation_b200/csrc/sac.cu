@@ -153,50 +153,72 @@ __device__ __forceinline__ float hi32(unsigned long long v) { return __uint_as_f
 
 template <int KH, int TPB, int TILE>
 __global__ void __launch_bounds__(TPB)
-plane_score_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict__ recs, int H, int pts_per_cta,
-                   float thr_up, float one_rt, int* __restrict__ counts) {
+plane_score_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict__ recs, int H, int n_ptiles,
+                   int n_items, float thr_up, float one_rt, int* __restrict__ work_counter, int* __restrict__ counts) {
+  // Persistent CTAs pull work items (hypothesis block hb, point tile pt) from an atomic counter:
+  // item = hb * n_ptiles + pt. The next item's tile is prefetched with cp.async while the current
+  // one is scored, so the FP32 pipe never waits on L2/HBM and there is no wave-quantisation tail.
   __shared__ __align__(16) float4 s_pts[2][TILE];
+  __shared__ int s_item[2];
   const unsigned long long ONE = pack2(one_rt, one_rt);
   constexpr int KP = KH / 2;
-  const int h_base = (blockIdx.y * TPB + threadIdx.x) * KH;
   unsigned long long A[KP], B[KP], C[KP], D[KP];
   int cnt[KH];
+  int cur_hb = -1;
+  auto flush = [&]() {
+    if (cur_hb < 0) return;
+    const int h_base = (cur_hb * TPB + threadIdx.x) * KH;
 #pragma unroll
-  for (int k = 0; k < KP; ++k) {
-    float4 r0 = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F), r1 = r0;
-    if (h_base + 2 * k < H) r0 = __ldg(reinterpret_cast<const float4*>(recs[h_base + 2 * k].v));
-    if (h_base + 2 * k + 1 < H) r1 = __ldg(reinterpret_cast<const float4*>(recs[h_base + 2 * k + 1].v));
-    A[k] = pack2(r0.x, r1.x); B[k] = pack2(r0.y, r1.y); C[k] = pack2(r0.z, r1.z); D[k] = pack2(r0.w, r1.w);
-    cnt[2 * k] = 0; cnt[2 * k + 1] = 0;
-  }
-  const int p_begin = blockIdx.x * pts_per_cta;
-  const int p_end = min(n, p_begin + pts_per_cta);
-  const int n_tiles = (p_end - p_begin + TILE - 1) / TILE;
-  // double-buffered tile staging with cp.async (LDGSTS)
-  auto stage = [&](int t, int buf) {
-    int base = p_begin + t * TILE;
-    for (int i = threadIdx.x; i < TILE; i += TPB) {
-      int gi = base + i;
-      if (gi < p_end) {
-        unsigned saddr = (unsigned)__cvta_generic_to_shared(&s_pts[buf][i]);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(xyz + gi));
-      } else {
-        s_pts[buf][i] = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+    for (int k = 0; k < KH; ++k)
+      if (h_base + k < H && cnt[k]) atomicAdd(&counts[h_base + k], cnt[k]);
+  };
+  auto load_hyps = [&](int hb) {
+    const int h_base = (hb * TPB + threadIdx.x) * KH;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      float4 r0 = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F), r1 = r0;
+      if (h_base + 2 * k < H) r0 = __ldg(reinterpret_cast<const float4*>(recs[h_base + 2 * k].v));
+      if (h_base + 2 * k + 1 < H) r1 = __ldg(reinterpret_cast<const float4*>(recs[h_base + 2 * k + 1].v));
+      A[k] = pack2(r0.x, r1.x); B[k] = pack2(r0.y, r1.y); C[k] = pack2(r0.z, r1.z); D[k] = pack2(r0.w, r1.w);
+      cnt[2 * k] = 0; cnt[2 * k + 1] = 0;
+    }
+    cur_hb = hb;
+  };
+  auto stage = [&](int item, int buf) {
+    if (item < n_items) {
+      const int base = (item % n_ptiles) * TILE;
+      for (int i = threadIdx.x; i < TILE; i += TPB) {
+        int gi = base + i;
+        if (gi < n) {
+          unsigned saddr = (unsigned)__cvta_generic_to_shared(&s_pts[buf][i]);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(xyz + gi));
+        } else {
+          s_pts[buf][i] = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+        }
       }
     }
     asm volatile("cp.async.commit_group;");
   };
-  if (n_tiles > 0) stage(0, 0);
-  for (int t = 0; t < n_tiles; ++t) {
-    if (t + 1 < n_tiles) {
-      stage(t + 1, (t + 1) & 1);
-      asm volatile("cp.async.wait_group 1;");
-    } else {
-      asm volatile("cp.async.wait_group 0;");
+  if (threadIdx.x == 0) s_item[0] = atomicAdd(work_counter, 1);
+  __syncthreads();
+  int item = s_item[0];
+  stage(item, 0);
+  int it = 0;
+  while (item < n_items) {
+    // claim the next item and start its loads before scoring the current tile
+    if (threadIdx.x == 0) s_item[(it + 1) & 1] = atomicAdd(work_counter, 1);
+    asm volatile("cp.async.wait_group 0;");
+    __syncthreads();  // tile `it` landed for everyone; s_item[(it+1)&1] visible; buffer (it+1)&1 is free
+    const int next = s_item[(it + 1) & 1];
+    stage(next, (it + 1) & 1);
+    const int hb = item / n_ptiles;
+    if (hb != cur_hb) {
+      flush();
+      load_hyps(hb);
     }
-    __syncthreads();
-    const float4* tile = s_pts[t & 1];
+    const float4* tile = s_pts[it & 1];
     // two points per step (ILP): 6 packed FP32 instructions + 2x(FSETP, @p IADD3) per evaluation pair
+#pragma unroll 2
     for (int i = 0; i < TILE; i += 2) {
       float4 p = tile[i], q = tile[i + 1];  // LDS.128 broadcasts
       unsigned long long PX = pack2(p.x, p.x), PY = pack2(p.y, p.y), PZ = pack2(p.z, p.z);
@@ -214,11 +236,11 @@ plane_score_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restri
         count_if_lt(cnt[2 * k + 1], fabsf(hi32(sq)), thr_up);
       }
     }
-    __syncthreads();
+    item = next;
+    ++it;
   }
-#pragma unroll
-  for (int k = 0; k < KH; ++k)
-    if (h_base + k < H && cnt[k]) atomicAdd(&counts[h_base + k], cnt[k]);
+  asm volatile("cp.async.wait_group 0;");
+  flush();
 }
 
 // =====================================================================================
@@ -558,16 +580,20 @@ static int launch_score_plane_packed(pitt_ctx* ctx, const pitt_cloud* c, const H
                                      int* d_counts) {
   constexpr int KH = 8, TPB = 128, TILE = 512;
   const int n = c->n;
-  int hblocks = cdiv(H, KH * TPB);
-  int want_ctas = ctx->sm_count * 8;
-  int pblocks = want_ctas / hblocks;
-  if (pblocks < 1) pblocks = 1;
-  int tiles = cdiv(n, TILE);
-  if (pblocks > tiles) pblocks = tiles;
-  int pts_per_cta = cdiv(tiles, pblocks) * TILE;
-  pblocks = cdiv(n, pts_per_cta);
-  dim3 grid(pblocks, hblocks);
-  plane_score_kernel<KH, TPB, TILE><<<grid, TPB, 0, ctx->stream>>>(c->d_xyz, n, d_recs, H, pts_per_cta, sp.thr_up, 1.0f, d_counts);
+  const int hblocks = cdiv(H, KH * TPB);
+  const int n_ptiles = cdiv(n, TILE);
+  const long long items = (long long)hblocks * n_ptiles;
+  if (items > INT_MAX) return fail(ctx, PITT_ERR_INVALID, "plane scoring: too many work items");
+  int ctas_per_sm = 0;
+  PITT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, plane_score_kernel<KH, TPB, TILE>, TPB, 0));
+  if (ctas_per_sm < 1) ctas_per_sm = 1;
+  int grid = ctx->sm_count * ctas_per_sm;
+  if ((long long)grid > items) grid = (int)items;
+  int* d_work = nullptr;
+  PITT_TRY(arena_alloc(ctx, 1, &d_work));
+  PITT_CUDA(ctx, cudaMemsetAsync(d_work, 0, sizeof(int), ctx->stream));
+  plane_score_kernel<KH, TPB, TILE><<<grid, TPB, 0, ctx->stream>>>(c->d_xyz, n, d_recs, H, n_ptiles, (int)items, sp.thr_up,
+                                                                  1.0f, d_work, d_counts);
   PITT_LAUNCH_CHECK(ctx, "plane_score_kernel");
   return PITT_OK;
 }

@@ -3,9 +3,6 @@
 using namespace pitt;
 extern "C" {
 #define NOT_YET(ctx, name) (ctx ? fail(ctx, PITT_ERR_INVALID, name ": not implemented yet") : PITT_ERR_CUDA)
-int pitt_estimate_normals(pitt_ctx* ctx, pitt_cloud*, int, const float*) { return NOT_YET(ctx, "pitt_estimate_normals"); }
-int pitt_knn(pitt_ctx* ctx, const pitt_cloud*, int, int32_t*, float*) { return NOT_YET(ctx, "pitt_knn"); }
-int pitt_euclidean_clusters(pitt_ctx* ctx, const pitt_cloud*, double, int, int, int32_t*, int*) { return NOT_YET(ctx, "pitt_euclidean_clusters"); }
 int pitt_find_supports(pitt_ctx* ctx, const pitt_cloud*, const pitt_support_params*, pitt_support_result*) { return NOT_YET(ctx, "pitt_find_supports"); }
 int pitt_cluster_service(pitt_ctx* ctx, const pitt_cloud*, const pitt_cluster_params*, pitt_clusters_result*) { return NOT_YET(ctx, "pitt_cluster_service"); }
 int pitt_primitive_service(pitt_ctx* ctx, const pitt_cloud*, const pitt_sac_params*, pitt_primitive_result*) { return NOT_YET(ctx, "pitt_primitive_service"); }

@@ -1,17 +1,519 @@
-// lm.cu — Levenberg-Marquardt refinement of sphere / cylinder / cone (K7). PLACEHOLDER: copies the
-// un-refined model and reports status -100 until the device LM lands.
+// lm.cu — Levenberg-Marquardt refinement of sphere / cylinder / cone coefficients (K7).
+//
+// Replaces SampleConsensusModel{Sphere,Cylinder,Cone}::optimizeModelCoefficients, i.e.
+// Eigen::LevenbergMarquardt<Eigen::NumericalDiff<Functor>, float>::minimize() (Eigen 3.2
+// unsupported/NonLinearOptimization) reached from seg.segment() with
+// setOptimizeCoefficients(true) at sphere_segmentation_srv.cpp:60, cylinder…:114, cone…:115.
+//
+// One CTA per problem. The m residual rows live in global/L2 memory (fvec, the m x n Jacobian);
+// every O(m) step is data parallel over the CTA, every reduction over m is accumulated in
+// double-double by a fixed-shape tree and rounded once to float (the oracle defines those sums as
+// exact sums rounded once), and the n x n algebra (n <= 7: lmpar, qrsolv, Givens) runs on thread 0.
+#include <cfloat>
+
 #include "pitt_common.cuh"
 #include "sac.cuh"
 
 namespace pitt {
-__global__ void lm_copy_kernel(const float* __restrict__ m, float* __restrict__ r, int* __restrict__ info) {
-  if (threadIdx.x < 8) r[threadIdx.x] = m[threadIdx.x];
-  if (threadIdx.x == 0) { info[0] = -100; info[1] = 0; }
+
+constexpr int LM_TPB = 512;
+constexpr int LM_NW = LM_TPB / 32;
+
+struct dd {
+  double hi, lo;
+};
+__device__ __forceinline__ void dd_add(dd& s, double x) {
+  double t = s.hi + x;
+  double bb = t - s.hi;
+  double err = (s.hi - (t - bb)) + (x - bb);
+  s.hi = t;
+  s.lo += err;
 }
-int lm_refine(pitt_ctx* ctx, const pitt_cloud*, int, const float* d_model, const int*, const int*, int, float* d_refined,
-              int* d_lm_info) {
-  lm_copy_kernel<<<1, 32, 0, ctx->stream>>>(d_model, d_refined, d_lm_info);
+__device__ __forceinline__ void dd_merge(dd& s, double ohi, double olo) {
+  dd_add(s, ohi);
+  s.lo += olo;
+}
+
+struct LmShared {
+  float x[8], xs[8], diag[8], qtf[8], wa1[8], wa2[8], wa3[8], hcoef[8], colSq[8];
+  float r[64];
+  int perm[8], transp[8];
+  double red_hi[LM_NW], red_lo[LM_NW];
+  float bcast[4];
+  int ibcast[4];
+};
+
+// sum over i in [r0, m) of a[i]*b[i], exact-to-double-double, rounded once to float; all threads get it
+__device__ float block_dot(const float* __restrict__ a, const float* __restrict__ b, int r0, int m, LmShared& S) {
+  dd s{0.0, 0.0};
+  for (int i = r0 + threadIdx.x; i < m; i += LM_TPB) dd_add(s, (double)a[i] * (double)b[i]);
+  for (int o = 16; o > 0; o >>= 1) {
+    double ohi = __shfl_down_sync(0xffffffffu, s.hi, o), olo = __shfl_down_sync(0xffffffffu, s.lo, o);
+    dd_merge(s, ohi, olo);
+  }
+  __syncthreads();  // protect S.red_* / S.bcast from the previous call's readers
+  if ((threadIdx.x & 31) == 0) { S.red_hi[threadIdx.x >> 5] = s.hi; S.red_lo[threadIdx.x >> 5] = s.lo; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    dd t{0.0, 0.0};
+    for (int w = 0; w < LM_NW; ++w) dd_merge(t, S.red_hi[w], S.red_lo[w]);
+    S.bcast[0] = (float)(t.hi + t.lo);
+  }
+  __syncthreads();
+  return S.bcast[0];
+}
+
+// ---- residual functors (float sequences of the PCL OptimizationFunctor::operator())
+template <int MODEL>
+__device__ void eval_residuals(const float4* __restrict__ xyz, const int* __restrict__ idx, int m, const float* x,
+                               float* __restrict__ fvec) {
+  if (MODEL == PITT_MODEL_SPHERE) {
+    const float x0 = x[0], x1 = x[1], x2 = x[2], x3 = x[3];
+    for (int i = threadIdx.x; i < m; i += LM_TPB) {
+      float4 p = __ldg(xyz + idx[i]);
+      float c0 = p.x - x0, c1 = p.y - x1, c2 = p.z - x2;
+      fvec[i] = sqrtf((c0 * c0 + c2 * c2) + c1 * c1) - x3;
+    }
+  } else if (MODEL == PITT_MODEL_CYLINDER) {
+    const f3 lp = mk3(x[0], x[1], x[2]), ld = mk3(x[3], x[4], x[5]);
+    const float rr = x[6] * x[6];
+    for (int i = threadIdx.x; i < m; i += LM_TPB) {
+      float4 p = __ldg(xyz + idx[i]);
+      fvec[i] = (float)((double)sqr_pt_line(mk3(p.x, p.y, p.z), lp, ld) - (double)rr);
+    }
+  } else {
+    const f3 apex = mk3(x[0], x[1], x[2]), ad = mk3(x[3], x[4], x[5]);
+    const float apexdotdir = dot0(apex, ad);
+    const float dirdotdir = 1.0f / dot0(ad, ad);
+    const float tan_a = tanf_d(x[6]);
+    for (int i = threadIdx.x; i < m; i += LM_TPB) {
+      float4 p4 = __ldg(xyz + idx[i]);
+      f3 pt = mk3(p4.x, p4.y, p4.z);
+      float k = (dot0(pt, ad) - apexdotdir) * dirdotdir;
+      f3 proj = apex + k * ad;
+      f3 height = apex - proj;
+      float r = tan_a * nrm0(height);
+      fvec[i] = (float)((double)sqr_pt_line(pt, apex, ad) - (double)(r * r));
+    }
+  }
+}
+
+__device__ __forceinline__ float norm_n(const float* a, int n) {
+  float s = 0.0f;
+  for (int i = 0; i < n; ++i) s += a[i] * a[i];
+  return sqrtf(s);
+}
+__device__ void make_givens(float p, float q, float& c, float& s) {
+  if (q == 0.0f) { c = p < 0.0f ? -1.0f : 1.0f; s = 0.0f; }
+  else if (p == 0.0f) { c = 0.0f; s = q < 0.0f ? 1.0f : -1.0f; }
+  else if (fabsf(p) > fabsf(q)) {
+    float t = q / p;
+    float u = sqrtf(1.0f + t * t);
+    if (p < 0.0f) u = -u;
+    c = 1.0f / u;
+    s = -t * c;
+  } else {
+    float t = p / q;
+    float u = sqrtf(1.0f + t * t);
+    if (q < 0.0f) u = -u;
+    s = -1.0f / u;
+    c = -t * s;
+  }
+}
+// Eigen internal::qrsolv (n x n, row i col j at s[i*8+j]); thread 0 only
+__device__ void qrsolv(float* s, int n, const int* ipvt, const float* diag, const float* qtb, float* x, float* sdiag) {
+  float wa[8];
+  for (int j = 0; j < n; ++j) { x[j] = s[j * 8 + j]; wa[j] = qtb[j]; }
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < i; ++j) s[i * 8 + j] = s[j * 8 + i];
+  for (int j = 0; j < n; ++j) {
+    int l = ipvt[j];
+    if (diag[l] == 0.0f) break;
+    for (int k = j; k < n; ++k) sdiag[k] = 0.0f;
+    sdiag[j] = diag[l];
+    float qtbpj = 0.0f;
+    for (int k = j; k < n; ++k) {
+      float gc, gs;
+      make_givens(-s[k * 8 + k], sdiag[k], gc, gs);
+      s[k * 8 + k] = gc * s[k * 8 + k] + gs * sdiag[k];
+      float temp = gc * wa[k] + gs * qtbpj;
+      qtbpj = -gs * wa[k] + gc * qtbpj;
+      wa[k] = temp;
+      for (int i = k + 1; i < n; ++i) {
+        temp = gc * s[i * 8 + k] + gs * sdiag[i];
+        sdiag[i] = -gs * s[i * 8 + k] + gc * sdiag[i];
+        s[i * 8 + k] = temp;
+      }
+    }
+  }
+  int nsing;
+  for (nsing = 0; nsing < n && sdiag[nsing] != 0.0f; nsing++) {}
+  for (int j = nsing; j < n; ++j) wa[j] = 0.0f;
+  for (int i = nsing - 1; i >= 0; --i) {
+    float acc = 0.0f;
+    for (int j = i + 1; j < nsing; ++j) acc += s[j * 8 + i] * wa[j];
+    wa[i] = (wa[i] - acc) / s[i * 8 + i];
+  }
+  for (int j = 0; j < n; ++j) { sdiag[j] = s[j * 8 + j]; s[j * 8 + j] = x[j]; }
+  for (int j = 0; j < n; ++j) x[ipvt[j]] = wa[j];
+}
+// Eigen internal::lmpar2; thread 0 only
+__device__ void lmpar2(const float* r, int n, const int* perm, int rank, const float* diag, const float* qtb, float delta,
+                       float& par, float* x) {
+  const float dwarf = FLT_MIN;
+  float wa1[8], wa2[8];
+  for (int j = 0; j < n; ++j) wa1[j] = qtb[j];
+  for (int j = rank; j < n; ++j) wa1[j] = 0.0f;
+  for (int i = rank - 1; i >= 0; --i) {
+    wa1[i] /= r[i * 8 + i];
+    for (int q = 0; q < i; ++q) wa1[q] -= wa1[i] * r[q * 8 + i];
+  }
+  for (int j = 0; j < n; ++j) x[perm[j]] = wa1[j];
+  int iter = 0;
+  for (int j = 0; j < n; ++j) wa2[j] = diag[j] * x[j];
+  float dxnorm = norm_n(wa2, n);
+  float fp = dxnorm - delta;
+  if (fp <= 0.1f * delta) { par = 0.0f; return; }
+  float parl = 0.0f;
+  if (rank == n) {
+    for (int j = 0; j < n; ++j) wa1[j] = diag[perm[j]] * wa2[perm[j]] / dxnorm;
+    for (int i = 0; i < n; ++i) {
+      float acc = 0.0f;
+      for (int j = 0; j < i; ++j) acc += r[j * 8 + i] * wa1[j];
+      wa1[i] = (wa1[i] - acc) / r[i * 8 + i];
+    }
+    float temp = norm_n(wa1, n);
+    parl = fp / delta / temp / temp;
+  }
+  for (int j = 0; j < n; ++j) {
+    float acc = 0.0f;
+    for (int i = 0; i <= j; ++i) acc += r[i * 8 + j] * qtb[i];
+    wa1[j] = acc / diag[perm[j]];
+  }
+  float gnorm = norm_n(wa1, n);
+  float paru = gnorm / delta;
+  if (paru == 0.0f) paru = dwarf / fminf(delta, 0.1f);
+  par = fmaxf(par, parl);
+  par = fminf(par, paru);
+  if (par == 0.0f) par = gnorm / dxnorm;
+  float s[64], sdiag[8];
+  for (int i = 0; i < 64; ++i) s[i] = r[i];
+  for (;;) {
+    ++iter;
+    if (par == 0.0f) par = fmaxf(dwarf, 0.001f * paru);
+    float sp = sqrtf(par);
+    for (int j = 0; j < n; ++j) wa1[j] = sp * diag[j];
+    qrsolv(s, n, perm, wa1, qtb, x, sdiag);
+    for (int j = 0; j < n; ++j) wa2[j] = diag[j] * x[j];
+    dxnorm = norm_n(wa2, n);
+    float temp = fp;
+    fp = dxnorm - delta;
+    if (fabsf(fp) <= 0.1f * delta || (parl == 0.0f && fp <= temp && temp < 0.0f) || iter == 10) break;
+    for (int j = 0; j < n; ++j) wa1[j] = diag[perm[j]] * (wa2[perm[j]] / dxnorm);
+    for (int j = 0; j < n; ++j) {
+      wa1[j] /= sdiag[j];
+      temp = wa1[j];
+      for (int i = j + 1; i < n; ++i) wa1[i] -= s[i * 8 + j] * temp;
+    }
+    temp = norm_n(wa1, n);
+    float parc = fp / delta / temp / temp;
+    if (fp > 0.0f) parl = fmaxf(parl, par);
+    if (fp < 0.0f) paru = fminf(paru, par);
+    par = fmaxf(parl, par + parc);
+  }
+  if (iter == 0) par = 0.0f;
+}
+
+// work layout (floats): fjac [n*m_cap] | fvec [m_cap] | wa4 [m_cap] | val2 [m_cap]
+template <int MODEL>
+__global__ void __launch_bounds__(LM_TPB)
+lm_kernel(const float4* __restrict__ xyz, const int* __restrict__ idx, const int* __restrict__ n_idx_ptr, int m_cap,
+          const float* __restrict__ model_in, float* __restrict__ work, float* __restrict__ refined, int* __restrict__ info_out) {
+  __shared__ LmShared S;
+  constexpr int n = (MODEL == PITT_MODEL_SPHERE) ? 4 : 7;
+  const int m = min(*n_idx_ptr, m_cap);
+  float* fjac = work;
+  float* fvec = work + (size_t)n * m_cap;
+  float* wa4 = fvec + m_cap;
+  float* val2 = wa4 + m_cap;
+  const float eps = 1.1920928955078125e-07f;
+  const float ftol = sqrtf(eps), xtol = sqrtf(eps), gtol = 0.0f, factor = 100.0f;
+  const int maxfev = 400;
+  if (threadIdx.x < 8) S.x[threadIdx.x] = model_in[threadIdx.x];
+  __syncthreads();
+  int status = -1, nfev = 0;
+  bool run = true;
+  if (MODEL == PITT_MODEL_SPHERE) { if (m <= 4) { run = false; status = 0; } }
+  else if (m == 0) { run = false; status = 0; }
+  bool minimized = run;
+  if (run && m < n) { run = false; status = 0; }  // ImproperInputParameters: x untouched
+  float fnorm = 0.f, par = 0.f, delta = 0.f, xnorm = 0.f;
+  int iter = 1;
+  if (run) {
+    nfev = 1;
+    eval_residuals<MODEL>(xyz, idx, m, S.x, fvec);
+    __syncthreads();
+    fnorm = sqrtf(block_dot(fvec, fvec, 0, m, S));
+  }
+  while (run && status == -1) {
+    // ---- NumericalDiff (forward): f(x) again, then one perturbed evaluation per parameter
+    const float h_eps = sqrtf(eps);
+    eval_residuals<MODEL>(xyz, idx, m, S.x, wa4);  // val1
+    nfev++;
+    __syncthreads();
+    for (int j = 0; j < n; ++j) {
+      if (threadIdx.x == 0) {
+        for (int q = 0; q < n; ++q) S.xs[q] = S.x[q];
+        float h = h_eps * fabsf(S.x[j]);
+        if (h == 0.0f) h = h_eps;
+        S.xs[j] += h;
+        S.bcast[1] = h;
+      }
+      __syncthreads();
+      const float h = S.bcast[1];
+      eval_residuals<MODEL>(xyz, idx, m, S.xs, val2);
+      nfev++;
+      __syncthreads();
+      float* cj = fjac + (size_t)j * m_cap;
+      for (int i = threadIdx.x; i < m; i += LM_TPB) cj[i] = (val2[i] - wa4[i]) / h;
+      __syncthreads();
+    }
+    // ---- column norms, ColPivHouseholderQR
+    for (int j = 0; j < n; ++j) {
+      float* cj = fjac + (size_t)j * m_cap;
+      float sq = block_dot(cj, cj, 0, m, S);
+      if (threadIdx.x == 0) { S.wa2[j] = sqrtf(sq); S.colSq[j] = sq; }
+    }
+    __syncthreads();
+    float threshold_helper, maxpivot = 0.0f;
+    int nonzero_pivots = n;
+    {
+      float mx = S.colSq[0];
+      for (int k = 1; k < n; ++k) mx = fmaxf(mx, S.colSq[k]);
+      threshold_helper = mx * (eps * eps) / (float)m;
+    }
+    for (int k = 0; k < n; ++k) {
+      int big = k;
+      for (int j = k + 1; j < n; ++j)
+        if (S.colSq[j] > S.colSq[big]) big = j;
+      float* cb = fjac + (size_t)big * m_cap;
+      float bigSq = block_dot(cb, cb, k, m, S);
+      if (threadIdx.x == 0) S.colSq[big] = bigSq;
+      __syncthreads();
+      if (bigSq < threshold_helper * (float)(m - k)) {
+        nonzero_pivots = k;
+        for (int j = k; j < n; ++j) {
+          if (threadIdx.x == 0) { S.hcoef[j] = 0.0f; S.transp[j] = j; }
+          float* cj = fjac + (size_t)j * m_cap;
+          for (int i = j + 1 + threadIdx.x; i < m; i += LM_TPB) cj[i] = 0.0f;
+        }
+        __syncthreads();
+        break;
+      }
+      if (threadIdx.x == 0) S.transp[k] = big;
+      float* ck = fjac + (size_t)k * m_cap;
+      if (k != big) {
+        for (int i = threadIdx.x; i < m; i += LM_TPB) { float t = ck[i]; ck[i] = cb[i]; cb[i] = t; }
+        if (threadIdx.x == 0) { float t = S.colSq[k]; S.colSq[k] = S.colSq[big]; S.colSq[big] = t; }
+        __syncthreads();
+      }
+      float tailSq = (m - k == 1) ? 0.0f : block_dot(ck, ck, k + 1, m, S);
+      float c0 = ck[k];
+      float tau, beta;
+      __syncthreads();  // everyone has read ck[k] before it is overwritten
+      if (tailSq == 0.0f) {
+        tau = 0.0f;
+        beta = c0;
+        for (int i = k + 1 + threadIdx.x; i < m; i += LM_TPB) ck[i] = 0.0f;
+      } else {
+        beta = sqrtf(c0 * c0 + tailSq);
+        if (c0 >= 0.0f) beta = -beta;
+        float den = c0 - beta;
+        for (int i = k + 1 + threadIdx.x; i < m; i += LM_TPB) ck[i] = ck[i] / den;
+        tau = (beta - c0) / beta;
+      }
+      if (threadIdx.x == 0) { S.hcoef[k] = tau; ck[k] = beta; }
+      if (fabsf(beta) > maxpivot) maxpivot = fabsf(beta);
+      __syncthreads();
+      for (int j = k + 1; j < n; ++j) {
+        float* cj = fjac + (size_t)j * m_cap;
+        if (m - k == 1) {
+          if (threadIdx.x == 0) cj[k] *= (1.0f - tau);
+        } else {
+          float tmp = block_dot(ck, cj, k + 1, m, S);
+          tmp += cj[k];
+          __syncthreads();
+          if (threadIdx.x == 0) cj[k] -= tau * tmp;
+          for (int i = k + 1 + threadIdx.x; i < m; i += LM_TPB) cj[i] -= tmp * (tau * ck[i]);
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0)
+        for (int j = k + 1; j < n; ++j) { float v = fjac[(size_t)j * m_cap + k]; S.colSq[j] -= v * v; }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      for (int j = 0; j < n; ++j) S.perm[j] = j;
+      for (int k = 0; k < nonzero_pivots; ++k) { int t = S.perm[k]; S.perm[k] = S.perm[S.transp[k]]; S.perm[S.transp[k]] = t; }
+      if (iter == 1) {
+        for (int j = 0; j < n; ++j) S.diag[j] = (S.wa2[j] == 0.0f) ? 1.0f : S.wa2[j];
+        float t[8];
+        for (int j = 0; j < n; ++j) t[j] = S.diag[j] * S.x[j];
+        S.bcast[2] = norm_n(t, n);
+      }
+    }
+    __syncthreads();
+    if (iter == 1) {
+      xnorm = S.bcast[2];
+      delta = factor * xnorm;
+      if (delta == 0.0f) delta = factor;
+    }
+    // ---- qtf = first n components of Q^T fvec
+    for (int i = threadIdx.x; i < m; i += LM_TPB) wa4[i] = fvec[i];
+    __syncthreads();
+    for (int k = 0; k < n; ++k) {
+      const float tau = S.hcoef[k];
+      const float* ck = fjac + (size_t)k * m_cap;
+      if (m - k == 1) {
+        if (threadIdx.x == 0) wa4[k] *= (1.0f - tau);
+      } else {
+        float tmp = block_dot(ck, wa4, k + 1, m, S);
+        tmp += wa4[k];
+        __syncthreads();
+        if (threadIdx.x == 0) wa4[k] -= tau * tmp;
+        for (int i = k + 1 + threadIdx.x; i < m; i += LM_TPB) wa4[i] -= tmp * (tau * ck[i]);
+      }
+      __syncthreads();
+    }
+    // ---- small algebra on thread 0
+    if (threadIdx.x == 0) {
+      for (int j = 0; j < n; ++j) S.qtf[j] = wa4[j];
+      for (int i = 0; i < 64; ++i) S.r[i] = 0.0f;
+      for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j) S.r[i * 8 + j] = fjac[(size_t)j * m_cap + i];
+      float gnorm = 0.0f;
+      if (fnorm != 0.0f)
+        for (int j = 0; j < n; ++j)
+          if (S.wa2[S.perm[j]] != 0.0f) {
+            float acc = 0.0f;
+            for (int i = 0; i <= j; ++i) acc += S.r[i * 8 + j] * (S.qtf[i] / fnorm);
+            gnorm = fmaxf(gnorm, fabsf(acc / S.wa2[S.perm[j]]));
+          }
+      S.bcast[3] = gnorm;
+      for (int j = 0; j < n; ++j) S.diag[j] = fmaxf(S.diag[j], S.wa2[j]);
+      int rank = 0;
+      float thr = fabsf(maxpivot) * (eps * (float)n);
+      for (int i = 0; i < nonzero_pivots; ++i) rank += (fabsf(S.r[i * 8 + i]) > thr) ? 1 : 0;
+      S.ibcast[0] = rank;
+    }
+    __syncthreads();
+    const float gnorm = S.bcast[3];
+    const int rank = S.ibcast[0];
+    if (gnorm <= gtol) { status = 4; break; }
+    float ratio = 0.0f;
+    do {
+      if (threadIdx.x == 0) {
+        float p = par;
+        lmpar2(S.r, n, S.perm, rank, S.diag, S.qtf, delta, p, S.wa1);
+        S.bcast[1] = p;
+        for (int j = 0; j < n; ++j) { S.wa1[j] = -S.wa1[j]; S.wa2[j] = S.x[j] + S.wa1[j]; }
+        float t[8];
+        for (int j = 0; j < n; ++j) t[j] = S.diag[j] * S.wa1[j];
+        S.bcast[2] = norm_n(t, n);
+        for (int i = 0; i < n; ++i) {
+          float acc = 0.0f;
+          for (int j = i; j < n; ++j) acc += S.r[i * 8 + j] * S.wa1[S.perm[j]];
+          S.wa3[i] = acc;
+        }
+      }
+      __syncthreads();
+      par = S.bcast[1];
+      const float pnorm = S.bcast[2];
+      if (iter == 1) delta = fminf(delta, pnorm);
+      eval_residuals<MODEL>(xyz, idx, m, S.wa2, wa4);
+      ++nfev;
+      __syncthreads();
+      const float fnorm1 = sqrtf(block_dot(wa4, wa4, 0, m, S));
+      float actred = -1.0f;
+      if (0.1f * fnorm1 < fnorm) { float q = fnorm1 / fnorm; actred = 1.0f - q * q; }
+      const float q1 = norm_n(S.wa3, n) / fnorm;
+      const float temp1 = q1 * q1;
+      const float q2 = sqrtf(par) * pnorm / fnorm;
+      const float temp2 = q2 * q2;
+      const float prered = temp1 + temp2 / 0.5f;
+      const float dirder = -(temp1 + temp2);
+      ratio = 0.0f;
+      if (prered != 0.0f) ratio = actred / prered;
+      if (ratio <= 0.25f) {
+        float temp = 0.0f;
+        if (actred >= 0.0f) temp = 0.5f;
+        if (actred < 0.0f) temp = 0.5f * dirder / (dirder + 0.5f * actred);
+        if (0.1f * fnorm1 >= fnorm || temp < 0.1f) temp = 0.1f;
+        delta = temp * fminf(delta, pnorm / 0.1f);
+        par /= temp;
+      } else if (!(par != 0.0f && ratio < 0.75f)) {
+        delta = pnorm / 0.5f;
+        par = 0.5f * par;
+      }
+      __syncthreads();  // all threads have read S.wa3 / S.wa2 / bcast before thread 0 rewrites them
+      if (ratio >= 1e-4f) {
+        if (threadIdx.x == 0) {
+          for (int j = 0; j < n; ++j) { S.x[j] = S.wa2[j]; S.wa2[j] = S.diag[j] * S.x[j]; }
+          S.bcast[2] = norm_n(S.wa2, n);
+        }
+        for (int i = threadIdx.x; i < m; i += LM_TPB) fvec[i] = wa4[i];
+        __syncthreads();
+        xnorm = S.bcast[2];
+        fnorm = fnorm1;
+        ++iter;
+      }
+      const bool small_red = fabsf(actred) <= ftol && prered <= ftol && 0.5f * ratio <= 1.0f;
+      if (small_red && delta <= xtol * xnorm) { status = 3; break; }
+      if (small_red) { status = 1; break; }
+      if (delta <= xtol * xnorm) { status = 2; break; }
+      if (nfev >= maxfev) { status = 5; break; }
+      if (fabsf(actred) <= eps && prered <= eps && 0.5f * ratio <= 1.0f) { status = 6; break; }
+      if (delta <= eps * xnorm) { status = 7; break; }
+      if (gnorm <= eps) { status = 8; break; }
+    } while (ratio < 1e-4f);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float out[8];
+    for (int i = 0; i < 8; ++i) out[i] = (i < n) ? S.x[i] : 0.0f;
+    if (MODEL != PITT_MODEL_SPHERE && minimized) {
+      float nn = sqrtf(out[3] * out[3] + out[4] * out[4] + out[5] * out[5]);
+      out[3] /= nn; out[4] /= nn; out[5] /= nn;
+    }
+    for (int i = 0; i < 8; ++i) refined[i] = out[i];
+    info_out[0] = status < 0 ? 0 : status;
+    info_out[1] = nfev;
+  }
+}
+
+int lm_refine(pitt_ctx* ctx, const pitt_cloud* c, int model, const float* d_model, const int* d_idx, const int* d_n_idx,
+              int n_idx_host, float* d_refined, int* d_lm_info) {
+  // m is only known on the device (d_n_idx); the workspace is sized for the worst case
+  const int m_cap = n_idx_host >= 0 ? std::max(n_idx_host, 1) : std::max(c->n, 1);
+  const int n = (model == PITT_MODEL_SPHERE) ? 4 : 7;
+  float* d_work = nullptr;
+  PITT_TRY(arena_alloc(ctx, (size_t)(n + 3) * m_cap, &d_work));
+  switch (model) {
+    case PITT_MODEL_SPHERE:
+      lm_kernel<PITT_MODEL_SPHERE><<<1, LM_TPB, 0, ctx->stream>>>(c->d_xyz, d_idx, d_n_idx, m_cap, d_model, d_work, d_refined, d_lm_info);
+      break;
+    case PITT_MODEL_CYLINDER:
+      lm_kernel<PITT_MODEL_CYLINDER><<<1, LM_TPB, 0, ctx->stream>>>(c->d_xyz, d_idx, d_n_idx, m_cap, d_model, d_work, d_refined, d_lm_info);
+      break;
+    case PITT_MODEL_CONE:
+      lm_kernel<PITT_MODEL_CONE><<<1, LM_TPB, 0, ctx->stream>>>(c->d_xyz, d_idx, d_n_idx, m_cap, d_model, d_work, d_refined, d_lm_info);
+      break;
+    default:
+      return fail(ctx, PITT_ERR_INVALID, "lm_refine: model has no LM refinement");
+  }
   ctx->launches++;
+  PITT_CUDA(ctx, cudaGetLastError());
   return PITT_OK;
 }
+
 }  // namespace pitt

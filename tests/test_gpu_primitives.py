@@ -1,0 +1,97 @@
+"""GPU parity: sphere / cylinder / cone RANSAC (sphere_segmentation_srv.cpp:58-73, cylinder…:111-126,
+cone…:112-127) incl. Levenberg-Marquardt refinement, through the C ABI vs the CPU oracle."""
+import numpy as np
+import pytest
+
+import pitt_object_table_segmentation_b200 as pkg
+from pitt_object_table_segmentation_b200 import _abi as A, scenes
+
+pytestmark = pytest.mark.gpu
+
+KINDS = {A.MODEL_PLANE: "plane", A.MODEL_SPHERE: "sphere", A.MODEL_CYLINDER: "cylinder", A.MODEL_CONE: "cone"}
+
+
+def _cluster(kind, n, seed, oracle):
+    xyz, truth = scenes.primitive_cluster(kind, n, seed)
+    nrm = oracle.estimate_normals(xyz, 50, (0.0, 0.0, 0.0))
+    return xyz, nrm, truth
+
+
+@pytest.mark.parametrize("model", [A.MODEL_SPHERE, A.MODEL_CYLINDER, A.MODEL_CONE])
+def test_score_counts_bit_exact(ctx, oracle, model):
+    xyz, nrm, _ = _cluster(KINDS[model], 6000, 100 + model, oracle)
+    cloud = ctx.stage(xyz, normals=nrm)
+    p = pkg.default_sac_params(model)
+    samples = oracle.pcl_sample_stream(xyz, model, 400)
+    c_gpu, co_gpu, v_gpu = ctx.sac_score(cloud, p, samples)
+    c_cpu, co_cpu, v_cpu = oracle.sac_score(xyz, nrm, p, samples)
+    assert np.array_equal(v_gpu, v_cpu)
+    assert np.array_equal(co_gpu.view(np.uint32), co_cpu.view(np.uint32))
+    assert np.array_equal(c_gpu, c_cpu)
+    assert c_gpu.max() > 1000  # the right model is among the hypotheses
+
+
+@pytest.mark.parametrize("model", [A.MODEL_CYLINDER, A.MODEL_CONE])
+def test_fast_path_equals_exact_path_on_wrong_shapes(ctx, oracle, model):
+    # scoring a cylinder on a cone cloud (and vice versa) puts many points near the threshold
+    other = "cone" if model == A.MODEL_CYLINDER else "cylinder"
+    xyz, nrm, _ = _cluster(other, 5000, 7, oracle)
+    cloud = ctx.stage(xyz, normals=nrm)
+    p = pkg.default_sac_params(model)
+    p.normal_distance_weight = 0.1  # widen the FP32 band
+    samples = oracle.pcl_sample_stream(xyz, model, 300)
+    c_gpu, _, _ = ctx.sac_score(cloud, p, samples)
+    c_cpu, _, _ = oracle.sac_score(xyz, nrm, p, samples)
+    assert np.array_equal(c_gpu, c_cpu)
+
+
+@pytest.mark.parametrize("model", [A.MODEL_SPHERE, A.MODEL_CYLINDER, A.MODEL_CONE])
+def test_lm_refine_bit_exact(ctx, oracle, model):
+    xyz, nrm, _ = _cluster(KINDS[model], 4000, 200 + model, oracle)
+    cloud = ctx.stage(xyz, normals=nrm)
+    p = pkg.default_sac_params(model)
+    p.optimize = 0
+    base = oracle.sac_segment(xyz, nrm, p)
+    assert len(base["inliers"]) > 500
+    ref_c, info_c = oracle.sac_refine(xyz, nrm, p, base["coeffs"], base["inliers"])
+    ref_g, info_g = ctx.sac_refine(cloud, p, base["coeffs"], base["inliers"])
+    assert (info_g.lm_info, info_g.lm_nfev) == (info_c.lm_info, info_c.lm_nfev)
+    assert np.array_equal(ref_g.view(np.uint32), ref_c.view(np.uint32)), (ref_g, ref_c)
+
+
+@pytest.mark.parametrize("model,n,seed", [(A.MODEL_SPHERE, 5000, 1), (A.MODEL_CYLINDER, 5000, 2), (A.MODEL_CONE, 5000, 3),
+                                          (A.MODEL_CYLINDER, 20000, 4), (A.MODEL_CONE, 12000, 5), (A.MODEL_SPHERE, 800, 6)])
+def test_segment_bit_exact(ctx, oracle, model, n, seed):
+    xyz, nrm, _ = _cluster(KINDS[model], n, seed, oracle)
+    cloud = ctx.stage(xyz, normals=nrm)
+    p = pkg.default_sac_params(model)
+    got = ctx.sac_segment(cloud, p)
+    want = oracle.sac_segment(xyz, nrm, p)
+    gi, wi = got["info"], want["info"]
+    assert (gi.iterations, gi.skipped, gi.best_hypothesis, gi.best_count, gi.n_inliers_model) == \
+           (wi.iterations, wi.skipped, wi.best_hypothesis, wi.best_count, wi.n_inliers_model)
+    assert (gi.lm_info, gi.lm_nfev) == (wi.lm_info, wi.lm_nfev)
+    # north star: coefficients within 1e-5 relative, inlier sets bit-exact; we get both bit-exact
+    np.testing.assert_allclose(got["coeffs"], want["coeffs"], rtol=1e-5, atol=1e-7)
+    assert np.array_equal(got["coeffs"].view(np.uint32), want["coeffs"].view(np.uint32))
+    assert np.array_equal(got["inliers"], want["inliers"])
+
+
+def test_wrong_model_on_each_shape(ctx, oracle):
+    # every model on every shape (what ransac_segmentation.cpp does per cluster)
+    for kind in ("sphere", "cylinder", "cone", "plane"):
+        xyz, nrm, _ = _cluster(kind, 3000, 77, oracle)
+        cloud = ctx.stage(xyz, normals=nrm)
+        for model in (A.MODEL_PLANE, A.MODEL_SPHERE, A.MODEL_CYLINDER, A.MODEL_CONE):
+            p = pkg.default_sac_params(model)
+            got = ctx.sac_segment(cloud, p)
+            want = oracle.sac_segment(xyz, nrm, p)
+            assert np.array_equal(got["inliers"], want["inliers"]), (kind, model)
+            assert np.array_equal(got["coeffs"].view(np.uint32), want["coeffs"].view(np.uint32)), (kind, model)
+
+
+def test_cylinder_needs_normals(ctx):
+    xyz, _ = scenes.primitive_cluster("cylinder", 500, 1)
+    cloud = ctx.stage(xyz)
+    with pytest.raises(pkg.PittError):
+        ctx.sac_segment(cloud, pkg.default_sac_params(A.MODEL_CYLINDER))

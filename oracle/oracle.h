@@ -42,6 +42,7 @@ int orc_find_supports(const float* xyz4, const float* nrm4, int n, const pitt_su
 int orc_cluster_service(const float* xyz4, int n, const pitt_cluster_params* params, pitt_clusters_result* result);
 int orc_primitive_service(const float* xyz4, const float* nrm4, int n, const pitt_sac_params* params,
                           pitt_primitive_result* result);
+int orc_select_primitive(int64_t plane_inl, int64_t sphere_inl, int64_t cylinder_inl, int64_t cone_inl, float prio);
 int orc_segment_frame(const float* xyz4, int n, const pitt_frame_params* params, pitt_frame_result* result);
 
 /* defaults shared with the product header semantics (reference launch parameters) */

@@ -161,3 +161,78 @@ def euclidean_clusters(xyz4, tolerance, min_size, max_size):
                                       C.byref(nc))
     assert st == 0, st
     return labels, nc.value
+
+
+# ---------------------------------------------------------------- service-shaped entry points
+from pitt_object_table_segmentation_b200 import _results as R  # noqa: E402
+
+
+def default_support_params():
+    p = A.SupportParams()
+    p.min_iterative_cloud_percentual_size = -1.0
+    p.min_iterative_plane_percentual_size = -1.0
+    p.variance_threshold_for_horizontal = -1.0
+    p.ransac_distance_point_in_shape_threshold = -1.0
+    p.ransac_model_normal_distance_weigth = -1.0
+    p.ransac_max_iteration_threshold = -1
+    p.horizontal_axis_len = 1
+    p.support_edge_remove_offset_len = 1
+    p.normals_k = 50
+    return p
+
+
+def default_cluster_params():
+    p = A.ClusterParams()
+    p.tolerance, p.min_rate, p.max_rate, p.min_input_size = 0.03, 0.01, 0.99, 30
+    return p
+
+
+def default_frame_params():
+    p = A.FrameParams()
+    p.support = default_support_params()
+    p.cluster = default_cluster_params()
+    p.plane = default_sac_params(A.MODEL_PLANE)
+    p.sphere = default_sac_params(A.MODEL_SPHERE)
+    p.cylinder = default_sac_params(A.MODEL_CYLINDER)
+    p.cone = default_sac_params(A.MODEL_CONE)
+    p.normals_k, p.min_points, p.cone_over_cylinder_priority = 50, 30, 0.9
+    return p
+
+
+def find_supports(xyz4, nrm4, params, supports_cap=4):
+    xyz4 = _f4(xyz4)
+    nrm4 = _f4(nrm4) if nrm4 is not None else None
+    b = R.SupportBuffers(xyz4.shape[0], supports_cap)
+    st = lib().orc_find_supports(_fp(xyz4), _fp(nrm4), xyz4.shape[0], C.byref(params), C.byref(b.res))
+    assert st == 0, st
+    return b.to_python()
+
+
+def cluster_service(xyz4, params):
+    xyz4 = _f4(xyz4)
+    b = R.ClusterBuffers(xyz4.shape[0])
+    st = lib().orc_cluster_service(_fp(xyz4), xyz4.shape[0], C.byref(params), C.byref(b.res))
+    assert st == 0, st
+    return b.to_python()
+
+
+def primitive_service(xyz4, nrm4, params):
+    xyz4 = _f4(xyz4)
+    nrm4 = _f4(nrm4) if nrm4 is not None else None
+    b = R.PrimitiveBuffers(xyz4.shape[0])
+    st = lib().orc_primitive_service(_fp(xyz4), _fp(nrm4), xyz4.shape[0], C.byref(params), C.byref(b.res))
+    assert st == 0, st
+    return b.to_python()
+
+
+def select_primitive(plane, sphere, cylinder, cone, prio=0.9):
+    return int(lib().orc_select_primitive(C.c_int64(plane), C.c_int64(sphere), C.c_int64(cylinder), C.c_int64(cone),
+                                          C.c_float(prio)))
+
+
+def segment_frame(xyz4, params, shapes_cap=64):
+    xyz4 = _f4(xyz4)
+    b = R.FrameBuffers(shapes_cap)
+    st = lib().orc_segment_frame(_fp(xyz4), xyz4.shape[0], C.byref(params), C.byref(b.res))
+    assert st == 0, st
+    return b.to_python()

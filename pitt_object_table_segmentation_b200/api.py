@@ -312,3 +312,44 @@ class Context:
         t = C.c_double(0)
         self._check(self.lib.pitt_fp32_peak(self.handle, int(kind), C.byref(t)))
         return t.value
+
+
+# ---------------------------------------------------------------- service-shaped entry points
+from . import _results as R  # noqa: E402
+
+
+def _find_supports(self, cloud, params=None, supports_cap=4):
+    """findSupports (supports_segmentation_srv.cpp:241-361) on a staged cloud."""
+    params = params if params is not None else default_support_params()
+    b = R.SupportBuffers(cloud.n, supports_cap)
+    self._check(self.lib.pitt_find_supports(self.handle, cloud.handle, C.byref(params), C.byref(b.res)))
+    return b.to_python()
+
+
+def _cluster_service(self, cloud, params=None):
+    """clusterize (cluster_segmentation_srv.cpp:38-108)."""
+    params = params if params is not None else default_cluster_params()
+    b = R.ClusterBuffers(cloud.n)
+    self._check(self.lib.pitt_cluster_service(self.handle, cloud.handle, C.byref(params), C.byref(b.res)))
+    return b.to_python()
+
+
+def _primitive_service(self, cloud, params):
+    """ransac{Plane,Sphere,Cylinder,Cone}Detection (…_segmentation_srv.cpp)."""
+    b = R.PrimitiveBuffers(cloud.n)
+    self._check(self.lib.pitt_primitive_service(self.handle, cloud.handle, C.byref(params), C.byref(b.res)))
+    return b.to_python()
+
+
+def _segment_frame(self, cloud, params=None, shapes_cap=64):
+    """depthAcquisition + clustersAcquisition from the world-frame cloud on."""
+    params = params if params is not None else default_frame_params()
+    b = R.FrameBuffers(shapes_cap)
+    self._check(self.lib.pitt_segment_frame(self.handle, cloud.handle, C.byref(params), C.byref(b.res)))
+    return b.to_python()
+
+
+Context.find_supports = _find_supports
+Context.cluster_service = _cluster_service
+Context.primitive_service = _primitive_service
+Context.segment_frame = _segment_frame

@@ -2,6 +2,8 @@
 #include <cfloat>
 #include <cmath>
 
+#include <math_constants.h>
+
 #include "grid.cuh"
 
 namespace pitt {
@@ -84,75 +86,104 @@ __global__ void __launch_bounds__(256) cell_scatter_kernel(const float4* __restr
   sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
 }
 
-// ---- multi-block exclusive scan (3 phases)
+// ---- multi-block exclusive scan (3 phases), generic in the value type and the associative op
 constexpr int SCAN_TPB = 256, SCAN_IPT = 8, SCAN_CHUNK = SCAN_TPB * SCAN_IPT;
-__global__ void __launch_bounds__(SCAN_TPB) scan_local_kernel(int* __restrict__ data, int n, int* __restrict__ block_sums) {
-  __shared__ int s_w[SCAN_TPB / 32];
+struct OpSumI {
+  typedef int T;
+  __device__ static int identity() { return 0; }
+  __device__ static int apply(int a, int b) { return a + b; }
+};
+struct OpMaxF {
+  typedef float T;
+  __device__ static float identity() { return -CUDART_INF_F; }
+  __device__ static float apply(float a, float b) { return fmaxf(a, b); }
+};
+template <typename Op>
+__device__ __forceinline__ typename Op::T warp_incl_scan(typename Op::T v) {
+  for (int o = 1; o < 32; o <<= 1) {
+    typename Op::T y = __shfl_up_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) >= o) v = Op::apply(y, v);
+  }
+  return v;
+}
+template <typename Op>
+__global__ void __launch_bounds__(SCAN_TPB) scan_local_kernel(typename Op::T* __restrict__ data, int n,
+                                                              typename Op::T* __restrict__ block_sums) {
+  typedef typename Op::T T;
+  __shared__ T s_w[SCAN_TPB / 32];
   const int base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_IPT;
-  int v[SCAN_IPT], sum = 0;
+  T v[SCAN_IPT], sum = Op::identity();
 #pragma unroll
   for (int j = 0; j < SCAN_IPT; ++j) {
-    v[j] = (base + j < n) ? data[base + j] : 0;
-    sum += v[j];
+    v[j] = (base + j < n) ? data[base + j] : Op::identity();
+    sum = Op::apply(sum, v[j]);
   }
-  int incl = sum;
-  for (int o = 1; o < 32; o <<= 1) {
-    int y = __shfl_up_sync(0xffffffffu, incl, o);
-    if ((threadIdx.x & 31) >= o) incl += y;
-  }
+  T incl = warp_incl_scan<Op>(sum);
   if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
   __syncthreads();
-  int woff = 0;
-  for (int w = 0; w < (threadIdx.x >> 5); ++w) woff += s_w[w];
-  int run = woff + incl - sum;
+  T run = Op::identity();
+  for (int w = 0; w < (threadIdx.x >> 5); ++w) run = Op::apply(run, s_w[w]);
+  // exclusive prefix of this thread = warps before + lanes before
+  T lane_excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  if ((threadIdx.x & 31) != 0) run = Op::apply(run, lane_excl);
 #pragma unroll
   for (int j = 0; j < SCAN_IPT; ++j) {
     if (base + j < n) data[base + j] = run;
-    run += v[j];
+    run = Op::apply(run, v[j]);
   }
   if (threadIdx.x == SCAN_TPB - 1) block_sums[blockIdx.x] = run;
 }
-__global__ void scan_sums_kernel(int* __restrict__ v, int nb, int* __restrict__ total) {
+template <typename Op>
+__global__ void scan_sums_kernel(typename Op::T* __restrict__ v, int nb, typename Op::T* __restrict__ total) {
   // single block, any nb: serial over chunks of blockDim
-  __shared__ int s_carry;
-  __shared__ int s_w[32];
-  if (threadIdx.x == 0) s_carry = 0;
+  typedef typename Op::T T;
+  __shared__ T s_carry;
+  __shared__ T s_w[32];
+  if (threadIdx.x == 0) s_carry = Op::identity();
   __syncthreads();
   for (int base = 0; base < nb; base += blockDim.x) {
     int i = base + threadIdx.x;
-    int x = (i < nb) ? v[i] : 0;
-    int incl = x;
-    for (int o = 1; o < 32; o <<= 1) {
-      int y = __shfl_up_sync(0xffffffffu, incl, o);
-      if ((threadIdx.x & 31) >= o) incl += y;
-    }
+    T x = (i < nb) ? v[i] : Op::identity();
+    T incl = warp_incl_scan<Op>(x);
     if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
     __syncthreads();
-    if (threadIdx.x < 32) {
-      int nw = blockDim.x >> 5;
-      int wv = (threadIdx.x < nw) ? s_w[threadIdx.x] : 0;
-      int wi = wv;
-      for (int o = 1; o < 32; o <<= 1) {
-        int y = __shfl_up_sync(0xffffffffu, wi, o);
-        if (threadIdx.x >= o) wi += y;
-      }
-      s_w[threadIdx.x] = wi - wv;
-    }
-    __syncthreads();
-    int excl = s_carry + s_w[threadIdx.x >> 5] + incl - x;
+    T excl = s_carry;
+    for (int w = 0; w < (threadIdx.x >> 5); ++w) excl = Op::apply(excl, s_w[w]);
+    T lane_excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if ((threadIdx.x & 31) != 0) excl = Op::apply(excl, lane_excl);
     if (i < nb) v[i] = excl;
     __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) s_carry = excl + x;
+    if (threadIdx.x == blockDim.x - 1) s_carry = Op::apply(excl, x);
     __syncthreads();
   }
   if (threadIdx.x == 0 && total) *total = s_carry;
 }
-__global__ void __launch_bounds__(SCAN_TPB) scan_add_kernel(int* __restrict__ data, int n, const int* __restrict__ block_offs) {
-  const int off = block_offs[blockIdx.x];
+template <typename Op>
+__global__ void __launch_bounds__(SCAN_TPB) scan_add_kernel(typename Op::T* __restrict__ data, int n,
+                                                            const typename Op::T* __restrict__ block_offs) {
+  const typename Op::T off = block_offs[blockIdx.x];
   const int base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_IPT;
 #pragma unroll
   for (int j = 0; j < SCAN_IPT; ++j)
-    if (base + j < n) data[base + j] += off;
+    if (base + j < n) data[base + j] = Op::apply(off, data[base + j]);
+}
+
+template <typename Op>
+static int device_scan_impl(pitt_ctx* ctx, typename Op::T* d_data, int n, typename Op::T* d_total) {
+  typedef typename Op::T T;
+  if (n <= 0) return PITT_OK;
+  const int nb = cdiv(n, SCAN_CHUNK);
+  T* d_sums = nullptr;
+  PITT_TRY(arena_alloc(ctx, (size_t)nb + 1, &d_sums));
+  scan_local_kernel<Op><<<nb, SCAN_TPB, 0, ctx->stream>>>(d_data, n, d_sums);
+  scan_sums_kernel<Op><<<1, 1024, 0, ctx->stream>>>(d_sums, nb, d_total);
+  if (nb > 1) {
+    scan_add_kernel<Op><<<nb, SCAN_TPB, 0, ctx->stream>>>(d_data, n, d_sums);
+    ctx->launches++;
+  }
+  ctx->launches += 2;
+  PITT_CUDA(ctx, cudaGetLastError());
+  return PITT_OK;
 }
 
 int device_exclusive_scan(pitt_ctx* ctx, int* d_data, int n, int* d_total) {
@@ -160,19 +191,10 @@ int device_exclusive_scan(pitt_ctx* ctx, int* d_data, int n, int* d_total) {
     if (d_total) PITT_CUDA(ctx, cudaMemsetAsync(d_total, 0, sizeof(int), ctx->stream));
     return PITT_OK;
   }
-  const int nb = cdiv(n, SCAN_CHUNK);
-  int* d_sums = nullptr;
-  PITT_TRY(arena_alloc(ctx, (size_t)nb + 1, &d_sums));
-  scan_local_kernel<<<nb, SCAN_TPB, 0, ctx->stream>>>(d_data, n, d_sums);
-  scan_sums_kernel<<<1, 1024, 0, ctx->stream>>>(d_sums, nb, d_total);
-  if (nb > 1) {
-    scan_add_kernel<<<nb, SCAN_TPB, 0, ctx->stream>>>(d_data, n, d_sums);
-    ctx->launches++;
-  }
-  ctx->launches += 2;
-  PITT_CUDA(ctx, cudaGetLastError());
-  return PITT_OK;
+  return device_scan_impl<OpSumI>(ctx, d_data, n, d_total);
 }
+// exclusive prefix maximum of n floats in place (first element becomes -inf)
+int device_exclusive_max_scan(pitt_ctx* ctx, float* d_data, int n) { return device_scan_impl<OpMaxF>(ctx, d_data, n, nullptr); }
 
 static void make_geom(const float mn[3], const float mx[3], float h, GridGeom* g, int* ncells) {
   // keep the dense table bounded: enlarge h until it fits 2^24 cells

@@ -34,5 +34,7 @@ int grid_build(pitt_ctx* ctx, const float4* d_xyz, int n, float h, float target_
 
 // exclusive scan of n ints (device, in place), total written to d_total[0] (may be null)
 int device_exclusive_scan(pitt_ctx* ctx, int* d_data, int n, int* d_total);
+// exclusive prefix maximum of n floats in place (element 0 becomes -inf)
+int device_exclusive_max_scan(pitt_ctx* ctx, float* d_data, int n);
 
 }  // namespace pitt

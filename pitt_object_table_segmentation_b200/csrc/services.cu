@@ -1,0 +1,812 @@
+// services.cu — the service-shaped entry points: findSupports, clusterize, ransac*Detection,
+// the primitive selection rule and the per-frame orchestration, all on device-resident clouds.
+//
+// Reference (paths under /root/reference/src):
+//   findSupports        segmentation_services/supports_segmentation_srv.cpp:241-361 (+ :114-238 helpers)
+//   clusterize          segmentation_services/cluster_segmentation_srv.cpp:38-108
+//   ransac*Detection    segmentation_services/{plane,sphere,cylinder,cone}_segmentation_srv.cpp
+//   inlierToVectorMsg   point_cloud_library/pc_manager.cpp:105-111
+//   clustersAcquisition ransac_segmentation.cpp:223-343; depthAcquisition obj_segmentation.cpp:251-316
+// The O(N*M) linear searches and the O(n^2) axis-extent loop of the reference become flag lookups,
+// prefix scans and a tiled all-pairs kernel; observable quirks are kept.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <vector>
+
+#include "cluster.cuh"
+#include "grid.cuh"
+#include "pitt_common.cuh"
+#include "sac.cuh"
+
+namespace pitt {
+
+// ------------------------------------------------------------------ small kernels
+__global__ void iota_kernel(int* p, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
+__global__ void set_flags_kernel(const int* __restrict__ idx, const int* __restrict__ n_idx, int* __restrict__ flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < *n_idx) flag[idx[i]] = 1;
+}
+__global__ void gather_points_kernel(const float4* __restrict__ src, const int* __restrict__ idx, int m, float4* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) dst[i] = src[idx[i]];
+}
+// keep[i] = 1 - flag[i] (in place scan input)
+__global__ void invert_flags_kernel(const int* __restrict__ flag, int n, int* __restrict__ keep) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keep[i] = flag[i] ? 0 : 1;
+}
+__global__ void scatter_rest_kernel(const float4* __restrict__ src, const int* __restrict__ flag, const int* __restrict__ pos,
+                                    int n, float4* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && !flag[i]) dst[pos[i]] = src[i];
+}
+// createNewIdxMap (supports…:139-157), pass 1: classify. cat: 0 propagate, 1 level, 2 running counter
+__global__ void idxmap_classify_kernel(const int* __restrict__ prev, int n0, const int* __restrict__ flag, int n_flag,
+                                       int level, int* __restrict__ is_else) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n0) return;
+  int v = prev[p];
+  int e;
+  if (v > level && v < 0) e = 0;
+  else if (v >= 0 && v < n_flag && flag[v]) e = 0;
+  else e = 1;
+  is_else[p] = e;
+}
+__global__ void idxmap_write_kernel(const int* __restrict__ prev, int n0, const int* __restrict__ flag, int n_flag, int level,
+                                    const int* __restrict__ else_pos, int* __restrict__ out) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n0) return;
+  int v = prev[p];
+  if (v > level && v < 0) out[p] = v;
+  else if (v >= 0 && v < n_flag && flag[v]) out[p] = level;
+  else out[p] = else_pos[p];
+}
+// getPointOnPlane (supports…:187-238) bounding box with the order dependent if / else-if scan:
+// max = plain maximum; min = minimum over the points that did NOT raise the running maximum.
+__global__ void copy_axis_kernel(const float4* __restrict__ pts, int m, int axis, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) out[i] = axis == 0 ? pts[i].x : pts[i].y;
+}
+// out[0..3] = xmax, xmin(masked), ...; deterministic single block reduction, doubles for z
+__global__ void __launch_bounds__(1024)
+bbox_quirk_kernel(const float4* __restrict__ pts, int m, const float* __restrict__ pmax_x, const float* __restrict__ pmax_y,
+                  double* __restrict__ out /*xMax,xMin,yMax,yMin,zSum*/) {
+  __shared__ double s[5][32];
+  double xMax = -INFINITY, xMin = INFINITY, yMax = -INFINITY, yMin = INFINITY, zs = 0.0;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    float4 p = pts[i];
+    if (p.x > pmax_x[i]) xMax = fmax(xMax, (double)p.x);  // raised the running maximum
+    else if ((double)p.x < xMin) xMin = (double)p.x;
+    if (p.y > pmax_y[i]) yMax = fmax(yMax, (double)p.y);
+    else if ((double)p.y < yMin) yMin = (double)p.y;
+    zs += (double)p.z;
+  }
+  double v[5] = {xMax, xMin, yMax, yMin, zs};
+  for (int o = 16; o > 0; o >>= 1) {
+    v[0] = fmax(v[0], __shfl_down_sync(0xffffffffu, v[0], o));
+    v[1] = fmin(v[1], __shfl_down_sync(0xffffffffu, v[1], o));
+    v[2] = fmax(v[2], __shfl_down_sync(0xffffffffu, v[2], o));
+    v[3] = fmin(v[3], __shfl_down_sync(0xffffffffu, v[3], o));
+    v[4] += __shfl_down_sync(0xffffffffu, v[4], o);
+  }
+  if ((threadIdx.x & 31) == 0)
+    for (int k = 0; k < 5; ++k) s[k][threadIdx.x >> 5] = v[k];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r[5] = {-INFINITY, INFINITY, -INFINITY, INFINITY, 0.0};
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      r[0] = fmax(r[0], s[0][w]); r[1] = fmin(r[1], s[1][w]);
+      r[2] = fmax(r[2], s[2][w]); r[3] = fmin(r[3], s[3][w]);
+      r[4] += s[4][w];
+    }
+    for (int k = 0; k < 5; ++k) out[k] = r[k];
+  }
+}
+__global__ void on_plane_flag_kernel(const float4* __restrict__ orig, const int* __restrict__ map, int n0, int level,
+                                     double xMin, double xMax, double yMin, double yMax, double zMed, int* __restrict__ keep) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n0) return;
+  float4 p = orig[i];
+  bool k = (map[i] != level) && ((double)p.x > xMin && (double)p.x < xMax && (double)p.z > zMed && (double)p.y > yMin && (double)p.y < yMax);
+  keep[i] = k ? 1 : 0;
+}
+__global__ void compact_points_kernel(const float4* __restrict__ src, const int* __restrict__ keep, const int* __restrict__ pos,
+                                      int n, float4* __restrict__ dst, int* __restrict__ dst_idx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && keep[i]) {
+    dst[pos[i]] = src[i];
+    if (dst_idx) dst_idx[pos[i]] = i;
+  }
+}
+
+// per-cluster centroid sums: one block per cluster, fixed-shape double tree (deterministic)
+__global__ void __launch_bounds__(256)
+cluster_centroid_kernel(const float4* __restrict__ pts, const int* __restrict__ idx, const int* __restrict__ offsets,
+                        float* __restrict__ out /*[c][3] sums rounded to float*/) {
+  __shared__ double s[3][8];
+  const int c = blockIdx.x;
+  const int b = offsets[c], e = offsets[c + 1];
+  double sx = 0, sy = 0, sz = 0;
+  for (int i = b + threadIdx.x; i < e; i += blockDim.x) {
+    float4 p = pts[idx[i]];
+    sx += (double)p.x; sy += (double)p.y; sz += (double)p.z;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    sx += __shfl_down_sync(0xffffffffu, sx, o);
+    sy += __shfl_down_sync(0xffffffffu, sy, o);
+    sz += __shfl_down_sync(0xffffffffu, sz, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s[0][threadIdx.x >> 5] = sx; s[1][threadIdx.x >> 5] = sy; s[2][threadIdx.x >> 5] = sz; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[3] = {0, 0, 0};
+    for (int w = 0; w < 8; ++w) { t[0] += s[0][w]; t[1] += s[1][w]; t[2] += s[2][w]; }
+    out[3 * c] = (float)t[0]; out[3 * c + 1] = (float)t[1]; out[3 * c + 2] = (float)t[2];
+  }
+}
+
+// ------------------------------------------------------------------ K11: axis extent (cylinder…:143-171, cone…:143-171)
+struct AxisFrame {
+  float a1x, a1y, a1z, dx, dy, dz, gdiv;  // A1, A1A2, |A1A2|^2 exactly as the reference computes them
+};
+__global__ void axis_project_kernel(const float4* __restrict__ pts, int n, AxisFrame f, float4* __restrict__ proj) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = pts[i];
+  float ax = p.x - f.a1x, ay = p.y - f.a1y, az = p.z - f.a1z;
+  float G = (ax * f.dx + ay * f.dy + az * f.dz) / f.gdiv;
+  proj[i] = make_float4(f.a1x + G * f.dx, f.a1y + G * f.dy, f.a1z + G * f.dz, 0.0f);
+}
+// all pairs (i > j): maximum of the float distances, first pair in (i, j) lexicographic order on ties
+constexpr int AP_TPB = 256;
+struct PairBest {
+  float d;
+  int i, j;
+};
+__device__ __forceinline__ bool pair_better(float d, int i, int j, const PairBest& b) {
+  return d > b.d || (d == b.d && b.i >= 0 && (i < b.i || (i == b.i && j < b.j)));
+}
+__global__ void __launch_bounds__(AP_TPB)
+axis_pairs_kernel(const float4* __restrict__ proj, int n, PairBest* __restrict__ block_best) {
+  __shared__ float4 s_j[AP_TPB];
+  __shared__ PairBest s_red[AP_TPB / 32];
+  const int i = blockIdx.x * AP_TPB + threadIdx.x;
+  const int jt = blockIdx.y;  // j tile
+  PairBest best{-1.0f, -1, -1};
+  if (jt * AP_TPB < (blockIdx.x + 1) * AP_TPB) {  // tile contains some j < max i of this block
+    const int j0 = jt * AP_TPB;
+    s_j[threadIdx.x] = (j0 + threadIdx.x < n) ? proj[j0 + threadIdx.x] : make_float4(0, 0, 0, 0);
+    __syncthreads();
+    if (i < n) {
+      const float4 pi = proj[i];
+      const int jend = min(min(AP_TPB, n - j0), i - j0);  // j < i
+      for (int t = 0; t < jend; ++t) {
+        const float4 pj = s_j[t];
+        const float ddx = pi.x - pj.x, ddy = pi.y - pj.y, ddz = pi.z - pj.z;
+        const float d = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
+        if (d > best.d) { best.d = d; best.i = i; best.j = j0 + t; }  // ascending j: first max kept
+      }
+    }
+  }
+  // block reduction (ties -> lexicographically smallest (i, j))
+  for (int o = 16; o > 0; o >>= 1) {
+    PairBest ob;
+    ob.d = __shfl_down_sync(0xffffffffu, best.d, o);
+    ob.i = __shfl_down_sync(0xffffffffu, best.i, o);
+    ob.j = __shfl_down_sync(0xffffffffu, best.j, o);
+    if (ob.i >= 0 && (best.i < 0 || pair_better(ob.d, ob.i, ob.j, best))) best = ob;
+  }
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    PairBest b = s_red[0];
+    for (int w = 1; w < AP_TPB / 32; ++w) {
+      PairBest ob = s_red[w];
+      if (ob.i >= 0 && (b.i < 0 || pair_better(ob.d, ob.i, ob.j, b))) b = ob;
+    }
+    block_best[blockIdx.y * gridDim.x + blockIdx.x] = b;
+  }
+}
+__global__ void __launch_bounds__(1024) axis_pairs_final_kernel(const PairBest* __restrict__ bb, int nb, const float4* __restrict__ proj,
+                                                                float* __restrict__ out /*height, idx1, idx2 (as float bits), p1 xyz, p2 xyz*/) {
+  __shared__ PairBest s_red[32];
+  PairBest best{-1.0f, -1, -1};
+  for (int t = threadIdx.x; t < nb; t += blockDim.x) {
+    PairBest ob = bb[t];
+    if (ob.i >= 0 && (best.i < 0 || pair_better(ob.d, ob.i, ob.j, best))) best = ob;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    PairBest ob;
+    ob.d = __shfl_down_sync(0xffffffffu, best.d, o);
+    ob.i = __shfl_down_sync(0xffffffffu, best.i, o);
+    ob.j = __shfl_down_sync(0xffffffffu, best.j, o);
+    if (ob.i >= 0 && (best.i < 0 || pair_better(ob.d, ob.i, ob.j, best))) best = ob;
+  }
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    PairBest b = s_red[0];
+    for (int w = 1; w < 32; ++w) {
+      PairBest ob = s_red[w];
+      if (ob.i >= 0 && (b.i < 0 || pair_better(ob.d, ob.i, ob.j, b))) b = ob;
+    }
+    out[0] = b.d;
+    out[1] = __int_as_float(b.i);
+    out[2] = __int_as_float(b.j);
+    if (b.i >= 0) {
+      float4 p1 = proj[b.i], p2 = proj[b.j];
+      out[3] = p1.x; out[4] = p1.y; out[5] = p1.z; out[6] = p2.x; out[7] = p2.y; out[8] = p2.z;
+    }
+  }
+}
+
+struct AxisExtent {
+  float height;
+  int idx1, idx2;
+  float p1[3], p2[3];
+  float dirn[3];
+};
+static int axis_extent(pitt_ctx* ctx, const float4* d_pts, int n, const float* co, AxisExtent* out) {
+  // getNormalizeAxesDirectionVector / getPointOnAxes / getVectorBetweenPoints in float, as the reference
+  float norm = sqrtf(co[3] * co[3] + co[4] * co[4] + co[5] * co[5]);
+  out->dirn[0] = co[3] / norm; out->dirn[1] = co[4] / norm; out->dirn[2] = co[5] / norm;
+  const float t1 = -1.0f, t2 = +1.0f;
+  float A1[3] = {co[0] + out->dirn[0] * t1, co[1] + out->dirn[1] * t1, co[2] + out->dirn[2] * t1};
+  float A2[3] = {co[0] + out->dirn[0] * t2, co[1] + out->dirn[1] * t2, co[2] + out->dirn[2] * t2};
+  AxisFrame f;
+  f.a1x = A1[0]; f.a1y = A1[1]; f.a1z = A1[2];
+  f.dx = A2[0] - A1[0]; f.dy = A2[1] - A1[1]; f.dz = A2[2] - A1[2];
+  f.gdiv = f.dx * f.dx + f.dy * f.dy + f.dz * f.dz;
+  out->height = -1.0f;
+  out->idx1 = out->idx2 = -1;
+  if (n <= 0) return PITT_OK;
+  float4* d_proj = nullptr;
+  PITT_TRY(arena_alloc(ctx, (size_t)n, &d_proj));
+  axis_project_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_pts, n, f, d_proj);
+  const int nt = cdiv(n, AP_TPB);
+  PairBest* d_bb = nullptr;
+  float* d_out = nullptr;
+  PITT_TRY(arena_alloc(ctx, (size_t)nt * nt, &d_bb));
+  PITT_TRY(arena_alloc(ctx, 16, &d_out));
+  axis_pairs_kernel<<<dim3(nt, nt), AP_TPB, 0, ctx->stream>>>(d_proj, n, d_bb);
+  axis_pairs_final_kernel<<<1, 1024, 0, ctx->stream>>>(d_bb, nt * nt, d_proj, d_out);
+  ctx->launches += 3;
+  float h[9];
+  PITT_CUDA(ctx, cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  out->height = h[0];
+  memcpy(&out->idx1, &h[1], 4);
+  memcpy(&out->idx2, &h[2], 4);
+  for (int k = 0; k < 3; ++k) { out->p1[k] = h[3 + k]; out->p2[k] = h[6 + k]; }
+  return PITT_OK;
+}
+
+// ------------------------------------------------------------------ supports
+struct SupportCfg {
+  float minCloudPct, minPlanePct, maxVar, minVar, thr, w;
+  int maxIter;
+  float axis[3], offset[3];
+};
+static SupportCfg resolve_support(const pitt_support_params& p) {
+  SupportCfg c;
+  // srvm::getServiceFloatParameter / IntParameter / 3DArrayParameter (srv_manager.h:163-188)
+  c.minCloudPct = p.min_iterative_cloud_percentual_size >= 0.0f ? p.min_iterative_cloud_percentual_size : 0.030f;
+  c.minPlanePct = p.min_iterative_plane_percentual_size >= 0.0f ? p.min_iterative_plane_percentual_size : 0.030f;
+  c.maxVar = p.variance_threshold_for_horizontal >= 0.0f ? p.variance_threshold_for_horizontal : 0.09f;
+  c.minVar = -1 * c.maxVar;
+  c.thr = p.ransac_distance_point_in_shape_threshold >= 0.0f ? p.ransac_distance_point_in_shape_threshold : 0.02f;
+  c.w = p.ransac_model_normal_distance_weigth >= 0.0f ? p.ransac_model_normal_distance_weigth : 0.9f;
+  c.maxIter = p.ransac_max_iteration_threshold >= 0 ? p.ransac_max_iteration_threshold : 10;
+  const float defAxis[3] = {0.0f, 0.0f, -1.0f};
+  const float defOff[3] = {0.02f, 0.02f, 0.005f};
+  for (int i = 0; i < 3; ++i) {
+    c.axis[i] = p.horizontal_axis_len == 3 ? p.horizontal_axis[i] : defAxis[i];
+    c.offset[i] = p.support_edge_remove_offset_len == 3 ? p.support_edge_remove_offset[i] : defOff[i];
+  }
+  return c;
+}
+static bool is_horizontal_plane(const float* co, const SupportCfg& c) {  // supports…:161-179
+  float div = sqrtf(co[0] * co[0] + co[1] * co[1] + co[2] * co[2]);
+  float nx = co[0] / div, ny = co[1] / div, nz = co[2] / div;
+  float crossX = ny * c.axis[2] - nz * c.axis[1];
+  float crossY = nz * c.axis[0] - nx * c.axis[2];
+  float crossZ = nx * c.axis[1] - ny * c.axis[0];
+  return ((crossX > c.minVar) && (crossX < c.maxVar)) && ((crossY > c.minVar) && (crossY < c.maxVar)) &&
+         ((crossZ > c.minVar) && (crossZ < c.maxVar));
+}
+
+struct SupportDev {
+  float co[4];
+  int n_support, n_on;
+  const int* d_map;          // N0 labels
+  const float4* d_support;   // support cloud
+  const float4* d_on;        // on-support cloud (points of the original cloud, original order)
+};
+
+static int find_supports_impl(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_support_params& params, SupportCfg* cfg_out,
+                              std::vector<SupportDev>* out, int* loop_trips) {
+  const SupportCfg c = resolve_support(params);
+  if (cfg_out) *cfg_out = c;
+  out->clear();
+  *loop_trips = 0;
+  const int n0 = cloud->n;
+  if (n0 <= 0) return PITT_OK;
+  pitt_sac_params sp;
+  pitt_default_support_sac_params(&sp);
+  sp.distance_threshold = (double)c.thr;
+  sp.normal_distance_weight = (double)c.w;
+  sp.max_iterations = c.maxIter;
+
+  pitt_cloud iter;  // non-owning view of the shrinking cloud
+  iter.n = n0;
+  iter.d_xyz = cloud->d_xyz;
+  iter.h_valid = false;
+  const int* d_prev_map = nullptr;  // nullptr = identity (first trip)
+  int idxMapLayer = -2, cnt = 0;
+  const int k = params.normals_k > 0 ? params.normals_k : 50;
+  for (;;) {
+    const int ni = iter.n;
+    SacDeviceResult r;
+    PITT_TRY(sac_segment_impl(ctx, &iter, sp, &r));
+    (*loop_trips)++;
+    const int n_inl = r.n_inliers;
+    if (n_inl == 0) break;
+    else if ((float)ni < (float)n0 * c.minCloudPct) break;
+    else if ((float)n_inl < (float)n0 * c.minPlanePct) break;
+    // removePlaneInliner: positive -> support cloud (gather, inliers are ascending), negative in place
+    int* d_flag = nullptr;
+    int* d_keep = nullptr;
+    int* d_n = nullptr;
+    float4* d_support = nullptr;
+    float4* d_rest = nullptr;
+    PITT_TRY(arena_alloc(ctx, (size_t)ni, &d_flag));
+    PITT_TRY(arena_alloc(ctx, (size_t)ni, &d_keep));
+    PITT_TRY(arena_alloc(ctx, 1, &d_n));
+    PITT_TRY(arena_alloc(ctx, (size_t)n_inl, &d_support));
+    PITT_TRY(arena_alloc(ctx, (size_t)std::max(ni - n_inl, 1), &d_rest));
+    PITT_CUDA(ctx, cudaMemsetAsync(d_flag, 0, (size_t)ni * sizeof(int), ctx->stream));
+    PITT_CUDA(ctx, cudaMemcpyAsync(d_n, &r.n_inliers, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    set_flags_kernel<<<cdiv(n_inl, 256), 256, 0, ctx->stream>>>(r.d_inliers, d_n, d_flag);
+    gather_points_kernel<<<cdiv(n_inl, 256), 256, 0, ctx->stream>>>(iter.d_xyz, r.d_inliers, n_inl, d_support);
+    invert_flags_kernel<<<cdiv(ni, 256), 256, 0, ctx->stream>>>(d_flag, ni, d_keep);
+    ctx->launches += 3;
+    PITT_TRY(device_exclusive_scan(ctx, d_keep, ni, nullptr));
+    scatter_rest_kernel<<<cdiv(ni, 256), 256, 0, ctx->stream>>>(iter.d_xyz, d_flag, d_keep, ni, d_rest);
+    ctx->launches++;
+    if (params.compute_discarded_normals) {
+      // supports…:297,300 — results are never used by the reference; offered for cost fidelity only
+      const float vp[3] = {0.f, 0.f, 0.f};
+      float4* d_scratch = nullptr;
+      PITT_TRY(arena_alloc(ctx, (size_t)std::max(ni, 1), &d_scratch));
+      PITT_TRY(estimate_normals_impl(ctx, d_rest, ni - n_inl, k, vp, d_scratch));
+      PITT_TRY(estimate_normals_impl(ctx, d_support, n_inl, k, vp, d_scratch));
+    }
+    const bool horizontal = is_horizontal_plane(r.coeffs, c);
+    const int level = horizontal ? idxMapLayer : -1;
+    // createNewIdxMap
+    int* d_prev = nullptr;
+    if (!d_prev_map) {
+      PITT_TRY(arena_alloc(ctx, (size_t)n0, &d_prev));
+      iota_kernel<<<cdiv(n0, 256), 256, 0, ctx->stream>>>(d_prev, n0);
+      ctx->launches++;
+      d_prev_map = d_prev;
+    }
+    int* d_else = nullptr;
+    int* d_new = nullptr;
+    PITT_TRY(arena_alloc(ctx, (size_t)n0, &d_else));
+    PITT_TRY(arena_alloc(ctx, (size_t)n0, &d_new));
+    idxmap_classify_kernel<<<cdiv(n0, 256), 256, 0, ctx->stream>>>(d_prev_map, n0, d_flag, ni, level, d_else);
+    ctx->launches++;
+    PITT_TRY(device_exclusive_scan(ctx, d_else, n0, nullptr));
+    idxmap_write_kernel<<<cdiv(n0, 256), 256, 0, ctx->stream>>>(d_prev_map, n0, d_flag, ni, level, d_else, d_new);
+    ctx->launches++;
+    if (horizontal) {
+      // getPointOnPlane
+      float* d_px = nullptr;
+      float* d_py = nullptr;
+      double* d_bb = nullptr;
+      PITT_TRY(arena_alloc(ctx, (size_t)n_inl, &d_px));
+      PITT_TRY(arena_alloc(ctx, (size_t)n_inl, &d_py));
+      PITT_TRY(arena_alloc(ctx, 8, &d_bb));
+      copy_axis_kernel<<<cdiv(n_inl, 256), 256, 0, ctx->stream>>>(d_support, n_inl, 0, d_px);
+      copy_axis_kernel<<<cdiv(n_inl, 256), 256, 0, ctx->stream>>>(d_support, n_inl, 1, d_py);
+      ctx->launches += 2;
+      PITT_TRY(device_exclusive_max_scan(ctx, d_px, n_inl));
+      PITT_TRY(device_exclusive_max_scan(ctx, d_py, n_inl));
+      bbox_quirk_kernel<<<1, 1024, 0, ctx->stream>>>(d_support, n_inl, d_px, d_py, d_bb);
+      ctx->launches++;
+      double bb[5];
+      PITT_CUDA(ctx, cudaMemcpyAsync(bb, d_bb, sizeof(bb), cudaMemcpyDeviceToHost, ctx->stream));
+      PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      double xMax = bb[0], xMin = bb[1], yMax = bb[2], yMin = bb[3], zMed = bb[4];
+      xMax -= c.offset[0];
+      xMin += c.offset[0];
+      yMax -= c.offset[1];
+      yMin += c.offset[1];
+      zMed = zMed / n_inl + c.offset[2];
+      int* d_onkeep = nullptr;
+      int* d_ontotal = nullptr;
+      PITT_TRY(arena_alloc(ctx, (size_t)n0 + 1, &d_onkeep));
+      PITT_TRY(arena_alloc(ctx, 1, &d_ontotal));
+      int* d_onflag = nullptr;
+      PITT_TRY(arena_alloc(ctx, (size_t)n0, &d_onflag));
+      on_plane_flag_kernel<<<cdiv(n0, 256), 256, 0, ctx->stream>>>(cloud->d_xyz, d_new, n0, level, xMin, xMax, yMin, yMax, zMed, d_onflag);
+      ctx->launches++;
+      PITT_CUDA(ctx, cudaMemcpyAsync(d_onkeep, d_onflag, (size_t)n0 * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+      PITT_TRY(device_exclusive_scan(ctx, d_onkeep, n0, d_ontotal));
+      int n_on = 0;
+      PITT_CUDA(ctx, cudaMemcpyAsync(&n_on, d_ontotal, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      float4* d_on = nullptr;
+      PITT_TRY(arena_alloc(ctx, (size_t)std::max(n_on, 1), &d_on));
+      compact_points_kernel<<<cdiv(n0, 256), 256, 0, ctx->stream>>>(cloud->d_xyz, d_onflag, d_onkeep, n0, d_on, nullptr);
+      ctx->launches++;
+      SupportDev S;
+      for (int i = 0; i < 4; ++i) S.co[i] = r.coeffs[i];
+      S.n_support = n_inl;
+      S.n_on = n_on;
+      S.d_map = d_new;
+      S.d_support = d_support;
+      S.d_on = d_on;
+      out->push_back(S);
+    }
+    d_prev_map = d_new;
+    iter.d_xyz = d_rest;
+    iter.n = ni - n_inl;
+    iter.h_valid = false;
+    iter.h_xyz.clear();
+    cnt++;
+    idxMapLayer--;
+    if (iter.n <= 0) {
+      // the reference would call RANSAC on an empty cloud, get no inliers and stop
+      (*loop_trips)++;
+      break;
+    }
+  }
+  (void)cnt;
+  PITT_CUDA(ctx, cudaGetLastError());
+  return PITT_OK;
+}
+
+// ------------------------------------------------------------------ clusters
+struct ClustersDev {
+  std::vector<int> sizes;     // per cluster (PCL order)
+  std::vector<int> offsets;   // sizes.size()+1
+  std::vector<int> indices;   // host copy, ascending per cluster
+  std::vector<float> centroid;// 3 per cluster (sum/(n+1))
+  const float4* d_points = nullptr;  // cluster clouds, contiguous in `offsets` order (device)
+};
+static int cluster_service_impl(pitt_ctx* ctx, const float4* d_xyz, int n, const pitt_cluster_params& p, ClustersDev* out) {
+  out->sizes.clear();
+  out->offsets.assign(1, 0);
+  out->indices.clear();
+  out->centroid.clear();
+  out->d_points = nullptr;
+  if (!(n >= p.min_input_size) || n <= 0) return PITT_OK;
+  const int min_sz = (int)round((double)n * p.min_rate);
+  const int max_sz = (int)round((double)n * p.max_rate);
+  int* d_labels = nullptr;
+  PITT_TRY(arena_alloc(ctx, (size_t)n, &d_labels));
+  std::vector<int> sizes;
+  PITT_TRY(euclidean_clusters_impl(ctx, d_xyz, n, p.tolerance, min_sz, max_sz, d_labels, &sizes));
+  const int nc = (int)sizes.size();
+  if (nc == 0) return PITT_OK;
+  std::vector<int> labels(n);
+  PITT_CUDA(ctx, cudaMemcpyAsync(labels.data(), d_labels, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  out->sizes = sizes;
+  out->offsets.resize(nc + 1);
+  out->offsets[0] = 0;
+  for (int c = 0; c < nc; ++c) out->offsets[c + 1] = out->offsets[c] + sizes[c];
+  const int total = out->offsets[nc];
+  out->indices.resize(total);
+  std::vector<int> cur(out->offsets.begin(), out->offsets.end() - 1);
+  for (int i = 0; i < n; ++i)
+    if (labels[i] >= 0) out->indices[cur[labels[i]]++] = i;  // ascending within each cluster
+  int* d_idx = nullptr;
+  int* d_off = nullptr;
+  float4* d_pts = nullptr;
+  float* d_cen = nullptr;
+  PITT_TRY(arena_alloc(ctx, (size_t)total, &d_idx));
+  PITT_TRY(arena_alloc(ctx, (size_t)nc + 1, &d_off));
+  PITT_TRY(arena_alloc(ctx, (size_t)total, &d_pts));
+  PITT_TRY(arena_alloc(ctx, (size_t)nc * 3, &d_cen));
+  PITT_CUDA(ctx, cudaMemcpyAsync(d_idx, out->indices.data(), (size_t)total * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  PITT_CUDA(ctx, cudaMemcpyAsync(d_off, out->offsets.data(), (size_t)(nc + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  gather_points_kernel<<<cdiv(total, 256), 256, 0, ctx->stream>>>(d_xyz, d_idx, total, d_pts);
+  cluster_centroid_kernel<<<nc, 256, 0, ctx->stream>>>(d_xyz, d_idx, d_off, d_cen);
+  ctx->launches += 2;
+  std::vector<float> sums((size_t)nc * 3);
+  PITT_CUDA(ctx, cudaMemcpyAsync(sums.data(), d_cen, sums.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  out->centroid.resize((size_t)nc * 3);
+  for (int c = 0; c < nc; ++c) {
+    int cntp1 = 1 + sizes[c];  // `int cnt = 1; ... cnt++` (cluster…:78,91)
+    for (int a = 0; a < 3; ++a) out->centroid[3 * c + a] = sums[3 * c + a] / cntp1;
+  }
+  out->d_points = d_pts;
+  return PITT_OK;
+}
+
+// ------------------------------------------------------------------ primitives
+struct PrimitiveHost {
+  SacDeviceResult sac;
+  int n_coefficients;
+  float coefficients[8];
+  float centroid[3];
+  int centroid_valid;
+};
+static int primitive_service_impl(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& p, PrimitiveHost* out) {
+  PITT_TRY(sac_segment_impl(ctx, c, p, &out->sac));
+  const SacDeviceResult& r = out->sac;
+  out->n_coefficients = r.n_coeffs;
+  for (int i = 0; i < 8; ++i) out->coefficients[i] = i < r.n_coeffs ? r.coeffs[i] : 0.0f;
+  out->centroid[0] = out->centroid[1] = out->centroid[2] = 0.0f;
+  out->centroid_valid = 0;
+  if (p.model == PITT_MODEL_SPHERE) {
+    if (r.n_coeffs > 0) {
+      for (int a = 0; a < 3; ++a) out->centroid[a] = r.coeffs[a];
+      out->centroid_valid = 1;
+    }
+  } else if (p.model == PITT_MODEL_CYLINDER || p.model == PITT_MODEL_CONE) {
+    float height = -1.0f;
+    if (r.n_inliers > 0) {
+      AxisExtent ax;
+      PITT_TRY(axis_extent(ctx, c->d_xyz, c->n, r.coeffs, &ax));
+      height = ax.height;
+      if (p.model == PITT_MODEL_CYLINDER) {
+        if (ax.idx1 >= 0) {
+          for (int a = 0; a < 3; ++a) out->centroid[a] = (ax.p1[a] + ax.p2[a]) / 2;
+          out->centroid_valid = 1;
+        }
+      } else {
+        for (int a = 0; a < 3; ++a) out->centroid[a] = r.coeffs[a] + 3.0f / 4.0f * height * ax.dirn[a];
+        out->centroid_valid = 1;
+      }
+    }
+    out->coefficients[r.n_coeffs] = height;  // coefficientVector.push_back(height)
+    out->n_coefficients = r.n_coeffs + 1;
+  }
+  return PITT_OK;
+}
+
+static int select_primitive_rule(int64_t planeInl, int64_t sphereInl, int64_t cylinderInl, int64_t coneInl, float prio) {
+  if ((!planeInl) && (!sphereInl) && (!cylinderInl) && (!coneInl)) return PITT_TAG_UNKNOWN;
+  if ((coneInl >= planeInl) && (coneInl >= sphereInl) && ((float)(uint64_t)coneInl >= (float)(uint64_t)cylinderInl * prio))
+    return PITT_TAG_CONE;
+  if ((cylinderInl >= planeInl) && (cylinderInl >= coneInl) && (cylinderInl >= sphereInl)) return PITT_TAG_CYLINDER;
+  if ((planeInl >= coneInl) && (planeInl >= sphereInl) && (planeInl >= cylinderInl)) return PITT_TAG_PLANE;
+  if ((sphereInl >= planeInl) && (sphereInl >= coneInl) && (sphereInl >= cylinderInl)) return PITT_TAG_SPHERE;
+  return PITT_TAG_UNKNOWN;
+}
+
+// number of inliers after inlierToVectorMsg: index VALUE 0 is dropped (pc_manager.cpp:108). The
+// ascending list starts with 0 iff point 0 is an inlier.
+static int count_after_zero_drop(pitt_ctx* ctx, const SacDeviceResult& r, int* out) {
+  *out = r.n_inliers;
+  if (r.n_inliers > 0) {
+    int first = -1;
+    PITT_CUDA(ctx, cudaMemcpyAsync(&first, r.d_inliers, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (first == 0) *out = r.n_inliers - 1;
+  }
+  return PITT_OK;
+}
+
+}  // namespace pitt
+
+using namespace pitt;
+
+extern "C" {
+
+int pitt_find_supports(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_support_params* params, pitt_support_result* res) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!cloud || !params || !res) return fail(ctx, PITT_ERR_INVALID, "pitt_find_supports arguments");
+  cudaSetDevice(ctx->device);
+  CallTimer timer(ctx);
+  std::vector<SupportDev> sup;
+  SupportCfg c;
+  int trips = 0;
+  PITT_TRY(find_supports_impl(ctx, cloud, *params, &c, &sup, &trips));
+  res->n_supports = 0;
+  res->loop_trips = trips;
+  res->maps_used = 0;
+  res->points_used = 0;
+  res->used_min_iterative_cloud_percentual_size = c.minCloudPct;
+  res->used_min_iterative_plane_percentual_size = c.minPlanePct;
+  res->used_max_variance_threshold_for_horizontal = c.maxVar;
+  res->used_min_variance_threshold_for_horizontal = c.minVar;
+  res->used_ransac_max_iteration_threshold = c.maxIter;
+  res->used_ransac_distance_point_in_shape_threshold = c.thr;
+  res->used_ransac_model_normal_distance_weigth = c.w;
+  for (int i = 0; i < 3; ++i) {
+    res->used_horizontal_axis[i] = c.axis[i];
+    res->used_support_edge_remove_offset[i] = c.offset[i];
+  }
+  const int n0 = cloud->n;
+  int status = PITT_OK;
+  for (size_t s = 0; s < sup.size(); ++s) {
+    const SupportDev& S = sup[s];
+    const int64_t need_pts = (int64_t)S.n_support + S.n_on;
+    if ((int)s < res->supports_cap && res->supports && res->maps && res->points && res->maps_used + n0 <= res->maps_cap &&
+        res->points_used + need_pts <= res->points_cap) {
+      pitt_support& O = res->supports[s];
+      O.n_map = n0;
+      O.n_support = S.n_support;
+      O.n_on_support = S.n_on;
+      O.a = S.co[0]; O.b = S.co[1]; O.c = S.co[2]; O.d = S.co[3];
+      O.map_offset = res->maps_used;
+      O.support_offset = res->points_used;
+      O.on_support_offset = res->points_used + S.n_support;
+      PITT_CUDA(ctx, cudaMemcpyAsync(res->maps + res->maps_used, S.d_map, (size_t)n0 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      PITT_CUDA(ctx, cudaMemcpyAsync(res->points + 4 * res->points_used, S.d_support, (size_t)S.n_support * 16, cudaMemcpyDeviceToHost, ctx->stream));
+      if (S.n_on > 0)
+        PITT_CUDA(ctx, cudaMemcpyAsync(res->points + 4 * (res->points_used + S.n_support), S.d_on, (size_t)S.n_on * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    } else {
+      status = PITT_ERR_CAPACITY;
+    }
+    res->maps_used += n0;
+    res->points_used += need_pts;
+    res->n_supports++;
+  }
+  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  timer.finish();
+  if (status == PITT_ERR_CAPACITY) return fail(ctx, status, "support result buffers too small (see maps_used / points_used)");
+  return status;
+}
+
+int pitt_cluster_service(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_cluster_params* params, pitt_clusters_result* res) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!cloud || !params || !res) return fail(ctx, PITT_ERR_INVALID, "pitt_cluster_service arguments");
+  cudaSetDevice(ctx->device);
+  CallTimer timer(ctx);
+  ClustersDev cd;
+  PITT_TRY(cluster_service_impl(ctx, cloud->d_xyz, cloud->n, *params, &cd));
+  res->n_clusters = 0;
+  res->indices_used = 0;
+  int status = PITT_OK;
+  for (size_t c = 0; c < cd.sizes.size(); ++c) {
+    const int sz = cd.sizes[c];
+    if ((int)c < res->clusters_cap && res->clusters && res->indices && res->indices_used + sz <= res->indices_cap) {
+      pitt_cluster& C = res->clusters[c];
+      C.n = sz;
+      C.offset = res->indices_used;
+      C.x_centroid = cd.centroid[3 * c]; C.y_centroid = cd.centroid[3 * c + 1]; C.z_centroid = cd.centroid[3 * c + 2];
+      memcpy(res->indices + res->indices_used, cd.indices.data() + cd.offsets[c], (size_t)sz * sizeof(int));
+    } else {
+      status = PITT_ERR_CAPACITY;
+    }
+    res->indices_used += sz;
+    res->n_clusters++;
+  }
+  timer.finish();
+  if (status == PITT_ERR_CAPACITY) return fail(ctx, status, "cluster result buffers too small");
+  return status;
+}
+
+int pitt_primitive_service(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_sac_params* params, pitt_primitive_result* res) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!cloud || !params || !res) return fail(ctx, PITT_ERR_INVALID, "pitt_primitive_service arguments");
+  cudaSetDevice(ctx->device);
+  CallTimer timer(ctx);
+  PrimitiveHost ph;
+  PITT_TRY(primitive_service_impl(ctx, cloud, *params, &ph));
+  res->n_coefficients = ph.n_coefficients;
+  for (int i = 0; i < 8; ++i) res->coefficients[i] = ph.coefficients[i];
+  res->x_centroid = ph.centroid[0]; res->y_centroid = ph.centroid[1]; res->z_centroid = ph.centroid[2];
+  res->centroid_valid = ph.centroid_valid;
+  res->info = ph.sac.info;
+  // PCManager::inlierToVectorMsg: drop index value 0
+  const int n_inl = ph.sac.n_inliers;
+  int status = PITT_OK;
+  res->n_inliers = 0;
+  if (n_inl > 0) {
+    std::vector<int> h(n_inl);
+    PITT_CUDA(ctx, cudaMemcpyAsync(h.data(), ph.sac.d_inliers, (size_t)n_inl * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int m = 0;
+    for (int i = 0; i < n_inl; ++i) {
+      if (h[i] == 0) continue;
+      if (res->inliers && m < res->inliers_cap) res->inliers[m] = h[i];
+      else if (res->inliers) status = PITT_ERR_CAPACITY;
+      ++m;
+    }
+    res->n_inliers = m;
+  }
+  timer.finish();
+  res->info.device_ms = ctx->last_ms;
+  if (status == PITT_ERR_CAPACITY) return fail(ctx, status, "primitive inlier buffer too small");
+  return status;
+}
+
+int pitt_select_primitive(int64_t plane_inl, int64_t sphere_inl, int64_t cylinder_inl, int64_t cone_inl, float prio) {
+  return select_primitive_rule(plane_inl, sphere_inl, cylinder_inl, cone_inl, prio);
+}
+
+int pitt_segment_frame(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_frame_params* fp, pitt_frame_result* res) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!cloud || !fp || !res) return fail(ctx, PITT_ERR_INVALID, "pitt_segment_frame arguments");
+  cudaSetDevice(ctx->device);
+  CallTimer timer(ctx);
+  res->n_supports = res->n_clusters = res->n_shapes = 0;
+  memset(res->support_coefficients, 0, sizeof(res->support_coefficients));
+  memset(res->support_sizes, 0, sizeof(res->support_sizes));
+  memset(res->on_support_sizes, 0, sizeof(res->on_support_sizes));
+  res->device_ms = 0.0;
+  const int n = cloud->n;
+  int status = PITT_OK;
+  if (n > fp->min_points) {  // obj_segmentation.cpp:251
+    // obj_segmentation.cpp:253 estimates the frame normals and ships them with the request; the
+    // supports service never uses them (plane RANSAC ignores normals). They are still
+    // computed here because they are part of the reference's request (and of its cost).
+    float4* d_nrm = nullptr;
+    PITT_TRY(arena_alloc(ctx, (size_t)n, &d_nrm));
+    PITT_TRY(estimate_normals_impl(ctx, cloud->d_xyz, n, fp->normals_k, fp->viewpoint, d_nrm));
+    std::vector<SupportDev> sup;
+    int trips = 0;
+    PITT_TRY(find_supports_impl(ctx, cloud, fp->support, nullptr, &sup, &trips));
+    res->n_supports = (int)sup.size();
+    for (size_t s = 0; s < sup.size(); ++s) {
+      const SupportDev& S = sup[s];
+      if (s < 8) {
+        for (int i = 0; i < 4; ++i) res->support_coefficients[4 * s + i] = S.co[i];
+        res->support_sizes[s] = S.n_support;
+        res->on_support_sizes[s] = S.n_on;
+      }
+      ClustersDev cd;
+      PITT_TRY(cluster_service_impl(ctx, S.d_on, S.n_on, fp->cluster, &cd));
+      for (size_t c = 0; c < cd.sizes.size(); ++c) {
+        pitt_cloud cc;  // non-owning view of the cluster cloud
+        cc.n = cd.sizes[c];
+        cc.d_xyz = const_cast<float4*>(cd.d_points) + cd.offsets[c];
+        float4* d_cn = nullptr;
+        PITT_TRY(arena_alloc(ctx, (size_t)cc.n, &d_cn));
+        PITT_TRY(estimate_normals_impl(ctx, cc.d_xyz, cc.n, fp->normals_k, fp->viewpoint, d_cn));
+        cc.d_nrm = d_cn;
+        cc.has_normals = true;
+        const pitt_sac_params* sp[4] = {&fp->sphere, &fp->cylinder, &fp->cone, &fp->plane};
+        PrimitiveHost ph[4];
+        int inl[4];
+        for (int m = 0; m < 4; ++m) {
+          PITT_TRY(primitive_service_impl(ctx, &cc, *sp[m], &ph[m]));
+          PITT_TRY(count_after_zero_drop(ctx, ph[m].sac, &inl[m]));
+        }
+        const int64_t sphereInl = inl[0], cylinderInl = inl[1], coneInl = inl[2], planeInl = inl[3];
+        const int tag = select_primitive_rule(planeInl, sphereInl, cylinderInl, coneInl, fp->cone_over_cylinder_priority);
+        if (res->shapes && res->n_shapes < res->shapes_cap) {
+          pitt_tracked_shape& T = res->shapes[res->n_shapes];
+          memset(&T, 0, sizeof(T));
+          T.object_id = res->n_clusters;
+          T.shape_tag = tag;
+          T.x_pc_centroid = cd.centroid[3 * c]; T.y_pc_centroid = cd.centroid[3 * c + 1]; T.z_pc_centroid = cd.centroid[3 * c + 2];
+          const PrimitiveHost* sel = tag == PITT_TAG_CONE ? &ph[2] : tag == PITT_TAG_CYLINDER ? &ph[1]
+                                     : tag == PITT_TAG_PLANE ? &ph[3] : tag == PITT_TAG_SPHERE ? &ph[0] : nullptr;
+          if (sel) {
+            T.x_est_centroid = sel->centroid[0]; T.y_est_centroid = sel->centroid[1]; T.z_est_centroid = sel->centroid[2];
+            T.n_coefficients = sel->n_coefficients;
+            for (int i = 0; i < 8; ++i) T.coefficients[i] = sel->coefficients[i];
+          }
+          T.n_points = cc.n;
+          T.inl_plane = (int)planeInl; T.inl_sphere = (int)sphereInl; T.inl_cylinder = (int)cylinderInl; T.inl_cone = (int)coneInl;
+        } else {
+          status = PITT_ERR_CAPACITY;
+        }
+        res->n_shapes++;
+        res->n_clusters++;
+        cc.d_xyz = nullptr;  // views own nothing
+        cc.d_nrm = nullptr;
+      }
+    }
+  }
+  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  timer.finish();
+  res->device_ms = ctx->last_ms;
+  if (status == PITT_ERR_CAPACITY) return fail(ctx, status, "shapes buffer too small");
+  return status;
+}
+
+}  // extern "C"

@@ -1,0 +1,174 @@
+"""Golden fixtures (tests/golden/*.npz, written by tests/golden/make_golden.py from the oracle):
+the oracle must keep reproducing them on CPU, and the CUDA path must reproduce them on the GPU."""
+import os
+
+import numpy as np
+import pytest
+
+from pitt_object_table_segmentation_b200 import _abi as A
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+KINDS = (("sphere", A.MODEL_SPHERE), ("cylinder", A.MODEL_CYLINDER), ("cone", A.MODEL_CONE))
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _info_vec(i):
+    return np.array([i.iterations, i.skipped, i.hypotheses, i.best_hypothesis, i.best_count, i.n_inliers_model,
+                     i.lm_info, i.lm_nfev], np.int32)
+
+
+class OracleBackend:
+    name = "oracle"
+
+    def __init__(self, oracle):
+        self.o = oracle
+
+    def params(self, model):
+        return self.o.default_sac_params(model)
+
+    def support_sac(self):
+        return self.o.default_support_sac_params()
+
+    def score(self, xyz, nrm, p, samples):
+        return self.o.sac_score(xyz, nrm, p, samples)
+
+    def segment(self, xyz, nrm, p):
+        return self.o.sac_segment(xyz, nrm, p)
+
+    def primitive(self, xyz, nrm, p):
+        return self.o.primitive_service(xyz, nrm, p)
+
+    def normals(self, xyz):
+        return self.o.estimate_normals(xyz, 50)
+
+    def knn(self, xyz, k):
+        return self.o.knn(xyz, k)[0]
+
+    def supports(self, xyz, nrm):
+        return self.o.find_supports(xyz, nrm, self.o.default_support_params())
+
+    def clusters(self, xyz, tol, mn, mx):
+        return self.o.euclidean_clusters(xyz, tol, mn, mx)
+
+    def frame(self, xyz):
+        return self.o.segment_frame(xyz, self.o.default_frame_params())
+
+
+class GpuBackend(OracleBackend):
+    name = "gpu"
+
+    def __init__(self, ctx):
+        import pitt_object_table_segmentation_b200 as pkg
+        self.c, self.pkg = ctx, pkg
+
+    def params(self, model):
+        return self.pkg.default_sac_params(model)
+
+    def support_sac(self):
+        return self.pkg.default_support_sac_params()
+
+    def score(self, xyz, nrm, p, samples):
+        return self.c.sac_score(self.c.stage(xyz, normals=nrm), p, samples)
+
+    def segment(self, xyz, nrm, p):
+        return self.c.sac_segment(self.c.stage(xyz, normals=nrm), p)
+
+    def primitive(self, xyz, nrm, p):
+        return self.c.primitive_service(self.c.stage(xyz, normals=nrm), p)
+
+    def normals(self, xyz):
+        return self.c.estimate_normals(self.c.stage(xyz), 50)
+
+    def knn(self, xyz, k):
+        return self.c.knn(self.c.stage(xyz), k)[0]
+
+    def supports(self, xyz, nrm):
+        return self.c.find_supports(self.c.stage(xyz, normals=nrm))
+
+    def clusters(self, xyz, tol, mn, mx):
+        return self.c.euclidean_clusters(self.c.stage(xyz), tol, mn, mx)
+
+    def frame(self, xyz):
+        return self.c.segment_frame(self.c.stage(xyz))
+
+
+def _check_plane(b):
+    g = np.load(os.path.join(G, "plane_c2_small.npz"))
+    p = b.support_sac()
+    counts, co, valid = b.score(g["xyz"], None, p, g["samples"])
+    assert np.array_equal(counts, g["counts"]) and np.array_equal(valid, g["valid"])
+    assert np.array_equal(_bits(co), _bits(g["coeffs"]))
+    seg = b.segment(g["xyz"], None, p)
+    assert np.array_equal(seg["inliers"], g["seg_inliers"]) and np.array_equal(_bits(seg["coeffs"]), _bits(g["seg_coeffs"]))
+    assert np.array_equal(_info_vec(seg["info"]), g["seg_info"])
+
+
+def _check_primitives(b):
+    for kind, model in KINDS:
+        g = np.load(os.path.join(G, f"primitive_{kind}.npz"))
+        p = b.params(model)
+        assert np.array_equal(_bits(b.normals(g["xyz"])), _bits(g["normals"])), kind
+        counts, co, valid = b.score(g["xyz"], g["normals"], p, g["samples"])
+        assert np.array_equal(counts, g["counts"]) and np.array_equal(valid, g["valid"]), kind
+        assert np.array_equal(_bits(co), _bits(g["coeffs"])), kind
+        seg = b.segment(g["xyz"], g["normals"], p)
+        assert np.array_equal(seg["inliers"], g["seg_inliers"]), kind
+        np.testing.assert_allclose(seg["coeffs"], g["seg_coeffs"], rtol=1e-5, atol=1e-7)  # north-star tolerance
+        assert np.array_equal(_bits(seg["coeffs"]), _bits(g["seg_coeffs"])), kind     # achieved: bit-exact
+        assert np.array_equal(_info_vec(seg["info"]), g["seg_info"]), kind
+        srv = b.primitive(g["xyz"], g["normals"], p)
+        assert np.array_equal(srv["inliers"], g["srv_inliers"]), kind
+        assert np.array_equal(_bits(srv["coefficients"]), _bits(g["srv_coeffs"])), kind
+        assert np.array_equal(_bits(srv["centroid"]), _bits(g["srv_centroid"])), kind
+
+
+def _check_tabletop(b):
+    g = np.load(os.path.join(G, "tabletop_160x120.npz"))
+    xyz = g["xyz"]
+    assert np.array_equal(_bits(b.normals(xyz)), _bits(g["normals"]))
+    assert np.array_equal(b.knn(xyz[:2000], 8), g["knn_idx_first2000_k8"])
+    sup = b.supports(xyz, g["normals"])
+    assert len(sup["supports"]) == 1
+    s = sup["supports"][0]
+    assert np.array_equal(_bits(s["coefficients"]), _bits(g["support_coeffs"]))
+    assert np.array_equal(s["inliers"], g["support_map"])
+    assert np.array_equal(_bits(s["on_support_cloud"]), _bits(g["on_support"]))
+    on = g["on_support"]
+    labels, nc = b.clusters(on, 0.03, int(round(len(on) * 0.01)), int(round(len(on) * 0.99)))
+    assert nc == int(g["n_clusters"]) and np.array_equal(labels, g["cluster_labels"])
+    fr = b.frame(xyz)
+    assert np.array_equal(np.array([t["tag"] for t in fr["shapes"]], np.int32), g["shape_tags"])
+    assert np.array_equal(np.array([t["inliers"] for t in fr["shapes"]], np.int32), g["shape_inliers"])
+    for t, co, ce in zip(fr["shapes"], g["shape_coeffs"], g["shape_est_centroid"]):
+        assert np.array_equal(_bits(np.pad(t["coefficients"], (0, 8 - len(t["coefficients"])))), _bits(co))
+        assert np.array_equal(_bits(t["est_centroid"]), _bits(ce))
+
+
+def test_oracle_reproduces_golden_plane(oracle):
+    _check_plane(OracleBackend(oracle))
+
+
+def test_oracle_reproduces_golden_primitives(oracle):
+    _check_primitives(OracleBackend(oracle))
+
+
+def test_oracle_reproduces_golden_tabletop(oracle):
+    _check_tabletop(OracleBackend(oracle))
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_golden_plane(ctx):
+    _check_plane(GpuBackend(ctx))
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_golden_primitives(ctx):
+    _check_primitives(GpuBackend(ctx))
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_golden_tabletop(ctx):
+    _check_tabletop(GpuBackend(ctx))

@@ -1,0 +1,257 @@
+"""CPU-only tests (run with -m "not gpu"): pin the oracle itself.
+
+The reference ships no tests or golden vectors: parity is unpinned by it. What pins the
+oracle: the mt19937 known-answer of the C++ standard, brute-force numpy restatements, analytic scenes
+with known ground truth, PCL-semantics properties, and the committed golden fixtures (tests/golden).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from pitt_object_table_segmentation_b200 import _abi as A, scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_mt19937_known_answer(oracle):
+    # ISO C++ [rand.predef]: the 10000th invocation of a default-constructed mt19937 yields 4123659995
+    assert oracle.mt19937_nth(5489, 10000) == 4123659995
+
+
+def test_sample_stream_is_partial_fisher_yates(oracle):
+    """drawIndexSample restated in numpy: rnd() = mt() >> 1, persistent shuffled_indices_."""
+    n = 1000
+    xyz = scenes.plane_outlier_cloud(n, seed=2)
+    got = oracle.pcl_sample_stream(xyz, A.MODEL_SPHERE, 50)  # sphere: isSampleGood is always true
+    # numpy's MT19937 with the same init_genrand seeding
+    bitgen = np.random.MT19937()
+    state = bitgen.state
+    key = np.zeros(624, np.uint32)
+    key[0] = 12345
+    for i in range(1, 624):
+        key[i] = (1812433253 * (int(key[i - 1]) ^ (int(key[i - 1]) >> 30)) + i) & 0xFFFFFFFF
+    state["state"]["key"] = key
+    state["state"]["pos"] = 624
+    bitgen.state = state
+    raw = bitgen.random_raw(50 * 4)
+    sh = np.arange(n)
+    t = 0
+    for h in range(50):
+        for i in range(4):
+            j = i + int((int(raw[t]) >> 1) % (n - i))
+            t += 1
+            sh[i], sh[j] = sh[j], sh[i]
+        assert list(sh[:4]) == list(got[h])
+
+
+def test_plane_scoring_matches_numpy(oracle):
+    xyz = scenes.plane_outlier_cloud(5000, seed=5)
+    p = oracle.default_support_sac_params()
+    samples = oracle.pcl_sample_stream(xyz, A.MODEL_PLANE, 40)
+    counts, co, valid = oracle.sac_score(xyz, None, p, samples)
+    assert valid.all()
+    x, y, z = (xyz[:, i].astype(np.float32) for i in range(3))
+    for h in range(40):
+        a, b, c, d = (np.float32(v) for v in co[h, :4])
+        s = (a * x + c * z) + (b * y + d)  # Eigen SSE2 dot order, float32 throughout
+        assert int((np.abs(s).astype(np.float64) < p.distance_threshold).sum()) == counts[h]
+        # coefficients: unit normal through the three sample points
+        assert abs(np.linalg.norm(co[h, :3]) - 1) < 1e-6
+        for idx in samples[h]:
+            assert abs(float(np.dot(co[h, :3], xyz[idx, :3]) + co[h, 3])) < 1e-5
+
+
+def test_ransac_pcl_semantics(oracle):
+    xyz = scenes.plane_outlier_cloud(8000, seed=6)
+    p = oracle.default_support_sac_params()
+    r = oracle.sac_segment(xyz, None, p)
+    info = r["info"]
+    samples = oracle.pcl_sample_stream(xyz, A.MODEL_PLANE, info.hypotheses)
+    counts, _, _ = oracle.sac_score(xyz, None, p, samples)
+    # winner = earliest maximum among the hypotheses tried (strict '>' keeps the earliest)
+    assert info.best_count == counts.max() and info.best_hypothesis == int(np.argmax(counts))
+    assert info.iterations <= p.max_iterations + 1
+    # the refined model's inliers are what is returned (SACSegmentation::segment)
+    assert np.array_equal(r["inliers"], oracle.sac_select(xyz, None, p, r["coeffs"]))
+    assert np.all(np.diff(r["inliers"]) > 0)
+    # deterministic: a fresh model reseeds mt19937(12345) on every segment()
+    r2 = oracle.sac_segment(xyz, None, p)
+    assert np.array_equal(r["inliers"], r2["inliers"]) and np.array_equal(r["coeffs"], r2["coeffs"])
+    # ground truth: plane z = 0
+    assert abs(abs(r["coeffs"][2]) - 1) < 1e-4 and abs(r["coeffs"][3]) < 1e-3
+
+
+def test_adaptive_stop_formula(oracle):
+    xyz = scenes.plane_outlier_cloud(4000, seed=8, plane_frac=0.9)
+    p = oracle.default_sac_params(A.MODEL_PLANE)
+    p.optimize = 0
+    r = oracle.sac_segment(xyz, None, p)
+    info = r["info"]
+    w = info.best_count / 4000.0
+    k = np.log(1 - 0.99) / np.log(min(1 - np.finfo(float).eps, max(np.finfo(float).eps, 1 - w ** 3)))
+    assert info.iterations >= k and info.iterations - 1 < max(k, 1.0) + 1e-9 or info.iterations == 1
+
+
+@pytest.mark.parametrize("kind,model", [("sphere", A.MODEL_SPHERE), ("cylinder", A.MODEL_CYLINDER), ("cone", A.MODEL_CONE)])
+def test_primitives_recover_ground_truth(oracle, kind, model):
+    xyz, truth = scenes.primitive_cluster(kind, 4000, 11)
+    nrm = oracle.estimate_normals(xyz, 50)
+    r = oracle.sac_segment(xyz, nrm, oracle.default_sac_params(model))
+    assert len(r["inliers"]) > 0.9 * 4000
+    if kind == "sphere":
+        assert abs(r["coeffs"][3] - truth["radius"]) < 1e-3
+    elif kind == "cylinder":
+        assert abs(r["coeffs"][6] - truth["radius"]) < 2e-3
+        axis = truth["R"] @ np.array([0, 0, 1.0])
+        assert abs(abs(np.dot(axis, r["coeffs"][3:6])) - 1) < 2e-3
+    else:
+        assert abs(r["coeffs"][6] - truth["half_angle"]) < 0.03
+    assert r["info"].lm_info in (1, 2, 3)  # Eigen LM converged
+
+
+def test_lm_improves_residual(oracle):
+    xyz, truth = scenes.primitive_cluster("sphere", 3000, 21, sigma=0.002)
+    p = oracle.default_sac_params(A.MODEL_SPHERE)
+    p.optimize = 0
+    base = oracle.sac_segment(xyz, None, p)
+    ref, info = oracle.sac_refine(xyz, None, p, base["coeffs"], base["inliers"])
+
+    def rms(c):
+        d = np.linalg.norm(xyz[base["inliers"], :3] - c[:3], axis=1) - c[3]
+        return np.sqrt((d ** 2).mean())
+    assert rms(ref) <= rms(base["coeffs"]) + 1e-9
+    assert abs(ref[3] - truth["radius"]) < 5e-4
+
+
+def test_knn_matches_brute_force(oracle):
+    xyz = scenes.tabletop_frame(seed=3, width=80, height=60)
+    idx, sq = oracle.knn(xyz, 12)
+    P = xyz[:, :3].astype(np.float32)
+    for q in range(0, len(P), 37):
+        d = P - P[q]
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]).astype(np.float32) + d[:, 2] * d[:, 2]
+        order = np.lexsort((np.arange(len(P)), d2))[:12]
+        assert np.array_equal(order, idx[q]) and np.array_equal(d2[order], sq[q])
+        assert idx[q, 0] == q  # the query is its own nearest neighbour (kept, as in PCL)
+
+
+def test_normals_on_analytic_surfaces(oracle):
+    r = np.random.default_rng(0)
+    pts = np.stack([r.uniform(-1, 1, 4000), r.uniform(-1, 1, 4000), np.zeros(4000)], 1)
+    Rm = np.array([[1, 0, 0], [0, 0.8, -0.6], [0, 0.6, 0.8]])
+    xyz = np.ones((4000, 4), np.float32)
+    xyz[:, :3] = pts @ Rm.T + np.array([0, 0, 2.0])
+    nrm = oracle.estimate_normals(xyz, 50, (0, 0, 0))
+    n_true = Rm @ np.array([0, 0, 1.0])
+    assert np.allclose(np.abs(nrm[:, :3] @ n_true), 1.0, atol=1e-3)
+    assert ((xyz[:, :3] * -1) * nrm[:, :3]).sum(1).min() >= 0  # flipped towards the viewpoint (origin)
+    assert nrm[:, 3].max() < 1e-3  # curvature of a plane
+
+
+def test_clusters_match_scipy_components(oracle):
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+    from scipy.spatial import cKDTree
+    xyz = scenes.tabletop_frame(seed=4, width=200, height=150)
+    xyz = np.ascontiguousarray(xyz[xyz[:, 2] > 0.012])
+    n = len(xyz)
+    labels, nc = oracle.euclidean_clusters(xyz, 0.03, 10, n)
+    pairs = cKDTree(xyz[:, :3].astype(np.float64)).query_pairs(0.03 * 0.9999, output_type="ndarray")
+    g = coo_matrix((np.ones(len(pairs)), (pairs[:, 0], pairs[:, 1])), shape=(n, n))
+    _, comp = connected_components(g, directed=False)
+    big = [c for c in np.unique(comp) if (comp == c).sum() >= 10]
+    assert nc == len(big)
+    for c in big:  # same partition (labels identical up to permutation)
+        assert len(np.unique(labels[comp == c])) == 1 and labels[comp == c][0] >= 0
+    sizes = np.bincount(labels[labels >= 0])
+    assert np.all(np.diff(sizes) <= 0)  # PCL order: size descending
+
+
+def test_supports_and_frame_on_tabletop(oracle):
+    xyz = scenes.tabletop_frame(seed=12345, width=320, height=240)
+    fr = oracle.segment_frame(xyz, oracle.default_frame_params())
+    assert fr["n_supports"] == 1 and fr["n_clusters"] == 3
+    co = fr["support_coefficients"][0]
+    assert abs(abs(co[2]) - 1) < 1e-3 and abs(co[3]) < 2e-3  # table plane z = 0
+    tags = sorted(s["tag_name"] for s in fr["shapes"])
+    assert tags == ["cone", "cylinder", "sphere"]
+    sph = [s for s in fr["shapes"] if s["tag_name"] == "sphere"][0]
+    assert abs(sph["coefficients"][3] - 0.06) < 2e-3
+    cyl = [s for s in fr["shapes"] if s["tag_name"] == "cylinder"][0]
+    assert abs(cyl["coefficients"][6] - 0.04) < 3e-3
+
+
+def test_idx_map_quirks(oracle):
+    """createNewIdxMap: labels -2, -3, ... for horizontal supports, running counters elsewhere"""
+    xyz = scenes.tabletop_frame(seed=2, width=160, height=120)
+    res = oracle.find_supports(xyz, None, oracle.default_support_params())
+    s = res["supports"][0]
+    m = s["inliers"]
+    assert (m == -2).sum() == len(s["support_cloud"])
+    rest = m[m >= 0]
+    assert np.array_equal(rest, np.arange(len(rest)))  # running counter over the remaining cloud
+    # on-support points are strictly inside the shrunken bounding box and above the mean height
+    on = s["on_support_cloud"]
+    assert (on[:, 2] > s["support_cloud"][:, 2].astype(np.float64).mean() + 0.005 - 1e-9).all()
+
+
+# ---------------------------------------------------------------- C ABI library (no GPU needed)
+def test_cabi_library_exports_every_declared_symbol(built):
+    import re
+    import pitt_object_table_segmentation_b200 as pkg
+    lib = C.CDLL(pkg.LIB_PATH)
+    header = open(os.path.join(ROOT, "include", "pitt_b200.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", header, flags=re.S)  # strip comments
+    declared = set(re.findall(r"\b(pitt_[a-z0-9_]+)\s*\(", code))
+    declared -= {"pitt_ctx", "pitt_cloud"}
+    assert len(declared) >= 35
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in pitt_b200.h but not exported"
+    assert declared == set(pkg.EXPORTED_SYMBOLS)
+
+
+def test_struct_layouts_match_header(built):
+    """sizeof of the ctypes mirrors == sizeof in C (compiled with gcc against the header)."""
+    import subprocess
+    import tempfile
+    src = '#include <stdio.h>\n#include "pitt_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
+          'sizeof(pitt_sac_params),sizeof(pitt_sac_info),sizeof(pitt_support_params),sizeof(pitt_support),' \
+          'sizeof(pitt_support_result),sizeof(pitt_cluster_params),sizeof(pitt_cluster),sizeof(pitt_clusters_result),' \
+          'sizeof(pitt_primitive_result),sizeof(pitt_tracked_shape),sizeof(pitt_frame_params));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
+        out = subprocess.check_output([os.path.join(d, "t")]).split()
+    mirrors = [A.SacParams, A.SacInfo, A.SupportParams, A.Support, A.SupportResult, A.ClusterParams, A.Cluster,
+               A.ClustersResult, A.PrimitiveResult, A.TrackedShape, A.FrameParams]
+    assert [int(v) for v in out] == [C.sizeof(m) for m in mirrors]
+
+
+def test_no_cpu_fallback(built):
+    import torch
+    import pitt_object_table_segmentation_b200 as pkg
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.PittError):
+        pkg.Context(0)
+    lib = pkg.load_library()
+    assert lib.pitt_device_count() == 0
+    assert not lib.pitt_create(0, 0)
+
+
+def test_defaults_match_reference_launch_parameters(built, oracle):
+    import pitt_object_table_segmentation_b200 as pkg
+    for model in range(4):
+        a, b = pkg.default_sac_params(model), oracle.default_sac_params(model)
+        assert bytes(a) == bytes(b)
+    assert bytes(pkg.default_support_sac_params()) == bytes(oracle.default_support_sac_params())
+    p = pkg.default_sac_params(A.MODEL_CYLINDER)  # cylinder_segmentation_srv.cpp:23-30
+    assert (p.normal_distance_weight, p.distance_threshold, p.radius_min, p.radius_max, p.max_iterations, p.eps_angle) == \
+           (0.001, 0.008, 0.005, 0.5, 1000, 0.0001)
+    p = pkg.default_sac_params(A.MODEL_CONE)  # cone_segmentation_srv.cpp:24-31
+    assert (p.normal_distance_weight, p.distance_threshold, p.eps_angle) == (0.0006, 0.0055, 0.4)
+    assert abs(p.min_angle - np.deg2rad(10)) < 1e-15 and abs(p.max_angle - np.deg2rad(170)) < 1e-15
+    c = pkg.default_cluster_params()
+    assert (c.tolerance, c.min_rate, c.max_rate, c.min_input_size) == (0.03, 0.01, 0.99, 30)

@@ -321,6 +321,14 @@ int pitt_select_primitive(int64_t plane_inl, int64_t sphere_inl, int64_t cylinde
 int pitt_segment_frame(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_frame_params* params,
                        pitt_frame_result* result);
 
+/* C4: a stream of frames. Thread t of n_ctx host threads drives ctxs[t] (one stream each; the
+ * contexts may sit on one GPU or on several) over frames t, t+n_ctx, ...: stage from the host
+ * pointer (frames[i], n_points[i], stride_bytes), pitt_segment_frame, release. results[i] must
+ * have its shapes buffer set. Returns the first non-OK status. */
+int pitt_segment_frames_batched(pitt_ctx* const* ctxs, int n_ctx, const void* const* frames, const int* n_points,
+                                int stride_bytes, int n_frames, const pitt_frame_params* params,
+                                pitt_frame_result* results);
+
 /* ------------------------------------------------------------------ measurement helpers */
 /* FP32 pipe micro-benchmark used as the roofline denominator of the scoring kernels:
  * kind 0 = FFMA, 1 = FMUL+FADD (unfused, what bit-exact scoring needs), 2 = packed f32x2 FMUL2+FADD2.

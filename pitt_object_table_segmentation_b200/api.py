@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "pitt_cloud_device_normals", "pitt_release_cloud", "pitt_estimate_normals", "pitt_get_normals", "pitt_knn",
     "pitt_sac_segment", "pitt_sac_score", "pitt_sac_score_device", "pitt_argmax_counts_device", "pitt_sac_select", "pitt_sac_refine",
     "pitt_pcl_sample_stream", "pitt_euclidean_clusters", "pitt_find_supports", "pitt_cluster_service",
-    "pitt_primitive_service", "pitt_select_primitive", "pitt_segment_frame", "pitt_fp32_peak", "pitt_last_device_ms",
+    "pitt_primitive_service", "pitt_select_primitive", "pitt_segment_frame", "pitt_segment_frames_batched", "pitt_fp32_peak", "pitt_last_device_ms",
     "pitt_kernel_launches",
 ]
 
@@ -80,6 +80,8 @@ def load_library():
     lib.pitt_primitive_service.argtypes = [vp, vp, C.POINTER(A.SacParams), C.POINTER(A.PrimitiveResult)]
     lib.pitt_select_primitive.argtypes = [C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_float]
     lib.pitt_segment_frame.argtypes = [vp, vp, C.POINTER(A.FrameParams), C.POINTER(A.FrameResult)]
+    lib.pitt_segment_frames_batched.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(vp), A.i32p, C.c_int, C.c_int,
+                                                C.POINTER(A.FrameParams), C.POINTER(A.FrameResult)]
     lib.pitt_fp32_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     lib.pitt_last_device_ms.restype = C.c_double
     lib.pitt_last_device_ms.argtypes = [vp]
@@ -353,3 +355,28 @@ Context.find_supports = _find_supports
 Context.cluster_service = _cluster_service
 Context.primitive_service = _primitive_service
 Context.segment_frame = _segment_frame
+
+
+def segment_frames_batched(contexts, frames, params=None, shapes_cap=64):
+    """pitt_segment_frames_batched: `frames` is a list of (n,4) float32 host arrays (ideally pinned);
+    one host thread per context drives its stream. Returns the per-frame result dicts."""
+    params = params if params is not None else default_frame_params()
+    lib = load_library()
+    n = len(frames)
+    frames = [np.ascontiguousarray(f, np.float32) for f in frames]
+    bufs = [R.FrameBuffers(shapes_cap) for _ in range(n)]
+    res = (A.FrameResult * n)()
+    for i, b in enumerate(bufs):
+        res[i] = b.res
+    ptrs = (C.c_void_p * n)(*[f.ctypes.data for f in frames])
+    counts = np.array([f.shape[0] for f in frames], np.int32)
+    ctxs = (C.c_void_p * len(contexts))(*[c.handle for c in contexts])
+    st = lib.pitt_segment_frames_batched(ctxs, len(contexts), ptrs, counts.ctypes.data_as(A.i32p), 16, n,
+                                         C.byref(params), res)
+    if st != A.PITT_OK:
+        raise PittError(f"pitt_segment_frames_batched status {st}")
+    out = []
+    for i, b in enumerate(bufs):
+        b.res = res[i]
+        out.append(b.to_python())
+    return out

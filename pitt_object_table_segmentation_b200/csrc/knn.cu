@@ -12,6 +12,7 @@
 namespace pitt {
 
 constexpr int KNN_KMAX = 64;
+constexpr int KNN_BRUTE_MAX = 4096;  // below this size the all-pairs kernel beats grid + ring search
 
 __device__ __forceinline__ bool cand_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
 
@@ -44,6 +45,11 @@ __device__ __forceinline__ void heap_sift_up(float* hd, int* hi, int pos) {
   hd[pos] = d;
   hi[pos] = i;
 }
+
+template <int MODE>
+__device__ __forceinline__ void knn_finish(float* hd, int* hi, int size, int k, int qi, float4 q, const float4* __restrict__ xyz,
+                                           float vpx, float vpy, float vpz, int* __restrict__ out_idx,
+                                           float* __restrict__ out_sq, float4* __restrict__ out_nrm);
 
 template <int MODE>  // 0: neighbour lists, 1: normals
 __global__ void __launch_bounds__(128)
@@ -103,6 +109,14 @@ knn_kernel(GridDev g, const float4* __restrict__ xyz, int k, float vpx, float vp
       if (bound > 0.0f && hd[0] < bound * bound) break;
     }
   }
+  knn_finish<MODE>(hd, hi, size, k, qi, q, xyz, vpx, vpy, vpz, out_idx, out_sq, out_nrm);
+}
+
+// heap -> sorted neighbour list -> outputs (shared by the grid and the brute-force kernels)
+template <int MODE>
+__device__ __forceinline__ void knn_finish(float* hd, int* hi, int size, int k, int qi, float4 q, const float4* __restrict__ xyz,
+                                           float vpx, float vpy, float vpz, int* __restrict__ out_idx,
+                                           float* __restrict__ out_sq, float4* __restrict__ out_nrm) {
   // heap sort -> ascending (distance, index)
   for (int s = size - 1; s > 0; --s) {
     float d = hd[0];
@@ -141,6 +155,47 @@ knn_kernel(GridDev g, const float4* __restrict__ xyz, int k, float vpx, float vp
   out_nrm[qi] = make_float4(nx, ny, nz, curv);
 }
 
+// small clouds (a few thousand points: object clusters): every query scans all points staged
+// through shared memory; no grid, no ring search, no host round trip
+template <int MODE>
+__global__ void __launch_bounds__(128)
+knn_brute_kernel(const float4* __restrict__ xyz, int n, int k, float vpx, float vpy, float vpz, int* __restrict__ out_idx,
+                 float* __restrict__ out_sq, float4* __restrict__ out_nrm) {
+  __shared__ float4 s_p[128];
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (qi < n) q = __ldg(xyz + qi);
+  const bool active = qi < n && isfinite(q.x) && isfinite(q.y) && isfinite(q.z);
+  float hd[KNN_KMAX];
+  int hi[KNN_KMAX];
+  int size = 0;
+  for (int base = 0; base < n; base += 128) {
+    __syncthreads();
+    if (base + threadIdx.x < n) s_p[threadIdx.x] = __ldg(xyz + base + threadIdx.x);
+    __syncthreads();
+    if (!active) continue;
+    const int m = min(128, n - base);
+    for (int t = 0; t < m; ++t) {
+      const float4 p = s_p[t];
+      if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) continue;
+      const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
+      const float d = (ddx * ddx + ddy * ddy) + ddz * ddz;
+      const int pi = base + t;
+      if (size < k) {
+        hd[size] = d;
+        hi[size] = pi;
+        heap_sift_up(hd, hi, size);
+        ++size;
+      } else if (cand_less(d, pi, hd[0], hi[0])) {
+        hd[0] = d;
+        hi[0] = pi;
+        heap_sift_down(hd, hi, size, 0);
+      }
+    }
+  }
+  if (active) knn_finish<MODE>(hd, hi, size, k, qi, q, xyz, vpx, vpy, vpz, out_idx, out_sq, out_nrm);
+}
+
 __global__ void fill_f4_kernel(float4* p, int n, float4 v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -159,6 +214,12 @@ int estimate_normals_impl(pitt_ctx* ctx, const float4* d_xyz, int n, int k, cons
   const float nan = nanf("");
   fill_f4_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_nrm, n, make_float4(nan, nan, nan, nan));
   ctx->launches++;
+  if (n <= KNN_BRUTE_MAX) {
+    knn_brute_kernel<1><<<cdiv(n, 128), 128, 0, ctx->stream>>>(d_xyz, n, k, vp[0], vp[1], vp[2], nullptr, nullptr, d_nrm);
+    ctx->launches++;
+    PITT_CUDA(ctx, cudaGetLastError());
+    return PITT_OK;
+  }
   GridDev g;
   PITT_TRY(grid_build(ctx, d_xyz, n, -1.0f, fmaxf(2.0f, (float)k / 4.0f), &g));
   if (g.n <= 0) return PITT_OK;
@@ -180,7 +241,7 @@ int pitt_estimate_normals(pitt_ctx* ctx, pitt_cloud* c, int k, const float viewp
   cudaSetDevice(ctx->device);
   CallTimer timer(ctx);
   if (c->n > 0) {
-    if (!c->d_nrm) PITT_CUDA(ctx, cudaMalloc((void**)&c->d_nrm, (size_t)c->n * sizeof(float4)));
+    if (!c->d_nrm) PITT_TRY(pool_alloc(ctx, (size_t)c->n * sizeof(float4), (void**)&c->d_nrm));
     PITT_TRY(estimate_normals_impl(ctx, c->d_xyz, c->n, k, viewpoint, c->d_nrm));
     PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
@@ -203,11 +264,16 @@ int pitt_knn(pitt_ctx* ctx, const pitt_cloud* c, int k, int32_t* out_idx, float*
     size_t tot = (size_t)n * k;
     fill_knn_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, ctx->stream>>>(d_idx, d_sq, tot);
     ctx->launches++;
-    GridDev g;
-    PITT_TRY(grid_build(ctx, c->d_xyz, n, -1.0f, fmaxf(2.0f, (float)k / 4.0f), &g));
-    if (g.n > 0) {
-      knn_kernel<0><<<cdiv(g.n, 128), 128, 0, ctx->stream>>>(g, c->d_xyz, k, 0.f, 0.f, 0.f, d_idx, d_sq, nullptr);
+    if (n <= KNN_BRUTE_MAX) {
+      knn_brute_kernel<0><<<cdiv(n, 128), 128, 0, ctx->stream>>>(c->d_xyz, n, k, 0.f, 0.f, 0.f, d_idx, d_sq, nullptr);
       ctx->launches++;
+    } else {
+      GridDev g;
+      PITT_TRY(grid_build(ctx, c->d_xyz, n, -1.0f, fmaxf(2.0f, (float)k / 4.0f), &g));
+      if (g.n > 0) {
+        knn_kernel<0><<<cdiv(g.n, 128), 128, 0, ctx->stream>>>(g, c->d_xyz, k, 0.f, 0.f, 0.f, d_idx, d_sq, nullptr);
+        ctx->launches++;
+      }
     }
     PITT_CUDA(ctx, cudaMemcpyAsync(out_idx, d_idx, tot * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (out_sqdist) PITT_CUDA(ctx, cudaMemcpyAsync(out_sqdist, d_sq, tot * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));

@@ -68,6 +68,7 @@ void pitt_destroy(pitt_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (void* p : ctx->d_overflow) cudaFree(p);
+  for (auto& b : ctx->cloud_pool) cudaFree(b.p);
   if (ctx->d_arena) cudaFree(ctx->d_arena);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   cudaEventDestroy(ctx->ev0);
@@ -179,8 +180,8 @@ int pitt_stage_cloud(pitt_ctx* ctx, const void* xyz, int stride_bytes, int n, pi
   pitt_cloud* c = new pitt_cloud();
   c->n = n;
   if (n > 0) {
-    cudaError_t e = cudaMalloc((void**)&c->d_xyz, (size_t)n * sizeof(float4));
-    if (e != cudaSuccess) { delete c; return fail(ctx, PITT_ERR_CUDA, "cudaMalloc(cloud)", e); }
+    cudaError_t e = cudaSuccess;
+    if (pool_alloc(ctx, (size_t)n * sizeof(float4), (void**)&c->d_xyz) != PITT_OK) { delete c; return PITT_ERR_CUDA; }
     if (stride_bytes == 16) {
       // pcl::PointXYZ / PointCloud2 point_step 16: already the HBM layout, one DMA
       e = cudaMemcpyAsync(c->d_xyz, xyz, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->stream);
@@ -209,8 +210,8 @@ int pitt_stage_cloud_device(pitt_ctx* ctx, const void* d_xyz4, int n, pitt_cloud
   pitt_cloud* c = new pitt_cloud();
   c->n = n;
   if (n > 0) {
-    cudaError_t e = cudaMalloc((void**)&c->d_xyz, (size_t)n * sizeof(float4));
-    if (e != cudaSuccess) { delete c; return fail(ctx, PITT_ERR_CUDA, "cudaMalloc(cloud)", e); }
+    cudaError_t e = cudaSuccess;
+    if (pool_alloc(ctx, (size_t)n * sizeof(float4), (void**)&c->d_xyz) != PITT_OK) { delete c; return PITT_ERR_CUDA; }
     e = cudaMemcpyAsync(c->d_xyz, d_xyz4, (size_t)n * 16, cudaMemcpyDeviceToDevice, ctx->stream);
     if (e != cudaSuccess) { cudaFree(c->d_xyz); delete c; return fail(ctx, PITT_ERR_CUDA, "cudaMemcpyAsync(D2D cloud)", e); }
   }
@@ -224,7 +225,7 @@ int pitt_set_normals(pitt_ctx* ctx, pitt_cloud* c, const void* normals, int stri
   cudaSetDevice(ctx->device);
   CallTimer timer(ctx);
   if (c->n > 0) {
-    if (!c->d_nrm) PITT_CUDA(ctx, cudaMalloc((void**)&c->d_nrm, (size_t)c->n * sizeof(float4)));
+    if (!c->d_nrm) PITT_TRY(pool_alloc(ctx, (size_t)c->n * sizeof(float4), (void**)&c->d_nrm));
     if (stride_bytes == 16) {
       PITT_CUDA(ctx, cudaMemcpyAsync(c->d_nrm, normals, (size_t)c->n * 16, cudaMemcpyHostToDevice, ctx->stream));
     } else {
@@ -252,8 +253,8 @@ void pitt_release_cloud(pitt_ctx* ctx, pitt_cloud* c) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
   }
-  if (c->d_xyz) cudaFree(c->d_xyz);
-  if (c->d_nrm) cudaFree(c->d_nrm);
+  pool_free(ctx, c->d_xyz, (size_t)c->n * sizeof(float4));
+  pool_free(ctx, c->d_nrm, (size_t)c->n * sizeof(float4));
   delete c;
 }
 

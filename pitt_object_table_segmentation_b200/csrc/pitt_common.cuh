@@ -32,6 +32,9 @@ struct pitt_ctx {
   size_t d_arena_off = 0;
   size_t d_call_total = 0;
   std::vector<void*> d_overflow;  // blocks allocated when the arena was too small (freed at reset)
+  // released cloud buffers kept for reuse (frame streams stage a same-sized cloud every step)
+  struct PoolBuf { void* p; size_t bytes; };
+  std::vector<PoolBuf> cloud_pool;
 };
 
 struct pitt_cloud {
@@ -151,6 +154,29 @@ inline int ensure_host_mirror(pitt_ctx* ctx, const pitt_cloud* cc) {
   }
   c->h_valid = true;
   return PITT_OK;
+}
+
+// device buffers of clouds come from a small per-context pool: cudaMalloc/cudaFree synchronise the
+// device and cost ~100 us each, which would dominate a 1 ms frame step
+inline int pool_alloc(pitt_ctx* ctx, size_t bytes, void** out) {
+  size_t best = (size_t)-1;
+  int bi = -1;
+  for (size_t i = 0; i < ctx->cloud_pool.size(); ++i)
+    if (ctx->cloud_pool[i].bytes >= bytes && ctx->cloud_pool[i].bytes < best) { best = ctx->cloud_pool[i].bytes; bi = (int)i; }
+  if (bi >= 0 && best <= bytes * 2 + 4096) {
+    *out = ctx->cloud_pool[bi].p;
+    ctx->cloud_pool.erase(ctx->cloud_pool.begin() + bi);
+    return PITT_OK;
+  }
+  cudaError_t e = cudaMalloc(out, bytes ? bytes : 16);
+  if (e != cudaSuccess) return fail(ctx, PITT_ERR_CUDA, "cudaMalloc(cloud)", e);
+  return PITT_OK;
+}
+inline size_t pool_bytes_of(size_t n_points) { return n_points * 16; }
+inline void pool_free(pitt_ctx* ctx, void* p, size_t bytes) {
+  if (!p) return;
+  if (ctx && ctx->cloud_pool.size() < 8) ctx->cloud_pool.push_back({p, bytes});
+  else cudaFree(p);
 }
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }

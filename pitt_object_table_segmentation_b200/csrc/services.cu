@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "cluster.cuh"
@@ -807,6 +809,34 @@ int pitt_segment_frame(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_frame_
   res->device_ms = ctx->last_ms;
   if (status == PITT_ERR_CAPACITY) return fail(ctx, status, "shapes buffer too small");
   return status;
+}
+
+int pitt_segment_frames_batched(pitt_ctx* const* ctxs, int n_ctx, const void* const* frames, const int* n_points,
+                                int stride_bytes, int n_frames, const pitt_frame_params* params, pitt_frame_result* results) {
+  if (!ctxs || n_ctx <= 0) return PITT_ERR_CUDA;
+  for (int t = 0; t < n_ctx; ++t)
+    if (!ctxs[t]) return PITT_ERR_CUDA;
+  if (n_frames < 0 || (n_frames > 0 && (!frames || !n_points || !results)) || !params)
+    return fail(ctxs[0], PITT_ERR_INVALID, "pitt_segment_frames_batched arguments");
+  std::atomic<int> first_error(PITT_OK);
+  auto worker = [&](int t) {
+    pitt_ctx* ctx = ctxs[t];
+    for (int i = t; i < n_frames; i += n_ctx) {
+      pitt_cloud* c = nullptr;
+      int st = pitt_stage_cloud(ctx, frames[i], stride_bytes, n_points[i], &c);
+      if (st == PITT_OK) st = pitt_segment_frame(ctx, c, params, &results[i]);
+      if (c) pitt_release_cloud(ctx, c);
+      if (st != PITT_OK) {
+        int expected = PITT_OK;
+        first_error.compare_exchange_strong(expected, st);
+      }
+    }
+  };
+  std::vector<std::thread> threads;
+  for (int t = 1; t < n_ctx; ++t) threads.emplace_back(worker, t);
+  worker(0);
+  for (auto& th : threads) th.join();
+  return first_error.load();
 }
 
 }  // extern "C"

@@ -173,3 +173,19 @@ def test_segment_frame(ctx, oracle, seed, w, h):
         assert _eq_f(g["est_centroid"], wv["est_centroid"])
     if w >= 320:  # enough points per object for the reference's selection rule to name all three
         assert sorted(s["tag_name"] for s in got["shapes"]) == ["cone", "cylinder", "sphere"]
+
+
+def test_segment_frames_batched_matches_single(ctx, oracle):
+    frames = [scenes.tabletop_frame(seed=s, width=200, height=150, random_poses=True) for s in range(6)]
+    ctxs = [pkg.Context(0, seed=12345) for _ in range(3)]
+    got = pkg.segment_frames_batched(ctxs, frames)
+    for f, g in zip(frames, got):
+        single = ctx.segment_frame(ctx.stage(f))
+        assert g["n_clusters"] == single["n_clusters"] and g["support_sizes"] == single["support_sizes"]
+        for a, b in zip(g["shapes"], single["shapes"]):
+            assert (a["tag"], a["inliers"]) == (b["tag"], b["inliers"])
+            assert _eq_f(a["coefficients"], b["coefficients"])
+    want = oracle.segment_frame(frames[0], oracle.default_frame_params())
+    assert [s["tag"] for s in got[0]["shapes"]] == [s["tag"] for s in want["shapes"]]
+    for c in ctxs:
+        c.close()

@@ -155,45 +155,170 @@ __device__ __forceinline__ void knn_finish(float* hd, int* hi, int size, int k, 
   out_nrm[qi] = make_float4(nx, ny, nz, curv);
 }
 
-// small clouds (a few thousand points: object clusters): every query scans all points staged
-// through shared memory; no grid, no ring search, no host round trip
-template <int MODE>
-__global__ void __launch_bounds__(128)
-knn_brute_kernel(const float4* __restrict__ xyz, int n, int k, float vpx, float vpy, float vpz, int* __restrict__ out_idx,
-                 float* __restrict__ out_sq, float4* __restrict__ out_nrm) {
-  __shared__ float4 s_p[128];
-  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
-  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (qi < n) q = __ldg(xyz + qi);
-  const bool active = qi < n && isfinite(q.x) && isfinite(q.y) && isfinite(q.z);
-  float hd[KNN_KMAX];
-  int hi[KNN_KMAX];
-  int size = 0;
-  for (int base = 0; base < n; base += 128) {
-    __syncthreads();
-    if (base + threadIdx.x < n) s_p[threadIdx.x] = __ldg(xyz + base + threadIdx.x);
-    __syncthreads();
-    if (!active) continue;
-    const int m = min(128, n - base);
-    for (int t = 0; t < m; ++t) {
-      const float4 p = s_p[t];
-      if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) continue;
-      const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
-      const float d = (ddx * ddx + ddy * ddy) + ddz * ddz;
-      const int pi = base + t;
-      if (size < k) {
-        hd[size] = d;
-        hi[size] = pi;
-        heap_sift_up(hd, hi, size);
-        ++size;
-      } else if (cand_less(d, pi, hd[0], hi[0])) {
-        hd[0] = d;
-        hi[0] = pi;
-        heap_sift_down(hd, hi, size, 0);
+// ---------------------------------------------------------------------------------------------
+// Small clouds (object clusters, a few thousand points): warp-cooperative exact selection.
+// A warp serves 32 queries one after the other. For one query the 32 lanes stream all candidate
+// points; candidates better than the current k-th best are appended to a 64-entry shared buffer
+// (ballot compaction); when the buffer fills, the warp bitonic-sorts {best 64, buffer 64} held four
+// per lane in registers. Unlike a per-thread heap this stays fast when the candidates arrive in
+// scan order (organised clouds: every candidate beats the current k-th best until the query row).
+// The sorted neighbour lists of the 32 queries go to shared memory; then lane l finishes query l
+// (sequential float covariance in neighbour order, eigen33) exactly like the per-thread kernels.
+// ---------------------------------------------------------------------------------------------
+constexpr int WS_WARPS = 8;  // warps (= queries) per CTA
+__device__ __forceinline__ void ws_cmpswap(float& da, int& ia, float& db, int& ib, bool up) {
+  // after the call (a, b) is ordered ascending when up, descending otherwise
+  const bool a_gt_b = cand_less(db, ib, da, ia);
+  if (a_gt_b == up) {
+    float td = da; da = db; db = td;
+    int ti = ia; ia = ib; ib = ti;
+  }
+}
+// full bitonic sort of 128 (d, i) keys: element position p = r*32 + lane, r = 0..3
+__device__ __forceinline__ void ws_sort128(float (&kd)[4], int (&ki)[4], int lane) {
+#pragma unroll
+  for (int size = 2; size <= 128; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (stride >= 32) {
+        const int rs = stride >> 5;  // partner differs in r
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          if ((r & rs) == 0) {
+            const int p = r * 32 + lane;
+            const bool up = ((p & size) == 0) || size == 128;
+            ws_cmpswap(kd[r], ki[r], kd[r | rs], ki[r | rs], up);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int p = r * 32 + lane;
+          const bool up = ((p & size) == 0) || size == 128;
+          const float od = __shfl_xor_sync(0xffffffffu, kd[r], stride);
+          const int oi = __shfl_xor_sync(0xffffffffu, ki[r], stride);
+          const bool lower = (lane & stride) == 0;  // this lane holds the lower position of the pair
+          // keep the smaller key at the lower position when ascending
+          const bool other_less = cand_less(od, oi, kd[r], ki[r]);
+          const bool take = (lower == up) ? other_less : !other_less && !(od == kd[r] && oi == ki[r]);
+          if (take) { kd[r] = od; ki[r] = oi; }
+        }
       }
     }
   }
-  if (active) knn_finish<MODE>(hd, hi, size, k, qi, q, xyz, vpx, vpy, vpz, out_idx, out_sq, out_nrm);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(WS_WARPS * 32)
+knn_brute_kernel(const float4* __restrict__ xyz, int n, int k, float vpx, float vpy, float vpz, int* __restrict__ out_idx,
+                 float* __restrict__ out_sq, float4* __restrict__ out_nrm) {
+  __shared__ float s_bd[WS_WARPS][64];
+  __shared__ int s_bi[WS_WARPS][64];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * WS_WARPS + warp;  // one warp per query
+  if (qi >= n) return;
+  const float4 q = __ldg(xyz + qi);
+  if (!(isfinite(q.x) && isfinite(q.y) && isfinite(q.z))) return;  // outputs stay NaN / -1
+  float kd[4];
+  int ki[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) { kd[r] = CUDART_INF_F; ki[r] = 0x7fffffff; }
+  float thr_d = CUDART_INF_F;
+  int thr_i = 0x7fffffff;
+  int count = 0;  // entries in the shared buffer (warp uniform)
+  auto flush = [&]() {
+    kd[2] = (lane < count) ? s_bd[warp][lane] : CUDART_INF_F;
+    ki[2] = (lane < count) ? s_bi[warp][lane] : 0x7fffffff;
+    kd[3] = (lane + 32 < count) ? s_bd[warp][lane + 32] : CUDART_INF_F;
+    ki[3] = (lane + 32 < count) ? s_bi[warp][lane + 32] : 0x7fffffff;
+    __syncwarp();
+    ws_sort128(kd, ki, lane);
+    count = 0;
+    // k-th best (position k-1) becomes the admission threshold
+    const int r = (k - 1) >> 5, l = (k - 1) & 31;
+    const float td = (r == 0) ? kd[0] : kd[1];
+    const int ti = (r == 0) ? ki[0] : ki[1];
+    thr_d = __shfl_sync(0xffffffffu, td, l);
+    thr_i = __shfl_sync(0xffffffffu, ti, l);
+  };
+  // Candidate chunks of 32 are visited outwards from the query's own index: in organised
+  // (scan-ordered) clouds index neighbours are spatial neighbours, so the admission threshold is
+  // tight after the first few chunks and almost everything else is rejected by one compare.
+  const int n_chunks = (n + 31) >> 5;
+  const int c0 = qi >> 5;
+  for (int step = 0; step < 2 * n_chunks; ++step) {
+    const int off = (step + 1) >> 1;
+    const int c = (step & 1) ? c0 - off : c0 + off;  // c0, c0-1, c0+1, c0-2, ...
+    if (step == 0 ? false : (c == c0)) continue;
+    if (c < 0 || c >= n_chunks) continue;
+    const int pi = (c << 5) + lane;
+    float d = CUDART_INF_F;
+    if (pi < n) {
+      const float4 p = __ldg(xyz + pi);
+      const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
+      d = (ddx * ddx + ddy * ddy) + ddz * ddz;
+    }
+    // non-finite candidates give inf / NaN distances and never pass
+    const bool pass = (d < CUDART_INF_F) && cand_less(d, pi, thr_d, thr_i);
+    const unsigned mask = __ballot_sync(0xffffffffu, pass);
+    if (mask) {
+      bool pass2 = pass;
+      unsigned mask2 = mask;
+      if (count + __popc(mask) > 64) {
+        flush();
+        pass2 = pass && cand_less(d, pi, thr_d, thr_i);  // the threshold is tighter after a flush
+        mask2 = __ballot_sync(0xffffffffu, pass2);
+      }
+      if (pass2) {
+        const int pos = count + __popc(mask2 & ((1u << lane) - 1u));
+        s_bd[warp][pos] = d;
+        s_bi[warp][pos] = pi;
+      }
+      count += __popc(mask2);
+      __syncwarp();
+    }
+  }
+  flush();
+  // sorted list: position t lives in lane t&31, register t>>5 (t < 64)
+  int size = 0;
+  {
+    const unsigned m0 = __ballot_sync(0xffffffffu, kd[0] < CUDART_INF_F), m1 = __ballot_sync(0xffffffffu, kd[1] < CUDART_INF_F);
+    size = min(k, __popc(m0) + __popc(m1));
+  }
+  if (MODE == 0) {
+    for (int t = lane; t < k; t += 32) {
+      const float dd_ = (t < 32) ? kd[0] : kd[1];
+      const int ii_ = (t < 32) ? ki[0] : ki[1];
+      out_idx[(size_t)qi * k + t] = t < size ? ii_ : -1;
+      if (out_sq) out_sq[(size_t)qi * k + t] = t < size ? dd_ : CUDART_INF_F;
+    }
+    return;
+  }
+  if (size < 3) return;
+  // computeMeanAndCovarianceMatrix: sequential float accumulation in neighbour order. Every lane
+  // runs the same sequence on broadcast neighbours (identical result), lane 0 stores it.
+  float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float4 p0 = (ki[0] < n) ? __ldg(xyz + ki[0]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 p1 = (ki[1] < n) ? __ldg(xyz + ki[1]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t = 0; t < size; ++t) {
+    const float4 src = (t < 32) ? p0 : p1;
+    const float px = __shfl_sync(0xffffffffu, src.x, t & 31), py = __shfl_sync(0xffffffffu, src.y, t & 31),
+                pz = __shfl_sync(0xffffffffu, src.z, t & 31);
+    accu[0] += px * px; accu[1] += px * py; accu[2] += px * pz;
+    accu[3] += py * py; accu[4] += py * pz; accu[5] += pz * pz;
+    accu[6] += px; accu[7] += py; accu[8] += pz;
+  }
+  if (lane != 0) return;
+  float cov[9], cen[3], ev, evec[3];
+  cov_from_accu(accu, (float)size, cov, cen);
+  eigen33(cov, ev, evec);
+  float nx = evec[0], ny = evec[1], nz = evec[2];
+  const float eig_sum = cov[0] + cov[4] + cov[8];
+  const float curv = (eig_sum != 0.0f) ? fabsf(ev / eig_sum) : 0.0f;
+  const float vx = vpx - q.x, vy = vpy - q.y, vz = vpz - q.z;
+  const float cos_theta = (vx * nx + vy * ny + vz * nz);
+  if (cos_theta < 0.0f) { nx = -nx; ny = -ny; nz = -nz; }
+  out_nrm[qi] = make_float4(nx, ny, nz, curv);
 }
 
 __global__ void fill_f4_kernel(float4* p, int n, float4 v) {
@@ -215,7 +340,7 @@ int estimate_normals_impl(pitt_ctx* ctx, const float4* d_xyz, int n, int k, cons
   fill_f4_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_nrm, n, make_float4(nan, nan, nan, nan));
   ctx->launches++;
   if (n <= KNN_BRUTE_MAX) {
-    knn_brute_kernel<1><<<cdiv(n, 128), 128, 0, ctx->stream>>>(d_xyz, n, k, vp[0], vp[1], vp[2], nullptr, nullptr, d_nrm);
+    knn_brute_kernel<1><<<cdiv(n, WS_WARPS), WS_WARPS * 32, 0, ctx->stream>>>(d_xyz, n, k, vp[0], vp[1], vp[2], nullptr, nullptr, d_nrm);
     ctx->launches++;
     PITT_CUDA(ctx, cudaGetLastError());
     return PITT_OK;
@@ -265,7 +390,7 @@ int pitt_knn(pitt_ctx* ctx, const pitt_cloud* c, int k, int32_t* out_idx, float*
     fill_knn_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, ctx->stream>>>(d_idx, d_sq, tot);
     ctx->launches++;
     if (n <= KNN_BRUTE_MAX) {
-      knn_brute_kernel<0><<<cdiv(n, 128), 128, 0, ctx->stream>>>(c->d_xyz, n, k, 0.f, 0.f, 0.f, d_idx, d_sq, nullptr);
+      knn_brute_kernel<0><<<cdiv(n, WS_WARPS), WS_WARPS * 32, 0, ctx->stream>>>(c->d_xyz, n, k, 0.f, 0.f, 0.f, d_idx, d_sq, nullptr);
       ctx->launches++;
     } else {
       GridDev g;

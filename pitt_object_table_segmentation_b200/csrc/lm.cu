@@ -39,28 +39,69 @@ struct LmShared {
   float r[64];
   int perm[8], transp[8];
   double red_hi[LM_NW], red_lo[LM_NW];
+  double md_hi[8][LM_NW], md_lo[8][LM_NW];
+  float mdot[8];
+  int cidx[8];
   float bcast[4];
   int ibcast[4];
 };
 
-// sum over i in [r0, m) of a[i]*b[i], exact-to-double-double, rounded once to float; all threads get it
+// Up to 8 simultaneous dot products sum_{i>=r0[j]} a[j][i]*b[j][i] in ONE pass and ONE reduction tree
+// (results in S.mdot[j], visible to all threads after return). The sums are exact to double-double,
+// so fusing them does not change a single bit compared with separate block_dot calls.
+struct DotSet {
+  const float* a[8];
+  const float* b[8];
+  int r0[8];
+  int nv;
+};
+__device__ void block_multidot(const DotSet& D, int m, LmShared& S) {
+  dd acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = dd{0.0, 0.0};
+  int rmin = m;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < D.nv) rmin = min(rmin, D.r0[j]);
+  for (int i = rmin + threadIdx.x; i < m; i += LM_TPB) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < D.nv && i >= D.r0[j]) dd_add(acc[j], (double)D.a[j][i] * (double)D.b[j][i]);
+  }
+  __syncthreads();  // previous readers of S.md_* / S.mdot are done
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j < D.nv) {
+      dd s = acc[j];
+      for (int o = 16; o > 0; o >>= 1) {
+        double ohi = __shfl_down_sync(0xffffffffu, s.hi, o), olo = __shfl_down_sync(0xffffffffu, s.lo, o);
+        dd_merge(s, ohi, olo);
+      }
+      if ((threadIdx.x & 31) == 0) { S.md_hi[j][threadIdx.x >> 5] = s.hi; S.md_lo[j][threadIdx.x >> 5] = s.lo; }
+    }
+  }
+  __syncthreads();
+  // warp j folds the LM_NW per-warp partials of dot j with a shuffle tree
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (w < D.nv) {
+    dd s{0.0, 0.0};
+    if (l < LM_NW) { s.hi = S.md_hi[w][l]; s.lo = S.md_lo[w][l]; }
+    for (int o = 16; o > 0; o >>= 1) {
+      double ohi = __shfl_down_sync(0xffffffffu, s.hi, o), olo = __shfl_down_sync(0xffffffffu, s.lo, o);
+      dd_merge(s, ohi, olo);
+    }
+    if (l == 0) S.mdot[w] = (float)(s.hi + s.lo);
+  }
+  __syncthreads();
+}
+
+// single dot product, same reduction machinery
 __device__ float block_dot(const float* __restrict__ a, const float* __restrict__ b, int r0, int m, LmShared& S) {
-  dd s{0.0, 0.0};
-  for (int i = r0 + threadIdx.x; i < m; i += LM_TPB) dd_add(s, (double)a[i] * (double)b[i]);
-  for (int o = 16; o > 0; o >>= 1) {
-    double ohi = __shfl_down_sync(0xffffffffu, s.hi, o), olo = __shfl_down_sync(0xffffffffu, s.lo, o);
-    dd_merge(s, ohi, olo);
-  }
-  __syncthreads();  // protect S.red_* / S.bcast from the previous call's readers
-  if ((threadIdx.x & 31) == 0) { S.red_hi[threadIdx.x >> 5] = s.hi; S.red_lo[threadIdx.x >> 5] = s.lo; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    dd t{0.0, 0.0};
-    for (int w = 0; w < LM_NW; ++w) dd_merge(t, S.red_hi[w], S.red_lo[w]);
-    S.bcast[0] = (float)(t.hi + t.lo);
-  }
-  __syncthreads();
-  return S.bcast[0];
+  DotSet D;
+  D.nv = 1;
+  D.a[0] = a; D.b[0] = b; D.r0[0] = r0;
+  block_multidot(D, m, S);
+  return S.mdot[0];
 }
 
 // ---- residual functors (float sequences of the PCL OptimizationFunctor::operator())
@@ -278,13 +319,20 @@ lm_kernel(const float4* __restrict__ xyz, const int* __restrict__ idx, const int
       for (int i = threadIdx.x; i < m; i += LM_TPB) cj[i] = (val2[i] - wa4[i]) / h;
       __syncthreads();
     }
-    // ---- column norms, ColPivHouseholderQR
-    for (int j = 0; j < n; ++j) {
-      float* cj = fjac + (size_t)j * m_cap;
-      float sq = block_dot(cj, cj, 0, m, S);
-      if (threadIdx.x == 0) { S.wa2[j] = sqrtf(sq); S.colSq[j] = sq; }
-    }
+    // ---- column norms, ColPivHouseholderQR (columns are swapped logically through S.cidx),
+    //      with Q^T fvec computed on the fly: wa4 rides along as an extra column
+    for (int i = threadIdx.x; i < m; i += LM_TPB) wa4[i] = fvec[i];
+    if (threadIdx.x < 8) S.cidx[threadIdx.x] = threadIdx.x;
     __syncthreads();
+    {
+      DotSet D;
+      D.nv = n;
+      for (int j = 0; j < n; ++j) { D.a[j] = D.b[j] = fjac + (size_t)j * m_cap; D.r0[j] = 0; }
+      block_multidot(D, m, S);
+      if (threadIdx.x == 0)
+        for (int j = 0; j < n; ++j) { S.wa2[j] = sqrtf(S.mdot[j]); S.colSq[j] = S.mdot[j]; }
+      __syncthreads();
+    }
     float threshold_helper, maxpivot = 0.0f;
     int nonzero_pivots = n;
     {
@@ -296,60 +344,75 @@ lm_kernel(const float4* __restrict__ xyz, const int* __restrict__ idx, const int
       int big = k;
       for (int j = k + 1; j < n; ++j)
         if (S.colSq[j] > S.colSq[big]) big = j;
-      float* cb = fjac + (size_t)big * m_cap;
-      float bigSq = block_dot(cb, cb, k, m, S);
-      if (threadIdx.x == 0) S.colSq[big] = bigSq;
+      float* cb = fjac + (size_t)S.cidx[big] * m_cap;
+      {
+        DotSet D;  // squared norm of the pivot column from row k, and of its tail from row k+1
+        D.nv = 2;
+        D.a[0] = D.b[0] = cb; D.r0[0] = k;
+        D.a[1] = D.b[1] = cb; D.r0[1] = k + 1;
+        block_multidot(D, m, S);
+      }
+      const float bigSq = S.mdot[0];
+      const float tailSq = (m - k == 1) ? 0.0f : S.mdot[1];
       __syncthreads();
       if (bigSq < threshold_helper * (float)(m - k)) {
+        if (threadIdx.x == 0) S.colSq[big] = bigSq;
         nonzero_pivots = k;
         for (int j = k; j < n; ++j) {
           if (threadIdx.x == 0) { S.hcoef[j] = 0.0f; S.transp[j] = j; }
-          float* cj = fjac + (size_t)j * m_cap;
+          float* cj = fjac + (size_t)S.cidx[j] * m_cap;
           for (int i = j + 1 + threadIdx.x; i < m; i += LM_TPB) cj[i] = 0.0f;
         }
         __syncthreads();
         break;
       }
-      if (threadIdx.x == 0) S.transp[k] = big;
-      float* ck = fjac + (size_t)k * m_cap;
-      if (k != big) {
-        for (int i = threadIdx.x; i < m; i += LM_TPB) { float t = ck[i]; ck[i] = cb[i]; cb[i] = t; }
-        if (threadIdx.x == 0) { float t = S.colSq[k]; S.colSq[k] = S.colSq[big]; S.colSq[big] = t; }
-        __syncthreads();
+      if (threadIdx.x == 0) {
+        S.colSq[big] = bigSq;
+        S.transp[k] = big;
+        if (k != big) {
+          int t = S.cidx[k]; S.cidx[k] = S.cidx[big]; S.cidx[big] = t;
+          float q = S.colSq[k]; S.colSq[k] = S.colSq[big]; S.colSq[big] = q;
+        }
       }
-      float tailSq = (m - k == 1) ? 0.0f : block_dot(ck, ck, k + 1, m, S);
-      float c0 = ck[k];
-      float tau, beta;
-      __syncthreads();  // everyone has read ck[k] before it is overwritten
+      __syncthreads();
+      float* ck = fjac + (size_t)S.cidx[k] * m_cap;
+      const float c0 = ck[k];
+      float tau, beta, den = 1.0f;
       if (tailSq == 0.0f) {
         tau = 0.0f;
         beta = c0;
-        for (int i = k + 1 + threadIdx.x; i < m; i += LM_TPB) ck[i] = 0.0f;
       } else {
         beta = sqrtf(c0 * c0 + tailSq);
         if (c0 >= 0.0f) beta = -beta;
-        float den = c0 - beta;
-        for (int i = k + 1 + threadIdx.x; i < m; i += LM_TPB) ck[i] = ck[i] / den;
+        den = c0 - beta;
         tau = (beta - c0) / beta;
       }
-      if (threadIdx.x == 0) { S.hcoef[k] = tau; ck[k] = beta; }
       if (fabsf(beta) > maxpivot) maxpivot = fabsf(beta);
-      __syncthreads();
-      for (int j = k + 1; j < n; ++j) {
-        float* cj = fjac + (size_t)j * m_cap;
+      // essential part of the reflector (in place), then v . (remaining columns and wa4) in one pass
+      for (int i = k + 1 + threadIdx.x; i < m; i += LM_TPB) ck[i] = (tailSq == 0.0f) ? 0.0f : ck[i] / den;
+      __syncthreads();  // everyone read c0 = ck[k] and the scaled tail is complete
+      if (threadIdx.x == 0) { S.hcoef[k] = tau; ck[k] = beta; }
+      DotSet D;
+      D.nv = 0;
+      for (int j = k + 1; j < n; ++j) { D.a[D.nv] = ck; D.b[D.nv] = fjac + (size_t)S.cidx[j] * m_cap; D.r0[D.nv] = k + 1; D.nv++; }
+      D.a[D.nv] = ck; D.b[D.nv] = wa4; D.r0[D.nv] = k + 1; D.nv++;
+      if (m - k > 1) block_multidot(D, m, S);
+      else __syncthreads();
+#pragma unroll 1
+      for (int t = 0; t < D.nv; ++t) {
+        float* cj = const_cast<float*>(D.b[t]);
         if (m - k == 1) {
           if (threadIdx.x == 0) cj[k] *= (1.0f - tau);
         } else {
-          float tmp = block_dot(ck, cj, k + 1, m, S);
-          tmp += cj[k];
-          __syncthreads();
-          if (threadIdx.x == 0) cj[k] -= tau * tmp;
+          const float tmp = S.mdot[t] + cj[k];
           for (int i = k + 1 + threadIdx.x; i < m; i += LM_TPB) cj[i] -= tmp * (tau * ck[i]);
+          __syncthreads();  // all threads have read cj[k]
+          if (threadIdx.x == 0) cj[k] -= tau * tmp;
         }
       }
       __syncthreads();
       if (threadIdx.x == 0)
-        for (int j = k + 1; j < n; ++j) { float v = fjac[(size_t)j * m_cap + k]; S.colSq[j] -= v * v; }
+        for (int j = k + 1; j < n; ++j) { float v = fjac[(size_t)S.cidx[j] * m_cap + k]; S.colSq[j] -= v * v; }
       __syncthreads();
     }
     if (threadIdx.x == 0) {
@@ -368,29 +431,12 @@ lm_kernel(const float4* __restrict__ xyz, const int* __restrict__ idx, const int
       delta = factor * xnorm;
       if (delta == 0.0f) delta = factor;
     }
-    // ---- qtf = first n components of Q^T fvec
-    for (int i = threadIdx.x; i < m; i += LM_TPB) wa4[i] = fvec[i];
-    __syncthreads();
-    for (int k = 0; k < n; ++k) {
-      const float tau = S.hcoef[k];
-      const float* ck = fjac + (size_t)k * m_cap;
-      if (m - k == 1) {
-        if (threadIdx.x == 0) wa4[k] *= (1.0f - tau);
-      } else {
-        float tmp = block_dot(ck, wa4, k + 1, m, S);
-        tmp += wa4[k];
-        __syncthreads();
-        if (threadIdx.x == 0) wa4[k] -= tau * tmp;
-        for (int i = k + 1 + threadIdx.x; i < m; i += LM_TPB) wa4[i] -= tmp * (tau * ck[i]);
-      }
-      __syncthreads();
-    }
     // ---- small algebra on thread 0
     if (threadIdx.x == 0) {
       for (int j = 0; j < n; ++j) S.qtf[j] = wa4[j];
       for (int i = 0; i < 64; ++i) S.r[i] = 0.0f;
       for (int i = 0; i < n; ++i)
-        for (int j = 0; j < n; ++j) S.r[i * 8 + j] = fjac[(size_t)j * m_cap + i];
+        for (int j = 0; j < n; ++j) S.r[i * 8 + j] = fjac[(size_t)S.cidx[j] * m_cap + i];
       float gnorm = 0.0f;
       if (fnorm != 0.0f)
         for (int j = 0; j < n; ++j)

@@ -558,14 +558,22 @@ static int launch_score_generic(pitt_ctx* ctx, const pitt_cloud* c, const HypRec
                                 int* d_counts) {
   constexpr int TPB = 256;
   const int n = c->n;
-  int hyp_chunk = H < 512 ? H : 512;
-  int n_chunks = cdiv(H, hyp_chunk);
-  // point blocks: enough CTAs for ~4 waves, each covering a whole number of TPB*P tiles
+  // Work split: big clouds are cut along the points (each CTA keeps up to 512 hypotheses in shared
+  // memory and streams its point tiles); small clouds (object clusters: a few thousand points,
+  // 1001 hypotheses) have too few point tiles to fill 148 SMs and are cut along the hypotheses.
   const int tile = TPB * P;
-  int want_ctas = ctx->sm_count * 8;
-  int pblocks = want_ctas / n_chunks;
+  const int tiles = cdiv(n, tile);
+  const int want_ctas = ctx->sm_count * 4;
+  int hyp_chunk = H < 512 ? H : 512;
+  if (tiles * cdiv(H, hyp_chunk) < want_ctas) {
+    int chunks_wanted = cdiv(want_ctas, tiles);
+    hyp_chunk = std::max(16, cdiv(H, chunks_wanted));
+    if (hyp_chunk > 512) hyp_chunk = 512;
+    if (hyp_chunk > H) hyp_chunk = H;
+  }
+  int n_chunks = cdiv(H, hyp_chunk);
+  int pblocks = (ctx->sm_count * 8) / n_chunks;
   if (pblocks < 1) pblocks = 1;
-  int tiles = cdiv(n, tile);
   if (pblocks > tiles) pblocks = tiles;
   int pts_per_cta = cdiv(tiles, pblocks) * tile;
   pblocks = cdiv(n, pts_per_cta);

@@ -161,108 +161,209 @@ __device__ void make_givens(float p, float q, float& c, float& s) {
     c = -t * s;
   }
 }
-// Eigen internal::qrsolv (n x n, row i col j at s[i*8+j]); thread 0 only
-__device__ void qrsolv(float* s, int n, const int* ipvt, const float* diag, const float* qtb, float* x, float* sdiag) {
-  float wa[8];
-  for (int j = 0; j < n; ++j) { x[j] = s[j * 8 + j]; wa[j] = qtb[j]; }
-  for (int i = 0; i < n; ++i)
-    for (int j = 0; j < i; ++j) s[i * 8 + j] = s[j * 8 + i];
-  for (int j = 0; j < n; ++j) {
-    int l = ipvt[j];
-    if (diag[l] == 0.0f) break;
-    for (int k = j; k < n; ++k) sdiag[k] = 0.0f;
-    sdiag[j] = diag[l];
-    float qtbpj = 0.0f;
-    for (int k = j; k < n; ++k) {
-      float gc, gs;
-      make_givens(-s[k * 8 + k], sdiag[k], gc, gs);
-      s[k * 8 + k] = gc * s[k * 8 + k] + gs * sdiag[k];
-      float temp = gc * wa[k] + gs * qtbpj;
-      qtbpj = -gs * wa[k] + gc * qtbpj;
-      wa[k] = temp;
-      for (int i = k + 1; i < n; ++i) {
-        temp = gc * s[i * 8 + k] + gs * sdiag[i];
-        sdiag[i] = -gs * s[i * 8 + k] + gc * sdiag[i];
-        s[i * 8 + k] = temp;
+// Eigen internal::qrsolv on the N x N triangle; thread 0 only. N is a compile-time constant and every
+// loop is fully unrolled so that s, sdiag, wa live in registers (the serial n x n algebra is the
+// latency floor of the LM kernel: no local-memory round trips).
+template <int N>
+__device__ __forceinline__ void qrsolv(float (&s)[N][N], const int* ipvt, const float (&diag)[N], const float (&qtb)[N],
+                                       float (&x)[N], float (&sdiag)[N]) {
+  float wa[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) { x[j] = s[j][j]; wa[j] = qtb[j]; }
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+      if (j < i) s[i][j] = s[j][i];
+  bool stop = false;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    float dl = 0.0f;
+#pragma unroll
+    for (int q = 0; q < N; ++q)
+      if (ipvt[j] == q) dl = diag[q];
+    if (dl == 0.0f) stop = true;
+    if (!stop) {
+#pragma unroll
+      for (int k = 0; k < N; ++k)
+        if (k >= j) sdiag[k] = 0.0f;
+      sdiag[j] = dl;
+      float qtbpj = 0.0f;
+#pragma unroll
+      for (int k = 0; k < N; ++k) {
+        if (k >= j) {
+          float gc, gs;
+          make_givens(-s[k][k], sdiag[k], gc, gs);
+          s[k][k] = gc * s[k][k] + gs * sdiag[k];
+          float temp = gc * wa[k] + gs * qtbpj;
+          qtbpj = -gs * wa[k] + gc * qtbpj;
+          wa[k] = temp;
+#pragma unroll
+          for (int i = 0; i < N; ++i) {
+            if (i > k) {
+              temp = gc * s[i][k] + gs * sdiag[i];
+              sdiag[i] = -gs * s[i][k] + gc * sdiag[i];
+              s[i][k] = temp;
+            }
+          }
+        }
       }
     }
   }
-  int nsing;
-  for (nsing = 0; nsing < n && sdiag[nsing] != 0.0f; nsing++) {}
-  for (int j = nsing; j < n; ++j) wa[j] = 0.0f;
-  for (int i = nsing - 1; i >= 0; --i) {
-    float acc = 0.0f;
-    for (int j = i + 1; j < nsing; ++j) acc += s[j * 8 + i] * wa[j];
-    wa[i] = (wa[i] - acc) / s[i * 8 + i];
-  }
-  for (int j = 0; j < n; ++j) { sdiag[j] = s[j * 8 + j]; s[j * 8 + j] = x[j]; }
-  for (int j = 0; j < n; ++j) x[ipvt[j]] = wa[j];
-}
-// Eigen internal::lmpar2; thread 0 only
-__device__ void lmpar2(const float* r, int n, const int* perm, int rank, const float* diag, const float* qtb, float delta,
-                       float& par, float* x) {
-  const float dwarf = FLT_MIN;
-  float wa1[8], wa2[8];
-  for (int j = 0; j < n; ++j) wa1[j] = qtb[j];
-  for (int j = rank; j < n; ++j) wa1[j] = 0.0f;
-  for (int i = rank - 1; i >= 0; --i) {
-    wa1[i] /= r[i * 8 + i];
-    for (int q = 0; q < i; ++q) wa1[q] -= wa1[i] * r[q * 8 + i];
-  }
-  for (int j = 0; j < n; ++j) x[perm[j]] = wa1[j];
-  int iter = 0;
-  for (int j = 0; j < n; ++j) wa2[j] = diag[j] * x[j];
-  float dxnorm = norm_n(wa2, n);
-  float fp = dxnorm - delta;
-  if (fp <= 0.1f * delta) { par = 0.0f; return; }
-  float parl = 0.0f;
-  if (rank == n) {
-    for (int j = 0; j < n; ++j) wa1[j] = diag[perm[j]] * wa2[perm[j]] / dxnorm;
-    for (int i = 0; i < n; ++i) {
+  int nsing = N;
+#pragma unroll
+  for (int j = N - 1; j >= 0; --j)
+    if (sdiag[j] == 0.0f) nsing = j;  // first zero of sdiag
+#pragma unroll
+  for (int j = 0; j < N; ++j)
+    if (j >= nsing) wa[j] = 0.0f;
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i) {
+    if (i < nsing) {
       float acc = 0.0f;
-      for (int j = 0; j < i; ++j) acc += r[j * 8 + i] * wa1[j];
-      wa1[i] = (wa1[i] - acc) / r[i * 8 + i];
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+        if (j > i && j < nsing) acc += s[j][i] * wa[j];
+      wa[i] = (wa[i] - acc) / s[i][i];
     }
-    float temp = norm_n(wa1, n);
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) { sdiag[j] = s[j][j]; s[j][j] = x[j]; }
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+#pragma unroll
+    for (int q = 0; q < N; ++q)
+      if (ipvt[j] == q) x[q] = wa[j];
+  }
+}
+template <int N>
+__device__ __forceinline__ float norm_t(const float (&a)[N]) {
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < N; ++i) s += a[i] * a[i];
+  return sqrtf(s);
+}
+// gather v[perm[j]] with compile-time indexable registers
+template <int N>
+__device__ __forceinline__ float pick(const float (&v)[N], int idx) {
+  float r = 0.0f;
+#pragma unroll
+  for (int q = 0; q < N; ++q)
+    if (idx == q) r = v[q];
+  return r;
+}
+// Eigen internal::lmpar2; thread 0 only. r8 = top N x N of the QR factor in shared memory (row stride 8).
+template <int N>
+__device__ void lmpar2(const float* r8, const int* perm, int rank, const float* diag_s, const float* qtb_s, float delta,
+                       float& par, float* x_out) {
+  const float dwarf = FLT_MIN;
+  float r[N][N], diag[N], qtb[N], x[N], wa1[N], wa2[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    diag[i] = diag_s[i];
+    qtb[i] = qtb_s[i];
+#pragma unroll
+    for (int j = 0; j < N; ++j) r[i][j] = r8[i * 8 + j];
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) wa1[j] = (j < rank) ? qtb[j] : 0.0f;
+#pragma unroll
+  for (int i = N - 1; i >= 0; --i) {
+    if (i < rank) {
+      wa1[i] /= r[i][i];
+#pragma unroll
+      for (int q = 0; q < N; ++q)
+        if (q < i) wa1[q] -= wa1[i] * r[q][i];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) x[j] = 0.0f;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+#pragma unroll
+    for (int q = 0; q < N; ++q)
+      if (perm[j] == q) x[q] = wa1[j];
+  }
+  int iter = 0;
+#pragma unroll
+  for (int j = 0; j < N; ++j) wa2[j] = diag[j] * x[j];
+  float dxnorm = norm_t<N>(wa2);
+  float fp = dxnorm - delta;
+  if (fp <= 0.1f * delta) {
+    par = 0.0f;
+#pragma unroll
+    for (int j = 0; j < N; ++j) x_out[j] = x[j];
+    return;
+  }
+  float parl = 0.0f;
+  if (rank == N) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) wa1[j] = pick<N>(diag, perm[j]) * pick<N>(wa2, perm[j]) / dxnorm;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      float acc = 0.0f;
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+        if (j < i) acc += r[j][i] * wa1[j];
+      wa1[i] = (wa1[i] - acc) / r[i][i];
+    }
+    float temp = norm_t<N>(wa1);
     parl = fp / delta / temp / temp;
   }
-  for (int j = 0; j < n; ++j) {
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
     float acc = 0.0f;
-    for (int i = 0; i <= j; ++i) acc += r[i * 8 + j] * qtb[i];
-    wa1[j] = acc / diag[perm[j]];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if (i <= j) acc += r[i][j] * qtb[i];
+    wa1[j] = acc / pick<N>(diag, perm[j]);
   }
-  float gnorm = norm_n(wa1, n);
+  float gnorm = norm_t<N>(wa1);
   float paru = gnorm / delta;
   if (paru == 0.0f) paru = dwarf / fminf(delta, 0.1f);
   par = fmaxf(par, parl);
   par = fminf(par, paru);
   if (par == 0.0f) par = gnorm / dxnorm;
-  float s[64], sdiag[8];
-  for (int i = 0; i < 64; ++i) s[i] = r[i];
+  float s[N][N], sdiag[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    sdiag[i] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < N; ++j) s[i][j] = r[i][j];
+  }
+#pragma unroll 1
   for (;;) {
     ++iter;
     if (par == 0.0f) par = fmaxf(dwarf, 0.001f * paru);
     float sp = sqrtf(par);
-    for (int j = 0; j < n; ++j) wa1[j] = sp * diag[j];
-    qrsolv(s, n, perm, wa1, qtb, x, sdiag);
-    for (int j = 0; j < n; ++j) wa2[j] = diag[j] * x[j];
-    dxnorm = norm_n(wa2, n);
+#pragma unroll
+    for (int j = 0; j < N; ++j) wa1[j] = sp * diag[j];
+    qrsolv<N>(s, perm, wa1, qtb, x, sdiag);
+#pragma unroll
+    for (int j = 0; j < N; ++j) wa2[j] = diag[j] * x[j];
+    dxnorm = norm_t<N>(wa2);
     float temp = fp;
     fp = dxnorm - delta;
     if (fabsf(fp) <= 0.1f * delta || (parl == 0.0f && fp <= temp && temp < 0.0f) || iter == 10) break;
-    for (int j = 0; j < n; ++j) wa1[j] = diag[perm[j]] * (wa2[perm[j]] / dxnorm);
-    for (int j = 0; j < n; ++j) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) wa1[j] = pick<N>(diag, perm[j]) * (pick<N>(wa2, perm[j]) / dxnorm);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
       wa1[j] /= sdiag[j];
       temp = wa1[j];
-      for (int i = j + 1; i < n; ++i) wa1[i] -= s[i * 8 + j] * temp;
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        if (i > j) wa1[i] -= s[i][j] * temp;
     }
-    temp = norm_n(wa1, n);
+    temp = norm_t<N>(wa1);
     float parc = fp / delta / temp / temp;
     if (fp > 0.0f) parl = fmaxf(parl, par);
     if (fp < 0.0f) paru = fminf(paru, par);
     par = fmaxf(parl, par + parc);
   }
   if (iter == 0) par = 0.0f;
+#pragma unroll
+  for (int j = 0; j < N; ++j) x_out[j] = x[j];
 }
 
 // work layout (floats): fjac [n*m_cap] | fvec [m_cap] | wa4 [m_cap] | val2 [m_cap]
@@ -460,7 +561,7 @@ lm_kernel(const float4* __restrict__ xyz, const int* __restrict__ idx, const int
     do {
       if (threadIdx.x == 0) {
         float p = par;
-        lmpar2(S.r, n, S.perm, rank, S.diag, S.qtf, delta, p, S.wa1);
+        lmpar2<n>(S.r, S.perm, rank, S.diag, S.qtf, delta, p, S.wa1);
         S.bcast[1] = p;
         for (int j = 0; j < n; ++j) { S.wa1[j] = -S.wa1[j]; S.wa2[j] = S.x[j] + S.wa1[j]; }
         float t[8];

@@ -479,5 +479,13 @@ int pitt_argmax_counts_device(pitt_ctx* ctx, const void* d_counts, int H, void* 
 
 /* test hook (not in the public header): route plane scoring through the generic kernel */
 void pitt_debug_force_generic_plane(int on) { g_force_generic_plane = on; }
+/* test hooks: plane scoring mode (0 = automatic: filter on large jobs, 1 = exact packed kernel only, 2 = FFMA filter + exact re-evaluation always) and
+ * the filter statistics of the last scoring call made while collection was enabled:
+ * out[0] = (hypothesis, point tile) pairs scored, out[1] = pairs re-evaluated exactly */
+void pitt_debug_plane_mode(int mode) { g_plane_mode = mode; }
+void pitt_debug_plane_filter_stats(int enable, uint64_t* out2) {
+  g_plane_filter_collect_stats = enable;
+  if (out2) { out2[0] = g_plane_filter_stats[0]; out2[1] = g_plane_filter_stats[1]; }
+}
 
 }  // extern "C"

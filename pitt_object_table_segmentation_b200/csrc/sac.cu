@@ -154,7 +154,9 @@ __device__ __forceinline__ float hi32(unsigned long long v) { return __uint_as_f
 template <int KH, int TPB, int TILE>
 __global__ void __launch_bounds__(TPB)
 plane_score_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict__ recs, int H, int n_ptiles,
-                   int n_items, float thr_up, float one_rt, int* __restrict__ work_counter, int* __restrict__ counts) {
+                   int n_items, float thr_up, float one_rt, int* __restrict__ work_counter, int* __restrict__ counts,
+                   const int* __restrict__ skip_if /*nullable: *skip_if != 0 => the filter kernel did the work*/) {
+  if (skip_if && *skip_if) return;
   // Persistent CTAs pull work items (hypothesis block hb, point tile pt) from an atomic counter:
   // item = hb * n_ptiles + pt. The next item's tile is prefetched with cp.async while the current
   // one is scored, so the FP32 pipe never waits on L2/HBM and there is no wave-quantisation tail.
@@ -241,6 +243,266 @@ plane_score_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restri
   }
   asm volatile("cp.async.wait_group 0;");
   flush();
+}
+
+// =====================================================================================
+// K3f: plane scoring with an FFMA filter and exact re-evaluation of the uncertain evaluations.
+//
+// The exact predicate |fl(fl(fl(a x)+fl(c z)) + fl(fl(b y)+d))| < thr needs 6 separately rounded
+// FP32 operations per evaluation. The filter evaluates s~ = fma(a',x, fma(b',y, fma(c',z, d')))
+// with the coefficients scaled by a power of two sigma, then t = fma(s~, s~, -T), T = fl(sigma^2 thr^2):
+// 4 FMA-pipe operations. Both s (exact order) and s~/sigma are within 3.0001 u m of the real dot
+// product (u = 2^-24, m = |a x|+|b y|+|c z|+|d| <= G), so their difference is below beta = 8 u G.
+// sigma is chosen (plane_filter_params_kernel) so that
+//     sigma^2 (beta + 2 thr u)(2 thr + beta + 2 thr u)(1 + 4u) < 2,
+// which makes |t| >= 2 (bit 30 of t set) imply ||s~|/sigma - thr| > beta + thr u, i.e. the sign of t
+// IS the exact predicate. The inner loop therefore only accumulates the sign bits of t (the count)
+// and the AND of the t words (bit 30 clear = some evaluation of this (hypothesis, tile) pair is
+// uncertain). Uncertain pairs are re-evaluated with the exact operation order by the whole warp
+// (lanes = points) and the filter's count for the pair is replaced: the result is bit-identical to
+// plane_score_kernel. Non-finite clouds and degenerate scales take plane_score_kernel instead.
+// =====================================================================================
+struct PlaneFilterParams {
+  float sigma;      // power of two
+  float neg_T;      // -fl(sigma^2 thr_up^2)
+  float G;          // bound on |a x|+|b y|+|c z|+|d| the scale was derived for
+  float sd_unc;     // d' of a hypothesis that must always be re-evaluated (t == +0)
+  float bx, by, bz; // cloud |x|,|y|,|z| maxima
+  int use_filter;   // 0: cloud not finite or scale out of range -> exact kernel
+};
+__global__ void __launch_bounds__(256) cloud_absmax_kernel(const float4* __restrict__ xyz, int n, unsigned* __restrict__ out3) {
+  unsigned mx = 0, my = 0, mz = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = __ldg(xyz + i);
+    // |v| as an unsigned word: ordered like the float for finite values, inf/NaN compare above every finite value
+    mx = max(mx, __float_as_uint(p.x) & 0x7fffffffu);
+    my = max(my, __float_as_uint(p.y) & 0x7fffffffu);
+    mz = max(mz, __float_as_uint(p.z) & 0x7fffffffu);
+  }
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  my = __reduce_max_sync(0xffffffffu, my);
+  mz = __reduce_max_sync(0xffffffffu, mz);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(out3 + 0, mx);
+    atomicMax(out3 + 1, my);
+    atomicMax(out3 + 2, mz);
+  }
+}
+__global__ void plane_filter_params_kernel(const unsigned* __restrict__ absmax, float thr_up, PlaneFilterParams* __restrict__ out) {
+  PlaneFilterParams P;
+  P.use_filter = 0;
+  P.sigma = 1.0f; P.neg_T = 0.0f; P.G = 0.0f; P.sd_unc = 0.0f; P.bx = P.by = P.bz = 0.0f;
+  const unsigned ux = absmax[0], uy = absmax[1], uz = absmax[2];
+  if (ux < 0x7f800000u && uy < 0x7f800000u && uz < 0x7f800000u && thr_up > 0.0f && thr_up < 1e18f) {
+    const double X = __uint_as_float(ux), Y = __uint_as_float(uy), Z = __uint_as_float(uz);
+    // a hypothesis through a cloud point with a unit normal has |d| <= |a|X+|b|Y+|c|Z <= R
+    const double R = sqrt(X * X + Y * Y + Z * Z);
+    const double G = 2.0 * R * (1.0 + 1e-6) + 1e-30;
+    const double u = 5.9604644775390625e-08;  // 2^-24
+    const double thr = (double)thr_up;
+    const double beta = 8.0 * u * G + 1e-30;
+    const double Q0 = (beta + 2.0 * thr * u) * (2.0 * thr + beta + 2.0 * thr * u) * (1.0 + 4.0 * u);
+    // largest sigma = 2^k with sigma^2 Q0 < 2
+    int e = 0;
+    frexp(2.0 / Q0, &e);            // 2/Q0 = f 2^e, f in [0.5,1)  =>  2^(e-1) <= 2/Q0
+    int k = (e - 1) / 2;
+    if ((e - 1) < 0 && ((e - 1) & 1)) k -= 1;  // floor for negative odd exponents
+    double sigma = ldexp(1.0, k);
+    while (sigma * sigma * Q0 >= 2.0) sigma *= 0.5;
+    if (sigma > 1073741824.0) sigma = 1073741824.0;
+    // keep every product finite and normal, and T small enough that fma(sqrt(T), sqrt(T), -T) stays below 2
+    if (sigma >= 1.0 && sigma * G < 1e18 && sigma * sigma * thr * thr < 1048576.0) {
+      const float T = (float)(sigma * sigma * thr * thr);
+      P.sigma = (float)sigma;
+      P.neg_T = -T;
+      P.G = (float)G;
+      P.sd_unc = sqrtf(T);  // fma(sd,sd,-T) is within an ulp of 0: bit 30 clear, always uncertain
+      P.bx = (float)X; P.by = (float)Y; P.bz = (float)Z;
+      P.use_filter = 1;
+    }
+  }
+  *out = P;
+}
+// scaled filter coefficients of one hypothesis (shared by the hot loop and the re-evaluation)
+__device__ __forceinline__ void plane_filter_coeffs(float4 r, const PlaneFilterParams& P, float& sa, float& sb, float& sc, float& sd) {
+  if (!(r.x == r.x)) {  // invalid hypothesis (all NaN): certain outlier everywhere, never re-evaluated
+    sa = sb = sc = 0.0f;
+    sd = 1e18f;
+    return;
+  }
+  const float m = (fabsf(r.x) * P.bx + fabsf(r.y) * P.by) + (fabsf(r.z) * P.bz + fabsf(r.w));
+  if (!(m <= P.G)) {    // outside the bound the scale was derived for (or NaN): always re-evaluated
+    sa = sb = sc = 0.0f;
+    sd = P.sd_unc;
+    return;
+  }
+  sa = r.x * P.sigma; sb = r.y * P.sigma; sc = r.z * P.sigma; sd = r.w * P.sigma;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+// Whole-warp re-evaluation of one (hypothesis, tile) pair: returns exact count - filter count
+// (filter_too) or the exact count alone. tile = shared memory, len points.
+__device__ __noinline__ int plane_recount(const float4* tile, int len, const HypRec* rec, const PlaneFilterParams* Pp,
+                                          float thr_up, int filter_too) {
+  const PlaneFilterParams P = *Pp;
+  const float4 r = __ldg(reinterpret_cast<const float4*>(rec->v));
+  float sa, sb, sc, sd;
+  plane_filter_coeffs(r, P, sa, sb, sc, sd);
+  int c = 0;
+  for (int i = threadIdx.x & 31; i < len; i += 32) {
+    const float4 p = tile[i];
+    const float s = (r.x * p.x + r.z * p.z) + (r.y * p.y + r.w);  // -fmad=false: unfused, Eigen order
+    c += (fabsf(s) < thr_up) ? 1 : 0;
+    if (filter_too) {
+      const float sf = __fmaf_rn(sa, p.x, __fmaf_rn(sb, p.y, __fmaf_rn(sc, p.z, sd)));
+      const float t = __fmaf_rn(sf, sf, P.neg_T);
+      c -= (int)(__float_as_uint(t) >> 31);
+    }
+  }
+  return __reduce_add_sync(0xffffffffu, c);
+}
+
+template <int KH, int TPB, int TILE>
+__global__ void __launch_bounds__(TPB)
+plane_filter_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict__ recs, int H, int n_ptiles,
+                    int n_items, float thr_up, const PlaneFilterParams* __restrict__ Pp, int* __restrict__ work_counter,
+                    int* __restrict__ counts, unsigned long long* __restrict__ stats /*[0] pairs, [1] re-evaluated pairs*/) {
+  __shared__ __align__(16) float4 s_pts[2][TILE];
+  __shared__ int s_item[2];
+  const PlaneFilterParams P = *Pp;
+  if (!P.use_filter) return;  // plane_score_kernel (launched right after) does the work
+  constexpr int KP = KH / 2;
+  const unsigned long long NEGT = pack2(P.neg_T, P.neg_T);
+  unsigned long long A[KP], B[KP], Cc[KP], D[KP];
+  int cnt[KH];
+  int cur_hb = -1;
+  int n_redo = 0;
+  auto flush = [&]() {
+    if (cur_hb < 0) return;
+    const int h_base = (cur_hb * TPB + threadIdx.x) * KH;
+#pragma unroll
+    for (int k = 0; k < KH; ++k)
+      if (h_base + k < H && cnt[k]) atomicAdd(&counts[h_base + k], cnt[k]);
+  };
+  auto load_hyps = [&](int hb) {
+    const int h_base = (hb * TPB + threadIdx.x) * KH;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      float4 r0 = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F), r1 = r0;
+      if (h_base + 2 * k < H) r0 = __ldg(reinterpret_cast<const float4*>(recs[h_base + 2 * k].v));
+      if (h_base + 2 * k + 1 < H) r1 = __ldg(reinterpret_cast<const float4*>(recs[h_base + 2 * k + 1].v));
+      float a0, b0, c0, d0, a1, b1, c1, d1;
+      plane_filter_coeffs(r0, P, a0, b0, c0, d0);
+      plane_filter_coeffs(r1, P, a1, b1, c1, d1);
+      A[k] = pack2(a0, a1); B[k] = pack2(b0, b1); Cc[k] = pack2(c0, c1); D[k] = pack2(d0, d1);
+      cnt[2 * k] = 0; cnt[2 * k + 1] = 0;
+    }
+    cur_hb = hb;
+  };
+  auto stage = [&](int item, int buf) {
+    if (item < n_items) {
+      const int base = (item % n_ptiles) * TILE;
+      for (int i = threadIdx.x; i < TILE; i += TPB) {
+        int gi = base + i;
+        if (gi < n) {
+          unsigned saddr = (unsigned)__cvta_generic_to_shared(&s_pts[buf][i]);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(xyz + gi));
+        } else {
+          s_pts[buf][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;");
+  };
+  if (threadIdx.x == 0) s_item[0] = atomicAdd(work_counter, 1);
+  __syncthreads();
+  int item = s_item[0];
+  stage(item, 0);
+  int it = 0;
+  const int lane = threadIdx.x & 31;
+  while (item < n_items) {
+    if (threadIdx.x == 0) s_item[(it + 1) & 1] = atomicAdd(work_counter, 1);
+    asm volatile("cp.async.wait_group 0;");
+    __syncthreads();
+    const int next = s_item[(it + 1) & 1];
+    stage(next, (it + 1) & 1);
+    const int hb = item / n_ptiles;
+    if (hb != cur_hb) {
+      flush();
+      load_hyps(hb);
+    }
+    const float4* tile = s_pts[it & 1];
+    const int len = min(TILE, n - (item % n_ptiles) * TILE);
+    const int warp_t0 = threadIdx.x & ~31;
+    if (len == TILE) {
+      unsigned andw[KH];
+#pragma unroll
+      for (int k = 0; k < KH; ++k) andw[k] = 0xffffffffu;
+      // (A software-pipelined variant that interleaves the ALU work of the previous point pair with the
+      // FMA work of the current one was measured slower, 1.20 vs 1.09 ms on C2: the loop is bound by
+      // register-file operand reads, not by pipe alternation; tools/plane_variants.cu)
+#pragma unroll 2
+      for (int i = 0; i < TILE; i += 2) {
+        float4 p = tile[i], q = tile[i + 1];  // LDS.128 broadcasts
+        unsigned long long PX = pack2(p.x, p.x), PY = pack2(p.y, p.y), PZ = pack2(p.z, p.z);
+        unsigned long long QX = pack2(q.x, q.x), QY = pack2(q.y, q.y), QZ = pack2(q.z, q.z);
+#pragma unroll
+        for (int k = 0; k < KP; ++k) {
+          unsigned long long sp = fma2(A[k], PX, fma2(B[k], PY, fma2(Cc[k], PZ, D[k])));
+          unsigned long long sq = fma2(A[k], QX, fma2(B[k], QY, fma2(Cc[k], QZ, D[k])));
+          unsigned long long tp = fma2(sp, sp, NEGT);
+          unsigned long long tq = fma2(sq, sq, NEGT);
+          const unsigned tp0 = (unsigned)tp, tp1 = (unsigned)(tp >> 32), tq0 = (unsigned)tq, tq1 = (unsigned)(tq >> 32);
+          cnt[2 * k] += (int)(tp0 >> 31);
+          cnt[2 * k] += (int)(tq0 >> 31);
+          cnt[2 * k + 1] += (int)(tp1 >> 31);
+          cnt[2 * k + 1] += (int)(tq1 >> 31);
+          andw[2 * k] &= tp0 & tq0;
+          andw[2 * k + 1] &= tp1 & tq1;
+        }
+      }
+      unsigned unc = 0;
+#pragma unroll
+      for (int k = 0; k < KH; ++k) unc |= ((andw[k] >> 30) & 1u) ? 0u : (1u << k);
+      if (__any_sync(0xffffffffu, unc != 0)) {
+#pragma unroll
+        for (int k = 0; k < KH; ++k) {
+          unsigned m = __ballot_sync(0xffffffffu, (unc >> k) & 1u);
+          while (m) {
+            const int L = __ffs(m) - 1;
+            m &= m - 1;
+            const int h = (cur_hb * TPB + warp_t0 + L) * KH + k;  // < H: padding hypotheses are never uncertain
+            const int delta = plane_recount(tile, TILE, recs + h, Pp, thr_up, 1);
+            if (lane == L) cnt[k] += delta;
+            if (lane == 0) ++n_redo;
+          }
+        }
+      }
+    } else {
+      // ragged last tile: exact counts for every hypothesis of the block
+#pragma unroll
+      for (int k = 0; k < KH; ++k) {
+#pragma unroll 1
+        for (int L = 0; L < 32; ++L) {
+          const int h = (cur_hb * TPB + warp_t0 + L) * KH + k;
+          if (h >= H) break;  // warp-uniform
+          const int c = plane_recount(tile, len, recs + h, Pp, thr_up, 0);
+          if (lane == L) cnt[k] += c;
+        }
+      }
+    }
+    item = next;
+    ++it;
+  }
+  asm volatile("cp.async.wait_group 0;");
+  flush();
+  if (stats && lane == 0) {
+    atomicAdd(stats + 0, (unsigned long long)it * 32ull * KH);
+    if (n_redo) atomicAdd(stats + 1, (unsigned long long)n_redo);
+  }
 }
 
 // =====================================================================================
@@ -584,6 +846,10 @@ static int launch_score_generic(pitt_ctx* ctx, const pitt_cloud* c, const HypRec
   return PITT_OK;
 }
 
+int g_plane_mode = 0;  // test hook: 0 automatic, 1 exact packed kernel only, 2 FFMA filter + exact re-evaluation always
+unsigned long long g_plane_filter_stats[2] = {0, 0};  // last call with stats enabled: pairs, re-evaluated pairs
+int g_plane_filter_collect_stats = 0;
+
 static int launch_score_plane_packed(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_recs, int H, const ScoreParams& sp,
                                      int* d_counts) {
   constexpr int KH = 8, TPB = 128, TILE = 512;
@@ -592,17 +858,53 @@ static int launch_score_plane_packed(pitt_ctx* ctx, const pitt_cloud* c, const H
   const int n_ptiles = cdiv(n, TILE);
   const long long items = (long long)hblocks * n_ptiles;
   if (items > INT_MAX) return fail(ctx, PITT_ERR_INVALID, "plane scoring: too many work items");
-  int ctas_per_sm = 0;
-  PITT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, plane_score_kernel<KH, TPB, TILE>, TPB, 0));
-  if (ctas_per_sm < 1) ctas_per_sm = 1;
-  int grid = ctx->sm_count * ctas_per_sm;
+  // scratch: [0..2] |x|,|y|,|z| maxima (as words), [3] exact-kernel work counter, [4] filter work counter,
+  // then the filter parameters and the statistics
+  unsigned* d_scr = nullptr;
+  PlaneFilterParams* d_P = nullptr;
+  unsigned long long* d_stats = nullptr;
+  PITT_TRY(arena_alloc(ctx, 8, &d_scr));
+  PITT_TRY(arena_alloc(ctx, 1, &d_P));
+  PITT_TRY(arena_alloc(ctx, 2, &d_stats));
+  PITT_CUDA(ctx, cudaMemsetAsync(d_scr, 0, 8 * sizeof(unsigned), ctx->stream));
+  PITT_CUDA(ctx, cudaMemsetAsync(d_P, 0, sizeof(PlaneFilterParams), ctx->stream));
+  // the filter's two set-up launches only pay off on large jobs; tests force it with mode 2
+  const bool filter = (g_plane_mode == 2) || (g_plane_mode == 0 && (double)n * (double)H >= 134217728.0);
+  if (filter) {
+    PITT_CUDA(ctx, cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    int ab = std::min(cdiv(n, 256 * 8), ctx->sm_count * 8);
+    cloud_absmax_kernel<<<ab, 256, 0, ctx->stream>>>(c->d_xyz, n, d_scr);
+    PITT_LAUNCH_CHECK(ctx, "cloud_absmax_kernel");
+    plane_filter_params_kernel<<<1, 1, 0, ctx->stream>>>(d_scr, sp.thr_up, d_P);
+    PITT_LAUNCH_CHECK(ctx, "plane_filter_params_kernel");
+    static int ctas_f = 0;
+    if (!ctas_f) {
+      PITT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_f, plane_filter_kernel<KH, TPB, TILE>, TPB, 0));
+      if (ctas_f < 1) ctas_f = 1;
+    }
+    int grid = ctx->sm_count * ctas_f;
+    if ((long long)grid > items) grid = (int)items;
+    plane_filter_kernel<KH, TPB, TILE><<<grid, TPB, 0, ctx->stream>>>(c->d_xyz, n, d_recs, H, n_ptiles, (int)items, sp.thr_up, d_P,
+                                                                     (int*)d_scr + 4, d_counts,
+                                                                     g_plane_filter_collect_stats ? d_stats : nullptr);
+    PITT_LAUNCH_CHECK(ctx, "plane_filter_kernel");
+  }
+  static int ctas_e = 0;
+  if (!ctas_e) {
+    PITT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_e, plane_score_kernel<KH, TPB, TILE>, TPB, 0));
+    if (ctas_e < 1) ctas_e = 1;
+  }
+  int grid = ctx->sm_count * ctas_e;
   if ((long long)grid > items) grid = (int)items;
-  int* d_work = nullptr;
-  PITT_TRY(arena_alloc(ctx, 1, &d_work));
-  PITT_CUDA(ctx, cudaMemsetAsync(d_work, 0, sizeof(int), ctx->stream));
-  plane_score_kernel<KH, TPB, TILE><<<grid, TPB, 0, ctx->stream>>>(c->d_xyz, n, d_recs, H, n_ptiles, (int)items, sp.thr_up,
-                                                                  1.0f, d_work, d_counts);
+  // exact kernel: the whole job in exact mode; returns at once when the filter kernel was eligible
+  plane_score_kernel<KH, TPB, TILE><<<grid, TPB, 0, ctx->stream>>>(c->d_xyz, n, d_recs, H, n_ptiles, (int)items, sp.thr_up, 1.0f,
+                                                                  (int*)d_scr + 3, d_counts,
+                                                                  filter ? &d_P->use_filter : nullptr);
   PITT_LAUNCH_CHECK(ctx, "plane_score_kernel");
+  if (filter && g_plane_filter_collect_stats) {
+    PITT_CUDA(ctx, cudaMemcpyAsync(g_plane_filter_stats, d_stats, sizeof(g_plane_filter_stats), cudaMemcpyDeviceToHost, ctx->stream));
+    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   return PITT_OK;
 }
 

@@ -48,5 +48,8 @@ int sac_segment_impl(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& 
 int fp32_peak(pitt_ctx* ctx, int kind, double* tflops);
 
 extern int g_force_generic_plane;
+extern int g_plane_mode;
+extern unsigned long long g_plane_filter_stats[2];
+extern int g_plane_filter_collect_stats;
 
 }  // namespace pitt

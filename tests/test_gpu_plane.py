@@ -1,5 +1,7 @@
 """GPU parity: plane RANSAC (supports_segmentation_srv.cpp:89-111, plane_segmentation_srv.cpp:52-67)
 through the C ABI vs the CPU oracle, bit-exact."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -43,10 +45,13 @@ def test_score_counts_all_hypotheses(ctx, oracle):
     p = pkg.default_support_sac_params()
     samples = oracle.pcl_sample_stream(xyz, A.MODEL_PLANE, 700)
     assert np.array_equal(ctx.pcl_sample_stream(cloud, A.MODEL_PLANE, 700), samples)
-    for force_generic in (0, 1):
+    # (generic kernel) / (FFMA filter + exact re-evaluation) / (exact packed kernel)
+    for force_generic, plane_mode in ((1, 0), (0, 2), (0, 1), (0, 0)):
         ctx.lib.pitt_debug_force_generic_plane(force_generic)
+        ctx.lib.pitt_debug_plane_mode(plane_mode)
         c_gpu, co_gpu, v_gpu = ctx.sac_score(cloud, p, samples)
         ctx.lib.pitt_debug_force_generic_plane(0)
+        ctx.lib.pitt_debug_plane_mode(0)
         c_cpu, co_cpu, v_cpu = oracle.sac_score(xyz, None, p, samples)
         assert np.array_equal(v_gpu, v_cpu)
         assert np.array_equal(co_gpu, co_cpu)
@@ -113,3 +118,100 @@ def test_philox_sampler_finds_the_plane(ctx):
     assert abs(abs(got["coeffs"][2]) - 1.0) < 1e-3 and len(got["inliers"]) > 0.68 * 50000
     again = ctx.sac_segment(cloud, p)
     assert np.array_equal(got["inliers"], again["inliers"])  # counter-based: reproducible
+
+
+def _filter_stats(ctx):
+    out = (C.c_uint64 * 2)()
+    ctx.lib.pitt_debug_plane_filter_stats(1, out)
+    return int(out[0]), int(out[1])
+
+
+def _score_with_stats(ctx, cloud, p, samples):
+    ctx.lib.pitt_debug_plane_filter_stats(1, None)
+    ctx.lib.pitt_debug_plane_mode(2)
+    try:
+        counts = ctx.sac_score(cloud, p, samples)[0]
+        pairs, redo = _filter_stats(ctx)
+    finally:
+        ctx.lib.pitt_debug_plane_filter_stats(0, None)
+        ctx.lib.pitt_debug_plane_mode(0)
+    return counts, pairs, redo
+
+
+@pytest.mark.parametrize("n", [512 * 40, 512 * 40 + 1, 512 * 40 + 511, 700])
+def test_filter_kernel_ragged_tiles(ctx, oracle, n):
+    """full tiles take the FFMA filter, the ragged last tile the exact warp path"""
+    xyz = scenes.plane_outlier_cloud(n, seed=71)
+    cloud = ctx.stage(xyz)
+    p = pkg.default_support_sac_params()
+    samples = np.random.default_rng(5).integers(0, n, (1100, 3)).astype(np.int32)
+    c_gpu, pairs, redo = _score_with_stats(ctx, cloud, p, samples)
+    c_cpu = oracle.sac_score(xyz, None, p, samples)[0]
+    assert np.array_equal(c_gpu, c_cpu)
+    assert pairs > 0  # the filter kernel did the work
+
+
+def test_filter_kernel_points_on_the_threshold(ctx, oracle):
+    """adversarial cloud: most points sit within a few ulps of |distance| == threshold of the hypotheses, so
+    nearly every (hypothesis, tile) pair is uncertain and must be re-evaluated in the exact operation order"""
+    rng = np.random.default_rng(9)
+    n = 512 * 24
+    thr = np.float32(0.02)
+    xyz = np.ones((n, 4), np.float32)
+    xyz[:, 0] = rng.uniform(-1, 1, n)
+    xyz[:, 1] = rng.uniform(-1, 1, n)
+    # heights at +-thr +- {0, 1, 2, 3} ulps, plus a few exact multiples
+    sign = rng.choice([-1.0, 1.0], n).astype(np.float32)
+    z = (sign * thr).astype(np.float32)
+    for k in range(4):
+        m = rng.random(n) < 0.4
+        up = rng.random(n) < 0.5
+        z = np.where(m & up, np.nextafter(z, np.float32(1)), np.where(m & ~up, np.nextafter(z, np.float32(-1)), z)).astype(np.float32)
+    xyz[:, 2] = z
+    xyz[:3] = [[0, 0, 0, 1], [1, 0, 0, 1], [0, 1, 0, 1]]  # the plane z = 0 as hypothesis 0
+    cloud = ctx.stage(xyz)
+    p = pkg.default_support_sac_params()
+    samples = np.vstack([np.array([[0, 1, 2]], np.int32), rng.integers(0, n, (1023, 3)).astype(np.int32)])
+    c_gpu, pairs, redo = _score_with_stats(ctx, cloud, p, samples)
+    c_cpu = oracle.sac_score(xyz, None, p, samples)[0]
+    assert np.array_equal(c_gpu, c_cpu)
+    assert redo >= n // 512  # at least every tile of hypothesis 0
+    ctx.lib.pitt_debug_plane_mode(1)
+    try:
+        c_exact = ctx.sac_score(cloud, p, samples)[0]
+    finally:
+        ctx.lib.pitt_debug_plane_mode(0)
+    assert np.array_equal(c_exact, c_cpu)
+
+
+@pytest.mark.parametrize("scale,thr", [(1.0, 0.02), (40.0, 0.02), (1e-3, 1e-4), (1.0, 3.0), (1e4, 0.05)])
+def test_filter_kernel_scales(ctx, oracle, scale, thr):
+    """the filter's scale and band follow the cloud extent and the threshold; out-of-range cases fall back"""
+    n = 512 * 30
+    xyz = scenes.plane_outlier_cloud(n, seed=81)
+    xyz[:, :3] *= np.float32(scale)
+    cloud = ctx.stage(xyz)
+    p = pkg.default_support_sac_params()
+    p.distance_threshold = thr
+    samples = np.random.default_rng(6).integers(0, n, (600, 3)).astype(np.int32)
+    c_gpu, pairs, redo = _score_with_stats(ctx, cloud, p, samples)
+    c_cpu = oracle.sac_score(xyz, None, p, samples)[0]
+    assert np.array_equal(c_gpu, c_cpu)
+    if pairs:
+        assert redo < 0.25 * pairs  # the band stays narrow on ordinary clouds
+
+
+def test_filter_kernel_non_finite_points_fall_back(ctx, oracle):
+    n = 512 * 20
+    xyz = scenes.plane_outlier_cloud(n, seed=91)
+    xyz[100, 0] = np.nan
+    xyz[2000, 2] = np.inf
+    xyz[7000, :3] = np.nan
+    cloud = ctx.stage(xyz)
+    p = pkg.default_support_sac_params()
+    samples = np.random.default_rng(7).integers(0, n, (512, 3)).astype(np.int32)
+    samples[5] = [100, 3, 4]  # a hypothesis built on a NaN point
+    c_gpu, pairs, redo = _score_with_stats(ctx, cloud, p, samples)
+    c_cpu = oracle.sac_score(xyz, None, p, samples)[0]
+    assert np.array_equal(c_gpu, c_cpu)
+    assert pairs == 0  # exact kernel took over

@@ -230,6 +230,11 @@ pitt_ctx* pitt_create(int device, uint64_t seed);
  * current stream, so that torch.cuda.Event brackets the work). */
 pitt_ctx* pitt_create_on_stream(int device, uint64_t seed, void* cuda_stream);
 void pitt_destroy(pitt_ctx* ctx);
+/* pitt_segment_frame runs the independent primitive fits of a frame (clusters x {sphere, cylinder,
+ * cone, plane}; the reference calls the four services one after the other, ransac_segmentation.cpp:
+ * 235-262) concurrently on n_workers helper streams, one host thread each. 0 = all on the ctx stream.
+ * Default 4. Results do not depend on it. */
+int pitt_set_workers(pitt_ctx* ctx, int n_workers);
 const char* pitt_last_error(const pitt_ctx* ctx);
 const char* pitt_version(void);
 int pitt_device_count(void);

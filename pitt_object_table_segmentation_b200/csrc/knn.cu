@@ -16,53 +16,75 @@ constexpr int KNN_BRUTE_MAX = 4096;  // below this size the all-pairs kernel bea
 
 __device__ __forceinline__ bool cand_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
 
-// max-heap on (d, i) in thread-local arrays
-__device__ __forceinline__ void heap_sift_down(float* hd, int* hi, int size, int pos) {
-  float d = hd[pos];
-  int i = hi[pos];
+// max-heap on (d, i). The heap of one thread lives in SHARED memory with the thread index as the
+// fastest dimension (entry p of thread t at [p * KNN_TPB + t]): whatever heap positions the 32 lanes of
+// a warp touch, they hit 32 different banks, so every access is one conflict-free wavefront. (A
+// thread-local array goes through L1 as local memory and divergent positions cost one sector each.)
+constexpr int KNN_TPB = 128;
+struct Heap {
+  float* d;  // [k][KNN_TPB]
+  int* i;
+  __device__ __forceinline__ float& D(int p) const { return d[p * KNN_TPB]; }
+  __device__ __forceinline__ int& I(int p) const { return i[p * KNN_TPB]; }
+};
+__device__ __forceinline__ void heap_sift_down(const Heap& h, int size, int pos) {
+  float d = h.D(pos);
+  int i = h.I(pos);
   for (;;) {
     int c = 2 * pos + 1;
     if (c >= size) break;
-    if (c + 1 < size && cand_less(hd[c], hi[c], hd[c + 1], hi[c + 1])) ++c;
-    if (!cand_less(d, i, hd[c], hi[c])) break;
-    hd[pos] = hd[c];
-    hi[pos] = hi[c];
+    float cd = h.D(c);
+    int ci = h.I(c);
+    if (c + 1 < size) {
+      const float cd1 = h.D(c + 1);
+      const int ci1 = h.I(c + 1);
+      if (cand_less(cd, ci, cd1, ci1)) { ++c; cd = cd1; ci = ci1; }
+    }
+    if (!cand_less(d, i, cd, ci)) break;
+    h.D(pos) = cd;
+    h.I(pos) = ci;
     pos = c;
   }
-  hd[pos] = d;
-  hi[pos] = i;
+  h.D(pos) = d;
+  h.I(pos) = i;
 }
-__device__ __forceinline__ void heap_sift_up(float* hd, int* hi, int pos) {
-  float d = hd[pos];
-  int i = hi[pos];
+__device__ __forceinline__ void heap_sift_up(const Heap& h, int pos) {
+  float d = h.D(pos);
+  int i = h.I(pos);
   while (pos > 0) {
     int p = (pos - 1) >> 1;
-    if (!cand_less(hd[p], hi[p], d, i)) break;
-    hd[pos] = hd[p];
-    hi[pos] = hi[p];
+    const float pd = h.D(p);
+    const int pi = h.I(p);
+    if (!cand_less(pd, pi, d, i)) break;
+    h.D(pos) = pd;
+    h.I(pos) = pi;
     pos = p;
   }
-  hd[pos] = d;
-  hi[pos] = i;
+  h.D(pos) = d;
+  h.I(pos) = i;
 }
 
 template <int MODE>
-__device__ __forceinline__ void knn_finish(float* hd, int* hi, int size, int k, int qi, float4 q, const float4* __restrict__ xyz,
+__device__ __forceinline__ void knn_finish(const Heap& h, int size, int k, int qi, float4 q, const float4* __restrict__ xyz,
                                            float vpx, float vpy, float vpz, int* __restrict__ out_idx,
                                            float* __restrict__ out_sq, float4* __restrict__ out_nrm);
 
 template <int MODE>  // 0: neighbour lists, 1: normals
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(KNN_TPB)
 knn_kernel(GridDev g, const float4* __restrict__ xyz, int k, float vpx, float vpy, float vpz, int* __restrict__ out_idx,
            float* __restrict__ out_sq, float4* __restrict__ out_nrm) {
+  extern __shared__ __align__(16) unsigned char knn_smem[];
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= g.n) return;
+  const int want = min(k, g.n);
+  Heap hp;
+  hp.d = reinterpret_cast<float*>(knn_smem) + threadIdx.x;
+  hp.i = reinterpret_cast<int*>(knn_smem) + (size_t)k * KNN_TPB + threadIdx.x;
   const float4 q = g.sorted[t];
   const int qi = __float_as_int(q.w);
-  float hd[KNN_KMAX];
-  int hi[KNN_KMAX];
   int size = 0;
-  const int want = min(k, g.n);
+  float top_d = 0.0f;  // register copy of the heap maximum (valid when size == want)
+  int top_i = 0;
   const int cx = grid_coord(q.x, g.mnx, g.inv_h, g.dx), cy = grid_coord(q.y, g.mny, g.inv_h, g.dy),
             cz = grid_coord(q.z, g.mnz, g.inv_h, g.dz);
   const int rmax = max(g.dx, max(g.dy, g.dz));
@@ -84,14 +106,17 @@ knn_kernel(GridDev g, const float4* __restrict__ xyz, int k, float vpx, float vp
             const float d = (ddx * ddx + ddy * ddy) + ddz * ddz;
             const int pi = __float_as_int(p.w);
             if (size < want) {
-              hd[size] = d;
-              hi[size] = pi;
-              heap_sift_up(hd, hi, size);
+              hp.D(size) = d;
+              hp.I(size) = pi;
+              heap_sift_up(hp, size);
               ++size;
-            } else if (cand_less(d, pi, hd[0], hi[0])) {
-              hd[0] = d;
-              hi[0] = pi;
-              heap_sift_down(hd, hi, size, 0);
+              if (size == want) { top_d = hp.D(0); top_i = hp.I(0); }
+            } else if (cand_less(d, pi, top_d, top_i)) {
+              hp.D(0) = d;
+              hp.I(0) = pi;
+              heap_sift_down(hp, size, 0);
+              top_d = hp.D(0);
+              top_i = hp.I(0);
             }
           }
         }
@@ -106,31 +131,31 @@ knn_kernel(GridDev g, const float4* __restrict__ xyz, int k, float vpx, float vp
       if (cz - r > 0) bound = fminf(bound, q.z - (g.mnz + (float)(cz - r) * g.h));
       if (cz + r < g.dz - 1) bound = fminf(bound, (g.mnz + (float)(cz + r + 1) * g.h) - q.z);
       bound -= 2e-3f * g.h;  // float rounding of the cell assignment
-      if (bound > 0.0f && hd[0] < bound * bound) break;
+      if (bound > 0.0f && top_d < bound * bound) break;
     }
   }
-  knn_finish<MODE>(hd, hi, size, k, qi, q, xyz, vpx, vpy, vpz, out_idx, out_sq, out_nrm);
+  knn_finish<MODE>(hp, size, k, qi, q, xyz, vpx, vpy, vpz, out_idx, out_sq, out_nrm);
 }
 
 // heap -> sorted neighbour list -> outputs (shared by the grid and the brute-force kernels)
 template <int MODE>
-__device__ __forceinline__ void knn_finish(float* hd, int* hi, int size, int k, int qi, float4 q, const float4* __restrict__ xyz,
+__device__ __forceinline__ void knn_finish(const Heap& h, int size, int k, int qi, float4 q, const float4* __restrict__ xyz,
                                            float vpx, float vpy, float vpz, int* __restrict__ out_idx,
                                            float* __restrict__ out_sq, float4* __restrict__ out_nrm) {
   // heap sort -> ascending (distance, index)
   for (int s = size - 1; s > 0; --s) {
-    float d = hd[0];
-    int i = hi[0];
-    hd[0] = hd[s];
-    hi[0] = hi[s];
-    hd[s] = d;
-    hi[s] = i;
-    heap_sift_down(hd, hi, s, 0);
+    float d = h.D(0);
+    int i = h.I(0);
+    h.D(0) = h.D(s);
+    h.I(0) = h.I(s);
+    h.D(s) = d;
+    h.I(s) = i;
+    heap_sift_down(h, s, 0);
   }
   if (MODE == 0) {
     for (int s = 0; s < k; ++s) {
-      out_idx[(size_t)qi * k + s] = s < size ? hi[s] : -1;
-      if (out_sq) out_sq[(size_t)qi * k + s] = s < size ? hd[s] : CUDART_INF_F;
+      out_idx[(size_t)qi * k + s] = s < size ? h.I(s) : -1;
+      if (out_sq) out_sq[(size_t)qi * k + s] = s < size ? h.D(s) : CUDART_INF_F;
     }
     return;
   }
@@ -138,7 +163,7 @@ __device__ __forceinline__ void knn_finish(float* hd, int* hi, int size, int k, 
   // computeMeanAndCovarianceMatrix: float accumulators in neighbour order
   float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int s = 0; s < size; ++s) {
-    const float4 p = __ldg(xyz + hi[s]);
+    const float4 p = __ldg(xyz + h.I(s));
     accu[0] += p.x * p.x; accu[1] += p.x * p.y; accu[2] += p.x * p.z;
     accu[3] += p.y * p.y; accu[4] += p.y * p.z; accu[5] += p.z * p.z;
     accu[6] += p.x; accu[7] += p.y; accu[8] += p.z;
@@ -333,6 +358,19 @@ __global__ void fill_knn_kernel(int* idx, float* sq, size_t n) {
   }
 }
 
+static size_t knn_smem_bytes(int k) { return (size_t)k * KNN_TPB * (sizeof(float) + sizeof(int)); }
+// heaps of up to KNN_KMAX entries need 64 KB of dynamic shared memory per CTA: opt in once per device
+static int knn_smem_opt_in(pitt_ctx* ctx) {
+  static bool done[64] = {false};
+  const int dev = ctx->device & 63;
+  if (done[dev]) return PITT_OK;
+  const int bytes = (int)knn_smem_bytes(KNN_KMAX);
+  PITT_CUDA(ctx, cudaFuncSetAttribute(knn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  PITT_CUDA(ctx, cudaFuncSetAttribute(knn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done[dev] = true;
+  return PITT_OK;
+}
+
 int estimate_normals_impl(pitt_ctx* ctx, const float4* d_xyz, int n, int k, const float vp[3], float4* d_nrm) {
   if (n <= 0) return PITT_OK;
   if (k < 1 || k > KNN_KMAX) return fail(ctx, PITT_ERR_INVALID, "k must be in [1, 64]");
@@ -348,7 +386,8 @@ int estimate_normals_impl(pitt_ctx* ctx, const float4* d_xyz, int n, int k, cons
   GridDev g;
   PITT_TRY(grid_build(ctx, d_xyz, n, -1.0f, fmaxf(2.0f, (float)k / 4.0f), &g));
   if (g.n <= 0) return PITT_OK;
-  knn_kernel<1><<<cdiv(g.n, 128), 128, 0, ctx->stream>>>(g, d_xyz, k, vp[0], vp[1], vp[2], nullptr, nullptr, d_nrm);
+  PITT_TRY(knn_smem_opt_in(ctx));
+  knn_kernel<1><<<cdiv(g.n, KNN_TPB), KNN_TPB, knn_smem_bytes(k), ctx->stream>>>(g, d_xyz, k, vp[0], vp[1], vp[2], nullptr, nullptr, d_nrm);
   ctx->launches++;
   PITT_CUDA(ctx, cudaGetLastError());
   return PITT_OK;
@@ -396,7 +435,8 @@ int pitt_knn(pitt_ctx* ctx, const pitt_cloud* c, int k, int32_t* out_idx, float*
       GridDev g;
       PITT_TRY(grid_build(ctx, c->d_xyz, n, -1.0f, fmaxf(2.0f, (float)k / 4.0f), &g));
       if (g.n > 0) {
-        knn_kernel<0><<<cdiv(g.n, 128), 128, 0, ctx->stream>>>(g, c->d_xyz, k, 0.f, 0.f, 0.f, d_idx, d_sq, nullptr);
+        PITT_TRY(knn_smem_opt_in(ctx));
+        knn_kernel<0><<<cdiv(g.n, KNN_TPB), KNN_TPB, knn_smem_bytes(k), ctx->stream>>>(g, c->d_xyz, k, 0.f, 0.f, 0.f, d_idx, d_sq, nullptr);
         ctx->launches++;
       }
     }

@@ -66,6 +66,8 @@ pitt_ctx* pitt_create_on_stream(int device, uint64_t seed, void* cuda_stream) {
 void pitt_destroy(pitt_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  workers_destroy(ctx);
+  if (ctx->ev_fan) cudaEventDestroy(ctx->ev_fan);
   cudaStreamSynchronize(ctx->stream);
   for (void* p : ctx->d_overflow) cudaFree(p);
   for (auto& b : ctx->cloud_pool) cudaFree(b.p);
@@ -80,6 +82,15 @@ void pitt_destroy(pitt_ctx* ctx) {
 const char* pitt_last_error(const pitt_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context (no CUDA device?)"; }
 double pitt_last_device_ms(const pitt_ctx* ctx) { return ctx ? ctx->last_ms : 0.0; }
 int64_t pitt_kernel_launches(const pitt_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int pitt_set_workers(pitt_ctx* ctx, int n_workers) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (n_workers < 0 || n_workers > 64) return fail(ctx, PITT_ERR_INVALID, "pitt_set_workers: 0..64");
+  if (n_workers != ctx->n_workers) {
+    workers_destroy(ctx);
+    ctx->n_workers = n_workers;
+  }
+  return PITT_OK;
+}
 int pitt_synchronize(pitt_ctx* ctx) {
   if (!ctx) return PITT_ERR_CUDA;
   PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

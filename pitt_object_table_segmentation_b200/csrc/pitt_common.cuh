@@ -35,6 +35,11 @@ struct pitt_ctx {
   // released cloud buffers kept for reuse (frame streams stage a same-sized cloud every step)
   struct PoolBuf { void* p; size_t bytes; };
   std::vector<PoolBuf> cloud_pool;
+  // helper contexts + host threads that run the independent primitive fits of a frame concurrently
+  // (services.cu); created on first use, n_workers = 0 keeps everything on this ctx's stream
+  struct pitt_workers* workers = nullptr;
+  int n_workers = 4;
+  cudaEvent_t ev_fan = nullptr;
 };
 
 struct pitt_cloud {
@@ -178,6 +183,9 @@ inline void pool_free(pitt_ctx* ctx, void* p, size_t bytes) {
   if (ctx && ctx->cloud_pool.size() < 8) ctx->cloud_pool.push_back({p, bytes});
   else cudaFree(p);
 }
+
+// services.cu: stops the worker threads and destroys the helper contexts
+void workers_destroy(pitt_ctx* ctx);
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -13,6 +13,10 @@
 #include <cfloat>
 #include <cmath>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -599,6 +603,87 @@ static int count_after_zero_drop(pitt_ctx* ctx, const SacDeviceResult& r, int* o
   return PITT_OK;
 }
 
+
+}  // namespace pitt
+
+// ------------------------------------------------------------------ frame workers
+// A frame has (clusters x 4) independent RANSAC fits whose device work is latency bound (one-CTA
+// Levenberg-Marquardt, small scoring grids). Each worker = one helper pitt_ctx (own stream, arena and
+// pinned scratch) + one host thread, so the fits overlap on the device and their host-side stop-rule
+// scans overlap on the host.
+struct pitt_workers {
+  std::vector<pitt_ctx*> ctxs;
+  std::vector<std::thread> threads;
+  std::mutex m;
+  std::condition_variable cv_work, cv_done;
+  std::deque<std::function<void(pitt_ctx*)>> q;
+  int pending = 0;
+  bool stop = false;
+};
+
+namespace pitt {
+
+static void worker_main(pitt_workers* W, int w) {
+  pitt_ctx* ctx = W->ctxs[w];
+  cudaSetDevice(ctx->device);
+  for (;;) {
+    std::function<void(pitt_ctx*)> fn;
+    {
+      std::unique_lock<std::mutex> lk(W->m);
+      W->cv_work.wait(lk, [&] { return W->stop || !W->q.empty(); });
+      if (W->stop && W->q.empty()) return;
+      fn = std::move(W->q.front());
+      W->q.pop_front();
+    }
+    fn(ctx);
+    {
+      std::lock_guard<std::mutex> lk(W->m);
+      if (--W->pending == 0) W->cv_done.notify_all();
+    }
+  }
+}
+static pitt_workers* workers_get(pitt_ctx* ctx) {
+  if (ctx->workers || ctx->n_workers <= 0) return ctx->workers;
+  pitt_workers* W = new pitt_workers();
+  for (int w = 0; w < ctx->n_workers; ++w) {
+    pitt_ctx* c = pitt_create(ctx->device, ctx->seed);
+    if (!c) break;
+    c->n_workers = 0;  // helpers never fan out themselves
+    W->ctxs.push_back(c);
+  }
+  if (W->ctxs.empty()) {
+    delete W;
+    return nullptr;
+  }
+  for (size_t w = 0; w < W->ctxs.size(); ++w) W->threads.emplace_back(worker_main, W, (int)w);
+  ctx->workers = W;
+  return W;
+}
+void workers_destroy(pitt_ctx* ctx) {
+  pitt_workers* W = ctx->workers;
+  if (!W) return;
+  {
+    std::lock_guard<std::mutex> lk(W->m);
+    W->stop = true;
+  }
+  W->cv_work.notify_all();
+  for (auto& t : W->threads) t.join();
+  for (pitt_ctx* c : W->ctxs) pitt_destroy(c);
+  delete W;
+  ctx->workers = nullptr;
+}
+// runs the tasks on the helpers and returns when all are done
+static void workers_run(pitt_workers* W, std::vector<std::function<void(pitt_ctx*)>>& tasks) {
+  {
+    std::lock_guard<std::mutex> lk(W->m);
+    for (auto& t : tasks) W->q.push_back(std::move(t));
+    W->pending += (int)tasks.size();
+  }
+  W->cv_work.notify_all();
+  std::unique_lock<std::mutex> lk(W->m);
+  W->cv_done.wait(lk, [&] { return W->pending == 0; });
+}
+
 }  // namespace pitt
 
 using namespace pitt;
@@ -761,23 +846,64 @@ int pitt_segment_frame(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_frame_
       }
       ClustersDev cd;
       PITT_TRY(cluster_service_impl(ctx, S.d_on, S.n_on, fp->cluster, &cd));
-      for (size_t c = 0; c < cd.sizes.size(); ++c) {
-        pitt_cloud cc;  // non-owning view of the cluster cloud
-        cc.n = cd.sizes[c];
-        cc.d_xyz = const_cast<float4*>(cd.d_points) + cd.offsets[c];
+      const int nc = (int)cd.sizes.size();
+      if (nc == 0) continue;
+      // cluster normals (ransac_segmentation.cpp:233) on this ctx's stream, then the 4 fits per cluster
+      std::vector<pitt_cloud> cc(nc);  // non-owning views of the cluster clouds
+      for (int c = 0; c < nc; ++c) {
+        cc[c].n = cd.sizes[c];
+        cc[c].d_xyz = const_cast<float4*>(cd.d_points) + cd.offsets[c];
         float4* d_cn = nullptr;
-        PITT_TRY(arena_alloc(ctx, (size_t)cc.n, &d_cn));
-        PITT_TRY(estimate_normals_impl(ctx, cc.d_xyz, cc.n, fp->normals_k, fp->viewpoint, d_cn));
-        cc.d_nrm = d_cn;
-        cc.has_normals = true;
-        const pitt_sac_params* sp[4] = {&fp->sphere, &fp->cylinder, &fp->cone, &fp->plane};
-        PrimitiveHost ph[4];
-        int inl[4];
-        for (int m = 0; m < 4; ++m) {
-          PITT_TRY(primitive_service_impl(ctx, &cc, *sp[m], &ph[m]));
-          PITT_TRY(count_after_zero_drop(ctx, ph[m].sac, &inl[m]));
-        }
-        const int64_t sphereInl = inl[0], cylinderInl = inl[1], coneInl = inl[2], planeInl = inl[3];
+        PITT_TRY(arena_alloc(ctx, (size_t)cc[c].n, &d_cn));
+        PITT_TRY(estimate_normals_impl(ctx, cc[c].d_xyz, cc[c].n, fp->normals_k, fp->viewpoint, d_cn));
+        cc[c].d_nrm = d_cn;
+        cc[c].has_normals = true;
+      }
+      const pitt_sac_params* sp[4] = {&fp->sphere, &fp->cylinder, &fp->cone, &fp->plane};
+      std::vector<PrimitiveHost> ph((size_t)nc * 4);
+      std::vector<int> inl((size_t)nc * 4, 0), st((size_t)nc * 4, PITT_OK);
+      pitt_workers* W = workers_get(ctx);
+      if (W) {
+        if (!ctx->ev_fan) PITT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fan, cudaEventDisableTiming));
+        PITT_CUDA(ctx, cudaEventRecord(ctx->ev_fan, ctx->stream));
+        std::vector<std::function<void(pitt_ctx*)>> tasks;
+        // longest fits first (cylinder, cone, sphere, plane) so the tail of the schedule is short
+        const int order[4] = {1, 2, 0, 3};
+        for (int oi = 0; oi < 4; ++oi)
+          for (int c = 0; c < nc; ++c) {
+            const int m = order[oi];
+            const int slot = c * 4 + m;
+            tasks.push_back([&, slot, c, m](pitt_ctx* h) {
+              arena_reset(h);
+              if (cudaStreamWaitEvent(h->stream, ctx->ev_fan, 0) != cudaSuccess) { st[slot] = PITT_ERR_CUDA; return; }
+              pitt_cloud view;  // private view: the lazy host mirror of a cloud is per task
+              view.n = cc[c].n; view.d_xyz = cc[c].d_xyz; view.d_nrm = cc[c].d_nrm; view.has_normals = true;
+              int s1 = primitive_service_impl(h, &view, *sp[m], &ph[slot]);
+              if (s1 == PITT_OK) s1 = count_after_zero_drop(h, ph[slot].sac, &inl[slot]);
+              if (s1 == PITT_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) s1 = PITT_ERR_CUDA;
+              ph[slot].sac.d_inliers = nullptr;  // helper arena memory: not valid after the task
+              st[slot] = s1;
+              view.d_xyz = nullptr; view.d_nrm = nullptr;
+            });
+          }
+        workers_run(W, tasks);
+        for (pitt_ctx* h : W->ctxs) { ctx->launches += h->launches; h->launches = 0; }
+        for (int i = 0; i < nc * 4; ++i)
+          if (st[i] != PITT_OK) {
+            for (pitt_ctx* h : W->ctxs)
+              if (!h->err.empty()) ctx->err = h->err;
+            for (auto& v : cc) { v.d_xyz = nullptr; v.d_nrm = nullptr; }
+            return st[i];
+          }
+      } else {
+        for (int c = 0; c < nc; ++c)
+          for (int m = 0; m < 4; ++m) {
+            PITT_TRY(primitive_service_impl(ctx, &cc[c], *sp[m], &ph[c * 4 + m]));
+            PITT_TRY(count_after_zero_drop(ctx, ph[c * 4 + m].sac, &inl[c * 4 + m]));
+          }
+      }
+      for (int c = 0; c < nc; ++c) {
+        const int64_t sphereInl = inl[c * 4 + 0], cylinderInl = inl[c * 4 + 1], coneInl = inl[c * 4 + 2], planeInl = inl[c * 4 + 3];
         const int tag = select_primitive_rule(planeInl, sphereInl, cylinderInl, coneInl, fp->cone_over_cylinder_priority);
         if (res->shapes && res->n_shapes < res->shapes_cap) {
           pitt_tracked_shape& T = res->shapes[res->n_shapes];
@@ -785,23 +911,22 @@ int pitt_segment_frame(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_frame_
           T.object_id = res->n_clusters;
           T.shape_tag = tag;
           T.x_pc_centroid = cd.centroid[3 * c]; T.y_pc_centroid = cd.centroid[3 * c + 1]; T.z_pc_centroid = cd.centroid[3 * c + 2];
-          const PrimitiveHost* sel = tag == PITT_TAG_CONE ? &ph[2] : tag == PITT_TAG_CYLINDER ? &ph[1]
-                                     : tag == PITT_TAG_PLANE ? &ph[3] : tag == PITT_TAG_SPHERE ? &ph[0] : nullptr;
+          const PrimitiveHost* sel = tag == PITT_TAG_CONE ? &ph[c * 4 + 2] : tag == PITT_TAG_CYLINDER ? &ph[c * 4 + 1]
+                                     : tag == PITT_TAG_PLANE ? &ph[c * 4 + 3] : tag == PITT_TAG_SPHERE ? &ph[c * 4 + 0] : nullptr;
           if (sel) {
             T.x_est_centroid = sel->centroid[0]; T.y_est_centroid = sel->centroid[1]; T.z_est_centroid = sel->centroid[2];
             T.n_coefficients = sel->n_coefficients;
             for (int i = 0; i < 8; ++i) T.coefficients[i] = sel->coefficients[i];
           }
-          T.n_points = cc.n;
+          T.n_points = cc[c].n;
           T.inl_plane = (int)planeInl; T.inl_sphere = (int)sphereInl; T.inl_cylinder = (int)cylinderInl; T.inl_cone = (int)coneInl;
         } else {
           status = PITT_ERR_CAPACITY;
         }
         res->n_shapes++;
         res->n_clusters++;
-        cc.d_xyz = nullptr;  // views own nothing
-        cc.d_nrm = nullptr;
       }
+      for (auto& v : cc) { v.d_xyz = nullptr; v.d_nrm = nullptr; }  // views own nothing
     }
   }
   PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -17,7 +17,7 @@ _LIB = None
 # every symbol declared in include/pitt_b200.h
 EXPORTED_SYMBOLS = [
     "pitt_create", "pitt_create_on_stream", "pitt_destroy", "pitt_last_error", "pitt_version", "pitt_device_count",
-    "pitt_synchronize", "pitt_default_sac_params", "pitt_default_support_sac_params", "pitt_default_support_params",
+    "pitt_synchronize", "pitt_set_workers", "pitt_default_sac_params", "pitt_default_support_sac_params", "pitt_default_support_params",
     "pitt_default_cluster_params", "pitt_default_frame_params", "pitt_stage_cloud", "pitt_stage_cloud_device",
     "pitt_set_normals", "pitt_cloud_size", "pitt_cloud_has_normals", "pitt_cloud_device_points",
     "pitt_cloud_device_normals", "pitt_release_cloud", "pitt_estimate_normals", "pitt_get_normals", "pitt_knn",
@@ -51,6 +51,7 @@ def load_library():
     lib.pitt_last_error.argtypes = [vp]
     lib.pitt_version.restype = C.c_char_p
     lib.pitt_synchronize.argtypes = [vp]
+    lib.pitt_set_workers.argtypes = [vp, C.c_int]
     lib.pitt_stage_cloud.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]
     lib.pitt_stage_cloud_device.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
     lib.pitt_set_normals.argtypes = [vp, vp, vp, C.c_int]
@@ -171,6 +172,10 @@ class Context:
             self.handle = self.lib.pitt_create_on_stream(int(device), int(seed), C.c_void_p(int(stream)))
         if not self.handle:
             raise PittError("pitt_create failed (no usable CUDA device)")
+
+    def set_workers(self, n_workers):
+        """helper streams/threads for the independent primitive fits of a frame (0 = all on this ctx's stream)"""
+        self._check(self.lib.pitt_set_workers(self.handle, int(n_workers)))
 
     def close(self):
         if getattr(self, "handle", None):

@@ -189,3 +189,24 @@ def test_segment_frames_batched_matches_single(ctx, oracle):
     assert [s["tag"] for s in got[0]["shapes"]] == [s["tag"] for s in want["shapes"]]
     for c in ctxs:
         c.close()
+
+
+@pytest.mark.parametrize("workers", [0, 1, 3, 12])
+def test_segment_frame_is_independent_of_worker_count(oracle, workers):
+    """the primitive fits of a frame fan out to helper streams/threads; results must not depend on that"""
+    xyz = scenes.tabletop_frame(seed=99, width=260, height=200, random_poses=True)
+    c = pkg.Context(0, seed=12345)
+    try:
+        c.set_workers(workers)
+        got = c.segment_frame(c.stage(xyz))
+        again = c.segment_frame(c.stage(xyz))  # helpers are reused across frames
+    finally:
+        c.close()
+    want = oracle.segment_frame(xyz, oracle.default_frame_params())
+    for res in (got, again):
+        assert (res["n_supports"], res["n_clusters"]) == (want["n_supports"], want["n_clusters"])
+        assert len(res["shapes"]) == len(want["shapes"])
+        for g, wv in zip(res["shapes"], want["shapes"]):
+            assert (g["tag"], g["n_points"], g["inliers"], g["object_id"]) == (wv["tag"], wv["n_points"], wv["inliers"], wv["object_id"])
+            assert _eq_f(g["coefficients"], wv["coefficients"])
+            assert _eq_f(g["est_centroid"], wv["est_centroid"])

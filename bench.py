@@ -12,8 +12,9 @@ value   = cloud resident in HBM, the step runs through pitt_sac_segment (count-o
 e2e     = same call with HOST buffers: pitt_stage_cloud from pinned memory (H2D of the cloud inside
           the timed region) + pitt_sac_segment + the inlier list copied back to the host.
 N > 1   = weak scaling of the hypothesis split (config 5 pattern): every rank holds the cloud and
-          scores its own 5000 hypotheses of a N x 5000 stream, the counts are all-gathered with NCCL
-          and every rank takes the earliest arg-max; rank 0 refines/selects the winner.
+          scores its own 5000 hypotheses of a N x 5000 stream, the counts are all-gathered with NCCL,
+          every rank takes the earliest arg-max, refines the winner and selects its final inliers
+          (pitt_sac_finish_device), i.e. the same work per rank as the N = 1 step.
 
 `--impl reference` times the CPU path (the oracle = the PCL restatement; the reference itself
 cannot be built here) on the host cores on a bounded sample of the same workload.
@@ -32,6 +33,9 @@ sys.path.insert(0, ROOT)
 # the frame stream drives many CUDA streams per GPU; with the default 8 hardware queues streams that share
 # a queue serialise falsely (measured 244 -> 362 frames/s at 4 contexts). Must be set before CUDA initialises.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# rank 0 prints exactly one JSON line on stdout: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 import numpy as np
 
@@ -196,6 +200,7 @@ def main():
 
     l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     d_samples = torch.from_numpy(samples).to(dev)
+    d_samples_all = torch.from_numpy(np.ascontiguousarray(samples_all)).to(dev)
     d_counts = torch.zeros(N_HYP, dtype=torch.int32, device=dev)
     d_all = torch.zeros(N_HYP * world, dtype=torch.int32, device=dev)
     d_best = torch.zeros(2, dtype=torch.int32, device=dev)
@@ -212,7 +217,8 @@ def main():
         ctx.sac_score_device(cloud, p, d_samples.data_ptr(), N_HYP, d_counts.data_ptr())
         dist.all_gather_into_tensor(d_all, d_counts)
         ctx.argmax_counts_device(d_all.data_ptr(), N_HYP * world, d_best.data_ptr())
-        return None
+        # every rank holds the cloud: refine the winner and select its final inliers (count only), like N = 1
+        return ctx.sac_finish_device(cloud, p, d_samples_all.data_ptr(), N_HYP * world, d_best.data_ptr())
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):

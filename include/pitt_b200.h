@@ -291,6 +291,13 @@ int pitt_sac_score_device(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_sac
 /* Earliest arg-max over H device-resident int32 counts (e.g. all-gathered over NVLink from the
  * ranks of a hypothesis split); d_best (device) receives {index, count}. */
 int pitt_argmax_counts_device(pitt_ctx* ctx, const void* d_counts, int n_hypotheses, void* d_best);
+/* Second half of seg.segment() for a hypothesis split: d_best (device, {index, count}) names the winner
+ * in the full device-resident sample table; its model is re-estimated from its sample, refined
+ * (optimizeModelCoefficients) and the final inliers selected. inliers may be NULL (count only). */
+int pitt_sac_finish_device(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_sac_params* params,
+                           const void* d_samples_all, int n_hypotheses_all, const void* d_best,
+                           int32_t* inliers, int inliers_cap, int* n_inliers, float* coeffs, int* n_coeffs,
+                           pitt_sac_info* info /* nullable */);
 /* selectWithinDistance for given coefficients (ascending indices). */
 int pitt_sac_select(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_sac_params* params,
                     const float* coeffs, int32_t* inliers, int inliers_cap, int* n_inliers);

@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "pitt_default_cluster_params", "pitt_default_frame_params", "pitt_stage_cloud", "pitt_stage_cloud_device",
     "pitt_set_normals", "pitt_cloud_size", "pitt_cloud_has_normals", "pitt_cloud_device_points",
     "pitt_cloud_device_normals", "pitt_release_cloud", "pitt_estimate_normals", "pitt_get_normals", "pitt_knn",
-    "pitt_sac_segment", "pitt_sac_score", "pitt_sac_score_device", "pitt_argmax_counts_device", "pitt_sac_select", "pitt_sac_refine",
+    "pitt_sac_segment", "pitt_sac_score", "pitt_sac_score_device", "pitt_argmax_counts_device", "pitt_sac_finish_device", "pitt_sac_select", "pitt_sac_refine",
     "pitt_pcl_sample_stream", "pitt_euclidean_clusters", "pitt_find_supports", "pitt_cluster_service",
     "pitt_primitive_service", "pitt_select_primitive", "pitt_segment_frame", "pitt_segment_frames_batched", "pitt_fp32_peak", "pitt_last_device_ms",
     "pitt_kernel_launches",
@@ -71,6 +71,8 @@ def load_library():
                                    C.POINTER(C.c_uint8)]
     lib.pitt_sac_score_device.argtypes = [vp, vp, C.POINTER(A.SacParams), vp, C.c_int, vp]
     lib.pitt_argmax_counts_device.argtypes = [vp, vp, C.c_int, vp]
+    lib.pitt_sac_finish_device.argtypes = [vp, vp, C.POINTER(A.SacParams), vp, C.c_int, vp, A.i32p, C.c_int,
+                                           C.POINTER(C.c_int), A.f32p, C.POINTER(C.c_int), C.POINTER(A.SacInfo)]
     lib.pitt_sac_select.argtypes = [vp, vp, C.POINTER(A.SacParams), A.f32p, A.i32p, C.c_int, C.POINTER(C.c_int)]
     lib.pitt_sac_refine.argtypes = [vp, vp, C.POINTER(A.SacParams), A.f32p, A.i32p, C.c_int, A.f32p,
                                     C.POINTER(A.SacInfo)]
@@ -254,6 +256,19 @@ class Context:
 
     def argmax_counts_device(self, d_counts, H, d_best):
         self._check(self.lib.pitt_argmax_counts_device(self.handle, C.c_void_p(d_counts), int(H), C.c_void_p(d_best)))
+
+    def sac_finish_device(self, cloud, params, d_samples_all, H_all, d_best, want_inliers=False):
+        """winner (device {index, count}) of a hypothesis split -> refined model + final inliers"""
+        n_inl, n_co = C.c_int(0), C.c_int(0)
+        co = np.zeros(8, np.float32)
+        info = A.SacInfo()
+        inl = np.empty(max(cloud.n, 1), np.int32) if want_inliers else None
+        self._check(self.lib.pitt_sac_finish_device(
+            self.handle, cloud.handle, C.byref(params), C.c_void_p(d_samples_all), int(H_all), C.c_void_p(d_best),
+            inl.ctypes.data_as(A.i32p) if want_inliers else None, cloud.n if want_inliers else 0, C.byref(n_inl),
+            co.ctypes.data_as(A.f32p), C.byref(n_co), C.byref(info)))
+        return {"n_inliers": n_inl.value, "coeffs": co[: n_co.value].copy(), "info": info,
+                "inliers": inl[: n_inl.value].copy() if want_inliers else None}
 
     def sac_segment(self, cloud, params):
         n = cloud.n

@@ -371,6 +371,37 @@ int pitt_sac_score_device(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_par
   return score_common(ctx, c, p, (const int*)d_samples, H, (int*)d_counts, nullptr, d_flags);
 }
 
+int pitt_sac_finish_device(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params* p, const void* d_samples_all, int H_all,
+                           const void* d_best, int32_t* inliers, int cap, int* n_inliers, float* coeffs, int* n_coeffs,
+                           pitt_sac_info* info) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!c || !p || !d_samples_all || !d_best || !n_inliers || !coeffs || !n_coeffs || H_all <= 0 || p->model < 0 || p->model > 3)
+    return fail(ctx, PITT_ERR_INVALID, "pitt_sac_finish_device arguments");
+  if ((p->model == PITT_MODEL_CYLINDER || p->model == PITT_MODEL_CONE) && !c->has_normals)
+    return fail(ctx, PITT_ERR_STATE, "cylinder/cone segmentation needs normals on the cloud");
+  cudaSetDevice(ctx->device);
+  CallTimer timer(ctx);
+  SacDeviceResult r;
+  PITT_TRY(sac_finish_from_winner(ctx, c, *p, (const int*)d_samples_all, H_all, (const int*)d_best, &r));
+  *n_inliers = r.n_inliers;
+  *n_coeffs = r.n_coeffs;
+  for (int i = 0; i < r.n_coeffs; ++i) coeffs[i] = r.coeffs[i];
+  int status = PITT_OK;
+  if (inliers && r.n_inliers > 0) {
+    if (cap < r.n_inliers) status = fail(ctx, PITT_ERR_CAPACITY, "inlier buffer too small");
+    else {
+      PITT_CUDA(ctx, cudaMemcpyAsync(inliers, r.d_inliers, (size_t)r.n_inliers * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  timer.finish();
+  if (info) {
+    *info = r.info;
+    info->device_ms = ctx->last_ms;
+  }
+  return status;
+}
+
 int pitt_sac_select(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params* p, const float* coeffs,
                     int32_t* inliers, int cap, int* n_inliers) {
   if (!ctx) return PITT_ERR_CUDA;

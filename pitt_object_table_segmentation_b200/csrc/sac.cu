@@ -1169,6 +1169,90 @@ static bool ransac_scan(RansacScan& sc, const pitt_sac_params& p, int n, int S, 
 int lm_refine(pitt_ctx* ctx, const pitt_cloud* c, int model, const float* d_model, const int* d_idx, const int* d_n_idx,
               int n_idx_host, float* d_refined, int* d_lm_info /*[2]: status,nfev*/);
 
+// refinement of the winning model + final inlier selection (SACSegmentation::segment after computeModel):
+// d_model[8] -> d_refined[8], *d_n_model = inliers of the unrefined model, *d_n_final / d_inl = final set
+int sac_finish(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& p, const Limits& L, const ScoreParams& sp,
+               const float* d_model, float* d_refined, int* d_n_model, int* d_n_final, int* d_lm, int* d_inl) {
+  const int model = p.model;
+  if (model == PITT_MODEL_PLANE) {
+    if (p.optimize) {
+      PITT_TRY(plane_refine(ctx, c, d_model, nullptr, nullptr, L, sp, d_refined, d_n_model));
+      PITT_TRY(sac_select(ctx, c, model, d_refined, L, sp, d_inl, d_n_final));
+    } else {
+      PITT_TRY(sac_select(ctx, c, model, d_model, L, sp, d_inl, d_n_final));
+      PITT_CUDA(ctx, cudaMemcpyAsync(d_refined, d_model, 8 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+      PITT_CUDA(ctx, cudaMemcpyAsync(d_n_model, d_n_final, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  } else {
+    PITT_TRY(sac_select(ctx, c, model, d_model, L, sp, d_inl, d_n_model));
+    if (p.optimize) {
+      PITT_TRY(lm_refine(ctx, c, model, d_model, d_inl, d_n_model, -1, d_refined, d_lm));
+      PITT_TRY(sac_select(ctx, c, model, d_refined, L, sp, d_inl, d_n_final));
+    } else {
+      PITT_CUDA(ctx, cudaMemcpyAsync(d_refined, d_model, 8 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+      PITT_CUDA(ctx, cudaMemcpyAsync(d_n_final, d_n_model, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  }
+  return PITT_OK;
+}
+
+// winner of a hypothesis split: the sample of hypothesis best[0] (all ranks hold the whole sample table)
+__global__ void pick_sample_kernel(const int* __restrict__ samples, int S, int H, const int* __restrict__ best, int* __restrict__ one) {
+  const int h = best[0];
+  if (threadIdx.x < S) one[threadIdx.x] = (h >= 0 && h < H) ? samples[(size_t)h * S + threadIdx.x] : 0;
+}
+int sac_finish_from_winner(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& p, const int* d_samples_all, int H_all,
+                           const int* d_best, SacDeviceResult* out) {
+  const int model = p.model;
+  const int S = sample_size(model);
+  memset(&out->info, 0, sizeof(out->info));
+  out->info.best_hypothesis = -1;
+  out->n_inliers = 0;
+  out->n_coeffs = 0;
+  out->d_inliers = nullptr;
+  if (c->n < S) return PITT_OK;
+  const Limits L = limits_for(p);
+  const ScoreParams sp = score_params_for(p, L);
+  int* d_ints = nullptr;
+  float* d_flt = nullptr;
+  int* d_one = nullptr;
+  int* d_inl = nullptr;
+  HypRec* d_rec = nullptr;
+  uint8_t* d_flag = nullptr;
+  PITT_TRY(arena_alloc(ctx, 8, &d_ints));
+  PITT_TRY(arena_alloc(ctx, 16, &d_flt));
+  PITT_TRY(arena_alloc(ctx, 4, &d_one));
+  PITT_TRY(arena_alloc(ctx, (size_t)c->n, &d_inl));
+  PITT_TRY(arena_alloc(ctx, 1, &d_rec));
+  PITT_TRY(arena_alloc(ctx, 4, &d_flag));
+  PITT_CUDA(ctx, cudaMemsetAsync(d_ints, 0, 8 * sizeof(int), ctx->stream));
+  pick_sample_kernel<<<1, 32, 0, ctx->stream>>>(d_samples_all, S, H_all, d_best, d_one);
+  PITT_LAUNCH_CHECK(ctx, "pick_sample_kernel");
+  PITT_TRY(sac_estimate(ctx, c, model, d_one, 1, L, d_rec, d_flt, d_flag));  // d_flt[0..8) = model coefficients
+  PITT_TRY(sac_finish(ctx, c, p, L, sp, d_flt, d_flt + 8, d_ints + 2, d_ints + 3, d_ints + 4, d_inl));
+  PITT_TRY(pinned_reserve(ctx, 256));
+  int* h_ints = (int*)ctx->h_pin;
+  float* h_flt = (float*)((char*)ctx->h_pin + 64);
+  int* h_best = (int*)((char*)ctx->h_pin + 192);
+  PITT_CUDA(ctx, cudaMemcpyAsync(h_ints, d_ints, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PITT_CUDA(ctx, cudaMemcpyAsync(h_flt, d_flt, 16 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  PITT_CUDA(ctx, cudaMemcpyAsync(h_best, d_best, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (h_best[0] < 0 || h_best[0] >= H_all) return PITT_OK;
+  const int NC = coeff_count(model);
+  out->info.best_hypothesis = h_best[0];
+  out->info.best_count = h_best[1];
+  out->info.n_inliers_model = h_ints[2];
+  out->info.lm_info = h_ints[4];
+  out->info.lm_nfev = h_ints[5];
+  for (int i = 0; i < 8; ++i) out->info.model_coeffs[i] = i < NC ? h_flt[i] : 0.0f;
+  for (int i = 0; i < 8; ++i) out->coeffs[i] = i < NC ? h_flt[8 + i] : 0.0f;
+  out->n_coeffs = NC;
+  out->n_inliers = h_ints[3];
+  out->d_inliers = d_inl;
+  return PITT_OK;
+}
+
 // ------------------------------------------------------------------ seg.segment()
 int sac_segment_impl(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& p, SacDeviceResult* out) {
   const int model = p.model;
@@ -1292,26 +1376,7 @@ int sac_segment_impl(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& 
   }
 
   const int NC = coeff_count(model);
-  // refinement + final inliers
-  if (model == PITT_MODEL_PLANE) {
-    if (p.optimize) {
-      PITT_TRY(plane_refine(ctx, c, d_model, nullptr, nullptr, L, sp, d_refined, d_n_model));
-      PITT_TRY(sac_select(ctx, c, model, d_refined, L, sp, d_inl, d_n_final));
-    } else {
-      PITT_TRY(sac_select(ctx, c, model, d_model, L, sp, d_inl, d_n_final));
-      PITT_CUDA(ctx, cudaMemcpyAsync(d_refined, d_model, 8 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
-      PITT_CUDA(ctx, cudaMemcpyAsync(d_n_model, d_n_final, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
-    }
-  } else {
-    PITT_TRY(sac_select(ctx, c, model, d_model, L, sp, d_inl, d_n_model));
-    if (p.optimize) {
-      PITT_TRY(lm_refine(ctx, c, model, d_model, d_inl, d_n_model, -1, d_refined, d_lm));
-      PITT_TRY(sac_select(ctx, c, model, d_refined, L, sp, d_inl, d_n_final));
-    } else {
-      PITT_CUDA(ctx, cudaMemcpyAsync(d_refined, d_model, 8 * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
-      PITT_CUDA(ctx, cudaMemcpyAsync(d_n_final, d_n_model, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
-    }
-  }
+  PITT_TRY(sac_finish(ctx, c, p, L, sp, d_model, d_refined, d_n_model, d_n_final, d_lm, d_inl));
   // one small D2H for the scalars
   PITT_TRY(pinned_reserve(ctx, 256));
   int* h_ints = (int*)ctx->h_pin;

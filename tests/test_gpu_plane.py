@@ -215,3 +215,34 @@ def test_filter_kernel_non_finite_points_fall_back(ctx, oracle):
     c_cpu = oracle.sac_score(xyz, None, p, samples)[0]
     assert np.array_equal(c_gpu, c_cpu)
     assert pairs == 0  # exact kernel took over
+
+
+def test_hypothesis_split_finish_matches_single_segment(ctx, oracle):
+    """config 5 pattern on one GPU: two 'ranks' score halves of the sample stream, the counts are
+    concatenated (the all-gather), earliest arg-max, pitt_sac_finish_device == one seg.segment() over all"""
+    import torch
+    xyz = scenes.plane_outlier_cloud(50000, seed=101)
+    cloud = ctx.stage(xyz)
+    H = 1200
+    samples = oracle.pcl_sample_stream(xyz, A.MODEL_PLANE, 2 * H)
+    p = pkg.default_support_sac_params()
+    p.sampler, p.stop, p.max_iterations = A.SAMPLER_REPLAY, A.STOP_ALL_H, 2 * H
+    p.replay_samples = samples.ctypes.data_as(A.i32p)
+    p.replay_count = 2 * H
+    want = oracle.sac_segment(xyz, None, p)
+    dev = torch.device("cuda", 0)
+    d_all_samples = torch.from_numpy(samples).to(dev)
+    d_counts = torch.zeros(2 * H, dtype=torch.int32, device=dev)
+    for r in range(2):
+        part = d_all_samples[r * H:(r + 1) * H].contiguous()
+        torch.cuda.synchronize()  # torch's stream and the ctx stream are independent
+        ctx.sac_score_device(cloud, p, part.data_ptr(), H, d_counts[r * H:].data_ptr())
+        ctx.synchronize()
+    d_best = torch.zeros(2, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    ctx.argmax_counts_device(d_counts.data_ptr(), 2 * H, d_best.data_ptr())
+    got = ctx.sac_finish_device(cloud, p, d_all_samples.data_ptr(), 2 * H, d_best.data_ptr(), want_inliers=True)
+    assert got["info"].best_hypothesis == want["info"].best_hypothesis
+    assert got["info"].best_count == want["info"].best_count
+    assert np.array_equal(got["inliers"], want["inliers"])
+    assert np.array_equal(got["coeffs"], want["coeffs"])

@@ -320,7 +320,7 @@ static int score_common(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_param
   const ScoreParams sp = score_params_for(*p, L);
   HypRec* d_recs = nullptr;
   PITT_TRY(arena_alloc(ctx, (size_t)H, &d_recs));
-  PITT_TRY(sac_estimate(ctx, c, p->model, d_samples, H, L, d_recs, d_coeffs8, d_flags));
+  PITT_TRY(sac_estimate(ctx, c, p->model, d_samples, H, L, sp, d_recs, d_coeffs8, d_flags));
   PITT_TRY(sac_score(ctx, c, p->model, d_recs, H, sp, d_counts));
   return PITT_OK;
 }

@@ -20,7 +20,7 @@ namespace pitt {
 // =====================================================================================
 template <int MODEL>
 __global__ void estimate_kernel(const float4* __restrict__ xyz, const float4* __restrict__ nrm,
-                                const int* __restrict__ samples, int H, Limits L, HypRec* __restrict__ recs,
+                                const int* __restrict__ samples, int H, Limits L, ScoreParams sp, HypRec* __restrict__ recs,
                                 float* __restrict__ coeffs8, uint8_t* __restrict__ flags) {
   int h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= H) return;
@@ -38,7 +38,7 @@ __global__ void estimate_kernel(const float4* __restrict__ xyz, const float4* __
   else ok = estimate_cone(xyz, nrm, s, L, mc);
   bool valid = ok && model_valid<MODEL>(L, mc);
   HypRec r;
-  make_rec<MODEL>(mc, valid, r);
+  make_rec<MODEL>(mc, valid, sp, r);
   recs[h] = r;
   if (coeffs8) {
 #pragma unroll
@@ -49,12 +49,12 @@ __global__ void estimate_kernel(const float4* __restrict__ xyz, const float4* __
 
 // coefficients (device, 8 floats) -> one scoring record (isModelValid applied)
 template <int MODEL>
-__global__ void prep_rec_kernel(const float* __restrict__ coeffs, Limits L, HypRec* __restrict__ rec) {
+__global__ void prep_rec_kernel(const float* __restrict__ coeffs, Limits L, ScoreParams sp, HypRec* __restrict__ rec) {
   float mc[8];
   for (int i = 0; i < 8; ++i) mc[i] = coeffs[i];
   bool valid = model_valid<MODEL>(L, mc);
   HypRec r;
-  make_rec<MODEL>(mc, valid, r);
+  make_rec<MODEL>(mc, valid, sp, r);
   *rec = r;
 }
 
@@ -797,21 +797,21 @@ ScoreParams score_params_for(const pitt_sac_params& p, const Limits& L) {
   } while (0)
 
 template <int MODEL>
-static int launch_estimate(pitt_ctx* ctx, const pitt_cloud* c, const int* d_samples, int H, const Limits& L,
+static int launch_estimate(pitt_ctx* ctx, const pitt_cloud* c, const int* d_samples, int H, const Limits& L, const ScoreParams& sp,
                            HypRec* d_recs, float* d_coeffs8, uint8_t* d_flags) {
-  estimate_kernel<MODEL><<<cdiv(H, 128), 128, 0, ctx->stream>>>(c->d_xyz, c->d_nrm, d_samples, H, L, d_recs, d_coeffs8, d_flags);
+  estimate_kernel<MODEL><<<cdiv(H, 128), 128, 0, ctx->stream>>>(c->d_xyz, c->d_nrm, d_samples, H, L, sp, d_recs, d_coeffs8, d_flags);
   PITT_LAUNCH_CHECK(ctx, "estimate_kernel");
   return PITT_OK;
 }
 
-int sac_estimate(pitt_ctx* ctx, const pitt_cloud* c, int model, const int* d_samples, int H, const Limits& L,
+int sac_estimate(pitt_ctx* ctx, const pitt_cloud* c, int model, const int* d_samples, int H, const Limits& L, const ScoreParams& sp,
                  HypRec* d_recs, float* d_coeffs8, uint8_t* d_flags) {
   if (H <= 0) return PITT_OK;
   switch (model) {
-    case PITT_MODEL_PLANE: return launch_estimate<PITT_MODEL_PLANE>(ctx, c, d_samples, H, L, d_recs, d_coeffs8, d_flags);
-    case PITT_MODEL_SPHERE: return launch_estimate<PITT_MODEL_SPHERE>(ctx, c, d_samples, H, L, d_recs, d_coeffs8, d_flags);
-    case PITT_MODEL_CYLINDER: return launch_estimate<PITT_MODEL_CYLINDER>(ctx, c, d_samples, H, L, d_recs, d_coeffs8, d_flags);
-    default: return launch_estimate<PITT_MODEL_CONE>(ctx, c, d_samples, H, L, d_recs, d_coeffs8, d_flags);
+    case PITT_MODEL_PLANE: return launch_estimate<PITT_MODEL_PLANE>(ctx, c, d_samples, H, L, sp, d_recs, d_coeffs8, d_flags);
+    case PITT_MODEL_SPHERE: return launch_estimate<PITT_MODEL_SPHERE>(ctx, c, d_samples, H, L, sp, d_recs, d_coeffs8, d_flags);
+    case PITT_MODEL_CYLINDER: return launch_estimate<PITT_MODEL_CYLINDER>(ctx, c, d_samples, H, L, sp, d_recs, d_coeffs8, d_flags);
+    default: return launch_estimate<PITT_MODEL_CONE>(ctx, c, d_samples, H, L, sp, d_recs, d_coeffs8, d_flags);
   }
 }
 
@@ -953,19 +953,19 @@ int sac_select(pitt_ctx* ctx, const pitt_cloud* c, int model, const float* d_coe
   PITT_TRY(arena_alloc(ctx, 1, &d_rec));
   switch (model) {
     case PITT_MODEL_PLANE:
-      prep_rec_kernel<PITT_MODEL_PLANE><<<1, 1, 0, ctx->stream>>>(d_coeffs, L, d_rec);
+      prep_rec_kernel<PITT_MODEL_PLANE><<<1, 1, 0, ctx->stream>>>(d_coeffs, L, sp, d_rec);
       PITT_LAUNCH_CHECK(ctx, "prep_rec_kernel");
       return launch_select<PITT_MODEL_PLANE>(ctx, c, d_rec, sp, d_out, d_total);
     case PITT_MODEL_SPHERE:
-      prep_rec_kernel<PITT_MODEL_SPHERE><<<1, 1, 0, ctx->stream>>>(d_coeffs, L, d_rec);
+      prep_rec_kernel<PITT_MODEL_SPHERE><<<1, 1, 0, ctx->stream>>>(d_coeffs, L, sp, d_rec);
       PITT_LAUNCH_CHECK(ctx, "prep_rec_kernel");
       return launch_select<PITT_MODEL_SPHERE>(ctx, c, d_rec, sp, d_out, d_total);
     case PITT_MODEL_CYLINDER:
-      prep_rec_kernel<PITT_MODEL_CYLINDER><<<1, 1, 0, ctx->stream>>>(d_coeffs, L, d_rec);
+      prep_rec_kernel<PITT_MODEL_CYLINDER><<<1, 1, 0, ctx->stream>>>(d_coeffs, L, sp, d_rec);
       PITT_LAUNCH_CHECK(ctx, "prep_rec_kernel");
       return launch_select<PITT_MODEL_CYLINDER>(ctx, c, d_rec, sp, d_out, d_total);
     default:
-      prep_rec_kernel<PITT_MODEL_CONE><<<1, 1, 0, ctx->stream>>>(d_coeffs, L, d_rec);
+      prep_rec_kernel<PITT_MODEL_CONE><<<1, 1, 0, ctx->stream>>>(d_coeffs, L, sp, d_rec);
       PITT_LAUNCH_CHECK(ctx, "prep_rec_kernel");
       return launch_select<PITT_MODEL_CONE>(ctx, c, d_rec, sp, d_out, d_total);
   }
@@ -980,7 +980,7 @@ int plane_refine(pitt_ctx* ctx, const pitt_cloud* c, const float* d_model, const
   HypRec* d_rec = nullptr;
   if (!d_idx) {
     PITT_TRY(arena_alloc(ctx, 1, &d_rec));
-    prep_rec_kernel<PITT_MODEL_PLANE><<<1, 1, 0, ctx->stream>>>(d_model, L, d_rec);
+    prep_rec_kernel<PITT_MODEL_PLANE><<<1, 1, 0, ctx->stream>>>(d_model, L, sp, d_rec);
     PITT_LAUNCH_CHECK(ctx, "prep_rec_kernel");
   }
   plane_sums_kernel<<<REF_BLOCKS, REF_TPB, 0, ctx->stream>>>(c->d_xyz, c->n, d_rec, d_idx, d_n_idx, sp, d_partial);
@@ -1228,7 +1228,7 @@ int sac_finish_from_winner(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_pa
   PITT_CUDA(ctx, cudaMemsetAsync(d_ints, 0, 8 * sizeof(int), ctx->stream));
   pick_sample_kernel<<<1, 32, 0, ctx->stream>>>(d_samples_all, S, H_all, d_best, d_one);
   PITT_LAUNCH_CHECK(ctx, "pick_sample_kernel");
-  PITT_TRY(sac_estimate(ctx, c, model, d_one, 1, L, d_rec, d_flt, d_flag));  // d_flt[0..8) = model coefficients
+  PITT_TRY(sac_estimate(ctx, c, model, d_one, 1, L, sp, d_rec, d_flt, d_flag));  // d_flt[0..8) = model coefficients
   PITT_TRY(sac_finish(ctx, c, p, L, sp, d_flt, d_flt + 8, d_ints + 2, d_ints + 3, d_ints + 4, d_inl));
   PITT_TRY(pinned_reserve(ctx, 256));
   int* h_ints = (int*)ctx->h_pin;
@@ -1331,7 +1331,7 @@ int sac_segment_impl(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& 
       memcpy(ctx->h_pin, h_samples.data(), (size_t)H_have * S * sizeof(int));
       PITT_CUDA(ctx, cudaMemcpyAsync(d_samples, ctx->h_pin, (size_t)H_have * S * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     }
-    PITT_TRY(sac_estimate(ctx, c, model, d_samples, H_have, L, d_recs, d_coeffs8, d_flags));
+    PITT_TRY(sac_estimate(ctx, c, model, d_samples, H_have, L, sp, d_recs, d_coeffs8, d_flags));
     PITT_TRY(sac_score(ctx, c, model, d_recs, H_have, sp, d_counts));
     out->info.hypotheses += H_have;
     if (all_h) {

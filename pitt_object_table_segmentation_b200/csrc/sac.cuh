@@ -31,7 +31,7 @@ class PclSampleStream {
 Limits limits_for(const pitt_sac_params& p);
 ScoreParams score_params_for(const pitt_sac_params& p, const Limits& L);
 
-int sac_estimate(pitt_ctx* ctx, const pitt_cloud* c, int model, const int* d_samples, int H, const Limits& L,
+int sac_estimate(pitt_ctx* ctx, const pitt_cloud* c, int model, const int* d_samples, int H, const Limits& L, const ScoreParams& sp,
                  HypRec* d_recs, float* d_coeffs8, uint8_t* d_flags);
 int sac_score(pitt_ctx* ctx, const pitt_cloud* c, int model, const HypRec* d_recs, int H, const ScoreParams& sp,
               int* d_counts);

@@ -14,10 +14,12 @@ namespace pitt {
 
 // One scored hypothesis, 64 B, laid out for LDS.128 broadcasts.
 //  plane    v[0..3]  = a,b,c,d
-//  sphere   v[0..3]  = cx,cy,cz,r
-//  cylinder v[0..2]  = point on axis, v[4..6] = axis dir, v[3] = r, v[7] = pt.dir, v[8] = 1/dir.dir
+//  sphere   v[0..3]  = cx,cy,cz,r, v[4..5] = [D_lo, D_hi]: the squared distances that are inliers (exact)
+//  cylinder v[0..2]  = point on axis, v[4..6] = axis dir, v[3] = r, v[7] = pt.dir, v[8] = 1/dir.dir,
+//           v[9..10] = (lo2, hi2): squared axis distances outside (lo2, hi2) are certain outliers
 //  cone     v[0..2]  = apex, v[4..6] = axis dir, v[3] = opening angle, v[7] = apex.dir,
-//           v[8] = 1/dir.dir, v[9] = sin(angle), v[10] = cos(angle), v[12..13] = tan(angle) as double
+//           v[8] = 1/dir.dir, v[9] = sin(angle), v[10] = cos(angle), v[11] = float tan(angle),
+//           v[12..13] = tan(angle) as double, v[14] = T: |axis distance - cone radius| >= T is a certain outlier
 // An invalid hypothesis is all NaN: every comparison is false, so it scores 0.
 struct __align__(16) HypRec {
   float v[16];
@@ -168,9 +170,41 @@ __device__ inline bool model_valid(const Limits& L, const float* mc) {
   return true;
 }
 
+// ---- exact reformulation of the sphere predicate |fl(fl(sqrt(d2)) - r)| < thr_up as D_lo <= d2 <= D_hi.
+// fl(s - r) is non-decreasing in s and fl(sqrt(d2)) is non-decreasing in d2 (both correctly rounded), so the
+// inlier set is an interval of floats in d2; its end points are found by bisection on the float ordering
+// (non-negative floats order like their bit patterns). No square root is left in the scoring loop.
+__device__ __forceinline__ float ord_f(unsigned u) { return __uint_as_float(u); }
+template <typename Pred>  // smallest non-negative finite-or-inf float (as bits, <= 0x7f800000) with pred true, pred monotone false->true
+__device__ inline unsigned first_true_bits(Pred pred) {
+  unsigned lo = 0u, hi = 0x7f800001u;  // hi = "none"
+  while (lo < hi) {
+    unsigned mid = lo + ((hi - lo) >> 1);
+    if (pred(ord_f(mid))) hi = mid;
+    else lo = mid + 1;
+  }
+  return lo;
+}
+__device__ inline void sphere_interval(float r, float thr_up, float& d_lo, float& d_hi) {
+  d_lo = CUDART_INF_F;
+  d_hi = -CUDART_INF_F;  // empty
+  if (!(r == r) || !(thr_up > 0.0f)) return;
+  // s range: -thr_up < fl(s - r) < thr_up
+  const unsigned s_min_b = first_true_bits([&](float sv) { return (sv - r) > -thr_up; });
+  const unsigned s_end_b = first_true_bits([&](float sv) { return (sv - r) >= thr_up; });  // first s that is NOT an inlier any more
+  if (s_min_b > 0x7f800000u || s_end_b == 0u || s_min_b >= s_end_b) return;
+  const float s_min = ord_f(s_min_b), s_max = ord_f(s_end_b - 1u);
+  // d2 range: s_min <= fl(sqrt(d2)) <= s_max
+  const unsigned d_lo_b = first_true_bits([&](float dv) { return sqrtf(dv) >= s_min; });
+  const unsigned d_end_b = first_true_bits([&](float dv) { return sqrtf(dv) > s_max; });
+  if (d_lo_b > 0x7f800000u || d_end_b == 0u || d_lo_b >= d_end_b) return;
+  d_lo = ord_f(d_lo_b);
+  d_hi = ord_f(d_end_b - 1u);
+}
+
 // coefficients (PCL order) -> scoring record with the per-hypothesis terms PCL hoists out of the loop
 template <int MODEL>
-__device__ inline void make_rec(const float* mc, bool ok, HypRec& r) {
+__device__ inline void make_rec(const float* mc, bool ok, const ScoreParams& sp, HypRec& r) {
   if (!ok) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) r.v[i] = CUDART_NAN_F;
@@ -180,18 +214,39 @@ __device__ inline void make_rec(const float* mc, bool ok, HypRec& r) {
   for (int i = 0; i < 16; ++i) r.v[i] = 0.0f;
   if (MODEL == PITT_MODEL_PLANE || MODEL == PITT_MODEL_SPHERE) {
     r.v[0] = mc[0]; r.v[1] = mc[1]; r.v[2] = mc[2]; r.v[3] = mc[3];
+    if (MODEL == PITT_MODEL_SPHERE) sphere_interval(mc[3], sp.thr_up, r.v[4], r.v[5]);
   } else {
     f3 p0 = mk3(mc[0], mc[1], mc[2]), dir = mk3(mc[3], mc[4], mc[5]);
     r.v[0] = p0.x; r.v[1] = p0.y; r.v[2] = p0.z; r.v[3] = mc[6];
     r.v[4] = dir.x; r.v[5] = dir.y; r.v[6] = dir.z;
     r.v[7] = dot0(p0, dir);
     r.v[8] = 1.0f / dot0(dir, dir);
+    // Certain-outlier bound shared by cylinder and cone: the weighted score is
+    // w*d_normal + (1-w)*d_euclid >= (1-w)*d_euclid (d_normal in [0, pi/2], 0 <= w <= 1), so
+    // d_euclid >= T = (thr + band)/(1-w) can never be an inlier, whatever the normal says.
+    float T = CUDART_INF_F;  // no pre-filter unless 0 <= w < 1
+    if (sp.w >= 0.0 && sp.w < 0.999) T = (float)((sp.thr + (double)sp.band) / (1.0 - sp.w) * (1.0 + 1e-5)) + 1e-30f;
+    if (MODEL == PITT_MODEL_CYLINDER) {
+      // d_euclid = |sqrt(sq) - r| >= T  <=>  sq >= (r+T)^2  or  (r-T > 0 and sq <= (r-T)^2); margins of 1e-5 relative
+      const float rr = mc[6];
+      float lo2 = -1.0f, hi2 = CUDART_INF_F;  // (lo2, hi2) = the interval that still needs the full evaluation
+      if (T < CUDART_INF_F && rr == rr) {
+        const float up = rr + T;
+        hi2 = up > 0.0f ? up * up * (1.0f + 1e-5f) : -1.0f;  // up <= 0: every point is a certain outlier
+        const float dn = rr - T;
+        if (dn > 0.0f) lo2 = dn * dn * (1.0f - 1e-5f);
+      }
+      r.v[9] = lo2;
+      r.v[10] = hi2;
+    }
     if (MODEL == PITT_MODEL_CONE) {
       r.v[9] = sinf_d(mc[6]);
       r.v[10] = cosf_d(mc[6]);
       double t = tan((double)mc[6]);
+      r.v[11] = (float)t;
       r.v[12] = __int_as_float(__double2loint(t));
       r.v[13] = __int_as_float(__double2hiint(t));
+      r.v[14] = T;
     }
   }
 }
@@ -217,12 +272,22 @@ struct RecRegs<PITT_MODEL_PLANE> {
 
 template <>
 struct RecRegs<PITT_MODEL_SPHERE> {
-  float cx, cy, cz, r;
+  float cx, cy, cz, r, d_lo, d_hi;
   __device__ __forceinline__ void load(const HypRec* rec) {
     float4 q = *reinterpret_cast<const float4*>(rec->v);
+    float2 iv = *reinterpret_cast<const float2*>(rec->v + 4);
     cx = q.x; cy = q.y; cz = q.z; r = q.w;
+    d_lo = iv.x; d_hi = iv.y;
   }
-  __device__ __forceinline__ bool inlier(f3 p, f3, const ScoreParams& sp) const {
+  // PCL: fabs(sqrtf(dx*dx + dy*dy + dz*dz) - r) < thr, evaluated as the equivalent interval test on the
+  // squared distance (sphere_interval above): same float d2, no sqrt, bit-identical predicate
+  __device__ __forceinline__ bool inlier(f3 p, f3, const ScoreParams&) const {
+    float dx = p.x - cx, dy = p.y - cy, dz = p.z - cz;
+    float d2 = dx * dx + dy * dy + dz * dz;
+    return d2 >= d_lo && d2 <= d_hi;
+  }
+  // the literal PCL sequence (kept for the parity test of the interval reformulation)
+  __device__ __forceinline__ bool inlier_literal(f3 p, const ScoreParams& sp) const {
     float dx = p.x - cx, dy = p.y - cy, dz = p.z - cz;
     float d = sqrtf(dx * dx + dy * dy + dz * dz) - r;
     return fabsf(d) < sp.thr_up;
@@ -238,14 +303,14 @@ __device__ __forceinline__ bool weighted_inlier(double d_normal, double d_euclid
 template <>
 struct RecRegs<PITT_MODEL_CYLINDER> {
   f3 p0, dir;
-  float r, ptdotdir, dirdotdir;
+  float r, ptdotdir, dirdotdir, lo2, hi2;
   __device__ __forceinline__ void load(const HypRec* rec) {
     float4 q0 = *reinterpret_cast<const float4*>(rec->v);
     float4 q1 = *reinterpret_cast<const float4*>(rec->v + 4);
     float4 q2 = *reinterpret_cast<const float4*>(rec->v + 8);
     p0 = mk3(q0.x, q0.y, q0.z); r = q0.w;
     dir = mk3(q1.x, q1.y, q1.z); ptdotdir = q1.w;
-    dirdotdir = q2.x;
+    dirdotdir = q2.x; lo2 = q2.y; hi2 = q2.z;
   }
   // exact PCL sequence (float geometry, double sqrt/acos/weighting)
   __device__ __forceinline__ bool inlier_exact(f3 pt, f3 n, const ScoreParams& sp) const {
@@ -260,6 +325,9 @@ struct RecRegs<PITT_MODEL_CYLINDER> {
   // are re-evaluated with the exact sequence, so the predicate is identical to inlier_exact.
   __device__ __forceinline__ bool inlier(f3 pt, f3 n, const ScoreParams& sp) const {
     float sq = sqr_pt_line(pt, p0, dir);
+    // certain outlier by the euclidean term alone (make_rec): the large majority of the evaluations of
+    // a random hypothesis stop here, before any sqrt / rsqrt / acos. NaN falls through and ends false.
+    if (sq >= hi2 || sq <= lo2) return false;
     float de = fabsf(sqrtf(sq) - r);
     float k = (dot0(pt, dir) - ptdotdir) * dirdotdir;
     f3 d = pt - (p0 + k * dir);
@@ -278,7 +346,7 @@ struct RecRegs<PITT_MODEL_CYLINDER> {
 template <>
 struct RecRegs<PITT_MODEL_CONE> {
   f3 apex, dir;
-  float angle, apexdotdir, dirdotdir, sin_a, cos_a;
+  float angle, apexdotdir, dirdotdir, sin_a, cos_a, tan_f, T;
   double tan_a;
   __device__ __forceinline__ void load(const HypRec* rec) {
     float4 q0 = *reinterpret_cast<const float4*>(rec->v);
@@ -287,8 +355,9 @@ struct RecRegs<PITT_MODEL_CONE> {
     float4 q3 = *reinterpret_cast<const float4*>(rec->v + 12);
     apex = mk3(q0.x, q0.y, q0.z); angle = q0.w;
     dir = mk3(q1.x, q1.y, q1.z); apexdotdir = q1.w;
-    dirdotdir = q2.x; sin_a = q2.y; cos_a = q2.z;
+    dirdotdir = q2.x; sin_a = q2.y; cos_a = q2.z; tan_f = q2.w;
     tan_a = __hiloint2double(__float_as_int(q3.y), __float_as_int(q3.x));
+    T = q3.z;
   }
   __device__ __forceinline__ bool inlier_exact(f3 pt, f3 n, const ScoreParams& sp) const {
     float k = (dot0(pt, dir) - apexdotdir) * dirdotdir;
@@ -307,13 +376,23 @@ struct RecRegs<PITT_MODEL_CONE> {
     f3 proj = apex + k * dir;
     f3 pp = pt - proj;
     f3 height = apex - proj;
-    float hn = nrm0(height);
+    const float hn2 = sqn0(height);
+    const float sq = sqr_pt_line(pt, apex, dir);
+    {
+      // certain outlier by the euclidean term alone: |sqrt(sq) - tan*|height|| >= T (make_rec). Squares are
+      // compared so that only one approximate rsqrt is needed; 1e-5 relative margins cover the float roundings.
+      const float ar = tan_f * (hn2 * rsqrtf(hn2));  // ~ tan * |height|; hn2 == 0 gives NaN and falls through
+      const float up = fabsf(ar) + T, dn = fabsf(ar) - T;
+      if (sq >= up * up * (1.0f + 1e-5f)) return false;
+      if (dn > 0.0f && sq <= dn * dn * (1.0f - 1e-5f)) return false;
+    }
+    float hn = sqrtf(hn2);
     float ppn = nrm0(pp);
     float actual_r = (float)tan_a * hn;
     // cone normal = sin * unit(height) + cos * unit(pp)
     float ih = 1.0f / hn, ip = 1.0f / ppn;
     f3 cn = (sin_a * ih) * height + (cos_a * ip) * pp;
-    float de = fabsf(sqrtf(sqr_pt_line(pt, apex, dir)) - actual_r);
+    float de = fabsf(sqrtf(sq) - actual_r);
     float cosang = dot0(n, cn) * rsqrtf(sqn0(n) * sqn0(cn));
     cosang = fminf(1.0f, fmaxf(-1.0f, cosang));
     float dn = acosf(cosang);

@@ -95,3 +95,75 @@ def test_cylinder_needs_normals(ctx):
     cloud = ctx.stage(xyz)
     with pytest.raises(pkg.PittError):
         ctx.sac_segment(cloud, pkg.default_sac_params(A.MODEL_CYLINDER))
+
+
+def _nudge(v, steps, rng):
+    """move each float32 of v by a random number of ulps in [-steps, steps]"""
+    out = v.astype(np.float32).copy()
+    k = rng.integers(-steps, steps + 1, out.shape)
+    for _ in range(steps):
+        up = k > 0
+        dn = k < 0
+        out = np.where(up, np.nextafter(out, np.float32(np.inf)), np.where(dn, np.nextafter(out, np.float32(-np.inf)), out)).astype(np.float32)
+        k = k - np.sign(k)
+    return out
+
+
+@pytest.mark.parametrize("thr,radius", [(0.007, 0.06), (0.007, 0.004), (1e-4, 0.5), (0.02, 3.0)])
+def test_sphere_interval_predicate_on_the_threshold(ctx, oracle, thr, radius):
+    """the sphere predicate is evaluated as an interval test on the squared distance; points whose distance to
+    the centre sits within a few ulps of r - thr, r + thr (and of r itself) must classify exactly like PCL"""
+    rng = np.random.default_rng(17)
+    n = 8192
+    c = np.array([0.3, -0.2, 0.9], np.float32)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    which = rng.integers(0, 3, n)
+    rad = np.where(which == 0, radius - thr, np.where(which == 1, radius + thr, radius))
+    rad = np.maximum(rad, 0.0)
+    xyz = np.ones((n, 4), np.float32)
+    xyz[:, :3] = _nudge((c + d * rad[:, None]).astype(np.float32), 3, rng)
+    # four exact points of the sphere first: hypothesis 0 = the true sphere (centre c up to rounding)
+    base = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [-1, 0, 0]], np.float32) * np.float32(radius) + c
+    xyz[:4, :3] = base
+    cloud = ctx.stage(xyz)
+    p = pkg.default_sac_params(A.MODEL_SPHERE)
+    p.distance_threshold = thr
+    p.radius_min, p.radius_max = 0.0, 100.0
+    samples = np.vstack([np.array([[0, 1, 2, 3]], np.int32), rng.integers(0, n, (255, 4)).astype(np.int32)])
+    c_gpu, co_gpu, v_gpu = ctx.sac_score(cloud, p, samples)
+    c_cpu, co_cpu, v_cpu = oracle.sac_score(xyz, None, p, samples)
+    assert np.array_equal(v_gpu, v_cpu)
+    assert np.array_equal(c_gpu, c_cpu)
+    inl_g = ctx.sac_select(cloud, p, co_cpu[0, :4])
+    inl_c = oracle.sac_select(xyz, None, p, co_cpu[0, :4])
+    assert np.array_equal(inl_g, inl_c)
+    if radius > thr:
+        assert 0 < len(inl_c) < n  # the construction really straddles the threshold
+
+
+@pytest.mark.parametrize("model,w", [(A.MODEL_CYLINDER, 0.001), (A.MODEL_CONE, 0.0006), (A.MODEL_CYLINDER, 0.0), (A.MODEL_CONE, 0.3),
+                                     (A.MODEL_CYLINDER, 1.0)])
+def test_cylinder_cone_prefilter_near_threshold(ctx, oracle, model, w):
+    """shell of points at axis distances spread tightly around r +- thr/(1-w): the certain-outlier pre-filter
+    (euclidean term only) must never change a count"""
+    rng = np.random.default_rng(23)
+    kind = KINDS[model]
+    xyz, nrm, truth = _cluster(kind, 4000, 31, oracle)
+    # radial jitter concentrated at the decision boundary of the true model
+    p = pkg.default_sac_params(model)
+    p.normal_distance_weight = w
+    thr = p.distance_threshold
+    centre = xyz[:, :3].mean(axis=0)
+    scale = 1.0 + rng.choice([-1.0, 1.0], len(xyz))[:, None] * (thr / max(1.0 - w, 0.05)) * rng.uniform(0.98, 1.02, (len(xyz), 1)) / 0.05
+    xyz2 = xyz.copy()
+    xyz2[:, :3] = (centre + (xyz[:, :3] - centre) * scale).astype(np.float32)
+    xyz2[:2000] = xyz[:2000]  # keep half of the true surface so that good hypotheses exist
+    nrm2 = oracle.estimate_normals(xyz2, 50, (0.0, 0.0, 0.0))
+    cloud = ctx.stage(xyz2, normals=nrm2)
+    samples = np.vstack([oracle.pcl_sample_stream(xyz2, model, 300),
+                         rng.integers(0, 2000, (300, A.SAMPLE_SIZE[model])).astype(np.int32)])
+    c_gpu, _, v_gpu = ctx.sac_score(cloud, p, samples)
+    c_cpu, _, v_cpu = oracle.sac_score(xyz2, nrm2, p, samples)
+    assert np.array_equal(v_gpu, v_cpu)
+    assert np.array_equal(c_gpu, c_cpu)

@@ -220,6 +220,27 @@ typedef struct pitt_frame_result {
   double device_ms;
 } pitt_frame_result;
 
+/* Pre-path of depthAcquisition (obj_segmentation.cpp:233-248): fromROSMsg -> PCManager::downSampling
+ * (VoxelGrid, pc_manager.cpp:55-67, leaf 0.01 :19) -> deep filter (deep_filter_srv.cpp:27-58, threshold
+ * 3.0 :21) -> pcl::transformPointCloud with the camera->world matrix (:248). The arm filter (:245,
+ * robot specific CropBox on live tf) is not part of it. */
+typedef struct pitt_prefilter_params {
+  float leaf[3];              /* VoxelGrid leaf size; any value <= 0 skips the down-sampling */
+  int32_t apply_deep_filter;  /* 1: drop z != z and z > deep_threshold (the "closer" cloud of the service) */
+  float deep_threshold;       /* < 0 -> 3.0 (srvm::getServiceFloatParameter) */
+  int32_t apply_transform;    /* 1: x' = m00 x + m01 y + m02 z + m03, ... (float, unfused, left to right) */
+  float transform[16];        /* row major 4x4 */
+} pitt_prefilter_params;
+
+typedef struct pitt_prefilter_info {
+  int32_t n_input;        /* points in the message */
+  int32_t n_voxel;        /* after the VoxelGrid (= n_input when skipped) */
+  int32_t n_closer;       /* deep filter: kept */
+  int32_t n_further;      /* deep filter: z > threshold */
+  int32_t voxel_overflow; /* 1: leaf too small for the extent (PCL warns and returns the input unchanged) */
+  float used_deep_threshold;
+} pitt_prefilter_info;
+
 /* ------------------------------------------------------------------ opaque handles */
 typedef struct pitt_ctx pitt_ctx;
 typedef struct pitt_cloud pitt_cloud; /* cloud staged in HBM as float4 {x,y,z,1} (+ normals float4) */
@@ -246,6 +267,7 @@ void pitt_default_support_sac_params(pitt_sac_params* out);        /* supportsâ€
 void pitt_default_support_params(pitt_support_params* out);        /* all negative â†’ defaults */
 void pitt_default_cluster_params(pitt_cluster_params* out);
 void pitt_default_frame_params(pitt_frame_params* out);
+void pitt_default_prefilter_params(pitt_prefilter_params* out);    /* leaf 0.01, deep 3.0, identity transform */
 
 /* ------------------------------------------------------------------ staging (K0; replaces fromROSMsg, pc_manager.cpp:85-94) */
 /* xyz: host pointer to n points, x,y,z float32 at byte offsets 0,4,8 of each stride_bytes record
@@ -262,6 +284,18 @@ int pitt_cloud_has_normals(const pitt_cloud* cloud);
 const void* pitt_cloud_device_points(const pitt_cloud* cloud);
 const void* pitt_cloud_device_normals(const pitt_cloud* cloud);
 void pitt_release_cloud(pitt_ctx* ctx, pitt_cloud* cloud);
+
+/* ------------------------------------------------------------------ pre-path (SURVEY Â§8f rows 1-3) */
+/* data: the PointCloud2 payload (host): n_points records of point_step bytes with x,y,z float32 at byte
+ * offsets 0,4,8 (PointXYZ, PointXYZRGB, ...). One H2D copy, then everything on the device. The result
+ * is a staged cloud in the world frame, ready for pitt_segment_frame. info is nullable. */
+int pitt_prefilter_cloud(pitt_ctx* ctx, const void* data, int point_step, int n_points,
+                         const pitt_prefilter_params* params, pitt_cloud** out, pitt_prefilter_info* info);
+/* the same on a cloud that is already staged (device to device) */
+int pitt_prefilter_staged(pitt_ctx* ctx, const pitt_cloud* in, const pitt_prefilter_params* params,
+                          pitt_cloud** out, pitt_prefilter_info* info);
+/* copy a staged cloud back as n x float4 (tests, debugging) */
+int pitt_get_points(pitt_ctx* ctx, const pitt_cloud* cloud, float* out4);
 
 /* ------------------------------------------------------------------ a1: PCManager::estimateNormal (pc_manager.cpp:68-78) */
 /* k nearest neighbours (query included, ties by lower index) â†’ 3x3 covariance â†’ eigen33 â†’
@@ -340,6 +374,11 @@ int pitt_segment_frame(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_frame_
 int pitt_segment_frames_batched(pitt_ctx* const* ctxs, int n_ctx, const void* const* frames, const int* n_points,
                                 int stride_bytes, int n_frames, const pitt_frame_params* params,
                                 pitt_frame_result* results);
+/* The same stream from raw sensor messages: every frame first goes through pitt_prefilter_cloud
+ * (prefilter may be NULL = frames are already world-frame clouds). */
+int pitt_segment_raw_frames_batched(pitt_ctx* const* ctxs, int n_ctx, const void* const* frames, const int* n_points,
+                                    int stride_bytes, int n_frames, const pitt_prefilter_params* prefilter,
+                                    const pitt_frame_params* params, pitt_frame_result* results);
 
 /* ------------------------------------------------------------------ measurement helpers */
 /* FP32 pipe micro-benchmark used as the roofline denominator of the scoring kernels:

@@ -45,6 +45,10 @@ int orc_primitive_service(const float* xyz4, const float* nrm4, int n, const pit
 int orc_select_primitive(int64_t plane_inl, int64_t sphere_inl, int64_t cylinder_inl, int64_t cone_inl, float prio);
 int orc_segment_frame(const float* xyz4, int n, const pitt_frame_params* params, pitt_frame_result* result);
 
+/* pre-path: VoxelGrid + deep filter + transformPointCloud; data = PointCloud2 payload (x,y,z @ 0,4,8) */
+int orc_prefilter(const void* data, int point_step, int n_points, const pitt_prefilter_params* p, float* out4, int cap,
+                  int* n_out, pitt_prefilter_info* info);
+
 /* defaults shared with the product header semantics (reference launch parameters) */
 void orc_default_sac_params(int model, pitt_sac_params* out);
 void orc_default_support_sac_params(pitt_sac_params* out);

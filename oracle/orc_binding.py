@@ -236,3 +236,16 @@ def segment_frame(xyz4, params, shapes_cap=64):
     st = lib().orc_segment_frame(_fp(xyz4), xyz4.shape[0], C.byref(params), C.byref(b.res))
     assert st == 0, st
     return b.to_python()
+
+
+def prefilter(raw, params):
+    """orc_prefilter: raw = (n, point_step/4) float32 payload; returns (world cloud n x 4, info dict)"""
+    raw = np.ascontiguousarray(raw, np.float32)
+    n = raw.shape[0]
+    out = np.zeros((max(n, 1), 4), np.float32)
+    n_out = C.c_int(0)
+    info = A.PrefilterInfo()
+    st = lib().orc_prefilter(C.c_void_p(raw.ctypes.data), raw.shape[1] * 4, n, C.byref(params), _fp(out), max(n, 1),
+                             C.byref(n_out), C.byref(info))
+    assert st == 0, st
+    return out[: n_out.value].copy(), {k: getattr(info, k) for k, _ in A.PrefilterInfo._fields_}

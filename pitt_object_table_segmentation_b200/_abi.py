@@ -114,6 +114,16 @@ class FrameParams(C.Structure):
     ]
 
 
+class PrefilterParams(C.Structure):
+    _fields_ = [("leaf", f32 * 3), ("apply_deep_filter", i32), ("deep_threshold", f32), ("apply_transform", i32),
+                ("transform", f32 * 16)]
+
+
+class PrefilterInfo(C.Structure):
+    _fields_ = [("n_input", i32), ("n_voxel", i32), ("n_closer", i32), ("n_further", i32), ("voxel_overflow", i32),
+                ("used_deep_threshold", f32)]
+
+
 class FrameResult(C.Structure):
     _fields_ = [
         ("n_supports", i32), ("n_clusters", i32), ("n_shapes", i32),

@@ -17,7 +17,8 @@ _LIB = None
 # every symbol declared in include/pitt_b200.h
 EXPORTED_SYMBOLS = [
     "pitt_create", "pitt_create_on_stream", "pitt_destroy", "pitt_last_error", "pitt_version", "pitt_device_count",
-    "pitt_synchronize", "pitt_set_workers", "pitt_default_sac_params", "pitt_default_support_sac_params", "pitt_default_support_params",
+    "pitt_synchronize", "pitt_set_workers", "pitt_default_prefilter_params", "pitt_prefilter_cloud",
+    "pitt_prefilter_staged", "pitt_get_points", "pitt_segment_raw_frames_batched", "pitt_default_sac_params", "pitt_default_support_sac_params", "pitt_default_support_params",
     "pitt_default_cluster_params", "pitt_default_frame_params", "pitt_stage_cloud", "pitt_stage_cloud_device",
     "pitt_set_normals", "pitt_cloud_size", "pitt_cloud_has_normals", "pitt_cloud_device_points",
     "pitt_cloud_device_normals", "pitt_release_cloud", "pitt_estimate_normals", "pitt_get_normals", "pitt_knn",
@@ -52,6 +53,10 @@ def load_library():
     lib.pitt_version.restype = C.c_char_p
     lib.pitt_synchronize.argtypes = [vp]
     lib.pitt_set_workers.argtypes = [vp, C.c_int]
+    lib.pitt_prefilter_cloud.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(A.PrefilterParams), C.POINTER(vp),
+                                         C.POINTER(A.PrefilterInfo)]
+    lib.pitt_prefilter_staged.argtypes = [vp, vp, C.POINTER(A.PrefilterParams), C.POINTER(vp), C.POINTER(A.PrefilterInfo)]
+    lib.pitt_get_points.argtypes = [vp, vp, A.f32p]
     lib.pitt_stage_cloud.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]
     lib.pitt_stage_cloud_device.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
     lib.pitt_set_normals.argtypes = [vp, vp, vp, C.c_int]
@@ -224,6 +229,23 @@ class Context:
         self._check(self.lib.pitt_stage_cloud(self.handle, C.c_void_p(ptr), stride, n, C.byref(h)))
         return Cloud(self, h, n)
 
+    def prefilter(self, raw, params=None):
+        """pitt_prefilter_cloud: raw = (n, point_step/4) float32 host array with x,y,z in columns 0..2
+        (a PointCloud2 payload). Returns (Cloud in the world frame, info dict)."""
+        raw = np.ascontiguousarray(raw, np.float32)
+        params = params if params is not None else default_prefilter_params()
+        h = C.c_void_p()
+        info = A.PrefilterInfo()
+        self._check(self.lib.pitt_prefilter_cloud(self.handle, C.c_void_p(raw.ctypes.data), raw.shape[1] * 4, raw.shape[0],
+                                                  C.byref(params), C.byref(h), C.byref(info)))
+        n = self.lib.pitt_cloud_size(h)
+        return Cloud(self, h, n), {k: getattr(info, k) for k, _ in A.PrefilterInfo._fields_}
+
+    def get_points(self, cloud):
+        out = np.zeros((cloud.n, 4), np.float32)
+        self._check(self.lib.pitt_get_points(self.handle, cloud.handle, out.ctypes.data_as(A.f32p)))
+        return out
+
     def stage_device(self, d_ptr, n):
         h = C.c_void_p()
         self._check(self.lib.pitt_stage_cloud_device(self.handle, C.c_void_p(d_ptr), n, C.byref(h)))
@@ -377,7 +399,13 @@ Context.primitive_service = _primitive_service
 Context.segment_frame = _segment_frame
 
 
-def segment_frames_batched(contexts, frames, params=None, shapes_cap=64):
+def default_prefilter_params():
+    p = A.PrefilterParams()
+    load_library().pitt_default_prefilter_params(C.byref(p))
+    return p
+
+
+def segment_frames_batched(contexts, frames, params=None, shapes_cap=64, prefilter=None):
     """pitt_segment_frames_batched: `frames` is a list of (n,4) float32 host arrays (ideally pinned);
     one host thread per context drives its stream. Returns the per-frame result dicts."""
     params = params if params is not None else default_frame_params()
@@ -391,8 +419,9 @@ def segment_frames_batched(contexts, frames, params=None, shapes_cap=64):
     ptrs = (C.c_void_p * n)(*[f.ctypes.data for f in frames])
     counts = np.array([f.shape[0] for f in frames], np.int32)
     ctxs = (C.c_void_p * len(contexts))(*[c.handle for c in contexts])
-    st = lib.pitt_segment_frames_batched(ctxs, len(contexts), ptrs, counts.ctypes.data_as(A.i32p), 16, n,
-                                         C.byref(params), res)
+    stride = int(frames[0].shape[1]) * 4 if n else 16
+    st = lib.pitt_segment_raw_frames_batched(ctxs, len(contexts), ptrs, counts.ctypes.data_as(A.i32p), stride, n,
+                                             C.byref(prefilter) if prefilter is not None else None, C.byref(params), res)
     if st != A.PITT_OK:
         raise PittError(f"pitt_segment_frames_batched status {st}")
     out = []

@@ -216,8 +216,8 @@ static void make_geom(const float mn[3], const float mx[3], float h, GridGeom* g
   *ncells = g->dx * g->dy * g->dz;
 }
 
-int grid_build(pitt_ctx* ctx, const float4* d_xyz, int n, float h, float target_per_cell, GridDev* out) {
-  memset(out, 0, sizeof(*out));
+int cloud_bbox(pitt_ctx* ctx, const float4* d_xyz, int n, float mn[3], float mx[3], int* n_finite) {
+  *n_finite = 0;
   if (n <= 0) return PITT_OK;
   int* d_bb = nullptr;
   PITT_TRY(arena_alloc(ctx, 8, &d_bb));
@@ -228,10 +228,18 @@ int grid_build(pitt_ctx* ctx, const float4* d_xyz, int n, float h, float target_
   int h_bb[8];
   PITT_CUDA(ctx, cudaMemcpyAsync(h_bb, d_bb, 7 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  const int n_finite = h_bb[6];
-  if (n_finite <= 0) return PITT_OK;
-  float mn[3], mx[3];
+  *n_finite = h_bb[6];
   for (int a = 0; a < 3; ++a) { mn[a] = ord2f_host(h_bb[a]); mx[a] = ord2f_host(h_bb[3 + a]); }
+  return PITT_OK;
+}
+
+int grid_build(pitt_ctx* ctx, const float4* d_xyz, int n, float h, float target_per_cell, GridDev* out) {
+  memset(out, 0, sizeof(*out));
+  if (n <= 0) return PITT_OK;
+  int n_finite = 0;
+  float mn[3], mx[3];
+  PITT_TRY(cloud_bbox(ctx, d_xyz, n, mn, mx, &n_finite));
+  if (n_finite <= 0) return PITT_OK;
   const float ext = std::max(std::max(mx[0] - mn[0], mx[1] - mn[1]), std::max(mx[2] - mn[2], 1e-6f));
   GridGeom g;
   int ncells = 0;

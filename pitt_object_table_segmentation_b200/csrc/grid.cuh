@@ -32,6 +32,9 @@ __device__ __forceinline__ int grid_cell(const GridDev& g, float x, float y, flo
 // h <= 0: pick the cell size so that occupied cells hold about `target_per_cell` points.
 int grid_build(pitt_ctx* ctx, const float4* d_xyz, int n, float h, float target_per_cell, GridDev* out);
 
+// minimum / maximum over the finite points (one small D2H + stream sync) and their number
+int cloud_bbox(pitt_ctx* ctx, const float4* d_xyz, int n, float mn[3], float mx[3], int* n_finite);
+
 // exclusive scan of n ints (device, in place), total written to d_total[0] (may be null)
 int device_exclusive_scan(pitt_ctx* ctx, int* d_data, int n, int* d_total);
 // exclusive prefix maximum of n floats in place (element 0 becomes -inf)

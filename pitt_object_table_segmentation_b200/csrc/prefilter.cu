@@ -1,0 +1,289 @@
+// prefilter.cu — the pre-path of depthAcquisition on the device:
+//   fromROSMsg               point_cloud_library/pc_manager.cpp:85-94    -> one strided H2D + pack
+//   PCManager::downSampling  pc_manager.cpp:55-67 (pcl::VoxelGrid, leaf 0.01 :19)
+//   deep filter              segmentation_services/deep_filter_srv.cpp:27-58 (threshold 3.0 :21)
+//   transformPointCloud      obj_segmentation.cpp:248 (camera -> world Matrix4f)
+// VoxelGrid = voxel keys -> stable radix sort of (key, point index) -> segment heads -> one thread per
+// voxel accumulates its points in ascending point index (float, like PCL) -> centroids in ascending voxel
+// index (PCL's output order). The deep filter and the transform are fused into one ordered compaction.
+// The sort is cub::DeviceRadixSort (CUDA toolkit); everything else is hand written.
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <limits>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "grid.cuh"
+#include "pitt_common.cuh"
+
+namespace pitt {
+
+// fromROSMsg: records of `stride` bytes with x,y,z float32 at 0,4,8 -> float4 {x,y,z,1}
+static __global__ void pf_pack_kernel(const unsigned char* __restrict__ src, int stride, int n, float4* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = reinterpret_cast<const float*>(src + (size_t)i * stride);
+  dst[i] = make_float4(p[0], p[1], p[2], 1.0f);
+}
+
+struct VoxGeom {
+  float inv0, inv1, inv2;
+  int min0, min1, min2;
+  int mul1, mul2;
+};
+__global__ void __launch_bounds__(256) voxel_key_kernel(const float4* __restrict__ xyz, int n, VoxGeom g, unsigned* __restrict__ key,
+                                                        int* __restrict__ idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = __ldg(xyz + i);
+  unsigned k = 0xffffffffu;  // non-finite points sort to the end and are cut off
+  if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+    // static_cast<int> (floor (x * inverse_leaf_size_[0]) - static_cast<float> (min_b_[0]))
+    const int i0 = (int)(floorf(p.x * g.inv0) - (float)g.min0);
+    const int i1 = (int)(floorf(p.y * g.inv1) - (float)g.min1);
+    const int i2 = (int)(floorf(p.z * g.inv2) - (float)g.min2);
+    k = (unsigned)(i0 + i1 * g.mul1 + i2 * g.mul2);
+  }
+  key[i] = k;
+  idx[i] = i;
+}
+__global__ void __launch_bounds__(256) voxel_heads_kernel(const unsigned* __restrict__ key_sorted, int m, int* __restrict__ head) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  head[i] = (i == 0 || key_sorted[i] != key_sorted[i - 1]) ? 1 : 0;
+}
+// rank[i] = exclusive scan of head = voxel number of sorted entry i; the thread of a segment head walks its segment
+__global__ void __launch_bounds__(128) voxel_centroid_kernel(const float4* __restrict__ xyz, const unsigned* __restrict__ key_sorted,
+                                                             const int* __restrict__ idx_sorted, const int* __restrict__ rank, int m,
+                                                             float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const unsigned k = key_sorted[i];
+  if (i > 0 && key_sorted[i - 1] == k) return;  // not a head
+  float4 p = __ldg(xyz + idx_sorted[i]);
+  float cx = p.x, cy = p.y, cz = p.z;
+  int j = i + 1;
+  for (; j < m && key_sorted[j] == k; ++j) {
+    p = __ldg(xyz + idx_sorted[j]);
+    cx += p.x; cy += p.y; cz += p.z;
+  }
+  const float cnt = (float)(j - i);
+  out[rank[i]] = make_float4(cx / cnt, cy / cnt, cz / cnt, 1.0f);
+}
+// deep filter: 1 = kept ("closer"), further counted on the side
+__global__ void __launch_bounds__(256) deep_flag_kernel(const float4* __restrict__ xyz, int n, float th, int apply, int* __restrict__ keep,
+                                                        int* __restrict__ n_further) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int far_ = 0;
+  if (i < n) {
+    const float z = xyz[i].z;
+    int k = 1;
+    if (apply) {
+      k = 0;
+      if (z == z) {
+        if (z > th) far_ = 1;
+        else k = 1;
+      }
+    }
+    keep[i] = k;
+  }
+  far_ = __reduce_add_sync(0xffffffffu, far_);
+  if ((threadIdx.x & 31) == 0 && far_) atomicAdd(n_further, far_);
+}
+struct Xform {
+  float m[12];
+  int apply;
+};
+__global__ void __launch_bounds__(256) compact_transform_kernel(const float4* __restrict__ src, const int* __restrict__ keep_flag,
+                                                                const int* __restrict__ pos, int n, Xform T, float4* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !keep_flag[i]) return;
+  float4 p = src[i];
+  if (T.apply && isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+    const float x = p.x, y = p.y, z = p.z;  // -fmad=false: every product and sum rounds once, left to right
+    p.x = T.m[0] * x + T.m[1] * y + T.m[2] * z + T.m[3];
+    p.y = T.m[4] * x + T.m[5] * y + T.m[6] * z + T.m[7];
+    p.z = T.m[8] * x + T.m[9] * y + T.m[10] * z + T.m[11];
+  }
+  p.w = 1.0f;
+  dst[pos[i]] = p;
+}
+
+// d_in: n float4 on the device. Writes a new pool-allocated cloud.
+static int prefilter_impl(pitt_ctx* ctx, const float4* d_in, int n, const pitt_prefilter_params& P, pitt_cloud** out,
+                          pitt_prefilter_info* info) {
+  pitt_prefilter_info I;
+  memset(&I, 0, sizeof(I));
+  I.n_input = n;
+  I.used_deep_threshold = P.deep_threshold >= 0.0f ? P.deep_threshold : 3.000f;
+  const float4* d_cur = d_in;
+  int n_cur = n;
+  // ---------------- VoxelGrid
+  if (n > 0 && P.leaf[0] > 0.0f && P.leaf[1] > 0.0f && P.leaf[2] > 0.0f) {
+    float mn[3], mx[3];
+    int n_finite = 0;
+    PITT_TRY(cloud_bbox(ctx, d_in, n, mn, mx, &n_finite));
+    if (n_finite == 0) {
+      n_cur = 0;
+    } else {
+      float inv[3];
+      for (int a = 0; a < 3; ++a) inv[a] = 1.0f / P.leaf[a];
+      const int64_t dx = (int64_t)((mx[0] - mn[0]) * inv[0]) + 1, dy = (int64_t)((mx[1] - mn[1]) * inv[1]) + 1,
+                    dz = (int64_t)((mx[2] - mn[2]) * inv[2]) + 1;
+      if (dx * dy * dz > (int64_t)std::numeric_limits<int32_t>::max()) {
+        I.voxel_overflow = 1;  // PCL: "Leaf size is too small for the input dataset": output = input
+      } else {
+        VoxGeom g;
+        int min_b[3], max_b[3], div_b[3];
+        for (int a = 0; a < 3; ++a) {
+          min_b[a] = (int)floorf(mn[a] * inv[a]);
+          max_b[a] = (int)floorf(mx[a] * inv[a]);
+          div_b[a] = max_b[a] - min_b[a] + 1;
+        }
+        g.inv0 = inv[0]; g.inv1 = inv[1]; g.inv2 = inv[2];
+        g.min0 = min_b[0]; g.min1 = min_b[1]; g.min2 = min_b[2];
+        g.mul1 = div_b[0]; g.mul2 = div_b[0] * div_b[1];
+        unsigned *d_key = nullptr, *d_key2 = nullptr;
+        int *d_idx = nullptr, *d_idx2 = nullptr, *d_head = nullptr, *d_total = nullptr;
+        float4* d_vox = nullptr;
+        PITT_TRY(arena_alloc(ctx, (size_t)n, &d_key));
+        PITT_TRY(arena_alloc(ctx, (size_t)n, &d_key2));
+        PITT_TRY(arena_alloc(ctx, (size_t)n, &d_idx));
+        PITT_TRY(arena_alloc(ctx, (size_t)n, &d_idx2));
+        PITT_TRY(arena_alloc(ctx, (size_t)n, &d_head));
+        PITT_TRY(arena_alloc(ctx, 1, &d_total));
+        PITT_TRY(arena_alloc(ctx, (size_t)n_finite, &d_vox));
+        voxel_key_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_in, n, g, d_key, d_idx);
+        ctx->launches++;
+        // stable LSD radix sort on the voxel key only: equal keys keep ascending point index
+        int end_bit = 32;
+        {
+          const int64_t max_key = (int64_t)div_b[0] * div_b[1] * div_b[2];
+          if (n_finite == n) {  // no 0xffffffff sentinels: only the bits a key can have
+            end_bit = 1;
+            while (end_bit < 32 && ((int64_t)1 << end_bit) < max_key) ++end_bit;
+          }
+        }
+        size_t tmp_bytes = 0;
+        PITT_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_key, d_key2, d_idx, d_idx2, n, 0, end_bit, ctx->stream));
+        unsigned char* d_tmp = nullptr;
+        PITT_TRY(arena_alloc(ctx, tmp_bytes + 16, &d_tmp));
+        PITT_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_key, d_key2, d_idx, d_idx2, n, 0, end_bit, ctx->stream));
+        ctx->launches += 4;  // cub: histogram + onesweep passes
+        const int m = n_finite;  // the finite points come first
+        voxel_heads_kernel<<<cdiv(m, 256), 256, 0, ctx->stream>>>(d_key2, m, d_head);
+        ctx->launches++;
+        PITT_TRY(device_exclusive_scan(ctx, d_head, m, d_total));
+        voxel_centroid_kernel<<<cdiv(m, 128), 128, 0, ctx->stream>>>(d_in, d_key2, d_idx2, d_head, m, d_vox);
+        ctx->launches++;
+        int n_vox = 0;
+        PITT_CUDA(ctx, cudaMemcpyAsync(&n_vox, d_total, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        d_cur = d_vox;
+        n_cur = n_vox;
+      }
+    }
+  }
+  I.n_voxel = n_cur;
+  // ---------------- deep filter + transform, fused into one ordered compaction
+  pitt_cloud* c = new pitt_cloud();
+  int n_out = n_cur;
+  if (n_cur > 0) {
+    int *d_keep = nullptr, *d_pos = nullptr, *d_cnt = nullptr;
+    PITT_TRY(arena_alloc(ctx, (size_t)n_cur, &d_keep));
+    PITT_TRY(arena_alloc(ctx, (size_t)n_cur, &d_pos));
+    PITT_TRY(arena_alloc(ctx, 2, &d_cnt));
+    PITT_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int), ctx->stream));
+    deep_flag_kernel<<<cdiv(n_cur, 256), 256, 0, ctx->stream>>>(d_cur, n_cur, I.used_deep_threshold, P.apply_deep_filter ? 1 : 0, d_keep, d_cnt + 1);
+    ctx->launches++;
+    PITT_CUDA(ctx, cudaMemcpyAsync(d_pos, d_keep, (size_t)n_cur * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    PITT_TRY(device_exclusive_scan(ctx, d_pos, n_cur, d_cnt));
+    int h_cnt[2] = {0, 0};
+    PITT_CUDA(ctx, cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, ctx->stream));
+    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    n_out = h_cnt[0];
+    I.n_further = h_cnt[1];
+    if (n_out > 0) {
+      int st = pool_alloc(ctx, (size_t)n_out * sizeof(float4), (void**)&c->d_xyz);
+      if (st != PITT_OK) { delete c; return st; }
+      Xform T;
+      for (int k = 0; k < 12; ++k) T.m[k] = P.transform[k];
+      T.apply = P.apply_transform ? 1 : 0;
+      compact_transform_kernel<<<cdiv(n_cur, 256), 256, 0, ctx->stream>>>(d_cur, d_keep, d_pos, n_cur, T, c->d_xyz);
+      ctx->launches++;
+    }
+  }
+  c->n = n_out;
+  I.n_closer = n_out;
+  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { pool_free(ctx, c->d_xyz, (size_t)c->n * sizeof(float4)); delete c; return fail(ctx, PITT_ERR_CUDA, "prefilter kernels", e); }
+  *out = c;
+  if (info) *info = I;
+  return PITT_OK;
+}
+
+}  // namespace pitt
+
+using namespace pitt;
+
+extern "C" {
+
+void pitt_default_prefilter_params(pitt_prefilter_params* p) {
+  memset(p, 0, sizeof(*p));
+  p->leaf[0] = p->leaf[1] = p->leaf[2] = 0.01f;  // PCManager::DEFAULT_DOWSEAMPLIG_RATE, pc_manager.cpp:19
+  p->apply_deep_filter = 1;
+  p->deep_threshold = -1.0f;                      // -> 3.0, deep_filter_srv.cpp:21
+  p->apply_transform = 1;
+  p->transform[0] = p->transform[5] = p->transform[10] = p->transform[15] = 1.0f;
+}
+
+int pitt_prefilter_cloud(pitt_ctx* ctx, const void* data, int point_step, int n_points, const pitt_prefilter_params* params,
+                         pitt_cloud** out, pitt_prefilter_info* info) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!params || !out || n_points < 0 || (n_points > 0 && !data) || point_step < 12 || (point_step & 3))
+    return fail(ctx, PITT_ERR_INVALID, "pitt_prefilter_cloud arguments (point_step >= 12, multiple of 4)");
+  cudaSetDevice(ctx->device);
+  CallTimer timer(ctx);
+  float4* d_in = nullptr;
+  if (n_points > 0) {
+    PITT_TRY(arena_alloc(ctx, (size_t)n_points, &d_in));
+    if (point_step == 16) {
+      PITT_CUDA(ctx, cudaMemcpyAsync(d_in, data, (size_t)n_points * 16, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+      unsigned char* d_raw = nullptr;
+      PITT_TRY(arena_alloc(ctx, (size_t)n_points * point_step, &d_raw));
+      PITT_CUDA(ctx, cudaMemcpyAsync(d_raw, data, (size_t)n_points * point_step, cudaMemcpyHostToDevice, ctx->stream));
+      pf_pack_kernel<<<cdiv(n_points, 256), 256, 0, ctx->stream>>>(d_raw, point_step, n_points, d_in);
+      ctx->launches++;
+    }
+  }
+  int st = prefilter_impl(ctx, d_in, n_points, *params, out, info);
+  timer.finish();
+  return st;
+}
+
+int pitt_prefilter_staged(pitt_ctx* ctx, const pitt_cloud* in, const pitt_prefilter_params* params, pitt_cloud** out,
+                          pitt_prefilter_info* info) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!in || !params || !out) return fail(ctx, PITT_ERR_INVALID, "pitt_prefilter_staged arguments");
+  cudaSetDevice(ctx->device);
+  CallTimer timer(ctx);
+  int st = prefilter_impl(ctx, in->d_xyz, in->n, *params, out, info);
+  timer.finish();
+  return st;
+}
+
+int pitt_get_points(pitt_ctx* ctx, const pitt_cloud* c, float* out4) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!c || (c->n > 0 && !out4)) return fail(ctx, PITT_ERR_INVALID, "pitt_get_points arguments");
+  cudaSetDevice(ctx->device);
+  if (c->n > 0) {
+    PITT_CUDA(ctx, cudaMemcpyAsync(out4, c->d_xyz, (size_t)c->n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return PITT_OK;
+}
+
+}  // extern "C"

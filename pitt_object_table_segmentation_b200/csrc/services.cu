@@ -936,8 +936,9 @@ int pitt_segment_frame(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_frame_
   return status;
 }
 
-int pitt_segment_frames_batched(pitt_ctx* const* ctxs, int n_ctx, const void* const* frames, const int* n_points,
-                                int stride_bytes, int n_frames, const pitt_frame_params* params, pitt_frame_result* results) {
+int pitt_segment_raw_frames_batched(pitt_ctx* const* ctxs, int n_ctx, const void* const* frames, const int* n_points,
+                                    int stride_bytes, int n_frames, const pitt_prefilter_params* prefilter,
+                                    const pitt_frame_params* params, pitt_frame_result* results) {
   if (!ctxs || n_ctx <= 0) return PITT_ERR_CUDA;
   for (int t = 0; t < n_ctx; ++t)
     if (!ctxs[t]) return PITT_ERR_CUDA;
@@ -948,7 +949,8 @@ int pitt_segment_frames_batched(pitt_ctx* const* ctxs, int n_ctx, const void* co
     pitt_ctx* ctx = ctxs[t];
     for (int i = t; i < n_frames; i += n_ctx) {
       pitt_cloud* c = nullptr;
-      int st = pitt_stage_cloud(ctx, frames[i], stride_bytes, n_points[i], &c);
+      int st = prefilter ? pitt_prefilter_cloud(ctx, frames[i], stride_bytes, n_points[i], prefilter, &c, nullptr)
+                         : pitt_stage_cloud(ctx, frames[i], stride_bytes, n_points[i], &c);
       if (st == PITT_OK) st = pitt_segment_frame(ctx, c, params, &results[i]);
       if (c) pitt_release_cloud(ctx, c);
       if (st != PITT_OK) {
@@ -962,6 +964,11 @@ int pitt_segment_frames_batched(pitt_ctx* const* ctxs, int n_ctx, const void* co
   worker(0);
   for (auto& th : threads) th.join();
   return first_error.load();
+}
+
+int pitt_segment_frames_batched(pitt_ctx* const* ctxs, int n_ctx, const void* const* frames, const int* n_points,
+                                int stride_bytes, int n_frames, const pitt_frame_params* params, pitt_frame_result* results) {
+  return pitt_segment_raw_frames_batched(ctxs, n_ctx, frames, n_points, stride_bytes, n_frames, nullptr, params, results);
 }
 
 }  // extern "C"

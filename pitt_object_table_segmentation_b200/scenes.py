@@ -127,6 +127,40 @@ def tabletop_frame(seed=12345, width=640, height=480, objects=DEFAULT_OBJECTS, n
     return _pack(xyz)
 
 
+def camera_pose():
+    """(4x4 float32 camera->world matrix, 4x4 world->camera) of the synthetic Kinect of tabletop_frame"""
+    pitch = np.deg2rad(40.0)
+    fwd = np.array([0.0, np.cos(pitch), -np.sin(pitch)])
+    right = np.array([1.0, 0.0, 0.0])
+    down = np.cross(fwd, right)
+    Rm = np.stack([right, down, fwd], 1)
+    o = np.array([0.0, -0.9 / np.tan(pitch) * 0.75, 0.9])
+    M = np.eye(4)
+    M[:3, :3] = Rm
+    M[:3, 3] = o
+    return M.astype(np.float32), np.linalg.inv(M).astype(np.float32)
+
+
+def raw_camera_frame(seed=12345, width=640, height=480, point_step=16, nan_fraction=0.02, far_fraction=0.01, **kw):
+    """What the sensor publishes (the input of depthAcquisition, obj_segmentation.cpp:233): the tabletop
+    frame in the CAMERA frame as a PointCloud2-like payload of `point_step` bytes per point (x,y,z float32
+    at 0,4,8; the rest is colour/padding), with some NaN returns and some points beyond the deep threshold."""
+    world = tabletop_frame(seed=seed, width=width, height=height, **kw)
+    _, w2c = camera_pose()
+    cam = (world[:, :3].astype(np.float64) @ w2c[:3, :3].astype(np.float64).T + w2c[:3, 3].astype(np.float64)).astype(np.float32)
+    r = _rng(seed + 977)
+    n = cam.shape[0]
+    far = r.random(n) < far_fraction
+    cam[far, 2] += np.float32(3.5)  # background returns
+    bad = r.random(n) < nan_fraction
+    cam[bad] = np.nan
+    raw = np.zeros((n, point_step // 4), np.float32)
+    raw[:, :3] = cam
+    if point_step >= 16:
+        raw[:, 3] = 1.0
+    return raw
+
+
 def voxel_downsample(xyz4, leaf=0.01):
     """pcl::VoxelGrid (centroid per occupied voxel, output ordered by voxel index) — host helper used
     to build the *faithful* C1 variant (PCManager::downSampling, pc_manager.cpp:55-67)."""

@@ -255,3 +255,37 @@ def test_defaults_match_reference_launch_parameters(built, oracle):
     assert abs(p.min_angle - np.deg2rad(10)) < 1e-15 and abs(p.max_angle - np.deg2rad(170)) < 1e-15
     c = pkg.default_cluster_params()
     assert (c.tolerance, c.min_rate, c.max_rate, c.min_input_size) == (0.03, 0.01, 0.99, 30)
+
+
+def test_oracle_prefilter_against_numpy_restatement(oracle):
+    """VoxelGrid + deep filter + transform of the oracle vs an independent numpy restatement: same voxels in
+    the same (ascending voxel index) order, centroids equal to float rounding, NaN and far points removed"""
+    import pitt_object_table_segmentation_b200 as pkg
+    from pitt_object_table_segmentation_b200 import scenes
+    raw = scenes.raw_camera_frame(seed=3, width=200, height=150, point_step=32)
+    p = pkg.default_prefilter_params()
+    c2w, _ = scenes.camera_pose()
+    for i, v in enumerate(c2w.ravel()):
+        p.transform[i] = float(v)
+    out, info = oracle.prefilter(raw, p)
+    xyz = raw[:, :3]
+    fin = np.isfinite(xyz).all(1)
+    pts = xyz[fin]
+    inv = np.float32(1.0) / np.float32(0.01)
+    mn = np.floor(pts.min(0) * inv).astype(np.int64)
+    mx = np.floor(pts.max(0) * inv).astype(np.int64)
+    div = mx - mn + 1
+    ijk = (np.floor(pts * inv) - mn.astype(np.float32)).astype(np.int64)
+    key = ijk[:, 0] + ijk[:, 1] * div[0] + ijk[:, 2] * div[0] * div[1]
+    order = np.argsort(key, kind="stable")
+    uniq, start, cnt = np.unique(key[order], return_index=True, return_counts=True)
+    cen = np.add.reduceat(pts[order].astype(np.float64), start, axis=0) / cnt[:, None]
+    keep = ~(cen[:, 2] > 3.0)
+    world = cen[keep] @ c2w[:3, :3].astype(np.float64).T + c2w[:3, 3].astype(np.float64)
+    assert info["n_input"] == len(raw) and info["n_voxel"] == len(uniq)
+    assert info["n_closer"] == int(keep.sum()) and info["n_further"] == int((~keep).sum()) and info["n_further"] > 0
+    assert out.shape == (int(keep.sum()), 4)
+    np.testing.assert_allclose(out[:, :3], world, rtol=0, atol=2e-6)
+    assert np.all(out[:, 3] == 1.0)
+    # the table is back at z = 0 in the world frame
+    assert abs(np.median(out[:, 2])) < 0.01

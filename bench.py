@@ -121,6 +121,32 @@ def cpu_baseline(xyz, samples, seconds_target=12.0, threads=None):
                       f"{dt:.1f} s wall", "checksum": int(sum(int(r.sum()) for r in res))}
 
 
+def cpu_frames_baseline(raws, pf, frames_per_thread=2):
+    """The oracle's pre-path + frame path (the reference's algorithm) on the host: one frame on one core (what
+    the reference's blocking service chain uses) and frame-parallel on all cores."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import orc_binding as O
+    fp = O.default_frame_params()
+
+    def one(raw):
+        world_cloud, _ = O.prefilter(raw, pf)
+        return O.segment_frame(world_cloud, fp)["n_clusters"]
+
+    one(raws[0])
+    t0 = time.perf_counter()
+    for r in raws[:2]:
+        one(r)
+    single = 2 / (time.perf_counter() - t0)
+    threads = os.cpu_count() or 1
+    work = [raws[i % len(raws)] for i in range(threads * frames_per_thread)]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:  # ctypes releases the GIL inside the oracle
+        list(ex.map(one, work))
+    allc = len(work) / (time.perf_counter() - t0)
+    return {"frames_per_s_1core": single, "frames_per_s_all_cores": allc, "cores": threads, "kind": "port",
+            "sample": f"2 frames on 1 core; {len(work)} frames on {threads} threads (oracle = PCL restatement, -O2)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -322,6 +348,34 @@ def main():
                                "cluster, selection; host buffers in (pinned), results out; wall clock, max over ranks"}
         for c in fctxs:
             c.close()
+        # faithful variant (BASELINE configs[0]): the raw 307 200-point camera-frame message (NaN returns, far
+        # background) through fromROSMsg + 1 cm VoxelGrid + deep filter + transform on the device, then the frame path
+        pf = pkg.default_prefilter_params()
+        c2w, _ = scenes.camera_pose()
+        for i, v in enumerate(c2w.ravel()):
+            pf.transform[i] = float(v)
+        raw_uniq = [torch.from_numpy(scenes.raw_camera_frame(seed=lo + i, random_poses=True)).pin_memory() for i in range(min(4, hi - lo))]
+        raws = [raw_uniq[i % len(raw_uniq)].numpy() for i in range(hi - lo)]
+        fctxs = [pkg.Context(local_rank, seed=12345) for _ in range(n_ctx)]
+        for c in fctxs:
+            c.set_workers(args.frame_workers)
+        pkg.segment_frames_batched(fctxs, raws[: 2 * n_ctx], prefilter=pf)
+        barrier()
+        t0 = time.perf_counter()
+        res_f = pkg.segment_frames_batched(fctxs, raws, prefilter=pf)
+        torch.cuda.synchronize()
+        dtf = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dtf, op=dist.ReduceOp.MAX)
+        for c in fctxs:
+            c.close()
+        frames_info["faithful"] = {
+            "frames_per_s": float(len(raws) * world / dtf.item()), "frames": len(raws) * world,
+            "points_per_message": int(raws[0].shape[0]), "shapes_first_frame": [s["tag_name"] for s in res_f[0]["shapes"]],
+            "note": "raw camera-frame PointCloud2 payload in (pinned host), VoxelGrid 0.01 + deep filter 3.0 + transform "
+                    "on the device, then normals/supports/clusters/primitive fits (obj_segmentation.cpp:233-316 order)"}
+        if rank == 0 and not args.no_cpu_baseline:
+            frames_info["faithful"]["cpu_baseline"] = cpu_frames_baseline(raws[:4], pf)
         # single-frame latency: one context, the fits of a frame fanned out to 4 helper streams
         lctx = pkg.Context(local_rank, seed=12345)
         lctx.set_workers(4)

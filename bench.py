@@ -306,18 +306,25 @@ def main():
     peak_ffma = ctx.fp32_peak(0)
     achieved = float(n) * N_HYP * FLOP_PER_EVAL / (k_ms * 1e-3) / 1e12
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_plane_score_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01_plane_filter_traffic.json")
     if os.path.exists(tpath):
         try:
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
+    # The dominant kernel is plane_filter_kernel: 4 FFMA-class operations per evaluation (3 for the dot product, 1 for
+    # s^2 - T) plus the exact re-evaluation of the rare uncertain (hypothesis, tile) pairs. Its pipe is the FP32 FMA pipe,
+    # so the denominator is the FFMA peak measured live (MEASURED_PEAKS.json has no CUDA-core figure); `achieved` counts the
+    # ALGORITHMIC 6 flop per evaluation of SURVEY 8d, not the 8 the kernel executes.
     roofline = {
-        "bound": "fp32", "kernel": "plane_score_kernel", "achieved": achieved, "peak": peak_unfused,
-        "unit": "TFLOP/s", "frac": achieved / peak_unfused, "traffic": traffic,
-        "peak_source": "measured live: pitt_fp32_peak(kind=1) = unfused FMUL+FADD issue rate (bit-exact scoring "
-                       "cannot use FMA); MEASURED_PEAKS.json has no FP32 CUDA-core figure",
-        "peak_ffma_tflops": peak_ffma, "kernel_ms": k_ms, "algorithmic_flop_per_launch": float(n) * N_HYP * 6,
+        "bound": "fp32", "kernel": "plane_filter_kernel", "achieved": achieved, "peak": peak_ffma,
+        "unit": "TFLOP/s", "frac": achieved / peak_ffma, "traffic": traffic,
+        "peak_source": "measured live: pitt_fp32_peak(kind=0) = FFMA issue rate with immediate operands",
+        "frac_of_unfused_peak": achieved / peak_unfused, "peak_unfused_tflops": peak_unfused,
+        "executed_flop_per_eval": 8, "frac_executed_flops": achieved * 8.0 / 6.0 / peak_ffma,
+        "note": "register-file operand bandwidth, not the FMA pipe, bounds 3-register-source FFMA2 streams at ~0.58 of the "
+                "immediate-operand peak (tools/plane_variants.cu, DESIGN.md section 4)",
+        "kernel_ms": k_ms, "algorithmic_flop_per_launch": float(n) * N_HYP * 6,
         "algorithmic_bytes_per_launch": n * 16 + N_HYP * (64 + 4),
     }
 

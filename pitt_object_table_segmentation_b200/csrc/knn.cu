@@ -88,6 +88,7 @@ knn_kernel(GridDev g, const float4* __restrict__ xyz, int k, float vpx, float vp
   const int cx = grid_coord(q.x, g.mnx, g.inv_h, g.dx), cy = grid_coord(q.y, g.mny, g.inv_h, g.dy),
             cz = grid_coord(q.z, g.mnz, g.inv_h, g.dz);
   const int rmax = max(g.dx, max(g.dy, g.dz));
+  const float slack = 2e-3f * g.h;
   for (int r = 0; r <= rmax; ++r) {
     const int z0 = max(cz - r, 0), z1 = min(cz + r, g.dz - 1);
     const int y0 = max(cy - r, 0), y1 = min(cy + r, g.dy - 1);
@@ -100,6 +101,16 @@ knn_kernel(GridDev g, const float4* __restrict__ xyz, int k, float vpx, float vp
           if (!face && abs(x - cx) != r) continue;
           const int cell = (z * g.dy + y) * g.dx + x;
           const int b = g.cell_start[cell], e = g.cell_start[cell + 1];
+          if (b == e) continue;
+          if (size == want) {
+            // prune: no point of this cell can beat the current k-th best if the cell's box is farther away.
+            // Walls are pulled in by slack = 2e-3 h (float rounding of the cell assignment), so the bound is safe.
+            const float lox = g.mnx + (float)x * g.h, loy = g.mny + (float)y * g.h, loz = g.mnz + (float)z * g.h;
+            const float gx = fmaxf(fmaxf(lox - q.x, q.x - (lox + g.h)) - slack, 0.0f);
+            const float gy = fmaxf(fmaxf(loy - q.y, q.y - (loy + g.h)) - slack, 0.0f);
+            const float gz = fmaxf(fmaxf(loz - q.z, q.z - (loz + g.h)) - slack, 0.0f);
+            if ((gx * gx + gy * gy) + gz * gz > top_d) continue;
+          }
           for (int j = b; j < e; ++j) {
             const float4 p = g.sorted[j];
             const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
@@ -358,6 +369,16 @@ __global__ void fill_knn_kernel(int* idx, float* sq, size_t n) {
   }
 }
 
+// occupied cells hold about k / KNN_CELL_DIV points (tuning knob, PITT_KNN_CELL_DIV overrides for experiments)
+static float knn_target_per_cell(int k) {
+  static float div = -1.0f;
+  if (div < 0.0f) {
+    const char* v = getenv("PITT_KNN_CELL_DIV");
+    div = v ? (float)atof(v) : 6.0f;  // measured on B200: 4 -> 1.28 ms, 6 -> 1.17 ms, 12 -> 1.12 ms (307 200 points, k = 50)
+    if (!(div > 0.0f)) div = 6.0f;
+  }
+  return fmaxf(2.0f, (float)k / div);
+}
 static size_t knn_smem_bytes(int k) { return (size_t)k * KNN_TPB * (sizeof(float) + sizeof(int)); }
 // heaps of up to KNN_KMAX entries need 64 KB of dynamic shared memory per CTA: opt in once per device
 static int knn_smem_opt_in(pitt_ctx* ctx) {
@@ -384,7 +405,7 @@ int estimate_normals_impl(pitt_ctx* ctx, const float4* d_xyz, int n, int k, cons
     return PITT_OK;
   }
   GridDev g;
-  PITT_TRY(grid_build(ctx, d_xyz, n, -1.0f, fmaxf(2.0f, (float)k / 4.0f), &g));
+  PITT_TRY(grid_build(ctx, d_xyz, n, -1.0f, knn_target_per_cell(k), &g));
   if (g.n <= 0) return PITT_OK;
   PITT_TRY(knn_smem_opt_in(ctx));
   knn_kernel<1><<<cdiv(g.n, KNN_TPB), KNN_TPB, knn_smem_bytes(k), ctx->stream>>>(g, d_xyz, k, vp[0], vp[1], vp[2], nullptr, nullptr, d_nrm);
@@ -433,7 +454,7 @@ int pitt_knn(pitt_ctx* ctx, const pitt_cloud* c, int k, int32_t* out_idx, float*
       ctx->launches++;
     } else {
       GridDev g;
-      PITT_TRY(grid_build(ctx, c->d_xyz, n, -1.0f, fmaxf(2.0f, (float)k / 4.0f), &g));
+      PITT_TRY(grid_build(ctx, c->d_xyz, n, -1.0f, knn_target_per_cell(k), &g));
       if (g.n > 0) {
         PITT_TRY(knn_smem_opt_in(ctx));
         knn_kernel<0><<<cdiv(g.n, KNN_TPB), KNN_TPB, knn_smem_bytes(k), ctx->stream>>>(g, c->d_xyz, k, 0.f, 0.f, 0.f, d_idx, d_sq, nullptr);

@@ -4,6 +4,8 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -186,6 +188,32 @@ inline void pool_free(pitt_ctx* ctx, void* p, size_t bytes) {
 
 // services.cu: stops the worker threads and destroys the helper contexts
 void workers_destroy(pitt_ctx* ctx);
+
+// PITT_TRACE=1: wall-clock phase log on stderr (development aid; one getenv per process)
+struct TraceScope {
+  const char* name;
+  pitt_ctx* ctx;
+  double t0;
+  static bool enabled() {
+    static int e = -1;
+    if (e < 0) { const char* v = getenv("PITT_TRACE"); e = (v && v[0] == '1') ? 1 : 0; }
+    return e == 1;
+  }
+  static double now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  }
+  TraceScope(pitt_ctx* c, const char* n) : name(n), ctx(c), t0(0) {
+    if (enabled()) t0 = now();
+  }
+  ~TraceScope() {
+    if (enabled()) {
+      cudaStreamSynchronize(ctx->stream);
+      fprintf(stderr, "[pitt trace] %-28s %8.3f ms\n", name, now() - t0);
+    }
+  }
+};
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }

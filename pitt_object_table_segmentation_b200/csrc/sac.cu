@@ -1288,6 +1288,7 @@ int sac_segment_impl(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& 
   int* d_inl = nullptr;
   PITT_TRY(arena_alloc(ctx, (size_t)n, &d_inl));
 
+  TraceScope ts_all(ctx, "  sac_segment_impl");
   PclSampleStream stream(n, model, (c->h_valid ? c->h_xyz.data() : nullptr));
   RansacScan scan;
   std::vector<int> h_samples;
@@ -1376,6 +1377,7 @@ int sac_segment_impl(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& 
   }
 
   const int NC = coeff_count(model);
+  TraceScope ts_fin(ctx, "    refine + select");
   PITT_TRY(sac_finish(ctx, c, p, L, sp, d_model, d_refined, d_n_model, d_n_final, d_lm, d_inl));
   // one small D2H for the scalars
   PITT_TRY(pinned_reserve(ctx, 256));

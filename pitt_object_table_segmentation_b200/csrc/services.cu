@@ -357,8 +357,12 @@ static int find_supports_impl(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt
   for (;;) {
     const int ni = iter.n;
     SacDeviceResult r;
-    PITT_TRY(sac_segment_impl(ctx, &iter, sp, &r));
+    {
+      TraceScope ts(ctx, "supports: plane RANSAC");
+      PITT_TRY(sac_segment_impl(ctx, &iter, sp, &r));
+    }
     (*loop_trips)++;
+    TraceScope ts_rest(ctx, "supports: rest of the trip");
     const int n_inl = r.n_inliers;
     if (n_inl == 0) break;
     else if ((float)ni < (float)n0 * c.minCloudPct) break;
@@ -832,7 +836,10 @@ int pitt_segment_frame(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_frame_
     // computed here because they are part of the reference's request (and of its cost).
     float4* d_nrm = nullptr;
     PITT_TRY(arena_alloc(ctx, (size_t)n, &d_nrm));
-    PITT_TRY(estimate_normals_impl(ctx, cloud->d_xyz, n, fp->normals_k, fp->viewpoint, d_nrm));
+    {
+      TraceScope ts(ctx, "frame: normals");
+      PITT_TRY(estimate_normals_impl(ctx, cloud->d_xyz, n, fp->normals_k, fp->viewpoint, d_nrm));
+    }
     std::vector<SupportDev> sup;
     int trips = 0;
     PITT_TRY(find_supports_impl(ctx, cloud, fp->support, nullptr, &sup, &trips));

@@ -1,0 +1,2 @@
+#pragma once
+#include "pitt_msgs/pitt_msgs.h"

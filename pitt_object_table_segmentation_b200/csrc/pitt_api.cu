@@ -530,4 +530,21 @@ void pitt_debug_plane_filter_stats(int enable, uint64_t* out2) {
   if (out2) { out2[0] = g_plane_filter_stats[0]; out2[1] = g_plane_filter_stats[1]; }
 }
 
+/* test hooks of the tensor-core plane path (plane_tc.cu): statistics of the last call made while collection was enabled
+ * (out[0] = (hypothesis, 128-point segment) pairs scored, out[1] = pairs re-evaluated exactly); raw accumulator dump of
+ * hypothesis block 0 x point tile 0 (128 x 256 floats, then sigma and C); accumulation error bound in units of u m */
+void pitt_debug_plane_tc_stats(int enable, uint64_t* out2) {
+  g_plane_tc_collect_stats = enable;
+  if (out2) { out2[0] = g_plane_tc_stats[0]; out2[1] = g_plane_tc_stats[1]; }
+}
+int pitt_debug_plane_tc_dump(int enable, float* out /*128*256 + 2, nullable*/) {
+  g_plane_tc_dump = enable;
+  if (out && !g_plane_tc_dump_host.empty()) {
+    memcpy(out, g_plane_tc_dump_host.data(), g_plane_tc_dump_host.size() * sizeof(float));
+    return (int)g_plane_tc_dump_host.size();
+  }
+  return 0;
+}
+void pitt_debug_plane_tc_acc_ulps(float ulps) { g_plane_tc_acc_ulps = ulps; }
+
 }  // extern "C"

@@ -1,0 +1,560 @@
+// plane_tc.cu — K3t: plane hypothesis scoring with the dot products on the 5th-generation tensor
+// cores (tcgen05.mma kind::tf32, accumulators in TMEM) and an exact re-evaluation of every
+// evaluation the tensor result cannot decide.
+//
+// Replaces the point loop of pcl::SampleConsensusModelPlane::countWithinDistance reached from
+// seg.segment() at supports_segmentation_srv.cpp:110 and plane_segmentation_srv.cpp:67
+// (SURVEY.md B.3): count_h = #{ i : |fl(a x_i + b y_i + c z_i + d)| < thr }.
+//
+// The exact predicate needs 6 separately rounded FP32 operations per evaluation. Here
+//   (1) every float is split without error into three TF32 pieces v = v1 + v2 + v3 (11 + 11 + 2
+//       significand bits, low 13 bits of each piece are zero, so the tensor core's TF32 read is exact),
+//   (2) three chained 128 x 256 x 8 MMAs sum the 18 products a_i x_j (i + j <= 4) and d1 + d2 + d3;
+//       what is dropped is below 2^-28 m, m = |a x| + |b y| + |c z| + |d|; the only real error is the
+//       tensor core's FP32 accumulation, bounded by TC_ACC_ULPS u m (u = 2^-24; measured,
+//       profiles/r01_plane_tc_numerics.md),
+//   (3) hypotheses are pre-scaled by a power of two sigma, so the accumulator holds s~ = sigma s and
+//       u = sat(C - |s~|), C = fl(sigma thr + 1/2), is exactly 1 for a certain inlier, exactly 0 for a
+//       certain outlier and fractional inside the window | |s~| - sigma thr | < 1/2, which sigma makes
+//       at least 1/0.36 times wider than the error bound of s~,
+//   (4) per (hypothesis, 128-point segment) the epilogue accumulates S1 = sum u and S2 = sum u^2 (3 FMA-pipe
+//       operations per evaluation, no integer work). S1 - S2 <= 0.1 proves that every fractional u is
+//       within 0.115 of 0 or 1, i.e. decided with margin, and that rint(S1) is the exact count;
+//       otherwise the segment is re-evaluated by the whole warp in the exact operation order.
+// Result: counts bit-identical to plane_score_kernel (tests/test_gpu_plane_tc.py).
+//
+// Thread = hypothesis (TMEM lane), columns = points: no cross-lane reduction anywhere. The point
+// chunk is stationary in shared memory (split once per chunk by the epilogue warps), hypothesis
+// blocks stream through a 3-stage cp.async.bulk pipeline, accumulators are double buffered in TMEM
+// (2 x 256 columns), counts for up to 5120 hypotheses are kept in shared memory and flushed once.
+#include <math_constants.h>
+
+#include "sac.cuh"
+
+namespace pitt {
+
+constexpr int TC_M = 128;                       // hypotheses per block (UMMA M, TMEM lanes)
+constexpr int TC_N = 256;                       // points per tile (UMMA N, TMEM columns)
+constexpr int TC_TILES = 2;                     // tiles per point chunk
+constexpr int TC_CHUNK = TC_N * TC_TILES;       // 512 points stationary in shared memory
+constexpr int TC_MMAS = 3;                      // chained MMAs per tile (K = 8 TF32 each)
+constexpr int TC_A_MMA_BYTES = TC_M * 32;       // 4096
+constexpr int TC_A_BLOCK_BYTES = TC_MMAS * TC_A_MMA_BYTES;  // 12288 per hypothesis block
+constexpr int TC_B_MMA_BYTES = TC_N * 32;       // 8192
+constexpr int TC_B_TILE_BYTES = TC_MMAS * TC_B_MMA_BYTES;   // 24576
+constexpr int TC_ASTAGES = 3;
+constexpr int TC_SB = 40;                       // hypothesis blocks per super-block (counts in smem)
+constexpr int TC_EPI_THREADS = 256;             // 8 epilogue warps
+constexpr int TC_THREADS = TC_EPI_THREADS + 64; // + MMA warp + producer warp
+constexpr float TC_ACC_ULPS = 8.0f;             // bound on the tensor core accumulation error, in u m
+constexpr float TC_WINDOW = 0.36f;              // sigma * beta_t must stay below this (see header)
+
+// shared memory carve-up (bytes)
+constexpr int TC_OFF_B = 0;
+constexpr int TC_OFF_A = TC_OFF_B + TC_TILES * TC_B_TILE_BYTES;       // 49152
+constexpr int TC_OFF_RAW = TC_OFF_A + TC_ASTAGES * TC_A_BLOCK_BYTES;  // 86016
+constexpr int TC_OFF_CNT = TC_OFF_RAW + TC_CHUNK * 16;                // 94208
+constexpr int TC_OFF_BAR = TC_OFF_CNT + TC_SB * TC_M * 2 * 4;         // 135168
+constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 16 * 8 + 16;
+
+struct PlaneTcParams {
+  float sigma;   // power of two
+  float C;       // fl(sigma * thr_up + 0.5)
+  float G;       // bound on m the scale was derived for
+  float d_unc;   // scaled d of a hypothesis that must always be re-evaluated (u = 0.5 everywhere)
+  float bx, by, bz;
+  int use;       // 0: cloud not finite or scale out of range -> exact kernel
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, no swizzle: 8-row x 16-byte core matrices; the two K halves of a row group are LBO = 128 B
+// apart, consecutive 8-row groups SBO = 256 B apart (cute::UMMA::SmemDescriptor, version 1).
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
+}
+// cute::UMMA::InstrDescriptor: D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+
+#define TC_R32(r) \
+  "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), \
+  "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),   \
+  "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),  \
+  "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+#define TC_RW32(r) \
+  "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), \
+  "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),   \
+  "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),  \
+  "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+// 32 lanes x 32 consecutive columns: lane i of the warp receives row (lane base + i), columns [col, col + 32)
+__device__ __forceinline__ void tc_ld32(uint32_t (&r)[32], uint32_t taddr) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+      "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : TC_R32(r)
+      : "r"(taddr));
+}
+// wait for the outstanding tcgen05.ld and make the registers "change" here, so no consumer is scheduled earlier
+__device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : TC_RW32(r)::"memory");
+}
+
+// exact TF32 pieces: v = v1 + v2 + v3, each with the low 13 significand bits clear
+__device__ __forceinline__ void tc_split3(float v, float& v1, float& v2, float& v3) {
+  v1 = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  const float r = v - v1;  // exact
+  v2 = __uint_as_float(__float_as_uint(r) & 0xFFFFE000u);
+  v3 = r - v2;             // exact, at most 2 significant bits
+}
+
+// ------------------------------------------------------------------------------------------------
+// set-up kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tc_absmax_kernel(const float4* __restrict__ xyz, int n, unsigned* __restrict__ out3) {
+  unsigned mx = 0, my = 0, mz = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = __ldg(xyz + i);
+    mx = max(mx, __float_as_uint(p.x) & 0x7fffffffu);
+    my = max(my, __float_as_uint(p.y) & 0x7fffffffu);
+    mz = max(mz, __float_as_uint(p.z) & 0x7fffffffu);
+  }
+  mx = __reduce_max_sync(0xffffffffu, mx);
+  my = __reduce_max_sync(0xffffffffu, my);
+  mz = __reduce_max_sync(0xffffffffu, mz);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(out3 + 0, mx);
+    atomicMax(out3 + 1, my);
+    atomicMax(out3 + 2, mz);
+  }
+}
+
+__global__ void tc_params_kernel(const unsigned* __restrict__ absmax, float thr_up, float acc_ulps, PlaneTcParams* __restrict__ out) {
+  PlaneTcParams P;
+  P.use = 0;
+  P.sigma = 1.0f; P.C = 0.0f; P.G = 0.0f; P.d_unc = 0.0f; P.bx = P.by = P.bz = 0.0f;
+  const unsigned ux = absmax[0], uy = absmax[1], uz = absmax[2];
+  if (ux < 0x7f800000u && uy < 0x7f800000u && uz < 0x7f800000u && thr_up > 0.0f && thr_up < 1e18f) {
+    const double X = __uint_as_float(ux), Y = __uint_as_float(uy), Z = __uint_as_float(uz);
+    // a unit-normal hypothesis through a cloud point has |d| <= |a|X+|b|Y+|c|Z <= R, so m <= 2R
+    const double R = sqrt(X * X + Y * Y + Z * Z);
+    const double G = 2.0 * R * (1.0 + 1e-6) + 1e-30;
+    const double u = 5.9604644775390625e-08;  // 2^-24
+    // |s~/sigma - s_exact_order| <= (3.0001 [exact order vs real] + 2^-4 [dropped products] + acc_ulps) u G
+    const double beta = (3.0001 + 0.0625 + (double)acc_ulps) * u * G + 1e-30;
+    const double thr = (double)thr_up;
+    // largest power of two with sigma beta + 2^-23 (sigma thr + 1) <= TC_WINDOW
+    // (the second term covers the rounding of C and of the saturating subtraction)
+    const double per_sigma = beta + thr * 1.1920928955078125e-07;
+    double sigma = 0.0;
+    if (per_sigma > 0.0) {
+      int e = 0;
+      frexp(((double)TC_WINDOW - 1.2e-7) / per_sigma, &e);  // = f 2^e, f in [0.5, 1)
+      sigma = ldexp(1.0, e - 1);
+      while (sigma * per_sigma + 1.2e-7 > (double)TC_WINDOW) sigma *= 0.5;
+    }
+    if (sigma > 1073741824.0) sigma = 1073741824.0;
+    if (sigma >= 1.0 && sigma * G < 1e18 && sigma * thr < 4194304.0) {
+      P.sigma = (float)sigma;
+      P.C = (float)(sigma * thr + 0.5);
+      P.G = (float)G;
+      P.d_unc = (float)(sigma * thr);  // exact: power-of-two scaling of a float
+      P.bx = (float)X; P.by = (float)Y; P.bz = (float)Z;
+      P.use = 1;
+    }
+  }
+  *out = P;
+}
+
+// A-operand image of all hypothesis blocks: per block 3 MMAs x (16 row groups x [8 rows x 16 B | 8 rows x 16 B]).
+//   MMA 0: k0..7 = a1 a2 a3 b1 | b2 b3 c1 c2     (times x3 x2 x1 y3 | y2 y1 z3 z2)
+//   MMA 1: k0..7 = c3 d3 a1 a2 | b1 b2 c1 c2     (times z1 1  x2 x1 | y2 y1 z2 z1)
+//   MMA 2: k0..7 = a1 b1 c1 d1 | d2 0  0  0      (times x1 y1 z1 1  | 1  0  0  0 )
+__global__ void __launch_bounds__(TC_M) tc_hyp_image_kernel(const HypRec* __restrict__ recs, int H, const PlaneTcParams* __restrict__ Pp,
+                                                            float4* __restrict__ image) {
+  const PlaneTcParams P = *Pp;
+  if (!P.use) return;
+  const int h = blockIdx.x * TC_M + threadIdx.x;
+  float a = 0.f, b = 0.f, c = 0.f, d = 1e18f;  // padding / invalid: certain outlier everywhere
+  if (h < H) {
+    const float4 r = __ldg(reinterpret_cast<const float4*>(recs[h].v));
+    if (r.x == r.x) {
+      const float m = (fabsf(r.x) * P.bx + fabsf(r.y) * P.by) + (fabsf(r.z) * P.bz + fabsf(r.w));
+      if (m <= P.G) {
+        a = r.x * P.sigma; b = r.y * P.sigma; c = r.z * P.sigma; d = r.w * P.sigma;
+      } else {
+        d = P.d_unc;  // outside the bound the scale was derived for (or NaN): u = 0.5 everywhere, always re-evaluated
+      }
+    }
+  }
+  float a1, a2, a3, b1, b2, b3, c1, c2, c3, d1, d2, d3;
+  tc_split3(a, a1, a2, a3);
+  tc_split3(b, b1, b2, b3);
+  tc_split3(c, c1, c2, c3);
+  tc_split3(d, d1, d2, d3);
+  const int row = threadIdx.x;
+  float4* blk = image + (size_t)blockIdx.x * (TC_A_BLOCK_BYTES / 16);
+  const int o = (row >> 3) * 16 + (row & 7);  // float4 index inside one MMA image; the second K half is 8 float4 further
+  blk[0 * 256 + o] = make_float4(a1, a2, a3, b1);
+  blk[0 * 256 + o + 8] = make_float4(b2, b3, c1, c2);
+  blk[1 * 256 + o] = make_float4(c3, d3, a1, a2);
+  blk[1 * 256 + o + 8] = make_float4(b1, b2, c1, c2);
+  blk[2 * 256 + o] = make_float4(a1, b1, c1, d1);
+  blk[2 * 256 + o + 8] = make_float4(d2, 0.f, 0.f, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the scoring kernel
+// ------------------------------------------------------------------------------------------------
+// exact count of one hypothesis over len points of shared memory, whole warp (lanes = points)
+__device__ __noinline__ int tc_recount(const float4* pts, int len, const HypRec* rec, float thr_up) {
+  const float4 r = __ldg(reinterpret_cast<const float4*>(rec->v));
+  int c = 0;
+  for (int i = threadIdx.x & 31; i < len; i += 32) {
+    const float4 p = pts[i];
+    const float s = (r.x * p.x + r.z * p.z) + (r.y * p.y + r.w);  // -fmad=false: unfused, Eigen order
+    c += (fabsf(s) < thr_up) ? 1 : 0;
+  }
+  return __reduce_add_sync(0xffffffffu, c);
+}
+
+__device__ __forceinline__ void tc_accumulate32(const uint32_t (&r)[32], float C, float (&S1)[4], float (&S2)[4]) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const float nv = -fabsf(__uint_as_float(r[i]));
+    float u;
+    asm("add.sat.f32 %0, %1, %2;" : "=f"(u) : "f"(nv), "f"(C));
+    S1[i & 3] = __fadd_rn(S1[i & 3], u);
+    S2[i & 3] = __fmaf_rn(u, u, S2[i & 3]);
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict__ recs, int H, const float4* __restrict__ image,
+                int n_hb /*hypothesis blocks*/, int n_chunks, int n_items, float thr_up, const PlaneTcParams* __restrict__ Pp,
+                int* __restrict__ counts, unsigned long long* __restrict__ stats /*nullable: [0] segments, [1] re-evaluated*/,
+                float* __restrict__ dbg /*nullable: s~ of hypothesis block 0 x tile 0 of item 0 (128 x 256)*/) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const PlaneTcParams P = *Pp;
+  if (!P.use) return;  // plane_score_kernel (launched right after) does the work
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t s_base = smem_u32(smem);
+  const uint32_t bar0 = s_base + TC_OFF_BAR;
+  // barriers: [0..2] a_full, [3..5] a_empty, [6..7] tmem_full, [8..9] tmem_empty, [10] b_full
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + TC_OFF_BAR + 16 * 8);
+  float4* s_raw = reinterpret_cast<float4*>(smem + TC_OFF_RAW);
+  int* s_cnt = reinterpret_cast<int*>(smem + TC_OFF_CNT);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TC_ASTAGES; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); }
+    mbar_init(BAR(6), 1); mbar_init(BAR(7), 1);
+    mbar_init(BAR(8), TC_EPI_THREADS / 32); mbar_init(BAR(9), TC_EPI_THREADS / 32);
+    mbar_init(BAR(10), TC_EPI_THREADS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = threadIdx.x; i < TC_SB * TC_M * 2; i += TC_THREADS) s_cnt[i] = 0;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *s_tmem;
+
+  const int n_sb = (n_hb + TC_SB - 1) / TC_SB;
+  (void)n_sb;
+
+  if (warp == 9) {
+    // ===================== producer: hypothesis block images, global -> shared (bulk async copy)
+    if (lane == 0) {
+      uint32_t ac = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int sb = item / n_chunks;
+        const int hb0 = sb * TC_SB, hb1 = min(n_hb, hb0 + TC_SB);
+        for (int hb = hb0; hb < hb1; ++hb, ++ac) {
+          const uint32_t st = ac % TC_ASTAGES, ph = (ac / TC_ASTAGES) & 1u;
+          mbar_wait(BAR(3 + st), ph ^ 1u);
+          mbar_expect_tx(BAR(st), TC_A_BLOCK_BYTES);
+          const float4* src = image + (size_t)hb * (TC_A_BLOCK_BYTES / 16);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(s_base + TC_OFF_A + st * TC_A_BLOCK_BYTES), "l"(src), "r"(TC_A_BLOCK_BYTES), "r"(BAR(st))
+                       : "memory");
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 8) {
+    // ===================== MMA issuer (one thread)
+    if (lane == 0) {
+      uint32_t ac = 0, tc = 0, cc = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++cc) {
+        const int sb = item / n_chunks;
+        const int hb0 = sb * TC_SB, hb1 = min(n_hb, hb0 + TC_SB);
+        mbar_wait(BAR(10), cc & 1u);  // the chunk's B image is in shared memory
+        tc_fence_after();
+        for (int hb = hb0; hb < hb1; ++hb, ++ac) {
+          const uint32_t st = ac % TC_ASTAGES, ph = (ac / TC_ASTAGES) & 1u;
+          mbar_wait(BAR(st), ph);
+          tc_fence_after();
+          const uint32_t a_addr = s_base + TC_OFF_A + st * TC_A_BLOCK_BYTES;
+#pragma unroll
+          for (int t = 0; t < TC_TILES; ++t, ++tc) {
+            const uint32_t buf = tc & 1u, tph = (tc >> 1) & 1u;
+            mbar_wait(BAR(8 + buf), tph ^ 1u);  // the epilogue drained this accumulator
+            tc_fence_after();
+            const uint32_t b_addr = s_base + TC_OFF_B + t * TC_B_TILE_BYTES;
+#pragma unroll
+            for (int j = 0; j < TC_MMAS; ++j)
+              tc_mma_tf32(tmem + buf * TC_N, tc_smem_desc(a_addr + j * TC_A_MMA_BYTES), tc_smem_desc(b_addr + j * TC_B_MMA_BYTES),
+                          TC_IDESC, j > 0 ? 1u : 0u);
+            tc_commit(BAR(6 + buf));
+          }
+          tc_commit(BAR(3 + st));  // the hypothesis stage is free once these MMAs have read it
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps 0..7: split the point chunk, drain TMEM, count
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
+    uint32_t tc = 0;
+    int cur_sb = -1;
+    unsigned long long n_seg = 0, n_redo = 0;
+    auto flush = [&]() {
+      if (cur_sb < 0) return;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = threadIdx.x; i < TC_SB * TC_M; i += TC_EPI_THREADS) {
+        const int h = cur_sb * TC_SB * TC_M + i;
+        const int v = s_cnt[2 * i] + s_cnt[2 * i + 1];
+        s_cnt[2 * i] = 0; s_cnt[2 * i + 1] = 0;
+        if (h < H && v) atomicAdd(&counts[h], v);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    };
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int sb = item / n_chunks, chunk = item % n_chunks;
+      if (sb != cur_sb) { flush(); cur_sb = sb; }
+      const int hb0 = sb * TC_SB, hb1 = min(n_hb, hb0 + TC_SB);
+      const int base = chunk * TC_CHUNK;
+      // every MMA that read the previous B image has completed (its accumulators were consumed);
+      // nobody may still be re-counting from s_raw
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+#pragma unroll
+      for (int k = 0; k < TC_CHUNK / TC_EPI_THREADS; ++k) {
+        const int pi = threadIdx.x + k * TC_EPI_THREADS;  // point of the chunk
+        const int gi = base + pi;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gi < n) p = __ldg(xyz + gi);
+        s_raw[pi] = p;
+        float x1, x2, x3, y1, y2, y3, z1, z2, z3;
+        tc_split3(p.x, x1, x2, x3);
+        tc_split3(p.y, y1, y2, y3);
+        tc_split3(p.z, z1, z2, z3);
+        const int t = pi / TC_N, pr = pi % TC_N;
+        float4* tb = reinterpret_cast<float4*>(smem + TC_OFF_B + t * TC_B_TILE_BYTES);
+        const int o = (pr >> 3) * 16 + (pr & 7);
+        tb[0 * 512 + o] = make_float4(x3, x2, x1, y3);
+        tb[0 * 512 + o + 8] = make_float4(y2, y1, z3, z2);
+        tb[1 * 512 + o] = make_float4(z1, 1.f, x2, x1);
+        tb[1 * 512 + o + 8] = make_float4(y2, y1, z2, z1);
+        tb[2 * 512 + o] = make_float4(x1, y1, z1, 1.f);
+        tb[2 * 512 + o + 8] = make_float4(1.f, 0.f, 0.f, 0.f);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(BAR(10));
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // s_raw visible to every epilogue warp
+
+      for (int hb = hb0; hb < hb1; ++hb) {
+        const int hbl = hb - hb0;
+#pragma unroll 1
+        for (int t = 0; t < TC_TILES; ++t, ++tc) {
+          const uint32_t buf = tc & 1u, tph = (tc >> 1) & 1u;
+          const int seg0 = t * TC_N + half * 128;  // first point of this thread's segment inside the chunk
+          const int len = min(128, n - (base + seg0));
+          mbar_wait(BAR(6 + buf), tph);
+          tc_fence_after();
+          const uint32_t taddr = tmem + t_lane + buf * TC_N + half * 128;
+          float S1[4] = {0.f, 0.f, 0.f, 0.f}, S2[4] = {0.f, 0.f, 0.f, 0.f};
+          uint32_t ra[32], rb[32];
+          tc_ld32(ra, taddr);
+          tc_ld_wait(ra);
+          tc_ld32(rb, taddr + 32);
+          if (dbg && item == 0 && hb == 0 && t == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dbg[row * TC_N + half * 128 + i] = __uint_as_float(ra[i]);
+          }
+          tc_accumulate32(ra, P.C, S1, S2);
+          tc_ld_wait(rb);
+          tc_ld32(ra, taddr + 64);
+          if (dbg && item == 0 && hb == 0 && t == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dbg[row * TC_N + half * 128 + 32 + i] = __uint_as_float(rb[i]);
+          }
+          tc_accumulate32(rb, P.C, S1, S2);
+          tc_ld_wait(ra);
+          tc_ld32(rb, taddr + 96);
+          if (dbg && item == 0 && hb == 0 && t == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dbg[row * TC_N + half * 128 + 64 + i] = __uint_as_float(ra[i]);
+          }
+          tc_accumulate32(ra, P.C, S1, S2);
+          tc_ld_wait(rb);
+          // this warp has read its part of the accumulator: hand the buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(8 + buf));
+          if (dbg && item == 0 && hb == 0 && t == 0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dbg[row * TC_N + half * 128 + 96 + i] = __uint_as_float(rb[i]);
+          }
+          tc_accumulate32(rb, P.C, S1, S2);
+          const float s1 = (S1[0] + S1[1]) + (S1[2] + S1[3]);
+          const float s2 = (S2[0] + S2[1]) + (S2[2] + S2[3]);
+          int c = (int)rintf(s1);
+          const int h = hb * TC_M + row;
+          bool redo;
+          if (len == 128) {
+            redo = (s1 - s2) > 0.1f;
+          } else {
+            redo = (len > 0) && (h < H);  // ragged segment: padding points were scored, count exactly
+            c = 0;
+          }
+          unsigned m = __ballot_sync(0xffffffffu, redo);
+          if (lane == 0) { n_seg += 32; n_redo += __popc(m); }
+          while (m) {
+            const int L = __ffs(m) - 1;
+            m &= m - 1;
+            const int hh = hb * TC_M + q * 32 + L;  // < H: padding hypotheses are never uncertain
+            const int e = tc_recount(s_raw + seg0, len, recs + hh, thr_up);
+            if (lane == L) c = e;
+          }
+          if (c) s_cnt[(hbl * TC_M + row) * 2 + half] += c;
+        }
+      }
+    }
+    flush();
+    if (stats && lane == 0) {
+      atomicAdd(stats + 0, n_seg);
+      if (n_redo) atomicAdd(stats + 1, n_redo);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+unsigned long long g_plane_tc_stats[2] = {0, 0};
+int g_plane_tc_collect_stats = 0;
+int g_plane_tc_dump = 0;
+float g_plane_tc_acc_ulps = TC_ACC_ULPS;
+std::vector<float> g_plane_tc_dump_host;  // 128 x 256 accumulators + sigma, C
+}  // namespace pitt
+
+namespace pitt {
+
+#define TC_LAUNCH_CHECK(ctx, what)                                        \
+  do {                                                                    \
+    cudaError_t e__ = cudaGetLastError();                                 \
+    if (e__ != cudaSuccess) return fail((ctx), PITT_ERR_CUDA, what, e__); \
+    (ctx)->launches++;                                                    \
+  } while (0)
+
+// Scores H plane hypotheses on the tensor path. *d_use_out points at an int that is 1 when the
+// tensor kernel did the work and 0 when the caller must run the exact kernel (non-finite cloud,
+// degenerate scale): the decision is made on the device, no host round trip.
+int launch_score_plane_tc(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_recs, int H, const ScoreParams& sp, int* d_counts,
+                          const int** d_use_out) {
+  const int n = c->n;
+  const int n_hb = cdiv(H, TC_M);
+  const int n_chunks = cdiv(n, TC_CHUNK);
+  const int n_sb = cdiv(n_hb, TC_SB);
+  const long long items = (long long)n_sb * n_chunks;
+  if (items > INT_MAX) return fail(ctx, PITT_ERR_INVALID, "plane scoring (tensor path): too many work items");
+  unsigned* d_scr = nullptr;
+  PlaneTcParams* d_P = nullptr;
+  unsigned long long* d_stats = nullptr;
+  float4* d_image = nullptr;
+  float* d_dbg = nullptr;
+  PITT_TRY(arena_alloc(ctx, 4, &d_scr));
+  PITT_TRY(arena_alloc(ctx, 1, &d_P));
+  PITT_TRY(arena_alloc(ctx, 2, &d_stats));
+  PITT_TRY(arena_alloc(ctx, (size_t)n_hb * (TC_A_BLOCK_BYTES / 16), &d_image));
+  if (g_plane_tc_dump) PITT_TRY(arena_alloc(ctx, (size_t)TC_M * TC_N, &d_dbg));
+  PITT_CUDA(ctx, cudaMemsetAsync(d_scr, 0, 4 * sizeof(unsigned), ctx->stream));
+  PITT_CUDA(ctx, cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  int ab = std::min(cdiv(n, 256 * 8), ctx->sm_count * 8);
+  tc_absmax_kernel<<<ab, 256, 0, ctx->stream>>>(c->d_xyz, n, d_scr);
+  TC_LAUNCH_CHECK(ctx, "tc_absmax_kernel");
+  tc_params_kernel<<<1, 1, 0, ctx->stream>>>(d_scr, sp.thr_up, g_plane_tc_acc_ulps, d_P);
+  TC_LAUNCH_CHECK(ctx, "tc_params_kernel");
+  tc_hyp_image_kernel<<<n_hb, TC_M, 0, ctx->stream>>>(d_recs, H, d_P, d_image);
+  TC_LAUNCH_CHECK(ctx, "tc_hyp_image_kernel");
+  static bool attr_set = false;
+  if (!attr_set) {
+    PITT_CUDA(ctx, cudaFuncSetAttribute(plane_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  int grid = ctx->sm_count;
+  if ((long long)grid > items) grid = (int)items;
+  plane_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(c->d_xyz, n, d_recs, H, d_image, n_hb, n_chunks, (int)items, sp.thr_up,
+                                                                    d_P, d_counts, g_plane_tc_collect_stats ? d_stats : nullptr, d_dbg);
+  TC_LAUNCH_CHECK(ctx, "plane_tc_kernel");
+  *d_use_out = &d_P->use;
+  if (g_plane_tc_collect_stats || g_plane_tc_dump) {
+    if (g_plane_tc_collect_stats)
+      PITT_CUDA(ctx, cudaMemcpyAsync(g_plane_tc_stats, d_stats, sizeof(g_plane_tc_stats), cudaMemcpyDeviceToHost, ctx->stream));
+    if (g_plane_tc_dump) {
+      g_plane_tc_dump_host.assign((size_t)TC_M * TC_N + 2, 0.f);
+      PITT_CUDA(ctx, cudaMemcpyAsync(g_plane_tc_dump_host.data(), d_dbg, (size_t)TC_M * TC_N * sizeof(float), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+      PITT_CUDA(ctx, cudaMemcpyAsync(g_plane_tc_dump_host.data() + (size_t)TC_M * TC_N, d_P, 2 * sizeof(float), cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+    }
+    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return PITT_OK;
+}
+
+}  // namespace pitt

@@ -846,7 +846,10 @@ static int launch_score_generic(pitt_ctx* ctx, const pitt_cloud* c, const HypRec
   return PITT_OK;
 }
 
-int g_plane_mode = 0;  // test hook: 0 automatic, 1 exact packed kernel only, 2 FFMA filter + exact re-evaluation always
+int g_plane_mode = 0;  // test hook: 0 automatic, 1 exact packed kernel only, 2 FFMA filter + exact re-evaluation always,
+                       // 3 tensor-core path (plane_tc.cu) + exact re-evaluation always
+int launch_score_plane_tc(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_recs, int H, const ScoreParams& sp, int* d_counts,
+                          const int** d_use_out);
 unsigned long long g_plane_filter_stats[2] = {0, 0};  // last call with stats enabled: pairs, re-evaluated pairs
 int g_plane_filter_collect_stats = 0;
 
@@ -869,8 +872,12 @@ static int launch_score_plane_packed(pitt_ctx* ctx, const pitt_cloud* c, const H
   PITT_CUDA(ctx, cudaMemsetAsync(d_scr, 0, 8 * sizeof(unsigned), ctx->stream));
   PITT_CUDA(ctx, cudaMemsetAsync(d_P, 0, sizeof(PlaneFilterParams), ctx->stream));
   // the filter's two set-up launches only pay off on large jobs; tests force it with mode 2
-  const bool filter = (g_plane_mode == 2) || (g_plane_mode == 0 && (double)n * (double)H >= 134217728.0);
+  const bool tensor = (g_plane_mode == 3);
+  const bool filter = !tensor && ((g_plane_mode == 2) || (g_plane_mode == 0 && (double)n * (double)H >= 134217728.0));
+  const int* d_skip = nullptr;  // device flag: non-zero = a fast kernel did the work, the exact kernel returns at once
+  if (tensor) PITT_TRY(launch_score_plane_tc(ctx, c, d_recs, H, sp, d_counts, &d_skip));
   if (filter) {
+    d_skip = &d_P->use_filter;
     PITT_CUDA(ctx, cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
     int ab = std::min(cdiv(n, 256 * 8), ctx->sm_count * 8);
     cloud_absmax_kernel<<<ab, 256, 0, ctx->stream>>>(c->d_xyz, n, d_scr);
@@ -898,8 +905,7 @@ static int launch_score_plane_packed(pitt_ctx* ctx, const pitt_cloud* c, const H
   if ((long long)grid > items) grid = (int)items;
   // exact kernel: the whole job in exact mode; returns at once when the filter kernel was eligible
   plane_score_kernel<KH, TPB, TILE><<<grid, TPB, 0, ctx->stream>>>(c->d_xyz, n, d_recs, H, n_ptiles, (int)items, sp.thr_up, 1.0f,
-                                                                  (int*)d_scr + 3, d_counts,
-                                                                  filter ? &d_P->use_filter : nullptr);
+                                                                  (int*)d_scr + 3, d_counts, d_skip);
   PITT_LAUNCH_CHECK(ctx, "plane_score_kernel");
   if (filter && g_plane_filter_collect_stats) {
     PITT_CUDA(ctx, cudaMemcpyAsync(g_plane_filter_stats, d_stats, sizeof(g_plane_filter_stats), cudaMemcpyDeviceToHost, ctx->stream));

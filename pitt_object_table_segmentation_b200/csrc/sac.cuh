@@ -53,5 +53,10 @@ extern int g_force_generic_plane;
 extern int g_plane_mode;
 extern unsigned long long g_plane_filter_stats[2];
 extern int g_plane_filter_collect_stats;
+extern unsigned long long g_plane_tc_stats[2];
+extern int g_plane_tc_collect_stats;
+extern int g_plane_tc_dump;
+extern float g_plane_tc_acc_ulps;
+extern std::vector<float> g_plane_tc_dump_host;
 
 }  // namespace pitt

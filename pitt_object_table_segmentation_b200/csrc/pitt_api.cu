@@ -537,6 +537,10 @@ void pitt_debug_plane_tc_stats(int enable, uint64_t* out2) {
   g_plane_tc_collect_stats = enable;
   if (out2) { out2[0] = g_plane_tc_stats[0]; out2[1] = g_plane_tc_stats[1]; }
 }
+/* per-CTA (SM id << 48 | cycles) of the last call made while statistics were enabled, 160 entries */
+void pitt_debug_plane_tc_cta_cycles(uint64_t* out160) {
+  for (int i = 0; i < 168; ++i) out160[i] = g_plane_tc_stats[2 + i];
+}
 int pitt_debug_plane_tc_dump(int enable, float* out /*128*256 + 2, nullable*/) {
   g_plane_tc_dump = enable;
   if (out && !g_plane_tc_dump_host.empty()) {
@@ -546,5 +550,7 @@ int pitt_debug_plane_tc_dump(int enable, float* out /*128*256 + 2, nullable*/) {
   return 0;
 }
 void pitt_debug_plane_tc_acc_ulps(float ulps) { g_plane_tc_acc_ulps = ulps; }
+void pitt_debug_plane_tc_variant(int v) { g_plane_tc_variant = v; }
+void pitt_debug_plane_tc_nwq(int v) { g_plane_tc_nwq = v; }
 
 }  // extern "C"

@@ -34,18 +34,16 @@
 namespace pitt {
 
 constexpr int TC_M = 128;                       // hypotheses per block (UMMA M, TMEM lanes)
-constexpr int TC_N = 256;                       // points per tile (UMMA N, TMEM columns)
-constexpr int TC_TILES = 2;                     // tiles per point chunk
+constexpr int TC_N = 128;                       // points per tile (UMMA N, TMEM columns)
+constexpr int TC_TILES = 4;                     // tiles per point chunk = TMEM accumulator buffers = epilogue warp groups
 constexpr int TC_CHUNK = TC_N * TC_TILES;       // 512 points stationary in shared memory
 constexpr int TC_MMAS = 3;                      // chained MMAs per tile (K = 8 TF32 each)
 constexpr int TC_A_MMA_BYTES = TC_M * 32;       // 4096
 constexpr int TC_A_BLOCK_BYTES = TC_MMAS * TC_A_MMA_BYTES;  // 12288 per hypothesis block
-constexpr int TC_B_MMA_BYTES = TC_N * 32;       // 8192
-constexpr int TC_B_TILE_BYTES = TC_MMAS * TC_B_MMA_BYTES;   // 24576
+constexpr int TC_B_MMA_BYTES = TC_N * 32;       // 4096
+constexpr int TC_B_TILE_BYTES = TC_MMAS * TC_B_MMA_BYTES;   // 12288
 constexpr int TC_ASTAGES = 3;
-constexpr int TC_SB = 40;                       // hypothesis blocks per super-block (counts in smem)
-constexpr int TC_EPI_THREADS = 256;             // 8 epilogue warps
-constexpr int TC_THREADS = TC_EPI_THREADS + 64; // + MMA warp + producer warp
+constexpr int TC_SB = 20;                       // hypothesis blocks per super-block (counts in smem)
 constexpr float TC_ACC_ULPS = 8.0f;             // bound on the tensor core accumulation error, in u m
 constexpr float TC_WINDOW = 0.36f;              // sigma * beta_t must stay below this (see header)
 
@@ -54,7 +52,7 @@ constexpr int TC_OFF_B = 0;
 constexpr int TC_OFF_A = TC_OFF_B + TC_TILES * TC_B_TILE_BYTES;       // 49152
 constexpr int TC_OFF_RAW = TC_OFF_A + TC_ASTAGES * TC_A_BLOCK_BYTES;  // 86016
 constexpr int TC_OFF_CNT = TC_OFF_RAW + TC_CHUNK * 16;                // 94208
-constexpr int TC_OFF_BAR = TC_OFF_CNT + TC_SB * TC_M * 2 * 4;         // 135168
+constexpr int TC_OFF_BAR = TC_OFF_CNT + TC_SB * TC_M * 4;             // 104448
 constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 16 * 8 + 16;
 
 struct PlaneTcParams {
@@ -83,11 +81,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   do {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(2000u) /* suspend-time hint (ns): sleep in hardware, wake on completion */
         : "memory");
   } while (!ok);
+}
+// one lane of the (converged) warp; the same lane every time for a full mask
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -239,11 +243,11 @@ __global__ void __launch_bounds__(TC_M) tc_hyp_image_kernel(const HypRec* __rest
 // ------------------------------------------------------------------------------------------------
 // the scoring kernel
 // ------------------------------------------------------------------------------------------------
-// exact count of one hypothesis over len points of shared memory, whole warp (lanes = points)
-__device__ __noinline__ int tc_recount(const float4* pts, int len, const HypRec* rec, float thr_up) {
-  const float4 r = __ldg(reinterpret_cast<const float4*>(rec->v));
+// exact count of one hypothesis (a, b, c, d broadcast from its owner lane) over len points of shared
+// memory, whole warp (lanes = points)
+__device__ __forceinline__ int tc_recount(const float4* pts, int len, float4 r, float thr_up, int lane) {
   int c = 0;
-  for (int i = threadIdx.x & 31; i < len; i += 32) {
+  for (int i = lane; i < len; i += 32) {
     const float4 p = pts[i];
     const float s = (r.x * p.x + r.z * p.z) + (r.y * p.y + r.w);  // -fmad=false: unfused, Eigen order
     c += (fabsf(s) < thr_up) ? 1 : 0;
@@ -251,57 +255,107 @@ __device__ __noinline__ int tc_recount(const float4* pts, int len, const HypRec*
   return __reduce_add_sync(0xffffffffu, c);
 }
 
-__device__ __forceinline__ void tc_accumulate32(const uint32_t (&r)[32], float C, float (&S1)[4], float (&S2)[4]) {
+// Packed FP32 pairs: one issue slot per two additions / FMAs (the FMA pipe is busy 2 cycles either way), which
+// leaves issue slots for the control instructions of the epilogue.
+__device__ __forceinline__ unsigned long long tc_pack2(float lo, float hi) {
+  unsigned long long d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+__device__ __forceinline__ unsigned long long tc_add2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long tc_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float tc_sum2(unsigned long long v) {
+  float lo, hi;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+  return lo + hi;
+}
+__device__ __forceinline__ void tc_accumulate32(const uint32_t (&r)[32], float C, unsigned long long (&S1)[4], unsigned long long (&S2)[4]) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const float nv = -fabsf(__uint_as_float(r[i]));
-    float u;
-    asm("add.sat.f32 %0, %1, %2;" : "=f"(u) : "f"(nv), "f"(C));
-    S1[i & 3] = __fadd_rn(S1[i & 3], u);
-    S2[i & 3] = __fmaf_rn(u, u, S2[i & 3]);
+  for (int i = 0; i < 32; i += 2) {
+    const float nv0 = -fabsf(__uint_as_float(r[i])), nv1 = -fabsf(__uint_as_float(r[i + 1]));
+    float u0, u1;
+    asm("add.sat.f32 %0, %1, %2;" : "=f"(u0) : "f"(nv0), "f"(C));
+    asm("add.sat.f32 %0, %1, %2;" : "=f"(u1) : "f"(nv1), "f"(C));
+    const unsigned long long U = tc_pack2(u0, u1);
+    S1[(i >> 1) & 3] = tc_add2(S1[(i >> 1) & 3], U);
+    S2[(i >> 1) & 3] = tc_fma2(U, U, S2[(i >> 1) & 3]);
   }
 }
+// ragged segment: only the first len columns are points of the cloud
+__device__ __forceinline__ void tc_accumulate32_masked(const uint32_t (&r)[32], float C, unsigned long long (&S1)[4],
+                                                       unsigned long long (&S2)[4], int len) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    const float nv0 = -fabsf(__uint_as_float(r[i])), nv1 = -fabsf(__uint_as_float(r[i + 1]));
+    float u0, u1;
+    asm("add.sat.f32 %0, %1, %2;" : "=f"(u0) : "f"(nv0), "f"(C));
+    asm("add.sat.f32 %0, %1, %2;" : "=f"(u1) : "f"(nv1), "f"(C));
+    if (i >= len) u0 = 0.f;
+    if (i + 1 >= len) u1 = 0.f;
+    const unsigned long long U = tc_pack2(u0, u1);
+    S1[(i >> 1) & 3] = tc_add2(S1[(i >> 1) & 3], U);
+    S2[(i >> 1) & 3] = tc_fma2(U, U, S2[(i >> 1) & 3]);
+  }
+}
+__device__ __forceinline__ void tc_ld_wait2(uint32_t (&a)[32], uint32_t (&b)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : TC_RW32(a), TC_RW32(b)::"memory");
+}
 
+// 16 epilogue warps = 4 groups x 4 TMEM lane quadrants. Group g owns accumulator buffer g (128 columns) and
+// tile g (128 points) of every chunk: its four warps each drain 32 hypotheses (lanes) x 128 points. The MMA
+// thread refills buffer g as soon as group g has loaded it, i.e. a whole epilogue pass ahead of its next use,
+// so the MMA / commit / wake-up latency never sits on the critical path. DBG adds the accumulator dump and the
+// timing experiments (variant bits: 1 = no accumulation, 2 = one MMA per tile, 4 = no TMEM loads).
+constexpr int TC_EPI_WARPS = 16, TC_EPI_THREADS = 32 * TC_EPI_WARPS;
+constexpr int TC_MMA_WARPS = 2;  // MMA issuing warps (on different SM sub-partitions), each feeding TC_TILES / TC_MMA_WARPS buffers
+constexpr int TC_THREADS = TC_EPI_THREADS + 32 * TC_MMA_WARPS + 32;
+template <bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict__ recs, int H, const float4* __restrict__ image,
                 int n_hb /*hypothesis blocks*/, int n_chunks, int n_items, float thr_up, const PlaneTcParams* __restrict__ Pp,
                 int* __restrict__ counts, unsigned long long* __restrict__ stats /*nullable: [0] segments, [1] re-evaluated*/,
-                float* __restrict__ dbg /*nullable: s~ of hypothesis block 0 x tile 0 of item 0 (128 x 256)*/) {
+                float* __restrict__ dbg /*DBG: s~ of hypothesis block 0 x tiles 0,1 of item 0 (128 x 256)*/, int variant /*DBG*/) {
   extern __shared__ __align__(128) unsigned char smem[];
   const PlaneTcParams P = *Pp;
   if (!P.use) return;  // plane_score_kernel (launched right after) does the work
+  const long long t_start = clock64();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t s_base = smem_u32(smem);
   const uint32_t bar0 = s_base + TC_OFF_BAR;
-  // barriers: [0..2] a_full, [3..5] a_empty, [6..7] tmem_full, [8..9] tmem_empty, [10] b_full
+  // barriers: [0..2] a_full, [3..5] a_empty, [6..9] tmem_full, [10..13] tmem_empty, [14] b_full
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + TC_OFF_BAR + 16 * 8);
   float4* s_raw = reinterpret_cast<float4*>(smem + TC_OFF_RAW);
   int* s_cnt = reinterpret_cast<int*>(smem + TC_OFF_CNT);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TC_ASTAGES; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), 1); }
-    mbar_init(BAR(6), 1); mbar_init(BAR(7), 1);
-    mbar_init(BAR(8), TC_EPI_THREADS / 32); mbar_init(BAR(9), TC_EPI_THREADS / 32);
-    mbar_init(BAR(10), TC_EPI_THREADS);
+    for (int i = 0; i < TC_ASTAGES; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), TC_MMA_WARPS); }
+    for (int i = 0; i < TC_TILES; ++i) { mbar_init(BAR(6 + i), 1); mbar_init(BAR(10 + i), 4); }
+    mbar_init(BAR(14), TC_EPI_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == TC_EPI_WARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int i = threadIdx.x; i < TC_SB * TC_M * 2; i += TC_THREADS) s_cnt[i] = 0;
+  for (int i = threadIdx.x; i < TC_SB * TC_M; i += TC_THREADS) s_cnt[i] = 0;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
-  const int n_sb = (n_hb + TC_SB - 1) / TC_SB;
-  (void)n_sb;
-
-  if (warp == 9) {
+  if (warp == TC_EPI_WARPS + TC_MMA_WARPS) {
     // ===================== producer: hypothesis block images, global -> shared (bulk async copy)
-    if (lane == 0) {
+    // (the whole warp runs the loop so that every operand stays warp-uniform; one elected lane issues)
+    {
       uint32_t ac = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int sb = item / n_chunks;
@@ -309,76 +363,100 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
         for (int hb = hb0; hb < hb1; ++hb, ++ac) {
           const uint32_t st = ac % TC_ASTAGES, ph = (ac / TC_ASTAGES) & 1u;
           mbar_wait(BAR(3 + st), ph ^ 1u);
-          mbar_expect_tx(BAR(st), TC_A_BLOCK_BYTES);
-          const float4* src = image + (size_t)hb * (TC_A_BLOCK_BYTES / 16);
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(s_base + TC_OFF_A + st * TC_A_BLOCK_BYTES), "l"(src), "r"(TC_A_BLOCK_BYTES), "r"(BAR(st))
-                       : "memory");
+          if (elect_one()) {
+            mbar_expect_tx(BAR(st), TC_A_BLOCK_BYTES);
+            const float4* src = image + (size_t)hb * (TC_A_BLOCK_BYTES / 16);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(s_base + TC_OFF_A + st * TC_A_BLOCK_BYTES), "l"(src), "r"(TC_A_BLOCK_BYTES), "r"(BAR(st))
+                         : "memory");
+          }
+          __syncwarp();
         }
       }
     }
     __syncwarp();
-  } else if (warp == 8) {
-    // ===================== MMA issuer (one thread)
-    if (lane == 0) {
-      uint32_t ac = 0, tc = 0, cc = 0;
+  } else if (warp >= TC_EPI_WARPS) {
+    // ===================== MMA issuers (the whole warp runs the loop, one elected lane issues)
+    {
+      constexpr int TPW = TC_TILES / TC_MMA_WARPS;
+      const int t_first = (warp - TC_EPI_WARPS) * TPW;
+      uint32_t ac = 0, cc = 0;
+      long long tw = 0, tm = 0, tcm = 0, ta = 0, tb = 0;  // DBG: cycles in empty-wait, MMA issue, commit, A wait, B wait
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++cc) {
         const int sb = item / n_chunks;
         const int hb0 = sb * TC_SB, hb1 = min(n_hb, hb0 + TC_SB);
-        mbar_wait(BAR(10), cc & 1u);  // the chunk's B image is in shared memory
+        long long c0 = DBG ? clock64() : 0;
+        mbar_wait(BAR(14), cc & 1u);  // the chunk's B image is in shared memory
         tc_fence_after();
+        if (DBG) tb += clock64() - c0;
         for (int hb = hb0; hb < hb1; ++hb, ++ac) {
           const uint32_t st = ac % TC_ASTAGES, ph = (ac / TC_ASTAGES) & 1u;
+          if (DBG) c0 = clock64();
           mbar_wait(BAR(st), ph);
           tc_fence_after();
+          if (DBG) ta += clock64() - c0;
           const uint32_t a_addr = s_base + TC_OFF_A + st * TC_A_BLOCK_BYTES;
 #pragma unroll
-          for (int t = 0; t < TC_TILES; ++t, ++tc) {
-            const uint32_t buf = tc & 1u, tph = (tc >> 1) & 1u;
-            mbar_wait(BAR(8 + buf), tph ^ 1u);  // the epilogue drained this accumulator
+          for (int tt = 0; tt < TPW; ++tt) {
+            const int t = t_first + tt;
+            if (DBG) c0 = clock64();
+            mbar_wait(BAR(10 + t), (ac & 1u) ^ 1u);  // group t has loaded the previous contents of buffer t
             tc_fence_after();
+            long long c1 = DBG ? clock64() : 0;
             const uint32_t b_addr = s_base + TC_OFF_B + t * TC_B_TILE_BYTES;
+            long long c2 = 0;
+            if (elect_one()) {
 #pragma unroll
-            for (int j = 0; j < TC_MMAS; ++j)
-              tc_mma_tf32(tmem + buf * TC_N, tc_smem_desc(a_addr + j * TC_A_MMA_BYTES), tc_smem_desc(b_addr + j * TC_B_MMA_BYTES),
-                          TC_IDESC, j > 0 ? 1u : 0u);
-            tc_commit(BAR(6 + buf));
+              for (int j = 0; j < TC_MMAS; ++j)
+                if (!DBG || j == 0 || !(variant & 2))
+                  tc_mma_tf32(tmem + t * TC_N, tc_smem_desc(a_addr + j * TC_A_MMA_BYTES), tc_smem_desc(b_addr + j * TC_B_MMA_BYTES),
+                              TC_IDESC, j > 0 ? 1u : 0u);
+              if (DBG) c2 = clock64();
+              tc_commit(BAR(6 + t));
+              if (tt == TPW - 1) tc_commit(BAR(3 + st));  // the hypothesis stage is free once these MMAs have read it
+            }
+            __syncwarp();
+            if (DBG) { tw += c1 - c0; tm += c2 - c1; tcm += clock64() - c2; }
           }
-          tc_commit(BAR(3 + st));  // the hypothesis stage is free once these MMAs have read it
         }
+      }
+      if (DBG && stats && blockIdx.x == 0 && lane == 0 && warp == TC_EPI_WARPS) {
+        stats[162] = tw; stats[163] = tm; stats[164] = tcm; stats[165] = ta; stats[166] = tb; stats[167] = ac * TPW;
       }
     }
     __syncwarp();
   } else {
-    // ===================== epilogue warps 0..7: split the point chunk, drain TMEM, count
-    const int q = warp & 3, half = warp >> 2;
+    // ===================== epilogue warps: split the point chunk, drain TMEM, count
+    const int q = warp & 3, g = warp >> 2;  // lane quadrant, group = tile = accumulator buffer
     const int row = q * 32 + lane;
-    const uint32_t t_lane = (uint32_t)(q * 32) << 16;
-    uint32_t tc = 0;
+    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + g * TC_N;
+    const int seg0 = g * TC_N;  // first point of this group's tile inside the chunk
+    uint32_t uc = 0;            // uses of buffer g so far
     int cur_sb = -1;
-    unsigned long long n_seg = 0, n_redo = 0;
+    unsigned n_seg = 0, n_redo = 0;
+    auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); };
     auto flush = [&]() {
       if (cur_sb < 0) return;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      epi_sync();
       for (int i = threadIdx.x; i < TC_SB * TC_M; i += TC_EPI_THREADS) {
         const int h = cur_sb * TC_SB * TC_M + i;
-        const int v = s_cnt[2 * i] + s_cnt[2 * i + 1];
-        s_cnt[2 * i] = 0; s_cnt[2 * i + 1] = 0;
+        const int v = s_cnt[i];
+        s_cnt[i] = 0;
         if (h < H && v) atomicAdd(&counts[h], v);
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      epi_sync();
     };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int sb = item / n_chunks, chunk = item % n_chunks;
       if (sb != cur_sb) { flush(); cur_sb = sb; }
       const int hb0 = sb * TC_SB, hb1 = min(n_hb, hb0 + TC_SB);
       const int base = chunk * TC_CHUNK;
+      const int len = min(TC_N, n - (base + seg0));
       // every MMA that read the previous B image has completed (its accumulators were consumed);
       // nobody may still be re-counting from s_raw
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-#pragma unroll
-      for (int k = 0; k < TC_CHUNK / TC_EPI_THREADS; ++k) {
-        const int pi = threadIdx.x + k * TC_EPI_THREADS;  // point of the chunk
+      epi_sync();
+      {
+        const int pi = threadIdx.x;  // point of the chunk (TC_CHUNK == TC_EPI_THREADS)
         const int gi = base + pi;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
         if (gi < n) p = __ldg(xyz + gi);
@@ -390,104 +468,116 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
         const int t = pi / TC_N, pr = pi % TC_N;
         float4* tb = reinterpret_cast<float4*>(smem + TC_OFF_B + t * TC_B_TILE_BYTES);
         const int o = (pr >> 3) * 16 + (pr & 7);
-        tb[0 * 512 + o] = make_float4(x3, x2, x1, y3);
-        tb[0 * 512 + o + 8] = make_float4(y2, y1, z3, z2);
-        tb[1 * 512 + o] = make_float4(z1, 1.f, x2, x1);
-        tb[1 * 512 + o + 8] = make_float4(y2, y1, z2, z1);
-        tb[2 * 512 + o] = make_float4(x1, y1, z1, 1.f);
-        tb[2 * 512 + o + 8] = make_float4(1.f, 0.f, 0.f, 0.f);
+        constexpr int MF4 = TC_B_MMA_BYTES / 16;  // float4 per MMA image
+        tb[0 * MF4 + o] = make_float4(x3, x2, x1, y3);
+        tb[0 * MF4 + o + 8] = make_float4(y2, y1, z3, z2);
+        tb[1 * MF4 + o] = make_float4(z1, 1.f, x2, x1);
+        tb[1 * MF4 + o + 8] = make_float4(y2, y1, z2, z1);
+        tb[2 * MF4 + o] = make_float4(x1, y1, z1, 1.f);
+        tb[2 * MF4 + o + 8] = make_float4(1.f, 0.f, 0.f, 0.f);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(BAR(10));
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // s_raw visible to every epilogue warp
+      mbar_arrive(BAR(14));
+      epi_sync();  // s_raw visible to every epilogue warp
 
-      for (int hb = hb0; hb < hb1; ++hb) {
-        const int hbl = hb - hb0;
 #pragma unroll 1
-        for (int t = 0; t < TC_TILES; ++t, ++tc) {
-          const uint32_t buf = tc & 1u, tph = (tc >> 1) & 1u;
-          const int seg0 = t * TC_N + half * 128;  // first point of this thread's segment inside the chunk
-          const int len = min(128, n - (base + seg0));
-          mbar_wait(BAR(6 + buf), tph);
-          tc_fence_after();
-          const uint32_t taddr = tmem + t_lane + buf * TC_N + half * 128;
-          float S1[4] = {0.f, 0.f, 0.f, 0.f}, S2[4] = {0.f, 0.f, 0.f, 0.f};
-          uint32_t ra[32], rb[32];
-          tc_ld32(ra, taddr);
-          tc_ld_wait(ra);
-          tc_ld32(rb, taddr + 32);
-          if (dbg && item == 0 && hb == 0 && t == 0) {
+      for (int hb = hb0; hb < hb1; ++hb, ++uc) {
+        const int h = hb * TC_M + row;
+        // this lane's hypothesis in the exact form, for re-evaluations (broadcast by shuffle, no memory latency there)
+        float4 myrec = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+        if (h < H) myrec = __ldg(reinterpret_cast<const float4*>(recs[h].v));
+        mbar_wait(BAR(6 + g), uc & 1u);
+        tc_fence_after();
+        unsigned long long S1[4] = {0ull, 0ull, 0ull, 0ull}, S2[4] = {0ull, 0ull, 0ull, 0ull};
+        uint32_t ra[32], rb[32];
+        if (DBG && (variant & 5)) {
+          if (!(variant & 4)) {
+            unsigned x = 0;
+            for (int k4 = 0; k4 < TC_N / 32; ++k4) {
+              tc_ld32(ra, taddr + 32 * k4);
+              tc_ld_wait(ra);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) dbg[row * TC_N + half * 128 + i] = __uint_as_float(ra[i]);
+              for (int i = 0; i < 32; ++i) x ^= ra[i];
+            }
+            if (x == 0x12345u) n_seg++;
           }
-          tc_accumulate32(ra, P.C, S1, S2);
-          tc_ld_wait(rb);
-          tc_ld32(ra, taddr + 64);
-          if (dbg && item == 0 && hb == 0 && t == 0) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) dbg[row * TC_N + half * 128 + 32 + i] = __uint_as_float(rb[i]);
-          }
-          tc_accumulate32(rb, P.C, S1, S2);
-          tc_ld_wait(ra);
-          tc_ld32(rb, taddr + 96);
-          if (dbg && item == 0 && hb == 0 && t == 0) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) dbg[row * TC_N + half * 128 + 64 + i] = __uint_as_float(ra[i]);
-          }
-          tc_accumulate32(ra, P.C, S1, S2);
-          tc_ld_wait(rb);
-          // this warp has read its part of the accumulator: hand the buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(8 + buf));
-          if (dbg && item == 0 && hb == 0 && t == 0) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) dbg[row * TC_N + half * 128 + 96 + i] = __uint_as_float(rb[i]);
-          }
-          tc_accumulate32(rb, P.C, S1, S2);
-          const float s1 = (S1[0] + S1[1]) + (S1[2] + S1[3]);
-          const float s2 = (S2[0] + S2[1]) + (S2[2] + S2[3]);
-          int c = (int)rintf(s1);
-          const int h = hb * TC_M + row;
-          bool redo;
-          if (len == 128) {
-            redo = (s1 - s2) > 0.1f;
-          } else {
-            redo = (len > 0) && (h < H);  // ragged segment: padding points were scored, count exactly
-            c = 0;
-          }
-          unsigned m = __ballot_sync(0xffffffffu, redo);
-          if (lane == 0) { n_seg += 32; n_redo += __popc(m); }
-          while (m) {
-            const int L = __ffs(m) - 1;
-            m &= m - 1;
-            const int hh = hb * TC_M + q * 32 + L;  // < H: padding hypotheses are never uncertain
-            const int e = tc_recount(s_raw + seg0, len, recs + hh, thr_up);
-            if (lane == L) c = e;
-          }
-          if (c) s_cnt[(hbl * TC_M + row) * 2 + half] += c;
+          if (lane == 0) mbar_arrive(BAR(10 + g));
+          continue;
         }
+#pragma unroll
+        for (int b = 0; b < TC_N / 64; ++b) {
+          tc_ld32(ra, taddr + 64 * b);
+          tc_ld32(rb, taddr + 64 * b + 32);
+          tc_ld_wait2(ra, rb);
+          if (b == TC_N / 64 - 1) {
+            // this warp has read its part of the accumulator: hand the buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(10 + g));
+          }
+          if (DBG && dbg && item == 0 && hb == 0 && g < 2) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              dbg[row * 256 + g * TC_N + 64 * b + i] = __uint_as_float(ra[i]);
+              dbg[row * 256 + g * TC_N + 64 * b + 32 + i] = __uint_as_float(rb[i]);
+            }
+          }
+          if (len == TC_N) {
+            tc_accumulate32(ra, P.C, S1, S2);
+            tc_accumulate32(rb, P.C, S1, S2);
+          } else {  // ragged last tile of the cloud (warp-uniform, once per hypothesis block)
+            tc_accumulate32_masked(ra, P.C, S1, S2, len - 64 * b);
+            tc_accumulate32_masked(rb, P.C, S1, S2, len - 64 * b - 32);
+          }
+        }
+        const float s1 = tc_sum2(tc_add2(tc_add2(S1[0], S1[1]), tc_add2(S1[2], S1[3])));
+        const float s2 = tc_sum2(tc_add2(tc_add2(S2[0], S2[1]), tc_add2(S2[2], S2[3])));
+        int c = (int)rintf(s1);
+        const bool redo = (s1 - s2) > 0.1f;
+        unsigned m = __ballot_sync(0xffffffffu, redo);
+        if (stats && lane == 0) { n_seg += 32; n_redo += __popc(m); }
+        while (m) {  // rare
+          const int L = __ffs(m) - 1;
+          m &= m - 1;
+          float4 r;
+          r.x = __shfl_sync(0xffffffffu, myrec.x, L);
+          r.y = __shfl_sync(0xffffffffu, myrec.y, L);
+          r.z = __shfl_sync(0xffffffffu, myrec.z, L);
+          r.w = __shfl_sync(0xffffffffu, myrec.w, L);
+          const int e = tc_recount(s_raw + seg0, max(len, 0), r, thr_up, lane);
+          if (lane == L) c = e;
+        }
+        if (c) atomicAdd(&s_cnt[(hb - hb0) * TC_M + row], c);
       }
     }
     flush();
     if (stats && lane == 0) {
-      atomicAdd(stats + 0, n_seg);
-      if (n_redo) atomicAdd(stats + 1, n_redo);
+      atomicAdd(stats + 0, (unsigned long long)n_seg);
+      if (n_redo) atomicAdd(stats + 1, (unsigned long long)n_redo);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == TC_EPI_WARPS) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+  }
+  if (stats && threadIdx.x == 0) {  // per-CTA cycles and SM id (load-balance diagnostics)
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    stats[2 + blockIdx.x] = ((unsigned long long)smid << 48) | (unsigned long long)(clock64() - t_start);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-unsigned long long g_plane_tc_stats[2] = {0, 0};
+unsigned long long g_plane_tc_stats[2 + 160 + 8] = {0, 0};
 int g_plane_tc_collect_stats = 0;
 int g_plane_tc_dump = 0;
+int g_plane_tc_variant = 0;
+int g_plane_tc_nwq = 4;
 float g_plane_tc_acc_ulps = TC_ACC_ULPS;
 std::vector<float> g_plane_tc_dump_host;  // 128 x 256 accumulators + sigma, C
 }  // namespace pitt
@@ -519,11 +609,11 @@ int launch_score_plane_tc(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_re
   float* d_dbg = nullptr;
   PITT_TRY(arena_alloc(ctx, 4, &d_scr));
   PITT_TRY(arena_alloc(ctx, 1, &d_P));
-  PITT_TRY(arena_alloc(ctx, 2, &d_stats));
+  PITT_TRY(arena_alloc(ctx, 2 + 160 + 8, &d_stats));
   PITT_TRY(arena_alloc(ctx, (size_t)n_hb * (TC_A_BLOCK_BYTES / 16), &d_image));
-  if (g_plane_tc_dump) PITT_TRY(arena_alloc(ctx, (size_t)TC_M * TC_N, &d_dbg));
+  if (g_plane_tc_dump) PITT_TRY(arena_alloc(ctx, (size_t)TC_M * 256, &d_dbg));
   PITT_CUDA(ctx, cudaMemsetAsync(d_scr, 0, 4 * sizeof(unsigned), ctx->stream));
-  PITT_CUDA(ctx, cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  PITT_CUDA(ctx, cudaMemsetAsync(d_stats, 0, (2 + 160 + 8) * sizeof(unsigned long long), ctx->stream));
   int ab = std::min(cdiv(n, 256 * 8), ctx->sm_count * 8);
   tc_absmax_kernel<<<ab, 256, 0, ctx->stream>>>(c->d_xyz, n, d_scr);
   TC_LAUNCH_CHECK(ctx, "tc_absmax_kernel");
@@ -531,25 +621,32 @@ int launch_score_plane_tc(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_re
   TC_LAUNCH_CHECK(ctx, "tc_params_kernel");
   tc_hyp_image_kernel<<<n_hb, TC_M, 0, ctx->stream>>>(d_recs, H, d_P, d_image);
   TC_LAUNCH_CHECK(ctx, "tc_hyp_image_kernel");
-  static bool attr_set = false;
-  if (!attr_set) {
-    PITT_CUDA(ctx, cudaFuncSetAttribute(plane_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    attr_set = true;
-  }
   int grid = ctx->sm_count;
   if ((long long)grid > items) grid = (int)items;
-  plane_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(c->d_xyz, n, d_recs, H, d_image, n_hb, n_chunks, (int)items, sp.thr_up,
-                                                                    d_P, d_counts, g_plane_tc_collect_stats ? d_stats : nullptr, d_dbg);
+  unsigned long long* st = g_plane_tc_collect_stats ? d_stats : nullptr;
+  const bool dbgk = g_plane_tc_dump || g_plane_tc_variant;
+#define TC_LAUNCH(DBGK)                                                                                                         \
+  do {                                                                                                                          \
+    static bool attr_set = false;                                                                                               \
+    if (!attr_set) {                                                                                                            \
+      PITT_CUDA(ctx, cudaFuncSetAttribute(plane_tc_kernel<DBGK>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));  \
+      attr_set = true;                                                                                                          \
+    }                                                                                                                           \
+    plane_tc_kernel<DBGK><<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(                                                    \
+        c->d_xyz, n, d_recs, H, d_image, n_hb, n_chunks, (int)items, sp.thr_up, d_P, d_counts, st, d_dbg, g_plane_tc_variant);  \
+  } while (0)
+  if (dbgk) TC_LAUNCH(true); else TC_LAUNCH(false);
+#undef TC_LAUNCH
   TC_LAUNCH_CHECK(ctx, "plane_tc_kernel");
   *d_use_out = &d_P->use;
   if (g_plane_tc_collect_stats || g_plane_tc_dump) {
     if (g_plane_tc_collect_stats)
       PITT_CUDA(ctx, cudaMemcpyAsync(g_plane_tc_stats, d_stats, sizeof(g_plane_tc_stats), cudaMemcpyDeviceToHost, ctx->stream));
     if (g_plane_tc_dump) {
-      g_plane_tc_dump_host.assign((size_t)TC_M * TC_N + 2, 0.f);
-      PITT_CUDA(ctx, cudaMemcpyAsync(g_plane_tc_dump_host.data(), d_dbg, (size_t)TC_M * TC_N * sizeof(float), cudaMemcpyDeviceToHost,
+      g_plane_tc_dump_host.assign((size_t)TC_M * 256 + 2, 0.f);
+      PITT_CUDA(ctx, cudaMemcpyAsync(g_plane_tc_dump_host.data(), d_dbg, (size_t)TC_M * 256 * sizeof(float), cudaMemcpyDeviceToHost,
                                      ctx->stream));
-      PITT_CUDA(ctx, cudaMemcpyAsync(g_plane_tc_dump_host.data() + (size_t)TC_M * TC_N, d_P, 2 * sizeof(float), cudaMemcpyDeviceToHost,
+      PITT_CUDA(ctx, cudaMemcpyAsync(g_plane_tc_dump_host.data() + (size_t)TC_M * 256, d_P, 2 * sizeof(float), cudaMemcpyDeviceToHost,
                                      ctx->stream));
     }
     PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

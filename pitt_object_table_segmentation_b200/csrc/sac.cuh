@@ -53,9 +53,11 @@ extern int g_force_generic_plane;
 extern int g_plane_mode;
 extern unsigned long long g_plane_filter_stats[2];
 extern int g_plane_filter_collect_stats;
-extern unsigned long long g_plane_tc_stats[2];
+extern unsigned long long g_plane_tc_stats[2 + 160 + 8];
 extern int g_plane_tc_collect_stats;
 extern int g_plane_tc_dump;
+extern int g_plane_tc_variant;
+extern int g_plane_tc_nwq;
 extern float g_plane_tc_acc_ulps;
 extern std::vector<float> g_plane_tc_dump_host;
 

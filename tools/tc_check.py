@@ -92,7 +92,9 @@ def timing(ctx, n, H):
     d_c = torch.zeros(H, dtype=torch.int32, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     res = {}
-    for mode in (2, 3):
+    variants = [int(v) for v in os.environ.get("TC_VARIANTS", "0").split(",")]
+    for mode, var in [(2, 0)] + [(3, v) for v in variants]:
+        ctx.lib.pitt_debug_plane_tc_variant(var)
         ctx.lib.pitt_debug_plane_mode(mode)
         ts = []
         for it in range(10):
@@ -104,13 +106,15 @@ def timing(ctx, n, H):
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         ctx.lib.pitt_debug_plane_mode(0)
-        res[mode] = (min(ts[2:]), d_c.cpu().numpy().copy())
-        print(f"mode {mode}: {min(ts[2:]):.3f} ms per call (whole pitt_sac_score_device) -> "
+        if var == 0:
+            res[mode] = (min(ts[2:]), d_c.cpu().numpy().copy())
+        print(f"mode {mode} variant {var}: {min(ts[2:]):.3f} ms per call (whole pitt_sac_score_device) -> "
               f"{n * H / min(ts[2:]) / 1e9:.2f} Gevals/ms ... {n * H / (min(ts[2:]) * 1e-3) / 1e12:.2f} Tevals/s")
     print("counts equal:", np.array_equal(res[2][1], res[3][1]))
 
 
 if __name__ == "__main__":
+    pkg.load_library().pitt_debug_plane_tc_nwq(int(os.environ.get("TC_NWQ", "4")))
     what = sys.argv[1]
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 20000
     H = int(sys.argv[3]) if len(sys.argv) > 3 else 512
@@ -123,3 +127,36 @@ if __name__ == "__main__":
     elif what == "time":
         timing(ctx, n, H)
     ctx.close()
+
+
+def cta_cycles(n, H):
+    """per-CTA cycle counts of one tensor-path launch (load balance)"""
+    ctx = pkg.Context(0)
+    xyz = scenes.plane_outlier_cloud(n, seed=12345)
+    cloud = ctx.stage(xyz)
+    p = pkg.default_support_sac_params()
+    samples = rand_samples(n, H, 7)
+    for var in [int(v) for v in os.environ.get("TC_VARIANTS", "8,9,12").split(",")]:  # 8 = DBG kernel with full work
+        ctx.lib.pitt_debug_plane_tc_variant(var)
+        score(ctx, cloud, p, samples, 3)
+        ctx.lib.pitt_debug_plane_tc_stats(1, None)
+        score(ctx, cloud, p, samples, 3)
+        ctx.lib.pitt_debug_plane_tc_stats(0, None)
+        buf = (C.c_uint64 * 168)()
+        ctx.lib.pitt_debug_plane_tc_cta_cycles(buf)
+        v = np.array(list(buf), dtype=np.uint64)[:148]
+        cyc = (v & np.uint64((1 << 48) - 1)).astype(np.int64)
+        sm = (v >> np.uint64(48)).astype(np.int64)
+        order = np.argsort(cyc)
+        print(f"variant {var}: cycles min {cyc.min()} median {int(np.median(cyc))} max {cyc.max()}; distinct SMs {len(set(sm.tolist()))}")
+        print("  slowest CTAs (block, sm, cycles):", [(int(b), int(sm[b]), int(cyc[b])) for b in order[-6:]])
+        print("  fastest CTAs (block, sm, cycles):", [(int(b), int(sm[b]), int(cyc[b])) for b in order[:4]])
+        mm = [int(x) for x in list(buf)[160:166]]
+        print(f"  MMA thread of CTA 0: tiles {mm[5]}; per tile cycles: empty-wait {mm[0] / max(mm[5], 1):.0f}, MMA issue {mm[1] / max(mm[5], 1):.0f}, "
+              f"commit {mm[2] / max(mm[5], 1):.0f}; per hb A-wait {mm[3] * 4 / max(mm[5], 1):.0f}; B-wait total {mm[4]}")
+        print("  blocks 0..29 mean", cyc[:30].mean(), " blocks 30..147 mean", cyc[30:].mean())
+    ctx.lib.pitt_debug_plane_tc_variant(0)
+
+
+if __name__ == "__main__" and sys.argv[1] == "cta":
+    cta_cycles(int(sys.argv[2]), int(sys.argv[3]))

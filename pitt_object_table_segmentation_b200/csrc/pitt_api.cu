@@ -521,7 +521,8 @@ int pitt_argmax_counts_device(pitt_ctx* ctx, const void* d_counts, int H, void* 
 
 /* test hook (not in the public header): route plane scoring through the generic kernel */
 void pitt_debug_force_generic_plane(int on) { g_force_generic_plane = on; }
-/* test hooks: plane scoring mode (0 = automatic: filter on large jobs, 1 = exact packed kernel only, 2 = FFMA filter + exact re-evaluation always) and
+/* test hooks: plane scoring mode (0 = automatic: tensor path on large jobs, 1 = exact packed kernel only, 2 = FFMA filter + exact
+ * re-evaluation always, 3 = tensor-core path + exact re-evaluation always) and
  * the filter statistics of the last scoring call made while collection was enabled:
  * out[0] = (hypothesis, point tile) pairs scored, out[1] = pairs re-evaluated exactly */
 void pitt_debug_plane_mode(int mode) { g_plane_mode = mode; }

@@ -277,7 +277,7 @@ __device__ __forceinline__ float tc_sum2(unsigned long long v) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
   return lo + hi;
 }
-__device__ __forceinline__ void tc_accumulate32(const uint32_t (&r)[32], float C, unsigned long long (&S1)[4], unsigned long long (&S2)[4]) {
+__device__ __forceinline__ void tc_accumulate32(const uint32_t (&r)[32], float C, unsigned long long (&S1)[2], unsigned long long (&S2)[2]) {
 #pragma unroll
   for (int i = 0; i < 32; i += 2) {
     const float nv0 = -fabsf(__uint_as_float(r[i])), nv1 = -fabsf(__uint_as_float(r[i + 1]));
@@ -285,13 +285,13 @@ __device__ __forceinline__ void tc_accumulate32(const uint32_t (&r)[32], float C
     asm("add.sat.f32 %0, %1, %2;" : "=f"(u0) : "f"(nv0), "f"(C));
     asm("add.sat.f32 %0, %1, %2;" : "=f"(u1) : "f"(nv1), "f"(C));
     const unsigned long long U = tc_pack2(u0, u1);
-    S1[(i >> 1) & 3] = tc_add2(S1[(i >> 1) & 3], U);
-    S2[(i >> 1) & 3] = tc_fma2(U, U, S2[(i >> 1) & 3]);
+    S1[(i >> 1) & 1] = tc_add2(S1[(i >> 1) & 1], U);
+    S2[(i >> 1) & 1] = tc_fma2(U, U, S2[(i >> 1) & 1]);
   }
 }
 // ragged segment: only the first len columns are points of the cloud
-__device__ __forceinline__ void tc_accumulate32_masked(const uint32_t (&r)[32], float C, unsigned long long (&S1)[4],
-                                                       unsigned long long (&S2)[4], int len) {
+__device__ __forceinline__ void tc_accumulate32_masked(const uint32_t (&r)[32], float C, unsigned long long (&S1)[2],
+                                                       unsigned long long (&S2)[2], int len) {
 #pragma unroll
   for (int i = 0; i < 32; i += 2) {
     const float nv0 = -fabsf(__uint_as_float(r[i])), nv1 = -fabsf(__uint_as_float(r[i + 1]));
@@ -301,8 +301,8 @@ __device__ __forceinline__ void tc_accumulate32_masked(const uint32_t (&r)[32], 
     if (i >= len) u0 = 0.f;
     if (i + 1 >= len) u1 = 0.f;
     const unsigned long long U = tc_pack2(u0, u1);
-    S1[(i >> 1) & 3] = tc_add2(S1[(i >> 1) & 3], U);
-    S2[(i >> 1) & 3] = tc_fma2(U, U, S2[(i >> 1) & 3]);
+    S1[(i >> 1) & 1] = tc_add2(S1[(i >> 1) & 1], U);
+    S2[(i >> 1) & 1] = tc_fma2(U, U, S2[(i >> 1) & 1]);
   }
 }
 __device__ __forceinline__ void tc_ld_wait2(uint32_t (&a)[32], uint32_t (&b)[32]) {
@@ -488,7 +488,7 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
         if (h < H) myrec = __ldg(reinterpret_cast<const float4*>(recs[h].v));
         mbar_wait(BAR(6 + g), uc & 1u);
         tc_fence_after();
-        unsigned long long S1[4] = {0ull, 0ull, 0ull, 0ull}, S2[4] = {0ull, 0ull, 0ull, 0ull};
+        unsigned long long S1[2] = {0ull, 0ull}, S2[2] = {0ull, 0ull};
         uint32_t ra[32], rb[32];
         if (DBG && (variant & 5)) {
           if (!(variant & 4)) {
@@ -532,8 +532,8 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
             tc_accumulate32_masked(rb, P.C, S1, S2, len - 64 * b - 32);
           }
         }
-        const float s1 = tc_sum2(tc_add2(tc_add2(S1[0], S1[1]), tc_add2(S1[2], S1[3])));
-        const float s2 = tc_sum2(tc_add2(tc_add2(S2[0], S2[1]), tc_add2(S2[2], S2[3])));
+        const float s1 = tc_sum2(tc_add2(S1[0], S1[1]));
+        const float s2 = tc_sum2(tc_add2(S2[0], S2[1]));
         int c = (int)rintf(s1);
         const bool redo = (s1 - s2) > 0.1f;
         unsigned m = __ballot_sync(0xffffffffu, redo);

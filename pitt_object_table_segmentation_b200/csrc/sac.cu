@@ -846,8 +846,8 @@ static int launch_score_generic(pitt_ctx* ctx, const pitt_cloud* c, const HypRec
   return PITT_OK;
 }
 
-int g_plane_mode = 0;  // test hook: 0 automatic, 1 exact packed kernel only, 2 FFMA filter + exact re-evaluation always,
-                       // 3 tensor-core path (plane_tc.cu) + exact re-evaluation always
+int g_plane_mode = 0;  // test hook: 0 automatic (tensor path on large jobs), 1 exact packed kernel only,
+                       // 2 FFMA filter + exact re-evaluation always, 3 tensor-core path (plane_tc.cu) always
 int launch_score_plane_tc(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_recs, int H, const ScoreParams& sp, int* d_counts,
                           const int** d_use_out);
 unsigned long long g_plane_filter_stats[2] = {0, 0};  // last call with stats enabled: pairs, re-evaluated pairs
@@ -872,8 +872,9 @@ static int launch_score_plane_packed(pitt_ctx* ctx, const pitt_cloud* c, const H
   PITT_CUDA(ctx, cudaMemsetAsync(d_scr, 0, 8 * sizeof(unsigned), ctx->stream));
   PITT_CUDA(ctx, cudaMemsetAsync(d_P, 0, sizeof(PlaneFilterParams), ctx->stream));
   // the filter's two set-up launches only pay off on large jobs; tests force it with mode 2
-  const bool tensor = (g_plane_mode == 3);
-  const bool filter = !tensor && ((g_plane_mode == 2) || (g_plane_mode == 0 && (double)n * (double)H >= 134217728.0));
+  // large jobs: dot products on the tensor cores (plane_tc.cu); the FFMA filter (mode 2) is the CUDA-core alternative
+  const bool tensor = (g_plane_mode == 3) || (g_plane_mode == 0 && (double)n * (double)H >= 134217728.0);
+  const bool filter = (g_plane_mode == 2);
   const int* d_skip = nullptr;  // device flag: non-zero = a fast kernel did the work, the exact kernel returns at once
   if (tensor) PITT_TRY(launch_score_plane_tc(ctx, c, d_recs, H, sp, d_counts, &d_skip));
   if (filter) {

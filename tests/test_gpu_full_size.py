@@ -21,7 +21,7 @@ def _device_counts(ctx, cloud, p, samples):
 
 
 def test_c2_full_size_plane(ctx, oracle):
-    """config 2: 1 M points x 5000 replayed hypotheses. (i) the FFMA filter kernel and the exact packed kernel agree on
+    """config 2: 1 M points x 5000 replayed hypotheses. (i) the tensor-core kernel, the FFMA filter kernel and the exact packed kernel agree on
     all 5000 counts, (ii) 40 random hypotheses + the winner agree with the oracle, (iii) the winner's refined model
     and final inlier set equal the oracle's refine + select of the same winner."""
     xyz = scenes.plane_outlier_cloud(1_000_000, seed=12345)
@@ -31,11 +31,13 @@ def test_c2_full_size_plane(ctx, oracle):
     p = pkg.default_support_sac_params()
     ctx.lib.pitt_debug_plane_mode(2)
     c_filter = _device_counts(ctx, cloud, p, samples)
+    ctx.lib.pitt_debug_plane_mode(3)
+    c_tensor = _device_counts(ctx, cloud, p, samples)
     ctx.lib.pitt_debug_plane_mode(1)
     c_exact = _device_counts(ctx, cloud, p, samples)
     ctx.lib.pitt_debug_plane_mode(0)
     c_auto = _device_counts(ctx, cloud, p, samples)
-    assert np.array_equal(c_filter, c_exact) and np.array_equal(c_auto, c_exact)
+    assert np.array_equal(c_filter, c_exact) and np.array_equal(c_tensor, c_exact) and np.array_equal(c_auto, c_exact)
     rng = np.random.default_rng(0)
     pick = np.unique(np.concatenate([rng.integers(0, H, 40), [int(np.argmax(c_exact))]]))
     c_cpu, co_cpu, _ = oracle.sac_score(xyz, None, p, samples[pick])
@@ -73,7 +75,7 @@ def test_c3_large_cluster_scoring(ctx, oracle, kind, model):
 
 def test_c5_size_plane_slice(ctx, oracle):
     """config 5 shape on one GPU: the 50 M-point cloud (0.8 GB) with one rank's slice of the hypothesis stream;
-    the filter and the exact kernel agree everywhere and 6 hypotheses agree with the oracle"""
+    the tensor-core kernel, the filter and the exact kernel agree everywhere and 6 hypotheses agree with the oracle"""
     n = 50_000_000
     xyz = scenes.plane_outlier_cloud(n, seed=5)
     cloud = ctx.stage(xyz)
@@ -83,10 +85,12 @@ def test_c5_size_plane_slice(ctx, oracle):
     p = pkg.default_support_sac_params()
     ctx.lib.pitt_debug_plane_mode(2)
     c_filter = _device_counts(ctx, cloud, p, samples)
+    ctx.lib.pitt_debug_plane_mode(3)
+    c_tensor = _device_counts(ctx, cloud, p, samples)
     ctx.lib.pitt_debug_plane_mode(1)
     c_exact = _device_counts(ctx, cloud, p, samples)
     ctx.lib.pitt_debug_plane_mode(0)
-    assert np.array_equal(c_filter, c_exact)
+    assert np.array_equal(c_filter, c_exact) and np.array_equal(c_tensor, c_exact)
     pick = rng.integers(0, H, 6)
     c_cpu = oracle.sac_score(xyz, None, p, samples[pick])[0]
     assert np.array_equal(c_exact[pick], c_cpu)

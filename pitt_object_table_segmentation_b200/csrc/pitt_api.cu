@@ -540,7 +540,7 @@ void pitt_debug_plane_tc_stats(int enable, uint64_t* out2) {
 }
 /* per-CTA (SM id << 48 | cycles) of the last call made while statistics were enabled, 160 entries */
 void pitt_debug_plane_tc_cta_cycles(uint64_t* out160) {
-  for (int i = 0; i < 168; ++i) out160[i] = g_plane_tc_stats[2 + i];
+  for (int i = 0; i < 176; ++i) out160[i] = g_plane_tc_stats[2 + i];
 }
 int pitt_debug_plane_tc_dump(int enable, float* out /*128*256 + 2, nullable*/) {
   g_plane_tc_dump = enable;

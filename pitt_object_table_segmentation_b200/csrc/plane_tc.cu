@@ -42,7 +42,7 @@ constexpr int TC_A_MMA_BYTES = TC_M * 32;       // 4096
 constexpr int TC_A_BLOCK_BYTES = TC_MMAS * TC_A_MMA_BYTES;  // 12288 per hypothesis block
 constexpr int TC_B_MMA_BYTES = TC_N * 32;       // 4096
 constexpr int TC_B_TILE_BYTES = TC_MMAS * TC_B_MMA_BYTES;   // 12288
-constexpr int TC_ASTAGES = 3;
+constexpr int TC_ASTAGES = 4;
 constexpr int TC_SB = 20;                       // hypothesis blocks per super-block (counts in smem)
 constexpr float TC_ACC_ULPS = 8.0f;             // bound on the tensor core accumulation error, in u m
 constexpr float TC_WINDOW = 0.36f;              // sigma * beta_t must stay below this (see header)
@@ -53,7 +53,7 @@ constexpr int TC_OFF_A = TC_OFF_B + TC_TILES * TC_B_TILE_BYTES;       // 49152
 constexpr int TC_OFF_RAW = TC_OFF_A + TC_ASTAGES * TC_A_BLOCK_BYTES;  // 86016
 constexpr int TC_OFF_CNT = TC_OFF_RAW + TC_CHUNK * 16;                // 94208
 constexpr int TC_OFF_BAR = TC_OFF_CNT + TC_SB * TC_M * 4;             // 104448
-constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 16 * 8 + 16;
+constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 24 * 8 + 16;
 
 struct PlaneTcParams {
   float sigma;   // power of two
@@ -315,8 +315,8 @@ __device__ __forceinline__ void tc_ld_wait2(uint32_t (&a)[32], uint32_t (&b)[32]
 // so the MMA / commit / wake-up latency never sits on the critical path. DBG adds the accumulator dump and the
 // timing experiments (variant bits: 1 = no accumulation, 2 = one MMA per tile, 4 = no TMEM loads).
 constexpr int TC_EPI_WARPS = 16, TC_EPI_THREADS = 32 * TC_EPI_WARPS;
-constexpr int TC_MMA_WARPS = 2;  // MMA issuing warps (on different SM sub-partitions), each feeding TC_TILES / TC_MMA_WARPS buffers
-constexpr int TC_THREADS = TC_EPI_THREADS + 32 * TC_MMA_WARPS + 32;
+constexpr int TC_MMA_WARPS = TC_TILES;  // one MMA issuing warp per accumulator buffer, one per SM sub-partition
+constexpr int TC_THREADS = TC_EPI_THREADS + 32 * TC_MMA_WARPS;
 template <bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict__ recs, int H, const float4* __restrict__ image,
@@ -330,16 +330,17 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t s_base = smem_u32(smem);
   const uint32_t bar0 = s_base + TC_OFF_BAR;
-  // barriers: [0..2] a_full, [3..5] a_empty, [6..9] tmem_full, [10..13] tmem_empty, [14] b_full
+  // barriers: [0..3] a_full, [4..7] a_empty, [8..11] tmem_full, [12..15] tmem_empty, [16] b_full
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + TC_OFF_BAR + 16 * 8);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + TC_OFF_BAR + 24 * 8);
   float4* s_raw = reinterpret_cast<float4*>(smem + TC_OFF_RAW);
   int* s_cnt = reinterpret_cast<int*>(smem + TC_OFF_CNT);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TC_ASTAGES; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(3 + i), TC_MMA_WARPS); }
-    for (int i = 0; i < TC_TILES; ++i) { mbar_init(BAR(6 + i), 1); mbar_init(BAR(10 + i), 4); }
-    mbar_init(BAR(14), TC_EPI_THREADS);
+    static_assert(TC_ASTAGES == 4 && TC_TILES == 4, "barrier numbering");
+    for (int i = 0; i < TC_ASTAGES; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(4 + i), TC_MMA_WARPS); }
+    for (int i = 0; i < TC_TILES; ++i) { mbar_init(BAR(8 + i), 1); mbar_init(BAR(12 + i), 4); }
+    mbar_init(BAR(16), TC_EPI_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_EPI_WARPS) {
@@ -352,43 +353,46 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
   tc_fence_after();
   const uint32_t tmem = *s_tmem;
 
-  if (warp == TC_EPI_WARPS + TC_MMA_WARPS) {
-    // ===================== producer: hypothesis block images, global -> shared (bulk async copy)
-    // (the whole warp runs the loop so that every operand stays warp-uniform; one elected lane issues)
+  if (warp >= TC_EPI_WARPS) {
+    // ===================== MMA issuers: warp w feeds accumulator buffer w (tile w of every chunk); warp 0 also
+    // streams the hypothesis block images global -> shared (bulk async copy), TC_ASTAGES - 1 blocks ahead.
+    // The whole warp runs the loop so that every operand stays warp-uniform; one elected lane issues.
     {
-      uint32_t ac = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int sb = item / n_chunks;
-        const int hb0 = sb * TC_SB, hb1 = min(n_hb, hb0 + TC_SB);
-        for (int hb = hb0; hb < hb1; ++hb, ++ac) {
-          const uint32_t st = ac % TC_ASTAGES, ph = (ac / TC_ASTAGES) & 1u;
-          mbar_wait(BAR(3 + st), ph ^ 1u);
+      const int t = warp - TC_EPI_WARPS;
+      uint32_t ac = 0, cc = 0;
+      long long tw = 0, tm = 0, tcm = 0, ta = 0, tb = 0;  // DBG: cycles in empty-wait, MMA issue, commit, A wait, B wait
+      // producer cursor: block sequence number, item and hypothesis block of the next image to request
+      uint32_t pa = 0;
+      int p_item = blockIdx.x, p_hb = (p_item < n_items) ? (p_item / n_chunks) * TC_SB : 0;
+      auto produce_until = [&](uint32_t limit) {
+        while (pa < limit && p_item < n_items) {
+          const uint32_t st = pa % TC_ASTAGES, ph = (pa / TC_ASTAGES) & 1u;
+          mbar_wait(BAR(4 + st), ph ^ 1u);  // every MMA that read the previous block of this stage has completed
           if (elect_one()) {
             mbar_expect_tx(BAR(st), TC_A_BLOCK_BYTES);
-            const float4* src = image + (size_t)hb * (TC_A_BLOCK_BYTES / 16);
+            const float4* src = image + (size_t)p_hb * (TC_A_BLOCK_BYTES / 16);
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(s_base + TC_OFF_A + st * TC_A_BLOCK_BYTES), "l"(src), "r"(TC_A_BLOCK_BYTES), "r"(BAR(st))
                          : "memory");
           }
           __syncwarp();
+          ++pa;
+          const int p_sb = p_item / n_chunks;
+          if (++p_hb >= min(n_hb, (p_sb + 1) * TC_SB)) {
+            p_item += gridDim.x;
+            p_hb = (p_item < n_items) ? (p_item / n_chunks) * TC_SB : 0;
+          }
         }
-      }
-    }
-    __syncwarp();
-  } else if (warp >= TC_EPI_WARPS) {
-    // ===================== MMA issuers (the whole warp runs the loop, one elected lane issues)
-    {
-      constexpr int TPW = TC_TILES / TC_MMA_WARPS;
-      const int t_first = (warp - TC_EPI_WARPS) * TPW;
-      uint32_t ac = 0, cc = 0;
-      long long tw = 0, tm = 0, tcm = 0, ta = 0, tb = 0;  // DBG: cycles in empty-wait, MMA issue, commit, A wait, B wait
+      };
+      if (t == 0) produce_until(TC_ASTAGES - 1);
       for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++cc) {
         const int sb = item / n_chunks;
         const int hb0 = sb * TC_SB, hb1 = min(n_hb, hb0 + TC_SB);
         long long c0 = DBG ? clock64() : 0;
-        mbar_wait(BAR(14), cc & 1u);  // the chunk's B image is in shared memory
+        mbar_wait(BAR(16), cc & 1u);  // the chunk's B image is in shared memory
         tc_fence_after();
         if (DBG) tb += clock64() - c0;
+        const uint32_t b_addr = s_base + TC_OFF_B + t * TC_B_TILE_BYTES;
         for (int hb = hb0; hb < hb1; ++hb, ++ac) {
           const uint32_t st = ac % TC_ASTAGES, ph = (ac / TC_ASTAGES) & 1u;
           if (DBG) c0 = clock64();
@@ -396,32 +400,28 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
           tc_fence_after();
           if (DBG) ta += clock64() - c0;
           const uint32_t a_addr = s_base + TC_OFF_A + st * TC_A_BLOCK_BYTES;
+          if (DBG) c0 = clock64();
+          mbar_wait(BAR(12 + t), (ac & 1u) ^ 1u);  // group t has loaded the previous contents of buffer t
+          tc_fence_after();
+          long long c1 = DBG ? clock64() : 0;
+          long long c2 = 0;
+          if (elect_one()) {
 #pragma unroll
-          for (int tt = 0; tt < TPW; ++tt) {
-            const int t = t_first + tt;
-            if (DBG) c0 = clock64();
-            mbar_wait(BAR(10 + t), (ac & 1u) ^ 1u);  // group t has loaded the previous contents of buffer t
-            tc_fence_after();
-            long long c1 = DBG ? clock64() : 0;
-            const uint32_t b_addr = s_base + TC_OFF_B + t * TC_B_TILE_BYTES;
-            long long c2 = 0;
-            if (elect_one()) {
-#pragma unroll
-              for (int j = 0; j < TC_MMAS; ++j)
-                if (!DBG || j == 0 || !(variant & 2))
-                  tc_mma_tf32(tmem + t * TC_N, tc_smem_desc(a_addr + j * TC_A_MMA_BYTES), tc_smem_desc(b_addr + j * TC_B_MMA_BYTES),
-                              TC_IDESC, j > 0 ? 1u : 0u);
-              if (DBG) c2 = clock64();
-              tc_commit(BAR(6 + t));
-              if (tt == TPW - 1) tc_commit(BAR(3 + st));  // the hypothesis stage is free once these MMAs have read it
-            }
-            __syncwarp();
-            if (DBG) { tw += c1 - c0; tm += c2 - c1; tcm += clock64() - c2; }
+            for (int j = 0; j < TC_MMAS; ++j)
+              if (!DBG || j == 0 || !(variant & 2))
+                tc_mma_tf32(tmem + t * TC_N, tc_smem_desc(a_addr + j * TC_A_MMA_BYTES), tc_smem_desc(b_addr + j * TC_B_MMA_BYTES),
+                            TC_IDESC, j > 0 ? 1u : 0u);
+            if (DBG) c2 = clock64();
+            tc_commit(BAR(8 + t));
+            tc_commit(BAR(4 + st));  // the hypothesis stage is free once the MMAs of all four warps have read it
           }
+          __syncwarp();
+          if (DBG) { tw += c1 - c0; tm += c2 - c1; tcm += clock64() - c2; }
+          if (t == 0) produce_until(ac + TC_ASTAGES);  // keep TC_ASTAGES - 1 blocks beyond the one just issued in flight
         }
       }
-      if (DBG && stats && blockIdx.x == 0 && lane == 0 && warp == TC_EPI_WARPS) {
-        stats[162] = tw; stats[163] = tm; stats[164] = tcm; stats[165] = ta; stats[166] = tb; stats[167] = ac * TPW;
+      if (DBG && stats && blockIdx.x == 0 && lane == 0 && t == 0) {
+        stats[162] = tw; stats[163] = tm; stats[164] = tcm; stats[165] = ta; stats[166] = tb; stats[167] = ac;
       }
     }
     __syncwarp();
@@ -434,6 +434,7 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
     uint32_t uc = 0;            // uses of buffer g so far
     int cur_sb = -1;
     unsigned n_seg = 0, n_redo = 0;
+    long long e_wait = 0, e_rt = 0, e_hold = 0, e_arr = 0, e_ld = 0, e_math = 0, e_tail = 0;  // DBG: cycles waiting for full, arrive -> next full seen, full seen -> arrive
     auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); };
     auto flush = [&]() {
       if (cur_sb < 0) return;
@@ -477,7 +478,7 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
         tb[2 * MF4 + o + 8] = make_float4(1.f, 0.f, 0.f, 0.f);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(BAR(14));
+      mbar_arrive(BAR(16));
       epi_sync();  // s_raw visible to every epilogue warp
 
 #pragma unroll 1
@@ -486,8 +487,10 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
         // this lane's hypothesis in the exact form, for re-evaluations (broadcast by shuffle, no memory latency there)
         float4 myrec = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
         if (h < H) myrec = __ldg(reinterpret_cast<const float4*>(recs[h].v));
-        mbar_wait(BAR(6 + g), uc & 1u);
+        long long e0 = DBG ? clock64() : 0;
+        mbar_wait(BAR(8 + g), uc & 1u);
         tc_fence_after();
+        if (DBG) { e_wait += clock64() - e0; if (e_arr) e_rt += clock64() - e_arr; e0 = clock64(); }
         unsigned long long S1[2] = {0ull, 0ull}, S2[2] = {0ull, 0ull};
         uint32_t ra[32], rb[32];
         if (DBG && (variant & 5)) {
@@ -503,19 +506,22 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
           }
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(10 + g));
+          if (lane == 0) mbar_arrive(BAR(12 + g));
           continue;
         }
 #pragma unroll
         for (int b = 0; b < TC_N / 64; ++b) {
+          long long p0 = DBG ? clock64() : 0;
           tc_ld32(ra, taddr + 64 * b);
           tc_ld32(rb, taddr + 64 * b + 32);
           tc_ld_wait2(ra, rb);
+          if (DBG) e_ld += clock64() - p0;
           if (b == TC_N / 64 - 1) {
             // this warp has read its part of the accumulator: hand the buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(10 + g));
+            if (lane == 0) mbar_arrive(BAR(12 + g));
+            if (DBG) { e_arr = clock64(); e_hold += e_arr - e0; }
           }
           if (DBG && dbg && item == 0 && hb == 0 && g < 2) {
 #pragma unroll
@@ -524,6 +530,7 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
               dbg[row * 256 + g * TC_N + 64 * b + 32 + i] = __uint_as_float(rb[i]);
             }
           }
+          if (DBG) p0 = clock64();
           if (len == TC_N) {
             tc_accumulate32(ra, P.C, S1, S2);
             tc_accumulate32(rb, P.C, S1, S2);
@@ -531,7 +538,9 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
             tc_accumulate32_masked(ra, P.C, S1, S2, len - 64 * b);
             tc_accumulate32_masked(rb, P.C, S1, S2, len - 64 * b - 32);
           }
+          if (DBG) { asm volatile("" : "+l"(S1[0]), "+l"(S1[1]), "+l"(S2[0]), "+l"(S2[1])); e_math += clock64() - p0; }
         }
+        long long p1 = DBG ? clock64() : 0;
         const float s1 = tc_sum2(tc_add2(S1[0], S1[1]));
         const float s2 = tc_sum2(tc_add2(S2[0], S2[1]));
         int c = (int)rintf(s1);
@@ -550,9 +559,11 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
           if (lane == L) c = e;
         }
         if (c) atomicAdd(&s_cnt[(hb - hb0) * TC_M + row], c);
+        if (DBG) e_tail += clock64() - p1;
       }
     }
     flush();
+    if (DBG && stats && blockIdx.x == 0 && threadIdx.x == 0) { stats[168] = e_wait; stats[169] = e_rt; stats[170] = e_hold; stats[171] = uc; stats[172] = e_ld; stats[173] = e_math; stats[174] = e_tail; }
     if (stats && lane == 0) {
       atomicAdd(stats + 0, (unsigned long long)n_seg);
       if (n_redo) atomicAdd(stats + 1, (unsigned long long)n_redo);
@@ -573,7 +584,7 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-unsigned long long g_plane_tc_stats[2 + 160 + 8] = {0, 0};
+unsigned long long g_plane_tc_stats[2 + 160 + 16] = {0, 0};
 int g_plane_tc_collect_stats = 0;
 int g_plane_tc_dump = 0;
 int g_plane_tc_variant = 0;
@@ -609,11 +620,11 @@ int launch_score_plane_tc(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_re
   float* d_dbg = nullptr;
   PITT_TRY(arena_alloc(ctx, 4, &d_scr));
   PITT_TRY(arena_alloc(ctx, 1, &d_P));
-  PITT_TRY(arena_alloc(ctx, 2 + 160 + 8, &d_stats));
+  PITT_TRY(arena_alloc(ctx, 2 + 160 + 16, &d_stats));
   PITT_TRY(arena_alloc(ctx, (size_t)n_hb * (TC_A_BLOCK_BYTES / 16), &d_image));
   if (g_plane_tc_dump) PITT_TRY(arena_alloc(ctx, (size_t)TC_M * 256, &d_dbg));
   PITT_CUDA(ctx, cudaMemsetAsync(d_scr, 0, 4 * sizeof(unsigned), ctx->stream));
-  PITT_CUDA(ctx, cudaMemsetAsync(d_stats, 0, (2 + 160 + 8) * sizeof(unsigned long long), ctx->stream));
+  PITT_CUDA(ctx, cudaMemsetAsync(d_stats, 0, (2 + 160 + 16) * sizeof(unsigned long long), ctx->stream));
   int ab = std::min(cdiv(n, 256 * 8), ctx->sm_count * 8);
   tc_absmax_kernel<<<ab, 256, 0, ctx->stream>>>(c->d_xyz, n, d_scr);
   TC_LAUNCH_CHECK(ctx, "tc_absmax_kernel");

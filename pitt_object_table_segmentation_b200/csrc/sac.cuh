@@ -53,7 +53,7 @@ extern int g_force_generic_plane;
 extern int g_plane_mode;
 extern unsigned long long g_plane_filter_stats[2];
 extern int g_plane_filter_collect_stats;
-extern unsigned long long g_plane_tc_stats[2 + 160 + 8];
+extern unsigned long long g_plane_tc_stats[2 + 160 + 16];
 extern int g_plane_tc_collect_stats;
 extern int g_plane_tc_dump;
 extern int g_plane_tc_variant;

@@ -142,7 +142,7 @@ def cta_cycles(n, H):
         ctx.lib.pitt_debug_plane_tc_stats(1, None)
         score(ctx, cloud, p, samples, 3)
         ctx.lib.pitt_debug_plane_tc_stats(0, None)
-        buf = (C.c_uint64 * 168)()
+        buf = (C.c_uint64 * 176)()
         ctx.lib.pitt_debug_plane_tc_cta_cycles(buf)
         v = np.array(list(buf), dtype=np.uint64)[:148]
         cyc = (v & np.uint64((1 << 48) - 1)).astype(np.int64)
@@ -154,6 +154,10 @@ def cta_cycles(n, H):
         mm = [int(x) for x in list(buf)[160:166]]
         print(f"  MMA thread of CTA 0: tiles {mm[5]}; per tile cycles: empty-wait {mm[0] / max(mm[5], 1):.0f}, MMA issue {mm[1] / max(mm[5], 1):.0f}, "
               f"commit {mm[2] / max(mm[5], 1):.0f}; per hb A-wait {mm[3] * 4 / max(mm[5], 1):.0f}; B-wait total {mm[4]}")
+        ee = [int(x) for x in list(buf)[166:173]]
+        print(f"  epilogue warp 0 of CTA 0: tiles {ee[3]}; per tile cycles: waiting for full {ee[0] / max(ee[3], 1):.0f}, "
+              f"arrive -> next full seen {ee[1] / max(ee[3], 1):.0f}, full seen -> arrive (TMEM loads + first half of the math) {ee[2] / max(ee[3], 1):.0f}; "
+              f"TMEM loads {ee[4] / max(ee[3], 1):.0f}, math {ee[5] / max(ee[3], 1):.0f}, tail {ee[6] / max(ee[3], 1):.0f}")
         print("  blocks 0..29 mean", cyc[:30].mean(), " blocks 30..147 mean", cyc[30:].mean())
     ctx.lib.pitt_debug_plane_tc_variant(0)
 

@@ -1,32 +1,38 @@
 // plane_tc.cu — K3t: plane hypothesis scoring with the dot products on the 5th-generation tensor
-// cores (tcgen05.mma kind::tf32, accumulators in TMEM) and an exact re-evaluation of every
-// evaluation the tensor result cannot decide.
+// cores (tcgen05.mma kind::f16 on BF16 pieces, FP32 accumulators in TMEM) and an exact re-evaluation
+// of every evaluation the tensor result cannot decide.
 //
 // Replaces the point loop of pcl::SampleConsensusModelPlane::countWithinDistance reached from
 // seg.segment() at supports_segmentation_srv.cpp:110 and plane_segmentation_srv.cpp:67
 // (SURVEY.md B.3): count_h = #{ i : |fl(a x_i + b y_i + c z_i + d)| < thr }.
 //
 // The exact predicate needs 6 separately rounded FP32 operations per evaluation. Here
-//   (1) every float is split without error into three TF32 pieces v = v1 + v2 + v3 (11 + 11 + 2
-//       significand bits, low 13 bits of each piece are zero, so the tensor core's TF32 read is exact),
-//   (2) three chained 128 x 256 x 8 MMAs sum the 18 products a_i x_j (i + j <= 4) and d1 + d2 + d3;
-//       what is dropped is below 2^-28 m, m = |a x| + |b y| + |c z| + |d|; the only real error is the
-//       tensor core's FP32 accumulation, bounded by TC_ACC_ULPS u m (u = 2^-24; measured,
-//       profiles/r01_plane_tc_numerics.md),
+//   (1) every float is split without error into three BF16 pieces v = v1 + v2 + v3 (8 + 8 + 8
+//       significand bits; each piece has its low 16 bits clear, so it IS a BF16 number),
+//   (2) two chained 128 x 256 x 16 MMAs sum, per coordinate, the 8 products a_i x_j with
+//       (i, j) != (3, 3), and d1 + d2 + d3 (27 of the 32 K slots); every product is exact (8 x 8 bits)
+//       and what is dropped, a3 x3, is below 2^-27 m, m = |a x| + |b y| + |c z| + |d|; the only real
+//       error is the tensor core's FP32 accumulation, bounded by TC_ACC_ULPS u m (u = 2^-24;
+//       measured, profiles/r01_plane_tc_numerics.md),
 //   (3) hypotheses are pre-scaled by a power of two sigma, so the accumulator holds s~ = sigma s and
 //       u = sat(C - |s~|), C = fl(sigma thr + 1/2), is exactly 1 for a certain inlier, exactly 0 for a
 //       certain outlier and fractional inside the window | |s~| - sigma thr | < 1/2, which sigma makes
 //       at least 1/0.36 times wider than the error bound of s~,
-//   (4) per (hypothesis, 128-point segment) the epilogue accumulates S1 = sum u and S2 = sum u^2 (3 FMA-pipe
-//       operations per evaluation, no integer work). S1 - S2 <= 0.1 proves that every fractional u is
-//       within 0.115 of 0 or 1, i.e. decided with margin, and that rint(S1) is the exact count;
-//       otherwise the segment is re-evaluated by the whole warp in the exact operation order.
+//   (4) per (hypothesis, 128-point segment) the epilogue accumulates S1 = sum u and S2 = sum u^2 (one
+//       FADD.SAT per evaluation, one packed FADD2 and one packed FFMA2 per two evaluations, no integer
+//       work). S1 - S2 <= 0.1 proves that every fractional u is within 0.115 of 0 or 1, i.e. decided
+//       with margin, and that rint(S1) is the exact count; otherwise the segment is re-evaluated by
+//       the whole warp in the exact operation order.
 // Result: counts bit-identical to plane_score_kernel (tests/test_gpu_plane_tc.py).
 //
-// Thread = hypothesis (TMEM lane), columns = points: no cross-lane reduction anywhere. The point
+// Thread = hypothesis (TMEM lane), columns = points: no cross-lane reduction anywhere. A 512-point
 // chunk is stationary in shared memory (split once per chunk by the epilogue warps), hypothesis
-// blocks stream through a 3-stage cp.async.bulk pipeline, accumulators are double buffered in TMEM
-// (2 x 256 columns), counts for up to 5120 hypotheses are kept in shared memory and flushed once.
+// block images stream through a 4-stage cp.async.bulk pipeline. TMEM holds two 256-column
+// accumulators = the two halves ("phases") of the chunk; each of the 16 epilogue warps takes 64
+// columns of accumulator 0, hands it back, does the arithmetic, then the same with accumulator 1:
+// an accumulator is refilled by the tensor pipe while the FMA pipe works on the other one, so the
+// two pipes overlap even though all warps run in lockstep. Counts for up to 2560 hypotheses are kept
+// in shared memory and flushed once per super-block.
 #include <math_constants.h>
 
 #include "sac.cuh"
@@ -34,26 +40,32 @@
 namespace pitt {
 
 constexpr int TC_M = 128;                       // hypotheses per block (UMMA M, TMEM lanes)
-constexpr int TC_N = 128;                       // points per tile (UMMA N, TMEM columns)
-constexpr int TC_TILES = 4;                     // tiles per point chunk = TMEM accumulator buffers = epilogue warp groups
-constexpr int TC_CHUNK = TC_N * TC_TILES;       // 512 points stationary in shared memory
-constexpr int TC_MMAS = 3;                      // chained MMAs per tile (K = 8 TF32 each)
+constexpr int TC_N = 256;                       // points per MMA (UMMA N) = columns of one accumulator
+constexpr int TC_PHASES = 2;                    // accumulators in TMEM = tiles per point chunk
+constexpr int TC_CHUNK = TC_N * TC_PHASES;      // 512 points stationary in shared memory
+constexpr int TC_RUN = 64;                      // columns one epilogue warp takes from an accumulator
+constexpr int TC_MMAS = 2;                      // chained MMAs per tile (K = 16 BF16 each)
 constexpr int TC_A_MMA_BYTES = TC_M * 32;       // 4096
-constexpr int TC_A_BLOCK_BYTES = TC_MMAS * TC_A_MMA_BYTES;  // 12288 per hypothesis block
-constexpr int TC_B_MMA_BYTES = TC_N * 32;       // 4096
-constexpr int TC_B_TILE_BYTES = TC_MMAS * TC_B_MMA_BYTES;   // 12288
+constexpr int TC_A_BLOCK_BYTES = TC_MMAS * TC_A_MMA_BYTES;  // 8192 per hypothesis block
+constexpr int TC_B_MMA_BYTES = TC_N * 32;       // 8192
+constexpr int TC_B_TILE_BYTES = TC_MMAS * TC_B_MMA_BYTES;   // 16384
 constexpr int TC_ASTAGES = 4;
 constexpr int TC_SB = 20;                       // hypothesis blocks per super-block (counts in smem)
+constexpr int TC_EPI_WARPS = 16, TC_EPI_THREADS = 32 * TC_EPI_WARPS;
+constexpr int TC_MMA_WARPS = TC_PHASES;         // one MMA issuing warp per accumulator; warp 0 also streams the images
+constexpr int TC_THREADS = TC_EPI_THREADS + 32 * TC_MMA_WARPS;
 constexpr float TC_ACC_ULPS = 8.0f;             // bound on the tensor core accumulation error, in u m
 constexpr float TC_WINDOW = 0.36f;              // sigma * beta_t must stay below this (see header)
 
 // shared memory carve-up (bytes)
 constexpr int TC_OFF_B = 0;
-constexpr int TC_OFF_A = TC_OFF_B + TC_TILES * TC_B_TILE_BYTES;       // 49152
-constexpr int TC_OFF_RAW = TC_OFF_A + TC_ASTAGES * TC_A_BLOCK_BYTES;  // 86016
-constexpr int TC_OFF_CNT = TC_OFF_RAW + TC_CHUNK * 16;                // 94208
-constexpr int TC_OFF_BAR = TC_OFF_CNT + TC_SB * TC_M * 4;             // 104448
-constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 24 * 8 + 16;
+constexpr int TC_OFF_A = TC_OFF_B + TC_PHASES * TC_B_TILE_BYTES;      // 32768
+constexpr int TC_OFF_RAW = TC_OFF_A + TC_ASTAGES * TC_A_BLOCK_BYTES;  // 65536
+constexpr int TC_OFF_CNT = TC_OFF_RAW + TC_CHUNK * 16;                // 73728
+constexpr int TC_OFF_BAR = TC_OFF_CNT + TC_SB * TC_M * 4;             // 83968
+constexpr int TC_SMEM_BYTES = TC_OFF_BAR + 16 * 8 + 16;
+// barriers
+constexpr int TC_BAR_AFULL = 0, TC_BAR_AEMPTY = 4, TC_BAR_FULL = 8, TC_BAR_EMPTY = 10, TC_BAR_B = 12;
 
 struct PlaneTcParams {
   float sigma;   // power of two
@@ -98,20 +110,20 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// K-major, no swizzle: 8-row x 16-byte core matrices; the two K halves of a row group are LBO = 128 B
-// apart, consecutive 8-row groups SBO = 256 B apart (cute::UMMA::SmemDescriptor, version 1).
+// K-major, no swizzle: 8-row x 16-byte core matrices (8 BF16 of K each); the two K halves of a row group are
+// LBO = 128 B apart, consecutive 8-row groups SBO = 256 B apart (cute::UMMA::SmemDescriptor, version 1).
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
 }
-// cute::UMMA::InstrDescriptor: D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+// cute::UMMA::InstrDescriptor: D = F32, A = B = BF16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
 
 #define TC_R32(r) \
   "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), \
@@ -136,13 +148,23 @@ __device__ __forceinline__ void tc_ld32(uint32_t (&r)[32], uint32_t taddr) {
 __device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" : TC_RW32(r)::"memory");
 }
+__device__ __forceinline__ void tc_ld_wait2(uint32_t (&a)[32], uint32_t (&b)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : TC_RW32(a), TC_RW32(b)::"memory");
+}
 
-// exact TF32 pieces: v = v1 + v2 + v3, each with the low 13 significand bits clear
+// exact BF16 pieces: v = v1 + v2 + v3, each with the low 16 bits of its FP32 pattern clear
 __device__ __forceinline__ void tc_split3(float v, float& v1, float& v2, float& v3) {
-  v1 = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  v1 = __uint_as_float(__float_as_uint(v) & 0xFFFF0000u);
   const float r = v - v1;  // exact
-  v2 = __uint_as_float(__float_as_uint(r) & 0xFFFFE000u);
-  v3 = r - v2;             // exact, at most 2 significant bits
+  v2 = __uint_as_float(__float_as_uint(r) & 0xFFFF0000u);
+  v3 = r - v2;             // exact, at most 8 significant bits
+}
+// two BF16-exact floats -> one word (lo in bits 0..15)
+__device__ __forceinline__ uint32_t tc_bf2(float lo, float hi) {
+  return __byte_perm(__float_as_uint(lo), __float_as_uint(hi), 0x7632);
+}
+__device__ __forceinline__ uint4 tc_bf8(float f0, float f1, float f2, float f3, float f4, float f5, float f6, float f7) {
+  return make_uint4(tc_bf2(f0, f1), tc_bf2(f2, f3), tc_bf2(f4, f5), tc_bf2(f6, f7));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -177,8 +199,8 @@ __global__ void tc_params_kernel(const unsigned* __restrict__ absmax, float thr_
     const double R = sqrt(X * X + Y * Y + Z * Z);
     const double G = 2.0 * R * (1.0 + 1e-6) + 1e-30;
     const double u = 5.9604644775390625e-08;  // 2^-24
-    // |s~/sigma - s_exact_order| <= (3.0001 [exact order vs real] + 2^-4 [dropped products] + acc_ulps) u G
-    const double beta = (3.0001 + 0.0625 + (double)acc_ulps) * u * G + 1e-30;
+    // |s~/sigma - s_exact_order| <= (3.0001 [exact order vs real] + 2^-3 [dropped a3 x3 products] + acc_ulps) u G
+    const double beta = (3.0001 + 0.125 + (double)acc_ulps) * u * G + 1e-30;
     const double thr = (double)thr_up;
     // largest power of two with sigma beta + 2^-23 (sigma thr + 1) <= TC_WINDOW
     // (the second term covers the rounding of C and of the saturating subtraction)
@@ -203,12 +225,14 @@ __global__ void tc_params_kernel(const unsigned* __restrict__ absmax, float thr_
   *out = P;
 }
 
-// A-operand image of all hypothesis blocks: per block 3 MMAs x (16 row groups x [8 rows x 16 B | 8 rows x 16 B]).
-//   MMA 0: k0..7 = a1 a2 a3 b1 | b2 b3 c1 c2     (times x3 x2 x1 y3 | y2 y1 z3 z2)
-//   MMA 1: k0..7 = c3 d3 a1 a2 | b1 b2 c1 c2     (times z1 1  x2 x1 | y2 y1 z2 z1)
-//   MMA 2: k0..7 = a1 b1 c1 d1 | d2 0  0  0      (times x1 y1 z1 1  | 1  0  0  0 )
+// K-slot assignment of the two MMAs (hypothesis piece, point piece); the point side mirrors it in tc_point_image.
+//   MMA 0 (small terms): (a1,x3) (a2,x2) (a3,x1) (a2,x3) (a3,x2) (b1,y3) (b2,y2) (b3,y1) |
+//                        (b2,y3) (b3,y2) (c1,z3) (c2,z2) (c3,z1) (c2,z3) (c3,z2) (d3,1)
+//   MMA 1 (large terms): (a1,x1) (a1,x2) (a2,x1) (b1,y1) (b1,y2) (b2,y1) (c1,z1) (c1,z2) |
+//                        (c2,z1) (d1,1) (d2,1) 0 0 0 0 0
+// A-operand image of one hypothesis block: 2 MMAs x (16 row groups x [8 rows x 16 B | 8 rows x 16 B]).
 __global__ void __launch_bounds__(TC_M) tc_hyp_image_kernel(const HypRec* __restrict__ recs, int H, const PlaneTcParams* __restrict__ Pp,
-                                                            float4* __restrict__ image) {
+                                                            uint4* __restrict__ image) {
   const PlaneTcParams P = *Pp;
   if (!P.use) return;
   const int h = blockIdx.x * TC_M + threadIdx.x;
@@ -230,14 +254,26 @@ __global__ void __launch_bounds__(TC_M) tc_hyp_image_kernel(const HypRec* __rest
   tc_split3(c, c1, c2, c3);
   tc_split3(d, d1, d2, d3);
   const int row = threadIdx.x;
-  float4* blk = image + (size_t)blockIdx.x * (TC_A_BLOCK_BYTES / 16);
-  const int o = (row >> 3) * 16 + (row & 7);  // float4 index inside one MMA image; the second K half is 8 float4 further
-  blk[0 * 256 + o] = make_float4(a1, a2, a3, b1);
-  blk[0 * 256 + o + 8] = make_float4(b2, b3, c1, c2);
-  blk[1 * 256 + o] = make_float4(c3, d3, a1, a2);
-  blk[1 * 256 + o + 8] = make_float4(b1, b2, c1, c2);
-  blk[2 * 256 + o] = make_float4(a1, b1, c1, d1);
-  blk[2 * 256 + o + 8] = make_float4(d2, 0.f, 0.f, 0.f);
+  uint4* blk = image + (size_t)blockIdx.x * (TC_A_BLOCK_BYTES / 16);
+  const int o = (row >> 3) * 16 + (row & 7);  // 16-byte index inside one MMA image; the second K half is 8 further
+  constexpr int MV = TC_A_MMA_BYTES / 16;
+  blk[0 * MV + o] = tc_bf8(a1, a2, a3, a2, a3, b1, b2, b3);
+  blk[0 * MV + o + 8] = tc_bf8(b2, b3, c1, c2, c3, c2, c3, d3);
+  blk[1 * MV + o] = tc_bf8(a1, a1, a2, b1, b1, b2, c1, c1);
+  blk[1 * MV + o + 8] = tc_bf8(c2, d1, d2, 0.f, 0.f, 0.f, 0.f, 0.f);
+}
+// B-operand rows of one point (pr = row inside its 256-point tile)
+__device__ __forceinline__ void tc_point_image(uint4* tile, int pr, float4 p) {
+  float x1, x2, x3, y1, y2, y3, z1, z2, z3;
+  tc_split3(p.x, x1, x2, x3);
+  tc_split3(p.y, y1, y2, y3);
+  tc_split3(p.z, z1, z2, z3);
+  const int o = (pr >> 3) * 16 + (pr & 7);
+  constexpr int MV = TC_B_MMA_BYTES / 16;
+  tile[0 * MV + o] = tc_bf8(x3, x2, x1, x3, x2, y3, y2, y1);
+  tile[0 * MV + o + 8] = tc_bf8(y3, y2, z3, z2, z1, z3, z2, 1.f);
+  tile[1 * MV + o] = tc_bf8(x1, x2, x1, y1, y2, y1, z1, z2);
+  tile[1 * MV + o + 8] = tc_bf8(z1, 1.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -255,8 +291,8 @@ __device__ __forceinline__ int tc_recount(const float4* pts, int len, float4 r, 
   return __reduce_add_sync(0xffffffffu, c);
 }
 
-// Packed FP32 pairs: one issue slot per two additions / FMAs (the FMA pipe is busy 2 cycles either way), which
-// leaves issue slots for the control instructions of the epilogue.
+// Packed FP32 pairs: FADD2 / FFMA2 retire two lanes per issue slot (tools/epi_probe.cu: 2.06 cycles per evaluation
+// for the whole FADD.SAT + FADD2/2 + FFMA2/2 sequence against 3.17 with scalar FADD / FFMA).
 __device__ __forceinline__ unsigned long long tc_pack2(float lo, float hi) {
   unsigned long long d;
   asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
@@ -289,7 +325,7 @@ __device__ __forceinline__ void tc_accumulate32(const uint32_t (&r)[32], float C
     S2[(i >> 1) & 1] = tc_fma2(U, U, S2[(i >> 1) & 1]);
   }
 }
-// ragged segment: only the first len columns are points of the cloud
+// ragged run: only the first len columns are points of the cloud
 __device__ __forceinline__ void tc_accumulate32_masked(const uint32_t (&r)[32], float C, unsigned long long (&S1)[2],
                                                        unsigned long long (&S2)[2], int len) {
 #pragma unroll
@@ -305,24 +341,17 @@ __device__ __forceinline__ void tc_accumulate32_masked(const uint32_t (&r)[32], 
     S2[(i >> 1) & 1] = tc_fma2(U, U, S2[(i >> 1) & 1]);
   }
 }
-__device__ __forceinline__ void tc_ld_wait2(uint32_t (&a)[32], uint32_t (&b)[32]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" : TC_RW32(a), TC_RW32(b)::"memory");
-}
 
-// 16 epilogue warps = 4 groups x 4 TMEM lane quadrants. Group g owns accumulator buffer g (128 columns) and
-// tile g (128 points) of every chunk: its four warps each drain 32 hypotheses (lanes) x 128 points. The MMA
-// thread refills buffer g as soon as group g has loaded it, i.e. a whole epilogue pass ahead of its next use,
-// so the MMA / commit / wake-up latency never sits on the critical path. DBG adds the accumulator dump and the
-// timing experiments (variant bits: 1 = no accumulation, 2 = one MMA per tile, 4 = no TMEM loads).
-constexpr int TC_EPI_WARPS = 16, TC_EPI_THREADS = 32 * TC_EPI_WARPS;
-constexpr int TC_MMA_WARPS = TC_TILES;  // one MMA issuing warp per accumulator buffer, one per SM sub-partition
-constexpr int TC_THREADS = TC_EPI_THREADS + 32 * TC_MMA_WARPS;
+// Epilogue warp w: TMEM lane quadrant q = w & 3 (hypotheses 32 q .. 32 q + 31 of the block), column run j = w >> 2
+// (columns 64 j .. 64 j + 63 of each accumulator, i.e. the points 256 b + 64 j .. + 63 of the chunk in phase b).
+// DBG adds the accumulator dump, phase timers and the timing experiments (variant bits: 1 = no accumulation,
+// 2 = one MMA per tile, 4 = no TMEM loads).
 template <bool DBG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict__ recs, int H, const float4* __restrict__ image,
+plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict__ recs, int H, const uint4* __restrict__ image,
                 int n_hb /*hypothesis blocks*/, int n_chunks, int n_items, float thr_up, const PlaneTcParams* __restrict__ Pp,
                 int* __restrict__ counts, unsigned long long* __restrict__ stats /*nullable: [0] segments, [1] re-evaluated*/,
-                float* __restrict__ dbg /*DBG: s~ of hypothesis block 0 x tiles 0,1 of item 0 (128 x 256)*/, int variant /*DBG*/) {
+                float* __restrict__ dbg /*DBG: s~ of hypothesis block 0 x points 0..255 of item 0 (128 x 256)*/, int variant /*DBG*/) {
   extern __shared__ __align__(128) unsigned char smem[];
   const PlaneTcParams P = *Pp;
   if (!P.use) return;  // plane_score_kernel (launched right after) does the work
@@ -330,17 +359,16 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t s_base = smem_u32(smem);
   const uint32_t bar0 = s_base + TC_OFF_BAR;
-  // barriers: [0..3] a_full, [4..7] a_empty, [8..11] tmem_full, [12..15] tmem_empty, [16] b_full
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + TC_OFF_BAR + 24 * 8);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + TC_OFF_BAR + 16 * 8);
   float4* s_raw = reinterpret_cast<float4*>(smem + TC_OFF_RAW);
   int* s_cnt = reinterpret_cast<int*>(smem + TC_OFF_CNT);
 
   if (threadIdx.x == 0) {
-    static_assert(TC_ASTAGES == 4 && TC_TILES == 4, "barrier numbering");
-    for (int i = 0; i < TC_ASTAGES; ++i) { mbar_init(BAR(i), 1); mbar_init(BAR(4 + i), TC_MMA_WARPS); }
-    for (int i = 0; i < TC_TILES; ++i) { mbar_init(BAR(8 + i), 1); mbar_init(BAR(12 + i), 4); }
-    mbar_init(BAR(16), TC_EPI_THREADS);
+    static_assert(TC_ASTAGES == 4 && TC_PHASES == 2, "barrier numbering");
+    for (int i = 0; i < TC_ASTAGES; ++i) { mbar_init(BAR(TC_BAR_AFULL + i), 1); mbar_init(BAR(TC_BAR_AEMPTY + i), TC_MMA_WARPS); }
+    for (int i = 0; i < TC_PHASES; ++i) { mbar_init(BAR(TC_BAR_FULL + i), 1); mbar_init(BAR(TC_BAR_EMPTY + i), TC_EPI_WARPS); }
+    mbar_init(BAR(TC_BAR_B), TC_EPI_THREADS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_EPI_WARPS) {
@@ -354,87 +382,84 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
   const uint32_t tmem = *s_tmem;
 
   if (warp >= TC_EPI_WARPS) {
-    // ===================== MMA issuers: warp w feeds accumulator buffer w (tile w of every chunk); warp 0 also
-    // streams the hypothesis block images global -> shared (bulk async copy), TC_ASTAGES - 1 blocks ahead.
+    // ===================== MMA issuers: warp t feeds accumulator t (phase t of every chunk); warp 0 also streams
+    // the hypothesis block images global -> shared (bulk async copy), TC_ASTAGES - 1 blocks ahead.
     // The whole warp runs the loop so that every operand stays warp-uniform; one elected lane issues.
-    {
-      const int t = warp - TC_EPI_WARPS;
-      uint32_t ac = 0, cc = 0;
-      long long tw = 0, tm = 0, tcm = 0, ta = 0, tb = 0;  // DBG: cycles in empty-wait, MMA issue, commit, A wait, B wait
-      // producer cursor: block sequence number, item and hypothesis block of the next image to request
-      uint32_t pa = 0;
-      int p_item = blockIdx.x, p_hb = (p_item < n_items) ? (p_item / n_chunks) * TC_SB : 0;
-      auto produce_until = [&](uint32_t limit) {
-        while (pa < limit && p_item < n_items) {
-          const uint32_t st = pa % TC_ASTAGES, ph = (pa / TC_ASTAGES) & 1u;
-          mbar_wait(BAR(4 + st), ph ^ 1u);  // every MMA that read the previous block of this stage has completed
-          if (elect_one()) {
-            mbar_expect_tx(BAR(st), TC_A_BLOCK_BYTES);
-            const float4* src = image + (size_t)p_hb * (TC_A_BLOCK_BYTES / 16);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(s_base + TC_OFF_A + st * TC_A_BLOCK_BYTES), "l"(src), "r"(TC_A_BLOCK_BYTES), "r"(BAR(st))
-                         : "memory");
-          }
-          __syncwarp();
-          ++pa;
-          const int p_sb = p_item / n_chunks;
-          if (++p_hb >= min(n_hb, (p_sb + 1) * TC_SB)) {
-            p_item += gridDim.x;
-            p_hb = (p_item < n_items) ? (p_item / n_chunks) * TC_SB : 0;
-          }
+    const int t = warp - TC_EPI_WARPS;
+    uint32_t ac = 0, cc = 0;
+    long long tw = 0, tm = 0, tcm = 0, ta = 0, tb = 0;  // DBG: cycles in empty-wait, MMA issue, commit, A wait, B wait
+    // producer cursor: block sequence number, item and hypothesis block of the next image to request
+    uint32_t pa = 0;
+    int p_item = blockIdx.x, p_hb = (p_item < n_items) ? (p_item / n_chunks) * TC_SB : 0;
+    auto produce_until = [&](uint32_t limit) {
+      while (pa < limit && p_item < n_items) {
+        const uint32_t st = pa % TC_ASTAGES, ph = (pa / TC_ASTAGES) & 1u;
+        mbar_wait(BAR(TC_BAR_AEMPTY + st), ph ^ 1u);  // every MMA that read the previous block of this stage has completed
+        if (elect_one()) {
+          mbar_expect_tx(BAR(TC_BAR_AFULL + st), TC_A_BLOCK_BYTES);
+          const uint4* src = image + (size_t)p_hb * (TC_A_BLOCK_BYTES / 16);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(s_base + TC_OFF_A + st * TC_A_BLOCK_BYTES), "l"(src), "r"(TC_A_BLOCK_BYTES), "r"(BAR(TC_BAR_AFULL + st))
+                       : "memory");
         }
-      };
-      if (t == 0) produce_until(TC_ASTAGES - 1);
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++cc) {
-        const int sb = item / n_chunks;
-        const int hb0 = sb * TC_SB, hb1 = min(n_hb, hb0 + TC_SB);
-        long long c0 = DBG ? clock64() : 0;
-        mbar_wait(BAR(16), cc & 1u);  // the chunk's B image is in shared memory
+        __syncwarp();
+        ++pa;
+        const int p_sb = p_item / n_chunks;
+        if (++p_hb >= min(n_hb, (p_sb + 1) * TC_SB)) {
+          p_item += gridDim.x;
+          p_hb = (p_item < n_items) ? (p_item / n_chunks) * TC_SB : 0;
+        }
+      }
+    };
+    if (t == 0) produce_until(TC_ASTAGES - 1);
+    const uint32_t b_addr = s_base + TC_OFF_B + t * TC_B_TILE_BYTES;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++cc) {
+      const int sb = item / n_chunks;
+      const int hb0 = sb * TC_SB, hb1 = min(n_hb, hb0 + TC_SB);
+      long long c0 = DBG ? clock64() : 0;
+      mbar_wait(BAR(TC_BAR_B), cc & 1u);  // the chunk's B image is in shared memory
+      tc_fence_after();
+      if (DBG) tb += clock64() - c0;
+      for (int hb = hb0; hb < hb1; ++hb, ++ac) {
+        const uint32_t st = ac % TC_ASTAGES, ph = (ac / TC_ASTAGES) & 1u;
+        if (DBG) c0 = clock64();
+        mbar_wait(BAR(TC_BAR_AFULL + st), ph);
         tc_fence_after();
-        if (DBG) tb += clock64() - c0;
-        const uint32_t b_addr = s_base + TC_OFF_B + t * TC_B_TILE_BYTES;
-        for (int hb = hb0; hb < hb1; ++hb, ++ac) {
-          const uint32_t st = ac % TC_ASTAGES, ph = (ac / TC_ASTAGES) & 1u;
-          if (DBG) c0 = clock64();
-          mbar_wait(BAR(st), ph);
-          tc_fence_after();
-          if (DBG) ta += clock64() - c0;
-          const uint32_t a_addr = s_base + TC_OFF_A + st * TC_A_BLOCK_BYTES;
-          if (DBG) c0 = clock64();
-          mbar_wait(BAR(12 + t), (ac & 1u) ^ 1u);  // group t has loaded the previous contents of buffer t
-          tc_fence_after();
-          long long c1 = DBG ? clock64() : 0;
-          long long c2 = 0;
-          if (elect_one()) {
+        if (DBG) ta += clock64() - c0;
+        const uint32_t a_addr = s_base + TC_OFF_A + st * TC_A_BLOCK_BYTES;
+        if (DBG) c0 = clock64();
+        mbar_wait(BAR(TC_BAR_EMPTY + t), (ac & 1u) ^ 1u);  // every epilogue warp has the previous contents in registers
+        tc_fence_after();
+        long long c1 = DBG ? clock64() : 0;
+        long long c2 = 0;
+        if (elect_one()) {
 #pragma unroll
-            for (int j = 0; j < TC_MMAS; ++j)
-              if (!DBG || j == 0 || !(variant & 2))
-                tc_mma_tf32(tmem + t * TC_N, tc_smem_desc(a_addr + j * TC_A_MMA_BYTES), tc_smem_desc(b_addr + j * TC_B_MMA_BYTES),
-                            TC_IDESC, j > 0 ? 1u : 0u);
-            if (DBG) c2 = clock64();
-            tc_commit(BAR(8 + t));
-            tc_commit(BAR(4 + st));  // the hypothesis stage is free once the MMAs of all four warps have read it
-          }
-          __syncwarp();
-          if (DBG) { tw += c1 - c0; tm += c2 - c1; tcm += clock64() - c2; }
-          if (t == 0) produce_until(ac + TC_ASTAGES);  // keep TC_ASTAGES - 1 blocks beyond the one just issued in flight
+          for (int j = 0; j < TC_MMAS; ++j)
+            if (!DBG || j == 0 || !(variant & 2))
+              tc_mma_bf16(tmem + t * TC_N, tc_smem_desc(a_addr + j * TC_A_MMA_BYTES), tc_smem_desc(b_addr + j * TC_B_MMA_BYTES),
+                          TC_IDESC, j > 0 ? 1u : 0u);
+          if (DBG) c2 = clock64();
+          tc_commit(BAR(TC_BAR_FULL + t));
+          tc_commit(BAR(TC_BAR_AEMPTY + st));  // the hypothesis stage is free once the MMAs of both warps have read it
         }
+        __syncwarp();
+        if (DBG) { tw += c1 - c0; tm += c2 - c1; tcm += clock64() - c2; }
+        if (t == 0) produce_until(ac + TC_ASTAGES);  // keep TC_ASTAGES - 1 blocks beyond the one just issued in flight
       }
-      if (DBG && stats && blockIdx.x == 0 && lane == 0 && t == 0) {
-        stats[162] = tw; stats[163] = tm; stats[164] = tcm; stats[165] = ta; stats[166] = tb; stats[167] = ac;
-      }
+    }
+    if (DBG && stats && blockIdx.x == 0 && lane == 0 && t == 0) {
+      stats[162] = tw; stats[163] = tm; stats[164] = tcm; stats[165] = ta; stats[166] = tb; stats[167] = ac;
     }
     __syncwarp();
   } else {
     // ===================== epilogue warps: split the point chunk, drain TMEM, count
-    const int q = warp & 3, g = warp >> 2;  // lane quadrant, group = tile = accumulator buffer
+    const int q = warp & 3, j = warp >> 2;  // lane quadrant, column run
     const int row = q * 32 + lane;
-    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + g * TC_N;
-    const int seg0 = g * TC_N;  // first point of this group's tile inside the chunk
-    uint32_t uc = 0;            // uses of buffer g so far
+    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + j * TC_RUN;
+    uint32_t uc = 0;  // uses of each accumulator so far
     int cur_sb = -1;
     unsigned n_seg = 0, n_redo = 0;
-    long long e_wait = 0, e_rt = 0, e_hold = 0, e_arr = 0, e_ld = 0, e_math = 0, e_tail = 0;  // DBG: cycles waiting for full, arrive -> next full seen, full seen -> arrive
+    long long e_wait = 0, e_ld = 0, e_math = 0, e_tail = 0;  // DBG: cycles per phase
     auto epi_sync = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(TC_EPI_THREADS) : "memory"); };
     auto flush = [&]() {
       if (cur_sb < 0) return;
@@ -452,7 +477,10 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
       if (sb != cur_sb) { flush(); cur_sb = sb; }
       const int hb0 = sb * TC_SB, hb1 = min(n_hb, hb0 + TC_SB);
       const int base = chunk * TC_CHUNK;
-      const int len = min(TC_N, n - (base + seg0));
+      // this warp's two runs of the chunk (phase 0 and 1) and how many of their points exist
+      const int run0 = j * TC_RUN, run1 = TC_N + j * TC_RUN;
+      const int len0 = max(0, min(TC_RUN, n - (base + run0))), len1 = max(0, min(TC_RUN, n - (base + run1)));
+      const bool full_runs = (len0 == TC_RUN) && (len1 == TC_RUN);
       // every MMA that read the previous B image has completed (its accumulators were consumed);
       // nobody may still be re-counting from s_raw
       epi_sync();
@@ -462,23 +490,10 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
         if (gi < n) p = __ldg(xyz + gi);
         s_raw[pi] = p;
-        float x1, x2, x3, y1, y2, y3, z1, z2, z3;
-        tc_split3(p.x, x1, x2, x3);
-        tc_split3(p.y, y1, y2, y3);
-        tc_split3(p.z, z1, z2, z3);
-        const int t = pi / TC_N, pr = pi % TC_N;
-        float4* tb = reinterpret_cast<float4*>(smem + TC_OFF_B + t * TC_B_TILE_BYTES);
-        const int o = (pr >> 3) * 16 + (pr & 7);
-        constexpr int MF4 = TC_B_MMA_BYTES / 16;  // float4 per MMA image
-        tb[0 * MF4 + o] = make_float4(x3, x2, x1, y3);
-        tb[0 * MF4 + o + 8] = make_float4(y2, y1, z3, z2);
-        tb[1 * MF4 + o] = make_float4(z1, 1.f, x2, x1);
-        tb[1 * MF4 + o + 8] = make_float4(y2, y1, z2, z1);
-        tb[2 * MF4 + o] = make_float4(x1, y1, z1, 1.f);
-        tb[2 * MF4 + o + 8] = make_float4(1.f, 0.f, 0.f, 0.f);
+        tc_point_image(reinterpret_cast<uint4*>(smem + TC_OFF_B + (pi / TC_N) * TC_B_TILE_BYTES), pi % TC_N, p);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_arrive(BAR(16));
+      mbar_arrive(BAR(TC_BAR_B));
       epi_sync();  // s_raw visible to every epilogue warp
 
 #pragma unroll 1
@@ -487,59 +502,58 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
         // this lane's hypothesis in the exact form, for re-evaluations (broadcast by shuffle, no memory latency there)
         float4 myrec = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
         if (h < H) myrec = __ldg(reinterpret_cast<const float4*>(recs[h].v));
-        long long e0 = DBG ? clock64() : 0;
-        mbar_wait(BAR(8 + g), uc & 1u);
-        tc_fence_after();
-        if (DBG) { e_wait += clock64() - e0; if (e_arr) e_rt += clock64() - e_arr; e0 = clock64(); }
         unsigned long long S1[2] = {0ull, 0ull}, S2[2] = {0ull, 0ull};
         uint32_t ra[32], rb[32];
-        if (DBG && (variant & 5)) {
-          if (!(variant & 4)) {
-            unsigned x = 0;
-            for (int k4 = 0; k4 < TC_N / 32; ++k4) {
-              tc_ld32(ra, taddr + 32 * k4);
-              tc_ld_wait(ra);
+        // An accumulator is handed back to its MMA warp as soon as this warp's 64 columns are in registers: the
+        // tensor pipe refills it (next hypothesis block) while the FMA pipe works through the other accumulator.
 #pragma unroll
-              for (int i = 0; i < 32; ++i) x ^= ra[i];
+        for (int b = 0; b < TC_PHASES; ++b) {
+          long long e0 = DBG ? clock64() : 0;
+          mbar_wait(BAR(TC_BAR_FULL + b), uc & 1u);
+          tc_fence_after();
+          if (DBG) { e_wait += clock64() - e0; e0 = clock64(); }
+          if (DBG && (variant & 5)) {
+            if (!(variant & 4)) {
+              unsigned x = 0;
+              for (int k4 = 0; k4 < TC_RUN / 32; ++k4) {
+                tc_ld32(ra, taddr + b * TC_N + 32 * k4);
+                tc_ld_wait(ra);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) x ^= ra[i];
+              }
+              if (x == 0x12345u) n_seg++;
             }
-            if (x == 0x12345u) n_seg++;
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(12 + g));
-          continue;
-        }
-#pragma unroll
-        for (int b = 0; b < TC_N / 64; ++b) {
-          long long p0 = DBG ? clock64() : 0;
-          tc_ld32(ra, taddr + 64 * b);
-          tc_ld32(rb, taddr + 64 * b + 32);
-          tc_ld_wait2(ra, rb);
-          if (DBG) e_ld += clock64() - p0;
-          if (b == TC_N / 64 - 1) {
-            // this warp has read its part of the accumulator: hand the buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(12 + g));
-            if (DBG) { e_arr = clock64(); e_hold += e_arr - e0; }
+            if (lane == 0) mbar_arrive(BAR(TC_BAR_EMPTY + b));
+            continue;
           }
-          if (DBG && dbg && item == 0 && hb == 0 && g < 2) {
+          tc_ld32(ra, taddr + b * TC_N);
+          tc_ld32(rb, taddr + b * TC_N + 32);
+          tc_ld_wait2(ra, rb);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(TC_BAR_EMPTY + b));
+          if (DBG) e_ld += clock64() - e0;
+          if (DBG && dbg && item == 0 && hb == 0 && b == 0) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              dbg[row * 256 + g * TC_N + 64 * b + i] = __uint_as_float(ra[i]);
-              dbg[row * 256 + g * TC_N + 64 * b + 32 + i] = __uint_as_float(rb[i]);
+              dbg[row * 256 + j * TC_RUN + i] = __uint_as_float(ra[i]);
+              dbg[row * 256 + j * TC_RUN + 32 + i] = __uint_as_float(rb[i]);
             }
           }
-          if (DBG) p0 = clock64();
-          if (len == TC_N) {
+          if (DBG) e0 = clock64();
+          if (full_runs) {
             tc_accumulate32(ra, P.C, S1, S2);
             tc_accumulate32(rb, P.C, S1, S2);
-          } else {  // ragged last tile of the cloud (warp-uniform, once per hypothesis block)
-            tc_accumulate32_masked(ra, P.C, S1, S2, len - 64 * b);
-            tc_accumulate32_masked(rb, P.C, S1, S2, len - 64 * b - 32);
+          } else {  // ragged last chunk of the cloud (warp-uniform)
+            const int len = b ? len1 : len0;
+            tc_accumulate32_masked(ra, P.C, S1, S2, len);
+            tc_accumulate32_masked(rb, P.C, S1, S2, len - 32);
           }
-          if (DBG) { asm volatile("" : "+l"(S1[0]), "+l"(S1[1]), "+l"(S2[0]), "+l"(S2[1])); e_math += clock64() - p0; }
+          if (DBG) { asm volatile("" : "+l"(S1[0]), "+l"(S1[1]), "+l"(S2[0]), "+l"(S2[1])); e_math += clock64() - e0; }
         }
+        if (DBG && (variant & 5)) continue;
         long long p1 = DBG ? clock64() : 0;
         const float s1 = tc_sum2(tc_add2(S1[0], S1[1]));
         const float s2 = tc_sum2(tc_add2(S2[0], S2[1]));
@@ -555,7 +569,7 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
           r.y = __shfl_sync(0xffffffffu, myrec.y, L);
           r.z = __shfl_sync(0xffffffffu, myrec.z, L);
           r.w = __shfl_sync(0xffffffffu, myrec.w, L);
-          const int e = tc_recount(s_raw + seg0, max(len, 0), r, thr_up, lane);
+          const int e = tc_recount(s_raw + run0, len0, r, thr_up, lane) + tc_recount(s_raw + run1, len1, r, thr_up, lane);
           if (lane == L) c = e;
         }
         if (c) atomicAdd(&s_cnt[(hb - hb0) * TC_M + row], c);
@@ -563,7 +577,9 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
       }
     }
     flush();
-    if (DBG && stats && blockIdx.x == 0 && threadIdx.x == 0) { stats[168] = e_wait; stats[169] = e_rt; stats[170] = e_hold; stats[171] = uc; stats[172] = e_ld; stats[173] = e_math; stats[174] = e_tail; }
+    if (DBG && stats && blockIdx.x == 0 && threadIdx.x == 0) {
+      stats[168] = e_wait; stats[169] = 0; stats[170] = 0; stats[171] = uc; stats[172] = e_ld; stats[173] = e_math; stats[174] = e_tail;
+    }
     if (stats && lane == 0) {
       atomicAdd(stats + 0, (unsigned long long)n_seg);
       if (n_redo) atomicAdd(stats + 1, (unsigned long long)n_redo);
@@ -591,9 +607,6 @@ int g_plane_tc_variant = 0;
 int g_plane_tc_nwq = 4;
 float g_plane_tc_acc_ulps = TC_ACC_ULPS;
 std::vector<float> g_plane_tc_dump_host;  // 128 x 256 accumulators + sigma, C
-}  // namespace pitt
-
-namespace pitt {
 
 #define TC_LAUNCH_CHECK(ctx, what)                                        \
   do {                                                                    \
@@ -616,7 +629,7 @@ int launch_score_plane_tc(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_re
   unsigned* d_scr = nullptr;
   PlaneTcParams* d_P = nullptr;
   unsigned long long* d_stats = nullptr;
-  float4* d_image = nullptr;
+  uint4* d_image = nullptr;
   float* d_dbg = nullptr;
   PITT_TRY(arena_alloc(ctx, 4, &d_scr));
   PITT_TRY(arena_alloc(ctx, 1, &d_P));

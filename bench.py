@@ -339,24 +339,31 @@ def main():
         except Exception:
             traffic = None
     # The dominant kernel is plane_tc_kernel (csrc/plane_tc.cu): the dot products run on the tensor cores (tcgen05.mma
-    # kind::tf32 on exact 3-piece splits, 24 TF32 MACs per evaluation), the CUDA cores execute 3 FMA-pipe operations per
-    # evaluation (saturating subtract, sum u, sum u^2) and that pipe is what bounds the kernel. The
-    # schema's roofline is therefore quoted against the FP32 FFMA peak measured live (MEASURED_PEAKS.json has no CUDA-core
-    # figure): `achieved` counts the ALGORITHMIC 6 flop per evaluation of SURVEY 8d; the executed-operation fraction of the
-    # FMA pipe and the tensor-pipe fraction are reported beside it.
+    # kind::f16 on exact 3-piece BF16 splits, two chained 128x256x16 MMAs = 32 BF16 MAC slots per evaluation), the CUDA
+    # cores execute 3 FMA-pipe operations per evaluation (saturating subtract, sum u, sum u^2; 2 issue slots because the two
+    # sums are packed FADD2 / FFMA2) and that pipe is what bounds the kernel. The schema's roofline is
+    # therefore quoted against the FP32 FFMA peak measured live (MEASURED_PEAKS.json has no CUDA-core figure): `achieved`
+    # counts the ALGORITHMIC 6 flop per evaluation of SURVEY 8d; the fraction of the kernel's own instruction-mix floor
+    # (tools/ldtm_probe.cu: 3.125 cycles per evaluation per sub-partition once the TMEM loads are included) and the
+    # tensor-pipe fraction are reported beside it.
     evals_s = float(n) * N_HYP / (k_ms * 1e-3)
     fma_ops_peak = peak_ffma * 1e12 / 2.0           # FMA-pipe operations per second (one FFMA = 2 flop)
-    tf32_peak = MEASURED.get("bf16_tflops", 1659.2) / 2.0  # TF32 dense = half the measured bf16 rate
+    bf16_peak = MEASURED.get("bf16_tflops", 1659.2)
+    sm_clock_hz = 1.965e9
+    floor_evals_s = 148 * 4 * 32 / 3.125 * sm_clock_hz  # measured floor of FADD.SAT + FADD2/2 + FFMA2/2 + tcgen05.ld per evaluation
     roofline = {
         "bound": "fp32", "kernel": "plane_tc_kernel", "achieved": achieved, "peak": peak_ffma,
         "unit": "TFLOP/s", "frac": achieved / peak_ffma, "traffic": traffic,
         "peak_source": "measured live: pitt_fp32_peak(kind=0) = FFMA issue rate with immediate operands",
         "frac_of_unfused_peak": achieved / peak_unfused, "peak_unfused_tflops": peak_unfused,
         "fma_pipe_ops_per_eval": 3, "frac_fma_pipe_ops": evals_s * 3.0 / fma_ops_peak,
-        "tensor_tf32_macs_per_eval": 24, "tensor_tflops": evals_s * 48.0 / 1e12,
-        "frac_tensor_of_half_measured_bf16": evals_s * 48.0 / 1e12 / tf32_peak,
-        "note": "dot products on tcgen05 (3 chained 128x128x8 TF32 MMAs per tile on exact splits), CUDA cores run the "
-                "3-operation saturating-count epilogue; kernel_ms brackets estimate + set-up + plane_tc_kernel "
+        "issue_slots_per_eval": 2, "frac_of_epilogue_floor": evals_s / floor_evals_s,
+        "epilogue_floor_note": "tools/ldtm_probe.cu on B200: 2.0 cycles/eval/sub-partition for the arithmetic alone, 3.125 with "
+                               "the TMEM->register loads (they do not overlap with arithmetic on the same sub-partition)",
+        "tensor_bf16_mac_slots_per_eval": 32, "tensor_tflops": evals_s * 64.0 / 1e12,
+        "frac_tensor_of_measured_bf16": evals_s * 64.0 / 1e12 / bf16_peak,
+        "note": "dot products on tcgen05 (2 chained 128x256x16 BF16 MMAs per tile on exact 3-piece splits, FP32 accumulators "
+                "in TMEM), CUDA cores run the saturating-count epilogue; kernel_ms brackets estimate + set-up + plane_tc_kernel "
                 "(pitt_sac_score_device); FFMA filter kernel (previous dominant kernel) = 1.09 ms on the same job",
         "kernel_ms": k_ms, "algorithmic_flop_per_launch": float(n) * N_HYP * 6,
         "algorithmic_bytes_per_launch": n * 16 + N_HYP * (64 + 4),

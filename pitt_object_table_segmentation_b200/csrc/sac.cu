@@ -117,6 +117,96 @@ score_kernel(const float4* __restrict__ xyz, const float4* __restrict__ nrm, int
 }
 
 // =====================================================================================
+// K3 (cylinder, cone): two tiers. Tier 1 classifies every evaluation from the axis distance alone
+// (Tier1<MODEL>::classify: certain outlier / certain inlier / undecided, ~20-60 instructions, no
+// sqrt/acos/division for the cylinder); the undecided ones (thin shells around the model surface, a
+// few per cent) are pushed as (hypothesis, point) pairs on a per-warp queue in shared memory and
+// evaluated 32 at a time, one pair per lane, with the full predicate RecRegs<MODEL>::inlier
+// (FP32 score, exact double sequence inside the band). Without the queue one undecided lane makes
+// the whole warp walk the ~200-instruction path: at 2 % undecided that is every second warp.
+// Counts are identical to score_kernel (test_two_tier_scoring_equals_generic).
+// =====================================================================================
+template <int MODEL, int P, int TPB>
+__global__ void __launch_bounds__(TPB)
+score2_kernel(const float4* __restrict__ xyz, const float4* __restrict__ nrm, int n, const HypRec* __restrict__ recs,
+              int H, int hyp_chunk, int pts_per_cta, ScoreParams sp, int* __restrict__ counts) {
+  constexpr int QCAP = 32 * P + 32;  // at most 31 left over + 32 * P pushed per hypothesis
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  HypRec* s_rec = reinterpret_cast<HypRec*>(smem_raw);
+  int* s_cnt = reinterpret_cast<int*>(smem_raw + (size_t)hyp_chunk * sizeof(HypRec));
+  int2* s_q = reinterpret_cast<int2*>(smem_raw + (size_t)hyp_chunk * (sizeof(HypRec) + sizeof(int)) + 8 - ((size_t)hyp_chunk * 4) % 8);
+  const int h0 = blockIdx.y * hyp_chunk;
+  const int hc = min(hyp_chunk, H - h0);
+  {
+    const float4* src = reinterpret_cast<const float4*>(recs + h0);
+    float4* dst = reinterpret_cast<float4*>(s_rec);
+    for (int i = threadIdx.x; i < hc * 4; i += TPB) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < hc; i += TPB) s_cnt[i] = 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  int2* q = s_q + (threadIdx.x >> 5) * QCAP;
+  const unsigned lt = (1u << lane) - 1u;
+  auto full_eval = [&](int2 e) {
+    RecRegs<MODEL> rr;
+    rr.load(s_rec + e.x);
+    const f3 pt = ld3(xyz, e.y), nv = ld3(nrm, e.y);
+    if (rr.inlier(pt, nv, sp)) atomicAdd(&s_cnt[e.x], 1);
+  };
+  const int p_begin = blockIdx.x * pts_per_cta;
+  const int p_end = min(n, p_begin + pts_per_cta);
+  for (int base = p_begin; base < p_end; base += TPB * P) {
+    f3 pt[P];
+    unsigned valid = 0, nice = 0;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const int i = base + p * TPB + threadIdx.x;
+      pt[p] = mk3(0.f, 0.f, 0.f);
+      if (i < p_end) {
+        pt[p] = ld3(xyz, i);
+        valid |= 1u << p;
+        if (nice_point(pt[p], ld3(nrm, i))) nice |= 1u << p;
+      }
+    }
+    int qn = 0;  // warp-uniform
+    for (int h = 0; h < hc; ++h) {
+      if (s_rec[h].v[0] != s_rec[h].v[0]) continue;  // invalid hypothesis (uniform branch)
+      Tier1<MODEL> r;
+      r.load(s_rec + h);
+      int c = 0;
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        const int cls = ((valid >> p) & 1u) ? r.classify(pt[p], (nice >> p) & 1u) : 0;
+        c += (cls == 1) ? 1 : 0;
+        const unsigned m = __ballot_sync(0xffffffffu, cls == 2);
+        if (m) {
+          if (cls == 2) q[qn + __popc(m & lt)] = make_int2(h, base + p * TPB + (int)threadIdx.x);
+          qn += __popc(m);
+        }
+      }
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (lane == 0 && c) atomicAdd(&s_cnt[h], c);
+      if (qn >= 32) {
+        __syncwarp();
+        do {
+          qn -= 32;
+          full_eval(q[qn + lane]);
+        } while (qn >= 32);
+        __syncwarp();
+      }
+    }
+    __syncwarp();
+    if (lane < qn) full_eval(q[lane]);
+    __syncwarp();
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < hc; i += TPB) {
+    int c = s_cnt[i];
+    if (c) atomicAdd(&counts[h0 + i], c);
+  }
+}
+
+// =====================================================================================
 // K3p: plane scoring, lanes = hypotheses, points broadcast from shared memory, packed f32x2
 // arithmetic (FMUL2/FADD2 are IEEE round-to-nearest per element => same bits as scalar).
 // Each thread owns KH hypotheses (KH/2 register pairs) and its own counters: no reduction at all
@@ -815,7 +905,7 @@ int sac_estimate(pitt_ctx* ctx, const pitt_cloud* c, int model, const int* d_sam
   }
 }
 
-template <int MODEL, int P>
+template <int MODEL, int P, bool TWO_TIER>
 static int launch_score_generic(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_recs, int H, const ScoreParams& sp,
                                 int* d_counts) {
   constexpr int TPB = 256;
@@ -841,11 +931,18 @@ static int launch_score_generic(pitt_ctx* ctx, const pitt_cloud* c, const HypRec
   pblocks = cdiv(n, pts_per_cta);
   size_t smem = (size_t)hyp_chunk * (sizeof(HypRec) + sizeof(int));
   dim3 grid(pblocks, n_chunks);
-  score_kernel<MODEL, P, TPB><<<grid, TPB, smem, ctx->stream>>>(c->d_xyz, c->d_nrm, n, d_recs, H, hyp_chunk, pts_per_cta, sp, d_counts);
-  PITT_LAUNCH_CHECK(ctx, "score_kernel");
+  if constexpr (TWO_TIER) {
+    smem += 8 + (size_t)(TPB / 32) * (32 * P + 32) * sizeof(int2);  // per-warp queues of undecided evaluations
+    score2_kernel<MODEL, P, TPB><<<grid, TPB, smem, ctx->stream>>>(c->d_xyz, c->d_nrm, n, d_recs, H, hyp_chunk, pts_per_cta, sp, d_counts);
+    PITT_LAUNCH_CHECK(ctx, "score2_kernel");
+  } else {
+    score_kernel<MODEL, P, TPB><<<grid, TPB, smem, ctx->stream>>>(c->d_xyz, c->d_nrm, n, d_recs, H, hyp_chunk, pts_per_cta, sp, d_counts);
+    PITT_LAUNCH_CHECK(ctx, "score_kernel");
+  }
   return PITT_OK;
 }
 
+int g_score_mode = 0;  // test hook: 0 two-tier kernel for cylinder/cone, 1 generic score_kernel for every model
 int g_plane_mode = 0;  // test hook: 0 automatic (tensor path on large jobs), 1 exact packed kernel only,
                        // 2 FFMA filter + exact re-evaluation always, 3 tensor-core path (plane_tc.cu) always
 int launch_score_plane_tc(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_recs, int H, const ScoreParams& sp, int* d_counts,
@@ -925,10 +1022,16 @@ int sac_score(pitt_ctx* ctx, const pitt_cloud* c, int model, const HypRec* d_rec
   switch (model) {
     case PITT_MODEL_PLANE:
       if (H >= 256 && !g_force_generic_plane) return launch_score_plane_packed(ctx, c, d_recs, H, sp, d_counts);
-      return launch_score_generic<PITT_MODEL_PLANE, 8>(ctx, c, d_recs, H, sp, d_counts);
-    case PITT_MODEL_SPHERE: return launch_score_generic<PITT_MODEL_SPHERE, 8>(ctx, c, d_recs, H, sp, d_counts);
-    case PITT_MODEL_CYLINDER: return launch_score_generic<PITT_MODEL_CYLINDER, 2>(ctx, c, d_recs, H, sp, d_counts);
-    default: return launch_score_generic<PITT_MODEL_CONE, 2>(ctx, c, d_recs, H, sp, d_counts);
+      return launch_score_generic<PITT_MODEL_PLANE, 8, false>(ctx, c, d_recs, H, sp, d_counts);
+    case PITT_MODEL_SPHERE: return launch_score_generic<PITT_MODEL_SPHERE, 8, false>(ctx, c, d_recs, H, sp, d_counts);
+    case PITT_MODEL_CYLINDER:
+      if (g_score_mode == 1) return launch_score_generic<PITT_MODEL_CYLINDER, 2, false>(ctx, c, d_recs, H, sp, d_counts);
+      if (c->n < 4096) return launch_score_generic<PITT_MODEL_CYLINDER, 1, true>(ctx, c, d_recs, H, sp, d_counts);
+      return launch_score_generic<PITT_MODEL_CYLINDER, 4, true>(ctx, c, d_recs, H, sp, d_counts);
+    default:
+      if (g_score_mode == 1) return launch_score_generic<PITT_MODEL_CONE, 2, false>(ctx, c, d_recs, H, sp, d_counts);
+      if (c->n < 4096) return launch_score_generic<PITT_MODEL_CONE, 1, true>(ctx, c, d_recs, H, sp, d_counts);
+      return launch_score_generic<PITT_MODEL_CONE, 4, true>(ctx, c, d_recs, H, sp, d_counts);
   }
 }
 

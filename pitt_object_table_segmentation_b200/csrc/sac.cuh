@@ -51,6 +51,7 @@ int fp32_peak(pitt_ctx* ctx, int kind, double* tflops);
 
 extern int g_force_generic_plane;
 extern int g_plane_mode;
+extern int g_score_mode;
 extern unsigned long long g_plane_filter_stats[2];
 extern int g_plane_filter_collect_stats;
 extern unsigned long long g_plane_tc_stats[2 + 160 + 16];

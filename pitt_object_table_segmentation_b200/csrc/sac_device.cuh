@@ -16,10 +16,13 @@ namespace pitt {
 //  plane    v[0..3]  = a,b,c,d
 //  sphere   v[0..3]  = cx,cy,cz,r, v[4..5] = [D_lo, D_hi]: the squared distances that are inliers (exact)
 //  cylinder v[0..2]  = point on axis, v[4..6] = axis dir, v[3] = r, v[7] = pt.dir, v[8] = 1/dir.dir,
-//           v[9..10] = (lo2, hi2): squared axis distances outside (lo2, hi2) are certain outliers
+//           v[9..10] = (lo2, hi2): squared axis distances outside (lo2, hi2) are certain outliers,
+//           v[11..14] = the same decisions as bounds on N = |dir x (p0 - pt)|^2, i.e. before the division by dir.dir
+//           (exact: fl(N / D) is monotone in N): N < v[11] or N >= v[12] certain outlier, v[13] <= N < v[14] certain inlier
 //  cone     v[0..2]  = apex, v[4..6] = axis dir, v[3] = opening angle, v[7] = apex.dir,
 //           v[8] = 1/dir.dir, v[9] = sin(angle), v[10] = cos(angle), v[11] = float tan(angle),
-//           v[12..13] = tan(angle) as double, v[14] = T: |axis distance - cone radius| >= T is a certain outlier
+//           v[12..13] = tan(angle) as double, v[14] = T: |axis distance - cone radius| >= T is a certain outlier,
+//           v[15] = D_in: |axis distance - cone radius| <= D_in is a certain inlier (-1: never)
 // An invalid hypothesis is all NaN: every comparison is false, so it scores 0.
 struct __align__(16) HypRec {
   float v[16];
@@ -226,6 +229,16 @@ __device__ inline void make_rec(const float* mc, bool ok, const ScoreParams& sp,
     // d_euclid >= T = (thr + band)/(1-w) can never be an inlier, whatever the normal says.
     float T = CUDART_INF_F;  // no pre-filter unless 0 <= w < 1
     if (sp.w >= 0.0 && sp.w < 0.999) T = (float)((sp.thr + (double)sp.band) / (1.0 - sp.w) * (1.0 + 1e-5)) + 1e-30f;
+    // Certain-inlier bound: the FP32 score of the fast path is w*dn + (1-w)*de with dn in [0, pi/2] whenever it is not
+    // NaN, so de <= D_in = ((thr - band) - w*pi/2) / (1-w) (margins of 2e-6 relative for the float roundings of the
+    // score) puts it below thr - band: the fast path returns true without looking at the normal. The NaN cases (normal
+    // not finite / zero, point on the axis, coordinates so large that the float difference pt - proj could vanish) are
+    // excluded by the callers: `nice` per point, axis distance >= 1 mm, |coordinates| <= 1000.
+    float D_in = -1.0f;
+    if (sp.w >= 0.0 && sp.w < 0.999 && fabsf(p0.x) <= 1000.0f && fabsf(p0.y) <= 1000.0f && fabsf(p0.z) <= 1000.0f) {
+      const double d = (((sp.thr - (double)sp.band) * (1.0 - 2e-6) - sp.w * 1.57079651) / (1.0 - sp.w)) * (1.0 - 2e-6);
+      if (d > 0.0) D_in = (float)(d * (1.0 - 3e-5));  // 3e-5: the squared-interval margins of the callers (1e-5 on sq) + rsqrt
+    }
     if (MODEL == PITT_MODEL_CYLINDER) {
       // d_euclid = |sqrt(sq) - r| >= T  <=>  sq >= (r+T)^2  or  (r-T > 0 and sq <= (r-T)^2); margins of 1e-5 relative
       const float rr = mc[6];
@@ -238,6 +251,26 @@ __device__ inline void make_rec(const float* mc, bool ok, const ScoreParams& sp,
       }
       r.v[9] = lo2;
       r.v[10] = hi2;
+      // certain inliers: in2_lo < sq < in2_hi
+      float in2_lo = CUDART_INF_F, in2_hi = -1.0f;
+      if (D_in > 0.0f && rr == rr) {
+        const float a = fmaxf(rr - D_in, 0.0f), b = rr + D_in;
+        in2_lo = fmaxf(a * a * (1.0f + 1e-5f), 1e-6f);
+        in2_hi = b * b * (1.0f - 1e-5f);
+      }
+      // the same four decisions on N = sqn0(cross0(dir, p0 - pt)): sq = fl(N / D) is non-decreasing in N
+      const float D = dot0(dir, dir);
+      float n_out_lo = 0.0f, n_out_hi = CUDART_INF_F, n_in_lo = CUDART_INF_F, n_in_end = 0.0f;
+      if (D > 0.0f && D < CUDART_INF_F) {
+        n_out_lo = ord_f(first_true_bits([&](float nv) { return (nv / D) > lo2; }));    // N < n_out_lo   <=> sq <= lo2
+        n_out_hi = ord_f(first_true_bits([&](float nv) { return (nv / D) >= hi2; }));   // N >= n_out_hi  <=> sq >= hi2
+        n_in_lo = ord_f(first_true_bits([&](float nv) { return (nv / D) > in2_lo; }));  // N >= n_in_lo   <=> sq > in2_lo
+        n_in_end = ord_f(first_true_bits([&](float nv) { return (nv / D) >= in2_hi; }));  // N < n_in_end <=> sq < in2_hi
+      }
+      r.v[11] = n_out_lo;
+      r.v[12] = n_out_hi;
+      r.v[13] = n_in_lo;
+      r.v[14] = n_in_end;
     }
     if (MODEL == PITT_MODEL_CONE) {
       r.v[9] = sinf_d(mc[6]);
@@ -247,6 +280,7 @@ __device__ inline void make_rec(const float* mc, bool ok, const ScoreParams& sp,
       r.v[12] = __int_as_float(__double2loint(t));
       r.v[13] = __int_as_float(__double2hiint(t));
       r.v[14] = T;
+      r.v[15] = (t > 0.0) ? D_in : -1.0f;  // a negative cone radius (opening angle > 90 deg) never takes the shortcut
     }
   }
 }
@@ -331,7 +365,11 @@ struct RecRegs<PITT_MODEL_CYLINDER> {
     float de = fabsf(sqrtf(sq) - r);
     float k = (dot0(pt, dir) - ptdotdir) * dirdotdir;
     f3 d = pt - (p0 + k * dir);
-    float cosang = dot0(n, d) * rsqrtf(sqn0(n) * sqn0(d));
+    const float nd2 = sqn0(n) * sqn0(d);
+    // the approximate rsqrt flushes denormals and overflows where the exact quotient does not: normals or offsets of
+    // absurd length (and NaN) take the exact sequence
+    if (!(nd2 > 1e-30f && nd2 < 1e30f)) return inlier_exact(pt, n, sp);
+    float cosang = dot0(n, d) * rsqrtf(nd2);
     cosang = fminf(1.0f, fmaxf(-1.0f, cosang));
     float dn = acosf(cosang);
     dn = fminf(dn, 3.14159265f - dn);
@@ -393,7 +431,9 @@ struct RecRegs<PITT_MODEL_CONE> {
     float ih = 1.0f / hn, ip = 1.0f / ppn;
     f3 cn = (sin_a * ih) * height + (cos_a * ip) * pp;
     float de = fabsf(sqrtf(sq) - actual_r);
-    float cosang = dot0(n, cn) * rsqrtf(sqn0(n) * sqn0(cn));
+    const float nc2 = sqn0(n) * sqn0(cn);
+    if (!(nc2 > 1e-30f && nc2 < 1e30f) || !(hn2 > 1e-30f)) return inlier_exact(pt, n, sp);  // see the cylinder
+    float cosang = dot0(n, cn) * rsqrtf(nc2);
     cosang = fminf(1.0f, fmaxf(-1.0f, cosang));
     float dn = acosf(cosang);
     dn = fminf(dn, 3.14159265f - dn);
@@ -402,6 +442,73 @@ struct RecRegs<PITT_MODEL_CONE> {
     float thr = (float)sp.thr;
     if (fabsf(score - thr) <= sp.band) return inlier_exact(pt, n, sp);
     return score < thr;  // NaN (point on the axis, zero normal, padding) is false on both paths
+  }
+};
+
+// ------------------------------------------------------------------ tier-1 classification (cylinder, cone)
+// The scoring kernel decides most evaluations from the axis distance alone: 0 = certain outlier, 1 = certain inlier
+// (both proven in make_rec to be what RecRegs::inlier would return), 2 = undecided -> RecRegs::inlier on a compacted
+// queue. `nice` = the point may take the certain-inlier shortcut (finite normal of sane length, |coordinates| <= 1000).
+__device__ __forceinline__ bool nice_point(f3 pt, f3 nv) {
+  const float n2 = sqn0(nv);
+  return fabsf(pt.x) <= 1000.0f && fabsf(pt.y) <= 1000.0f && fabsf(pt.z) <= 1000.0f && fabsf(nv.x) < 1e9f && fabsf(nv.y) < 1e9f &&
+         fabsf(nv.z) < 1e9f && n2 > 1e-18f && n2 < 1e18f;
+}
+
+template <int MODEL>
+struct Tier1;
+
+template <>
+struct Tier1<PITT_MODEL_CYLINDER> {
+  f3 p0, dir;
+  float n_out_lo, n_out_hi, n_in_lo, n_in_end;
+  __device__ __forceinline__ void load(const HypRec* rec) {
+    float4 q0 = *reinterpret_cast<const float4*>(rec->v);
+    float4 q1 = *reinterpret_cast<const float4*>(rec->v + 4);
+    float4 q2 = *reinterpret_cast<const float4*>(rec->v + 8);
+    float4 q3 = *reinterpret_cast<const float4*>(rec->v + 12);
+    p0 = mk3(q0.x, q0.y, q0.z);
+    dir = mk3(q1.x, q1.y, q1.z);
+    n_out_lo = q2.w; n_out_hi = q3.x; n_in_lo = q3.y; n_in_end = q3.z;
+  }
+  __device__ __forceinline__ int classify(f3 pt, bool nice) const {
+    const float N = sqn0(cross0(dir, p0 - pt));  // numerator of pcl::sqrPointToLineDistance, same operations as sqr_pt_line
+    if (N >= n_out_hi || N < n_out_lo) return 0;
+    if (nice && N >= n_in_lo && N < n_in_end) return 1;
+    return 2;  // includes NaN
+  }
+};
+
+template <>
+struct Tier1<PITT_MODEL_CONE> {
+  f3 apex, dir;
+  float apexdotdir, dirdotdir, tan_f, T, D_in;
+  __device__ __forceinline__ void load(const HypRec* rec) {
+    float4 q0 = *reinterpret_cast<const float4*>(rec->v);
+    float4 q1 = *reinterpret_cast<const float4*>(rec->v + 4);
+    float4 q2 = *reinterpret_cast<const float4*>(rec->v + 8);
+    float4 q3 = *reinterpret_cast<const float4*>(rec->v + 12);
+    apex = mk3(q0.x, q0.y, q0.z);
+    dir = mk3(q1.x, q1.y, q1.z); apexdotdir = q1.w;
+    dirdotdir = q2.x; tan_f = q2.w;
+    T = q3.z; D_in = q3.w;
+  }
+  __device__ __forceinline__ int classify(f3 pt, bool nice) const {
+    // same float quantities as RecRegs<CONE>::inlier
+    const float k = (dot0(pt, dir) - apexdotdir) * dirdotdir;
+    const f3 proj = apex + k * dir;
+    const f3 height = apex - proj;
+    const float hn2 = sqn0(height);
+    const float sq = sqr_pt_line(pt, apex, dir);
+    const float ar = tan_f * (hn2 * rsqrtf(hn2));  // ~ tan * |height| (within 1e-6 relative of the fast path's actual_r)
+    const float up = fabsf(ar) + T, dn = fabsf(ar) - T;
+    if (sq >= up * up * (1.0f + 1e-5f)) return 0;
+    if (dn > 0.0f && sq <= dn * dn * (1.0f - 1e-5f)) return 0;
+    if (nice && D_in > 0.0f && hn2 >= 1e-12f && sq >= 1e-6f) {  // D_in > 0 implies tan > 0: ar is the cone radius itself
+      const float b = ar + D_in, a = fmaxf(ar - D_in, 0.0f);
+      if (sq < b * b * (1.0f - 1e-5f) && sq > a * a * (1.0f + 1e-5f)) return 1;
+    }
+    return 2;
   }
 };
 

@@ -167,3 +167,84 @@ def test_cylinder_cone_prefilter_near_threshold(ctx, oracle, model, w):
     c_cpu, _, v_cpu = oracle.sac_score(xyz2, nrm2, p, samples)
     assert np.array_equal(v_gpu, v_cpu)
     assert np.array_equal(c_gpu, c_cpu)
+
+
+def _score_modes(ctx, cloud, p, samples):
+    """counts from the two-tier kernel (default) and from the generic kernel (test hook)"""
+    c2, _, v2 = ctx.sac_score(cloud, p, samples)
+    ctx.lib.pitt_debug_score_mode(1)
+    try:
+        c1, _, v1 = ctx.sac_score(cloud, p, samples)
+    finally:
+        ctx.lib.pitt_debug_score_mode(0)
+    return c2, v2, c1, v1
+
+
+@pytest.mark.parametrize("model,w,normals", [(A.MODEL_CYLINDER, 0.001, "random"), (A.MODEL_CONE, 0.0006, "random"),
+                                             (A.MODEL_CYLINDER, 0.001, "broken"), (A.MODEL_CONE, 0.0006, "broken"),
+                                             (A.MODEL_CYLINDER, 0.003, "random"), (A.MODEL_CONE, 0.002, "estimated")])
+def test_certain_inlier_shortcut_near_its_boundary(ctx, oracle, model, w, normals):
+    """the two-tier kernel accepts an evaluation without looking at the normal when the euclidean term alone keeps the
+    score below the threshold for ANY angle (d_euclid <= D_in = (thr - band - w pi/2) / (1 - w)). Points are spread
+    tightly around that boundary and given random / zero / NaN / huge normals: counts must equal PCL's."""
+    rng = np.random.default_rng(29)
+    kind = KINDS[model]
+    xyz, nrm, truth = _cluster(kind, 4000, 41, oracle)
+    p = pkg.default_sac_params(model)
+    p.normal_distance_weight = w
+    thr = p.distance_threshold
+    band = 2e-3 * w + 2e-6
+    d_in = (thr - band - w * np.pi / 2) / (1.0 - w)
+    assert d_in > 0
+    centre = xyz[:, :3].mean(axis=0)
+    # radial jitter (relative to the cluster centre, which is on the axis for these scenes only approximately: the
+    # spread factor makes up for it) concentrated at +- d_in
+    scale = 1.0 + rng.choice([-1.0, 1.0], len(xyz))[:, None] * d_in * rng.uniform(0.9, 1.1, (len(xyz), 1)) / 0.05
+    xyz2 = xyz.copy()
+    xyz2[:, :3] = (centre + (xyz[:, :3] - centre) * scale).astype(np.float32)
+    xyz2[:1500] = xyz[:1500]
+    if normals == "estimated":
+        nrm2 = oracle.estimate_normals(xyz2, 50, (0.0, 0.0, 0.0))
+    else:
+        nrm2 = nrm.copy()
+        v = rng.normal(size=(len(xyz2), 3)).astype(np.float32)
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
+        nrm2[1500:, :3] = v[1500:]  # the angle term is as large as it gets for half of the cloud
+        if normals == "broken":
+            nrm2[1500:1700, :3] = 0.0
+            nrm2[1700:1800, 0] = np.nan
+            nrm2[1800:1900, :3] *= np.float32(1e20)
+            nrm2[1900:2000, :3] *= np.float32(1e-20)
+            nrm2[2000:2050, 1] = np.inf
+    cloud = ctx.stage(xyz2, normals=nrm2)
+    samples = np.vstack([oracle.pcl_sample_stream(xyz2, model, 200),
+                         rng.integers(0, 1500, (400, A.SAMPLE_SIZE[model])).astype(np.int32)])
+    c2, v2, c1, v1 = _score_modes(ctx, cloud, p, samples)
+    c_cpu, _, v_cpu = oracle.sac_score(xyz2, nrm2, p, samples)
+    assert np.array_equal(v2, v_cpu) and np.array_equal(v1, v_cpu)
+    assert np.array_equal(c1, c_cpu)
+    assert np.array_equal(c2, c_cpu)
+    assert c_cpu.max() > 500
+
+
+@pytest.mark.parametrize("model", [A.MODEL_CYLINDER, A.MODEL_CONE])
+@pytest.mark.parametrize("n,offset", [(50000, 0.0), (3000, 0.0), (20000, 1500.0), (4097, 0.0)])
+def test_two_tier_scoring_equals_generic(ctx, oracle, model, n, offset):
+    """C3-shaped job (big cluster, thousands of hypotheses): the two-tier kernel against the generic one; a slice against
+    the oracle. offset = 1500 m moves the cloud beyond the |coordinate| <= 1000 guard of the certain-inlier shortcut."""
+    rng = np.random.default_rng(5)
+    xyz, _ = scenes.primitive_cluster(KINDS[model], n, 9)
+    xyz[:, :3] += np.float32(offset)
+    cloud = ctx.stage(xyz)
+    vp = (float(offset), float(offset), float(offset))
+    nrm = ctx.estimate_normals(cloud, 50, vp)
+    p = pkg.default_sac_params(model)
+    S = A.SAMPLE_SIZE[model]
+    samples = rng.integers(0, n, (2000, S)).astype(np.int32)
+    c2, v2, c1, v1 = _score_modes(ctx, cloud, p, samples)
+    assert np.array_equal(v2, v1)
+    assert np.array_equal(c2, c1)
+    if offset == 0.0:
+        assert c2.max() > n // 4
+    c_cpu, _, v_cpu = oracle.sac_score(xyz, nrm, p, samples[:48])
+    assert np.array_equal(c2[:48], c_cpu)

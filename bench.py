@@ -205,6 +205,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-primitives", action="store_true", help="skip the C3-shaped sphere/cylinder/cone scoring figures")
     ap.add_argument("--frames", type=int, default=256, help="frames per GPU for the secondary frames/s metric (0 = skip)")
     ap.add_argument("--frame-contexts", type=int, default=16, help="host threads / CUDA streams per GPU for the frame stream")
     ap.add_argument("--frame-workers", type=int, default=0,
@@ -439,6 +440,34 @@ def main():
         frames_info["frame_latency_note"] = "one frame at a time: stage (H2D) + segment_frame + results, 1 context + 4 helper streams"
         lctx.close()
 
+    # ---- BASELINE.json configs[2] (C3) in one line per model: a 50 000-point cluster x 10 000 hypotheses of the PCL sample
+    # stream, estimate + score on the device, 20 calls back to back between two CUDA events (rank 0's GPU; per-GPU figure)
+    primitives = None
+    if rank == 0 and not args.no_primitives:
+        from pitt_object_table_segmentation_b200 import scenes
+        primitives = {"points": 50000, "hypotheses": 10000, "note": "per GPU; algorithmic flop per evaluation from SURVEY 8d "
+                      "(sphere 10, cylinder 69, cone 91) against the live FFMA peak"}
+        for kind, model, flop in (("sphere", A.MODEL_SPHERE, 10), ("cylinder", A.MODEL_CYLINDER, 69), ("cone", A.MODEL_CONE, 91)):
+            pxyz, _ = scenes.primitive_cluster(kind, 50000, 5)
+            pcloud = ctx.stage(pxyz)
+            ctx.estimate_normals(pcloud, 50)
+            pp = pkg.default_sac_params(model)
+            ps = torch.from_numpy(ctx.pcl_sample_stream(pcloud, model, 10000)).to(dev)
+            pc = torch.zeros(10000, dtype=torch.int32, device=dev)
+            for _ in range(5):
+                ctx.sac_score_device(pcloud, pp, ps.data_ptr(), 10000, pc.data_ptr())
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                ctx.sac_score_device(pcloud, pp, ps.data_ptr(), 10000, pc.data_ptr())
+            e1.record()
+            torch.cuda.synchronize()
+            pms = e0.elapsed_time(e1) / 20
+            ev = 50000.0 * 10000.0 / (pms * 1e-3)
+            primitives[kind] = {"ms": pms, "evals_per_s": ev, "algorithmic_tflops": ev * flop / 1e12,
+                                "frac_of_ffma_peak": ev * flop / 1e12 / peak_ffma, "best_count": int(pc.max().item())}
+            pcloud.release()
+
     line = None
     if rank == 0:
         line = {
@@ -455,6 +484,7 @@ def main():
             "gpu_launches": int(launches),
             "roofline": roofline,
             "frames": frames_info,
+            "primitives": primitives,
             "wall_s_timed_region": wall,
         }
         if not args.no_cpu_baseline:

@@ -10,6 +10,8 @@
 #include <unordered_map>
 
 #include "pitt_common.cuh"
+#include <type_traits>
+
 #include "sac.cuh"
 #include "sac_device.cuh"
 
@@ -169,32 +171,44 @@ score2_kernel(const float4* __restrict__ xyz, const float4* __restrict__ nrm, in
       }
     }
     int qn = 0;  // warp-uniform
-    for (int h = 0; h < hc; ++h) {
-      if (s_rec[h].v[0] != s_rec[h].v[0]) continue;  // invalid hypothesis (uniform branch)
-      Tier1<MODEL> r;
-      r.load(s_rec + h);
-      int c = 0;
+    // Full tiles whose points may all take the certain-inlier shortcut (the normal case) run the loop without the two
+    // per-point masks (warp-uniform choice).
+    const bool plain = __all_sync(0xffffffffu, valid == (1u << P) - 1u && nice == (1u << P) - 1u);
+    auto hyp_loop = [&](auto plain_tag) {
+      constexpr bool PLAIN = decltype(plain_tag)::value;
+      for (int h = 0; h < hc; ++h) {
+        if (s_rec[h].v[0] != s_rec[h].v[0]) continue;  // invalid hypothesis (uniform branch)
+        Tier1<MODEL> r;
+        r.load(s_rec + h);
+        int c = 0;
 #pragma unroll
-      for (int p = 0; p < P; ++p) {
-        const int cls = ((valid >> p) & 1u) ? r.classify(pt[p], (nice >> p) & 1u) : 0;
-        c += (cls == 1) ? 1 : 0;
-        const unsigned m = __ballot_sync(0xffffffffu, cls == 2);
-        if (m) {
-          if (cls == 2) q[qn + __popc(m & lt)] = make_int2(h, base + p * TPB + (int)threadIdx.x);
-          qn += __popc(m);
+        for (int p = 0; p < P; ++p) {
+          bool in, und;
+          r.classify(pt[p], PLAIN ? true : (bool)((nice >> p) & 1u), in, und);
+          if (!PLAIN) {  // padding lanes classify garbage
+            const bool v = (valid >> p) & 1u;
+            in &= v;
+            und &= v;
+          }
+          c += in ? 1 : 0;
+          const unsigned m = __ballot_sync(0xffffffffu, und);
+          if (und) q[qn + __popc(m & lt)] = make_int2(h, base + p * TPB + (int)threadIdx.x);  // no branch around the push:
+          qn += __popc(m);                                                                    // it is taken 4 times out of 5
+        }
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (lane == 0 && c) atomicAdd(&s_cnt[h], c);
+        if (qn >= 32) {
+          __syncwarp();
+          do {
+            qn -= 32;
+            full_eval(q[qn + lane]);
+          } while (qn >= 32);
+          __syncwarp();
         }
       }
-      c = __reduce_add_sync(0xffffffffu, c);
-      if (lane == 0 && c) atomicAdd(&s_cnt[h], c);
-      if (qn >= 32) {
-        __syncwarp();
-        do {
-          qn -= 32;
-          full_eval(q[qn + lane]);
-        } while (qn >= 32);
-        __syncwarp();
-      }
-    }
+    };
+    if (plain) hyp_loop(std::true_type{});
+    else hyp_loop(std::false_type{});
     __syncwarp();
     if (lane < qn) full_eval(q[lane]);
     __syncwarp();
@@ -917,6 +931,9 @@ static int launch_score_generic(pitt_ctx* ctx, const pitt_cloud* c, const HypRec
   const int tiles = cdiv(n, tile);
   const int want_ctas = ctx->sm_count * 4;
   int hyp_chunk = H < 512 ? H : 512;
+  // Big jobs: many small CTAs (128 hypotheses x one point range), so that the last, partially filled wave of CTAs is a
+  // small fraction of the run (600 CTAs on 296 slots ran as 3 waves for 2.03 waves of work).
+  if (TWO_TIER && (long long)tiles * cdiv(H, 128) >= 6LL * want_ctas) hyp_chunk = 128;
   if (tiles * cdiv(H, hyp_chunk) < want_ctas) {
     int chunks_wanted = cdiv(want_ctas, tiles);
     hyp_chunk = std::max(16, cdiv(H, chunks_wanted));
@@ -1027,7 +1044,8 @@ int sac_score(pitt_ctx* ctx, const pitt_cloud* c, int model, const HypRec* d_rec
     case PITT_MODEL_CYLINDER:
       if (g_score_mode == 1) return launch_score_generic<PITT_MODEL_CYLINDER, 2, false>(ctx, c, d_recs, H, sp, d_counts);
       if (c->n < 4096) return launch_score_generic<PITT_MODEL_CYLINDER, 1, true>(ctx, c, d_recs, H, sp, d_counts);
-      return launch_score_generic<PITT_MODEL_CYLINDER, 4, true>(ctx, c, d_recs, H, sp, d_counts);
+      if (c->n < 32768) return launch_score_generic<PITT_MODEL_CYLINDER, 4, true>(ctx, c, d_recs, H, sp, d_counts);
+      return launch_score_generic<PITT_MODEL_CYLINDER, 8, true>(ctx, c, d_recs, H, sp, d_counts);
     default:
       if (g_score_mode == 1) return launch_score_generic<PITT_MODEL_CONE, 2, false>(ctx, c, d_recs, H, sp, d_counts);
       if (c->n < 4096) return launch_score_generic<PITT_MODEL_CONE, 1, true>(ctx, c, d_recs, H, sp, d_counts);

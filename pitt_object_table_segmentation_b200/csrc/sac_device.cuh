@@ -471,11 +471,12 @@ struct Tier1<PITT_MODEL_CYLINDER> {
     dir = mk3(q1.x, q1.y, q1.z);
     n_out_lo = q2.w; n_out_hi = q3.x; n_in_lo = q3.y; n_in_end = q3.z;
   }
-  __device__ __forceinline__ int classify(f3 pt, bool nice) const {
+  // in = certain inlier, und = undecided (needs RecRegs::inlier); neither = certain outlier. NaN ends undecided.
+  __device__ __forceinline__ void classify(f3 pt, bool nice, bool& in, bool& und) const {
     const float N = sqn0(cross0(dir, p0 - pt));  // numerator of pcl::sqrPointToLineDistance, same operations as sqr_pt_line
-    if (N >= n_out_hi || N < n_out_lo) return 0;
-    if (nice && N >= n_in_lo && N < n_in_end) return 1;
-    return 2;  // includes NaN
+    const bool out = (N >= n_out_hi) | (N < n_out_lo);
+    in = nice & (N >= n_in_lo) & (N < n_in_end);
+    und = !(out | in);
   }
 };
 
@@ -493,7 +494,7 @@ struct Tier1<PITT_MODEL_CONE> {
     dirdotdir = q2.x; tan_f = q2.w;
     T = q3.z; D_in = q3.w;
   }
-  __device__ __forceinline__ int classify(f3 pt, bool nice) const {
+  __device__ __forceinline__ void classify(f3 pt, bool nice, bool& in, bool& und) const {
     // same float quantities as RecRegs<CONE>::inlier
     const float k = (dot0(pt, dir) - apexdotdir) * dirdotdir;
     const f3 proj = apex + k * dir;
@@ -502,13 +503,11 @@ struct Tier1<PITT_MODEL_CONE> {
     const float sq = sqr_pt_line(pt, apex, dir);
     const float ar = tan_f * (hn2 * rsqrtf(hn2));  // ~ tan * |height| (within 1e-6 relative of the fast path's actual_r)
     const float up = fabsf(ar) + T, dn = fabsf(ar) - T;
-    if (sq >= up * up * (1.0f + 1e-5f)) return 0;
-    if (dn > 0.0f && sq <= dn * dn * (1.0f - 1e-5f)) return 0;
-    if (nice && D_in > 0.0f && hn2 >= 1e-12f && sq >= 1e-6f) {  // D_in > 0 implies tan > 0: ar is the cone radius itself
-      const float b = ar + D_in, a = fmaxf(ar - D_in, 0.0f);
-      if (sq < b * b * (1.0f - 1e-5f) && sq > a * a * (1.0f + 1e-5f)) return 1;
-    }
-    return 2;
+    const bool out = (sq >= up * up * (1.0f + 1e-5f)) | ((dn > 0.0f) & (sq <= dn * dn * (1.0f - 1e-5f)));
+    // D_in > 0 implies tan > 0: ar is the cone radius itself
+    const float b = ar + D_in, a = fmaxf(ar - D_in, 0.0f);
+    in = nice & (D_in > 0.0f) & (hn2 >= 1e-12f) & (sq >= 1e-6f) & (sq < b * b * (1.0f - 1e-5f)) & (sq > a * a * (1.0f + 1e-5f)) & !out;
+    und = !(out | in);
   }
 };
 

@@ -11,7 +11,9 @@ import pitt_object_table_segmentation_b200 as pkg
 from pitt_object_table_segmentation_b200 import _abi as A, scenes
 
 FLOP = {"sphere": 10, "cylinder": 69, "cone": 91}
-ctx = pkg.Context(0)
+import torch
+
+ctx = pkg.Context(0, seed=1, stream=torch.cuda.current_stream().cuda_stream)
 peak = ctx.fp32_peak(0)
 out = {"fp32_ffma_peak_tflops": peak}
 for kind, model in (("cylinder", A.MODEL_CYLINDER), ("cone", A.MODEL_CONE), ("sphere", A.MODEL_SPHERE)):
@@ -30,12 +32,23 @@ for kind, model in (("cylinder", A.MODEL_CYLINDER), ("cone", A.MODEL_CONE), ("sp
                 if kind == "sphere" and mode == 1:
                     continue
                 ctx.lib.pitt_debug_score_mode(mode)
+                counts, _, valid = ctx.sac_score(cloud, p, samples)
+                d_s = torch.from_numpy(samples).cuda()
+                d_c = torch.zeros(H, dtype=torch.int32, device="cuda")
+                for _ in range(10):  # warm-up: clocks ramp up only under continuous load
+                    ctx.sac_score_device(cloud, p, d_s.data_ptr(), H, d_c.data_ptr())
                 ms = []
-                for _ in range(6):
-                    counts, _, valid = ctx.sac_score(cloud, p, samples)
-                    ms.append(ctx.last_device_ms)
+                for _ in range(3):  # estimate + score on device-resident samples, 20 calls back to back between two events
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(20):
+                        ctx.sac_score_device(cloud, p, d_s.data_ptr(), H, d_c.data_ptr())
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ms.append(e0.elapsed_time(e1) / 20)
                 ctx.lib.pitt_debug_score_mode(0)
-                t = float(np.median(ms[2:]))
+                assert np.array_equal(d_c.cpu().numpy(), counts)
+                t = float(np.median(ms))
                 ev = n * H / (t * 1e-3)
                 key = f"{kind}_n{n}_{sampler}_{'two_tier' if mode == 0 else 'generic'}"
                 out[key] = {"device_ms": t, "gevals_per_s": ev / 1e9, "algorithmic_tflops": ev * FLOP[kind] / 1e12,

@@ -304,19 +304,20 @@ def main():
     value = evals_step / (ms_step * 1e-3)
 
     # ---- end-to-end arm: host buffers in, host buffers out, through the C ABI
-    inl_host = np.empty(n, np.int32)
+    inl_pinned = torch.empty(n, dtype=torch.int32).pin_memory()  # the response's index vector (pinned, like the request's cloud)
+    inl_host = inl_pinned.numpy()
     n_inl, n_co = C.c_int(0), C.c_int(0)
     co = np.zeros(8, np.float32)
     handle = C.c_void_p()
     d2h_bytes = [0]
 
     def step_e2e():
-        st = ctx.lib.pitt_stage_cloud(ctx.handle, C.c_void_p(host_pinned.data_ptr()), 16, n, C.byref(handle))
+        # the call a service callback makes: the cloud of the request (pinned host memory) in, inliers + coefficients out;
+        # the library overlaps the host -> device copy with the scoring (pitt_sac_segment_host)
+        st = ctx.lib.pitt_sac_segment_host(ctx.handle, C.c_void_p(host_pinned.data_ptr()), 16, n, C.byref(p),
+                                           inl_host.ctypes.data_as(A.i32p), n, C.byref(n_inl), co.ctypes.data_as(A.f32p),
+                                           C.byref(n_co), None)
         assert st == 0, st
-        st = ctx.lib.pitt_sac_segment(ctx.handle, handle, C.byref(p), inl_host.ctypes.data_as(A.i32p), n,
-                                      C.byref(n_inl), co.ctypes.data_as(A.f32p), C.byref(n_co), None)
-        assert st == 0, st
-        ctx.lib.pitt_release_cloud(ctx.handle, handle)
         d2h_bytes[0] = n_inl.value * 4 + 8 * 4 + 16 * 4
         if world > 1:
             dist.all_gather_into_tensor(d_all, d_counts)

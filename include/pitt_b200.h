@@ -310,6 +310,15 @@ int pitt_knn(pitt_ctx* ctx, const pitt_cloud* cloud, int k, int32_t* out_idx, fl
 int pitt_sac_segment(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_sac_params* params,
                      int32_t* inliers /* NULL: count only */, int inliers_cap, int* n_inliers,
                      float coeffs[8], int* n_coeffs, pitt_sac_info* info /* nullable */);
+/* The same on a cloud that is still in host memory, i.e. what a service callback has in hand: fromROSMsg
+ * (pc_manager.cpp:85-94) + seg.segment() (supports_segmentation_srv.cpp:110, plane_segmentation_srv.cpp:67) in one call,
+ * without the intermediate synchronisations; clouds of 16 M points and more travel in chunks on a second CUDA stream and
+ * are scored chunk by chunk while the rest is still being copied (plane models on point_step-16 clouds of >= 2^18 points;
+ * any other input is staged, segmented and released in sequence).
+ * xyz is borrowed for the call. Results are identical to pitt_stage_cloud + pitt_sac_segment. */
+int pitt_sac_segment_host(pitt_ctx* ctx, const void* xyz, int stride_bytes, int n, const pitt_sac_params* params,
+                          int32_t* inliers /* NULL: count only */, int inliers_cap, int* n_inliers,
+                          float coeffs[8], int* n_coeffs, pitt_sac_info* info /* nullable */);
 
 /* Parity/bench hook below segment(): score a caller supplied sample table. For hypothesis h the
  * library estimates the model from samples[h*S .. h*S+S) (computeModelCoefficients), then counts

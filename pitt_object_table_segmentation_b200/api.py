@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "pitt_default_cluster_params", "pitt_default_frame_params", "pitt_stage_cloud", "pitt_stage_cloud_device",
     "pitt_set_normals", "pitt_cloud_size", "pitt_cloud_has_normals", "pitt_cloud_device_points",
     "pitt_cloud_device_normals", "pitt_release_cloud", "pitt_estimate_normals", "pitt_get_normals", "pitt_knn",
-    "pitt_sac_segment", "pitt_sac_score", "pitt_sac_score_device", "pitt_argmax_counts_device", "pitt_sac_finish_device", "pitt_sac_select", "pitt_sac_refine",
+    "pitt_sac_segment", "pitt_sac_segment_host", "pitt_sac_score", "pitt_sac_score_device", "pitt_argmax_counts_device", "pitt_sac_finish_device", "pitt_sac_select", "pitt_sac_refine",
     "pitt_pcl_sample_stream", "pitt_euclidean_clusters", "pitt_find_supports", "pitt_cluster_service",
     "pitt_primitive_service", "pitt_select_primitive", "pitt_segment_frame", "pitt_segment_frames_batched", "pitt_fp32_peak", "pitt_last_device_ms",
     "pitt_kernel_launches",
@@ -72,6 +72,8 @@ def load_library():
     lib.pitt_knn.argtypes = [vp, vp, C.c_int, A.i32p, A.f32p]
     lib.pitt_sac_segment.argtypes = [vp, vp, C.POINTER(A.SacParams), A.i32p, C.c_int, C.POINTER(C.c_int), A.f32p,
                                      C.POINTER(C.c_int), C.POINTER(A.SacInfo)]
+    lib.pitt_sac_segment_host.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(A.SacParams), A.i32p, C.c_int, C.POINTER(C.c_int),
+                                          A.f32p, C.POINTER(C.c_int), C.POINTER(A.SacInfo)]
     lib.pitt_sac_score.argtypes = [vp, vp, C.POINTER(A.SacParams), A.i32p, C.c_int, A.i32p, A.f32p,
                                    C.POINTER(C.c_uint8)]
     lib.pitt_sac_score_device.argtypes = [vp, vp, C.POINTER(A.SacParams), vp, C.c_int, vp]
@@ -300,6 +302,20 @@ class Context:
         info = A.SacInfo()
         self._check(self.lib.pitt_sac_segment(self.handle, cloud.handle, C.byref(params), inl.ctypes.data_as(A.i32p), n,
                                               C.byref(n_inl), co.ctypes.data_as(A.f32p), C.byref(n_co), C.byref(info)))
+        return {"inliers": inl[: n_inl.value].copy(), "coeffs": co[: n_co.value].copy(), "info": info}
+
+    def sac_segment_host(self, xyz, params, host_ptr=None):
+        """fromROSMsg + seg.segment() on a host cloud (n x 4 float32, or n x 3) in one call; host_ptr = address of a pinned
+        copy of the same array (the H2D then runs at full PCIe speed and overlaps the scoring)."""
+        xyz = np.ascontiguousarray(xyz, np.float32)
+        n, stride = xyz.shape[0], xyz.shape[1] * 4
+        inl = np.empty(max(n, 1), np.int32)
+        n_inl, n_co = C.c_int(0), C.c_int(0)
+        co = np.zeros(8, np.float32)
+        info = A.SacInfo()
+        ptr = C.c_void_p(host_ptr) if host_ptr is not None else xyz.ctypes.data_as(C.c_void_p)
+        self._check(self.lib.pitt_sac_segment_host(self.handle, ptr, stride, n, C.byref(params), inl.ctypes.data_as(A.i32p), n,
+                                                   C.byref(n_inl), co.ctypes.data_as(A.f32p), C.byref(n_co), C.byref(info)))
         return {"inliers": inl[: n_inl.value].copy(), "coeffs": co[: n_co.value].copy(), "info": info}
 
     def sac_score(self, cloud, params, samples):

@@ -73,6 +73,10 @@ void pitt_destroy(pitt_ctx* ctx) {
   for (auto& b : ctx->cloud_pool) cudaFree(b.p);
   if (ctx->d_arena) cudaFree(ctx->d_arena);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  if (ctx->h_pin2) cudaFreeHost(ctx->h_pin2);
+  for (cudaEvent_t e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
+  if (ctx->ev_copy_gate) cudaEventDestroy(ctx->ev_copy_gate);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -309,6 +313,105 @@ int pitt_sac_segment(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params* 
     *info = r.info;
     info->device_ms = ctx->last_ms;
   }
+  return status;
+}
+
+static int g_stream_chunks = -1;  // -1: read PITT_STREAM_CHUNKS on first use; 0: by cloud size; k: k equal chunks
+void pitt_debug_stream_chunks(int k) { g_stream_chunks = k < 0 ? 0 : (k > 8 ? 8 : k); }
+
+/* seg.segment() on a cloud that is still in host memory (the PointCloud2 payload of the service request): stage + segment +
+ * release in one call. Plane models on point_step-16 clouds of at least 2^18 points take the fused path (sample points
+ * fetched ahead, no intermediate synchronisation; clouds of 16 M points and more travel in chunks on a second stream and
+ * are scored chunk by chunk under the copy); everything else is the three calls one after the other.
+ * Results are identical to pitt_stage_cloud + pitt_sac_segment (tests/test_gpu_plane.py::test_segment_host_*). */
+int pitt_sac_segment_host(pitt_ctx* ctx, const void* xyz, int stride_bytes, int n, const pitt_sac_params* p, int32_t* inliers, int cap,
+                          int* n_inliers, float coeffs[8], int* n_coeffs, pitt_sac_info* info) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!p || !n_inliers || !coeffs || !n_coeffs || n < 0 || (n > 0 && !xyz)) return fail(ctx, PITT_ERR_INVALID, "pitt_sac_segment_host arguments");
+  cudaSetDevice(ctx->device);
+  const bool streaming = (p->model == PITT_MODEL_PLANE) && stride_bytes == 16 && n >= (1 << 18) && p->sampler != PITT_SAMPLER_PHILOX;
+  if (!streaming) {
+    pitt_cloud* c = nullptr;
+    PITT_TRY(pitt_stage_cloud(ctx, xyz, stride_bytes, n, &c));
+    const int st = pitt_sac_segment(ctx, c, p, inliers, cap, n_inliers, coeffs, n_coeffs, info);
+    pitt_release_cloud(ctx, c);
+    return st;
+  }
+  // Chunk plan. Every extra chunk costs one more scoring launch (set-up kernels, pipeline fill, an imbalanced last round:
+  // ~0.1 ms measured), a chunk's copy hides only while the previous chunk is being scored: chunks of at least 8 M points
+  // (128 MB, 2.3 ms of PCIe time). A 1 M-point cloud (C2) therefore travels in one piece - the fused call still saves the
+  // stage/segment/release round trips (1.27 vs 1.40 ms) -, a 50 M-point cloud (C5) in 6.
+  // PITT_STREAM_CHUNKS=k / pitt_debug_stream_chunks(k) (1..8): k equal chunks whatever the size (tuning hook, tests).
+  if (g_stream_chunks < 0) {
+    const char* v = getenv("PITT_STREAM_CHUNKS");
+    g_stream_chunks = v ? std::max(1, std::min(8, atoi(v))) : 0;
+  }
+  const int K_env = g_stream_chunks;
+  const int K_equal = K_env > 0 ? K_env : std::max(1, std::min(8, n / (8 << 20)));
+  if (!ctx->copy_stream) {
+    PITT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 8; ++k) PITT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_chunk[k], cudaEventDisableTiming));
+    PITT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy_gate, cudaEventDisableTiming));
+  }
+  trace_mark("segment_host: enter");
+  CallTimer timer(ctx);
+  pitt_cloud* c = new pitt_cloud();
+  c->n = n;
+  if (pool_alloc(ctx, (size_t)n * sizeof(float4), (void**)&c->d_xyz) != PITT_OK) { delete c; return PITT_ERR_CUDA; }
+  trace_mark("segment_host: pool_alloc done");
+  c->h_src = static_cast<const float*>(xyz);
+  {
+    auto round512 = [](long long v) { return (int)(((v + 511) / 512) * 512); };  // whole 512-point chunks of the scoring kernels
+    int k = 0;
+    c->stream_off[0] = 0;
+    const int step = round512(cdiv(n, K_equal));
+    while (c->stream_off[k] < n) { c->stream_off[k + 1] = std::min(n, c->stream_off[k] + step); ++k; }
+    c->stream_chunks = k;
+  }
+  // the buffer may have been used by earlier work of this context's stream
+  cudaEventRecord(ctx->ev_copy_gate, ctx->stream);
+  cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy_gate, 0);
+  for (int k = 0; k < c->stream_chunks; ++k) {
+    const size_t off = (size_t)c->stream_off[k];
+    const size_t cnt = (size_t)c->stream_off[k + 1] - off;
+    cudaError_t e = cudaMemcpyAsync(c->d_xyz + off, (const char*)xyz + off * 16, cnt * 16, cudaMemcpyHostToDevice, ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_chunk[k], ctx->copy_stream);
+    if (e != cudaSuccess) {
+      cudaStreamSynchronize(ctx->copy_stream);
+      pitt_release_cloud(ctx, c);
+      return fail(ctx, PITT_ERR_CUDA, "chunked H2D of the cloud", e);
+    }
+  }
+  trace_mark("segment_host: chunk copies issued");
+  SacDeviceResult r;
+  *n_inliers = 0;
+  *n_coeffs = 0;
+  int status = sac_segment_impl(ctx, c, *p, &r);
+  trace_mark("segment_host: sac_segment_impl returned");
+  if (status == PITT_OK) {
+    *n_inliers = r.n_inliers;
+    *n_coeffs = r.n_coeffs;
+    for (int i = 0; i < 8; ++i) coeffs[i] = r.coeffs[i];
+    if (r.n_inliers > 0 && inliers) {
+      if (cap < r.n_inliers) {
+        status = fail(ctx, PITT_ERR_CAPACITY, "inlier buffer too small");
+      } else {
+        cudaError_t e = cudaMemcpyAsync(inliers, r.d_inliers, (size_t)r.n_inliers * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e != cudaSuccess) status = fail(ctx, PITT_ERR_CUDA, "D2H of the inlier list", e);
+      }
+    }
+  }
+  // the caller's buffer is only borrowed for the call: every copy has left it (early returns of the segmentation included)
+  cudaStreamSynchronize(ctx->copy_stream);
+  cudaStreamSynchronize(ctx->stream);
+  trace_mark("segment_host: inliers on the host");
+  c->stream_chunks = 0;
+  timer.finish();
+  if (info && status == PITT_OK) {
+    *info = r.info;
+    info->device_ms = ctx->last_ms;
+  }
+  pitt_release_cloud(ctx, c);
   return status;
 }
 

@@ -42,6 +42,12 @@ struct pitt_ctx {
   struct pitt_workers* workers = nullptr;
   int n_workers = 4;
   cudaEvent_t ev_fan = nullptr;
+  // pitt_sac_segment_host: the cloud travels host -> device in chunks on a second stream while the first chunks are scored
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_copy_gate = nullptr;
+  void* h_pin2 = nullptr;  // pinned block for the gathered sample points (h_pin holds the sample indices at that time)
+  size_t h_pin2_bytes = 0;
 };
 
 struct pitt_cloud {
@@ -51,6 +57,11 @@ struct pitt_cloud {
   bool has_normals = false;
   std::vector<float> h_xyz;  // lazy host mirror (n*4)
   bool h_valid = false;
+  // streaming stage (pitt_sac_segment_host only): chunk k is on the device once
+  // ctx->ev_chunk[k] has fired; h_src = the caller's buffer (point_step 16), valid for the duration of the fused call
+  mutable int stream_chunks = 0;
+  int stream_off[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // chunk k = points [stream_off[k], stream_off[k + 1])
+  const float* h_src = nullptr;
 };
 
 namespace pitt {
@@ -124,6 +135,19 @@ inline int pinned_reserve(pitt_ctx* ctx, size_t bytes) {
   cudaError_t e = cudaMallocHost(&ctx->h_pin, want);
   if (e != cudaSuccess) return fail(ctx, PITT_ERR_CUDA, "cudaMallocHost", e);
   ctx->h_pin_bytes = want;
+  return PITT_OK;
+}
+
+inline int pinned2_reserve(pitt_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->h_pin2_bytes) return PITT_OK;
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->h_pin2) cudaFreeHost(ctx->h_pin2);
+  ctx->h_pin2 = nullptr;
+  ctx->h_pin2_bytes = 0;
+  size_t want = bytes + bytes / 4 + 4096;
+  cudaError_t e = cudaMallocHost(&ctx->h_pin2, want);
+  if (e != cudaSuccess) return fail(ctx, PITT_ERR_CUDA, "cudaMallocHost", e);
+  ctx->h_pin2_bytes = want;
   return PITT_OK;
 }
 
@@ -214,6 +238,17 @@ struct TraceScope {
     }
   }
 };
+
+// PITT_TRACE=2: host time stamps without synchronisation (where the host thread is when)
+inline void trace_mark(const char* what) {
+  static int e = -1;
+  static double t_prev = 0.0;
+  if (e < 0) { const char* v = getenv("PITT_TRACE"); e = (v && v[0] == '2') ? 1 : 0; }
+  if (e != 1) return;
+  const double t = TraceScope::now();
+  fprintf(stderr, "[pitt mark] %-40s +%8.3f ms\n", what, t_prev == 0.0 ? 0.0 : t - t_prev);
+  t_prev = t;
+}
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -618,8 +618,10 @@ std::vector<float> g_plane_tc_dump_host;  // 128 x 256 accumulators + sigma, C
 // Scores H plane hypotheses on the tensor path. *d_use_out points at an int that is 1 when the
 // tensor kernel did the work and 0 when the caller must run the exact kernel (non-finite cloud,
 // degenerate scale): the decision is made on the device, no host round trip.
+// d_extra (nullable): further points every hypothesis may pass through (the sample points when c is only a chunk of the
+// cloud): they enter the coordinate bounds the scale is derived from.
 int launch_score_plane_tc(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_recs, int H, const ScoreParams& sp, int* d_counts,
-                          const int** d_use_out) {
+                          const int** d_use_out, const float4* d_extra, int n_extra) {
   const int n = c->n;
   const int n_hb = cdiv(H, TC_M);
   const int n_chunks = cdiv(n, TC_CHUNK);
@@ -641,6 +643,10 @@ int launch_score_plane_tc(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_re
   int ab = std::min(cdiv(n, 256 * 8), ctx->sm_count * 8);
   tc_absmax_kernel<<<ab, 256, 0, ctx->stream>>>(c->d_xyz, n, d_scr);
   TC_LAUNCH_CHECK(ctx, "tc_absmax_kernel");
+  if (d_extra && n_extra > 0) {
+    tc_absmax_kernel<<<std::min(cdiv(n_extra, 256 * 8), ctx->sm_count * 8), 256, 0, ctx->stream>>>(d_extra, n_extra, d_scr);
+    TC_LAUNCH_CHECK(ctx, "tc_absmax_kernel");
+  }
   tc_params_kernel<<<1, 1, 0, ctx->stream>>>(d_scr, sp.thr_up, g_plane_tc_acc_ulps, d_P);
   TC_LAUNCH_CHECK(ctx, "tc_params_kernel");
   tc_hyp_image_kernel<<<n_hb, TC_M, 0, ctx->stream>>>(d_recs, H, d_P, d_image);

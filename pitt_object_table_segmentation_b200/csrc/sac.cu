@@ -963,12 +963,12 @@ int g_score_mode = 0;  // test hook: 0 two-tier kernel for cylinder/cone, 1 gene
 int g_plane_mode = 0;  // test hook: 0 automatic (tensor path on large jobs), 1 exact packed kernel only,
                        // 2 FFMA filter + exact re-evaluation always, 3 tensor-core path (plane_tc.cu) always
 int launch_score_plane_tc(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_recs, int H, const ScoreParams& sp, int* d_counts,
-                          const int** d_use_out);
+                          const int** d_use_out, const float4* d_extra, int n_extra);
 unsigned long long g_plane_filter_stats[2] = {0, 0};  // last call with stats enabled: pairs, re-evaluated pairs
 int g_plane_filter_collect_stats = 0;
 
 static int launch_score_plane_packed(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_recs, int H, const ScoreParams& sp,
-                                     int* d_counts) {
+                                     int* d_counts, const float4* d_extra = nullptr, int n_extra = 0) {
   constexpr int KH = 8, TPB = 128, TILE = 512;
   const int n = c->n;
   const int hblocks = cdiv(H, KH * TPB);
@@ -990,8 +990,9 @@ static int launch_score_plane_packed(pitt_ctx* ctx, const pitt_cloud* c, const H
   const bool tensor = (g_plane_mode == 3) || (g_plane_mode == 0 && (double)n * (double)H >= 134217728.0);
   const bool filter = (g_plane_mode == 2);
   const int* d_skip = nullptr;  // device flag: non-zero = a fast kernel did the work, the exact kernel returns at once
-  if (tensor) PITT_TRY(launch_score_plane_tc(ctx, c, d_recs, H, sp, d_counts, &d_skip));
+  if (tensor) PITT_TRY(launch_score_plane_tc(ctx, c, d_recs, H, sp, d_counts, &d_skip, d_extra, n_extra));
   if (filter) {
+    if (d_extra) return fail(ctx, PITT_ERR_STATE, "plane filter mode does not take a chunked cloud");
     d_skip = &d_P->use_filter;
     PITT_CUDA(ctx, cudaMemsetAsync(d_stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
     int ab = std::min(cdiv(n, 256 * 8), ctx->sm_count * 8);
@@ -1030,6 +1031,33 @@ static int launch_score_plane_packed(pitt_ctx* ctx, const pitt_cloud* c, const H
 }
 
 int g_force_generic_plane = 0;  // test hook: 1 routes plane scoring through the generic kernel
+
+// Plane scoring of a cloud that is still arriving (pitt_sac_segment_host): chunk k is scored as soon as its copy has
+// completed, while the copy engine brings in chunk k + 1. Counts add up over the chunks. d_gather = the sample points
+// (every hypothesis passes through three of them): with the chunk's own points they bound the tensor path's scale.
+int sac_score_plane_streaming(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_recs, int H, const ScoreParams& sp, int* d_counts,
+                              const float4* d_gather, int n_gather) {
+  PITT_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (size_t)H * sizeof(int), ctx->stream));
+  for (int k = 0; k < c->stream_chunks; ++k) {
+    PITT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[k], 0));
+    const int off = c->stream_off[k];
+    pitt_cloud view;
+    view.n = c->stream_off[k + 1] - off;
+    view.d_xyz = c->d_xyz + off;
+    if (view.n <= 0) continue;
+    if (H >= 256 && !g_force_generic_plane) PITT_TRY(launch_score_plane_packed(ctx, &view, d_recs, H, sp, d_counts, d_gather, n_gather));
+    else PITT_TRY((launch_score_generic<PITT_MODEL_PLANE, 8, false>(ctx, &view, d_recs, H, sp, d_counts)));
+  }
+  c->stream_chunks = 0;  // everything this stream does from here on is ordered after the last chunk
+  return PITT_OK;
+}
+
+// a consumer that needs the whole cloud at once
+static int stream_complete(pitt_ctx* ctx, const pitt_cloud* c) {
+  for (int k = 0; k < c->stream_chunks; ++k) PITT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[k], 0));
+  c->stream_chunks = 0;
+  return PITT_OK;
+}
 
 int sac_score(pitt_ctx* ctx, const pitt_cloud* c, int model, const HypRec* d_recs, int H, const ScoreParams& sp,
               int* d_counts) {
@@ -1382,6 +1410,15 @@ int sac_finish_from_winner(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_pa
 }
 
 // ------------------------------------------------------------------ seg.segment()
+// sample points of a cloud that is still in (pinned, device-mapped) host memory -> contiguous device copy + identity sample table
+__global__ void gather_points_kernel(const float4* __restrict__ host_xyz, const int* __restrict__ samples, int ns,
+                                     float4* __restrict__ out, int* __restrict__ iota) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ns) return;
+  out[i] = host_xyz[samples[i]];
+  iota[i] = i;
+}
+
 int sac_segment_impl(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& p, SacDeviceResult* out) {
   const int model = p.model;
   const int S = sample_size(model);
@@ -1417,7 +1454,8 @@ int sac_segment_impl(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& 
   PITT_TRY(arena_alloc(ctx, (size_t)n, &d_inl));
 
   TraceScope ts_all(ctx, "  sac_segment_impl");
-  PclSampleStream stream(n, model, (c->h_valid ? c->h_xyz.data() : nullptr));
+  PclSampleStream stream(n, model, (c->h_valid ? c->h_xyz.data() : c->h_src));
+  if (c->stream_chunks > 0 && (model != PITT_MODEL_PLANE || p.sampler == PITT_SAMPLER_PHILOX)) PITT_TRY(stream_complete(ctx, c));
   RansacScan scan;
   std::vector<int> h_samples;
   int H_total = 0;
@@ -1460,9 +1498,44 @@ int sac_segment_impl(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& 
       memcpy(ctx->h_pin, h_samples.data(), (size_t)H_have * S * sizeof(int));
       PITT_CUDA(ctx, cudaMemcpyAsync(d_samples, ctx->h_pin, (size_t)H_have * S * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     }
-    PITT_TRY(sac_estimate(ctx, c, model, d_samples, H_have, L, sp, d_recs, d_coeffs8, d_flags));
-    PITT_TRY(sac_score(ctx, c, model, d_recs, H_have, sp, d_counts));
+    trace_mark("  impl: samples ready + upload issued");
+    if (c->stream_chunks > 0) {
+      // The cloud is still arriving: the sample points are gathered on the host and sent ahead, the hypotheses are
+      // estimated from that copy, and every chunk is scored as soon as it is complete.
+      const size_t ns = (size_t)H_have * S;
+      float4* d_gather = nullptr;
+      int* d_iota = nullptr;
+      PITT_TRY(arena_alloc(ctx, ns, &d_gather));
+      PITT_TRY(arena_alloc(ctx, ns, &d_iota));
+      cudaPointerAttributes attr;
+      const bool mapped = cudaPointerGetAttributes(&attr, c->h_src) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer;
+      if (mapped) {
+        // pinned caller buffer: the GPU fetches the 3 H sample points straight from host memory (zero copy, ~20 us); a
+        // host-side gather of 15 000 random cache misses would delay the first kernel by far more
+        gather_points_kernel<<<cdiv((int)ns, 256), 256, 0, ctx->stream>>>(reinterpret_cast<const float4*>(attr.devicePointer), d_samples,
+                                                                           (int)ns, d_gather, d_iota);
+        PITT_LAUNCH_CHECK(ctx, "gather_points_kernel");
+      } else {
+        cudaGetLastError();  // pageable memory: cudaPointerGetAttributes may have set an error on old drivers
+        PITT_TRY(pinned2_reserve(ctx, ns * 20));
+        float4* hg = reinterpret_cast<float4*>(ctx->h_pin2);
+        int* hi = reinterpret_cast<int*>((char*)ctx->h_pin2 + ns * 16);
+        const float4* src = reinterpret_cast<const float4*>(c->h_src);
+        for (size_t i = 0; i < ns; ++i) { hg[i] = src[h_samples[i]]; hi[i] = (int)i; }
+        PITT_CUDA(ctx, cudaMemcpyAsync(d_gather, ctx->h_pin2, ns * 16, cudaMemcpyHostToDevice, ctx->stream));
+        PITT_CUDA(ctx, cudaMemcpyAsync(d_iota, (char*)ctx->h_pin2 + ns * 16, ns * 4, cudaMemcpyHostToDevice, ctx->stream));
+      }
+      pitt_cloud sample_view;
+      sample_view.n = (int)ns;
+      sample_view.d_xyz = d_gather;
+      PITT_TRY(sac_estimate(ctx, &sample_view, model, d_iota, H_have, L, sp, d_recs, d_coeffs8, d_flags));
+      PITT_TRY(sac_score_plane_streaming(ctx, c, d_recs, H_have, sp, d_counts, d_gather, (int)ns));
+    } else {
+      PITT_TRY(sac_estimate(ctx, c, model, d_samples, H_have, L, sp, d_recs, d_coeffs8, d_flags));
+      PITT_TRY(sac_score(ctx, c, model, d_recs, H_have, sp, d_counts));
+    }
     out->info.hypotheses += H_have;
+    trace_mark("  impl: estimate + score issued");
     if (all_h) {
       PITT_TRY(sac_winner(ctx, d_counts, d_flags, H_have, d_coeffs8, d_best, d_model));
       winner = -2;  // decided on the device
@@ -1513,7 +1586,9 @@ int sac_segment_impl(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& 
   float* h_flt = (float*)((char*)ctx->h_pin + 64);
   PITT_CUDA(ctx, cudaMemcpyAsync(h_ints, d_ints, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   PITT_CUDA(ctx, cudaMemcpyAsync(h_flt, d_flt, 16 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  trace_mark("  impl: finish issued");
   PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  trace_mark("  impl: scalars on the host");
   if (all_h) {
     winner = h_ints[0];
     winner_count = h_ints[1];

@@ -95,3 +95,26 @@ def test_c5_size_plane_slice(ctx, oracle):
     c_cpu = oracle.sac_score(xyz, None, p, samples[pick])[0]
     assert np.array_equal(c_exact[pick], c_cpu)
     cloud.release()
+
+
+def test_segment_host_chunks_a_big_cloud_by_itself(ctx):
+    """20 M points (320 MB): pitt_sac_segment_host copies in 2 chunks on its second stream and scores the first while the
+    second travels; result identical to the staged sequence"""
+    n = 20_000_000
+    xyz = scenes.plane_outlier_cloud(n, seed=77)
+    rng = np.random.default_rng(3)
+    H = 300
+    samples = rng.integers(0, n, (H, 3)).astype(np.int32)
+    p = pkg.default_support_sac_params()
+    p.stop, p.max_iterations, p.sampler = A.STOP_ALL_H, H, A.SAMPLER_REPLAY
+    keep = np.ascontiguousarray(samples)
+    p.replay_samples = keep.ctypes.data_as(A.i32p)
+    p.replay_count = H
+    got = ctx.sac_segment_host(xyz, p)
+    cloud = ctx.stage(xyz)
+    staged = ctx.sac_segment(cloud, p)
+    cloud.release()
+    assert np.array_equal(got["inliers"], staged["inliers"])
+    assert np.array_equal(got["coeffs"].view(np.uint32), staged["coeffs"].view(np.uint32))
+    assert got["info"].best_hypothesis == staged["info"].best_hypothesis and got["info"].best_count == staged["info"].best_count
+    assert len(got["inliers"]) > n // 2

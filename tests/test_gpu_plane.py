@@ -246,3 +246,91 @@ def test_hypothesis_split_finish_matches_single_segment(ctx, oracle):
     assert got["info"].best_count == want["info"].best_count
     assert np.array_equal(got["inliers"], want["inliers"])
     assert np.array_equal(got["coeffs"], want["coeffs"])
+
+
+def _same_result(a, b):
+    assert np.array_equal(a["inliers"], b["inliers"])
+    assert np.array_equal(a["coeffs"].view(np.uint32), b["coeffs"].view(np.uint32))
+    ai, bi = a["info"], b["info"]
+    assert (ai.iterations, ai.skipped, ai.best_hypothesis, ai.best_count, ai.n_inliers_model, ai.hypotheses) == \
+           (bi.iterations, bi.skipped, bi.best_hypothesis, bi.best_count, bi.n_inliers_model, bi.hypotheses)
+
+
+@pytest.fixture
+def chunked(ctx, request):
+    """force the chunked copy of pitt_sac_segment_host (by default only clouds of >= 16 M points are chunked)"""
+    k = getattr(request, "param", 4)
+    ctx.lib.pitt_debug_stream_chunks(k)
+    yield k
+    ctx.lib.pitt_debug_stream_chunks(0)
+
+
+@pytest.mark.parametrize("chunked", [0, 1, 3, 4], indirect=True)
+@pytest.mark.parametrize("n", [1 << 18, (1 << 18) + 777, 300000])
+def test_segment_host_streams_the_cloud_and_matches_pcl(ctx, oracle, n, chunked):
+    """pitt_sac_segment_host (fromROSMsg + seg.segment() fused; the H2D copy in chunks under the scoring) against the staged
+    call and the oracle, with the reference's own parameters (mt19937 sampler, adaptive stop, 10 iterations)"""
+    xyz = scenes.plane_outlier_cloud(n, seed=31)
+    p = pkg.default_support_sac_params()
+    got = ctx.sac_segment_host(xyz, p)
+    cloud = ctx.stage(xyz)
+    staged = ctx.sac_segment(cloud, p)
+    _same_result(got, staged)
+    want = oracle.sac_segment(xyz, None, oracle.default_support_sac_params())
+    assert np.array_equal(got["inliers"], want["inliers"])
+    assert np.array_equal(got["coeffs"], want["coeffs"])
+    assert len(got["inliers"]) > n // 2
+
+
+@pytest.mark.parametrize("plane_mode,H", [(0, 700), (3, 700), (1, 300), (0, 40)])
+def test_segment_host_all_hypotheses_replay(ctx, oracle, plane_mode, H, chunked):
+    """ALL_H over a replayed sample table: exact, tensor-core (forced per chunk) and generic scoring kernels on chunks"""
+    n = 280000
+    xyz = scenes.plane_outlier_cloud(n, seed=32, plane_frac=0.5)
+    samples = oracle.pcl_sample_stream(xyz, A.MODEL_PLANE, H)
+    p = pkg.default_support_sac_params()
+    p.stop, p.max_iterations, p.sampler = A.STOP_ALL_H, H, A.SAMPLER_REPLAY
+    keep = np.ascontiguousarray(samples)
+    p.replay_samples = keep.ctypes.data_as(A.i32p)
+    p.replay_count = H
+    ctx.lib.pitt_debug_plane_mode(plane_mode)
+    try:
+        got = ctx.sac_segment_host(xyz, p)
+    finally:
+        ctx.lib.pitt_debug_plane_mode(0)
+    cloud = ctx.stage(xyz)
+    staged = ctx.sac_segment(cloud, p)
+    _same_result(got, staged)
+    c_cpu, _, _ = oracle.sac_score(xyz, None, p, samples)
+    assert got["info"].best_hypothesis == int(np.argmax(c_cpu)) and got["info"].best_count == int(c_cpu.max())
+
+
+def test_segment_host_on_an_organised_frame(ctx, oracle, chunked):
+    """a Kinect-ordered frame: the four chunks are image stripes with different extents (the tensor path derives its scale
+    per chunk from the chunk and the sample points)"""
+    xyz = scenes.tabletop_frame(seed=3)
+    p = pkg.default_support_sac_params()
+    p.stop, p.max_iterations, p.sampler = A.STOP_ALL_H, 600, A.SAMPLER_PCL_MT19937
+    ctx.lib.pitt_debug_plane_mode(3)
+    try:
+        got = ctx.sac_segment_host(xyz, p)
+    finally:
+        ctx.lib.pitt_debug_plane_mode(0)
+    cloud = ctx.stage(xyz)
+    ctx.lib.pitt_debug_plane_mode(1)
+    try:
+        staged = ctx.sac_segment(cloud, p)
+    finally:
+        ctx.lib.pitt_debug_plane_mode(0)
+    _same_result(got, staged)
+
+
+@pytest.mark.parametrize("n,cols", [(5000, 4), (270000, 3), (0, 4), (2, 4)])
+def test_segment_host_falls_back_to_the_staged_sequence(ctx, oracle, n, cols):
+    """small clouds, point_step 12 and empty inputs take stage + segment + release"""
+    xyz = scenes.plane_outlier_cloud(max(n, 1), seed=33)[:n]
+    p = pkg.default_support_sac_params()
+    got = ctx.sac_segment_host(xyz[:, :cols], p)
+    want = oracle.sac_segment(xyz, None, oracle.default_support_sac_params())
+    assert np.array_equal(got["inliers"], want["inliers"])
+    assert np.array_equal(got["coeffs"], want["coeffs"])

@@ -241,6 +241,21 @@ typedef struct pitt_prefilter_info {
   float used_deep_threshold;
 } pitt_prefilter_info;
 
+/* the arm filter service (segmentation_services/arm_filter_srv.cpp). armFiltering (:66-103) runs a
+ * pcl::CropBox with setNegative(true) per arm link: min/max corner in the link frame (generateBoxVector :105-109, defaults
+ * :32-35), translation = origin of the tf frame (:78-80), rotation = its roll/pitch/yaw (:73, :83-85); the service
+ * chains four of them (left/right forearm, left/right elbow :134-141). The tf look-ups stay with the caller. */
+typedef struct pitt_crop_box {
+  float min_pt[3], max_pt[3];
+  float translation[3];
+  float rotation_rpy[3];
+} pitt_crop_box;
+typedef struct pitt_arm_filter_params {
+  int32_t n_boxes;         /* 0..4; 0 = the service's tfError branch: output = input */
+  int32_t input_is_dense;  /* PointCloud::is_dense of the request: 0 drops non-finite points before the box test */
+  pitt_crop_box box[4];
+} pitt_arm_filter_params;
+
 /* ------------------------------------------------------------------ opaque handles */
 typedef struct pitt_ctx pitt_ctx;
 typedef struct pitt_cloud pitt_cloud; /* cloud staged in HBM as float4 {x,y,z,1} (+ normals float4) */
@@ -268,6 +283,7 @@ void pitt_default_support_params(pitt_support_params* out);        /* all negati
 void pitt_default_cluster_params(pitt_cluster_params* out);
 void pitt_default_frame_params(pitt_frame_params* out);
 void pitt_default_prefilter_params(pitt_prefilter_params* out);    /* leaf 0.01, deep 3.0, identity transform */
+void pitt_default_arm_filter_params(pitt_arm_filter_params* out);  /* 4 boxes with the default corners, identity frames */
 
 /* ------------------------------------------------------------------ staging (K0; replaces fromROSMsg, pc_manager.cpp:85-94) */
 /* xyz: host pointer to n points, x,y,z float32 at byte offsets 0,4,8 of each stride_bytes record
@@ -294,6 +310,10 @@ int pitt_prefilter_cloud(pitt_ctx* ctx, const void* data, int point_step, int n_
 /* the same on a cloud that is already staged (device to device) */
 int pitt_prefilter_staged(pitt_ctx* ctx, const pitt_cloud* in, const pitt_prefilter_params* params,
                           pitt_cloud** out, pitt_prefilter_info* info);
+/* arm filter (CropBox x n_boxes, negative): the points outside every box, in input order. removed[k] (nullable, 4 ints) =
+ * points removed by box k, as the service logs them (arm_filter_srv.cpp:135-141). */
+int pitt_arm_filter(pitt_ctx* ctx, const pitt_cloud* in, const pitt_arm_filter_params* params, pitt_cloud** out,
+                    int32_t* removed);
 /* copy a staged cloud back as n x float4 (tests, debugging) */
 int pitt_get_points(pitt_ctx* ctx, const pitt_cloud* cloud, float* out4);
 

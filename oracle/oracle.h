@@ -49,6 +49,9 @@ int orc_segment_frame(const float* xyz4, int n, const pitt_frame_params* params,
 int orc_prefilter(const void* data, int point_step, int n_points, const pitt_prefilter_params* p, float* out4, int cap,
                   int* n_out, pitt_prefilter_info* info);
 
+/* arm filter: chained negative CropBoxes (arm_filter_srv.cpp:66-103, 134-141); removed = 4 ints, nullable */
+int orc_arm_filter(const float* xyz4, int n, const pitt_arm_filter_params* p, float* out4, int cap, int* n_out, int* removed);
+
 /* defaults shared with the product header semantics (reference launch parameters) */
 void orc_default_sac_params(int model, pitt_sac_params* out);
 void orc_default_support_sac_params(pitt_sac_params* out);

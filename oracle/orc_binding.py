@@ -249,3 +249,15 @@ def prefilter(raw, params):
                              C.byref(n_out), C.byref(info))
     assert st == 0, st
     return out[: n_out.value].copy(), {k: getattr(info, k) for k, _ in A.PrefilterInfo._fields_}
+
+
+def arm_filter(xyz4, params):
+    """orc_arm_filter: chained negative CropBoxes; returns (kept cloud n x 4, removed per box)"""
+    xyz4 = np.ascontiguousarray(xyz4, np.float32)
+    n = xyz4.shape[0]
+    out = np.zeros((max(n, 1), 4), np.float32)
+    n_out = C.c_int(0)
+    removed = (C.c_int * 4)()
+    st = lib().orc_arm_filter(_fp(xyz4), n, C.byref(params), _fp(out), max(n, 1), C.byref(n_out), removed)
+    assert st == 0, st
+    return out[: n_out.value].copy(), list(removed)

@@ -144,3 +144,81 @@ extern "C" int orc_prefilter(const void* data, int point_step, int n_points, con
   }
   return PITT_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Arm filter: segmentation_services/arm_filter_srv.cpp. armFiltering (:66-103) = one pcl::CropBox with
+// setMin/setMax (corners in the link frame), setTranslation (tf origin :78-80), setRotation (roll, pitch, yaw of the tf
+// rotation :73, :83-85), setTransform(identity), setNegative(true); filter() chains four of them, each on the previous
+// output (:134-141). PCL 1.7.2 filters/impl/crop_box.hpp, restated (PARITY UNPINNED, like the rest of the oracle):
+//   transform = getTransformation(0, 0, 0, roll, pitch, yaw) and inverse_transform = transform.inverse() when the
+//   rotation is not zero; per point: skipped when the cloud is not dense and the point is not finite; local = point;
+//   local -= translation when the translation is not zero; local = inverse_transform * local when it is not the identity;
+//   "outside" = any coordinate below min or above max; negative => the outside points are kept, in order. The output of
+//   a CropBox is marked dense, so only the first box of the chain looks at finiteness.
+// Pinned choices: cosf/sinf = the double function rounded once; Eigen's Affine inverse of a rotation = the 3x3 cofactor
+// inverse (compute_inverse_size3: det from the first column, (a + b) + c); matrix * vector = (m0 x + m1 y) + m2 z.
+namespace {
+struct Box {
+  bool rot, tr;
+  float inv[3][3];
+  float t[3], mn[3], mx[3];
+};
+void rotation_inverse(const float rpy[3], float inv[3][3]) {
+  const float roll = rpy[0], pitch = rpy[1], yaw = rpy[2];
+  const float A = (float)std::cos((double)yaw), B = (float)std::sin((double)yaw);
+  const float C = (float)std::cos((double)pitch), D = (float)std::sin((double)pitch);
+  const float E = (float)std::cos((double)roll), F = (float)std::sin((double)roll);
+  const float DE = D * E, DF = D * F;
+  const float t[3][3] = {{A * C, A * DF - B * E, B * F + A * DE}, {B * C, A * E + B * DF, B * DE - A * F}, {-D, C * F, C * E}};
+  float cofactor[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      const int ia = (i + 1) % 3, ib = (i + 2) % 3, ja = (j + 1) % 3, jb = (j + 2) % 3;
+      cofactor[i][j] = t[ia][ja] * t[ib][jb] - t[ia][jb] * t[ib][ja];
+    }
+  const float det = (cofactor[0][0] * t[0][0] + cofactor[1][0] * t[1][0]) + cofactor[2][0] * t[2][0];
+  const float invdet = 1.0f / det;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) inv[r][c] = cofactor[c][r] * invdet;
+}
+}  // namespace
+
+extern "C" int orc_arm_filter(const float* xyz4, int n, const pitt_arm_filter_params* p, float* out4, int cap, int* n_out,
+                              int* removed) {
+  if (!p || p->n_boxes < 0 || p->n_boxes > 4 || !n_out) return PITT_ERR_INVALID;
+  std::vector<P3> cur((size_t)std::max(n, 0));
+  for (int i = 0; i < n; ++i) cur[i] = {xyz4[4 * i], xyz4[4 * i + 1], xyz4[4 * i + 2]};
+  bool dense = p->input_is_dense != 0;
+  for (int k = 0; k < p->n_boxes; ++k) {
+    const pitt_crop_box& b = p->box[k];
+    Box B;
+    B.rot = !(b.rotation_rpy[0] == 0.0f && b.rotation_rpy[1] == 0.0f && b.rotation_rpy[2] == 0.0f);
+    B.tr = !(b.translation[0] == 0.0f && b.translation[1] == 0.0f && b.translation[2] == 0.0f);
+    if (B.rot) rotation_inverse(b.rotation_rpy, B.inv);
+    std::vector<P3> kept;
+    for (const P3& q : cur) {
+      if (!dense && !(std::isfinite(q.x) && std::isfinite(q.y) && std::isfinite(q.z))) continue;
+      P3 l = q;
+      if (B.tr) { l.x -= b.translation[0]; l.y -= b.translation[1]; l.z -= b.translation[2]; }
+      if (B.rot) {
+        const float x = l.x, y = l.y, z = l.z;
+        l.x = (B.inv[0][0] * x + B.inv[0][1] * y) + B.inv[0][2] * z;
+        l.y = (B.inv[1][0] * x + B.inv[1][1] * y) + B.inv[1][2] * z;
+        l.z = (B.inv[2][0] * x + B.inv[2][1] * y) + B.inv[2][2] * z;
+      }
+      const bool outside = (l.x < b.min_pt[0] || l.y < b.min_pt[1] || l.z < b.min_pt[2]) ||
+                           (l.x > b.max_pt[0] || l.y > b.max_pt[1] || l.z > b.max_pt[2]);
+      if (outside) kept.push_back(q);
+    }
+    if (removed) removed[k] = (int)(cur.size() - kept.size());
+    cur.swap(kept);
+    dense = true;  // CropBox marks its output dense
+  }
+  if (removed) for (int k = p->n_boxes; k < 4; ++k) removed[k] = 0;
+  *n_out = (int)cur.size();
+  if ((int)cur.size() > cap) return PITT_ERR_CAPACITY;
+  for (size_t i = 0; i < cur.size(); ++i) {
+    out4[4 * i] = cur[i].x; out4[4 * i + 1] = cur[i].y; out4[4 * i + 2] = cur[i].z; out4[4 * i + 3] = 1.0f;
+  }
+  return PITT_OK;
+}

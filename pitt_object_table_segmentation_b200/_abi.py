@@ -50,6 +50,14 @@ class SupportParams(C.Structure):
     ]
 
 
+class CropBox(C.Structure):
+    _fields_ = [("min_pt", f32 * 3), ("max_pt", f32 * 3), ("translation", f32 * 3), ("rotation_rpy", f32 * 3)]
+
+
+class ArmFilterParams(C.Structure):
+    _fields_ = [("n_boxes", i32), ("input_is_dense", i32), ("box", CropBox * 4)]
+
+
 class Support(C.Structure):
     _fields_ = [
         ("n_map", i32), ("n_support", i32), ("n_on_support", i32),

@@ -18,7 +18,7 @@ _LIB = None
 EXPORTED_SYMBOLS = [
     "pitt_create", "pitt_create_on_stream", "pitt_destroy", "pitt_last_error", "pitt_version", "pitt_device_count",
     "pitt_synchronize", "pitt_set_workers", "pitt_default_prefilter_params", "pitt_prefilter_cloud",
-    "pitt_prefilter_staged", "pitt_get_points", "pitt_segment_raw_frames_batched", "pitt_default_sac_params", "pitt_default_support_sac_params", "pitt_default_support_params",
+    "pitt_prefilter_staged", "pitt_default_arm_filter_params", "pitt_arm_filter", "pitt_get_points", "pitt_segment_raw_frames_batched", "pitt_default_sac_params", "pitt_default_support_sac_params", "pitt_default_support_params",
     "pitt_default_cluster_params", "pitt_default_frame_params", "pitt_stage_cloud", "pitt_stage_cloud_device",
     "pitt_set_normals", "pitt_cloud_size", "pitt_cloud_has_normals", "pitt_cloud_device_points",
     "pitt_cloud_device_normals", "pitt_release_cloud", "pitt_estimate_normals", "pitt_get_normals", "pitt_knn",
@@ -57,6 +57,8 @@ def load_library():
                                          C.POINTER(A.PrefilterInfo)]
     lib.pitt_prefilter_staged.argtypes = [vp, vp, C.POINTER(A.PrefilterParams), C.POINTER(vp), C.POINTER(A.PrefilterInfo)]
     lib.pitt_get_points.argtypes = [vp, vp, A.f32p]
+    lib.pitt_default_arm_filter_params.argtypes = [C.POINTER(A.ArmFilterParams)]
+    lib.pitt_arm_filter.argtypes = [vp, vp, C.POINTER(A.ArmFilterParams), C.POINTER(vp), A.i32p]
     lib.pitt_stage_cloud.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(vp)]
     lib.pitt_stage_cloud_device.argtypes = [vp, vp, C.c_int, C.POINTER(vp)]
     lib.pitt_set_normals.argtypes = [vp, vp, vp, C.c_int]
@@ -243,6 +245,13 @@ class Context:
         n = self.lib.pitt_cloud_size(h)
         return Cloud(self, h, n), {k: getattr(info, k) for k, _ in A.PrefilterInfo._fields_}
 
+    def arm_filter(self, cloud, params):
+        """pitt_arm_filter: chained negative CropBoxes (arm_filter_srv.cpp:66-103). Returns (Cloud, removed per box)."""
+        h = C.c_void_p()
+        removed = (C.c_int32 * 4)()
+        self._check(self.lib.pitt_arm_filter(self.handle, cloud.handle, C.byref(params), C.byref(h), removed))
+        return Cloud(self, h, self.lib.pitt_cloud_size(h)), list(removed)
+
     def get_points(self, cloud):
         out = np.zeros((cloud.n, 4), np.float32)
         self._check(self.lib.pitt_get_points(self.handle, cloud.handle, out.ctypes.data_as(A.f32p)))
@@ -413,6 +422,12 @@ Context.find_supports = _find_supports
 Context.cluster_service = _cluster_service
 Context.primitive_service = _primitive_service
 Context.segment_frame = _segment_frame
+
+
+def default_arm_filter_params():
+    p = A.ArmFilterParams()
+    load_library().pitt_default_arm_filter_params(C.byref(p))
+    return p
 
 
 def default_prefilter_params():

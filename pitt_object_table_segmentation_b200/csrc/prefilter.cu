@@ -110,6 +110,72 @@ __global__ void __launch_bounds__(256) compact_transform_kernel(const float4* __
   dst[pos[i]] = p;
 }
 
+// ---- arm filter: pcl::CropBox (negative) per box, chained (arm_filter_srv.cpp:66-103, 134-141)
+struct CropDev {
+  float inv[9];  // inverse of the rotation (row major); identity when apply_rot == 0
+  float t[3];
+  float mn[3], mx[3];
+  int apply_rot, apply_t;
+};
+struct CropSet {
+  CropDev b[4];
+  int n, dense;
+};
+// which box removes the point: 0 = none (kept), k + 1 = box k (the first one in the chain that contains it), 5 = dropped as
+// non-finite by the first CropBox
+__global__ void __launch_bounds__(256) crop_flag_kernel(const float4* __restrict__ xyz, int n, CropSet S, int* __restrict__ keep,
+                                                        int* __restrict__ removed /*[5]*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int who = 0;
+  if (i < n) {
+    const float4 p = xyz[i];
+    if (!S.dense && !(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) {
+      who = 5;
+    } else {
+      for (int k = 0; k < S.n && who == 0; ++k) {
+        const CropDev& B = S.b[k];
+        float x = p.x, y = p.y, z = p.z;
+        if (B.apply_t) { x -= B.t[0]; y -= B.t[1]; z -= B.t[2]; }
+        if (B.apply_rot) {  // Eigen 3x3 * vector, coefficient based: (m0 x + m1 y) + m2 z, unfused
+          const float lx = (B.inv[0] * x + B.inv[1] * y) + B.inv[2] * z;
+          const float ly = (B.inv[3] * x + B.inv[4] * y) + B.inv[5] * z;
+          const float lz = (B.inv[6] * x + B.inv[7] * y) + B.inv[8] * z;
+          x = lx; y = ly; z = lz;
+        }
+        const bool outside = (x < B.mn[0] || y < B.mn[1] || z < B.mn[2]) || (x > B.mx[0] || y > B.mx[1] || z > B.mx[2]);
+        if (!outside) who = k + 1;  // NaN compares false everywhere: "inside", removed (negative filter)
+      }
+    }
+    keep[i] = who == 0 ? 1 : 0;
+  }
+#pragma unroll
+  for (int k = 1; k <= 5; ++k) {
+    const unsigned m = __ballot_sync(0xffffffffu, who == k);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&removed[k - 1], __popc(m));
+  }
+}
+// pcl::getTransformation(0, 0, 0, roll, pitch, yaw) followed by Eigen's Affine3f::inverse() (3x3 cofactor inverse); float,
+// cos/sin = the double function rounded once (the convention of pitt_math.cuh for PCL's float transcendentals)
+static void crop_inverse_rotation(const float rpy[3], float inv[9]) {
+  const float A = (float)cos((double)rpy[2]), B = (float)sin((double)rpy[2]), C = (float)cos((double)rpy[1]),
+              D = (float)sin((double)rpy[1]), E = (float)cos((double)rpy[0]), F = (float)sin((double)rpy[0]);
+  const float DE = D * E, DF = D * F;
+  float m[3][3];
+  m[0][0] = A * C;  m[0][1] = A * DF - B * E;  m[0][2] = B * F + A * DE;
+  m[1][0] = B * C;  m[1][1] = A * E + B * DF;  m[1][2] = B * DE - A * F;
+  m[2][0] = -D;     m[2][1] = C * F;           m[2][2] = C * E;
+  auto cof = [&](int i, int j) {
+    const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    return m[i1][j1] * m[i2][j2] - m[i1][j2] * m[i2][j1];
+  };
+  const float c0 = cof(0, 0), c1 = cof(1, 0), c2 = cof(2, 0);
+  const float det = (c0 * m[0][0] + c1 * m[1][0]) + c2 * m[2][0];
+  const float invdet = 1.0f / det;
+  inv[0] = c0 * invdet; inv[1] = c1 * invdet; inv[2] = c2 * invdet;
+  for (int i = 1; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) inv[3 * i + j] = cof(j, i) * invdet;
+}
+
 // d_in: n float4 on the device. Writes a new pool-allocated cloud.
 static int prefilter_impl(pitt_ctx* ctx, const float4* d_in, int n, const pitt_prefilter_params& P, pitt_cloud** out,
                           pitt_prefilter_info* info) {
@@ -273,6 +339,79 @@ int pitt_prefilter_staged(pitt_ctx* ctx, const pitt_cloud* in, const pitt_prefil
   int st = prefilter_impl(ctx, in->d_xyz, in->n, *params, out, info);
   timer.finish();
   return st;
+}
+
+void pitt_default_arm_filter_params(pitt_arm_filter_params* p) {
+  memset(p, 0, sizeof(*p));
+  p->n_boxes = 4;
+  const float mn_f[3] = {-0.040f, -0.120f, -0.190f}, mx_f[3] = {0.340f, 0.120f, 0.105f};   // arm_filter_srv.cpp:32-33
+  const float mn_e[3] = {-0.090f, -0.135f, -0.160f}, mx_e[3] = {0.440f, 0.135f, 0.110f};   // :34-35
+  for (int k = 0; k < 4; ++k)
+    for (int a = 0; a < 3; ++a) {
+      p->box[k].min_pt[a] = k < 2 ? mn_f[a] : mn_e[a];  // left forearm, right forearm, left elbow, right elbow (:134-141)
+      p->box[k].max_pt[a] = k < 2 ? mx_f[a] : mx_e[a];
+    }
+}
+
+int pitt_arm_filter(pitt_ctx* ctx, const pitt_cloud* in, const pitt_arm_filter_params* P, pitt_cloud** out, int32_t* removed) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!in || !P || !out || P->n_boxes < 0 || P->n_boxes > 4) return fail(ctx, PITT_ERR_INVALID, "pitt_arm_filter arguments");
+  cudaSetDevice(ctx->device);
+  CallTimer timer(ctx);
+  CropSet S;
+  memset(&S, 0, sizeof(S));
+  S.n = P->n_boxes;
+  S.dense = P->input_is_dense ? 1 : 0;
+  for (int k = 0; k < S.n; ++k) {
+    const pitt_crop_box& b = P->box[k];
+    CropDev& d = S.b[k];
+    d.apply_rot = (b.rotation_rpy[0] != 0.0f || b.rotation_rpy[1] != 0.0f || b.rotation_rpy[2] != 0.0f) ? 1 : 0;
+    d.apply_t = (b.translation[0] != 0.0f || b.translation[1] != 0.0f || b.translation[2] != 0.0f) ? 1 : 0;
+    if (d.apply_rot) crop_inverse_rotation(b.rotation_rpy, d.inv);
+    for (int a = 0; a < 3; ++a) { d.t[a] = b.translation[a]; d.mn[a] = b.min_pt[a]; d.mx[a] = b.max_pt[a]; }
+  }
+  pitt_cloud* c = new pitt_cloud();
+  const int n = in->n;
+  int h_rem[5] = {0, 0, 0, 0, 0};
+  int n_out = 0;
+  if (n > 0 && S.n == 0) {  // tfError branch: no operation performed
+    n_out = n;
+    if (pool_alloc(ctx, (size_t)n * sizeof(float4), (void**)&c->d_xyz) != PITT_OK) { delete c; return PITT_ERR_CUDA; }
+    PITT_CUDA(ctx, cudaMemcpyAsync(c->d_xyz, in->d_xyz, (size_t)n * 16, cudaMemcpyDeviceToDevice, ctx->stream));
+  } else if (n > 0) {
+    int *d_keep = nullptr, *d_pos = nullptr, *d_cnt = nullptr;
+    PITT_TRY(arena_alloc(ctx, (size_t)n, &d_keep));
+    PITT_TRY(arena_alloc(ctx, (size_t)n, &d_pos));
+    PITT_TRY(arena_alloc(ctx, 8, &d_cnt));
+    PITT_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, 8 * sizeof(int), ctx->stream));
+    crop_flag_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(in->d_xyz, n, S, d_keep, d_cnt + 1);
+    ctx->launches++;
+    PITT_CUDA(ctx, cudaMemcpyAsync(d_pos, d_keep, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    PITT_TRY(device_exclusive_scan(ctx, d_pos, n, d_cnt));
+    int h_cnt[6];
+    PITT_CUDA(ctx, cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, ctx->stream));
+    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    n_out = h_cnt[0];
+    for (int k = 0; k < 5; ++k) h_rem[k] = h_cnt[1 + k];
+    if (n_out > 0) {
+      if (pool_alloc(ctx, (size_t)n_out * sizeof(float4), (void**)&c->d_xyz) != PITT_OK) { delete c; return PITT_ERR_CUDA; }
+      Xform T;
+      memset(&T, 0, sizeof(T));
+      compact_transform_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(in->d_xyz, d_keep, d_pos, n, T, c->d_xyz);
+      ctx->launches++;
+    }
+  }
+  c->n = n_out;
+  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { pool_free(ctx, c->d_xyz, (size_t)c->n * sizeof(float4)); delete c; return fail(ctx, PITT_ERR_CUDA, "arm filter kernels", e); }
+  timer.finish();
+  if (removed) {
+    for (int k = 0; k < 4; ++k) removed[k] = h_rem[k];
+    removed[0] += h_rem[4];  // non-finite points leave with the first CropBox of the chain
+  }
+  *out = c;
+  return PITT_OK;
 }
 
 int pitt_get_points(pitt_ctx* ctx, const pitt_cloud* c, float* out4) {

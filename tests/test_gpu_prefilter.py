@@ -79,3 +79,79 @@ def test_raw_frame_stream_matches_manual_pipeline(ctx, oracle):
             assert (a["tag"], a["n_points"], a["inliers"]) == (b["tag"], b["n_points"], b["inliers"])
             assert np.array_equal(np.asarray(a["coefficients"], np.float32).view(np.uint32),
                                   np.asarray(b["coefficients"], np.float32).view(np.uint32))
+
+
+def _arm_params(rng, n_boxes=4, dense=0, rotate=True, translate=True, centre=(0.0, 0.0, 1.0)):
+    p = pkg.default_arm_filter_params()
+    p.n_boxes = n_boxes
+    p.input_is_dense = dense
+    for k in range(4):
+        for a in range(3):
+            p.box[k].translation[a] = float(centre[a] + rng.uniform(-0.3, 0.3)) if translate else 0.0
+            p.box[k].rotation_rpy[a] = float(rng.uniform(-3.0, 3.0)) if rotate else 0.0
+    return p
+
+
+@pytest.mark.parametrize("n_boxes,dense,rotate,translate", [(4, 0, True, True), (4, 1, True, True), (1, 0, False, True),
+                                                            (2, 0, True, False), (3, 1, False, False), (0, 0, True, True)])
+def test_arm_filter_matches_oracle(ctx, oracle, n_boxes, dense, rotate, translate):
+    """chained negative CropBoxes of the arm filter service (arm_filter_srv.cpp:66-103, 134-141)"""
+    rng = np.random.default_rng(100 + n_boxes * 8 + dense * 4 + rotate * 2 + translate)
+    raw = scenes.raw_camera_frame(seed=9, width=320, height=240, point_step=16)  # camera frame, NaN returns included
+    xyz = np.ones((len(raw), 4), np.float32)
+    xyz[:, :3] = raw[:, :3]
+    xyz[::97, 0] = np.inf  # a few infinite coordinates as well
+    p = _arm_params(rng, n_boxes, dense, rotate, translate)
+    # make the boxes big enough to bite into the scene
+    for k in range(4):
+        for a in range(3):
+            p.box[k].min_pt[a] *= 3.0
+            p.box[k].max_pt[a] *= 3.0
+    cloud = ctx.stage(xyz)
+    out, removed = ctx.arm_filter(cloud, p)
+    got = ctx.get_points(out)
+    want, wremoved = oracle.arm_filter(xyz, p)
+    assert removed == wremoved
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    if n_boxes == 0:
+        assert len(got) == len(xyz)
+    else:
+        assert 0 < len(got) < len(xyz) and sum(removed) == len(xyz) - len(got)
+
+
+def test_arm_filter_points_on_the_box_faces(ctx, oracle):
+    """points exactly on a face are inside (the comparisons are strict), one ulp further they are outside"""
+    rng = np.random.default_rng(7)
+    p = pkg.default_arm_filter_params()
+    p.n_boxes = 1
+    p.input_is_dense = 1
+    lo = np.array(p.box[0].min_pt[:], np.float32)
+    hi = np.array(p.box[0].max_pt[:], np.float32)
+    pts = rng.uniform(lo, hi, (6000, 3)).astype(np.float32)
+    face = rng.integers(0, 6, len(pts))
+    for f in range(6):
+        sel = face == f
+        a = f % 3
+        v = lo[a] if f < 3 else hi[a]
+        pts[sel, a] = v
+    nudged = pts.copy()
+    for f in range(6):
+        sel = (face == f) & (rng.random(len(pts)) < 0.5)
+        a = f % 3
+        nudged[sel, a] = np.nextafter(pts[sel, a], np.float32(-np.inf if f < 3 else np.inf))
+    xyz = np.ones((len(pts), 4), np.float32)
+    xyz[:, :3] = nudged
+    cloud = ctx.stage(xyz)
+    out, removed = ctx.arm_filter(cloud, p)
+    got = ctx.get_points(out)
+    want, wremoved = oracle.arm_filter(xyz, p)
+    assert removed == wremoved and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert 0.3 * len(pts) < len(got) < 0.7 * len(pts)
+
+
+def test_arm_filter_empty_cloud(ctx, oracle):
+    p = pkg.default_arm_filter_params()
+    cloud = ctx.stage(np.zeros((0, 4), np.float32))
+    out, removed = ctx.arm_filter(cloud, p)
+    assert out.n == 0 and removed == [0, 0, 0, 0]

@@ -216,16 +216,17 @@ def test_struct_layouts_match_header(built):
     """sizeof of the ctypes mirrors == sizeof in C (compiled with gcc against the header)."""
     import subprocess
     import tempfile
-    src = '#include <stdio.h>\n#include "pitt_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
+    src = '#include <stdio.h>\n#include "pitt_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
           'sizeof(pitt_sac_params),sizeof(pitt_sac_info),sizeof(pitt_support_params),sizeof(pitt_support),' \
           'sizeof(pitt_support_result),sizeof(pitt_cluster_params),sizeof(pitt_cluster),sizeof(pitt_clusters_result),' \
-          'sizeof(pitt_primitive_result),sizeof(pitt_tracked_shape),sizeof(pitt_frame_params));return 0;}\n'
+          'sizeof(pitt_primitive_result),sizeof(pitt_tracked_shape),sizeof(pitt_frame_params),sizeof(pitt_crop_box),' \
+          'sizeof(pitt_arm_filter_params));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
         out = subprocess.check_output([os.path.join(d, "t")]).split()
     mirrors = [A.SacParams, A.SacInfo, A.SupportParams, A.Support, A.SupportResult, A.ClusterParams, A.Cluster,
-               A.ClustersResult, A.PrimitiveResult, A.TrackedShape, A.FrameParams]
+               A.ClustersResult, A.PrimitiveResult, A.TrackedShape, A.FrameParams, A.CropBox, A.ArmFilterParams]
     assert [int(v) for v in out] == [C.sizeof(m) for m in mirrors]
 
 
@@ -289,6 +290,53 @@ def test_oracle_prefilter_against_numpy_restatement(oracle):
     assert np.all(out[:, 3] == 1.0)
     # the table is back at z = 0 in the world frame
     assert abs(np.median(out[:, 2])) < 0.01
+
+
+def test_oracle_arm_filter_against_numpy_restatement(oracle):
+    """chained negative CropBoxes (arm_filter_srv.cpp:66-103) vs a float64 numpy restatement with scipy-free rotation
+    matrices: same kept set for every point that is not within 1e-5 of a box face; order preserved; NaN points dropped"""
+    import pitt_object_table_segmentation_b200 as pkg
+    rng = np.random.default_rng(11)
+    n = 20000
+    xyz = np.ones((n, 4), np.float32)
+    xyz[:, :3] = rng.uniform(-1.0, 1.0, (n, 3)).astype(np.float32)
+    xyz[::50, 1] = np.nan
+    p = pkg.default_arm_filter_params()
+    p.n_boxes = 4
+    p.input_is_dense = 0
+    for k in range(4):
+        for a in range(3):
+            p.box[k].translation[a] = float(rng.uniform(-0.4, 0.4))
+            p.box[k].rotation_rpy[a] = float(rng.uniform(-3.0, 3.0))
+    out, removed = oracle.arm_filter(xyz, p)
+    P = xyz[:, :3].astype(np.float64)
+    keep = np.isfinite(P).all(1)
+    near_face = np.zeros(n, bool)
+    for k in range(4):
+        r, pi_, y = [float(v) for v in p.box[k].rotation_rpy[:]]
+        Rx = np.array([[1, 0, 0], [0, np.cos(r), -np.sin(r)], [0, np.sin(r), np.cos(r)]])
+        Ry = np.array([[np.cos(pi_), 0, np.sin(pi_)], [0, 1, 0], [-np.sin(pi_), 0, np.cos(pi_)]])
+        Rz = np.array([[np.cos(y), -np.sin(y), 0], [np.sin(y), np.cos(y), 0], [0, 0, 1]])
+        R = Rz @ Ry @ Rx  # pcl::getTransformation: yaw * pitch * roll
+        local = (np.nan_to_num(P) - np.array(p.box[k].translation[:], np.float64)) @ R  # R^T applied to column vectors
+        lo, hi = np.array(p.box[k].min_pt[:], np.float64), np.array(p.box[k].max_pt[:], np.float64)
+        inside = ((local >= lo) & (local <= hi)).all(1)
+        near_face |= (np.abs(local - lo) < 1e-5).any(1) | (np.abs(local - hi) < 1e-5).any(1)
+        keep &= ~inside
+    assert removed[0] >= int((~np.isfinite(P).all(1)).sum())
+    assert sum(removed) == n - len(out)
+    # order preserved and same set away from the faces
+    kept_idx = np.nonzero(keep)[0]
+    got_set = {tuple(v) for v in out[:, :3].view(np.uint32)}
+    sure = kept_idx[~near_face[kept_idx]]
+    assert all(tuple(v) in got_set for v in xyz[sure, :3].view(np.uint32))
+    sure_removed = np.nonzero(~keep & ~near_face & np.isfinite(P).all(1))[0]
+    assert not any(tuple(v) in got_set for v in xyz[sure_removed, :3].view(np.uint32))
+    assert 0.02 * n < n - len(out) < 0.9 * n
+    # ascending original index
+    pos = {tuple(v): i for i, v in enumerate(xyz[:, :3].view(np.uint32))}
+    idx = [pos[tuple(v)] for v in out[:, :3].view(np.uint32)]
+    assert idx == sorted(idx)
 
 
 def test_ros_shims_compile_against_the_c_abi():

@@ -74,6 +74,8 @@ void pitt_destroy(pitt_ctx* ctx) {
   if (ctx->d_arena) cudaFree(ctx->d_arena);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   if (ctx->h_pin2) cudaFreeHost(ctx->h_pin2);
+  if (ctx->h_one) cudaFreeHost(ctx->h_one);
+  if (ctx->d_ready) cudaFree(ctx->d_ready);
   for (cudaEvent_t e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
   if (ctx->ev_copy_gate) cudaEventDestroy(ctx->ev_copy_gate);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -347,11 +349,19 @@ int pitt_sac_segment_host(pitt_ctx* ctx, const void* xyz, int stride_bytes, int 
     g_stream_chunks = v ? std::max(1, std::min(8, atoi(v))) : 0;
   }
   const int K_env = g_stream_chunks;
-  const int K_equal = K_env > 0 ? K_env : std::max(1, std::min(8, n / (8 << 20)));
+  // Large scoring jobs take the tensor path: ONE launch whose CTAs poll per-chunk arrival flags (8 chunks; a chunk costs
+  // nothing but a 4-byte flag copy there), so only the first chunk's copy is exposed.
+  const int H_first = p->stop == PITT_STOP_ALL_H ? p->max_iterations : p->max_iterations + 1;
+  const bool single_launch = K_env == 0 && plane_job_takes_tensor_path(n, H_first) &&
+                             (p->sampler != PITT_SAMPLER_REPLAY || p->replay_count >= H_first);
+  const int K_equal = single_launch ? 8 : (K_env > 0 ? K_env : std::max(1, std::min(8, n / (8 << 20))));
   if (!ctx->copy_stream) {
     PITT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     for (int k = 0; k < 8; ++k) PITT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_chunk[k], cudaEventDisableTiming));
     PITT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy_gate, cudaEventDisableTiming));
+    PITT_CUDA(ctx, cudaMalloc((void**)&ctx->d_ready, 16 * sizeof(int)));
+    PITT_CUDA(ctx, cudaMallocHost((void**)&ctx->h_one, sizeof(int)));
+    *ctx->h_one = 1;
   }
   trace_mark("segment_host: enter");
   CallTimer timer(ctx);
@@ -371,10 +381,16 @@ int pitt_sac_segment_host(pitt_ctx* ctx, const void* xyz, int stride_bytes, int 
   // the buffer may have been used by earlier work of this context's stream
   cudaEventRecord(ctx->ev_copy_gate, ctx->stream);
   cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy_gate, 0);
+  if (single_launch) {
+    cudaMemsetAsync(ctx->d_ready, 0, 16 * sizeof(int), ctx->copy_stream);
+    c->d_ready = ctx->d_ready;
+  }
   for (int k = 0; k < c->stream_chunks; ++k) {
     const size_t off = (size_t)c->stream_off[k];
     const size_t cnt = (size_t)c->stream_off[k + 1] - off;
     cudaError_t e = cudaMemcpyAsync(c->d_xyz + off, (const char*)xyz + off * 16, cnt * 16, cudaMemcpyHostToDevice, ctx->copy_stream);
+    if (e == cudaSuccess && single_launch)  // the flag travels behind its chunk on the same stream
+      e = cudaMemcpyAsync(ctx->d_ready + k, ctx->h_one, sizeof(int), cudaMemcpyHostToDevice, ctx->copy_stream);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_chunk[k], ctx->copy_stream);
     if (e != cudaSuccess) {
       cudaStreamSynchronize(ctx->copy_stream);

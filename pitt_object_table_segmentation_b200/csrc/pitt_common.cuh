@@ -46,6 +46,8 @@ struct pitt_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_copy_gate = nullptr;
+  int* d_ready = nullptr;   // 16 arrival flags (device) and the pinned word they are raised from
+  int* h_one = nullptr;
   void* h_pin2 = nullptr;  // pinned block for the gathered sample points (h_pin holds the sample indices at that time)
   size_t h_pin2_bytes = 0;
 };
@@ -62,6 +64,7 @@ struct pitt_cloud {
   mutable int stream_chunks = 0;
   int stream_off[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // chunk k = points [stream_off[k], stream_off[k + 1])
   const float* h_src = nullptr;
+  const int* d_ready = nullptr;  // per-chunk arrival flags for the single-launch tensor path (equal chunks of stream_off[1] points)
 };
 
 namespace pitt {

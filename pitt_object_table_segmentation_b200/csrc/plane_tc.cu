@@ -225,6 +225,23 @@ __global__ void tc_params_kernel(const unsigned* __restrict__ absmax, float thr_
   *out = P;
 }
 
+// Streaming cloud: the coordinate maxima come from the sample points alone and are doubled; tc_verify_kernel checks after
+// the run that no point exceeded them (and that nothing was non-finite or timed out). When the check fails the counts
+// are cleared and *ok = 0 sends the job to the exact kernel.
+__global__ void tc_widen_kernel(unsigned* __restrict__ absmax) {
+  if (threadIdx.x < 3) {
+    const float v = __uint_as_float(absmax[threadIdx.x]);
+    absmax[threadIdx.x] = __float_as_uint(v * 2.0f);  // inf / NaN stay what they are: the tensor path is then not used at all
+  }
+}
+__global__ void tc_verify_kernel(const unsigned* __restrict__ assumed, const unsigned* __restrict__ seen, const PlaneTcParams* __restrict__ Pp,
+                                 int* __restrict__ counts, int H, int* __restrict__ ok_out) {
+  const bool ok = Pp->use && seen[0] <= assumed[0] && seen[1] <= assumed[1] && seen[2] <= assumed[2] && seen[3] == 0u;
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (!ok && h < H) counts[h] = 0;
+  if (h == 0) *ok_out = ok ? 1 : 0;
+}
+
 // K-slot assignment of the two MMAs (hypothesis piece, point piece); the point side mirrors it in tc_point_image.
 //   MMA 0 (small terms): (a1,x3) (a2,x2) (a3,x1) (a2,x3) (a3,x2) (b1,y3) (b2,y2) (b3,y1) |
 //                        (b2,y3) (b3,y2) (c1,z3) (c2,z2) (c3,z1) (c2,z3) (c3,z2) (d3,1)
@@ -351,7 +368,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict__ recs, int H, const uint4* __restrict__ image,
                 int n_hb /*hypothesis blocks*/, int n_chunks, int n_items, float thr_up, const PlaneTcParams* __restrict__ Pp,
                 int* __restrict__ counts, unsigned long long* __restrict__ stats /*nullable: [0] segments, [1] re-evaluated*/,
-                float* __restrict__ dbg /*DBG: s~ of hypothesis block 0 x points 0..255 of item 0 (128 x 256)*/, int variant /*DBG*/) {
+                float* __restrict__ dbg /*DBG: s~ of hypothesis block 0 x points 0..255 of item 0 (128 x 256)*/, int variant /*DBG*/,
+                const int* ready /*nullable: streaming cloud, ready[k] != 0 once points [k ready_pts, (k+1) ready_pts) have landed*/,
+                int ready_pts, unsigned* __restrict__ seen /*streaming: [0..2] |x|,|y|,|z| maxima of the points read, [3] time-out*/) {
   extern __shared__ __align__(128) unsigned char smem[];
   const PlaneTcParams P = *Pp;
   if (!P.use) return;  // plane_score_kernel (launched right after) does the work
@@ -488,7 +507,30 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
         const int pi = threadIdx.x;  // point of the chunk (TC_CHUNK == TC_EPI_THREADS)
         const int gi = base + pi;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gi < n) p = __ldg(xyz + gi);
+        if (ready) {
+          // The cloud is still arriving from the host (pitt_sac_segment_host): the copy stream raises ready[k] after chunk k.
+          // One lane polls (acquire, so the points read below are the copied ones); a time-out flags the run as invalid
+          // instead of hanging the GPU (the host then rescoring on the complete cloud).
+          if (lane == 0) {
+            const int* f = ready + base / ready_pts;
+            int v, spins = 0;
+            for (;;) {
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+              if (v) break;
+              __nanosleep(200);
+              if (++spins > (1 << 23)) { atomicExch(seen + 3, 1u); break; }
+            }
+          }
+          __syncwarp();
+          if (gi < n) p = __ldcg(xyz + gi);
+          // the scale was derived from the sample points only: record what the cloud really contains
+          unsigned mx = __reduce_max_sync(0xffffffffu, __float_as_uint(p.x) & 0x7fffffffu);
+          unsigned my = __reduce_max_sync(0xffffffffu, __float_as_uint(p.y) & 0x7fffffffu);
+          unsigned mz = __reduce_max_sync(0xffffffffu, __float_as_uint(p.z) & 0x7fffffffu);
+          if (lane == 0) { atomicMax(seen + 0, mx); atomicMax(seen + 1, my); atomicMax(seen + 2, mz); }
+        } else if (gi < n) {
+          p = __ldg(xyz + gi);
+        }
         s_raw[pi] = p;
         tc_point_image(reinterpret_cast<uint4*>(smem + TC_OFF_B + (pi / TC_N) * TC_B_TILE_BYTES), pi % TC_N, p);
       }
@@ -621,7 +663,7 @@ std::vector<float> g_plane_tc_dump_host;  // 128 x 256 accumulators + sigma, C
 // d_extra (nullable): further points every hypothesis may pass through (the sample points when c is only a chunk of the
 // cloud): they enter the coordinate bounds the scale is derived from.
 int launch_score_plane_tc(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_recs, int H, const ScoreParams& sp, int* d_counts,
-                          const int** d_use_out, const float4* d_extra, int n_extra) {
+                          const int** d_use_out, const float4* d_extra, int n_extra, const int* d_ready, int ready_pts) {
   const int n = c->n;
   const int n_hb = cdiv(H, TC_M);
   const int n_chunks = cdiv(n, TC_CHUNK);
@@ -638,14 +680,27 @@ int launch_score_plane_tc(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_re
   PITT_TRY(arena_alloc(ctx, 2 + 160 + 16, &d_stats));
   PITT_TRY(arena_alloc(ctx, (size_t)n_hb * (TC_A_BLOCK_BYTES / 16), &d_image));
   if (g_plane_tc_dump) PITT_TRY(arena_alloc(ctx, (size_t)TC_M * 256, &d_dbg));
+  const bool streaming = d_ready != nullptr;  // one launch over a cloud that is still being copied
+  if (streaming && !(d_extra && n_extra > 0)) return fail(ctx, PITT_ERR_INVALID, "streaming tensor path needs the sample points");
+  unsigned* d_seen = nullptr;
+  int* d_ok = nullptr;
+  PITT_TRY(arena_alloc(ctx, 4, &d_seen));
+  PITT_TRY(arena_alloc(ctx, 1, &d_ok));
+  PITT_CUDA(ctx, cudaMemsetAsync(d_seen, 0, 4 * sizeof(unsigned), ctx->stream));
   PITT_CUDA(ctx, cudaMemsetAsync(d_scr, 0, 4 * sizeof(unsigned), ctx->stream));
   PITT_CUDA(ctx, cudaMemsetAsync(d_stats, 0, (2 + 160 + 16) * sizeof(unsigned long long), ctx->stream));
-  int ab = std::min(cdiv(n, 256 * 8), ctx->sm_count * 8);
-  tc_absmax_kernel<<<ab, 256, 0, ctx->stream>>>(c->d_xyz, n, d_scr);
-  TC_LAUNCH_CHECK(ctx, "tc_absmax_kernel");
+  if (!streaming) {
+    int ab = std::min(cdiv(n, 256 * 8), ctx->sm_count * 8);
+    tc_absmax_kernel<<<ab, 256, 0, ctx->stream>>>(c->d_xyz, n, d_scr);
+    TC_LAUNCH_CHECK(ctx, "tc_absmax_kernel");
+  }
   if (d_extra && n_extra > 0) {
     tc_absmax_kernel<<<std::min(cdiv(n_extra, 256 * 8), ctx->sm_count * 8), 256, 0, ctx->stream>>>(d_extra, n_extra, d_scr);
     TC_LAUNCH_CHECK(ctx, "tc_absmax_kernel");
+  }
+  if (streaming) {
+    tc_widen_kernel<<<1, 32, 0, ctx->stream>>>(d_scr);
+    TC_LAUNCH_CHECK(ctx, "tc_widen_kernel");
   }
   tc_params_kernel<<<1, 1, 0, ctx->stream>>>(d_scr, sp.thr_up, g_plane_tc_acc_ulps, d_P);
   TC_LAUNCH_CHECK(ctx, "tc_params_kernel");
@@ -663,12 +718,18 @@ int launch_score_plane_tc(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_re
       attr_set = true;                                                                                                          \
     }                                                                                                                           \
     plane_tc_kernel<DBGK><<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(                                                    \
-        c->d_xyz, n, d_recs, H, d_image, n_hb, n_chunks, (int)items, sp.thr_up, d_P, d_counts, st, d_dbg, g_plane_tc_variant);  \
+        c->d_xyz, n, d_recs, H, d_image, n_hb, n_chunks, (int)items, sp.thr_up, d_P, d_counts, st, d_dbg, g_plane_tc_variant,  \
+        d_ready, ready_pts, d_seen);                                                                                            \
   } while (0)
   if (dbgk) TC_LAUNCH(true); else TC_LAUNCH(false);
 #undef TC_LAUNCH
   TC_LAUNCH_CHECK(ctx, "plane_tc_kernel");
   *d_use_out = &d_P->use;
+  if (streaming) {
+    tc_verify_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(d_scr, d_seen, d_P, d_counts, H, d_ok);
+    TC_LAUNCH_CHECK(ctx, "tc_verify_kernel");
+    *d_use_out = d_ok;
+  }
   if (g_plane_tc_collect_stats || g_plane_tc_dump) {
     if (g_plane_tc_collect_stats)
       PITT_CUDA(ctx, cudaMemcpyAsync(g_plane_tc_stats, d_stats, sizeof(g_plane_tc_stats), cudaMemcpyDeviceToHost, ctx->stream));

@@ -959,16 +959,26 @@ static int launch_score_generic(pitt_ctx* ctx, const pitt_cloud* c, const HypRec
   return PITT_OK;
 }
 
+int g_force_generic_plane = 0;  // test hook: 1 routes plane scoring through the generic kernel
 int g_score_mode = 0;  // test hook: 0 two-tier kernel for cylinder/cone, 1 generic score_kernel for every model
 int g_plane_mode = 0;  // test hook: 0 automatic (tensor path on large jobs), 1 exact packed kernel only,
                        // 2 FFMA filter + exact re-evaluation always, 3 tensor-core path (plane_tc.cu) always
 int launch_score_plane_tc(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_recs, int H, const ScoreParams& sp, int* d_counts,
-                          const int** d_use_out, const float4* d_extra, int n_extra);
+                          const int** d_use_out, const float4* d_extra, int n_extra, const int* d_ready, int ready_pts);
 unsigned long long g_plane_filter_stats[2] = {0, 0};  // last call with stats enabled: pairs, re-evaluated pairs
 int g_plane_filter_collect_stats = 0;
 
+// tensor path on large jobs? (shared with pitt_sac_segment_host, which plans its copy accordingly)
+bool plane_job_takes_tensor_path(int n, int H) {
+  return H >= 256 && !g_force_generic_plane &&
+         ((g_plane_mode == 3) || (g_plane_mode == 0 && (double)n * (double)H >= 134217728.0));
+}
+
+// d_ready != NULL: c is the WHOLE cloud, still arriving; the tensor kernel polls the flags, every other kernel here waits
+// for ev_all (the last chunk) first.
 static int launch_score_plane_packed(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_recs, int H, const ScoreParams& sp,
-                                     int* d_counts, const float4* d_extra = nullptr, int n_extra = 0) {
+                                     int* d_counts, const float4* d_extra = nullptr, int n_extra = 0, const int* d_ready = nullptr,
+                                     int ready_pts = 0, cudaEvent_t ev_all = nullptr) {
   constexpr int KH = 8, TPB = 128, TILE = 512;
   const int n = c->n;
   const int hblocks = cdiv(H, KH * TPB);
@@ -990,7 +1000,9 @@ static int launch_score_plane_packed(pitt_ctx* ctx, const pitt_cloud* c, const H
   const bool tensor = (g_plane_mode == 3) || (g_plane_mode == 0 && (double)n * (double)H >= 134217728.0);
   const bool filter = (g_plane_mode == 2);
   const int* d_skip = nullptr;  // device flag: non-zero = a fast kernel did the work, the exact kernel returns at once
-  if (tensor) PITT_TRY(launch_score_plane_tc(ctx, c, d_recs, H, sp, d_counts, &d_skip, d_extra, n_extra));
+  if (d_ready && !tensor) return fail(ctx, PITT_ERR_STATE, "streaming scoring needs the tensor path");
+  if (tensor) PITT_TRY(launch_score_plane_tc(ctx, c, d_recs, H, sp, d_counts, &d_skip, d_extra, n_extra, d_ready, ready_pts));
+  if (d_ready) PITT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_all, 0));  // the exact kernel (fallback) reads the whole cloud
   if (filter) {
     if (d_extra) return fail(ctx, PITT_ERR_STATE, "plane filter mode does not take a chunked cloud");
     d_skip = &d_P->use_filter;
@@ -1030,7 +1042,15 @@ static int launch_score_plane_packed(pitt_ctx* ctx, const pitt_cloud* c, const H
   return PITT_OK;
 }
 
-int g_force_generic_plane = 0;  // test hook: 1 routes plane scoring through the generic kernel
+
+// a consumer that needs the whole cloud at once
+static int stream_complete(pitt_ctx* ctx, const pitt_cloud* c) {
+  for (int k = 0; k < c->stream_chunks; ++k) PITT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[k], 0));
+  c->stream_chunks = 0;
+  return PITT_OK;
+}
+
+int sac_score(pitt_ctx* ctx, const pitt_cloud* c, int model, const HypRec* d_recs, int H, const ScoreParams& sp, int* d_counts);
 
 // Plane scoring of a cloud that is still arriving (pitt_sac_segment_host): chunk k is scored as soon as its copy has
 // completed, while the copy engine brings in chunk k + 1. Counts add up over the chunks. d_gather = the sample points
@@ -1038,6 +1058,20 @@ int g_force_generic_plane = 0;  // test hook: 1 routes plane scoring through the
 int sac_score_plane_streaming(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_recs, int H, const ScoreParams& sp, int* d_counts,
                               const float4* d_gather, int n_gather) {
   PITT_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (size_t)H * sizeof(int), ctx->stream));
+  if (c->d_ready && !plane_job_takes_tensor_path(c->n, H)) {  // fewer hypotheses than planned: wait for the cloud, score normally
+    PITT_TRY(stream_complete(ctx, c));
+    return sac_score(ctx, c, PITT_MODEL_PLANE, d_recs, H, sp, d_counts);
+  }
+  if (c->d_ready) {
+    // one launch: the persistent tensor kernel consumes the chunks as their flags come up
+    pitt_cloud view;
+    view.n = c->n;
+    view.d_xyz = c->d_xyz;
+    PITT_TRY(launch_score_plane_packed(ctx, &view, d_recs, H, sp, d_counts, d_gather, n_gather, c->d_ready, c->stream_off[1],
+                                       ctx->ev_chunk[c->stream_chunks - 1]));
+    c->stream_chunks = 0;
+    return PITT_OK;
+  }
   for (int k = 0; k < c->stream_chunks; ++k) {
     PITT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[k], 0));
     const int off = c->stream_off[k];
@@ -1052,12 +1086,6 @@ int sac_score_plane_streaming(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* 
   return PITT_OK;
 }
 
-// a consumer that needs the whole cloud at once
-static int stream_complete(pitt_ctx* ctx, const pitt_cloud* c) {
-  for (int k = 0; k < c->stream_chunks; ++k) PITT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[k], 0));
-  c->stream_chunks = 0;
-  return PITT_OK;
-}
 
 int sac_score(pitt_ctx* ctx, const pitt_cloud* c, int model, const HypRec* d_recs, int H, const ScoreParams& sp,
               int* d_counts) {

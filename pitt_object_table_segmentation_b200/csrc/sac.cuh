@@ -51,6 +51,7 @@ int fp32_peak(pitt_ctx* ctx, int kind, double* tflops);
 
 extern int g_force_generic_plane;
 extern int g_plane_mode;
+bool plane_job_takes_tensor_path(int n, int H);
 extern int g_score_mode;
 extern unsigned long long g_plane_filter_stats[2];
 extern int g_plane_filter_collect_stats;

@@ -282,6 +282,7 @@ def test_segment_host_streams_the_cloud_and_matches_pcl(ctx, oracle, n, chunked)
     assert len(got["inliers"]) > n // 2
 
 
+@pytest.mark.parametrize("chunked", [0, 4], indirect=True)
 @pytest.mark.parametrize("plane_mode,H", [(0, 700), (3, 700), (1, 300), (0, 40)])
 def test_segment_host_all_hypotheses_replay(ctx, oracle, plane_mode, H, chunked):
     """ALL_H over a replayed sample table: exact, tensor-core (forced per chunk) and generic scoring kernels on chunks"""
@@ -305,6 +306,7 @@ def test_segment_host_all_hypotheses_replay(ctx, oracle, plane_mode, H, chunked)
     assert got["info"].best_hypothesis == int(np.argmax(c_cpu)) and got["info"].best_count == int(c_cpu.max())
 
 
+@pytest.mark.parametrize("chunked", [0, 4], indirect=True)
 def test_segment_host_on_an_organised_frame(ctx, oracle, chunked):
     """a Kinect-ordered frame: the four chunks are image stripes with different extents (the tensor path derives its scale
     per chunk from the chunk and the sample points)"""
@@ -334,3 +336,38 @@ def test_segment_host_falls_back_to_the_staged_sequence(ctx, oracle, n, cols):
     want = oracle.sac_segment(xyz, None, oracle.default_support_sac_params())
     assert np.array_equal(got["inliers"], want["inliers"])
     assert np.array_equal(got["coeffs"], want["coeffs"])
+
+
+@pytest.mark.parametrize("spoil", ["far_points", "nan_points", "inf_points"])
+def test_segment_host_single_launch_bounds_check(ctx, oracle, spoil):
+    """single-launch streaming derives the tensor path's scale from the sample points (doubled) and verifies afterwards that
+    no point of the cloud exceeded it: points far outside, NaN and inf coordinates that are not among the samples must send
+    the job to the exact kernel and change nothing in the result"""
+    n, H = 300000, 700
+    xyz = scenes.plane_outlier_cloud(n, seed=35)
+    rng = np.random.default_rng(4)
+    samples = rng.integers(0, n - 100, (H, 3)).astype(np.int32)  # the last 100 points are never sampled
+    samples[:, 1] = (samples[:, 0] + 1 + rng.integers(0, n - 200, H)) % (n - 100)
+    samples[:, 2] = (samples[:, 1] + 7) % (n - 100)
+    if spoil == "far_points":
+        xyz[-50:, :3] *= np.float32(500.0)
+    elif spoil == "nan_points":
+        xyz[-50:, 1] = np.nan
+    else:
+        xyz[-50:, 2] = np.inf
+    p = pkg.default_support_sac_params()
+    p.stop, p.max_iterations, p.sampler = A.STOP_ALL_H, H, A.SAMPLER_REPLAY
+    keep = np.ascontiguousarray(samples)
+    p.replay_samples = keep.ctypes.data_as(A.i32p)
+    p.replay_count = H
+    got = ctx.sac_segment_host(xyz, p)
+    cloud = ctx.stage(xyz)
+    ctx.lib.pitt_debug_plane_mode(1)
+    try:
+        staged = ctx.sac_segment(cloud, p)
+    finally:
+        ctx.lib.pitt_debug_plane_mode(0)
+    _same_result(got, staged)
+    c_cpu, _, _ = oracle.sac_score(xyz, None, p, samples[:40])
+    c_gpu, _, _ = ctx.sac_score(cloud, p, samples[:40])
+    assert np.array_equal(c_cpu, c_gpu)

@@ -172,7 +172,19 @@ __device__ __forceinline__ uint4 tc_bf8(float f0, float f1, float f2, float f3, 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) tc_absmax_kernel(const float4* __restrict__ xyz, int n, unsigned* __restrict__ out3) {
   unsigned mx = 0, my = 0, mz = 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  const int stride = gridDim.x * blockDim.x;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // four independent loads in flight per thread: the kernel is a pure HBM/L2 read of the cloud
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    const float4 p0 = __ldg(xyz + i), p1 = __ldg(xyz + i + stride), p2 = __ldg(xyz + i + 2 * stride), p3 = __ldg(xyz + i + 3 * stride);
+    mx = max(max(mx, __float_as_uint(p0.x) & 0x7fffffffu), max(__float_as_uint(p1.x) & 0x7fffffffu,
+             max(__float_as_uint(p2.x) & 0x7fffffffu, __float_as_uint(p3.x) & 0x7fffffffu)));
+    my = max(max(my, __float_as_uint(p0.y) & 0x7fffffffu), max(__float_as_uint(p1.y) & 0x7fffffffu,
+             max(__float_as_uint(p2.y) & 0x7fffffffu, __float_as_uint(p3.y) & 0x7fffffffu)));
+    mz = max(max(mz, __float_as_uint(p0.z) & 0x7fffffffu), max(__float_as_uint(p1.z) & 0x7fffffffu,
+             max(__float_as_uint(p2.z) & 0x7fffffffu, __float_as_uint(p3.z) & 0x7fffffffu)));
+  }
+  for (; i < n; i += stride) {
     float4 p = __ldg(xyz + i);
     mx = max(mx, __float_as_uint(p.x) & 0x7fffffffu);
     my = max(my, __float_as_uint(p.y) & 0x7fffffffu);
@@ -690,7 +702,7 @@ int launch_score_plane_tc(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_re
   PITT_CUDA(ctx, cudaMemsetAsync(d_scr, 0, 4 * sizeof(unsigned), ctx->stream));
   PITT_CUDA(ctx, cudaMemsetAsync(d_stats, 0, (2 + 160 + 16) * sizeof(unsigned long long), ctx->stream));
   if (!streaming) {
-    int ab = std::min(cdiv(n, 256 * 8), ctx->sm_count * 8);
+    int ab = std::min(cdiv(n, 256 * 4), ctx->sm_count * 8);
     tc_absmax_kernel<<<ab, 256, 0, ctx->stream>>>(c->d_xyz, n, d_scr);
     TC_LAUNCH_CHECK(ctx, "tc_absmax_kernel");
   }

@@ -793,9 +793,14 @@ plane_sums_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restric
 __global__ void plane_refine_final_kernel(const double* __restrict__ partial, int blocks, const float* __restrict__ model,
                                           float* __restrict__ refined, int* __restrict__ n_model_inliers) {
   __shared__ double s[10];
+  __shared__ double s_part[REF_BLOCKS * 10];
+  // all threads fetch the partial sums at once (one L2 round trip instead of `blocks` dependent ones); the additions keep
+  // their order (block 0, 1, 2, ...), so the sums are bit-identical to the sequential loop
+  for (int i = threadIdx.x; i < blocks * 10; i += blockDim.x) s_part[i] = partial[i];
+  __syncthreads();
   if (threadIdx.x < 10) {
     double t = 0.0;
-    for (int b = 0; b < blocks; ++b) t += partial[(size_t)b * 10 + threadIdx.x];
+    for (int b = 0; b < blocks; ++b) t += s_part[b * 10 + threadIdx.x];
     s[threadIdx.x] = t;
   }
   __syncthreads();
@@ -1169,7 +1174,7 @@ int plane_refine(pitt_ctx* ctx, const pitt_cloud* c, const float* d_model, const
   }
   plane_sums_kernel<<<REF_BLOCKS, REF_TPB, 0, ctx->stream>>>(c->d_xyz, c->n, d_rec, d_idx, d_n_idx, sp, d_partial);
   PITT_LAUNCH_CHECK(ctx, "plane_sums_kernel");
-  plane_refine_final_kernel<<<1, 32, 0, ctx->stream>>>(d_partial, REF_BLOCKS, d_model, d_refined, d_n_model_inliers);
+  plane_refine_final_kernel<<<1, 256, 0, ctx->stream>>>(d_partial, REF_BLOCKS, d_model, d_refined, d_n_model_inliers);
   PITT_LAUNCH_CHECK(ctx, "plane_refine_final_kernel");
   return PITT_OK;
 }

@@ -17,7 +17,7 @@ _LIB = None
 # every symbol declared in include/pitt_b200.h
 EXPORTED_SYMBOLS = [
     "pitt_create", "pitt_create_on_stream", "pitt_destroy", "pitt_last_error", "pitt_version", "pitt_device_count",
-    "pitt_synchronize", "pitt_set_workers", "pitt_default_prefilter_params", "pitt_prefilter_cloud",
+    "pitt_synchronize", "pitt_set_blocking_sync", "pitt_set_workers", "pitt_default_prefilter_params", "pitt_prefilter_cloud",
     "pitt_prefilter_staged", "pitt_default_arm_filter_params", "pitt_arm_filter", "pitt_get_points", "pitt_segment_raw_frames_batched", "pitt_default_sac_params", "pitt_default_support_sac_params", "pitt_default_support_params",
     "pitt_default_cluster_params", "pitt_default_frame_params", "pitt_stage_cloud", "pitt_stage_cloud_device",
     "pitt_set_normals", "pitt_cloud_size", "pitt_cloud_has_normals", "pitt_cloud_device_points",
@@ -53,6 +53,7 @@ def load_library():
     lib.pitt_version.restype = C.c_char_p
     lib.pitt_synchronize.argtypes = [vp]
     lib.pitt_set_workers.argtypes = [vp, C.c_int]
+    lib.pitt_set_blocking_sync.argtypes = [vp, C.c_int]
     lib.pitt_prefilter_cloud.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(A.PrefilterParams), C.POINTER(vp),
                                          C.POINTER(A.PrefilterInfo)]
     lib.pitt_prefilter_staged.argtypes = [vp, vp, C.POINTER(A.PrefilterParams), C.POINTER(vp), C.POINTER(A.PrefilterInfo)]
@@ -244,6 +245,9 @@ class Context:
                                                   C.byref(params), C.byref(h), C.byref(info)))
         n = self.lib.pitt_cloud_size(h)
         return Cloud(self, h, n), {k: getattr(info, k) for k, _ in A.PrefilterInfo._fields_}
+
+    def set_blocking_sync(self, enable=True):
+        self._check(self.lib.pitt_set_blocking_sync(self.handle, 1 if enable else 0))
 
     def arm_filter(self, cloud, params):
         """pitt_arm_filter: chained negative CropBoxes (arm_filter_srv.cpp:66-103). Returns (Cloud, removed per box)."""

@@ -144,12 +144,12 @@ int euclidean_clusters_impl(pitt_ctx* ctx, const float4* d_xyz, int n, double to
     cc_roots_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_parent, d_size, n, std::max(min_size, 1), max_size, d_nroots, d_roots, cap);
     ctx->launches += 3;
     PITT_CUDA(ctx, cudaMemcpyAsync(&h_nroots, d_nroots, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PITT_CUDA(ctx, pitt::stream_sync(ctx));
     h_nroots = std::min(h_nroots, cap);
     roots.resize(h_nroots);
     if (h_nroots > 0) {
       PITT_CUDA(ctx, cudaMemcpyAsync(roots.data(), d_roots, (size_t)h_nroots * sizeof(int2), cudaMemcpyDeviceToHost, ctx->stream));
-      PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      PITT_CUDA(ctx, pitt::stream_sync(ctx));
       // PCL order: size descending; equal sizes by smallest point index (the root)
       std::sort(roots.begin(), roots.end(), [](const int2& a, const int2& b) { return a.y != b.y ? a.y > b.y : a.x < b.x; });
       PITT_CUDA(ctx, cudaMemcpyAsync(d_roots, roots.data(), (size_t)h_nroots * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream));
@@ -182,7 +182,7 @@ extern "C" int pitt_euclidean_clusters(pitt_ctx* ctx, const pitt_cloud* c, doubl
     std::vector<int> sizes;
     PITT_TRY(euclidean_clusters_impl(ctx, c->d_xyz, c->n, tolerance, min_size, max_size, d_labels, &sizes));
     PITT_CUDA(ctx, cudaMemcpyAsync(labels, d_labels, (size_t)c->n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PITT_CUDA(ctx, pitt::stream_sync(ctx));
     *n_clusters = (int)sizes.size();
   }
   timer.finish();

@@ -227,7 +227,7 @@ int cloud_bbox(pitt_ctx* ctx, const float4* d_xyz, int n, float mn[3], float mx[
   ctx->launches += 2;
   int h_bb[8];
   PITT_CUDA(ctx, cudaMemcpyAsync(h_bb, d_bb, 7 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PITT_CUDA(ctx, pitt::stream_sync(ctx));
   *n_finite = h_bb[6];
   for (int a = 0; a < 3; ++a) { mn[a] = ord2f_host(h_bb[a]); mx[a] = ord2f_host(h_bb[3 + a]); }
   return PITT_OK;
@@ -257,7 +257,7 @@ int grid_build(pitt_ctx* ctx, const float4* d_xyz, int n, float h, float target_
     ctx->launches += 2;
     int m0 = 0;
     PITT_CUDA(ctx, cudaMemcpyAsync(&m0, d_cnt + ncells + 1, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PITT_CUDA(ctx, pitt::stream_sync(ctx));
     if (m0 < 1) m0 = 1;
     h = h0 * sqrtf(target_per_cell * (float)m0 / (float)n_finite);
     h = std::max(h, ext * 1e-5f);

@@ -428,7 +428,7 @@ int pitt_estimate_normals(pitt_ctx* ctx, pitt_cloud* c, int k, const float viewp
   if (c->n > 0) {
     if (!c->d_nrm) PITT_TRY(pool_alloc(ctx, (size_t)c->n * sizeof(float4), (void**)&c->d_nrm));
     PITT_TRY(estimate_normals_impl(ctx, c->d_xyz, c->n, k, viewpoint, c->d_nrm));
-    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PITT_CUDA(ctx, pitt::stream_sync(ctx));
   }
   c->has_normals = true;
   timer.finish();
@@ -463,7 +463,7 @@ int pitt_knn(pitt_ctx* ctx, const pitt_cloud* c, int k, int32_t* out_idx, float*
     }
     PITT_CUDA(ctx, cudaMemcpyAsync(out_idx, d_idx, tot * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (out_sqdist) PITT_CUDA(ctx, cudaMemcpyAsync(out_sqdist, d_sq, tot * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PITT_CUDA(ctx, pitt::stream_sync(ctx));
   }
   timer.finish();
   return PITT_OK;

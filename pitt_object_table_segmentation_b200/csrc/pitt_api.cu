@@ -53,6 +53,10 @@ static pitt_ctx* create_impl(int device, uint64_t seed, void* stream, bool own) 
   }
   cudaEventCreate(&ctx->ev0);
   cudaEventCreate(&ctx->ev1);
+  {
+    const char* v = getenv("PITT_BLOCKING_SYNC");
+    if (v && v[0] == '1') cudaEventCreateWithFlags(&ctx->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
+  }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
   return ctx;
@@ -68,7 +72,7 @@ void pitt_destroy(pitt_ctx* ctx) {
   cudaSetDevice(ctx->device);
   workers_destroy(ctx);
   if (ctx->ev_fan) cudaEventDestroy(ctx->ev_fan);
-  cudaStreamSynchronize(ctx->stream);
+  pitt::stream_sync(ctx);
   for (void* p : ctx->d_overflow) cudaFree(p);
   for (auto& b : ctx->cloud_pool) cudaFree(b.p);
   if (ctx->d_arena) cudaFree(ctx->d_arena);
@@ -79,6 +83,7 @@ void pitt_destroy(pitt_ctx* ctx) {
   for (cudaEvent_t e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
   if (ctx->ev_copy_gate) cudaEventDestroy(ctx->ev_copy_gate);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -97,9 +102,20 @@ int pitt_set_workers(pitt_ctx* ctx, int n_workers) {
   }
   return PITT_OK;
 }
+int pitt_set_blocking_sync(pitt_ctx* ctx, int enable) {
+  if (!ctx) return PITT_ERR_CUDA;
+  cudaSetDevice(ctx->device);
+  if (enable && !ctx->ev_block) {
+    PITT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
+  } else if (!enable && ctx->ev_block) {
+    cudaEventDestroy(ctx->ev_block);
+    ctx->ev_block = nullptr;
+  }
+  return PITT_OK;
+}
 int pitt_synchronize(pitt_ctx* ctx) {
   if (!ctx) return PITT_ERR_CUDA;
-  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PITT_CUDA(ctx, pitt::stream_sync(ctx));
   return PITT_OK;
 }
 
@@ -212,7 +228,7 @@ int pitt_stage_cloud(pitt_ctx* ctx, const void* xyz, int stride_bytes, int n, pi
       pack_xyz_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_raw, stride_bytes, n, c->d_xyz);
       ctx->launches++;
     }
-    e = cudaStreamSynchronize(ctx->stream);  // the caller's buffer is only borrowed for the call
+    e = pitt::stream_sync(ctx);  // the caller's buffer is only borrowed for the call
     if (e != cudaSuccess) { cudaFree(c->d_xyz); delete c; return fail(ctx, PITT_ERR_CUDA, "stage sync", e); }
   }
   timer.finish();
@@ -252,7 +268,7 @@ int pitt_set_normals(pitt_ctx* ctx, pitt_cloud* c, const void* normals, int stri
       pack_normals_kernel<<<cdiv(c->n, 256), 256, 0, ctx->stream>>>(d_raw, stride_bytes, 4, c->n, c->d_nrm);
       ctx->launches++;
     }
-    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PITT_CUDA(ctx, pitt::stream_sync(ctx));
   }
   c->has_normals = true;
   timer.finish();
@@ -268,7 +284,7 @@ void pitt_release_cloud(pitt_ctx* ctx, pitt_cloud* c) {
   if (!c) return;
   if (ctx) {
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    pitt::stream_sync(ctx);
   }
   pool_free(ctx, c->d_xyz, (size_t)c->n * sizeof(float4));
   pool_free(ctx, c->d_nrm, (size_t)c->n * sizeof(float4));
@@ -282,7 +298,7 @@ int pitt_get_normals(pitt_ctx* ctx, const pitt_cloud* c, float* out4) {
   cudaSetDevice(ctx->device);
   if (c->n > 0) {
     PITT_CUDA(ctx, cudaMemcpyAsync(out4, c->d_nrm, (size_t)c->n * 16, cudaMemcpyDeviceToHost, ctx->stream));
-    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PITT_CUDA(ctx, pitt::stream_sync(ctx));
   }
   return PITT_OK;
 }
@@ -307,7 +323,7 @@ int pitt_sac_segment(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params* 
       status = fail(ctx, PITT_ERR_CAPACITY, "inlier buffer too small");
     } else {
       PITT_CUDA(ctx, cudaMemcpyAsync(inliers, r.d_inliers, (size_t)r.n_inliers * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-      PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      PITT_CUDA(ctx, pitt::stream_sync(ctx));
     }
   }
   timer.finish();
@@ -419,7 +435,7 @@ int pitt_sac_segment_host(pitt_ctx* ctx, const void* xyz, int stride_bytes, int 
   }
   // the caller's buffer is only borrowed for the call: every copy has left it (early returns of the segmentation included)
   cudaStreamSynchronize(ctx->copy_stream);
-  cudaStreamSynchronize(ctx->stream);
+  pitt::stream_sync(ctx);
   trace_mark("segment_host: inliers on the host");
   c->stream_chunks = 0;
   timer.finish();
@@ -471,7 +487,7 @@ int pitt_sac_score(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params* p,
     flags.resize(H);
     PITT_CUDA(ctx, cudaMemcpyAsync(flags.data(), d_flags, (size_t)H, cudaMemcpyDeviceToHost, ctx->stream));
   }
-  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PITT_CUDA(ctx, pitt::stream_sync(ctx));
   if (valid)
     for (int h = 0; h < H; ++h) valid[h] = flags[h] & 1;
   timer.finish();
@@ -510,7 +526,7 @@ int pitt_sac_finish_device(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_pa
     if (cap < r.n_inliers) status = fail(ctx, PITT_ERR_CAPACITY, "inlier buffer too small");
     else {
       PITT_CUDA(ctx, cudaMemcpyAsync(inliers, r.d_inliers, (size_t)r.n_inliers * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-      PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      PITT_CUDA(ctx, pitt::stream_sync(ctx));
     }
   }
   timer.finish();
@@ -544,14 +560,14 @@ int pitt_sac_select(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params* p
   PITT_TRY(sac_select(ctx, c, p->model, d_co, L, sp, d_out, d_total));
   int total = 0;
   PITT_CUDA(ctx, cudaMemcpyAsync(&total, d_total, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PITT_CUDA(ctx, pitt::stream_sync(ctx));
   *n_inliers = total;
   int status = PITT_OK;
   if (total > 0) {
     if (!inliers || cap < total) status = fail(ctx, PITT_ERR_CAPACITY, "inlier buffer too small");
     else {
       PITT_CUDA(ctx, cudaMemcpyAsync(inliers, d_out, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-      PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      PITT_CUDA(ctx, pitt::stream_sync(ctx));
     }
   }
   timer.finish();
@@ -589,7 +605,7 @@ int pitt_sac_refine(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params* p
   float h_ref[8];
   PITT_CUDA(ctx, cudaMemcpyAsync(h_ref, d_ref, sizeof(h_ref), cudaMemcpyDeviceToHost, ctx->stream));
   PITT_CUDA(ctx, cudaMemcpyAsync(h_ints, d_ints, sizeof(h_ints), cudaMemcpyDeviceToHost, ctx->stream));
-  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PITT_CUDA(ctx, pitt::stream_sync(ctx));
   for (int i = 0; i < NC; ++i) refined[i] = h_ref[i];
   timer.finish();
   if (info) {

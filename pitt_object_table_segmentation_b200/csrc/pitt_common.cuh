@@ -46,6 +46,9 @@ struct pitt_ctx {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_copy_gate = nullptr;
+  // PITT_BLOCKING_SYNC=1: host waits sleep on an event (cudaEventBlockingSync) instead of spinning; for frame streams
+  // with more host threads than cores (16 contexts x 8 ranks on one box)
+  cudaEvent_t ev_block = nullptr;
   int* d_ready = nullptr;   // 16 arrival flags (device) and the pinned word they are raised from
   int* h_one = nullptr;
   void* h_pin2 = nullptr;  // pinned block for the gathered sample points (h_pin holds the sample indices at that time)
@@ -68,6 +71,14 @@ struct pitt_cloud {
 };
 
 namespace pitt {
+
+// every host wait on the context's stream goes through here
+inline cudaError_t stream_sync(pitt_ctx* ctx) {
+  if (!ctx->ev_block) return cudaStreamSynchronize(ctx->stream);
+  cudaError_t e = cudaEventRecord(ctx->ev_block, ctx->stream);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(ctx->ev_block);
+}
 
 inline int fail(pitt_ctx* ctx, int code, const char* what, cudaError_t e = cudaSuccess) {
   if (ctx) {
@@ -96,7 +107,7 @@ inline int fail(pitt_ctx* ctx, int code, const char* what, cudaError_t e = cudaS
 inline void arena_reset(pitt_ctx* ctx) {
   // blocks that did not fit last time are released and the arena grown to last call's total
   if (!ctx->d_overflow.empty() || ctx->d_call_total > ctx->d_arena_bytes) {
-    cudaStreamSynchronize(ctx->stream);
+    pitt::stream_sync(ctx);
     for (void* p : ctx->d_overflow) cudaFree(p);
     ctx->d_overflow.clear();
     if (ctx->d_call_total > ctx->d_arena_bytes) {
@@ -130,7 +141,7 @@ inline int arena_alloc(pitt_ctx* ctx, size_t count, T** out) {
 }
 inline int pinned_reserve(pitt_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->h_pin_bytes) return PITT_OK;
-  cudaStreamSynchronize(ctx->stream);
+  pitt::stream_sync(ctx);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   ctx->h_pin = nullptr;
   ctx->h_pin_bytes = 0;
@@ -143,7 +154,7 @@ inline int pinned_reserve(pitt_ctx* ctx, size_t bytes) {
 
 inline int pinned2_reserve(pitt_ctx* ctx, size_t bytes) {
   if (bytes <= ctx->h_pin2_bytes) return PITT_OK;
-  cudaStreamSynchronize(ctx->stream);
+  pitt::stream_sync(ctx);
   if (ctx->h_pin2) cudaFreeHost(ctx->h_pin2);
   ctx->h_pin2 = nullptr;
   ctx->h_pin2_bytes = 0;
@@ -184,7 +195,7 @@ inline int ensure_host_mirror(pitt_ctx* ctx, const pitt_cloud* cc) {
   c->h_xyz.resize((size_t)c->n * 4);
   if (c->n > 0) {
     PITT_CUDA(ctx, cudaMemcpyAsync(c->h_xyz.data(), c->d_xyz, (size_t)c->n * 16, cudaMemcpyDeviceToHost, ctx->stream));
-    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PITT_CUDA(ctx, pitt::stream_sync(ctx));
   }
   c->h_valid = true;
   return PITT_OK;
@@ -236,7 +247,7 @@ struct TraceScope {
   }
   ~TraceScope() {
     if (enabled()) {
-      cudaStreamSynchronize(ctx->stream);
+      pitt::stream_sync(ctx);
       fprintf(stderr, "[pitt trace] %-28s %8.3f ms\n", name, now() - t0);
     }
   }

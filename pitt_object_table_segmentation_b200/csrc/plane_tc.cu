@@ -752,7 +752,7 @@ int launch_score_plane_tc(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_re
       PITT_CUDA(ctx, cudaMemcpyAsync(g_plane_tc_dump_host.data() + (size_t)TC_M * 256, d_P, 2 * sizeof(float), cudaMemcpyDeviceToHost,
                                      ctx->stream));
     }
-    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PITT_CUDA(ctx, pitt::stream_sync(ctx));
   }
   return PITT_OK;
 }

@@ -245,7 +245,7 @@ static int prefilter_impl(pitt_ctx* ctx, const float4* d_in, int n, const pitt_p
         ctx->launches++;
         int n_vox = 0;
         PITT_CUDA(ctx, cudaMemcpyAsync(&n_vox, d_total, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        PITT_CUDA(ctx, pitt::stream_sync(ctx));
         d_cur = d_vox;
         n_cur = n_vox;
       }
@@ -267,7 +267,7 @@ static int prefilter_impl(pitt_ctx* ctx, const float4* d_in, int n, const pitt_p
     PITT_TRY(device_exclusive_scan(ctx, d_pos, n_cur, d_cnt));
     int h_cnt[2] = {0, 0};
     PITT_CUDA(ctx, cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, ctx->stream));
-    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PITT_CUDA(ctx, pitt::stream_sync(ctx));
     n_out = h_cnt[0];
     I.n_further = h_cnt[1];
     if (n_out > 0) {
@@ -282,7 +282,7 @@ static int prefilter_impl(pitt_ctx* ctx, const float4* d_in, int n, const pitt_p
   }
   c->n = n_out;
   I.n_closer = n_out;
-  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PITT_CUDA(ctx, pitt::stream_sync(ctx));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { pool_free(ctx, c->d_xyz, (size_t)c->n * sizeof(float4)); delete c; return fail(ctx, PITT_ERR_CUDA, "prefilter kernels", e); }
   *out = c;
@@ -390,7 +390,7 @@ int pitt_arm_filter(pitt_ctx* ctx, const pitt_cloud* in, const pitt_arm_filter_p
     PITT_TRY(device_exclusive_scan(ctx, d_pos, n, d_cnt));
     int h_cnt[6];
     PITT_CUDA(ctx, cudaMemcpyAsync(h_cnt, d_cnt, sizeof(h_cnt), cudaMemcpyDeviceToHost, ctx->stream));
-    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PITT_CUDA(ctx, pitt::stream_sync(ctx));
     n_out = h_cnt[0];
     for (int k = 0; k < 5; ++k) h_rem[k] = h_cnt[1 + k];
     if (n_out > 0) {
@@ -402,7 +402,7 @@ int pitt_arm_filter(pitt_ctx* ctx, const pitt_cloud* in, const pitt_arm_filter_p
     }
   }
   c->n = n_out;
-  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PITT_CUDA(ctx, pitt::stream_sync(ctx));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { pool_free(ctx, c->d_xyz, (size_t)c->n * sizeof(float4)); delete c; return fail(ctx, PITT_ERR_CUDA, "arm filter kernels", e); }
   timer.finish();
@@ -420,7 +420,7 @@ int pitt_get_points(pitt_ctx* ctx, const pitt_cloud* c, float* out4) {
   cudaSetDevice(ctx->device);
   if (c->n > 0) {
     PITT_CUDA(ctx, cudaMemcpyAsync(out4, c->d_xyz, (size_t)c->n * 16, cudaMemcpyDeviceToHost, ctx->stream));
-    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PITT_CUDA(ctx, pitt::stream_sync(ctx));
   }
   return PITT_OK;
 }

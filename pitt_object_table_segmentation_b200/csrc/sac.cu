@@ -1042,7 +1042,7 @@ static int launch_score_plane_packed(pitt_ctx* ctx, const pitt_cloud* c, const H
   PITT_LAUNCH_CHECK(ctx, "plane_score_kernel");
   if (filter && g_plane_filter_collect_stats) {
     PITT_CUDA(ctx, cudaMemcpyAsync(g_plane_filter_stats, d_stats, sizeof(g_plane_filter_stats), cudaMemcpyDeviceToHost, ctx->stream));
-    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PITT_CUDA(ctx, pitt::stream_sync(ctx));
   }
   return PITT_OK;
 }
@@ -1426,7 +1426,7 @@ int sac_finish_from_winner(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_pa
   PITT_CUDA(ctx, cudaMemcpyAsync(h_ints, d_ints, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   PITT_CUDA(ctx, cudaMemcpyAsync(h_flt, d_flt, 16 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   PITT_CUDA(ctx, cudaMemcpyAsync(h_best, d_best, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PITT_CUDA(ctx, pitt::stream_sync(ctx));
   if (h_best[0] < 0 || h_best[0] >= H_all) return PITT_OK;
   const int NC = coeff_count(model);
   out->info.best_hypothesis = h_best[0];
@@ -1580,7 +1580,7 @@ int sac_segment_impl(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& 
     h_flags.resize(H_total + H_have);
     PITT_CUDA(ctx, cudaMemcpyAsync(h_counts.data() + H_total, d_counts, (size_t)H_have * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     PITT_CUDA(ctx, cudaMemcpyAsync(h_flags.data() + H_total, d_flags, (size_t)H_have, cudaMemcpyDeviceToHost, ctx->stream));
-    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PITT_CUDA(ctx, pitt::stream_sync(ctx));
     if (model == PITT_MODEL_PLANE && p.sampler == PITT_SAMPLER_PCL_MT19937 && !c->h_valid) {
       // speculative draws: a collinear triple would have been redrawn by getSamples. Extremely
       // rare; fetch the host mirror and restart with exact isSampleGood on the host.
@@ -1620,7 +1620,7 @@ int sac_segment_impl(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& 
   PITT_CUDA(ctx, cudaMemcpyAsync(h_ints, d_ints, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   PITT_CUDA(ctx, cudaMemcpyAsync(h_flt, d_flt, 16 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   trace_mark("  impl: finish issued");
-  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PITT_CUDA(ctx, pitt::stream_sync(ctx));
   trace_mark("  impl: scalars on the host");
   if (all_h) {
     winner = h_ints[0];

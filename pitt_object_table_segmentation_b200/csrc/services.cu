@@ -283,7 +283,7 @@ static int axis_extent(pitt_ctx* ctx, const float4* d_pts, int n, const float* c
   ctx->launches += 3;
   float h[9];
   PITT_CUDA(ctx, cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PITT_CUDA(ctx, pitt::stream_sync(ctx));
   out->height = h[0];
   memcpy(&out->idx1, &h[1], 4);
   memcpy(&out->idx2, &h[2], 4);
@@ -431,7 +431,7 @@ static int find_supports_impl(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt
       ctx->launches++;
       double bb[5];
       PITT_CUDA(ctx, cudaMemcpyAsync(bb, d_bb, sizeof(bb), cudaMemcpyDeviceToHost, ctx->stream));
-      PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      PITT_CUDA(ctx, pitt::stream_sync(ctx));
       double xMax = bb[0], xMin = bb[1], yMax = bb[2], yMin = bb[3], zMed = bb[4];
       xMax -= c.offset[0];
       xMin += c.offset[0];
@@ -450,7 +450,7 @@ static int find_supports_impl(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt
       PITT_TRY(device_exclusive_scan(ctx, d_onkeep, n0, d_ontotal));
       int n_on = 0;
       PITT_CUDA(ctx, cudaMemcpyAsync(&n_on, d_ontotal, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-      PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      PITT_CUDA(ctx, pitt::stream_sync(ctx));
       float4* d_on = nullptr;
       PITT_TRY(arena_alloc(ctx, (size_t)std::max(n_on, 1), &d_on));
       compact_points_kernel<<<cdiv(n0, 256), 256, 0, ctx->stream>>>(cloud->d_xyz, d_onflag, d_onkeep, n0, d_on, nullptr);
@@ -507,7 +507,7 @@ static int cluster_service_impl(pitt_ctx* ctx, const float4* d_xyz, int n, const
   if (nc == 0) return PITT_OK;
   std::vector<int> labels(n);
   PITT_CUDA(ctx, cudaMemcpyAsync(labels.data(), d_labels, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PITT_CUDA(ctx, pitt::stream_sync(ctx));
   out->sizes = sizes;
   out->offsets.resize(nc + 1);
   out->offsets[0] = 0;
@@ -532,7 +532,7 @@ static int cluster_service_impl(pitt_ctx* ctx, const float4* d_xyz, int n, const
   ctx->launches += 2;
   std::vector<float> sums((size_t)nc * 3);
   PITT_CUDA(ctx, cudaMemcpyAsync(sums.data(), d_cen, sums.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PITT_CUDA(ctx, pitt::stream_sync(ctx));
   out->centroid.resize((size_t)nc * 3);
   for (int c = 0; c < nc; ++c) {
     int cntp1 = 1 + sizes[c];  // `int cnt = 1; ... cnt++` (cluster…:78,91)
@@ -601,7 +601,7 @@ static int count_after_zero_drop(pitt_ctx* ctx, const SacDeviceResult& r, int* o
   if (r.n_inliers > 0) {
     int first = -1;
     PITT_CUDA(ctx, cudaMemcpyAsync(&first, r.d_inliers, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PITT_CUDA(ctx, pitt::stream_sync(ctx));
     if (first == 0) *out = r.n_inliers - 1;
   }
   return PITT_OK;
@@ -744,7 +744,7 @@ int pitt_find_supports(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_suppor
     res->points_used += need_pts;
     res->n_supports++;
   }
-  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PITT_CUDA(ctx, pitt::stream_sync(ctx));
   timer.finish();
   if (status == PITT_ERR_CAPACITY) return fail(ctx, status, "support result buffers too small (see maps_used / points_used)");
   return status;
@@ -798,7 +798,7 @@ int pitt_primitive_service(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_sa
   if (n_inl > 0) {
     std::vector<int> h(n_inl);
     PITT_CUDA(ctx, cudaMemcpyAsync(h.data(), ph.sac.d_inliers, (size_t)n_inl * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PITT_CUDA(ctx, pitt::stream_sync(ctx));
     int m = 0;
     for (int i = 0; i < n_inl; ++i) {
       if (h[i] == 0) continue;
@@ -887,7 +887,7 @@ int pitt_segment_frame(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_frame_
               view.n = cc[c].n; view.d_xyz = cc[c].d_xyz; view.d_nrm = cc[c].d_nrm; view.has_normals = true;
               int s1 = primitive_service_impl(h, &view, *sp[m], &ph[slot]);
               if (s1 == PITT_OK) s1 = count_after_zero_drop(h, ph[slot].sac, &inl[slot]);
-              if (s1 == PITT_OK && cudaStreamSynchronize(h->stream) != cudaSuccess) s1 = PITT_ERR_CUDA;
+              if (s1 == PITT_OK && pitt::stream_sync(h) != cudaSuccess) s1 = PITT_ERR_CUDA;
               ph[slot].sac.d_inliers = nullptr;  // helper arena memory: not valid after the task
               st[slot] = s1;
               view.d_xyz = nullptr; view.d_nrm = nullptr;
@@ -936,7 +936,7 @@ int pitt_segment_frame(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_frame_
       for (auto& v : cc) { v.d_xyz = nullptr; v.d_nrm = nullptr; }  // views own nothing
     }
   }
-  PITT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PITT_CUDA(ctx, pitt::stream_sync(ctx));
   timer.finish();
   res->device_ms = ctx->last_ms;
   if (status == PITT_ERR_CAPACITY) return fail(ctx, status, "shapes buffer too small");

@@ -475,6 +475,36 @@ def main():
             primitives[kind] = {"ms": pms, "evals_per_s": ev, "algorithmic_tflops": ev * flop / 1e12,
                                 "frac_of_ffma_peak": ev * flop / 1e12 / peak_ffma, "best_count": int(pc.max().item())}
             pcloud.release()
+        # the whole C3 job as the reference would run it: 64 clusters of 5 000 .. 50 000 points (32 cylinders, 32 cones), per
+        # cluster k = 50 normals + SACSegmentationFromNormals with setMaxIterations(10000) and PCL's adaptive stop + LM
+        # refinement + inlier list; clusters resident on the device, results (coefficients, inlier count) on the host
+        sizes = np.linspace(5000, 50000, 64).astype(int)
+        jobs = []
+        for i, sz in enumerate(sizes):
+            kind, model = (("cylinder", A.MODEL_CYLINDER), ("cone", A.MODEL_CONE))[i % 2]
+            cxyz, _ = scenes.primitive_cluster(kind, int(sz), 100 + i)
+            pj = pkg.default_sac_params(model)
+            pj.max_iterations = 10000
+            jobs.append((ctx.stage(cxyz), pj))
+
+        def c3_pass():
+            tot = 0
+            for cl, pj in jobs:
+                ctx.estimate_normals_device(cl, 50)
+                tot += ctx.sac_segment_count_only(cl, pj)["n_inliers"]
+            return tot
+
+        c3_pass()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        inl_total = c3_pass()
+        torch.cuda.synchronize()
+        c3_s = time.perf_counter() - t0
+        primitives["c3_job"] = {"clusters": 64, "points_total": int(sizes.sum()), "max_iterations": 10000, "seconds": c3_s,
+                                "clusters_per_s": 64 / c3_s, "inliers_total": int(inl_total),
+                                "note": "wall clock, one context, clusters one after the other (normals + segment each)"}
+        for cl, _ in jobs:
+            cl.release()
 
     line = None
     if rank == 0:

@@ -274,6 +274,11 @@ class Context:
         self._check(self.lib.pitt_get_normals(self.handle, cloud.handle, out.ctypes.data_as(A.f32p)))
         return out
 
+    def estimate_normals_device(self, cloud, k=50, viewpoint=(0.0, 0.0, 0.0)):
+        """pitt_estimate_normals without copying the normals back (they stay attached to the cloud)"""
+        vp = (C.c_float * 3)(*viewpoint)
+        self._check(self.lib.pitt_estimate_normals(self.handle, cloud.handle, int(k), vp))
+
     def knn(self, cloud, k):
         idx = np.zeros((cloud.n, k), np.int32)
         sq = np.zeros((cloud.n, k), np.float32)

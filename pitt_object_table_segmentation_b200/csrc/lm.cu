@@ -5,7 +5,11 @@
 // unsupported/NonLinearOptimization) reached from seg.segment() with
 // setOptimizeCoefficients(true) at sphere_segmentation_srv.cpp:60, cylinder…:114, cone…:115.
 //
-// One CTA per problem. The m residual rows live in global/L2 memory (fvec, the m x n Jacobian);
+// One CTA per problem, or for big problems (m_cap >= LM_CLUSTER_MIN rows: the C3 clusters) one thread-block CLUSTER of 8
+// CTAs: rows are owned by (CTA, thread) in a fixed stride, every CTA keeps its own copy of the small state and runs the
+// same control flow (all decisions derive from bit-identical reductions), reductions over m exchange one double-double
+// partial per CTA through L2, and barrier.cluster (release/acquire) replaces __syncthreads.
+// The m residual rows live in global/L2 memory (fvec, the m x n Jacobian);
 // every O(m) step is data parallel over the CTA, every reduction over m is accumulated in
 // double-double by a fixed-shape tree and rounded once to float (the oracle defines those sums as
 // exact sums rounded once), and the n x n algebra (n <= 7: lmpar, qrsolv, Givens) runs on thread 0.
@@ -18,6 +22,28 @@ namespace pitt {
 
 constexpr int LM_TPB = 512;
 constexpr int LM_NW = LM_TPB / 32;
+constexpr int LM_CLUSTER = 8;           // CTAs per problem on the cluster path (portable maximum)
+constexpr int LM_CLUSTER_MIN = 4096;    // rows from which the cluster path pays (tools/lm_crossover.py: 4000 rows 1.74 -> 1.53 ms, 50 000 rows 10.8 -> 2.3 ms)
+constexpr int LM_XCH_DOUBLES = 2 * 8 * LM_CLUSTER * 2;  // exchange area: 2 buffers x 8 dots x CTAs x (hi, lo)
+
+template <int CL>
+__device__ __forceinline__ int lm_rank() {
+  if (CL == 1) return 0;
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return (int)r;
+}
+// barrier over the problem's threads; on the cluster path it also orders the global-memory writes of the CTAs
+template <int CL>
+__device__ __forceinline__ void lm_sync() {
+  if (CL == 1) {
+    __syncthreads();
+  } else {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+}
+// scalar written by another CTA of the cluster: read it from L2, never from this SM's L1
+__device__ __forceinline__ float lm_peek(const float* p) { return __ldcg(p); }
 
 struct dd {
   double hi, lo;
@@ -55,7 +81,8 @@ struct DotSet {
   int r0[8];
   int nv;
 };
-__device__ void block_multidot(const DotSet& D, int m, LmShared& S) {
+template <int CL>
+__device__ void block_multidot(const DotSet& D, int m, LmShared& S, double* xch, int& xch_parity) {
   dd acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = dd{0.0, 0.0};
@@ -63,7 +90,9 @@ __device__ void block_multidot(const DotSet& D, int m, LmShared& S) {
 #pragma unroll
   for (int j = 0; j < 8; ++j)
     if (j < D.nv) rmin = min(rmin, D.r0[j]);
-  for (int i = rmin + threadIdx.x; i < m; i += LM_TPB) {
+  const int rank = lm_rank<CL>();
+  for (int i = rank * LM_TPB + threadIdx.x; i < m; i += LM_TPB * CL) {
+    if (i < rmin) continue;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (j < D.nv && i >= D.r0[j]) dd_add(acc[j], (double)D.a[j][i] * (double)D.b[j][i]);
@@ -83,9 +112,39 @@ __device__ void block_multidot(const DotSet& D, int m, LmShared& S) {
   __syncthreads();
   // warp j folds the LM_NW per-warp partials of dot j with a shuffle tree
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (CL == 1) {
+    if (w < D.nv) {
+      dd s{0.0, 0.0};
+      if (l < LM_NW) { s.hi = S.md_hi[w][l]; s.lo = S.md_lo[w][l]; }
+      for (int o = 16; o > 0; o >>= 1) {
+        double ohi = __shfl_down_sync(0xffffffffu, s.hi, o), olo = __shfl_down_sync(0xffffffffu, s.lo, o);
+        dd_merge(s, ohi, olo);
+      }
+      if (l == 0) S.mdot[w] = (float)(s.hi + s.lo);
+    }
+    __syncthreads();
+    return;
+  }
+  // cluster: every CTA publishes its partial (double buffered: a CTA can be one reduction ahead of the slowest reader),
+  // then every CTA folds the CL partials in the same order, so that all of them hold the same bits
+  double* buf = xch + (size_t)(xch_parity & 1) * (8 * CL * 2);
+  xch_parity ^= 1;
   if (w < D.nv) {
     dd s{0.0, 0.0};
     if (l < LM_NW) { s.hi = S.md_hi[w][l]; s.lo = S.md_lo[w][l]; }
+    for (int o = 16; o > 0; o >>= 1) {
+      double ohi = __shfl_down_sync(0xffffffffu, s.hi, o), olo = __shfl_down_sync(0xffffffffu, s.lo, o);
+      dd_merge(s, ohi, olo);
+    }
+    if (l == 0) {
+      __stcg(buf + ((size_t)w * CL + rank) * 2, s.hi);
+      __stcg(buf + ((size_t)w * CL + rank) * 2 + 1, s.lo);
+    }
+  }
+  lm_sync<CL>();
+  if (w < D.nv) {
+    dd s{0.0, 0.0};
+    if (l < CL) { s.hi = __ldcg(buf + ((size_t)w * CL + l) * 2); s.lo = __ldcg(buf + ((size_t)w * CL + l) * 2 + 1); }
     for (int o = 16; o > 0; o >>= 1) {
       double ohi = __shfl_down_sync(0xffffffffu, s.hi, o), olo = __shfl_down_sync(0xffffffffu, s.lo, o);
       dd_merge(s, ohi, olo);
@@ -96,21 +155,23 @@ __device__ void block_multidot(const DotSet& D, int m, LmShared& S) {
 }
 
 // single dot product, same reduction machinery
-__device__ float block_dot(const float* __restrict__ a, const float* __restrict__ b, int r0, int m, LmShared& S) {
+template <int CL>
+__device__ float block_dot(const float* __restrict__ a, const float* __restrict__ b, int r0, int m, LmShared& S, double* xch,
+                           int& xch_parity) {
   DotSet D;
   D.nv = 1;
   D.a[0] = a; D.b[0] = b; D.r0[0] = r0;
-  block_multidot(D, m, S);
+  block_multidot<CL>(D, m, S, xch, xch_parity);
   return S.mdot[0];
 }
 
 // ---- residual functors (float sequences of the PCL OptimizationFunctor::operator())
 template <int MODEL>
 __device__ void eval_residuals(const float4* __restrict__ xyz, const int* __restrict__ idx, int m, const float* x,
-                               float* __restrict__ fvec) {
+                               float* __restrict__ fvec, int first, int stride) {
   if (MODEL == PITT_MODEL_SPHERE) {
     const float x0 = x[0], x1 = x[1], x2 = x[2], x3 = x[3];
-    for (int i = threadIdx.x; i < m; i += LM_TPB) {
+    for (int i = first; i < m; i += stride) {
       float4 p = __ldg(xyz + idx[i]);
       float c0 = p.x - x0, c1 = p.y - x1, c2 = p.z - x2;
       fvec[i] = sqrtf((c0 * c0 + c2 * c2) + c1 * c1) - x3;
@@ -118,7 +179,7 @@ __device__ void eval_residuals(const float4* __restrict__ xyz, const int* __rest
   } else if (MODEL == PITT_MODEL_CYLINDER) {
     const f3 lp = mk3(x[0], x[1], x[2]), ld = mk3(x[3], x[4], x[5]);
     const float rr = x[6] * x[6];
-    for (int i = threadIdx.x; i < m; i += LM_TPB) {
+    for (int i = first; i < m; i += stride) {
       float4 p = __ldg(xyz + idx[i]);
       fvec[i] = (float)((double)sqr_pt_line(mk3(p.x, p.y, p.z), lp, ld) - (double)rr);
     }
@@ -127,7 +188,7 @@ __device__ void eval_residuals(const float4* __restrict__ xyz, const int* __rest
     const float apexdotdir = dot0(apex, ad);
     const float dirdotdir = 1.0f / dot0(ad, ad);
     const float tan_a = tanf_d(x[6]);
-    for (int i = threadIdx.x; i < m; i += LM_TPB) {
+    for (int i = first; i < m; i += stride) {
       float4 p4 = __ldg(xyz + idx[i]);
       f3 pt = mk3(p4.x, p4.y, p4.z);
       float k = (dot0(pt, ad) - apexdotdir) * dirdotdir;
@@ -366,8 +427,9 @@ __device__ void lmpar2(const float* r8, const int* perm, int rank, const float* 
   for (int j = 0; j < N; ++j) x_out[j] = x[j];
 }
 
-// work layout (floats): fjac [n*m_cap] | fvec [m_cap] | wa4 [m_cap] | val2 [m_cap]
-template <int MODEL>
+// work layout (floats): fjac [n*m_cap] | fvec [m_cap] | wa4 [m_cap] | val2 [m_cap] | (cluster) exchange area
+// CL = 1: one CTA. CL = LM_CLUSTER: launched with a cluster dimension of CL; row i belongs to thread (i mod (LM_TPB CL)).
+template <int MODEL, int CL>
 __global__ void __launch_bounds__(LM_TPB)
 lm_kernel(const float4* __restrict__ xyz, const int* __restrict__ idx, const int* __restrict__ n_idx_ptr, int m_cap,
           const float* __restrict__ model_in, float* __restrict__ work, float* __restrict__ refined, int* __restrict__ info_out) {
@@ -378,11 +440,17 @@ lm_kernel(const float4* __restrict__ xyz, const int* __restrict__ idx, const int
   float* fvec = work + (size_t)n * m_cap;
   float* wa4 = fvec + m_cap;
   float* val2 = wa4 + m_cap;
+  double* xch = reinterpret_cast<double*>(((uintptr_t)(val2 + m_cap) + 15) & ~(uintptr_t)15);  // cluster path only
+  int xch_parity = 0;
+  const int rank = lm_rank<CL>();
+  const int g0 = rank * LM_TPB + threadIdx.x;  // first row of this thread
+  constexpr int GS = LM_TPB * CL;              // row stride
+  const bool lead = (threadIdx.x == 0) && (rank == 0);  // the one thread that writes single global elements
   const float eps = 1.1920928955078125e-07f;
   const float ftol = sqrtf(eps), xtol = sqrtf(eps), gtol = 0.0f, factor = 100.0f;
   const int maxfev = 400;
   if (threadIdx.x < 8) S.x[threadIdx.x] = model_in[threadIdx.x];
-  __syncthreads();
+  lm_sync<CL>();
   int status = -1, nfev = 0;
   bool run = true;
   if (MODEL == PITT_MODEL_SPHERE) { if (m <= 4) { run = false; status = 0; } }
@@ -393,16 +461,16 @@ lm_kernel(const float4* __restrict__ xyz, const int* __restrict__ idx, const int
   int iter = 1;
   if (run) {
     nfev = 1;
-    eval_residuals<MODEL>(xyz, idx, m, S.x, fvec);
-    __syncthreads();
-    fnorm = sqrtf(block_dot(fvec, fvec, 0, m, S));
+    eval_residuals<MODEL>(xyz, idx, m, S.x, fvec, g0, GS);
+    lm_sync<CL>();
+    fnorm = sqrtf(block_dot<CL>(fvec, fvec, 0, m, S, xch, xch_parity));
   }
   while (run && status == -1) {
     // ---- NumericalDiff (forward): f(x) again, then one perturbed evaluation per parameter
     const float h_eps = sqrtf(eps);
-    eval_residuals<MODEL>(xyz, idx, m, S.x, wa4);  // val1
+    eval_residuals<MODEL>(xyz, idx, m, S.x, wa4, g0, GS);  // val1
     nfev++;
-    __syncthreads();
+    lm_sync<CL>();
     for (int j = 0; j < n; ++j) {
       if (threadIdx.x == 0) {
         for (int q = 0; q < n; ++q) S.xs[q] = S.x[q];
@@ -411,28 +479,28 @@ lm_kernel(const float4* __restrict__ xyz, const int* __restrict__ idx, const int
         S.xs[j] += h;
         S.bcast[1] = h;
       }
-      __syncthreads();
+      lm_sync<CL>();
       const float h = S.bcast[1];
-      eval_residuals<MODEL>(xyz, idx, m, S.xs, val2);
+      eval_residuals<MODEL>(xyz, idx, m, S.xs, val2, g0, GS);
       nfev++;
-      __syncthreads();
+      lm_sync<CL>();
       float* cj = fjac + (size_t)j * m_cap;
-      for (int i = threadIdx.x; i < m; i += LM_TPB) cj[i] = (val2[i] - wa4[i]) / h;
-      __syncthreads();
+      for (int i = g0; i < m; i += GS) cj[i] = (val2[i] - wa4[i]) / h;
+      lm_sync<CL>();
     }
     // ---- column norms, ColPivHouseholderQR (columns are swapped logically through S.cidx),
     //      with Q^T fvec computed on the fly: wa4 rides along as an extra column
-    for (int i = threadIdx.x; i < m; i += LM_TPB) wa4[i] = fvec[i];
+    for (int i = g0; i < m; i += GS) wa4[i] = fvec[i];
     if (threadIdx.x < 8) S.cidx[threadIdx.x] = threadIdx.x;
-    __syncthreads();
+    lm_sync<CL>();
     {
       DotSet D;
       D.nv = n;
       for (int j = 0; j < n; ++j) { D.a[j] = D.b[j] = fjac + (size_t)j * m_cap; D.r0[j] = 0; }
-      block_multidot(D, m, S);
+      block_multidot<CL>(D, m, S, xch, xch_parity);
       if (threadIdx.x == 0)
         for (int j = 0; j < n; ++j) { S.wa2[j] = sqrtf(S.mdot[j]); S.colSq[j] = S.mdot[j]; }
-      __syncthreads();
+      lm_sync<CL>();
     }
     float threshold_helper, maxpivot = 0.0f;
     int nonzero_pivots = n;
@@ -451,20 +519,20 @@ lm_kernel(const float4* __restrict__ xyz, const int* __restrict__ idx, const int
         D.nv = 2;
         D.a[0] = D.b[0] = cb; D.r0[0] = k;
         D.a[1] = D.b[1] = cb; D.r0[1] = k + 1;
-        block_multidot(D, m, S);
+        block_multidot<CL>(D, m, S, xch, xch_parity);
       }
       const float bigSq = S.mdot[0];
       const float tailSq = (m - k == 1) ? 0.0f : S.mdot[1];
-      __syncthreads();
+      lm_sync<CL>();
       if (bigSq < threshold_helper * (float)(m - k)) {
         if (threadIdx.x == 0) S.colSq[big] = bigSq;
         nonzero_pivots = k;
         for (int j = k; j < n; ++j) {
           if (threadIdx.x == 0) { S.hcoef[j] = 0.0f; S.transp[j] = j; }
           float* cj = fjac + (size_t)S.cidx[j] * m_cap;
-          for (int i = j + 1 + threadIdx.x; i < m; i += LM_TPB) cj[i] = 0.0f;
+          for (int i = g0; i < m; i += GS) if (i >= j + 1) cj[i] = 0.0f;
         }
-        __syncthreads();
+        lm_sync<CL>();
         break;
       }
       if (threadIdx.x == 0) {
@@ -475,9 +543,9 @@ lm_kernel(const float4* __restrict__ xyz, const int* __restrict__ idx, const int
           float q = S.colSq[k]; S.colSq[k] = S.colSq[big]; S.colSq[big] = q;
         }
       }
-      __syncthreads();
+      lm_sync<CL>();
       float* ck = fjac + (size_t)S.cidx[k] * m_cap;
-      const float c0 = ck[k];
+      const float c0 = lm_peek(ck + k);
       float tau, beta, den = 1.0f;
       if (tailSq == 0.0f) {
         tau = 0.0f;
@@ -490,31 +558,32 @@ lm_kernel(const float4* __restrict__ xyz, const int* __restrict__ idx, const int
       }
       if (fabsf(beta) > maxpivot) maxpivot = fabsf(beta);
       // essential part of the reflector (in place), then v . (remaining columns and wa4) in one pass
-      for (int i = k + 1 + threadIdx.x; i < m; i += LM_TPB) ck[i] = (tailSq == 0.0f) ? 0.0f : ck[i] / den;
-      __syncthreads();  // everyone read c0 = ck[k] and the scaled tail is complete
-      if (threadIdx.x == 0) { S.hcoef[k] = tau; ck[k] = beta; }
+      for (int i = g0; i < m; i += GS) if (i >= k + 1) ck[i] = (tailSq == 0.0f) ? 0.0f : ck[i] / den;
+      lm_sync<CL>();  // everyone read c0 = ck[k] and the scaled tail is complete
+      if (threadIdx.x == 0) S.hcoef[k] = tau;
+      if (lead) ck[k] = beta;
       DotSet D;
       D.nv = 0;
       for (int j = k + 1; j < n; ++j) { D.a[D.nv] = ck; D.b[D.nv] = fjac + (size_t)S.cidx[j] * m_cap; D.r0[D.nv] = k + 1; D.nv++; }
       D.a[D.nv] = ck; D.b[D.nv] = wa4; D.r0[D.nv] = k + 1; D.nv++;
-      if (m - k > 1) block_multidot(D, m, S);
-      else __syncthreads();
+      if (m - k > 1) block_multidot<CL>(D, m, S, xch, xch_parity);
+      else lm_sync<CL>();
 #pragma unroll 1
       for (int t = 0; t < D.nv; ++t) {
         float* cj = const_cast<float*>(D.b[t]);
         if (m - k == 1) {
-          if (threadIdx.x == 0) cj[k] *= (1.0f - tau);
+          if (lead) cj[k] *= (1.0f - tau);
         } else {
-          const float tmp = S.mdot[t] + cj[k];
-          for (int i = k + 1 + threadIdx.x; i < m; i += LM_TPB) cj[i] -= tmp * (tau * ck[i]);
-          __syncthreads();  // all threads have read cj[k]
-          if (threadIdx.x == 0) cj[k] -= tau * tmp;
+          const float tmp = S.mdot[t] + lm_peek(cj + k);
+          for (int i = g0; i < m; i += GS) if (i >= k + 1) cj[i] -= tmp * (tau * ck[i]);
+          lm_sync<CL>();  // all threads have read cj[k]
+          if (lead) cj[k] -= tau * tmp;
         }
       }
-      __syncthreads();
+      lm_sync<CL>();
       if (threadIdx.x == 0)
-        for (int j = k + 1; j < n; ++j) { float v = fjac[(size_t)S.cidx[j] * m_cap + k]; S.colSq[j] -= v * v; }
-      __syncthreads();
+        for (int j = k + 1; j < n; ++j) { float v = lm_peek(fjac + (size_t)S.cidx[j] * m_cap + k); S.colSq[j] -= v * v; }
+      lm_sync<CL>();
     }
     if (threadIdx.x == 0) {
       for (int j = 0; j < n; ++j) S.perm[j] = j;
@@ -526,7 +595,7 @@ lm_kernel(const float4* __restrict__ xyz, const int* __restrict__ idx, const int
         S.bcast[2] = norm_n(t, n);
       }
     }
-    __syncthreads();
+    lm_sync<CL>();
     if (iter == 1) {
       xnorm = S.bcast[2];
       delta = factor * xnorm;
@@ -534,10 +603,10 @@ lm_kernel(const float4* __restrict__ xyz, const int* __restrict__ idx, const int
     }
     // ---- small algebra on thread 0
     if (threadIdx.x == 0) {
-      for (int j = 0; j < n; ++j) S.qtf[j] = wa4[j];
+      for (int j = 0; j < n; ++j) S.qtf[j] = lm_peek(wa4 + j);
       for (int i = 0; i < 64; ++i) S.r[i] = 0.0f;
       for (int i = 0; i < n; ++i)
-        for (int j = 0; j < n; ++j) S.r[i * 8 + j] = fjac[(size_t)S.cidx[j] * m_cap + i];
+        for (int j = 0; j < n; ++j) S.r[i * 8 + j] = lm_peek(fjac + (size_t)S.cidx[j] * m_cap + i);
       float gnorm = 0.0f;
       if (fnorm != 0.0f)
         for (int j = 0; j < n; ++j)
@@ -553,7 +622,7 @@ lm_kernel(const float4* __restrict__ xyz, const int* __restrict__ idx, const int
       for (int i = 0; i < nonzero_pivots; ++i) rank += (fabsf(S.r[i * 8 + i]) > thr) ? 1 : 0;
       S.ibcast[0] = rank;
     }
-    __syncthreads();
+    lm_sync<CL>();
     const float gnorm = S.bcast[3];
     const int rank = S.ibcast[0];
     if (gnorm <= gtol) { status = 4; break; }
@@ -573,14 +642,14 @@ lm_kernel(const float4* __restrict__ xyz, const int* __restrict__ idx, const int
           S.wa3[i] = acc;
         }
       }
-      __syncthreads();
+      lm_sync<CL>();
       par = S.bcast[1];
       const float pnorm = S.bcast[2];
       if (iter == 1) delta = fminf(delta, pnorm);
-      eval_residuals<MODEL>(xyz, idx, m, S.wa2, wa4);
+      eval_residuals<MODEL>(xyz, idx, m, S.wa2, wa4, g0, GS);
       ++nfev;
-      __syncthreads();
-      const float fnorm1 = sqrtf(block_dot(wa4, wa4, 0, m, S));
+      lm_sync<CL>();
+      const float fnorm1 = sqrtf(block_dot<CL>(wa4, wa4, 0, m, S, xch, xch_parity));
       float actred = -1.0f;
       if (0.1f * fnorm1 < fnorm) { float q = fnorm1 / fnorm; actred = 1.0f - q * q; }
       const float q1 = norm_n(S.wa3, n) / fnorm;
@@ -602,14 +671,14 @@ lm_kernel(const float4* __restrict__ xyz, const int* __restrict__ idx, const int
         delta = pnorm / 0.5f;
         par = 0.5f * par;
       }
-      __syncthreads();  // all threads have read S.wa3 / S.wa2 / bcast before thread 0 rewrites them
+      lm_sync<CL>();  // all threads have read S.wa3 / S.wa2 / bcast before thread 0 rewrites them
       if (ratio >= 1e-4f) {
         if (threadIdx.x == 0) {
           for (int j = 0; j < n; ++j) { S.x[j] = S.wa2[j]; S.wa2[j] = S.diag[j] * S.x[j]; }
           S.bcast[2] = norm_n(S.wa2, n);
         }
-        for (int i = threadIdx.x; i < m; i += LM_TPB) fvec[i] = wa4[i];
-        __syncthreads();
+        for (int i = g0; i < m; i += GS) fvec[i] = wa4[i];
+        lm_sync<CL>();
         xnorm = S.bcast[2];
         fnorm = fnorm1;
         ++iter;
@@ -624,8 +693,8 @@ lm_kernel(const float4* __restrict__ xyz, const int* __restrict__ idx, const int
       if (gnorm <= eps) { status = 8; break; }
     } while (ratio < 1e-4f);
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  lm_sync<CL>();
+  if (lead) {
     float out[8];
     for (int i = 0; i < 8; ++i) out[i] = (i < n) ? S.x[i] : 0.0f;
     if (MODEL != PITT_MODEL_SPHERE && minimized) {
@@ -638,28 +707,54 @@ lm_kernel(const float4* __restrict__ xyz, const int* __restrict__ idx, const int
   }
 }
 
+template <int MODEL>
+static cudaError_t lm_launch(pitt_ctx* ctx, bool cluster, const float4* xyz, const int* d_idx, const int* d_n_idx, int m_cap,
+                             const float* d_model, float* d_work, float* d_refined, int* d_lm_info) {
+  if (!cluster) {
+    lm_kernel<MODEL, 1><<<1, LM_TPB, 0, ctx->stream>>>(xyz, d_idx, d_n_idx, m_cap, d_model, d_work, d_refined, d_lm_info);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(LM_CLUSTER);
+  cfg.blockDim = dim3(LM_TPB);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = LM_CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, lm_kernel<MODEL, LM_CLUSTER>, xyz, d_idx, d_n_idx, m_cap, d_model, d_work, d_refined, d_lm_info);
+}
+
+int g_lm_cluster_min = LM_CLUSTER_MIN;  // test hook: rows from which the cluster path is used
+
 int lm_refine(pitt_ctx* ctx, const pitt_cloud* c, int model, const float* d_model, const int* d_idx, const int* d_n_idx,
               int n_idx_host, float* d_refined, int* d_lm_info) {
   // m is only known on the device (d_n_idx); the workspace is sized for the worst case
   const int m_cap = n_idx_host >= 0 ? std::max(n_idx_host, 1) : std::max(c->n, 1);
   const int n = (model == PITT_MODEL_SPHERE) ? 4 : 7;
+  const bool cluster = m_cap >= g_lm_cluster_min;
   float* d_work = nullptr;
-  PITT_TRY(arena_alloc(ctx, (size_t)(n + 3) * m_cap, &d_work));
+  PITT_TRY(arena_alloc(ctx, (size_t)(n + 3) * m_cap + 16 + 2 * LM_XCH_DOUBLES, &d_work));
+  cudaError_t e;
   switch (model) {
     case PITT_MODEL_SPHERE:
-      lm_kernel<PITT_MODEL_SPHERE><<<1, LM_TPB, 0, ctx->stream>>>(c->d_xyz, d_idx, d_n_idx, m_cap, d_model, d_work, d_refined, d_lm_info);
+      e = lm_launch<PITT_MODEL_SPHERE>(ctx, cluster, c->d_xyz, d_idx, d_n_idx, m_cap, d_model, d_work, d_refined, d_lm_info);
       break;
     case PITT_MODEL_CYLINDER:
-      lm_kernel<PITT_MODEL_CYLINDER><<<1, LM_TPB, 0, ctx->stream>>>(c->d_xyz, d_idx, d_n_idx, m_cap, d_model, d_work, d_refined, d_lm_info);
+      e = lm_launch<PITT_MODEL_CYLINDER>(ctx, cluster, c->d_xyz, d_idx, d_n_idx, m_cap, d_model, d_work, d_refined, d_lm_info);
       break;
     case PITT_MODEL_CONE:
-      lm_kernel<PITT_MODEL_CONE><<<1, LM_TPB, 0, ctx->stream>>>(c->d_xyz, d_idx, d_n_idx, m_cap, d_model, d_work, d_refined, d_lm_info);
+      e = lm_launch<PITT_MODEL_CONE>(ctx, cluster, c->d_xyz, d_idx, d_n_idx, m_cap, d_model, d_work, d_refined, d_lm_info);
       break;
     default:
       return fail(ctx, PITT_ERR_INVALID, "lm_refine: model has no LM refinement");
   }
   ctx->launches++;
-  PITT_CUDA(ctx, cudaGetLastError());
+  if (e != cudaSuccess) return fail(ctx, PITT_ERR_CUDA, "lm_kernel launch", e);
   return PITT_OK;
 }
 

@@ -1493,6 +1493,11 @@ int sac_segment_impl(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& 
   std::vector<int> h_samples;
   int H_total = 0;
   int batch = H_first;
+  // PCL's adaptive stop usually ends a 10 000-iteration job (C3) after a handful of hypotheses: big jobs are scored in
+  // batches of the sample stream (256, then 4096 at a time) and the host scan decides after each batch whether PCL would
+  // have stopped inside it. Results do not depend on the batching (the scan runs in stream order); small jobs (the frame
+  // path: at most 1001 hypotheses on a few thousand points) stay one batch = one round trip.
+  if (!all_h && c->stream_chunks == 0 && (double)n * (double)H_first >= 33554432.0) batch = 256;
   int* d_samples = nullptr;
   HypRec* d_recs = nullptr;
   float* d_coeffs8 = nullptr;

@@ -45,14 +45,24 @@ def test_fast_path_equals_exact_path_on_wrong_shapes(ctx, oracle, model):
     assert np.array_equal(c_gpu, c_cpu)
 
 
+@pytest.fixture
+def lm_path(ctx, request):
+    """Levenberg-Marquardt on one CTA (small problems) or on a cluster of 8 CTAs (>= 4096 rows by default): force either"""
+    ctx.lib.pitt_debug_lm_cluster_min(1 if request.param == "cluster" else 1 << 30)
+    yield request.param
+    ctx.lib.pitt_debug_lm_cluster_min(4096)
+
+
+@pytest.mark.parametrize("lm_path", ["cta", "cluster"], indirect=True)
+@pytest.mark.parametrize("n", [4000, 700, 23000])
 @pytest.mark.parametrize("model", [A.MODEL_SPHERE, A.MODEL_CYLINDER, A.MODEL_CONE])
-def test_lm_refine_bit_exact(ctx, oracle, model):
-    xyz, nrm, _ = _cluster(KINDS[model], 4000, 200 + model, oracle)
+def test_lm_refine_bit_exact(ctx, oracle, model, n, lm_path):
+    xyz, nrm, _ = _cluster(KINDS[model], n, 200 + model, oracle)
     cloud = ctx.stage(xyz, normals=nrm)
     p = pkg.default_sac_params(model)
     p.optimize = 0
     base = oracle.sac_segment(xyz, nrm, p)
-    assert len(base["inliers"]) > 500
+    assert len(base["inliers"]) > n // 8
     ref_c, info_c = oracle.sac_refine(xyz, nrm, p, base["coeffs"], base["inliers"])
     ref_g, info_g = ctx.sac_refine(cloud, p, base["coeffs"], base["inliers"])
     assert (info_g.lm_info, info_g.lm_nfev) == (info_c.lm_info, info_c.lm_nfev)
@@ -75,6 +85,12 @@ def test_segment_bit_exact(ctx, oracle, model, n, seed):
     np.testing.assert_allclose(got["coeffs"], want["coeffs"], rtol=1e-5, atol=1e-7)
     assert np.array_equal(got["coeffs"].view(np.uint32), want["coeffs"].view(np.uint32))
     assert np.array_equal(got["inliers"], want["inliers"])
+
+
+@pytest.mark.parametrize("lm_path", ["cluster"], indirect=True)
+def test_wrong_model_on_each_shape_cluster_lm(ctx, oracle, lm_path):
+    """degenerate fits (rank-deficient Jacobians, early exits) through the cluster path of the LM kernel"""
+    test_wrong_model_on_each_shape(ctx, oracle)
 
 
 def test_wrong_model_on_each_shape(ctx, oracle):
@@ -248,3 +264,33 @@ def test_two_tier_scoring_equals_generic(ctx, oracle, model, n, offset):
         assert c2.max() > n // 4
     c_cpu, _, v_cpu = oracle.sac_score(xyz, nrm, p, samples[:48])
     assert np.array_equal(c2[:48], c_cpu)
+
+
+@pytest.mark.parametrize("model,n,outliers", [(A.MODEL_CYLINDER, 30000, 0.0), (A.MODEL_CONE, 30000, 0.0), (A.MODEL_CONE, 4000, 0.8),
+                                               (A.MODEL_CYLINDER, 4000, 0.93), (A.MODEL_SPHERE, 6000, 0.85)])
+def test_c3_segment_with_10000_iterations(ctx, oracle, model, n, outliers):
+    """config 3 as the reference would run it: setMaxIterations(10000) with PCL's adaptive stop. The device scores the sample
+    stream in batches (256, then 4096) and stops where PCL stops; clean clusters end after a few hypotheses, clusters
+    drowned in outliers need several batches. Everything equal to the oracle, iteration counts included."""
+    rng = np.random.default_rng(77)
+    xyz, _ = scenes.primitive_cluster(KINDS[model], n, 21)
+    if outliers > 0:
+        m = int(n * outliers)
+        lo, hi = xyz[:, :3].min(0) - 0.05, xyz[:, :3].max(0) + 0.05
+        xyz[rng.choice(n, m, replace=False), :3] = rng.uniform(lo, hi, (m, 3)).astype(np.float32)
+    nrm = oracle.estimate_normals(xyz, 50, (0.0, 0.0, 0.0))
+    cloud = ctx.stage(xyz, normals=nrm)
+    p = pkg.default_sac_params(model)
+    p.max_iterations = 10000
+    got = ctx.sac_segment(cloud, p)
+    want = oracle.sac_segment(xyz, nrm, p)
+    gi, wi = got["info"], want["info"]
+    assert (gi.iterations, gi.skipped, gi.best_hypothesis, gi.best_count, gi.n_inliers_model) == \
+           (wi.iterations, wi.skipped, wi.best_hypothesis, wi.best_count, wi.n_inliers_model)
+    assert (gi.lm_info, gi.lm_nfev) == (wi.lm_info, wi.lm_nfev)
+    assert np.array_equal(got["coeffs"].view(np.uint32), want["coeffs"].view(np.uint32))
+    assert np.array_equal(got["inliers"], want["inliers"])
+    if outliers > 0:
+        assert gi.iterations > 200 and (model == A.MODEL_CYLINDER or gi.iterations + gi.skipped > 256)  # beyond the first batch
+    else:
+        assert gi.iterations < 256 and gi.hypotheses <= 256  # ... and here inside it: 256 hypotheses scored, not 10 001

@@ -483,7 +483,7 @@ struct Tier1<PITT_MODEL_CYLINDER> {
 template <>
 struct Tier1<PITT_MODEL_CONE> {
   f3 apex, dir;
-  float apexdotdir, dirdotdir, tan_f, T, D_in;
+  float apexdotdir, dirdotdir, tan_f, T, D_in, Dp, Dm;
   __device__ __forceinline__ void load(const HypRec* rec) {
     float4 q0 = *reinterpret_cast<const float4*>(rec->v);
     float4 q1 = *reinterpret_cast<const float4*>(rec->v + 4);
@@ -493,6 +493,11 @@ struct Tier1<PITT_MODEL_CONE> {
     dir = mk3(q1.x, q1.y, q1.z); apexdotdir = q1.w;
     dirdotdir = q2.x; tan_f = q2.w;
     T = q3.z; D_in = q3.w;
+    // sq = fl(N / D) with N = |dir x (apex - pt)|^2, D = dir.dir: the tests on sq (margins of 1e-5, see make_rec) are made
+    // on N against bounds scaled by D (1 +- 2e-5), which implies them whatever the rounding of the division: no division here
+    const float D = dot0(dir, dir);
+    Dp = D * (1.0f + 2e-5f);
+    Dm = D * (1.0f - 2e-5f);
   }
   __device__ __forceinline__ void classify(f3 pt, bool nice, bool& in, bool& und) const {
     // same float quantities as RecRegs<CONE>::inlier
@@ -500,13 +505,13 @@ struct Tier1<PITT_MODEL_CONE> {
     const f3 proj = apex + k * dir;
     const f3 height = apex - proj;
     const float hn2 = sqn0(height);
-    const float sq = sqr_pt_line(pt, apex, dir);
+    const float N = sqn0(cross0(dir, apex - pt));  // numerator of sqr_pt_line(pt, apex, dir)
     const float ar = tan_f * (hn2 * rsqrtf(hn2));  // ~ tan * |height| (within 1e-6 relative of the fast path's actual_r)
     const float up = fabsf(ar) + T, dn = fabsf(ar) - T;
-    const bool out = (sq >= up * up * (1.0f + 1e-5f)) | ((dn > 0.0f) & (sq <= dn * dn * (1.0f - 1e-5f)));
+    const bool out = (N >= up * up * Dp) | ((dn > 0.0f) & (N <= dn * dn * Dm));
     // D_in > 0 implies tan > 0: ar is the cone radius itself
     const float b = ar + D_in, a = fmaxf(ar - D_in, 0.0f);
-    in = nice & (D_in > 0.0f) & (hn2 >= 1e-12f) & (sq >= 1e-6f) & (sq < b * b * (1.0f - 1e-5f)) & (sq > a * a * (1.0f + 1e-5f)) & !out;
+    in = nice & (D_in > 0.0f) & (hn2 >= 1e-12f) & (N >= 1e-6f * Dp) & (N < b * b * Dm) & (N > a * a * Dp) & !out;
     und = !(out | in);
   }
 };

@@ -370,6 +370,14 @@ def main():
                 "(pitt_sac_score_device); FFMA filter kernel (previous dominant kernel) = 1.09 ms on the same job",
         "kernel_ms": k_ms, "algorithmic_flop_per_launch": float(n) * N_HYP * 6,
         "algorithmic_bytes_per_launch": n * 16 + N_HYP * (64 + 4),
+        # the same launch against the two ceilings of the schema (MEASURED_PEAKS.json), for completeness: it is neither
+        "as_hbm": {"bound": "hbm", "achieved": (n * 16 + N_HYP * (64 + 4)) / (k_ms * 1e-3) / 1e9,
+                   "peak": MEASURED.get("hbm_gbs", 6523.3), "unit": "GB/s",
+                   "frac": (n * 16 + N_HYP * (64 + 4)) / (k_ms * 1e-3) / 1e9 / MEASURED.get("hbm_gbs", 6523.3),
+                   "note": "every byte of the cloud is read once per launch (traffic == algorithmic bytes); 16 MB against 3e10 flop"},
+        "as_tensor": {"bound": "tensor", "achieved": evals_s * 64.0 / 1e12, "peak": bf16_peak, "unit": "TFLOP/s",
+                      "frac": evals_s * 64.0 / 1e12 / bf16_peak,
+                      "note": "executed BF16 MMA flop (32 MAC slots per evaluation), not algorithmic flop; ncu: tensor pipe 26 % active"},
     }
 
     # ---- secondary metric of BASELINE.json: segmented frames/s on 307k-point Kinect-shaped frames (C1/C4)

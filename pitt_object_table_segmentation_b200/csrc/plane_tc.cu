@@ -554,8 +554,6 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
       for (int hb = hb0; hb < hb1; ++hb, ++uc) {
         const int h = hb * TC_M + row;
         // this lane's hypothesis in the exact form, for re-evaluations (broadcast by shuffle, no memory latency there)
-        float4 myrec = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
-        if (h < H) myrec = __ldg(reinterpret_cast<const float4*>(recs[h].v));
         unsigned long long S1[2] = {0ull, 0ull}, S2[2] = {0ull, 0ull};
         uint32_t ra[32], rb[32];
         // An accumulator is handed back to its MMA warp as soon as this warp's 64 columns are in registers: the
@@ -614,15 +612,13 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
         int c = (int)rintf(s1);
         const bool redo = (s1 - s2) > 0.1f;
         unsigned m = __ballot_sync(0xffffffffu, redo);
-        if (stats && lane == 0) { n_seg += 32; n_redo += __popc(m); }
+        if (DBG && stats && lane == 0) { n_seg += 32; n_redo += __popc(m); }
         while (m) {  // rare
           const int L = __ffs(m) - 1;
           m &= m - 1;
           float4 r;
-          r.x = __shfl_sync(0xffffffffu, myrec.x, L);
-          r.y = __shfl_sync(0xffffffffu, myrec.y, L);
-          r.z = __shfl_sync(0xffffffffu, myrec.z, L);
-          r.w = __shfl_sync(0xffffffffu, myrec.w, L);
+          // (a segment is only re-evaluated for a real hypothesis: padding rows are certain outliers everywhere)
+          r = __ldg(reinterpret_cast<const float4*>(recs[hb * TC_M + q * 32 + L].v));
           const int e = tc_recount(s_raw + run0, len0, r, thr_up, lane) + tc_recount(s_raw + run1, len1, r, thr_up, lane);
           if (lane == L) c = e;
         }
@@ -634,7 +630,7 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
     if (DBG && stats && blockIdx.x == 0 && threadIdx.x == 0) {
       stats[168] = e_wait; stats[169] = 0; stats[170] = 0; stats[171] = uc; stats[172] = e_ld; stats[173] = e_math; stats[174] = e_tail;
     }
-    if (stats && lane == 0) {
+    if (DBG && stats && lane == 0) {
       atomicAdd(stats + 0, (unsigned long long)n_seg);
       if (n_redo) atomicAdd(stats + 1, (unsigned long long)n_redo);
     }
@@ -644,7 +640,7 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
   if (warp == TC_EPI_WARPS) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
   }
-  if (stats && threadIdx.x == 0) {  // per-CTA cycles and SM id (load-balance diagnostics)
+  if (DBG && stats && threadIdx.x == 0) {  // per-CTA cycles and SM id (load-balance diagnostics)
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
     stats[2 + blockIdx.x] = ((unsigned long long)smid << 48) | (unsigned long long)(clock64() - t_start);
@@ -721,7 +717,7 @@ int launch_score_plane_tc(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_re
   int grid = ctx->sm_count;
   if ((long long)grid > items) grid = (int)items;
   unsigned long long* st = g_plane_tc_collect_stats ? d_stats : nullptr;
-  const bool dbgk = g_plane_tc_dump || g_plane_tc_variant;
+  const bool dbgk = g_plane_tc_dump || g_plane_tc_variant || g_plane_tc_collect_stats;  // statistics live in the DBG kernel only
 #define TC_LAUNCH(DBGK)                                                                                                         \
   do {                                                                                                                          \
     static bool attr_set = false;                                                                                               \

@@ -483,36 +483,61 @@ def main():
             primitives[kind] = {"ms": pms, "evals_per_s": ev, "algorithmic_tflops": ev * flop / 1e12,
                                 "frac_of_ffma_peak": ev * flop / 1e12 / peak_ffma, "best_count": int(pc.max().item())}
             pcloud.release()
-        # the whole C3 job as the reference would run it: 64 clusters of 5 000 .. 50 000 points (32 cylinders, 32 cones), per
-        # cluster k = 50 normals + SACSegmentationFromNormals with setMaxIterations(10000) and PCL's adaptive stop + LM
-        # refinement + inlier list; clusters resident on the device, results (coefficients, inlier count) on the host
+    # ---- the whole C3 job as the reference would run it: 64 clusters of 5 000 .. 50 000 points (32 cylinders, 32 cones), per
+    # cluster k = 50 normals + SACSegmentationFromNormals with setMaxIterations(10000) and PCL's adaptive stop + LM refinement;
+    # clusters resident on the device, results (coefficients, inlier count) on the host. Clusters are independent units
+    # (SURVEY 8e): size-balanced over the ranks (greedy_balance), and on each GPU over 8 contexts = 8 host threads + streams.
+    if not args.no_primitives:
+        from concurrent.futures import ThreadPoolExecutor
+        from pitt_object_table_segmentation_b200 import scenes
         sizes = np.linspace(5000, 50000, 64).astype(int)
-        jobs = []
-        for i, sz in enumerate(sizes):
+        owner = sharding.greedy_balance([int(v) for v in sizes], world)
+        mine = [i for i in range(64) if owner[i] == rank]
+        n_c3 = 8
+        cctx = [pkg.Context(local_rank, seed=12345) for _ in range(n_c3)]
+        slot = sharding.greedy_balance([int(sizes[i]) for i in mine], n_c3)
+        jobs = [[] for _ in range(n_c3)]
+        for j, i in enumerate(mine):
             kind, model = (("cylinder", A.MODEL_CYLINDER), ("cone", A.MODEL_CONE))[i % 2]
-            cxyz, _ = scenes.primitive_cluster(kind, int(sz), 100 + i)
+            cxyz, _ = scenes.primitive_cluster(kind, int(sizes[i]), 100 + i)
             pj = pkg.default_sac_params(model)
             pj.max_iterations = 10000
-            jobs.append((ctx.stage(cxyz), pj))
+            jobs[slot[j]].append((cctx[slot[j]].stage(cxyz), pj))
 
-        def c3_pass():
+        def c3_worker(k):
             tot = 0
-            for cl, pj in jobs:
-                ctx.estimate_normals_device(cl, 50)
-                tot += ctx.sac_segment_count_only(cl, pj)["n_inliers"]
+            for cl, pj in jobs[k]:
+                cctx[k].estimate_normals_device(cl, 50)
+                tot += cctx[k].sac_segment_count_only(cl, pj)["n_inliers"]
             return tot
 
-        c3_pass()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        inl_total = c3_pass()
-        torch.cuda.synchronize()
-        c3_s = time.perf_counter() - t0
-        primitives["c3_job"] = {"clusters": 64, "points_total": int(sizes.sum()), "max_iterations": 10000, "seconds": c3_s,
-                                "clusters_per_s": 64 / c3_s, "inliers_total": int(inl_total),
-                                "note": "wall clock, one context, clusters one after the other (normals + segment each)"}
-        for cl, _ in jobs:
-            cl.release()
+        def c3_pass(pool):
+            return sum(pool.map(c3_worker, range(n_c3)))
+
+        with ThreadPoolExecutor(n_c3) as pool:
+            c3_pass(pool)
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            inl_mine = c3_pass(pool)
+            torch.cuda.synchronize()
+            c3_t = torch.tensor([time.perf_counter() - t0, float(inl_mine)], dtype=torch.float64, device=dev)
+        if world > 1:
+            c3_max = c3_t.clone()
+            dist.all_reduce(c3_max, op=dist.ReduceOp.MAX)
+            dist.all_reduce(c3_t, op=dist.ReduceOp.SUM)
+            c3_s, inl_total = float(c3_max[0].item()), int(c3_t[1].item())
+        else:
+            c3_s, inl_total = float(c3_t[0].item()), int(c3_t[1].item())
+        if primitives is not None:
+            primitives["c3_job"] = {"clusters": 64, "points_total": int(sizes.sum()), "max_iterations": 10000, "seconds": c3_s,
+                                    "clusters_per_s": 64 / c3_s, "inliers_total": inl_total, "contexts_per_gpu": n_c3,
+                                    "note": "wall clock, max over ranks; clusters size-balanced over ranks and contexts, "
+                                            "normals + segment() each"}
+        for k in range(n_c3):
+            for cl, _ in jobs[k]:
+                cl.release()
+            cctx[k].close()
 
     line = None
     if rank == 0:

@@ -346,3 +346,22 @@ def test_ros_shims_compile_against_the_c_abi():
     out = subprocess.run(["make", "-C", os.path.join(ROOT, "ros"), "check"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "syntax ok" in out.stdout
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` times the oracle on the host cores (no GPU needed) and prints ONE JSON line with the
+    keys the driver reads"""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "RANSAC hypothesis-point evals/s" and d["unit"] == "evals/s"
+    assert d["higher_is_better"] is True and d["value"] > 1e7 and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]

@@ -750,6 +750,61 @@ select_write_kernel(const float4* __restrict__ xyz, const float4* __restrict__ n
     if (m & (1u << j)) out[pos++] = first + j;
 }
 
+// Small clouds (the object clusters of a frame, <= SEL_SMALL_MAX points): record preparation, predicate and ordered
+// compaction in ONE single-CTA launch instead of four (prep_rec, count, scan, write). A frame makes 24 such selections.
+constexpr int SEL_SMALL_TPB = 1024;
+constexpr int SEL_SMALL_MAX = 16384;
+template <int MODEL>
+__global__ void __launch_bounds__(SEL_SMALL_TPB)
+select_small_kernel(const float4* __restrict__ xyz, const float4* __restrict__ nrm, int n, const float* __restrict__ coeffs, Limits L,
+                    ScoreParams sp, int* __restrict__ out, int* __restrict__ total) {
+  constexpr bool NEED_N = (MODEL == PITT_MODEL_CYLINDER || MODEL == PITT_MODEL_CONE);
+  __shared__ HypRec s_rec;
+  __shared__ int s_w[SEL_SMALL_TPB / 32];
+  __shared__ int s_base, s_tile_total;
+  static_assert(SEL_SMALL_TPB == 1024, "warp 0 scans exactly 32 warp counts");
+  if (threadIdx.x == 0) {
+    float mc[8];
+    for (int i = 0; i < 8; ++i) mc[i] = coeffs[i];
+    const bool valid = model_valid<MODEL>(L, mc);
+    make_rec<MODEL>(mc, valid, sp, s_rec);
+    s_base = 0;
+  }
+  __syncthreads();
+  RecRegs<MODEL> r;
+  r.load(&s_rec);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int tile = 0; tile < n; tile += SEL_SMALL_TPB) {
+    const int i = tile + threadIdx.x;
+    bool in = false;
+    if (i < n) {
+      const f3 pt = ld3(xyz, i);
+      const f3 nv = NEED_N ? ld3(nrm, i) : mk3(0.f, 0.f, 0.f);
+      in = r.inlier(pt, nv, sp);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, in);
+    if (lane == 0) s_w[warp] = __popc(m);
+    __syncthreads();
+    if (warp == 0) {  // warp 0 scans the 32 warp counts
+      const int v = s_w[lane];
+      int incl = v;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      s_w[lane] = incl - v;  // exclusive offsets
+      if (lane == 31) s_tile_total = incl;
+    }
+    __syncthreads();
+    const int base = s_base;
+    if (in) out[base + s_w[warp] + __popc(m & ((1u << lane) - 1u))] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) s_base = base + s_tile_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = s_base;
+}
+
 // =====================================================================================
 // K6: plane refinement = computeMeanAndCovarianceMatrix over the winner's inliers + eigen33.
 // The nine sums are accumulated in double by a fixed-shape tree (deterministic) and rounded once
@@ -965,6 +1020,7 @@ static int launch_score_generic(pitt_ctx* ctx, const pitt_cloud* c, const HypRec
 }
 
 int g_force_generic_plane = 0;  // test hook: 1 routes plane scoring through the generic kernel
+int g_select_no_fuse = 0;       // test hook: 1 keeps small selections on the four-launch path
 int g_score_mode = 0;  // test hook: 0 two-tier kernel for cylinder/cone, 1 generic score_kernel for every model
 int g_plane_mode = 0;  // test hook: 0 automatic (tensor path on large jobs), 1 exact packed kernel only,
                        // 2 FFMA filter + exact re-evaluation always, 3 tensor-core path (plane_tc.cu) always
@@ -1136,6 +1192,24 @@ int sac_select(pitt_ctx* ctx, const pitt_cloud* c, int model, const float* d_coe
                const ScoreParams& sp, int* d_out, int* d_total) {
   if (c->n <= 0) {
     PITT_CUDA(ctx, cudaMemsetAsync(d_total, 0, sizeof(int), ctx->stream));
+    return PITT_OK;
+  }
+  if (c->n <= SEL_SMALL_MAX && !g_select_no_fuse) {
+    switch (model) {
+      case PITT_MODEL_PLANE:
+        select_small_kernel<PITT_MODEL_PLANE><<<1, SEL_SMALL_TPB, 0, ctx->stream>>>(c->d_xyz, c->d_nrm, c->n, d_coeffs, L, sp, d_out, d_total);
+        break;
+      case PITT_MODEL_SPHERE:
+        select_small_kernel<PITT_MODEL_SPHERE><<<1, SEL_SMALL_TPB, 0, ctx->stream>>>(c->d_xyz, c->d_nrm, c->n, d_coeffs, L, sp, d_out, d_total);
+        break;
+      case PITT_MODEL_CYLINDER:
+        select_small_kernel<PITT_MODEL_CYLINDER><<<1, SEL_SMALL_TPB, 0, ctx->stream>>>(c->d_xyz, c->d_nrm, c->n, d_coeffs, L, sp, d_out, d_total);
+        break;
+      default:
+        select_small_kernel<PITT_MODEL_CONE><<<1, SEL_SMALL_TPB, 0, ctx->stream>>>(c->d_xyz, c->d_nrm, c->n, d_coeffs, L, sp, d_out, d_total);
+        break;
+    }
+    PITT_LAUNCH_CHECK(ctx, "select_small_kernel");
     return PITT_OK;
   }
   HypRec* d_rec = nullptr;

@@ -53,6 +53,7 @@ extern int g_force_generic_plane;
 extern int g_plane_mode;
 bool plane_job_takes_tensor_path(int n, int H);
 extern int g_score_mode;
+extern int g_select_no_fuse;
 extern int g_lm_cluster_min;
 extern unsigned long long g_plane_filter_stats[2];
 extern int g_plane_filter_collect_stats;

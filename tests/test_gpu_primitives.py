@@ -294,3 +294,34 @@ def test_c3_segment_with_10000_iterations(ctx, oracle, model, n, outliers):
         assert gi.iterations > 200 and (model == A.MODEL_CYLINDER or gi.iterations + gi.skipped > 256)  # beyond the first batch
     else:
         assert gi.iterations < 256 and gi.hypotheses <= 256  # ... and here inside it: 256 hypotheses scored, not 10 001
+
+
+@pytest.mark.parametrize("model", [A.MODEL_PLANE, A.MODEL_SPHERE, A.MODEL_CYLINDER, A.MODEL_CONE])
+@pytest.mark.parametrize("n", [5, 31, 1023, 1024, 1025, 5000, 16384])
+def test_fused_select_of_small_clouds(ctx, oracle, model, n):
+    """selectWithinDistance on clouds of <= 16384 points is one single-CTA launch (record preparation + predicate + ordered
+    compaction); same ascending index list as the four-launch path and the oracle"""
+    xyz, _ = scenes.primitive_cluster(KINDS[model], max(n, 64), 300 + model)
+    xyz = np.ascontiguousarray(xyz[:n])
+    nrm = oracle.estimate_normals(xyz, min(50, n), (0.0, 0.0, 0.0)) if n >= 3 else np.zeros((n, 4), np.float32)
+    cloud = ctx.stage(xyz, normals=nrm)
+    p = pkg.default_sac_params(model)
+    p0 = p.copy()
+    p0.optimize = 0
+    if n >= 1000:
+        co = oracle.sac_segment(xyz, nrm, p0)["coeffs"]  # a good model of this very cloud
+    else:
+        big, _ = scenes.primitive_cluster(KINDS[model], 4000, 300 + model)
+        bn = oracle.estimate_normals(big, 50, (0.0, 0.0, 0.0))
+        co = oracle.sac_segment(big, bn, p0)["coeffs"]  # some model of the same kind
+    got = ctx.sac_select(cloud, p, co)
+    ctx.lib.pitt_debug_select_no_fuse(1)
+    try:
+        unfused = ctx.sac_select(cloud, p, co)
+    finally:
+        ctx.lib.pitt_debug_select_no_fuse(0)
+    want = oracle.sac_select(xyz, nrm, p, co)
+    assert np.array_equal(got, unfused)
+    assert np.array_equal(got, want)
+    if n >= 1000:
+        assert len(want) > n // 8

@@ -365,15 +365,15 @@ int pitt_sac_segment_host(pitt_ctx* ctx, const void* xyz, int stride_bytes, int 
     g_stream_chunks = v ? std::max(1, std::min(8, atoi(v))) : 0;
   }
   const int K_env = g_stream_chunks;
-  // Large scoring jobs take the tensor path: ONE launch whose CTAs poll per-chunk arrival flags (8 chunks; a chunk costs
+  // Large scoring jobs take the tensor path: ONE launch whose CTAs poll per-chunk arrival flags (16 chunks; a chunk costs
   // nothing but a 4-byte flag copy there), so only the first chunk's copy is exposed.
   const int H_first = p->stop == PITT_STOP_ALL_H ? p->max_iterations : p->max_iterations + 1;
   const bool single_launch = K_env == 0 && plane_job_takes_tensor_path(n, H_first) &&
                              (p->sampler != PITT_SAMPLER_REPLAY || p->replay_count >= H_first);
-  const int K_equal = single_launch ? 8 : (K_env > 0 ? K_env : std::max(1, std::min(8, n / (8 << 20))));
+  const int K_equal = single_launch ? 16 : (K_env > 0 ? K_env : std::max(1, std::min(8, n / (8 << 20))));
   if (!ctx->copy_stream) {
     PITT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    for (int k = 0; k < 8; ++k) PITT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_chunk[k], cudaEventDisableTiming));
+    for (int k = 0; k < 16; ++k) PITT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_chunk[k], cudaEventDisableTiming));
     PITT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_copy_gate, cudaEventDisableTiming));
     PITT_CUDA(ctx, cudaMalloc((void**)&ctx->d_ready, 16 * sizeof(int)));
     PITT_CUDA(ctx, cudaMallocHost((void**)&ctx->h_one, sizeof(int)));

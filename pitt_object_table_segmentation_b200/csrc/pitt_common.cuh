@@ -44,7 +44,7 @@ struct pitt_ctx {
   cudaEvent_t ev_fan = nullptr;
   // pitt_sac_segment_host: the cloud travels host -> device in chunks on a second stream while the first chunks are scored
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_chunk[16] = {};
   cudaEvent_t ev_copy_gate = nullptr;
   // PITT_BLOCKING_SYNC=1: host waits sleep on an event (cudaEventBlockingSync) instead of spinning; for frame streams
   // with more host threads than cores (16 contexts x 8 ranks on one box)
@@ -65,7 +65,7 @@ struct pitt_cloud {
   // streaming stage (pitt_sac_segment_host only): chunk k is on the device once
   // ctx->ev_chunk[k] has fired; h_src = the caller's buffer (point_step 16), valid for the duration of the fused call
   mutable int stream_chunks = 0;
-  int stream_off[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // chunk k = points [stream_off[k], stream_off[k + 1])
+  int stream_off[17] = {};  // chunk k = points [stream_off[k], stream_off[k + 1])
   const float* h_src = nullptr;
   const int* d_ready = nullptr;  // per-chunk arrival flags for the single-launch tensor path (equal chunks of stream_off[1] points)
 };

@@ -333,9 +333,25 @@ def main():
         ctx.sac_score_device(cloud, p, d_samples.data_ptr(), N_HYP, d_counts.data_ptr())
 
     k_ms, _ = timed(kernel_only, max(5, min(args.steps, 20)), 3)
+    # the dominant kernel alone: the library brackets the plane_tc_kernel launch with two CUDA events on its stream
+    ctx.lib.pitt_debug_plane_tc_kernel_ms.restype = C.c_double
+    ctx.lib.pitt_debug_plane_tc_kernel_ms.argtypes = [C.c_void_p]
+    ctx.lib.pitt_debug_plane_tc_time_kernel(1)
+    kk = []
+    for _ in range(3 + max(5, min(args.steps, 20))):
+        l2_flush.zero_()
+        kernel_only()
+        kk.append(float(ctx.lib.pitt_debug_plane_tc_kernel_ms(ctx.handle)))
+    ctx.lib.pitt_debug_plane_tc_time_kernel(0)
+    kk = [v for v in kk[3:] if v > 0]
+    kern_ms = float(np.mean(kk)) if kk else k_ms
+    if world > 1:
+        tk = torch.tensor([kern_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+        kern_ms = float(tk.item())
     peak_unfused = ctx.fp32_peak(1)
     peak_ffma = ctx.fp32_peak(0)
-    achieved = float(n) * N_HYP * FLOP_PER_EVAL / (k_ms * 1e-3) / 1e12
+    achieved = float(n) * N_HYP * FLOP_PER_EVAL / (kern_ms * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_plane_tc_traffic.json")
     if os.path.exists(tpath):
@@ -351,7 +367,7 @@ def main():
     # counts the ALGORITHMIC 6 flop per evaluation of SURVEY 8d; the fraction of the kernel's own instruction-mix floor
     # (tools/ldtm_probe.cu: 3.125 cycles per evaluation per sub-partition once the TMEM loads are included) and the
     # tensor-pipe fraction are reported beside it.
-    evals_s = float(n) * N_HYP / (k_ms * 1e-3)
+    evals_s = float(n) * N_HYP / (kern_ms * 1e-3)
     fma_ops_peak = peak_ffma * 1e12 / 2.0           # FMA-pipe operations per second (one FFMA = 2 flop)
     bf16_peak = MEASURED.get("bf16_tflops", 1659.2)
     sm_clock_hz = 1.965e9
@@ -368,14 +384,17 @@ def main():
         "tensor_bf16_mac_slots_per_eval": 32, "tensor_tflops": evals_s * 64.0 / 1e12,
         "frac_tensor_of_measured_bf16": evals_s * 64.0 / 1e12 / bf16_peak,
         "note": "dot products on tcgen05 (2 chained 128x256x16 BF16 MMAs per tile on exact 3-piece splits, FP32 accumulators "
-                "in TMEM), CUDA cores run the saturating-count epilogue; kernel_ms brackets estimate + set-up + plane_tc_kernel "
-                "(pitt_sac_score_device); FFMA filter kernel (previous dominant kernel) = 1.09 ms on the same job",
-        "kernel_ms": k_ms, "algorithmic_flop_per_launch": float(n) * N_HYP * 6,
+                "in TMEM), CUDA cores run the saturating-count epilogue; FFMA filter kernel (previous dominant kernel) = 1.09 ms on "
+                "the same job",
+        "kernel_ms": kern_ms, "kernel_ms_note": "plane_tc_kernel alone: CUDA events recorded by the library around that launch, "
+                                                "mean over the timed calls, L2 flushed before each",
+        "score_call_ms": k_ms, "score_call_note": "estimate + set-up kernels + plane_tc_kernel (pitt_sac_score_device)",
+        "algorithmic_flop_per_launch": float(n) * N_HYP * 6,
         "algorithmic_bytes_per_launch": n * 16 + N_HYP * (64 + 4),
         # the same launch against the two ceilings of the schema (MEASURED_PEAKS.json), for completeness: it is neither
-        "as_hbm": {"bound": "hbm", "achieved": (n * 16 + N_HYP * (64 + 4)) / (k_ms * 1e-3) / 1e9,
+        "as_hbm": {"bound": "hbm", "achieved": (n * 16 + N_HYP * (64 + 4)) / (kern_ms * 1e-3) / 1e9,
                    "peak": MEASURED.get("hbm_gbs", 6523.3), "unit": "GB/s",
-                   "frac": (n * 16 + N_HYP * (64 + 4)) / (k_ms * 1e-3) / 1e9 / MEASURED.get("hbm_gbs", 6523.3),
+                   "frac": (n * 16 + N_HYP * (64 + 4)) / (kern_ms * 1e-3) / 1e9 / MEASURED.get("hbm_gbs", 6523.3),
                    "note": "every byte of the cloud is read once per launch (traffic == algorithmic bytes); 16 MB against 3e10 flop"},
         "as_tensor": {"bound": "tensor", "achieved": evals_s * 64.0 / 1e12, "peak": bf16_peak, "unit": "TFLOP/s",
                       "frac": evals_s * 64.0 / 1e12 / bf16_peak,

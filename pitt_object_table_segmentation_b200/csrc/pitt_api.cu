@@ -84,6 +84,7 @@ void pitt_destroy(pitt_ctx* ctx) {
   if (ctx->ev_copy_gate) cudaEventDestroy(ctx->ev_copy_gate);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
+  if (ctx->ev_k0) { cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1); }
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -690,6 +691,16 @@ int pitt_debug_plane_tc_dump(int enable, float* out /*128*256 + 2, nullable*/) {
 }
 void pitt_debug_plane_tc_acc_ulps(float ulps) { g_plane_tc_acc_ulps = ulps; }
 void pitt_debug_plane_tc_variant(int v) { g_plane_tc_variant = v; }
+/* enable: every tensor-path scoring call records two CUDA events around the plane_tc_kernel launch alone (on the
+ * context's stream); pitt_debug_plane_tc_kernel_ms waits for the last pair and returns the kernel's duration (< 0: none) */
+void pitt_debug_plane_tc_time_kernel(int enable) { g_plane_tc_time_kernel = enable; }
+double pitt_debug_plane_tc_kernel_ms(pitt_ctx* ctx) {
+  if (!ctx || !ctx->ev_k0) return -1.0;
+  float ms = -1.0f;
+  if (cudaEventSynchronize(ctx->ev_k1) != cudaSuccess) return -1.0;
+  if (cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
 void pitt_debug_plane_tc_nwq(int v) { g_plane_tc_nwq = v; }
 
 }  // extern "C"

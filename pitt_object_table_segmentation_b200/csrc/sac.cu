@@ -350,6 +350,114 @@ plane_score_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restri
 }
 
 // =====================================================================================
+// K3s: sphere scoring for large jobs, same structure as plane_score_kernel: lanes = hypotheses (KH per
+// thread as KH/2 packed pairs), points broadcast from shared memory, persistent CTAs pulling
+// (hypothesis block, point tile) items, no reduction until the final RED per hypothesis.
+// Per evaluation: d2 = (dx*dx + dy*dy) + dz*dz in PCL's operation order (8 separately rounded FP32
+// operations = 4 packed instructions) and the interval test d_lo <= d2 <= d_hi of
+// RecRegs<PITT_MODEL_SPHERE>::inlier (two chained FSETP + a predicated IADD3 on the ALU pipe).
+// NaN points and invalid (all-NaN) hypotheses compare false. Counts are identical to
+// score_kernel<PITT_MODEL_SPHERE> (test_sphere_packed_kernel_equals_generic).
+// =====================================================================================
+// cnt += (lo <= a && a <= hi)
+__device__ __forceinline__ void count_if_within(int& cnt, float a, float lo, float hi) {
+  asm("{\n\t.reg .pred p;\n\tsetp.ge.f32 p, %1, %2;\n\tsetp.le.and.f32 p, %1, %3, p;\n\t@p add.s32 %0, %0, 1;\n\t}"
+      : "+r"(cnt) : "f"(a), "f"(lo), "f"(hi));
+}
+
+template <int KH, int TPB, int TILE>
+__global__ void __launch_bounds__(TPB)
+sphere_score_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict__ recs, int H, int n_ptiles,
+                    int n_items, float one_rt, int* __restrict__ work_counter, int* __restrict__ counts) {
+  __shared__ __align__(16) float4 s_pts[2][TILE];
+  __shared__ int s_item[2];
+  const unsigned long long ONE = pack2(one_rt, one_rt);
+  constexpr int KP = KH / 2;
+  unsigned long long NX[KP], NY[KP], NZ[KP];  // minus the centre: x - cx == x + (-cx) bit for bit
+  float lo[KH], hi[KH];
+  int cnt[KH];
+  int cur_hb = -1;
+  auto flush = [&]() {
+    if (cur_hb < 0) return;
+    const int h_base = (cur_hb * TPB + threadIdx.x) * KH;
+#pragma unroll
+    for (int k = 0; k < KH; ++k)
+      if (h_base + k < H && cnt[k]) atomicAdd(&counts[h_base + k], cnt[k]);
+  };
+  auto load_hyps = [&](int hb) {
+    const int h_base = (hb * TPB + threadIdx.x) * KH;
+    const float nanv = CUDART_NAN_F;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      float4 r0 = make_float4(nanv, nanv, nanv, nanv), r1 = r0;
+      float2 i0 = make_float2(nanv, nanv), i1 = i0;
+      if (h_base + 2 * k < H) {
+        r0 = __ldg(reinterpret_cast<const float4*>(recs[h_base + 2 * k].v));
+        i0 = __ldg(reinterpret_cast<const float2*>(recs[h_base + 2 * k].v + 4));
+      }
+      if (h_base + 2 * k + 1 < H) {
+        r1 = __ldg(reinterpret_cast<const float4*>(recs[h_base + 2 * k + 1].v));
+        i1 = __ldg(reinterpret_cast<const float2*>(recs[h_base + 2 * k + 1].v + 4));
+      }
+      NX[k] = pack2(-r0.x, -r1.x); NY[k] = pack2(-r0.y, -r1.y); NZ[k] = pack2(-r0.z, -r1.z);
+      lo[2 * k] = i0.x; hi[2 * k] = i0.y; lo[2 * k + 1] = i1.x; hi[2 * k + 1] = i1.y;
+      cnt[2 * k] = 0; cnt[2 * k + 1] = 0;
+    }
+    cur_hb = hb;
+  };
+  auto stage = [&](int item, int buf) {
+    if (item < n_items) {
+      const int base = (item % n_ptiles) * TILE;
+      for (int i = threadIdx.x; i < TILE; i += TPB) {
+        int gi = base + i;
+        if (gi < n) {
+          unsigned saddr = (unsigned)__cvta_generic_to_shared(&s_pts[buf][i]);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(xyz + gi));
+        } else {
+          s_pts[buf][i] = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;");
+  };
+  if (threadIdx.x == 0) s_item[0] = atomicAdd(work_counter, 1);
+  __syncthreads();
+  int item = s_item[0];
+  stage(item, 0);
+  int it = 0;
+  while (item < n_items) {
+    if (threadIdx.x == 0) s_item[(it + 1) & 1] = atomicAdd(work_counter, 1);
+    asm volatile("cp.async.wait_group 0;");
+    __syncthreads();
+    const int next = s_item[(it + 1) & 1];
+    stage(next, (it + 1) & 1);
+    const int hb = item / n_ptiles;
+    if (hb != cur_hb) {
+      flush();
+      load_hyps(hb);
+    }
+    const float4* tile = s_pts[it & 1];
+#pragma unroll 2
+    for (int i = 0; i < TILE; ++i) {
+      float4 p = tile[i];  // LDS.128 broadcast
+      unsigned long long PX = pack2(p.x, p.x), PY = pack2(p.y, p.y), PZ = pack2(p.z, p.z);
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        unsigned long long dx = add2(PX, NX[k]), dy = add2(PY, NY[k]), dz = add2(PZ, NZ[k]);
+        // (dx*dx + dy*dy) + dz*dz with every product and sum rounded on its own (see fadd2_exact)
+        unsigned long long d2 = fadd2_exact(fadd2_exact(mul2(dx, dx), mul2(dy, dy), ONE), mul2(dz, dz), ONE);
+        count_if_within(cnt[2 * k], lo32(d2), lo[2 * k], hi[2 * k]);
+        count_if_within(cnt[2 * k + 1], hi32(d2), lo[2 * k + 1], hi[2 * k + 1]);
+      }
+    }
+    item = next;
+    ++it;
+  }
+  asm volatile("cp.async.wait_group 0;");
+  flush();
+}
+
+// =====================================================================================
 // K3f: plane scoring with an FFMA filter and exact re-evaluation of the uncertain evaluations.
 //
 // The exact predicate |fl(fl(fl(a x)+fl(c z)) + fl(fl(b y)+d))| < thr needs 6 separately rounded
@@ -1021,7 +1129,7 @@ static int launch_score_generic(pitt_ctx* ctx, const pitt_cloud* c, const HypRec
 
 int g_force_generic_plane = 0;  // test hook: 1 routes plane scoring through the generic kernel
 int g_select_no_fuse = 0;       // test hook: 1 keeps small selections on the four-launch path
-int g_score_mode = 0;  // test hook: 0 two-tier kernel for cylinder/cone, 1 generic score_kernel for every model
+int g_score_mode = 0;  // test hook (2 / 3: sphere packed kernel with 512- / 128-point tiles): 0 two-tier kernel for cylinder/cone, 1 generic score_kernel for every model
 int g_plane_mode = 0;  // test hook: 0 automatic (tensor path on large jobs), 1 exact packed kernel only,
                        // 2 FFMA filter + exact re-evaluation always, 3 tensor-core path (plane_tc.cu) always
 int launch_score_plane_tc(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_recs, int H, const ScoreParams& sp, int* d_counts,
@@ -1104,6 +1212,38 @@ static int launch_score_plane_packed(pitt_ctx* ctx, const pitt_cloud* c, const H
 }
 
 
+template <int TILE>
+static int launch_score_sphere_packed_t(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_recs, int H, int* d_counts) {
+  constexpr int KH = 8, TPB = 128;
+  const int n = c->n;
+  const int hblocks = cdiv(H, KH * TPB);
+  const int n_ptiles = cdiv(n, TILE);
+  const long long items = (long long)hblocks * n_ptiles;
+  if (items > INT_MAX) return fail(ctx, PITT_ERR_INVALID, "sphere scoring: too many work items");
+  int* d_work = nullptr;
+  PITT_TRY(arena_alloc(ctx, 1, &d_work));
+  PITT_CUDA(ctx, cudaMemsetAsync(d_work, 0, sizeof(int), ctx->stream));
+  static int ctas = 0;
+  if (!ctas) {
+    PITT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, sphere_score_kernel<KH, TPB, TILE>, TPB, 0));
+    if (ctas < 1) ctas = 1;
+  }
+  int grid = ctx->sm_count * ctas;
+  if ((long long)grid > items) grid = (int)items;
+  sphere_score_kernel<KH, TPB, TILE><<<grid, TPB, 0, ctx->stream>>>(c->d_xyz, n, d_recs, H, n_ptiles, (int)items, 1.0f, d_work, d_counts);
+  PITT_LAUNCH_CHECK(ctx, "sphere_score_kernel");
+  return PITT_OK;
+}
+// Tile size (measured, 10 000 hypotheses): jobs of at most ~4 items per SM run as one partial wave of 512-point items
+// (20 000 points: 0.099 ms against 0.116); beyond that 128-point items, several per persistent CTA with the next tile
+// prefetched, leave a smaller last round (50 000 points: 0.218 against 0.231; 500 000 points: no difference)
+static int launch_score_sphere_packed(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_recs, int H, int* d_counts) {
+  const long long items512 = (long long)cdiv(H, 1024) * cdiv(c->n, 512);
+  const bool small_tiles = g_score_mode == 3 || (g_score_mode != 2 && items512 > 4LL * ctx->sm_count);
+  if (small_tiles) return launch_score_sphere_packed_t<128>(ctx, c, d_recs, H, d_counts);
+  return launch_score_sphere_packed_t<512>(ctx, c, d_recs, H, d_counts);
+}
+
 // a consumer that needs the whole cloud at once
 static int stream_complete(pitt_ctx* ctx, const pitt_cloud* c) {
   for (int k = 0; k < c->stream_chunks; ++k) PITT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[k], 0));
@@ -1157,7 +1297,12 @@ int sac_score(pitt_ctx* ctx, const pitt_cloud* c, int model, const HypRec* d_rec
     case PITT_MODEL_PLANE:
       if (H >= 256 && !g_force_generic_plane) return launch_score_plane_packed(ctx, c, d_recs, H, sp, d_counts);
       return launch_score_generic<PITT_MODEL_PLANE, 8, false>(ctx, c, d_recs, H, sp, d_counts);
-    case PITT_MODEL_SPHERE: return launch_score_generic<PITT_MODEL_SPHERE, 8, false>(ctx, c, d_recs, H, sp, d_counts);
+    case PITT_MODEL_SPHERE:
+      // large jobs (C3 clusters x 10 000 hypotheses): lanes = hypotheses, no per-(warp, hypothesis) reduction; below 1e8
+      // evaluations the generic kernel is as fast (5 000 x 10 000: 0.048 ms against 0.051)
+      if (g_score_mode >= 2 || (g_score_mode == 0 && H >= 512 && (double)c->n * (double)H >= 1.0e8))
+        return launch_score_sphere_packed(ctx, c, d_recs, H, d_counts);
+      return launch_score_generic<PITT_MODEL_SPHERE, 8, false>(ctx, c, d_recs, H, sp, d_counts);
     case PITT_MODEL_CYLINDER:
       if (g_score_mode == 1) return launch_score_generic<PITT_MODEL_CYLINDER, 2, false>(ctx, c, d_recs, H, sp, d_counts);
       if (c->n < 4096) return launch_score_generic<PITT_MODEL_CYLINDER, 1, true>(ctx, c, d_recs, H, sp, d_counts);

@@ -325,3 +325,45 @@ def test_fused_select_of_small_clouds(ctx, oracle, model, n):
     assert np.array_equal(got, want)
     if n >= 1000:
         assert len(want) > n // 8
+
+
+@pytest.mark.parametrize("n,H,mode", [(100001, 1003, 0), (200001, 512, 0), (33000, 4097, 0), (40000, 1003, 2), (40000, 1003, 3)])
+def test_sphere_packed_kernel_equals_generic(ctx, oracle, n, H, mode):
+    """large sphere jobs (n x H >= 1e8, H >= 512) take sphere_score_kernel (lanes = hypotheses, packed f32x2): counts must
+    equal the generic kernel's and the oracle's for every hypothesis; ragged n and H, NaN / infinite points,
+    half of the points moved onto the two surfaces |d - r| = thr of the true sphere"""
+    rng = np.random.default_rng(n + H)
+    xyz, truth = scenes.primitive_cluster("sphere", n, 3)
+    p = pkg.default_sac_params(A.MODEL_SPHERE)
+    thr = p.distance_threshold
+    P = xyz[:, :3].astype(np.float64)
+    sol = np.linalg.lstsq(np.c_[2.0 * P, np.ones(n)], (P * P).sum(axis=1), rcond=None)[0]  # algebraic sphere fit
+    centre = sol[:3]
+    v = P - centre
+    r = np.linalg.norm(v, axis=1, keepdims=True)
+    r0 = float(np.median(r))
+    assert abs(r0 - truth["radius"]) < 1e-3
+    k = n // 2
+    target = r0 + rng.choice([-1.0, 1.0], (k, 1)) * thr * (1.0 + rng.integers(-4, 5, (k, 1)) * 6e-8)
+    xyz[:k, :3] = (centre + v[:k] / r[:k] * target).astype(np.float32)
+    xyz[k] = (np.nan, 0.0, 0.0, 1.0)
+    xyz[k + 1] = (np.inf, 0.1, 0.2, 1.0)
+    xyz[k + 2] = (1e20, -1e20, 3.0, 1.0)
+    cloud = ctx.stage(xyz)
+    samples = oracle.pcl_sample_stream(xyz, A.MODEL_SPHERE, H)
+    samples[5] = samples[5][0]            # degenerate sample: invalid hypothesis
+    samples[H - 1] = (k, 1, 2, 3)         # through the NaN point
+    ctx.lib.pitt_debug_score_mode(mode)  # 0: automatic (packed kernel at this size), 2 / 3: packed kernel, 512- / 128-point tiles
+    try:
+        c2, _, v2 = ctx.sac_score(cloud, p, samples)
+        ctx.lib.pitt_debug_score_mode(1)  # generic kernel
+        c1, _, v1 = ctx.sac_score(cloud, p, samples)
+    finally:
+        ctx.lib.pitt_debug_score_mode(0)
+    assert np.array_equal(v2, v1)
+    assert np.array_equal(c2, c1)
+    c_cpu, _, v_cpu = oracle.sac_score(xyz, None, p, samples)
+    assert np.array_equal(c2, c_cpu) and np.array_equal(v2, v_cpu)
+    assert c2[5] == 0 and c2[H - 1] == 0
+    assert c2.max() > n // 4
+    cloud.release()

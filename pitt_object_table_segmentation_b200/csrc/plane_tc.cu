@@ -506,20 +506,30 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
         tc_fence_after();
         if (DBG) ta += clock64() - c0;
         const uint32_t a_addr = s_base + TC_OFF_A + st * TC_A_BLOCK_BYTES;
+        // Everything the issue needs is in registers BEFORE the wait for the drained accumulator: the epilogue warps wait for
+        // this warp's MMAs (wake-up + issue + 256 tensor cycles + commit), and this warp shares its issue port with four of them
+        uint64_t da[TC_MMAS], db[TC_MMAS];
+#pragma unroll
+        for (int j = 0; j < TC_MMAS; ++j) {
+          da[j] = tc_smem_desc(a_addr + j * TC_A_MMA_BYTES);
+          db[j] = tc_smem_desc(b_addr + j * TC_B_MMA_BYTES);
+          asm volatile("" : "+l"(da[j]), "+l"(db[j]));
+        }
+        const uint32_t bar_full = BAR(TC_BAR_FULL + t), bar_aempty = BAR(TC_BAR_AEMPTY + st), d_tmem = tmem + t * TC_N;
+        const bool leader = elect_one();
         if (DBG) c0 = clock64();
         mbar_wait(BAR(TC_BAR_EMPTY + t), (ac & 1u) ^ 1u);  // every epilogue warp has the previous contents in registers
         tc_fence_after();
         long long c1 = DBG ? clock64() : 0;
         long long c2 = 0;
-        if (elect_one()) {
+        if (leader) {
 #pragma unroll
           for (int j = 0; j < TC_MMAS; ++j)
             if (!DBG || j == 0 || !(variant & 2))
-              tc_mma_bf16(tmem + t * TC_N, tc_smem_desc(a_addr + j * TC_A_MMA_BYTES), tc_smem_desc(b_addr + j * TC_B_MMA_BYTES),
-                          TC_IDESC, j > 0 ? 1u : 0u);
+              tc_mma_bf16(d_tmem, da[j], db[j], TC_IDESC, j > 0 ? 1u : 0u);
           if (DBG) c2 = clock64();
-          tc_commit(BAR(TC_BAR_FULL + t));
-          tc_commit(BAR(TC_BAR_AEMPTY + st));  // the hypothesis stage is free once the MMAs of both warps have read it
+          tc_commit(bar_full);
+          tc_commit(bar_aempty);  // the hypothesis stage is free once the MMAs of both warps have read it
         }
         __syncwarp();
         if (DBG) { tw += c1 - c0; tm += c2 - c1; tcm += clock64() - c2; }

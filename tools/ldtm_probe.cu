@@ -47,12 +47,24 @@ __device__ __forceinline__ void math32(const unsigned (&r)[32], float C, unsigne
     S2[(i >> 1) & 1] = fma2(U, U, S2[(i >> 1) & 1]);
   }
 }
+// variant: S1 = sum u as before (FADD2), certificate sum on the ALU pipe: SI += bits(u0) + bits(u1) (one IADD3 per two evaluations)
+__device__ __forceinline__ void math32_int(const unsigned (&r)[32], float C, unsigned long long (&S1)[2], unsigned (&SI)[2]) {
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    float u0, u1;
+    asm("add.sat.f32 %0, %1, %2;" : "=f"(u0) : "f"(-fabsf(__uint_as_float(r[i]))), "f"(C));
+    asm("add.sat.f32 %0, %1, %2;" : "=f"(u1) : "f"(-fabsf(__uint_as_float(r[i + 1]))), "f"(C));
+    unsigned long long U = pack2(u0, u1);
+    S1[(i >> 1) & 1] = add2(S1[(i >> 1) & 1], U);
+    SI[(i >> 1) & 1] = SI[(i >> 1) & 1] + __float_as_uint(u0) + __float_as_uint(u1);
+  }
+}
 // MODE 0: loads only   1: arithmetic only (registers)   2: load 64 columns, wait, arithmetic on them (free-running warps)
 // MODE 3: software pipeline inside the warp (load of the next 32 columns in flight under the arithmetic of the current 32)
 // MODE 4: as 2, warps of a sub-partition start staggered by a quarter of the iteration
 // MODE 5: as 2 with x16 loads (4 per 64 columns)
 template <int MODE>
-__global__ void __launch_bounds__(512, 1) probe(float* out, int iters, float C, int stagger) {
+__global__ void __launch_bounds__(MODE == 11 ? 1024 : 512, 1) probe(float* out, int iters, float C, int stagger) {
   __shared__ unsigned s_tmem;
   const int warp = threadIdx.x >> 5;
   if (warp == 0) {
@@ -68,6 +80,7 @@ __global__ void __launch_bounds__(512, 1) probe(float* out, int iters, float C, 
   unsigned ra[32], rb[32];
   unsigned long long S1[2] = {0, 0}, S2[2] = {0, 0};
   unsigned x = 0;
+  unsigned SI[2] = {0, 0};
 #pragma unroll
   for (int i = 0; i < 32; ++i) { ra[i] = 0x3f000000u + i; rb[i] = 0x3e000000u + i; }
   if (MODE == 4) { long long t = clock64(); while (clock64() - t < (long long)j * stagger) {} }
@@ -109,6 +122,17 @@ __global__ void __launch_bounds__(512, 1) probe(float* out, int iters, float C, 
     } else if (MODE == 8) {  // load 32, wait, arithmetic 32 (finer interleave)
       ld32(ra, taddr + col); ld_wait(ra); math32(ra, C, S1, S2);
       ld32(rb, taddr + col + 32); ld_wait(rb); math32(rb, C, S1, S2);
+    } else if (MODE == 9) {   // arithmetic only, integer certificate
+#pragma unroll
+      for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(ra[i]), "+r"(rb[i]));
+      math32_int(ra, C, S1, SI); math32_int(rb, C, S1, SI);
+    } else if (MODE == 10) {  // load 64, wait, arithmetic with the integer certificate
+      ld32(ra, taddr + col); ld32(rb, taddr + col + 32);
+      ld_wait(ra); ld_wait(rb);
+      math32_int(ra, C, S1, SI); math32_int(rb, C, S1, SI);
+    } else if (MODE == 11) {  // 32 columns per step (one register block): runs with up to 8 warps per sub-partition
+      ld32(ra, taddr + col); ld_wait(ra); math32(ra, C, S1, S2);
+      ld32(ra, taddr + col + 32); ld_wait(ra); math32(ra, C, S1, S2);
     } else if (MODE == 3) {
       ld32(rb, taddr + col + 32);
       math32(ra, C, S1, S2);
@@ -119,7 +143,7 @@ __global__ void __launch_bounds__(512, 1) probe(float* out, int iters, float C, 
     }
   }
   long long t1 = clock64();
-  float acc = __uint_as_float(x);
+  float acc = __uint_as_float(x ^ SI[0] ^ SI[1]);
 #pragma unroll
   for (int k = 0; k < 2; ++k) acc += __uint_as_float((unsigned)S1[k]) + __uint_as_float((unsigned)(S2[k] >> 32));
   out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
@@ -160,6 +184,11 @@ int main() {
   run<6>("x8 loads (8 per 64 columns)", out, 512);
   run<7>("2 warps load only + 2 warps arithmetic only", out, 512);
   run<8>("load 32, wait, arithmetic 32", out, 512);
+  run<11>("load 32, wait, arithmetic 32, one register block", out, 512);
+  run<11>("load 32, wait, arithmetic 32, one register block", out, 768);
+  run<11>("load 32, wait, arithmetic 32, one register block", out, 1024);
+  run<9>("arithmetic only, IADD3 certificate", out, 512);
+  run<10>("load 64, wait, arithmetic, IADD3 certificate", out, 512);
   run<4>("free running, staggered start 100", out, 512, 100);
   run<4>("free running, staggered start 300", out, 512, 300);
   return 0;

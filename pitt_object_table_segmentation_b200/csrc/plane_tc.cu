@@ -40,10 +40,13 @@
 namespace pitt {
 
 constexpr int TC_M = 128;                       // hypotheses per block (UMMA M, TMEM lanes)
-constexpr int TC_N = 256;                       // points per MMA (UMMA N) = columns of one accumulator
+#ifndef TC_E24
+#define TC_E24 0  // 1: 24 epilogue warps (six per sub-partition) on two 192-column accumulators, 32 columns per warp and phase
+#endif            // 0: 16 epilogue warps on two 256-column accumulators, 64 columns per warp and phase
+constexpr int TC_N = TC_E24 ? 192 : 256;        // points per MMA (UMMA N) = columns of one accumulator
 constexpr int TC_PHASES = 2;                    // accumulators in TMEM = tiles per point chunk
 constexpr int TC_CHUNK = TC_N * TC_PHASES;      // 512 points stationary in shared memory
-constexpr int TC_RUN = 64;                      // columns one epilogue warp takes from an accumulator
+constexpr int TC_RUN = TC_E24 ? 32 : 64;        // columns one epilogue warp takes from an accumulator
 constexpr int TC_MMAS = 2;                      // chained MMAs per tile (K = 16 BF16 each)
 constexpr int TC_A_MMA_BYTES = TC_M * 32;       // 4096
 constexpr int TC_A_BLOCK_BYTES = TC_MMAS * TC_A_MMA_BYTES;  // 8192 per hypothesis block
@@ -51,7 +54,8 @@ constexpr int TC_B_MMA_BYTES = TC_N * 32;       // 8192
 constexpr int TC_B_TILE_BYTES = TC_MMAS * TC_B_MMA_BYTES;   // 16384
 constexpr int TC_ASTAGES = 4;
 constexpr int TC_SB = 40;                       // hypothesis blocks per super-block (counts in smem): 5120 hypotheses
-constexpr int TC_EPI_WARPS = 16, TC_EPI_THREADS = 32 * TC_EPI_WARPS;
+constexpr int TC_EPI_WARPS = 4 * (TC_N / TC_RUN), TC_EPI_THREADS = 32 * TC_EPI_WARPS;
+static_assert(TC_CHUNK <= TC_EPI_THREADS, "one thread per point of a chunk");
 constexpr int TC_MMA_WARPS = TC_PHASES;         // one MMA issuing warp per accumulator; warp 0 also streams the images
 constexpr int TC_THREADS = TC_EPI_THREADS + 32 * TC_MMA_WARPS;
 constexpr float TC_ACC_ULPS = 8.0f;             // bound on the tensor core accumulation error, in u m
@@ -573,15 +577,18 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
       // nobody may still be re-counting from s_raw
       epi_sync();
       {
-        const int pi = threadIdx.x;  // point of the chunk (TC_CHUNK == TC_EPI_THREADS)
+        const int pi = threadIdx.x;  // point of the chunk (TC_CHUNK <= TC_EPI_THREADS)
         const int gi = base + pi;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ready) {
+        if (pi >= TC_CHUNK) {
+          // (24-warp shape: 768 threads, 384 points) nothing to split; warp-uniform, TC_CHUNK is a multiple of 32
+        } else if (ready) {
           // The cloud is still arriving from the host (pitt_sac_segment_host): the copy stream raises ready[k] after chunk k.
           // One lane polls (acquire, so the points read below are the copied ones); a time-out flags the run as invalid
           // instead of hanging the GPU (the host then rescoring on the complete cloud).
           if (lane == 0) {
-            const int* f = ready + base / ready_pts;
+            // flags come up in copy order: the one of the chunk's last point covers a chunk that straddles two regions
+            const int* f = ready + (min(base + TC_CHUNK, n) - 1) / ready_pts;
             int v, spins = 0;
             for (;;) {
               asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
@@ -600,8 +607,10 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
         } else if (gi < n) {
           p = __ldg(xyz + gi);
         }
-        s_raw[pi] = p;
-        tc_point_image(reinterpret_cast<uint4*>(smem + TC_OFF_B + (pi / TC_N) * TC_B_TILE_BYTES), pi % TC_N, p);
+        if (pi < TC_CHUNK) {
+          s_raw[pi] = p;
+          tc_point_image(reinterpret_cast<uint4*>(smem + TC_OFF_B + (pi / TC_N) * TC_B_TILE_BYTES), pi % TC_N, p);
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_arrive(BAR(TC_BAR_B));
@@ -638,8 +647,12 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
             continue;
           }
           tc_ld32(ra, taddr + b * TC_N);
-          tc_ld32(rb, taddr + b * TC_N + 32);
-          tc_ld_wait2(ra, rb);
+          if (TC_RUN == 64) {
+            tc_ld32(rb, taddr + b * TC_N + 32);
+            tc_ld_wait2(ra, rb);
+          } else {
+            tc_ld_wait(ra);
+          }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(TC_BAR_EMPTY + b));
@@ -648,17 +661,17 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
               dbg[row * 256 + j * TC_RUN + i] = __uint_as_float(ra[i]);
-              dbg[row * 256 + j * TC_RUN + 32 + i] = __uint_as_float(rb[i]);
+              if (TC_RUN == 64) dbg[row * 256 + j * TC_RUN + 32 + i] = __uint_as_float(rb[i]);
             }
           }
           if (DBG) e0 = clock64();
           if (full_runs) {
             tc_accumulate32(ra, P.C, S1, S2);
-            tc_accumulate32(rb, P.C, S1, S2);
+            if (TC_RUN == 64) tc_accumulate32(rb, P.C, S1, S2);
           } else {  // ragged last chunk of the cloud (warp-uniform)
             const int len = b ? len1 : len0;
             tc_accumulate32_masked(ra, P.C, S1, S2, len);
-            tc_accumulate32_masked(rb, P.C, S1, S2, len - 32);
+            if (TC_RUN == 64) tc_accumulate32_masked(rb, P.C, S1, S2, len - 32);
           }
           if (DBG) { asm volatile("" : "+l"(S1[0]), "+l"(S1[1]), "+l"(S2[0]), "+l"(S2[1])); e_math += clock64() - e0; }
         }

@@ -46,7 +46,10 @@ constexpr int TC_M = 128;                       // hypotheses per block (UMMA M,
 constexpr int TC_N = TC_E24 ? 192 : 256;        // points per MMA (UMMA N) = columns of one accumulator
 constexpr int TC_PHASES = 2;                    // accumulators in TMEM = tiles per point chunk
 constexpr int TC_CHUNK = TC_N * TC_PHASES;      // 512 points stationary in shared memory
-constexpr int TC_RUN = TC_E24 ? 32 : 64;        // columns one epilogue warp takes from an accumulator
+#ifndef TC_E8
+#define TC_E8 0   // 1: 8 epilogue warps (two per sub-partition), 128 columns per warp and phase in two 64-column steps
+#endif
+constexpr int TC_RUN = TC_E24 ? 32 : (TC_E8 ? 128 : 64);  // columns one epilogue warp takes from an accumulator
 constexpr int TC_MMAS = 2;                      // chained MMAs per tile (K = 16 BF16 each)
 constexpr int TC_A_MMA_BYTES = TC_M * 32;       // 4096
 constexpr int TC_A_BLOCK_BYTES = TC_MMAS * TC_A_MMA_BYTES;  // 8192 per hypothesis block
@@ -55,7 +58,7 @@ constexpr int TC_B_TILE_BYTES = TC_MMAS * TC_B_MMA_BYTES;   // 16384
 constexpr int TC_ASTAGES = 4;
 constexpr int TC_SB = 40;                       // hypothesis blocks per super-block (counts in smem): 5120 hypotheses
 constexpr int TC_EPI_WARPS = 4 * (TC_N / TC_RUN), TC_EPI_THREADS = 32 * TC_EPI_WARPS;
-static_assert(TC_CHUNK <= TC_EPI_THREADS, "one thread per point of a chunk");
+static_assert(TC_CHUNK <= TC_EPI_THREADS || TC_CHUNK % TC_EPI_THREADS == 0, "whole passes of the epilogue threads over a chunk");
 constexpr int TC_MMA_WARPS = TC_PHASES;         // one MMA issuing warp per accumulator; warp 0 also streams the images
 constexpr int TC_THREADS = TC_EPI_THREADS + 32 * TC_MMA_WARPS;
 constexpr float TC_ACC_ULPS = 8.0f;             // bound on the tensor core accumulation error, in u m
@@ -576,8 +579,7 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
       // every MMA that read the previous B image has completed (its accumulators were consumed);
       // nobody may still be re-counting from s_raw
       epi_sync();
-      {
-        const int pi = threadIdx.x;  // point of the chunk (TC_CHUNK <= TC_EPI_THREADS)
+      for (int pi = threadIdx.x; pi < max(TC_CHUNK, TC_EPI_THREADS); pi += TC_EPI_THREADS) {  // point of the chunk
         const int gi = base + pi;
         float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
         if (pi >= TC_CHUNK) {
@@ -646,32 +648,38 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
             if (lane == 0) mbar_arrive(BAR(TC_BAR_EMPTY + b));
             continue;
           }
-          tc_ld32(ra, taddr + b * TC_N);
-          if (TC_RUN == 64) {
-            tc_ld32(rb, taddr + b * TC_N + 32);
-            tc_ld_wait2(ra, rb);
-          } else {
-            tc_ld_wait(ra);
-          }
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(TC_BAR_EMPTY + b));
-          if (DBG) e_ld += clock64() - e0;
-          if (DBG && dbg && blockIdx.x == 0 && jj == 0 && hb == 0 && b == 0) {
+          constexpr int STEPS = TC_RUN > 64 ? TC_RUN / 64 : 1;  // 64-column steps of this warp's run (8-warp shape: two)
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              dbg[row * 256 + j * TC_RUN + i] = __uint_as_float(ra[i]);
-              if (TC_RUN == 64) dbg[row * 256 + j * TC_RUN + 32 + i] = __uint_as_float(rb[i]);
+          for (int ks = 0; ks < STEPS; ++ks) {
+            tc_ld32(ra, taddr + b * TC_N + 64 * ks);
+            if (TC_RUN >= 64) {
+              tc_ld32(rb, taddr + b * TC_N + 64 * ks + 32);
+              tc_ld_wait2(ra, rb);
+            } else {
+              tc_ld_wait(ra);
             }
-          }
-          if (DBG) e0 = clock64();
-          if (full_runs) {
-            tc_accumulate32(ra, P.C, S1, S2);
-            if (TC_RUN == 64) tc_accumulate32(rb, P.C, S1, S2);
-          } else {  // ragged last chunk of the cloud (warp-uniform)
-            const int len = b ? len1 : len0;
-            tc_accumulate32_masked(ra, P.C, S1, S2, len);
-            if (TC_RUN == 64) tc_accumulate32_masked(rb, P.C, S1, S2, len - 32);
+            if (ks == STEPS - 1) {  // the whole run is in registers (or consumed): hand the accumulator back
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(BAR(TC_BAR_EMPTY + b));
+            }
+            if (DBG && ks == 0) e_ld += clock64() - e0;
+            if (DBG && dbg && blockIdx.x == 0 && jj == 0 && hb == 0 && b == 0 && STEPS == 1) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                dbg[row * 256 + j * TC_RUN + i] = __uint_as_float(ra[i]);
+                if (TC_RUN == 64) dbg[row * 256 + j * TC_RUN + 32 + i] = __uint_as_float(rb[i]);
+              }
+            }
+            if (DBG) e0 = clock64();
+            if (full_runs) {
+              tc_accumulate32(ra, P.C, S1, S2);
+              if (TC_RUN >= 64) tc_accumulate32(rb, P.C, S1, S2);
+            } else {  // ragged last chunk of the cloud (warp-uniform)
+              const int len = (b ? len1 : len0) - 64 * ks;
+              tc_accumulate32_masked(ra, P.C, S1, S2, len);
+              if (TC_RUN >= 64) tc_accumulate32_masked(rb, P.C, S1, S2, len - 32);
+            }
           }
           if (DBG) { asm volatile("" : "+l"(S1[0]), "+l"(S1[1]), "+l"(S2[0]), "+l"(S2[1])); e_math += clock64() - e0; }
         }

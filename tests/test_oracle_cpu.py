@@ -63,6 +63,60 @@ def test_plane_scoring_matches_numpy(oracle):
             assert abs(float(np.dot(co[h, :3], xyz[idx, :3]) + co[h, 3])) < 1e-5
 
 
+def _angle3d(v1, v2):
+    num = (v1 * v2).sum(-1)
+    den = np.sqrt((v1 * v1).sum(-1) * (v2 * v2).sum(-1))
+    with np.errstate(all="ignore"):
+        return np.arccos(np.clip(num / den, -1.0, 1.0))
+
+
+def _np_count(model, co, P, N, p):
+    """countWithinDistance of SampleConsensusModel{Sphere,Cylinder,Cone} written from the formulas of SURVEY B.4-B.6 in
+    float64 numpy (an independent derivation: no operation order shared with oracle/orc_sac.cpp)"""
+    thr, w = p.distance_threshold, p.normal_distance_weight
+    co = co.astype(np.float64)
+    if model == A.MODEL_SPHERE:
+        return int((np.abs(np.linalg.norm(P - co[:3], axis=1) - co[3]) < thr).sum())
+    if model == A.MODEL_CYLINDER:
+        pt0, dr, r = co[:3], co[3:6], co[6]
+        d_euclid = np.abs(np.linalg.norm(np.cross(P - pt0, dr), axis=1) / np.linalg.norm(dr) - r)
+        k = (P @ dr - pt0 @ dr) / (dr @ dr)
+        dirv = P - (pt0 + k[:, None] * dr)
+        d_normal = np.abs(_angle3d(N, dirv))
+        d_normal = np.minimum(d_normal, np.pi - d_normal)
+        return int((np.abs(w * d_normal + (1 - w) * d_euclid) < thr).sum())
+    apex, ax, ang = co[:3], co[3:6], co[6]
+    k = (P @ ax - apex @ ax) / (ax @ ax)
+    proj = apex + k[:, None] * ax
+    pp_dir = P - proj
+    pp_dir /= np.linalg.norm(pp_dir, axis=1, keepdims=True)
+    height = apex - proj
+    hn = np.linalg.norm(height, axis=1, keepdims=True)
+    cone_normal = np.sin(ang) * (height / hn) + np.cos(ang) * pp_dir
+    d_euclid = np.abs(np.linalg.norm(np.cross(P - apex, ax), axis=1) / np.linalg.norm(ax) - np.tan(ang) * hn[:, 0])
+    d_normal = np.abs(_angle3d(N, cone_normal))
+    d_normal = np.minimum(d_normal, np.pi - d_normal)
+    return int((np.abs(w * d_normal + (1 - w) * d_euclid) < thr).sum())
+
+
+@pytest.mark.parametrize("kind,model", [("sphere", A.MODEL_SPHERE), ("cylinder", A.MODEL_CYLINDER), ("cone", A.MODEL_CONE)])
+def test_primitive_scoring_matches_numpy(oracle, kind, model):
+    """the oracle's per-hypothesis inlier counts against the float64 restatement above, on the hypotheses of the PCL sample
+    stream; a point within rounding of the threshold may flip: counts may differ by at most 2 and must agree exactly for
+    at least 95 % of the valid hypotheses"""
+    xyz, _ = scenes.primitive_cluster(kind, 3000, 11)
+    nrm = oracle.estimate_normals(xyz, 50, (0.0, 0.0, 0.0))
+    p = oracle.default_sac_params(model)
+    samples = oracle.pcl_sample_stream(xyz, model, 200)
+    c, co, v = oracle.sac_score(xyz, nrm, p, samples)
+    P, N = xyz[:, :3].astype(np.float64), nrm[:, :3].astype(np.float64)
+    diffs = np.array([_np_count(model, co[h], P, N, p) - int(c[h]) for h in range(len(c)) if v[h] and c[h] > 0])
+    assert len(diffs) >= 50
+    assert np.abs(diffs).max() <= 2, diffs
+    assert (diffs == 0).mean() >= 0.95
+    assert c.max() > 2000  # the right model is among them
+
+
 def test_ransac_pcl_semantics(oracle):
     xyz = scenes.plane_outlier_cloud(8000, seed=6)
     p = oracle.default_support_sac_params()

@@ -233,6 +233,46 @@ def test_lm_improves_residual(oracle):
     assert abs(ref[3] - truth["radius"]) < 5e-4
 
 
+@pytest.mark.parametrize("kind,model", [("sphere", A.MODEL_SPHERE), ("cylinder", A.MODEL_CYLINDER), ("cone", A.MODEL_CONE)])
+def test_lm_reaches_the_minimum_scipy_finds(oracle, kind, model):
+    """optimizeModelCoefficients (Eigen's LevenbergMarquardt<NumericalDiff>, restated in oracle/orc_lm.h, float) against
+    scipy's MINPACK LM in float64 on the same residuals (SURVEY B.4-B.6 "Refine"), started from the same RANSAC model: the
+    sum of squared residuals the oracle ends at is within 0.1 % of scipy's minimum"""
+    from scipy.optimize import least_squares
+
+    def line_d2(P, pt, dr):
+        return (np.cross(P - pt, dr) ** 2).sum(1) / (dr @ dr)
+
+    xyz, truth = scenes.primitive_cluster(kind, 3000, 21, sigma=0.002)
+    nrm = oracle.estimate_normals(xyz, 50, (0.0, 0.0, 0.0))
+    p = oracle.default_sac_params(model)
+    p.optimize = 0
+    base = oracle.sac_segment(xyz, nrm, p)
+    ref, info = oracle.sac_refine(xyz, nrm, p, base["coeffs"], base["inliers"])
+    P = xyz[base["inliers"], :3].astype(np.float64)
+    if model == A.MODEL_SPHERE:
+        def f(c):
+            return np.linalg.norm(P - c[:3], axis=1) - c[3]
+    elif model == A.MODEL_CYLINDER:
+        def f(c):
+            return line_d2(P, c[:3], c[3:6]) - c[6] ** 2
+    else:
+        def f(c):
+            apex, ax = c[:3], c[3:6]
+            proj = apex + ((((P - apex) @ ax) / (ax @ ax))[:, None]) * ax
+            return line_d2(P, apex, ax) - (np.tan(c[6]) * np.linalg.norm(apex - proj, axis=1)) ** 2
+
+    def cost(c):
+        return float((f(np.asarray(c, np.float64)) ** 2).sum())
+
+    x0 = base["coeffs"][: A.N_COEFFS[model]].astype(np.float64)
+    best = least_squares(f, x0, method="lm", xtol=1e-12, ftol=1e-12)
+    assert cost(ref) < cost(x0)
+    assert cost(ref) <= cost(best.x) * 1.001, (cost(ref), cost(best.x))
+    if model != A.MODEL_CONE:  # the radius is well determined (the cone's angle sits in a flat valley with the apex)
+        assert abs(ref[-1] - best.x[-1]) < 1e-5
+
+
 def test_knn_matches_brute_force(oracle):
     xyz = scenes.tabletop_frame(seed=3, width=80, height=60)
     idx, sq = oracle.knn(xyz, 12)

@@ -298,6 +298,48 @@ def test_normals_on_analytic_surfaces(oracle):
     assert nrm[:, 3].max() < 1e-3  # curvature of a plane
 
 
+def test_normals_match_numpy_pca(oracle):
+    """NormalEstimation on a curved, noisy surface against brute-force kNN + numpy's symmetric
+    eigen-solver in float64: same direction (up to the sign fixed by the viewpoint) and same curvature
+    lambda_0 / (lambda_0 + lambda_1 + lambda_2)"""
+    xyz, _ = scenes.primitive_cluster("sphere", 1500, 4, sigma=0.001)
+    nrm = oracle.estimate_normals(xyz, 50, (0.0, 0.0, 0.0))
+    P = xyz[:, :3].astype(np.float64)
+    d2 = ((P[:, None, :] - P[None, :, :]) ** 2).sum(-1)
+    nn = np.argsort(d2, axis=1, kind="stable")[:, :50]
+    d_dir, d_curv = [], []
+    for i in range(0, len(P), 7):
+        Q = P[nn[i]]
+        w, V = np.linalg.eigh(np.cov(Q.T, bias=True))
+        n_np = V[:, 0]
+        if n_np @ (-P[i]) < 0:
+            n_np = -n_np
+        d_dir.append(1.0 - float(nrm[i, :3].astype(np.float64) @ n_np))
+        d_curv.append(abs(float(nrm[i, 3]) - w[0] / w.sum()))
+    # PCL's one-pass float covariance (E[xx] - mean^2 on coordinates of ~0.5 m, variances of ~1e-5 m^2) carries a relative
+    # error of a few 1e-3: the directions agree to 1 - cos < 1e-4 in the median (worst case a few degrees)
+    assert np.median(d_dir) < 1e-4 and max(d_dir) < 5e-3, (np.median(d_dir), max(d_dir))
+    assert np.median(d_curv) < 5e-3 and max(d_curv) < 5e-2, (np.median(d_curv), max(d_curv))
+
+
+def test_plane_refinement_matches_numpy_pca(oracle):
+    """optimizeModelCoefficients of the plane model (mean + covariance + smallest eigenvector) against
+    numpy in float64 on the same inliers"""
+    xyz = scenes.plane_outlier_cloud(20000, seed=3)
+    p = oracle.default_support_sac_params()
+    p.optimize = 0
+    base = oracle.sac_segment(xyz, None, p)
+    ref, _ = oracle.sac_refine(xyz, None, p, base["coeffs"], base["inliers"])
+    Q = xyz[base["inliers"], :3].astype(np.float64)
+    mean = Q.mean(0)
+    w, V = np.linalg.eigh(np.cov(Q.T, bias=True))
+    n_np = V[:, 0]
+    if n_np @ ref[:3] < 0:
+        n_np = -n_np
+    assert 1.0 - float(ref[:3].astype(np.float64) @ n_np) < 1e-6
+    assert abs(float(ref[3]) + float(n_np @ mean)) < 1e-5
+
+
 def test_clusters_match_scipy_components(oracle):
     from scipy.sparse import coo_matrix
     from scipy.sparse.csgraph import connected_components

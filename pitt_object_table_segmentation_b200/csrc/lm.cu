@@ -719,12 +719,12 @@ static cudaError_t lm_launch(pitt_ctx* ctx, bool cluster, const float4* xyz, con
                              const float* d_model, float* d_work, float* d_refined, int* d_lm_info) {
   constexpr int n = (MODEL == PITT_MODEL_SPHERE) ? 4 : 7;
   if (!cluster && m_cap <= LM_SMEM_ROWS) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {false};  // the opt-in is per device (and per template instantiation)
+    if (!attr_set[ctx->device & 63]) {
       cudaError_t e = cudaFuncSetAttribute(lm_kernel<MODEL, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (n + 3) * LM_SMEM_ROWS * (int)sizeof(float));
       if (e != cudaSuccess) return e;
-      attr_set = true;
+      attr_set[ctx->device & 63] = true;
     }
     const size_t smem = (size_t)(n + 3) * m_cap * sizeof(float);
     // (128 / 256 threads for the smallest fits were measured: 0.75 vs 0.77 ms at 300 rows, slower from 1000 rows on)

@@ -799,10 +799,10 @@ int launch_score_plane_tc(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_re
   const bool dbgk = g_plane_tc_dump || g_plane_tc_variant || g_plane_tc_collect_stats;  // statistics live in the DBG kernel only
 #define TC_LAUNCH(DBGK)                                                                                                         \
   do {                                                                                                                          \
-    static bool attr_set = false;                                                                                               \
-    if (!attr_set) {                                                                                                            \
+    static bool attr_set[64] = {false}; /* the opt-in is per device */                                                          \
+    if (!attr_set[ctx->device & 63]) {                                                                                          \
       PITT_CUDA(ctx, cudaFuncSetAttribute(plane_tc_kernel<DBGK>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));  \
-      attr_set = true;                                                                                                          \
+      attr_set[ctx->device & 63] = true;                                                                                        \
     }                                                                                                                           \
     plane_tc_kernel<DBGK><<<grid, TC_THREADS, TC_SMEM_BYTES, ctx->stream>>>(                                                    \
         c->d_xyz, n, d_recs, H, d_image, n_hb, n_chunks, (int)items, sp.thr_up, d_P, d_counts, st, d_dbg, g_plane_tc_variant,  \

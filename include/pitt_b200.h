@@ -365,6 +365,16 @@ int pitt_sac_finish_device(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_sa
                            const void* d_samples_all, int n_hypotheses_all, const void* d_best,
                            int32_t* inliers, int inliers_cap, int* n_inliers, float* coeffs, int* n_coeffs,
                            pitt_sac_info* info /* nullable */);
+/* SURVEY 8e / BASELINE configs[4]: seg.segment() of one cloud with the hypothesis set split over `world` ranks (one process
+ * per GPU; every rank holds the cloud). params->stop must be PITT_STOP_ALL_H; params->max_iterations = hypotheses of the WHOLE
+ * job (rank r scores stream positions [r*Hl, (r+1)*Hl), Hl = ceil(H / world)). `allgather` is the caller's collective (NCCL over
+ * NVLink in a ROS node or under torchrun): it must gather count_per_rank int32 from d_send of every rank
+ * into d_recv in rank order, enqueued on cuda_stream (or ordered after it), and return 0. With world == 1 it may be NULL.
+ * Every rank returns the result pitt_sac_segment gives on one GPU. */
+typedef int (*pitt_allgather_fn)(void* user, const void* d_send, void* d_recv, int count_per_rank, void* cuda_stream);
+int pitt_sac_segment_split(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_sac_params* params, int rank, int world,
+                           pitt_allgather_fn allgather, void* user, int32_t* inliers /* NULL: count only */, int inliers_cap,
+                           int* n_inliers, float coeffs[8], int* n_coeffs, pitt_sac_info* info /* nullable */);
 /* selectWithinDistance for given coefficients (ascending indices). */
 int pitt_sac_select(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_sac_params* params,
                     const float* coeffs, int32_t* inliers, int inliers_cap, int* n_inliers);
@@ -412,6 +422,11 @@ int pitt_segment_frames_batched(pitt_ctx* const* ctxs, int n_ctx, const void* co
 int pitt_segment_raw_frames_batched(pitt_ctx* const* ctxs, int n_ctx, const void* const* frames, const int* n_points,
                                     int stride_bytes, int n_frames, const pitt_prefilter_params* prefilter,
                                     const pitt_frame_params* params, pitt_frame_result* results);
+
+/* The same stream over clouds that are already staged in HBM (any context of the same device may have staged them):
+ * the resident-input arm of bench.py, and callers that keep the sensor's frames on the device. */
+int pitt_segment_clouds_batched(pitt_ctx* const* ctxs, int n_ctx, const pitt_cloud* const* clouds, int n_frames,
+                                const pitt_frame_params* params, pitt_frame_result* results);
 
 /* ------------------------------------------------------------------ measurement helpers */
 /* FP32 pipe micro-benchmark used as the roofline denominator of the scoring kernels:

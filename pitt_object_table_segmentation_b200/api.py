@@ -25,8 +25,49 @@ EXPORTED_SYMBOLS = [
     "pitt_sac_segment", "pitt_sac_segment_host", "pitt_sac_score", "pitt_sac_score_device", "pitt_argmax_counts_device", "pitt_sac_finish_device", "pitt_sac_select", "pitt_sac_refine",
     "pitt_pcl_sample_stream", "pitt_euclidean_clusters", "pitt_find_supports", "pitt_cluster_service",
     "pitt_primitive_service", "pitt_select_primitive", "pitt_segment_frame", "pitt_segment_frames_batched", "pitt_fp32_peak", "pitt_last_device_ms",
-    "pitt_kernel_launches",
+    "pitt_kernel_launches", "pitt_segment_clouds_batched", "pitt_sac_segment_split",
 ]
+# include/pitt_b200_debug.h: test / measurement hooks, not part of the drop-in boundary
+DEBUG_SYMBOLS = [
+    "pitt_debug_plane_mode", "pitt_debug_force_generic_plane", "pitt_debug_score_mode", "pitt_debug_select_no_fuse",
+    "pitt_debug_lm_cluster_min", "pitt_debug_stream_chunks", "pitt_debug_plane_filter_stats", "pitt_debug_plane_tc_stats",
+    "pitt_debug_plane_tc_cta_cycles", "pitt_debug_plane_tc_dump", "pitt_debug_plane_tc_acc_ulps", "pitt_debug_plane_tc_variant",
+    "pitt_debug_plane_tc_nwq", "pitt_debug_plane_tc_time_kernel", "pitt_debug_plane_tc_kernel_ms",
+]
+
+
+# pitt_allgather_fn of include/pitt_b200.h: (user, d_send, d_recv, count_per_rank, cuda_stream) -> 0 on success
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
+
+
+class _DevArray:
+    """a raw device pointer as a __cuda_array_interface__ object (int32), so that torch can wrap it without a copy"""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<i4", "data": (int(ptr), False), "version": 2}
+
+
+def torch_allgather_callback(group=None):
+    """pitt_allgather_fn on top of torch.distributed (NCCL under torchrun, gloo in the CPU tests is not applicable: the
+    buffers are device memory). The collective is ordered on the context's stream (passed to the callback)."""
+    import torch
+    import torch.distributed as dist
+
+    def _cb(user, d_send, d_recv, count, stream):
+        try:
+            world = dist.get_world_size(group)
+            # the counts are produced on the context's stream: make it torch's current stream for the collective
+            with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+                send = torch.as_tensor(_DevArray(d_send, count), device="cuda")
+                recv = torch.as_tensor(_DevArray(d_recv, count * world), device="cuda")
+                dist.all_gather_into_tensor(recv, send, group=group)
+            return 0
+        except Exception as e:  # noqa: BLE001 - reported through the status code
+            import sys
+            print(f"[pitt] all-gather callback failed: {e}", file=sys.stderr)
+            return 1
+
+    return ALLGATHER_FN(_cb)
 
 
 class PittError(RuntimeError):
@@ -95,6 +136,14 @@ def load_library():
     lib.pitt_segment_frame.argtypes = [vp, vp, C.POINTER(A.FrameParams), C.POINTER(A.FrameResult)]
     lib.pitt_segment_frames_batched.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(vp), A.i32p, C.c_int, C.c_int,
                                                 C.POINTER(A.FrameParams), C.POINTER(A.FrameResult)]
+    lib.pitt_sac_segment_split.argtypes = [vp, vp, C.POINTER(A.SacParams), C.c_int, C.c_int, ALLGATHER_FN, vp, A.i32p, C.c_int,
+                                           C.POINTER(C.c_int), A.f32p, C.POINTER(C.c_int), C.POINTER(A.SacInfo)]
+    lib.pitt_segment_clouds_batched.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(vp), C.c_int, C.POINTER(A.FrameParams),
+                                                C.POINTER(A.FrameResult)]
+    lib.pitt_debug_plane_tc_time_kernel.argtypes = [vp, C.c_int]
+    lib.pitt_debug_plane_tc_time_kernel.restype = None
+    lib.pitt_debug_plane_tc_kernel_ms.argtypes = [vp]
+    lib.pitt_debug_plane_tc_kernel_ms.restype = C.c_double
     lib.pitt_fp32_peak.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     lib.pitt_last_device_ms.restype = C.c_double
     lib.pitt_last_device_ms.argtypes = [vp]
@@ -322,6 +371,21 @@ class Context:
                                               C.byref(n_inl), co.ctypes.data_as(A.f32p), C.byref(n_co), C.byref(info)))
         return {"inliers": inl[: n_inl.value].copy(), "coeffs": co[: n_co.value].copy(), "info": info}
 
+    def sac_segment_split(self, cloud, params, rank, world, allgather=None, want_inliers=True):
+        """pitt_sac_segment_split: one cloud, the hypothesis set split over `world` ranks; `allgather` = an ALLGATHER_FN
+        (torch_allgather_callback() under torchrun), None with world == 1"""
+        n = cloud.n
+        inl = np.empty(max(n, 1), np.int32) if want_inliers else None
+        n_inl, n_co = C.c_int(0), C.c_int(0)
+        co = np.zeros(8, np.float32)
+        info = A.SacInfo()
+        cb = allgather if allgather is not None else C.cast(None, ALLGATHER_FN)
+        self._check(self.lib.pitt_sac_segment_split(self.handle, cloud.handle, C.byref(params), int(rank), int(world), cb, None,
+                                                    inl.ctypes.data_as(A.i32p) if want_inliers else None, n if want_inliers else 0,
+                                                    C.byref(n_inl), co.ctypes.data_as(A.f32p), C.byref(n_co), C.byref(info)))
+        return {"n_inliers": n_inl.value, "inliers": inl[: n_inl.value].copy() if want_inliers else None,
+                "coeffs": co[: n_co.value].copy(), "info": info}
+
     def sac_segment_host(self, xyz, params, host_ptr=None):
         """fromROSMsg + seg.segment() on a host cloud (n x 4 float32, or n x 3) in one call; host_ptr = address of a pinned
         copy of the same array (the H2D then runs at full PCIe speed and overlaps the scoring)."""
@@ -443,6 +507,28 @@ def default_prefilter_params():
     p = A.PrefilterParams()
     load_library().pitt_default_prefilter_params(C.byref(p))
     return p
+
+
+def segment_clouds_batched(contexts, clouds, params=None, shapes_cap=64, bufs=None):
+    """pitt_segment_clouds_batched: the frame stream over clouds that are already staged in HBM. `bufs` (a list of
+    FrameBuffers, one per cloud) can be passed to keep allocations out of a timed region."""
+    params = params if params is not None else default_frame_params()
+    lib = load_library()
+    n = len(clouds)
+    bufs = bufs if bufs is not None else [R.FrameBuffers(shapes_cap) for _ in range(n)]
+    res = (A.FrameResult * n)()
+    for i, b in enumerate(bufs):
+        res[i] = b.res
+    handles = (C.c_void_p * n)(*[c.handle for c in clouds])
+    ctxs = (C.c_void_p * len(contexts))(*[c.handle for c in contexts])
+    st = lib.pitt_segment_clouds_batched(ctxs, len(contexts), handles, n, C.byref(params), res)
+    if st != A.PITT_OK:
+        raise PittError(f"pitt_segment_clouds_batched status {st}")
+    out = []
+    for i, b in enumerate(bufs):
+        b.res = res[i]
+        out.append(b.to_python())
+    return out
 
 
 def segment_frames_batched(contexts, frames, params=None, shapes_cap=64, prefilter=None):

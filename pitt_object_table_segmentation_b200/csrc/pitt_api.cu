@@ -5,6 +5,7 @@
 
 #include "pitt_common.cuh"
 #include "sac.cuh"
+#include "../../include/pitt_b200_debug.h"
 
 using namespace pitt;
 
@@ -655,6 +656,127 @@ int pitt_argmax_counts_device(pitt_ctx* ctx, const void* d_counts, int H, void* 
   return sac_winner(ctx, (const int*)d_counts, d_flags, H, d_dummy, (int*)d_best, d_dummy + (size_t)H * 8);
 }
 
+
+namespace pitt {
+// hypothesis split: hypotheses whose model could not be estimated (PCL skips them) and the padding of the last rank's slice
+// must never win the arg-max: their count becomes -1
+__global__ void split_mask_counts_kernel(int* __restrict__ counts, const uint8_t* __restrict__ flags, int h_have, int h_loc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= h_loc) return;
+  if (i >= h_have || !(flags[i] & 1)) counts[i] = -1;
+}
+}  // namespace pitt
+
+/* SURVEY 8e / BASELINE configs[4]: seg.segment() of ONE cloud with the hypothesis set split over `world` ranks (one process
+ * per GPU, every rank holds the cloud). Rank r estimates and scores hypotheses [r*Hl, (r+1)*Hl) of the sample stream,
+ * Hl = ceil(H / world); `allgather` (the caller's NCCL all-gather over NVLink) collects the Hl int32
+ * counts of every rank in rank order; every rank then takes the earliest arg-max (PCL keeps the first best model: strict '>'
+ * in ransac.hpp), re-estimates the winner from its sample, refines it and selects the final inliers, so all ranks return
+ * the same result as pitt_sac_segment on one GPU with stop = ALL_H. */
+int pitt_sac_segment_split(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params* p, int rank, int world,
+                           pitt_allgather_fn allgather, void* user, int32_t* inliers, int cap, int* n_inliers, float coeffs[8],
+                           int* n_coeffs, pitt_sac_info* info) {
+  if (!ctx) return PITT_ERR_CUDA;
+  if (!c || !p || !n_inliers || !coeffs || !n_coeffs || world < 1 || rank < 0 || rank >= world || (world > 1 && !allgather) ||
+      p->model < 0 || p->model > 3)
+    return fail(ctx, PITT_ERR_INVALID, "pitt_sac_segment_split arguments");
+  if (p->stop != PITT_STOP_ALL_H) return fail(ctx, PITT_ERR_INVALID, "pitt_sac_segment_split: only stop = PITT_STOP_ALL_H can be split");
+  if ((p->model == PITT_MODEL_CYLINDER || p->model == PITT_MODEL_CONE) && !c->has_normals)
+    return fail(ctx, PITT_ERR_STATE, "cylinder/cone segmentation needs normals on the cloud");
+  cudaSetDevice(ctx->device);
+  CallTimer timer(ctx);
+  *n_inliers = 0;
+  *n_coeffs = 0;
+  if (info) {
+    memset(info, 0, sizeof(*info));
+    info->best_hypothesis = -1;
+  }
+  const int S = p->model == PITT_MODEL_PLANE ? 3 : p->model == PITT_MODEL_SPHERE ? 4 : p->model == PITT_MODEL_CYLINDER ? 2 : 3;
+  int H_all = p->max_iterations;
+  if (p->sampler == PITT_SAMPLER_REPLAY) {
+    if (!p->replay_samples) return fail(ctx, PITT_ERR_INVALID, "replay_samples is null");
+    H_all = std::min(H_all, p->replay_count);
+  }
+  if (H_all <= 0 || c->n < S) {
+    timer.finish();
+    return PITT_OK;
+  }
+  const int H_loc = (H_all + world - 1) / world;
+  const int h0 = std::min(H_all, rank * H_loc);
+  const int H_have = std::max(0, std::min(H_all, h0 + H_loc) - h0);
+  int* d_samples_all = nullptr;
+  int* d_counts = nullptr;
+  int* d_counts_all = nullptr;
+  int* d_best = nullptr;
+  uint8_t* d_flags = nullptr;
+  float* d_dummy = nullptr;
+  uint8_t* d_ones = nullptr;
+  PITT_TRY(arena_alloc(ctx, (size_t)H_all * S, &d_samples_all));
+  PITT_TRY(arena_alloc(ctx, (size_t)H_loc, &d_counts));
+  PITT_TRY(arena_alloc(ctx, (size_t)H_loc * world, &d_counts_all));
+  PITT_TRY(arena_alloc(ctx, 2, &d_best));
+  PITT_TRY(arena_alloc(ctx, (size_t)H_loc, &d_flags));
+  PITT_TRY(arena_alloc(ctx, (size_t)H_loc * world, &d_ones));
+  PITT_TRY(arena_alloc(ctx, 16, &d_dummy));
+  // the whole sample stream on every rank (the winner's sample is needed everywhere)
+  if (p->sampler == PITT_SAMPLER_PHILOX) {
+    PITT_TRY(sac_philox_samples(ctx, d_samples_all, H_all, S, c->n, 1u));
+  } else {
+    PITT_TRY(pinned_reserve(ctx, (size_t)H_all * S * sizeof(int)));
+    int* h = (int*)ctx->h_pin;
+    if (p->sampler == PITT_SAMPLER_REPLAY) {
+      for (size_t i = 0; i < (size_t)H_all * S; ++i) {
+        const int v = p->replay_samples[i];
+        if (v < 0 || v >= c->n) return fail(ctx, PITT_ERR_INVALID, "sample index out of range");
+        h[i] = v;
+      }
+    } else {
+      if (p->model == PITT_MODEL_PLANE) PITT_TRY(ensure_host_mirror(ctx, c));
+      PclSampleStream s(c->n, p->model, p->model == PITT_MODEL_PLANE ? c->h_xyz.data() : nullptr);
+      for (int i = 0; i < H_all; ++i)
+        if (!s.next(h + (size_t)i * S)) return fail(ctx, PITT_ERR_INVALID, "cloud smaller than the sample size");
+    }
+    PITT_CUDA(ctx, cudaMemcpyAsync(d_samples_all, h, (size_t)H_all * S * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  PITT_CUDA(ctx, cudaMemsetAsync(d_flags, 0, (size_t)H_loc, ctx->stream));
+  PITT_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (size_t)H_loc * sizeof(int), ctx->stream));
+  if (H_have > 0) PITT_TRY(score_common(ctx, c, p, d_samples_all + (size_t)h0 * S, H_have, d_counts, nullptr, d_flags));
+  split_mask_counts_kernel<<<cdiv(H_loc, 256), 256, 0, ctx->stream>>>(d_counts, d_flags, H_have, H_loc);
+  ctx->launches++;
+  const int* d_gathered = d_counts;
+  if (world > 1) {
+    const int st = allgather(user, d_counts, d_counts_all, H_loc, (void*)ctx->stream);
+    if (st != 0) return fail(ctx, PITT_ERR_CUDA, "pitt_sac_segment_split: the caller's all-gather failed");
+    d_gathered = d_counts_all;
+  }
+  // earliest arg-max over the gathered counts: global stream position = rank * H_loc + i (padding and failed models are -1)
+  PITT_CUDA(ctx, cudaMemsetAsync(d_ones, 1, (size_t)H_loc * world, ctx->stream));
+  PITT_TRY(sac_winner(ctx, d_gathered, d_ones, H_loc * world, nullptr, d_best, d_dummy));
+  SacDeviceResult r;
+  PITT_TRY(sac_finish_from_winner(ctx, c, *p, d_samples_all, H_all, d_best, &r));
+  int status = PITT_OK;
+  if (r.info.best_hypothesis >= 0 && r.info.best_count >= 0) {
+    *n_inliers = r.n_inliers;
+    *n_coeffs = r.n_coeffs;
+    for (int i = 0; i < r.n_coeffs; ++i) coeffs[i] = r.coeffs[i];
+    if (inliers && r.n_inliers > 0) {
+      if (cap < r.n_inliers) status = fail(ctx, PITT_ERR_CAPACITY, "inlier buffer too small");
+      else {
+        PITT_CUDA(ctx, cudaMemcpyAsync(inliers, r.d_inliers, (size_t)r.n_inliers * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        PITT_CUDA(ctx, pitt::stream_sync(ctx));
+      }
+    }
+  }
+  timer.finish();
+  if (info) {
+    *info = r.info;
+    info->iterations = H_all;
+    info->hypotheses = H_have;
+    info->device_ms = ctx->last_ms;
+  }
+  return status;
+}
+
 /* test hook (not in the public header): route plane scoring through the generic kernel */
 void pitt_debug_force_generic_plane(int on) { g_force_generic_plane = on; }
 /* test hooks: plane scoring mode (0 = automatic: tensor path on large jobs, 1 = exact packed kernel only, 2 = FFMA filter + exact
@@ -693,7 +815,9 @@ void pitt_debug_plane_tc_acc_ulps(float ulps) { g_plane_tc_acc_ulps = ulps; }
 void pitt_debug_plane_tc_variant(int v) { g_plane_tc_variant = v; }
 /* enable: every tensor-path scoring call records two CUDA events around the plane_tc_kernel launch alone (on the
  * context's stream); pitt_debug_plane_tc_kernel_ms waits for the last pair and returns the kernel's duration (< 0: none) */
-void pitt_debug_plane_tc_time_kernel(int enable) { g_plane_tc_time_kernel = enable; }
+void pitt_debug_plane_tc_time_kernel(pitt_ctx* ctx, int enable) {
+  if (ctx) ctx->time_tc_kernel = enable != 0;
+}
 double pitt_debug_plane_tc_kernel_ms(pitt_ctx* ctx) {
   if (!ctx || !ctx->ev_k0) return -1.0;
   float ms = -1.0f;

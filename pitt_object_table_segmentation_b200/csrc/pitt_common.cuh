@@ -50,6 +50,7 @@ struct pitt_ctx {
   // with more host threads than cores (16 contexts x 8 ranks on one box)
   cudaEvent_t ev_block = nullptr;
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // bracket of the last plane_tc_kernel launch (pitt_debug_plane_tc_kernel_ms)
+  bool time_tc_kernel = false;                   // pitt_debug_plane_tc_time_kernel(ctx, 1)
   int* d_ready = nullptr;   // 16 arrival flags (device) and the pinned word they are raised from
   int* h_one = nullptr;
   void* h_pin2 = nullptr;  // pinned block for the gathered sample points (h_pin holds the sample indices at that time)

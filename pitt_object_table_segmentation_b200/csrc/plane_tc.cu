@@ -732,7 +732,6 @@ unsigned long long g_plane_tc_stats[2 + 160 + 16] = {0, 0};
 int g_plane_tc_collect_stats = 0;
 int g_plane_tc_dump = 0;
 int g_plane_tc_variant = 0;
-int g_plane_tc_time_kernel = 0;  // test / bench hook: bracket the plane_tc_kernel launch alone with two CUDA events
 int g_plane_tc_nwq = 4;
 float g_plane_tc_acc_ulps = TC_ACC_ULPS;
 std::vector<float> g_plane_tc_dump_host;  // 128 x 256 accumulators + sigma, C
@@ -808,7 +807,7 @@ int launch_score_plane_tc(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_re
         c->d_xyz, n, d_recs, H, d_image, n_hb, n_chunks, (int)items, sp.thr_up, d_P, d_counts, st, d_dbg, g_plane_tc_variant,  \
         d_ready, ready_pts, d_seen);                                                                                            \
   } while (0)
-  if (g_plane_tc_time_kernel) {
+  if (ctx->time_tc_kernel) {
     if (!ctx->ev_k0) {
       PITT_CUDA(ctx, cudaEventCreate(&ctx->ev_k0));
       PITT_CUDA(ctx, cudaEventCreate(&ctx->ev_k1));
@@ -816,7 +815,7 @@ int launch_score_plane_tc(pitt_ctx* ctx, const pitt_cloud* c, const HypRec* d_re
     PITT_CUDA(ctx, cudaEventRecord(ctx->ev_k0, ctx->stream));
   }
   if (dbgk) TC_LAUNCH(true); else TC_LAUNCH(false);
-  if (g_plane_tc_time_kernel) PITT_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
+  if (ctx->time_tc_kernel) PITT_CUDA(ctx, cudaEventRecord(ctx->ev_k1, ctx->stream));
 #undef TC_LAUNCH
   TC_LAUNCH_CHECK(ctx, "plane_tc_kernel");
   *d_use_out = &d_P->use;

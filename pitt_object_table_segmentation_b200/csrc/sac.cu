@@ -751,7 +751,7 @@ __global__ void winner_kernel(const int* __restrict__ counts, const uint8_t* __r
     }
     __syncwarp();
     int idx = __shfl_sync(0xffffffffu, (l == 0) ? ((bi == INT_MAX) ? -1 : bi) : 0, 0);
-    if (l < 8) best_coeffs[l] = (idx >= 0) ? coeffs8[(size_t)idx * 8 + l] : 0.0f;
+    if (l < 8) best_coeffs[l] = (idx >= 0 && coeffs8) ? coeffs8[(size_t)idx * 8 + l] : 0.0f;
   }
 }
 

@@ -61,7 +61,6 @@ extern unsigned long long g_plane_tc_stats[2 + 160 + 16];
 extern int g_plane_tc_collect_stats;
 extern int g_plane_tc_dump;
 extern int g_plane_tc_variant;
-extern int g_plane_tc_time_kernel;
 extern int g_plane_tc_nwq;
 extern float g_plane_tc_acc_ulps;
 extern std::vector<float> g_plane_tc_dump_host;

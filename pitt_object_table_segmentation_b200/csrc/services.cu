@@ -996,4 +996,28 @@ int pitt_segment_frames_batched(pitt_ctx* const* ctxs, int n_ctx, const void* co
   return pitt_segment_raw_frames_batched(ctxs, n_ctx, frames, n_points, stride_bytes, n_frames, nullptr, params, results);
 }
 
+int pitt_segment_clouds_batched(pitt_ctx* const* ctxs, int n_ctx, const pitt_cloud* const* clouds, int n_frames,
+                                const pitt_frame_params* params, pitt_frame_result* results) {
+  if (!ctxs || n_ctx <= 0) return PITT_ERR_CUDA;
+  for (int t = 0; t < n_ctx; ++t)
+    if (!ctxs[t]) return PITT_ERR_CUDA;
+  if (n_frames < 0 || (n_frames > 0 && (!clouds || !results)) || !params)
+    return fail(ctxs[0], PITT_ERR_INVALID, "pitt_segment_clouds_batched arguments");
+  std::atomic<int> first_error(PITT_OK);
+  auto worker = [&](int t) {
+    for (int i = t; i < n_frames; i += n_ctx) {
+      const int st = clouds[i] ? pitt_segment_frame(ctxs[t], clouds[i], params, &results[i]) : PITT_ERR_INVALID;
+      if (st != PITT_OK) {
+        int expected = PITT_OK;
+        first_error.compare_exchange_strong(expected, st);
+      }
+    }
+  };
+  std::vector<std::thread> threads;
+  for (int t = 1; t < n_ctx; ++t) threads.emplace_back(worker, t);
+  worker(0);
+  for (auto& th : threads) th.join();
+  return first_error.load();
+}
+
 }  // extern "C"

@@ -400,6 +400,17 @@ def test_cabi_library_exports_every_declared_symbol(built):
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in pitt_b200.h but not exported"
     assert declared == set(pkg.EXPORTED_SYMBOLS)
+    # the test / measurement hooks have their own header; together the two headers declare EVERY pitt_* export of the library
+    dbg = open(os.path.join(ROOT, "include", "pitt_b200_debug.h")).read()
+    dbg = re.sub(r"/\*.*?\*/", "", dbg, flags=re.S)
+    declared_dbg = set(re.findall(r"\b(pitt_debug_[a-z0-9_]+)\s*\(", dbg))
+    assert declared_dbg == set(pkg.DEBUG_SYMBOLS)
+    for name in sorted(declared_dbg):
+        assert hasattr(lib, name), f"{name} declared in pitt_b200_debug.h but not exported"
+    import subprocess
+    nm = subprocess.run(["nm", "-D", "--defined-only", pkg.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {ln.split()[-1] for ln in nm.splitlines() if " T pitt_" in ln}
+    assert exported == declared | declared_dbg, sorted(exported ^ (declared | declared_dbg))
 
 
 def test_struct_layouts_match_header(built):
@@ -538,20 +549,32 @@ def test_ros_shims_compile_against_the_c_abi():
     assert "syntax ok" in out.stdout
 
 
-def test_bench_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` times the oracle on the host cores (no GPU needed) and prints ONE JSON line with the
-    keys the driver reads"""
+def _bench_reference_line(*extra):
     import json
     import subprocess
     import sys
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
-                         capture_output=True, text=True, timeout=300)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", *extra],
+                         capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
-    d = json.loads(lines[0])
-    assert d["impl"] == "reference" and d["metric"] == "RANSAC hypothesis-point evals/s" and d["unit"] == "evals/s"
-    assert d["higher_is_better"] is True and d["value"] > 1e7 and d["n_gpus"] == 1 and d["steps"] == 1
+    return json.loads(lines[0])
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` times the oracle's frame path on the host cores (no GPU needed) and prints ONE JSON line
+    with the keys the driver reads: the headline metric is segmented frames/s on 307 200-point frames"""
+    d = _bench_reference_line()
+    assert d["impl"] == "reference" and d["metric"] == "segmented frames/s (307k-pt cloud)" and d["unit"] == "frames/s"
+    assert d["higher_is_better"] is True and 0.05 < d["value"] < 1e4 and d["n_gpus"] == 1 and d["steps"] == 1
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "307200" in d["config"]["workload"]
+
+
+def test_bench_reference_arm_c2_workload():
+    """--workload c2: the table-plane RANSAC configuration (evals/s) as the printed metric"""
+    d = _bench_reference_line("--workload", "c2")
+    assert d["impl"] == "reference" and d["metric"] == "RANSAC hypothesis-point evals/s" and d["unit"] == "evals/s"
+    assert d["value"] > 1e7 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"]

@@ -48,6 +48,12 @@ void pitt_debug_plane_tc_nwq(int v);
 void pitt_debug_plane_tc_time_kernel(pitt_ctx* ctx, int enable);
 double pitt_debug_plane_tc_kernel_ms(pitt_ctx* ctx);
 
+/* enable = collect diagnostics in the large-cloud k-NN calls that follow (process wide); out16 (nullable) = those of the last
+ * call of ctx: [0] finite points, [1] queries that took the general ring search, [2..5] fast-path attempts at level 0..3,
+ * [6] candidates inside the guaranteed radius, [7] / [8] attempts with > 64 candidates below the threshold (first / later
+ * bucket), [9] attempts with < k candidates inside the guaranteed radius, [10] most candidates of one attempt */
+int pitt_debug_knn_stats(pitt_ctx* ctx, int enable, int64_t* out16);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,10 +1,14 @@
-// knn.cu — exact k-nearest-neighbour search on the uniform grid and the normal estimator (K8).
+// knn.cu — exact k-nearest-neighbour search (multi-level grid for large clouds, warp-cooperative all-pairs selection for
+// object clusters) and the normal estimator (K8).
 //
 // Replaces ne.compute() of PCManager::estimateNormal (reference: src/point_cloud_library/
 // pc_manager.cpp:68-78; pcl::NormalEstimation::computeFeature + KdTreeFLANN::nearestKSearch,
 // SURVEY.md B.7/B.8): k neighbours including the query, ordered by (squared distance, index);
 // float covariance accumulated in that order; eigen33; curvature; flip towards the viewpoint.
+#include <climits>
 #include <cmath>
+#include <cstdlib>
+#include <algorithm>
 
 #include "grid.cuh"
 #include "pitt_math.cuh"
@@ -15,181 +19,6 @@ constexpr int KNN_KMAX = 64;
 constexpr int KNN_BRUTE_MAX = 4096;  // below this size the all-pairs kernel beats grid + ring search
 
 __device__ __forceinline__ bool cand_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
-
-// max-heap on (d, i). The heap of one thread lives in SHARED memory with the thread index as the
-// fastest dimension (entry p of thread t at [p * KNN_TPB + t]): whatever heap positions the 32 lanes of
-// a warp touch, they hit 32 different banks, so every access is one conflict-free wavefront. (A
-// thread-local array goes through L1 as local memory and divergent positions cost one sector each.)
-constexpr int KNN_TPB = 128;
-struct Heap {
-  float* d;  // [k][KNN_TPB]
-  int* i;
-  __device__ __forceinline__ float& D(int p) const { return d[p * KNN_TPB]; }
-  __device__ __forceinline__ int& I(int p) const { return i[p * KNN_TPB]; }
-};
-__device__ __forceinline__ void heap_sift_down(const Heap& h, int size, int pos) {
-  float d = h.D(pos);
-  int i = h.I(pos);
-  for (;;) {
-    int c = 2 * pos + 1;
-    if (c >= size) break;
-    float cd = h.D(c);
-    int ci = h.I(c);
-    if (c + 1 < size) {
-      const float cd1 = h.D(c + 1);
-      const int ci1 = h.I(c + 1);
-      if (cand_less(cd, ci, cd1, ci1)) { ++c; cd = cd1; ci = ci1; }
-    }
-    if (!cand_less(d, i, cd, ci)) break;
-    h.D(pos) = cd;
-    h.I(pos) = ci;
-    pos = c;
-  }
-  h.D(pos) = d;
-  h.I(pos) = i;
-}
-__device__ __forceinline__ void heap_sift_up(const Heap& h, int pos) {
-  float d = h.D(pos);
-  int i = h.I(pos);
-  while (pos > 0) {
-    int p = (pos - 1) >> 1;
-    const float pd = h.D(p);
-    const int pi = h.I(p);
-    if (!cand_less(pd, pi, d, i)) break;
-    h.D(pos) = pd;
-    h.I(pos) = pi;
-    pos = p;
-  }
-  h.D(pos) = d;
-  h.I(pos) = i;
-}
-
-template <int MODE>
-__device__ __forceinline__ void knn_finish(const Heap& h, int size, int k, int qi, float4 q, const float4* __restrict__ xyz,
-                                           float vpx, float vpy, float vpz, int* __restrict__ out_idx,
-                                           float* __restrict__ out_sq, float4* __restrict__ out_nrm);
-
-template <int MODE>  // 0: neighbour lists, 1: normals
-__global__ void __launch_bounds__(KNN_TPB)
-knn_kernel(GridDev g, const float4* __restrict__ xyz, int k, float vpx, float vpy, float vpz, int* __restrict__ out_idx,
-           float* __restrict__ out_sq, float4* __restrict__ out_nrm) {
-  extern __shared__ __align__(16) unsigned char knn_smem[];
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= g.n) return;
-  const int want = min(k, g.n);
-  Heap hp;
-  hp.d = reinterpret_cast<float*>(knn_smem) + threadIdx.x;
-  hp.i = reinterpret_cast<int*>(knn_smem) + (size_t)k * KNN_TPB + threadIdx.x;
-  const float4 q = g.sorted[t];
-  const int qi = __float_as_int(q.w);
-  int size = 0;
-  float top_d = 0.0f;  // register copy of the heap maximum (valid when size == want)
-  int top_i = 0;
-  const int cx = grid_coord(q.x, g.mnx, g.inv_h, g.dx), cy = grid_coord(q.y, g.mny, g.inv_h, g.dy),
-            cz = grid_coord(q.z, g.mnz, g.inv_h, g.dz);
-  const int rmax = max(g.dx, max(g.dy, g.dz));
-  const float slack = 2e-3f * g.h;
-  for (int r = 0; r <= rmax; ++r) {
-    const int z0 = max(cz - r, 0), z1 = min(cz + r, g.dz - 1);
-    const int y0 = max(cy - r, 0), y1 = min(cy + r, g.dy - 1);
-    const int x0 = max(cx - r, 0), x1 = min(cx + r, g.dx - 1);
-    for (int z = z0; z <= z1; ++z)
-      for (int y = y0; y <= y1; ++y) {
-        const bool face = (abs(z - cz) == r) || (abs(y - cy) == r);
-        const int step = face ? 1 : max(1, x1 - x0);  // interior rows: only the two end cells
-        for (int x = x0; x <= x1; x += step) {
-          if (!face && abs(x - cx) != r) continue;
-          const int cell = (z * g.dy + y) * g.dx + x;
-          const int b = g.cell_start[cell], e = g.cell_start[cell + 1];
-          if (b == e) continue;
-          if (size == want) {
-            // prune: no point of this cell can beat the current k-th best if the cell's box is farther away.
-            // Walls are pulled in by slack = 2e-3 h (float rounding of the cell assignment), so the bound is safe.
-            const float lox = g.mnx + (float)x * g.h, loy = g.mny + (float)y * g.h, loz = g.mnz + (float)z * g.h;
-            const float gx = fmaxf(fmaxf(lox - q.x, q.x - (lox + g.h)) - slack, 0.0f);
-            const float gy = fmaxf(fmaxf(loy - q.y, q.y - (loy + g.h)) - slack, 0.0f);
-            const float gz = fmaxf(fmaxf(loz - q.z, q.z - (loz + g.h)) - slack, 0.0f);
-            if ((gx * gx + gy * gy) + gz * gz > top_d) continue;
-          }
-          for (int j = b; j < e; ++j) {
-            const float4 p = g.sorted[j];
-            const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
-            const float d = (ddx * ddx + ddy * ddy) + ddz * ddz;
-            const int pi = __float_as_int(p.w);
-            if (size < want) {
-              hp.D(size) = d;
-              hp.I(size) = pi;
-              heap_sift_up(hp, size);
-              ++size;
-              if (size == want) { top_d = hp.D(0); top_i = hp.I(0); }
-            } else if (cand_less(d, pi, top_d, top_i)) {
-              hp.D(0) = d;
-              hp.I(0) = pi;
-              heap_sift_down(hp, size, 0);
-              top_d = hp.D(0);
-              top_i = hp.I(0);
-            }
-          }
-        }
-      }
-    if (size >= want) {
-      // every point outside the cube of r cells around the query cell is farther than `bound`
-      float bound = 3.0e38f;
-      if (cx - r > 0) bound = fminf(bound, q.x - (g.mnx + (float)(cx - r) * g.h));
-      if (cx + r < g.dx - 1) bound = fminf(bound, (g.mnx + (float)(cx + r + 1) * g.h) - q.x);
-      if (cy - r > 0) bound = fminf(bound, q.y - (g.mny + (float)(cy - r) * g.h));
-      if (cy + r < g.dy - 1) bound = fminf(bound, (g.mny + (float)(cy + r + 1) * g.h) - q.y);
-      if (cz - r > 0) bound = fminf(bound, q.z - (g.mnz + (float)(cz - r) * g.h));
-      if (cz + r < g.dz - 1) bound = fminf(bound, (g.mnz + (float)(cz + r + 1) * g.h) - q.z);
-      bound -= 2e-3f * g.h;  // float rounding of the cell assignment
-      if (bound > 0.0f && top_d < bound * bound) break;
-    }
-  }
-  knn_finish<MODE>(hp, size, k, qi, q, xyz, vpx, vpy, vpz, out_idx, out_sq, out_nrm);
-}
-
-// heap -> sorted neighbour list -> outputs (shared by the grid and the brute-force kernels)
-template <int MODE>
-__device__ __forceinline__ void knn_finish(const Heap& h, int size, int k, int qi, float4 q, const float4* __restrict__ xyz,
-                                           float vpx, float vpy, float vpz, int* __restrict__ out_idx,
-                                           float* __restrict__ out_sq, float4* __restrict__ out_nrm) {
-  // heap sort -> ascending (distance, index)
-  for (int s = size - 1; s > 0; --s) {
-    float d = h.D(0);
-    int i = h.I(0);
-    h.D(0) = h.D(s);
-    h.I(0) = h.I(s);
-    h.D(s) = d;
-    h.I(s) = i;
-    heap_sift_down(h, s, 0);
-  }
-  if (MODE == 0) {
-    for (int s = 0; s < k; ++s) {
-      out_idx[(size_t)qi * k + s] = s < size ? h.I(s) : -1;
-      if (out_sq) out_sq[(size_t)qi * k + s] = s < size ? h.D(s) : CUDART_INF_F;
-    }
-    return;
-  }
-  if (size < 3) return;  // stays NaN
-  // computeMeanAndCovarianceMatrix: float accumulators in neighbour order
-  float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int s = 0; s < size; ++s) {
-    const float4 p = __ldg(xyz + h.I(s));
-    accu[0] += p.x * p.x; accu[1] += p.x * p.y; accu[2] += p.x * p.z;
-    accu[3] += p.y * p.y; accu[4] += p.y * p.z; accu[5] += p.z * p.z;
-    accu[6] += p.x; accu[7] += p.y; accu[8] += p.z;
-  }
-  float cov[9], cen[3], ev, evec[3];
-  cov_from_accu(accu, (float)size, cov, cen);
-  eigen33(cov, ev, evec);
-  float nx = evec[0], ny = evec[1], nz = evec[2];
-  const float eig_sum = cov[0] + cov[4] + cov[8];
-  const float curv = (eig_sum != 0.0f) ? fabsf(ev / eig_sum) : 0.0f;
-  const float vx = vpx - q.x, vy = vpy - q.y, vz = vpz - q.z;
-  const float cos_theta = (vx * nx + vy * ny + vz * nz);
-  if (cos_theta < 0.0f) { nx = -nx; ny = -ny; nz = -nz; }
-  out_nrm[qi] = make_float4(nx, ny, nz, curv);
-}
 
 // ---------------------------------------------------------------------------------------------
 // Small clouds (object clusters, a few thousand points): warp-cooperative exact selection.
@@ -369,26 +198,740 @@ __global__ void fill_knn_kernel(int* idx, float* sq, size_t n) {
   }
 }
 
-// occupied cells hold about k / KNN_CELL_DIV points (tuning knob, PITT_KNN_CELL_DIV overrides for experiments)
-static float knn_target_per_cell(int k) {
-  static float div = -1.0f;
-  if (div < 0.0f) {
-    const char* v = getenv("PITT_KNN_CELL_DIV");
-    div = v ? (float)atof(v) : 6.0f;  // measured on B200: 4 -> 1.28 ms, 6 -> 1.17 ms, 12 -> 1.12 ms (307 200 points, k = 50)
-    if (!(div > 0.0f)) div = 6.0f;
-  }
-  return fmaxf(2.0f, (float)k / div);
+
+// =====================================================================================================================
+// Multi-level grid + exact k-NN for large clouds (the 307 200-point frame of the headline metric).
+//
+// A Kinect-shaped frame is a surface seen in perspective: its point density varies by more than an order of magnitude
+// between the near and the far end of the table, so no single cell size of a uniform grid suits every query. The grid here
+// is ONE dense table of fine cells laid out block-Morton: blocks of 8 x 8 x 8 fine cells are ordered linearly, the 512
+// cells inside a block in Morton (z-order) code. An aligned cube of 2^l fine cells per side (l = 0..3) is then a contiguous
+// range of the table AND of the counting-sorted point array, i.e. the same table serves four cell sizes hf, 2hf, 4hf, 8hf.
+// Everything is built on the device from device-resident geometry (no host round trip): bounding box -> geometry -> cell
+// histogram -> block totals -> scan of the block totals -> per-block scan -> scatter (the histogram counts back down to zero).
+//
+// knn_fast_kernel: one thread per query, 32 consecutive queries of the Morton-sorted array per warp (spatial neighbours:
+// their loops have the same shape, 31 of 32 lanes active on the frame). A query picks the finest level whose PARENT cell holds
+// >= `need` points and looks at the 3 x 3 x 3 cells around it at that level:
+//   pass 1  histogram of the squared distances (32 buckets of 1/8 octave below the distance to the faces of the 27-cell block,
+//           inside which every point closer than that is guaranteed to lie) -> the bucket edge T at which the cumulative count
+//           reaches k; usable when T exists and at most 64 candidates lie below it
+//   pass 2  the <= 64 candidates with d2 <= T go to the thread's column of a shared-memory buffer as 64-bit keys
+//           (bits(d2) << 32 | index): unsigned order == (distance, index) order, the tie rule of the oracle
+//   sort    64 keys in REGISTERS with Batcher's odd-even merge network (543 compare-exchanges, compile-time indices)
+//   finish  the first k keys in order: neighbour lists, or the sequential float covariance + eigen33 + flip of
+//           NormalEstimation::computeFeature, bit-identical to the warp-cooperative kernels.
+// No heap, no data-dependent sift loops, branch-free inner loops (rejected candidates go to a spare bucket / key slot), four
+// loads in flight per lane.
+// knn_wide_kernel: the general exact search, one warp per query (ballot compaction + register bitonic top-64 like the
+// all-pairs kernel), over the 27 cells at rising levels and then over growing cubes of the coarsest cells, for the queries the
+// fast path hands over (0.4 % of the frame: sparse corners, density steps, > 64 candidates in one bucket, duplicates) and for
+// k > KNN_FAST_KMAX. Measured on B200 (307 200-point frame, k = 50): build 0.05 ms, fast 0.78 ms, wide 0.23 ms
+// (profiles/r02_knn_ncu.md); the round-1 heap kernel took 1.01 ms after a 0.15 ms build with two host round trips.
+// =====================================================================================================================
+constexpr int MG_CAP_CELLS = 1 << 22;  // dense table: at most 4 M fine cells (16 MB of int)
+constexpr int MG_CAP_BLOCKS = MG_CAP_CELLS >> 9;
+constexpr int MG_MAXLVL = 3;
+constexpr int KNN_FAST_KMAX = 56;      // 64-key buffer: k plus the contents of one 1/8-octave bucket
+constexpr int KNN_FAST_TPB = 128;
+
+struct MGrid {
+  float mnx, mny, mnz, hf, inv_hf;
+  int dx, dy, dz;     // fine cells per axis (multiples of 8)
+  int nbx, nby, nbz;  // blocks per axis
+  int ncells, nblocks;
+  int n_finite;
+};
+
+__device__ __forceinline__ int mg_spread3(int v) { return (v & 1) | ((v & 2) << 2) | ((v & 4) << 4); }
+__device__ __forceinline__ int mg_index(const MGrid& g, int cx, int cy, int cz) {
+  const int blk = ((cz >> 3) * g.nby + (cy >> 3)) * g.nbx + (cx >> 3);
+  return (blk << 9) | mg_spread3(cx & 7) | (mg_spread3(cy & 7) << 1) | (mg_spread3(cz & 7) << 2);
 }
-static size_t knn_smem_bytes(int k) { return (size_t)k * KNN_TPB * (sizeof(float) + sizeof(int)); }
-// heaps of up to KNN_KMAX entries need 64 KB of dynamic shared memory per CTA: opt in once per device
+__device__ __forceinline__ int mg_f2ord(float f) {
+  int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float mg_ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+__device__ __forceinline__ bool mg_finite3(float4 p) { return isfinite(p.x) && isfinite(p.y) && isfinite(p.z); }
+
+// scratch ints: [0..2] min, [3..5] max (ordered ints), [6] finite points, [7] fallback queue length
+__global__ void mg_init_kernel(int* __restrict__ bb) {
+  if (threadIdx.x < 3) bb[threadIdx.x] = INT_MAX;
+  else if (threadIdx.x < 6) bb[threadIdx.x] = INT_MIN;
+  else if (threadIdx.x < 8) bb[threadIdx.x] = 0;
+}
+__global__ void __launch_bounds__(256) mg_bbox_kernel(const float4* __restrict__ xyz, int n, int* __restrict__ bb) {
+  __shared__ int s_red[8][7];
+  int mn[3] = {INT_MAX, INT_MAX, INT_MAX}, mx[3] = {INT_MIN, INT_MIN, INT_MIN};
+  int cnt = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = __ldg(xyz + i);
+    if (!mg_finite3(p)) continue;
+    const int o[3] = {mg_f2ord(p.x), mg_f2ord(p.y), mg_f2ord(p.z)};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { mn[a] = min(mn[a], o[a]); mx[a] = max(mx[a], o[a]); }
+    ++cnt;
+  }
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    mn[a] = __reduce_min_sync(0xffffffffu, mn[a]);
+    mx[a] = __reduce_max_sync(0xffffffffu, mx[a]);
+  }
+  cnt = __reduce_add_sync(0xffffffffu, cnt);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) { s_red[w][a] = mn[a]; s_red[w][3 + a] = mx[a]; }
+    s_red[w][6] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x < 7) {  // one atomic per CTA and quantity (a warp-level atomic per quantity serialised 67 000 of them on the frame)
+    int v = s_red[0][threadIdx.x];
+    for (int i = 1; i < 8; ++i) {
+      const int o = s_red[i][threadIdx.x];
+      v = threadIdx.x < 3 ? min(v, o) : threadIdx.x < 6 ? max(v, o) : v + o;
+    }
+    if (threadIdx.x < 3) atomicMin(&bb[threadIdx.x], v);
+    else if (threadIdx.x < 6) atomicMax(&bb[threadIdx.x], v);
+    else if (v) atomicAdd(&bb[6], v);
+  }
+}
+// geometry on the device: fine cell size from the mean surface density (about c_avg points per fine cell if the cloud were a
+// uniform sheet over the two largest extents), enlarged until the table fits; one thread
+__global__ void mg_geom_kernel(const int* __restrict__ bb, float c_avg, MGrid* __restrict__ G) {
+  MGrid g;
+  g.n_finite = bb[6];
+  if (g.n_finite <= 0) {
+    g.mnx = g.mny = g.mnz = 0.0f; g.hf = g.inv_hf = 1.0f;
+    g.dx = g.dy = g.dz = 8; g.nbx = g.nby = g.nbz = 1; g.nblocks = 1; g.ncells = 512;
+    *G = g;
+    return;
+  }
+  const float mn[3] = {mg_ord2f(bb[0]), mg_ord2f(bb[1]), mg_ord2f(bb[2])};
+  const float mx[3] = {mg_ord2f(bb[3]), mg_ord2f(bb[4]), mg_ord2f(bb[5])};
+  float e[3] = {mx[0] - mn[0], mx[1] - mn[1], mx[2] - mn[2]};
+  float emax = fmaxf(e[0], fmaxf(e[1], e[2]));
+  float emin = fminf(e[0], fminf(e[1], e[2]));
+  float emid = (e[0] + e[1] + e[2]) - emax - emin;
+  if (!(emax > 1e-30f)) emax = 1e-30f;
+  const float area = fmaxf(emax * emid, emax * emax * 1e-6f);
+  float h = sqrtf(c_avg * area / (float)g.n_finite);
+  h = fmaxf(h, emax * 1e-5f);
+  int d[3], nb[3];
+  for (int it = 0; it < 200; ++it) {
+    const float inv = 1.0f / h;
+    double total = 1.0;
+    bool fits = true;
+    for (int a = 0; a < 3; ++a) {
+      const float c = floorf((mx[a] - mn[a]) * inv);  // the cell of the largest coordinate, same expression as mg_coord
+      if (!(c < 2.0e6f)) { fits = false; break; }
+      d[a] = (int)c + 1;
+      nb[a] = (d[a] + 7) >> 3;
+      total *= (double)nb[a];
+    }
+    if (fits && total * 512.0 <= (double)MG_CAP_CELLS) {
+      g.inv_hf = inv;
+      break;
+    }
+    h *= 1.26f;
+    g.inv_hf = 1.0f / h;
+  }
+  g.hf = 1.0f / g.inv_hf;
+  g.mnx = mn[0]; g.mny = mn[1]; g.mnz = mn[2];
+  g.nbx = nb[0]; g.nby = nb[1]; g.nbz = nb[2];
+  g.dx = nb[0] << 3; g.dy = nb[1] << 3; g.dz = nb[2] << 3;
+  g.nblocks = nb[0] * nb[1] * nb[2];
+  g.ncells = g.nblocks << 9;
+  *G = g;
+}
+__device__ __forceinline__ int mg_coord(float v, float mn, float inv_h, int dim) {
+  const int c = (int)floorf((v - mn) * inv_h);
+  return min(max(c, 0), dim - 1);
+}
+__global__ void __launch_bounds__(256) mg_zero_kernel(const MGrid* __restrict__ G, int4* __restrict__ cnt4) {
+  const int nc4 = (G->ncells >> 2) + 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nc4; i += gridDim.x * blockDim.x) cnt4[i] = make_int4(0, 0, 0, 0);
+}
+__global__ void __launch_bounds__(256) mg_hist_kernel(const float4* __restrict__ xyz, int n, const MGrid* __restrict__ G,
+                                                      int* __restrict__ cnt, int* __restrict__ cellid) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const MGrid g = *G;
+  const float4 p = __ldg(xyz + i);
+  int cell = -1;
+  if (mg_finite3(p)) {
+    cell = mg_index(g, mg_coord(p.x, g.mnx, g.inv_hf, g.dx), mg_coord(p.y, g.mny, g.inv_hf, g.dy), mg_coord(p.z, g.mnz, g.inv_hf, g.dz));
+    atomicAdd(&cnt[cell], 1);
+  }
+  cellid[i] = cell;
+}
+// block totals: one warp per block of 512 cells
+__global__ void __launch_bounds__(256) mg_blocksum_kernel(const MGrid* __restrict__ G, const int* __restrict__ cnt, int* __restrict__ bsum) {
+  const int blk = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (blk >= G->nblocks) return;
+  const int4* src = reinterpret_cast<const int4*>(cnt + ((size_t)blk << 9) + lane * 16);
+  int sum = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int4 q = src[j];
+    sum += (q.x + q.y) + (q.z + q.w);
+  }
+  sum = __reduce_add_sync(0xffffffffu, sum);
+  if (lane == 0) bsum[blk] = sum;
+}
+// exclusive scan of the block totals (at most MG_CAP_BLOCKS = 8192: 8 per thread), one CTA
+__global__ void __launch_bounds__(1024) mg_top_kernel(const MGrid* __restrict__ G, const int* __restrict__ bsum, int* __restrict__ bbase,
+                                                      int* __restrict__ start) {
+  __shared__ int s_w[32];
+  const int nblk = G->nblocks;
+  int v[8], sum = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int i = threadIdx.x * 8 + j;
+    v[j] = i < nblk ? bsum[i] : 0;
+    sum += v[j];
+  }
+  int incl = sum;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if ((threadIdx.x & 31) >= o) incl += y;
+  }
+  if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int w = s_w[threadIdx.x];
+    int wi = w;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, wi, o);
+      if ((int)threadIdx.x >= o) wi += y;
+    }
+    s_w[threadIdx.x] = wi - w;
+  }
+  __syncthreads();
+  int run = s_w[threadIdx.x >> 5] + incl - sum;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int i = threadIdx.x * 8 + j;
+    if (i < nblk) bbase[i] = run;
+    run += v[j];
+  }
+  if (threadIdx.x == 1023) start[G->ncells] = run;  // == number of finite points
+}
+// one warp per block of 512 cells: lane l scans cells [16 l, 16 l + 16)
+__global__ void __launch_bounds__(256) mg_blockscan_kernel(const MGrid* __restrict__ G, const int* __restrict__ cnt,
+                                                           const int* __restrict__ bbase, int* __restrict__ start) {
+  const int blk = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (blk >= G->nblocks) return;
+  const int4* src = reinterpret_cast<const int4*>(cnt + ((size_t)blk << 9) + lane * 16);
+  int v[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int4 q = src[j];
+    v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+  }
+  int sum = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) sum += v[j];
+  int incl = sum;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  int run = bbase[blk] + incl - sum;
+  int4* dst = reinterpret_cast<int4*>(start + ((size_t)blk << 9) + lane * 16);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int4 q;
+    q.x = run; run += v[4 * j];
+    q.y = run; run += v[4 * j + 1];
+    q.z = run; run += v[4 * j + 2];
+    q.w = run; run += v[4 * j + 3];
+    dst[j] = q;
+  }
+}
+__global__ void __launch_bounds__(256) mg_scatter_kernel(const float4* __restrict__ xyz, int n, const int* __restrict__ cellid,
+                                                         const int* __restrict__ start, int* __restrict__ cnt,
+                                                         float4* __restrict__ sorted) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int cell = cellid[i];
+  if (cell < 0) return;
+  const float4 p = __ldg(xyz + i);
+  const int pos = start[cell] + atomicSub(&cnt[cell], 1) - 1;  // the histogram counts down to zero: no second table
+  sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+}
+
+// ---- per-query geometry at level l
+// squared distance below which every point is guaranteed to lie inside the (2r+1)^3 cells around the query's level-l cell
+// (faces on the border of the grid do not count: nothing lies beyond them); INF when the cube covers the whole grid
+__device__ __forceinline__ float mg_bound(const MGrid& g, float4 q, int X, int Y, int Z, int l, int r) {
+  float b = CUDART_INF_F;
+  const int lo[3] = {X - r, Y - r, Z - r}, hi[3] = {X + r + 1, Y + r + 1, Z + r + 1};
+  const int dim[3] = {g.dx, g.dy, g.dz};
+  const float mn[3] = {g.mnx, g.mny, g.mnz}, qq[3] = {q.x, q.y, q.z};
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    if (lo[a] > 0) b = fminf(b, qq[a] - (mn[a] + (float)(lo[a] << l) * g.hf));
+    if ((hi[a] << l) < dim[a]) b = fminf(b, (mn[a] + (float)(hi[a] << l) * g.hf) - qq[a]);
+  }
+  b -= 2e-3f * g.hf;  // float rounding of the cell assignment
+  return b;
+}
+
+#define CE(i, j)                                       \
+  {                                                    \
+    const unsigned long long a_ = key[i], b_ = key[j]; \
+    const bool s_ = b_ < a_;                           \
+    key[i] = s_ ? b_ : a_;                             \
+    key[j] = s_ ? a_ : b_;                             \
+  }
+
+// finest level l such that the query's ancestor cell one level up holds at least `need` points (monotone in l), MG_MAXLVL if
+// even the coarsest cell is that sparse. Judging by the PARENT cell keeps points that float next to a dense surface (object
+// rims, mixed pixels) at a fine level: their own cells are almost empty at every level, the surface next to them is not.
+__device__ __forceinline__ int mg_pick_level(const int* __restrict__ start, int m, int need) {
+  int lvl = MG_MAXLVL;
+#pragma unroll
+  for (int l = MG_MAXLVL; l >= 1; --l) {
+    const int base = (m >> (3 * l)) << (3 * l);
+    const int c = __ldg(start + base + (1 << (3 * l))) - __ldg(start + base);
+    if (c >= need) lvl = l - 1;
+  }
+  return lvl;
+}
+
+// visits the points of the 27 level-l cells around (X, Y, Z): f(point, valid). Four loads are in flight per lane (indices
+// clamped to the range, the surplus masked), so the L1 / L2 latency of a lane's private candidate stream overlaps with the
+// arithmetic of the previous four.
+template <typename F>
+__device__ __forceinline__ void mg_for_block27(const MGrid& g, const int* __restrict__ start, const float4* __restrict__ sorted, int X,
+                                               int Y, int Z, int l, F f) {
+  const int nx = g.dx >> l, ny = g.dy >> l, nz = g.dz >> l, span = 1 << (3 * l);
+  for (int c = -1; c <= 1; ++c) {
+    const int z = Z + c;
+    if (z < 0 || z >= nz) continue;
+    for (int b = -1; b <= 1; ++b) {
+      const int y = Y + b;
+      if (y < 0 || y >= ny) continue;
+      for (int a = -1; a <= 1; ++a) {
+        const int x = X + a;
+        if (x < 0 || x >= nx) continue;
+        const int idx = mg_index(g, x << l, y << l, z << l);
+        const int jb = __ldg(start + idx), je = __ldg(start + idx + span);
+        if (jb >= je) continue;
+        const int last = je - 1;
+        float4 c0 = __ldg(sorted + jb), c1 = __ldg(sorted + min(jb + 1, last)), c2 = __ldg(sorted + min(jb + 2, last)),
+               c3 = __ldg(sorted + min(jb + 3, last));
+        for (int j = jb; j < je; j += 4) {
+          // the next four are requested before the current four are consumed
+          const float4 n0 = __ldg(sorted + min(j + 4, last)), n1 = __ldg(sorted + min(j + 5, last)),
+                       n2 = __ldg(sorted + min(j + 6, last)), n3 = __ldg(sorted + min(j + 7, last));
+          f(c0, true);
+          f(c1, j + 1 < je);
+          f(c2, j + 2 < je);
+          f(c3, j + 3 < je);
+          c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        }
+      }
+    }
+  }
+}
+// number of points in those 27 cells
+__device__ __forceinline__ int mg_block27_count(const MGrid& g, const int* __restrict__ start, int X, int Y, int Z, int l) {
+  const int nx = g.dx >> l, ny = g.dy >> l, nz = g.dz >> l, span = 1 << (3 * l);
+  int tot = 0;
+  for (int c = -1; c <= 1; ++c) {
+    const int z = Z + c;
+    if (z < 0 || z >= nz) continue;
+    for (int b = -1; b <= 1; ++b) {
+      const int y = Y + b;
+      if (y < 0 || y >= ny) continue;
+      for (int a = -1; a <= 1; ++a) {
+        const int x = X + a;
+        if (x < 0 || x >= nx) continue;
+        const int idx = mg_index(g, x << l, y << l, z << l);
+        tot += __ldg(start + idx + span) - __ldg(start + idx);
+      }
+    }
+  }
+  return tot;
+}
+
+constexpr int KF_MCAP = 1536;  // queries with more points than this in their 27 cells go to the warp-per-query kernel
+
+template <int MODE>  // 0: neighbour lists, 1: normals
+__global__ void __launch_bounds__(KNN_FAST_TPB, 3)
+knn_fast_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, const float4* __restrict__ sorted,
+                const float4* __restrict__ xyz, int k, int need, float vpx, float vpy, float vpz, int* __restrict__ out_idx,
+                float* __restrict__ out_sq, float4* __restrict__ out_nrm, int* __restrict__ fb_count, int* __restrict__ fb_list,
+                unsigned long long* __restrict__ dbg) {
+  extern __shared__ __align__(16) unsigned long long knn_keys[];  // [warps][66][32]
+  const MGrid g = *G;
+  const int t = blockIdx.x * KNN_FAST_TPB + threadIdx.x;
+  if (t >= g.n_finite) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // key slot s of this thread: kcol[s * 32] (slot 64 takes the rejected candidates: no branch around the store);
+  // histogram bucket b: hcol[b * 32] (bucket 32 takes the candidates outside the window); the histogram aliases the key slots
+  // of the same warp, it is dead before the first key is written (__syncwarp in between)
+  unsigned long long* kcol = knn_keys + (size_t)warp * 66 * 32 + lane;
+  unsigned* hcol = reinterpret_cast<unsigned*>(knn_keys + (size_t)warp * 66 * 32) + lane;
+  const float4 q = __ldg(sorted + t);
+  const int cx = mg_coord(q.x, g.mnx, g.inv_hf, g.dx), cy = mg_coord(q.y, g.mny, g.inv_hf, g.dy), cz = mg_coord(q.z, g.mnz, g.inv_hf, g.dz);
+  const int lvl = mg_pick_level(start, mg_index(g, cx, cy, cz), need);
+  const int X = cx >> lvl, Y = cy >> lvl, Z = cz >> lvl;
+  // one attempt at this level; whatever does not fit (too many points around, fewer than k inside the guaranteed radius, more
+  // than 64 candidates below the bucket edge) is handed to the warp-per-query kernel with a level hint
+  int hand_over = -1;
+  unsigned tsel = 0;
+  const float bound = mg_bound(g, q, X, Y, Z, lvl, 1);
+  const float hl = g.hf * (float)(1 << lvl);
+  const float top = (bound > 0.0f) ? fminf(bound * bound, 27.5f * hl * hl) : 0.0f;  // cube = whole grid: its diagonal
+  const unsigned btop = __float_as_uint(top);
+  const int mtot = mg_block27_count(g, start, X, Y, Z, lvl);
+  if (btop < (40u << 20)) {
+    hand_over = lvl;
+  } else if (mtot > KF_MCAP) {
+    hand_over = max(lvl - 1, 0);  // far more points around than the level choice expected (a density step): try finer cells first
+  } else {
+#pragma unroll
+    for (int b = 0; b < 33; ++b) hcol[b * 32] = 0u;
+    mg_for_block27(g, start, sorted, X, Y, Z, lvl, [&](const float4 p, bool valid) {
+      const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
+      const unsigned db = __float_as_uint((ddx * ddx + ddy * ddy) + ddz * ddz);
+      const unsigned qq = min((btop - db) >> 20, 31u);
+      const unsigned bucket = (valid && db <= btop) ? 31u - qq : 32u;
+      hcol[bucket * 32] += 1u;
+    });
+    int cum = 0, bsel = -1, cat = 0;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+      cum += (int)hcol[b * 32];
+      if (bsel < 0 && cum >= k) { bsel = b; cat = cum; }
+    }
+    if (dbg) {  // diagnostics (pitt_debug_knn_stats)
+      atomicAdd(&dbg[lvl], 1ull);
+      atomicAdd(&dbg[4], (unsigned long long)cum);
+      if (bsel >= 0 && cat > 64) atomicAdd(&dbg[5 + (bsel == 0 ? 0 : 1)], 1ull);
+      if (bsel < 0) atomicAdd(&dbg[7], 1ull);
+      atomicMax(&dbg[8], (unsigned long long)mtot);
+    }
+    if (bsel < 0) hand_over = lvl + 1;        // fewer than k points inside the guaranteed radius: a cube twice as wide
+    else if (cat > 64) hand_over = lvl;       // the k-th neighbour lies far below the window, or > 64 candidates in one bucket
+    else tsel = btop - ((unsigned)(31 - bsel) << 20);
+  }
+  if (hand_over >= 0) {
+    if (dbg && mtot > KF_MCAP) atomicAdd(&dbg[9], 1ull);
+    const int pos = atomicAdd(fb_count, 1);
+    fb_list[pos] = t | (hand_over << 28);
+  }
+  __syncwarp();  // the histogram columns are dead: the key columns may be written
+  if (hand_over < 0) {
+    int c = 0;
+    mg_for_block27(g, start, sorted, X, Y, Z, lvl, [&](const float4 p, bool valid) {
+      const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
+      const unsigned db = __float_as_uint((ddx * ddx + ddy * ddy) + ddz * ddz);
+      const bool in = valid && db <= tsel;
+      kcol[(in ? c : 64) * 32] = ((unsigned long long)db << 32) | (unsigned long long)(unsigned)__float_as_int(p.w);
+      c += in ? 1 : 0;
+    });
+    unsigned long long key[64];
+#pragma unroll
+    for (int s = 0; s < 64; ++s) key[s] = (s < c) ? kcol[s * 32] : ~0ull;
+#include "knn_sort64.inc"
+    const int qi = __float_as_int(q.w);
+    if (MODE == 0) {
+#pragma unroll
+      for (int s = 0; s < KNN_FAST_KMAX; ++s) {
+        if (s < k) {
+          out_idx[(size_t)qi * k + s] = (int)(unsigned)(key[s] & 0xffffffffull);
+          if (out_sq) out_sq[(size_t)qi * k + s] = __uint_as_float((unsigned)(key[s] >> 32));
+        }
+      }
+    } else {
+      // computeMeanAndCovarianceMatrix: float accumulators in neighbour order (k >= 3 on this path: the cloud has > 4096 points)
+      float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int s = 0; s < KNN_FAST_KMAX; ++s) {
+        if (s < k) {
+          const float4 p = __ldg(xyz + (int)(unsigned)(key[s] & 0xffffffffull));
+          accu[0] += p.x * p.x; accu[1] += p.x * p.y; accu[2] += p.x * p.z;
+          accu[3] += p.y * p.y; accu[4] += p.y * p.z; accu[5] += p.z * p.z;
+          accu[6] += p.x; accu[7] += p.y; accu[8] += p.z;
+        }
+      }
+      if (k >= 3) {
+        float cov[9], cen[3], ev, evec[3];
+        cov_from_accu(accu, (float)k, cov, cen);
+        eigen33(cov, ev, evec);
+        float nx = evec[0], ny = evec[1], nz = evec[2];
+        const float eig_sum = cov[0] + cov[4] + cov[8];
+        const float curv = (eig_sum != 0.0f) ? fabsf(ev / eig_sum) : 0.0f;
+        const float vx = vpx - q.x, vy = vpy - q.y, vz = vpz - q.z;
+        const float cos_theta = (vx * nx + vy * ny + vz * nz);
+        if (cos_theta < 0.0f) { nx = -nx; ny = -ny; nz = -nz; }
+        out_nrm[qi] = make_float4(nx, ny, nz, curv);
+      }
+    }
+  }
+}
+#undef CE
+
+// General exact search, one WARP per query (the selection machinery of knn_brute_kernel: ballot compaction of the candidates
+// that beat the current k-th best, register bitonic top-64, ties by index): the candidates are the 27 cells around the query at
+// its level; if the k-th best found there is not closer than the guaranteed radius, the level goes up; above MG_MAXLVL the
+// whole point array is the candidate set, which always ends the search. Serves the queries the fast kernel hands over (list,
+// *n_list on the device) and, with list == nullptr, every point (k > KNN_FAST_KMAX).
+template <int MODE>
+__global__ void __launch_bounds__(WS_WARPS * 32)
+knn_wide_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, const float4* __restrict__ sorted,
+                const float4* __restrict__ xyz, int n_xyz, int k, int need, float vpx, float vpy, float vpz, int* __restrict__ out_idx,
+                float* __restrict__ out_sq, float4* __restrict__ out_nrm, const int* __restrict__ n_list, const int* __restrict__ list) {
+  __shared__ float s_bd[WS_WARPS][64];
+  __shared__ int s_bi[WS_WARPS][64];
+  __shared__ int s_rb[WS_WARPS][32], s_pre[WS_WARPS][32];
+  const MGrid g = *G;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nq = list ? *n_list : g.n_finite;
+  // a fixed grid of warps strides over the queries (launching a CTA per 8 potential queries, almost all of them empty, costs
+  // more than the search itself)
+  for (int slot = blockIdx.x * WS_WARPS + warp; slot < nq; slot += gridDim.x * WS_WARPS) {
+  int t = slot, l = -1;
+  if (list) {
+    const int e = list[slot];
+    t = e & 0x0fffffff;
+    l = (e >> 28) & 7;
+  }
+  const float4 q = __ldg(sorted + t);
+  const int qi = __float_as_int(q.w);
+  const int cx = mg_coord(q.x, g.mnx, g.inv_hf, g.dx), cy = mg_coord(q.y, g.mny, g.inv_hf, g.dy), cz = mg_coord(q.z, g.mnz, g.inv_hf, g.dz);
+  if (l < 0) l = mg_pick_level(start, mg_index(g, cx, cy, cz), need);
+  const int want = min(k, g.n_finite);
+  float kd[4];
+  int ki[4];
+  float thr_d;
+  int thr_i, count;
+  auto flush = [&]() {
+    kd[2] = (lane < count) ? s_bd[warp][lane] : CUDART_INF_F;
+    ki[2] = (lane < count) ? s_bi[warp][lane] : 0x7fffffff;
+    kd[3] = (lane + 32 < count) ? s_bd[warp][lane + 32] : CUDART_INF_F;
+    ki[3] = (lane + 32 < count) ? s_bi[warp][lane + 32] : 0x7fffffff;
+    __syncwarp();
+    ws_sort128(kd, ki, lane);
+    count = 0;
+    const int r = (k - 1) >> 5, ll = (k - 1) & 31;
+    const float td = (r == 0) ? kd[0] : kd[1];
+    const int ti = (r == 0) ? ki[0] : ki[1];
+    thr_d = __shfl_sync(0xffffffffu, td, ll);
+    thr_i = __shfl_sync(0xffffffffu, ti, ll);
+  };
+  // search sequence: the 27 cells at level l, l + 1, ... MG_MAXLVL, then cubes of 5^3, 7^3, ... cells at MG_MAXLVL; a cube that
+  // covers the whole grid has an infinite guaranteed radius and ends the search
+  l = min(l, MG_MAXLVL);
+  for (int rad = 1;;) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { kd[r] = CUDART_INF_F; ki[r] = 0x7fffffff; }
+    thr_d = CUDART_INF_F;
+    thr_i = 0x7fffffff;
+    count = 0;
+    const int X = cx >> l, Y = cy >> l, Z = cz >> l;
+    const int side = 2 * rad + 1, ncell = side * side * side;
+    const float bound = mg_bound(g, q, X, Y, Z, l, rad);
+    for (int cb = 0; cb < ncell; cb += 32) {  // 32 cells at a time: one range per lane
+      int jb = 0, len = 0;
+      const int ci = cb + lane;
+      if (ci < ncell) {
+        const int x = X + (ci % side) - rad, y = Y + ((ci / side) % side) - rad, z = Z + (ci / (side * side)) - rad;
+        if (x >= 0 && y >= 0 && z >= 0 && x < (g.dx >> l) && y < (g.dy >> l) && z < (g.dz >> l)) {
+          const int idx = mg_index(g, x << l, y << l, z << l);
+          jb = __ldg(start + idx);
+          len = __ldg(start + idx + (1 << (3 * l))) - jb;
+        }
+      }
+      int incl = len;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      const int mtot = __shfl_sync(0xffffffffu, incl, 31);
+      if (mtot == 0) continue;
+      __syncwarp();
+      s_rb[warp][lane] = jb;
+      s_pre[warp][lane] = incl - len;
+      __syncwarp();
+      for (int base = 0; base < mtot; base += 32) {
+        const int fi = base + lane;
+        float d = CUDART_INF_F;
+        int pi = 0x7fffffff;
+        if (fi < mtot) {
+          int r = 0;
+#pragma unroll
+          for (int s = 16; s > 0; s >>= 1)
+            if (s_pre[warp][r + s] <= fi) r += s;
+          const float4 p = __ldg(sorted + s_rb[warp][r] + (fi - s_pre[warp][r]));
+          const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
+          d = (ddx * ddx + ddy * ddy) + ddz * ddz;
+          pi = __float_as_int(p.w);
+        }
+        const bool pass = (d < CUDART_INF_F) && cand_less(d, pi, thr_d, thr_i);
+        const unsigned mask = __ballot_sync(0xffffffffu, pass);
+        if (mask) {
+          bool pass2 = pass;
+          unsigned mask2 = mask;
+          if (count + __popc(mask) > 64) {
+            flush();
+            pass2 = pass && cand_less(d, pi, thr_d, thr_i);  // the threshold is tighter after a flush
+            mask2 = __ballot_sync(0xffffffffu, pass2);
+          }
+          if (pass2) {
+            const int pos = count + __popc(mask2 & ((1u << lane) - 1u));
+            s_bd[warp][pos] = d;
+            s_bi[warp][pos] = pi;
+          }
+          count += __popc(mask2);
+          __syncwarp();
+        }
+      }
+    }
+    flush();
+    // exact iff the k-th best is closer than everything outside the cube can be (an infinite bound: the cube is the grid)
+    if (!(bound < CUDART_INF_F)) break;
+    if (thr_d < CUDART_INF_F && bound > 0.0f && thr_d < bound * bound) break;
+    if (l < MG_MAXLVL) ++l;
+    else ++rad;
+  }
+  int size = 0;
+  {
+    const unsigned m0 = __ballot_sync(0xffffffffu, kd[0] < CUDART_INF_F), m1 = __ballot_sync(0xffffffffu, kd[1] < CUDART_INF_F);
+    size = min(want, __popc(m0) + __popc(m1));
+  }
+  if (MODE == 0) {
+    for (int tt = lane; tt < k; tt += 32) {
+      const float dd_ = (tt < 32) ? kd[0] : kd[1];
+      const int ii_ = (tt < 32) ? ki[0] : ki[1];
+      out_idx[(size_t)qi * k + tt] = tt < size ? ii_ : -1;
+      if (out_sq) out_sq[(size_t)qi * k + tt] = tt < size ? dd_ : CUDART_INF_F;
+    }
+    continue;
+  }
+  if (size < 3) continue;
+  float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float4 p0 = (ki[0] >= 0 && ki[0] < n_xyz) ? __ldg(xyz + ki[0]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 p1 = (ki[1] >= 0 && ki[1] < n_xyz) ? __ldg(xyz + ki[1]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int tt = 0; tt < size; ++tt) {
+    const float4 src = (tt < 32) ? p0 : p1;
+    const float px = __shfl_sync(0xffffffffu, src.x, tt & 31), py = __shfl_sync(0xffffffffu, src.y, tt & 31),
+                pz = __shfl_sync(0xffffffffu, src.z, tt & 31);
+    accu[0] += px * px; accu[1] += px * py; accu[2] += px * pz;
+    accu[3] += py * py; accu[4] += py * pz; accu[5] += pz * pz;
+    accu[6] += px; accu[7] += py; accu[8] += pz;
+  }
+  if (lane != 0) continue;
+  float cov[9], cen[3], ev, evec[3];
+  cov_from_accu(accu, (float)size, cov, cen);
+  eigen33(cov, ev, evec);
+  float nx = evec[0], ny = evec[1], nz = evec[2];
+  const float eig_sum = cov[0] + cov[4] + cov[8];
+  const float curv = (eig_sum != 0.0f) ? fabsf(ev / eig_sum) : 0.0f;
+  const float vx = vpx - q.x, vy = vpy - q.y, vz = vpz - q.z;
+  const float cos_theta = (vx * nx + vy * ny + vz * nz);
+  if (cos_theta < 0.0f) { nx = -nx; ny = -ny; nz = -nz; }
+  out_nrm[qi] = make_float4(nx, ny, nz, curv);
+  }  // queries of this warp
+}
+
+int g_knn_stats = 0;  // pitt_debug_knn_stats(ctx, out, enable): collect the diagnostics of knn_fast_kernel
+static float knn_env(const char* name, float dflt) {
+  const char* v = getenv(name);
+  if (!v) return dflt;
+  const float f = (float)atof(v);
+  return f > 0.0f ? f : dflt;
+}
+// tuning knobs (measured on B200, 307 200-point frame, k = 50; the environment variables are for experiments only)
+static float knn_c_avg() { static float v = knn_env("PITT_KNN_CAVG", 2.5f); return v; }             // mean points per fine cell
+static int knn_need(int k) { static float f = knn_env("PITT_KNN_NEED", 2.0f); return std::max(8, (int)ceilf(f * (float)k)); }  // points in the parent cell
+
+constexpr size_t KNN_FAST_SMEM = (size_t)(KNN_FAST_TPB / 32) * 66 * 32 * sizeof(unsigned long long);
+// the fast kernel needs more than 48 KB of dynamic shared memory: opt in once per device
 static int knn_smem_opt_in(pitt_ctx* ctx) {
   static bool done[64] = {false};
   const int dev = ctx->device & 63;
   if (done[dev]) return PITT_OK;
-  const int bytes = (int)knn_smem_bytes(KNN_KMAX);
-  PITT_CUDA(ctx, cudaFuncSetAttribute(knn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  PITT_CUDA(ctx, cudaFuncSetAttribute(knn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  PITT_CUDA(ctx, cudaFuncSetAttribute(knn_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KNN_FAST_SMEM));
+  PITT_CUDA(ctx, cudaFuncSetAttribute(knn_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KNN_FAST_SMEM));
   done[dev] = true;
+  return PITT_OK;
+}
+
+struct MGridBuf {
+  MGrid* d_G;
+  int* d_start;
+  float4* d_sorted;
+  int* d_scr;      // [0..5] bounding box, [6] finite points, [7] ring-search queue length, [8..] 64-bit diagnostics
+  int* d_fb_list;
+};
+// Builds the multi-level grid of d_xyz[0..n) on ctx->stream; nothing here waits for the device. The two dense tables live
+// in the context (allocated once, reused by every call: calls of one context are ordered on its stream), the n-sized arrays
+// in the per-call arena.
+static int mgrid_build(pitt_ctx* ctx, const float4* d_xyz, int n, MGridBuf* out) {
+  if (!ctx->mg_tables) {
+    const size_t bytes = (size_t)(2 * (MG_CAP_CELLS + 4) + 2 * MG_CAP_BLOCKS) * sizeof(int) + 256;
+    PITT_CUDA(ctx, cudaMalloc(&ctx->mg_tables, bytes));
+  }
+  int* d_cnt = reinterpret_cast<int*>(ctx->mg_tables);
+  int* d_start = d_cnt + MG_CAP_CELLS + 4;
+  int* d_bsum = d_start + MG_CAP_CELLS + 4;
+  int* d_bbase = d_bsum + MG_CAP_BLOCKS;
+  MGrid* d_G = reinterpret_cast<MGrid*>(d_bbase + MG_CAP_BLOCKS);
+  int* d_scr = nullptr;
+  int* d_cellid = nullptr;
+  PITT_TRY(arena_alloc(ctx, 8 + 32, &d_scr));
+  PITT_CUDA(ctx, cudaMemsetAsync(d_scr + 8, 0, 32 * sizeof(int), ctx->stream));
+  PITT_TRY(arena_alloc(ctx, (size_t)n, &d_cellid));
+  PITT_TRY(arena_alloc(ctx, (size_t)n, &out->d_sorted));
+  PITT_TRY(arena_alloc(ctx, (size_t)n, &out->d_fb_list));
+  const int pb = std::max(1, std::min(cdiv(n, 2048), ctx->sm_count * 2));
+  mg_init_kernel<<<1, 32, 0, ctx->stream>>>(d_scr);
+  mg_bbox_kernel<<<pb, 256, 0, ctx->stream>>>(d_xyz, n, d_scr);
+  mg_geom_kernel<<<1, 1, 0, ctx->stream>>>(d_scr, knn_c_avg(), d_G);
+  mg_zero_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_G, reinterpret_cast<int4*>(d_cnt));
+  mg_hist_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_xyz, n, d_G, d_cnt, d_cellid);
+  mg_blocksum_kernel<<<MG_CAP_BLOCKS / 8, 256, 0, ctx->stream>>>(d_G, d_cnt, d_bsum);
+  mg_top_kernel<<<1, 1024, 0, ctx->stream>>>(d_G, d_bsum, d_bbase, d_start);
+  mg_blockscan_kernel<<<MG_CAP_BLOCKS / 8, 256, 0, ctx->stream>>>(d_G, d_cnt, d_bbase, d_start);
+  mg_scatter_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_xyz, n, d_cellid, d_start, d_cnt, out->d_sorted);
+  ctx->launches += 9;
+  PITT_CUDA(ctx, cudaGetLastError());
+  out->d_G = d_G;
+  out->d_start = d_start;
+  out->d_scr = d_scr;
+  return PITT_OK;
+}
+
+// exact k-NN of every point of a large cloud; MODE 0 writes the neighbour lists, MODE 1 the normals
+template <int MODE>
+static int knn_large(pitt_ctx* ctx, const float4* d_xyz, int n, int k, const float vp[3], int* d_idx, float* d_sq, float4* d_nrm) {
+  MGridBuf mg;
+  PITT_TRY(mgrid_build(ctx, d_xyz, n, &mg));
+  PITT_TRY(knn_smem_opt_in(ctx));
+  const int need = knn_need(k);
+  if (k <= KNN_FAST_KMAX && n < (1 << 28)) {
+    knn_fast_kernel<MODE><<<cdiv(n, KNN_FAST_TPB), KNN_FAST_TPB, KNN_FAST_SMEM, ctx->stream>>>(
+        mg.d_G, mg.d_start, mg.d_sorted, d_xyz, k, need, vp[0], vp[1], vp[2], d_idx, d_sq, d_nrm, mg.d_scr + 7, mg.d_fb_list,
+        g_knn_stats ? reinterpret_cast<unsigned long long*>(mg.d_scr + 8) : nullptr);
+    // the queries the fast path handed over, a warp each (their number is only known on the device: CTAs beyond it return at
+    // once; a few per cent of the points at most, so a quarter of the worst case is launched and the rest, if any, follows)
+    knn_wide_kernel<MODE><<<std::min(cdiv(n, WS_WARPS), ctx->sm_count * 8), WS_WARPS * 32, 0, ctx->stream>>>(
+        mg.d_G, mg.d_start, mg.d_sorted, d_xyz, n, k, need, vp[0], vp[1], vp[2], d_idx, d_sq, d_nrm, mg.d_scr + 7, mg.d_fb_list);
+    ctx->launches += 2;
+  } else {
+    knn_wide_kernel<MODE><<<std::min(cdiv(n, WS_WARPS), ctx->sm_count * 8), WS_WARPS * 32, 0, ctx->stream>>>(
+        mg.d_G, mg.d_start, mg.d_sorted, d_xyz, n, k, need, vp[0], vp[1], vp[2], d_idx, d_sq, d_nrm, nullptr, nullptr);
+    ctx->launches++;
+  }
+  PITT_CUDA(ctx, cudaGetLastError());
+  ctx->knn_scr = mg.d_scr;  // diagnostics: pitt_debug_knn_stats reads [6] (finite points) and [7] (ring-search queries)
   return PITT_OK;
 }
 
@@ -404,14 +947,7 @@ int estimate_normals_impl(pitt_ctx* ctx, const float4* d_xyz, int n, int k, cons
     PITT_CUDA(ctx, cudaGetLastError());
     return PITT_OK;
   }
-  GridDev g;
-  PITT_TRY(grid_build(ctx, d_xyz, n, -1.0f, knn_target_per_cell(k), &g));
-  if (g.n <= 0) return PITT_OK;
-  PITT_TRY(knn_smem_opt_in(ctx));
-  knn_kernel<1><<<cdiv(g.n, KNN_TPB), KNN_TPB, knn_smem_bytes(k), ctx->stream>>>(g, d_xyz, k, vp[0], vp[1], vp[2], nullptr, nullptr, d_nrm);
-  ctx->launches++;
-  PITT_CUDA(ctx, cudaGetLastError());
-  return PITT_OK;
+  return knn_large<1>(ctx, d_xyz, n, k, vp, nullptr, nullptr, d_nrm);
 }
 
 }  // namespace pitt
@@ -453,19 +989,35 @@ int pitt_knn(pitt_ctx* ctx, const pitt_cloud* c, int k, int32_t* out_idx, float*
       knn_brute_kernel<0><<<cdiv(n, WS_WARPS), WS_WARPS * 32, 0, ctx->stream>>>(c->d_xyz, n, k, 0.f, 0.f, 0.f, d_idx, d_sq, nullptr);
       ctx->launches++;
     } else {
-      GridDev g;
-      PITT_TRY(grid_build(ctx, c->d_xyz, n, -1.0f, knn_target_per_cell(k), &g));
-      if (g.n > 0) {
-        PITT_TRY(knn_smem_opt_in(ctx));
-        knn_kernel<0><<<cdiv(g.n, KNN_TPB), KNN_TPB, knn_smem_bytes(k), ctx->stream>>>(g, c->d_xyz, k, 0.f, 0.f, 0.f, d_idx, d_sq, nullptr);
-        ctx->launches++;
-      }
+      const float vp[3] = {0.f, 0.f, 0.f};
+      PITT_TRY(knn_large<0>(ctx, c->d_xyz, n, k, vp, d_idx, d_sq, nullptr));
     }
     PITT_CUDA(ctx, cudaMemcpyAsync(out_idx, d_idx, tot * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (out_sqdist) PITT_CUDA(ctx, cudaMemcpyAsync(out_sqdist, d_sq, tot * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     PITT_CUDA(ctx, pitt::stream_sync(ctx));
   }
   timer.finish();
+  return PITT_OK;
+}
+
+/* test / measurement hook (include/pitt_b200_debug.h): enable = collect diagnostics in the following large-cloud k-NN calls;
+ * out16 (nullable) = those of the last call of this context (waits for the stream): [0] finite points, [1] queries that took
+ * the ring search, [2..5] fast-path attempts at level 0..3, [6] candidates inside the guaranteed radius (sum over attempts),
+ * [7] / [8] attempts with more than 64 candidates below the threshold (first bucket / later bucket), [9] attempts with fewer
+ * than k candidates inside the guaranteed radius, [10] largest number of candidates of one attempt */
+int pitt_debug_knn_stats(pitt_ctx* ctx, int enable, int64_t* out16) {
+  g_knn_stats = enable;
+  if (!out16) return PITT_OK;
+  if (!ctx || !ctx->knn_scr) return PITT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  int h[8 + 32] = {0};
+  PITT_CUDA(ctx, cudaMemcpyAsync(h, ctx->knn_scr, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  PITT_CUDA(ctx, pitt::stream_sync(ctx));
+  for (int i = 0; i < 16; ++i) out16[i] = 0;
+  out16[0] = h[6];
+  out16[1] = h[7];
+  const unsigned long long* d = reinterpret_cast<const unsigned long long*>(h + 8);
+  for (int i = 0; i < 9; ++i) out16[2 + i] = (int64_t)d[i];
   return PITT_OK;
 }
 

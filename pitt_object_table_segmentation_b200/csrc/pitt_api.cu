@@ -77,6 +77,7 @@ void pitt_destroy(pitt_ctx* ctx) {
   for (void* p : ctx->d_overflow) cudaFree(p);
   for (auto& b : ctx->cloud_pool) cudaFree(b.p);
   if (ctx->d_arena) cudaFree(ctx->d_arena);
+  if (ctx->mg_tables) cudaFree(ctx->mg_tables);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   if (ctx->h_pin2) cudaFreeHost(ctx->h_pin2);
   if (ctx->h_one) cudaFreeHost(ctx->h_one);

@@ -32,7 +32,7 @@ DEBUG_SYMBOLS = [
     "pitt_debug_plane_mode", "pitt_debug_force_generic_plane", "pitt_debug_score_mode", "pitt_debug_select_no_fuse",
     "pitt_debug_lm_cluster_min", "pitt_debug_stream_chunks", "pitt_debug_plane_filter_stats", "pitt_debug_plane_tc_stats",
     "pitt_debug_plane_tc_cta_cycles", "pitt_debug_plane_tc_dump", "pitt_debug_plane_tc_acc_ulps", "pitt_debug_plane_tc_variant",
-    "pitt_debug_plane_tc_nwq", "pitt_debug_plane_tc_time_kernel", "pitt_debug_plane_tc_kernel_ms", "pitt_debug_knn_stats",
+    "pitt_debug_plane_tc_nwq", "pitt_debug_plane_tc_time_kernel", "pitt_debug_plane_tc_kernel_ms", "pitt_debug_knn_stats", "pitt_debug_frame_mode",
 ]
 
 

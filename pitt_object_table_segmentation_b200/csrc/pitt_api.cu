@@ -78,6 +78,12 @@ void pitt_destroy(pitt_ctx* ctx) {
   for (auto& b : ctx->cloud_pool) cudaFree(b.p);
   if (ctx->d_arena) cudaFree(ctx->d_arena);
   if (ctx->mg_tables) cudaFree(ctx->mg_tables);
+  for (int i = 0; i < 4; ++i) {
+    if (ctx->fit_streams[i]) { cudaStreamSynchronize(ctx->fit_streams[i]); cudaStreamDestroy(ctx->fit_streams[i]); }
+    if (ctx->ev_fit_join[i]) cudaEventDestroy(ctx->ev_fit_join[i]);
+  }
+  if (ctx->ev_fit_fork) cudaEventDestroy(ctx->ev_fit_fork);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   if (ctx->h_pin2) cudaFreeHost(ctx->h_pin2);
   if (ctx->h_one) cudaFreeHost(ctx->h_one);
@@ -787,6 +793,7 @@ void pitt_debug_force_generic_plane(int on) { g_force_generic_plane = on; }
 void pitt_debug_plane_mode(int mode) { g_plane_mode = mode; }
 void pitt_debug_score_mode(int mode) { g_score_mode = mode; }
 void pitt_debug_select_no_fuse(int v) { g_select_no_fuse = v; }
+void pitt_debug_frame_mode(int legacy) { g_frame_legacy = legacy; }
 void pitt_debug_lm_cluster_min(int rows) { g_lm_cluster_min = rows; }
 void pitt_debug_plane_filter_stats(int enable, uint64_t* out2) {
   g_plane_filter_collect_stats = enable;

@@ -53,6 +53,13 @@ struct pitt_ctx {
   bool time_tc_kernel = false;                   // pitt_debug_plane_tc_time_kernel(ctx, 1)
   int* d_ready = nullptr;   // 16 arrival flags (device) and the pinned word they are raised from
   int* h_one = nullptr;
+  // services.cu: the primitive fits of a frame run as asynchronous chains on helper streams; pinned staging for their sample
+  // tables and result blocks
+  cudaStream_t fit_streams[4] = {};
+  cudaEvent_t ev_fit_join[4] = {};
+  cudaEvent_t ev_fit_fork = nullptr;
+  void* h_stage = nullptr;
+  size_t h_stage_bytes = 0;
   void* mg_tables = nullptr;  // knn.cu: the two dense cell tables of the multi-level grid (allocated on first use)
   int* knn_scr = nullptr;     // knn.cu: scratch of the last large-cloud k-NN (diagnostics, arena memory)
   void* h_pin2 = nullptr;  // pinned block for the gathered sample points (h_pin holds the sample indices at that time)

@@ -1865,4 +1865,157 @@ int sac_segment_impl(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& 
   return PITT_OK;
 }
 
+
+// ------------------------------------------------------------------ seg.segment() without host round trips
+// RandomSampleConsensus::computeModel's stop rule on the device: the same sequential scan as ransac_scan above (best-so-far with
+// strict '>', adaptive k from the inlier ratio, skipped samples, iterations_ > max_iterations_ break) over the H scored
+// hypotheses of the stream, by one thread on a shared-memory copy of the counts. pow / log are CUDA's double functions; where the
+// result could differ from the host's libm in a way that changes a decision (k within 1e-9 of an integer that still matters), or
+// the batch ends before the loop does, or a speculative plane sample turns out collinear, a flag is raised and the caller
+// repeats the fit on the synchronous path. ints: [0] best position, [1] best count, [6] iterations, [7] skipped, [8] flags.
+constexpr int SCAN_FLAG_NEED_MORE = 1, SCAN_FLAG_AMBIGUOUS = 2, SCAN_FLAG_BAD_SAMPLE = 4;
+__global__ void __launch_bounds__(256)
+ransac_scan_kernel(const int* __restrict__ counts, const uint8_t* __restrict__ flags, int H, int n, int S, int max_iterations,
+                   double log_probability, int speculative_plane, const float* __restrict__ coeffs8, int* __restrict__ ints,
+                   float* __restrict__ model_out) {
+  extern __shared__ __align__(16) unsigned char scan_smem[];
+  int* s_cnt = reinterpret_cast<int*>(scan_smem);
+  uint8_t* s_flag = reinterpret_cast<uint8_t*>(s_cnt + H);
+  for (int i = threadIdx.x; i < H; i += blockDim.x) { s_cnt[i] = counts[i]; s_flag[i] = flags[i]; }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  const double one_over_indices = 1.0 / (double)n;
+  const int max_skip = max_iterations * 10;
+  int iterations = 0, skipped = 0, pos = 0, best = -INT_MAX, best_pos = -1, fl = 0;
+  double k = 1.0;
+  while ((double)iterations < k && skipped < max_skip) {
+    if (pos >= H) { fl |= SCAN_FLAG_NEED_MORE; break; }
+    const int h = pos++;
+    if (!(s_flag[h] & 1)) {
+      if (speculative_plane) fl |= SCAN_FLAG_BAD_SAMPLE;  // getSamples would have redrawn this triple
+      ++skipped;
+      continue;
+    }
+    const int cnt = s_cnt[h];
+    if (cnt > best) {
+      best = cnt;
+      best_pos = h;
+      const double w = (double)cnt * one_over_indices;
+      double p_no = 1.0 - pow(w, (double)S);
+      p_no = fmax(DBL_EPSILON, p_no);
+      p_no = fmin(1.0 - DBL_EPSILON, p_no);
+      k = log_probability / log(p_no);
+      if (k < (double)max_iterations + 2.0 && fabs(k - rint(k)) <= 1e-9 * fmax(1.0, fabs(k))) fl |= SCAN_FLAG_AMBIGUOUS;
+    }
+    ++iterations;
+    if (iterations > max_iterations) break;
+  }
+  ints[0] = best_pos;
+  ints[1] = best_pos >= 0 ? best : 0;
+  ints[6] = iterations;
+  ints[7] = skipped;
+  ints[8] = fl;
+  for (int i = 0; i < 8; ++i) model_out[i] = best_pos >= 0 ? coeffs8[(size_t)best_pos * 8 + i] : 0.0f;
+}
+// ALL_H: the winner kernel's {index, count} plus the bookkeeping of the block above
+__global__ void all_h_info_kernel(int H, int* __restrict__ ints) {
+  ints[6] = H;
+  ints[7] = 0;
+  ints[8] = 0;
+}
+__global__ void first_inlier_kernel(const int* __restrict__ inl, const int* __restrict__ n_final, int* __restrict__ out) {
+  *out = (*n_final > 0) ? inl[0] : -1;
+}
+
+// Enqueues one whole seg.segment() on ctx->stream and returns at once. *issued = false: the call is trivially empty (no model,
+// nothing enqueued). Results: d_ints[0] best position (-1 none), [1] best count, [2] inliers of the un-refined model, [3] final
+// inliers, [4] LM status, [5] LM nfev, [6] iterations, [7] skipped, [8] flags (non-zero: repeat on the synchronous path),
+// [9] first final inlier index (-1 none); d_flt[0..8) model, [8..16) refined. h_stage: pinned memory for the sample table,
+// valid until the stream has consumed it.
+int sac_segment_async(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& p, int* h_stage, SacAsync* out, bool* issued) {
+  const int model = p.model;
+  const int S = sample_size(model);
+  const int n = c->n;
+  *issued = false;
+  out->d_inl = nullptr;
+  out->H = 0;
+  if (model < 0 || model > 3) return fail(ctx, PITT_ERR_INVALID, "bad model");
+  if ((model == PITT_MODEL_CYLINDER || model == PITT_MODEL_CONE) && !c->has_normals)
+    return fail(ctx, PITT_ERR_STATE, "cylinder/cone segmentation needs normals on the cloud");
+  if (n < S || p.max_iterations < 0) return PITT_OK;
+  const bool all_h = (p.stop == PITT_STOP_ALL_H);
+  int H = all_h ? p.max_iterations : p.max_iterations + 1;
+  if (H <= 0) return PITT_OK;
+  const Limits L = limits_for(p);
+  const ScoreParams sp = score_params_for(p, L);
+  int* d_samples = nullptr;
+  HypRec* d_recs = nullptr;
+  float* d_coeffs8 = nullptr;
+  uint8_t* d_flags = nullptr;
+  int* d_counts = nullptr;
+  if (!out->d_ints) PITT_TRY(arena_alloc(ctx, 16, &out->d_ints));  // the caller may supply the result block
+  if (!out->d_flt) PITT_TRY(arena_alloc(ctx, 16, &out->d_flt));
+  PITT_TRY(arena_alloc(ctx, (size_t)n, &out->d_inl));
+  PITT_CUDA(ctx, cudaMemsetAsync(out->d_ints, 0, 16 * sizeof(int), ctx->stream));
+  bool speculative = false;
+  if (p.sampler == PITT_SAMPLER_PHILOX) {
+    PITT_TRY(arena_alloc(ctx, (size_t)H * S, &d_samples));
+    PITT_TRY(sac_philox_samples(ctx, d_samples, H, S, n, 1u));
+  } else {
+    if (p.sampler == PITT_SAMPLER_REPLAY) {
+      if (!p.replay_samples) return fail(ctx, PITT_ERR_INVALID, "replay_samples is null");
+      H = std::min(H, p.replay_count);
+      if (H <= 0) return PITT_OK;
+      for (size_t i = 0; i < (size_t)H * S; ++i) {
+        const int v = p.replay_samples[i];
+        if (v < 0 || v >= n) return fail(ctx, PITT_ERR_INVALID, "sample index out of range");
+        h_stage[i] = v;
+      }
+    } else {
+      const float* h_xyz = c->h_valid ? c->h_xyz.data() : nullptr;
+      speculative = (model == PITT_MODEL_PLANE) && !h_xyz;
+      PclSampleStream stream(n, model, h_xyz);
+      int have = 0;
+      for (int h = 0; h < H; ++h) {
+        if (!stream.next(h_stage + (size_t)h * S)) break;
+        ++have;
+      }
+      H = have;
+      if (H <= 0) return PITT_OK;
+    }
+    PITT_TRY(arena_alloc(ctx, (size_t)H * S, &d_samples));
+    PITT_CUDA(ctx, cudaMemcpyAsync(d_samples, h_stage, (size_t)H * S * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  PITT_TRY(arena_alloc(ctx, (size_t)H, &d_recs));
+  PITT_TRY(arena_alloc(ctx, (size_t)H * 8, &d_coeffs8));
+  PITT_TRY(arena_alloc(ctx, (size_t)H, &d_flags));
+  PITT_TRY(arena_alloc(ctx, (size_t)H, &d_counts));
+  PITT_TRY(sac_estimate(ctx, c, model, d_samples, H, L, sp, d_recs, d_coeffs8, d_flags));
+  PITT_TRY(sac_score(ctx, c, model, d_recs, H, sp, d_counts));
+  int* d_ints = out->d_ints;
+  float* d_flt = out->d_flt;
+  if (all_h) {
+    PITT_TRY(sac_winner(ctx, d_counts, d_flags, H, d_coeffs8, d_ints, d_flt));
+    all_h_info_kernel<<<1, 1, 0, ctx->stream>>>(H, d_ints);
+    PITT_LAUNCH_CHECK(ctx, "all_h_info_kernel");
+  } else {
+    if ((size_t)H * 5 + 16 > 200 * 1024) return fail(ctx, PITT_ERR_INVALID, "sac_segment_async: too many hypotheses for the device scan");
+    const size_t smem = (size_t)H * 5 + 16;
+    static bool opt_in[64] = {false};
+    if (smem > 48 * 1024 && !opt_in[ctx->device & 63]) {
+      PITT_CUDA(ctx, cudaFuncSetAttribute(ransac_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      opt_in[ctx->device & 63] = true;
+    }
+    ransac_scan_kernel<<<1, 256, smem, ctx->stream>>>(d_counts, d_flags, H, n, S, p.max_iterations, log(1.0 - p.probability),
+                                                      speculative ? 1 : 0, d_coeffs8, d_ints, d_flt);
+    PITT_LAUNCH_CHECK(ctx, "ransac_scan_kernel");
+  }
+  PITT_TRY(sac_finish(ctx, c, p, L, sp, d_flt, d_flt + 8, d_ints + 2, d_ints + 3, d_ints + 4, out->d_inl));
+  first_inlier_kernel<<<1, 1, 0, ctx->stream>>>(out->d_inl, d_ints + 3, d_ints + 9);
+  PITT_LAUNCH_CHECK(ctx, "first_inlier_kernel");
+  out->H = H;
+  *issued = true;
+  return PITT_OK;
+}
+
 }  // namespace pitt

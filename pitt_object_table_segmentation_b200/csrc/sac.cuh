@@ -47,6 +47,14 @@ int sac_philox_samples(pitt_ctx* ctx, int* d_samples, int H, int S, int n, uint3
 int sac_finish_from_winner(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& p, const int* d_samples_all, int H_all,
                            const int* d_best, SacDeviceResult* out);
 int sac_segment_impl(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& p, SacDeviceResult* out);
+// seg.segment() enqueued on ctx->stream without any host round trip (sac.cu)
+struct SacAsync {
+  int* d_ints;   // 16 ints, see sac_segment_async
+  float* d_flt;  // model[8], refined[8]
+  int* d_inl;    // final inliers (ascending), capacity n
+  int H;         // hypotheses scored
+};
+int sac_segment_async(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& p, int* h_stage, SacAsync* out, bool* issued);
 int fp32_peak(pitt_ctx* ctx, int kind, double* tflops);
 
 extern int g_force_generic_plane;
@@ -54,6 +62,7 @@ extern int g_plane_mode;
 bool plane_job_takes_tensor_path(int n, int H);
 extern int g_score_mode;
 extern int g_select_no_fuse;
+extern int g_frame_legacy;
 extern int g_lm_cluster_min;
 extern unsigned long long g_plane_filter_stats[2];
 extern int g_plane_filter_collect_stats;

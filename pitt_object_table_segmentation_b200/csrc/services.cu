@@ -305,6 +305,130 @@ static int axis_extent(pitt_ctx* ctx, const float4* d_pts, int n, const float* c
   return PITT_OK;
 }
 
+// The same without the host in the loop: the axis frame is derived from the refined coefficients on the device (identical
+// float operations), gated by the fit's result block (ints[0] best position, ints[3] final inliers): no model or no inliers
+// -> height -1, as the reference leaves it.
+__device__ __forceinline__ void axis_frame_dev(const float* co, AxisFrame& f, float* dirn) {
+  const float norm = sqrtf(co[3] * co[3] + co[4] * co[4] + co[5] * co[5]);
+  dirn[0] = co[3] / norm; dirn[1] = co[4] / norm; dirn[2] = co[5] / norm;
+  const float t1 = -1.0f, t2 = +1.0f;
+  const float A1[3] = {co[0] + dirn[0] * t1, co[1] + dirn[1] * t1, co[2] + dirn[2] * t1};
+  const float A2[3] = {co[0] + dirn[0] * t2, co[1] + dirn[1] * t2, co[2] + dirn[2] * t2};
+  f.a1x = A1[0]; f.a1y = A1[1]; f.a1z = A1[2];
+  f.dx = A2[0] - A1[0]; f.dy = A2[1] - A1[1]; f.dz = A2[2] - A1[2];
+  f.gdiv = f.dx * f.dx + f.dy * f.dy + f.dz * f.dz;
+}
+__device__ __forceinline__ bool axis_gate(const int* ints) { return ints[0] >= 0 && ints[3] > 0; }
+__global__ void axis_project_dev_kernel(const float4* __restrict__ pts, int n, const float* __restrict__ co, const int* __restrict__ ints,
+                                        float4* __restrict__ proj) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !axis_gate(ints)) return;
+  AxisFrame f;
+  float dirn[3];
+  axis_frame_dev(co, f, dirn);
+  float4 p = pts[i];
+  float ax = p.x - f.a1x, ay = p.y - f.a1y, az = p.z - f.a1z;
+  float G = (ax * f.dx + ay * f.dy + az * f.dz) / f.gdiv;
+  proj[i] = make_float4(f.a1x + G * f.dx, f.a1y + G * f.dy, f.a1z + G * f.dz, 0.0f);
+}
+__global__ void __launch_bounds__(AP_TPB)
+axis_pairs_dev_kernel(const float4* __restrict__ proj, int n, const int* __restrict__ ints, PairBest* __restrict__ block_best) {
+  if (!axis_gate(ints)) return;
+  __shared__ float4 s_j[AP_TPB];
+  __shared__ PairBest s_red[AP_TPB / 32];
+  const int i = blockIdx.x * AP_TPB + threadIdx.x;
+  const int jt = blockIdx.y;
+  PairBest best{-1.0f, -1, -1};
+  if (jt * AP_TPB < (blockIdx.x + 1) * AP_TPB) {
+    const int j0 = jt * AP_TPB;
+    s_j[threadIdx.x] = (j0 + threadIdx.x < n) ? proj[j0 + threadIdx.x] : make_float4(0, 0, 0, 0);
+    __syncthreads();
+    if (i < n) {
+      const float4 pi = proj[i];
+      const int jend = min(min(AP_TPB, n - j0), i - j0);
+      for (int t = 0; t < jend; ++t) {
+        const float4 pj = s_j[t];
+        const float ddx = pi.x - pj.x, ddy = pi.y - pj.y, ddz = pi.z - pj.z;
+        const float d = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
+        if (d > best.d) { best.d = d; best.i = i; best.j = j0 + t; }
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    PairBest ob;
+    ob.d = __shfl_down_sync(0xffffffffu, best.d, o);
+    ob.i = __shfl_down_sync(0xffffffffu, best.i, o);
+    ob.j = __shfl_down_sync(0xffffffffu, best.j, o);
+    if (ob.i >= 0 && (best.i < 0 || pair_better(ob.d, ob.i, ob.j, best))) best = ob;
+  }
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    PairBest b = s_red[0];
+    for (int w = 1; w < AP_TPB / 32; ++w) {
+      PairBest ob = s_red[w];
+      if (ob.i >= 0 && (b.i < 0 || pair_better(ob.d, ob.i, ob.j, b))) b = ob;
+    }
+    block_best[blockIdx.y * gridDim.x + blockIdx.x] = b;
+  }
+}
+// out: [0] height, [1] idx1, [2] idx2 (int bits), [3..5] p1, [6..8] p2, [9..11] normalised axis direction
+__global__ void __launch_bounds__(1024) axis_pairs_final_dev_kernel(const PairBest* __restrict__ bb, int nb, const float4* __restrict__ proj,
+                                                                    const float* __restrict__ co, const int* __restrict__ ints,
+                                                                    float* __restrict__ out) {
+  __shared__ PairBest s_red[32];
+  if (!axis_gate(ints)) {
+    if (threadIdx.x == 0) { out[0] = -1.0f; out[1] = __int_as_float(-1); out[2] = __int_as_float(-1); }
+    return;
+  }
+  PairBest best{-1.0f, -1, -1};
+  for (int t = threadIdx.x; t < nb; t += blockDim.x) {
+    PairBest ob = bb[t];
+    if (ob.i >= 0 && (best.i < 0 || pair_better(ob.d, ob.i, ob.j, best))) best = ob;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    PairBest ob;
+    ob.d = __shfl_down_sync(0xffffffffu, best.d, o);
+    ob.i = __shfl_down_sync(0xffffffffu, best.i, o);
+    ob.j = __shfl_down_sync(0xffffffffu, best.j, o);
+    if (ob.i >= 0 && (best.i < 0 || pair_better(ob.d, ob.i, ob.j, best))) best = ob;
+  }
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    PairBest b = s_red[0];
+    for (int w = 1; w < 32; ++w) {
+      PairBest ob = s_red[w];
+      if (ob.i >= 0 && (b.i < 0 || pair_better(ob.d, ob.i, ob.j, b))) b = ob;
+    }
+    out[0] = b.d;
+    out[1] = __int_as_float(b.i);
+    out[2] = __int_as_float(b.j);
+    if (b.i >= 0) {
+      float4 p1 = proj[b.i], p2 = proj[b.j];
+      out[3] = p1.x; out[4] = p1.y; out[5] = p1.z; out[6] = p2.x; out[7] = p2.y; out[8] = p2.z;
+    }
+    AxisFrame f;
+    float dirn[3];
+    axis_frame_dev(co, f, dirn);
+    out[9] = dirn[0]; out[10] = dirn[1]; out[11] = dirn[2];
+  }
+}
+static int axis_extent_async(pitt_ctx* ctx, const float4* d_pts, int n, const float* d_co, const int* d_ints, float* d_out16) {
+  if (n <= 0) return PITT_OK;
+  float4* d_proj = nullptr;
+  PairBest* d_bb = nullptr;
+  const int nt = cdiv(n, AP_TPB);
+  PITT_TRY(arena_alloc(ctx, (size_t)n, &d_proj));
+  PITT_TRY(arena_alloc(ctx, (size_t)nt * nt, &d_bb));
+  axis_project_dev_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_pts, n, d_co, d_ints, d_proj);
+  axis_pairs_dev_kernel<<<dim3(nt, nt), AP_TPB, 0, ctx->stream>>>(d_proj, n, d_ints, d_bb);
+  axis_pairs_final_dev_kernel<<<1, 1024, 0, ctx->stream>>>(d_bb, nt * nt, d_proj, d_co, d_ints, d_out16);
+  ctx->launches += 3;
+  PITT_CUDA(ctx, cudaGetLastError());
+  return PITT_OK;
+}
+
 // ------------------------------------------------------------------ supports
 struct SupportCfg {
   float minCloudPct, minPlanePct, maxVar, minVar, thr, w;
@@ -708,6 +832,157 @@ static void workers_run(pitt_workers* W, std::vector<std::function<void(pitt_ctx
 
 }  // namespace pitt
 
+namespace pitt {
+
+int g_frame_legacy = 0;  // test hook (pitt_debug_frame_mode): 1 = the round-1 frame path (one synchronous seg.segment() per fit)
+
+constexpr int FIT_WORDS = 48;  // result block of one fit: 16 ints (sac_segment_async) + model[8] + refined[8] + axis extent[16]
+constexpr int FIT_STREAMS = 4;
+
+static int stage_reserve(pitt_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->h_stage_bytes) return PITT_OK;
+  PITT_CUDA(ctx, cudaDeviceSynchronize());  // helper streams may still read the old block
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  ctx->h_stage = nullptr;
+  ctx->h_stage_bytes = 0;
+  const size_t want = bytes + bytes / 2 + 4096;
+  PITT_CUDA(ctx, cudaMallocHost(&ctx->h_stage, want));
+  ctx->h_stage_bytes = want;
+  return PITT_OK;
+}
+
+// All primitive fits of one support (clusters x {sphere, cylinder, cone, plane}; the reference calls the four services one after
+// the other for every cluster, ransac_segmentation.cpp:235-262) enqueued WITHOUT a host round trip: every fit is one chain of
+// launches (sample table upload, estimate, score, device-side PCL stop rule, select, refine, select, axis extent) on one of four
+// helper streams, all result blocks come back in ONE copy behind ONE synchronisation. A fit whose device-side scan raised a flag
+// (batch exhausted, a decision libm could round differently, a collinear speculative plane sample) is repeated on the
+// synchronous path; results are identical either way.
+static int frame_fits_async(pitt_ctx* ctx, std::vector<pitt_cloud>& cc, const pitt_sac_params* const sp[4], std::vector<PrimitiveHost>& ph,
+                            std::vector<int>& inl) {
+  const int nc = (int)cc.size(), nfits = nc * 4;
+  if (nfits == 0) return PITT_OK;
+  size_t words = (size_t)nfits * FIT_WORDS;
+  std::vector<size_t> sample_off((size_t)nfits, 0);
+  for (int c = 0; c < nc; ++c)
+    for (int m = 0; m < 4; ++m) {
+      sample_off[c * 4 + m] = words;
+      const int S = sp[m]->model == PITT_MODEL_PLANE ? 3 : sp[m]->model == PITT_MODEL_SPHERE ? 4 : sp[m]->model == PITT_MODEL_CYLINDER ? 2 : 3;
+      words += (size_t)(std::max(sp[m]->max_iterations, 0) + 1) * S + 4;
+    }
+  PITT_TRY(stage_reserve(ctx, words * 4));
+  int* h_stage = reinterpret_cast<int*>(ctx->h_stage);
+  int* d_res = nullptr;
+  PITT_TRY(arena_alloc(ctx, (size_t)nfits * FIT_WORDS, &d_res));
+  PITT_CUDA(ctx, cudaMemsetAsync(d_res, 0, (size_t)nfits * FIT_WORDS * sizeof(int), ctx->stream));
+  if (!ctx->fit_streams[0]) {
+    for (int i = 0; i < FIT_STREAMS; ++i) {
+      PITT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->fit_streams[i], cudaStreamNonBlocking));
+      PITT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fit_join[i], cudaEventDisableTiming));
+    }
+    PITT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fit_fork, cudaEventDisableTiming));
+  }
+  PITT_CUDA(ctx, cudaEventRecord(ctx->ev_fit_fork, ctx->stream));
+  for (int i = 0; i < FIT_STREAMS; ++i) PITT_CUDA(ctx, cudaStreamWaitEvent(ctx->fit_streams[i], ctx->ev_fit_fork, 0));
+  std::vector<char> issued((size_t)nfits, 0);
+  cudaStream_t main_stream = ctx->stream;
+  int status = PITT_OK, k = 0;
+  const int order[4] = {1, 2, 0, 3};  // longest chains first (cylinder, cone, sphere, plane)
+  for (int oi = 0; oi < 4 && status == PITT_OK; ++oi)
+    for (int c = 0; c < nc && status == PITT_OK; ++c, ++k) {
+      const int m = order[oi], slot = c * 4 + m;
+      ctx->stream = ctx->fit_streams[k % FIT_STREAMS];
+      SacAsync sa;
+      sa.d_ints = d_res + (size_t)slot * FIT_WORDS;
+      sa.d_flt = reinterpret_cast<float*>(sa.d_ints + 16);
+      bool did = false;
+      status = sac_segment_async(ctx, &cc[c], *sp[m], h_stage + sample_off[slot], &sa, &did);
+      issued[slot] = did ? 1 : 0;
+      if (status == PITT_OK && did && (sp[m]->model == PITT_MODEL_CYLINDER || sp[m]->model == PITT_MODEL_CONE))
+        status = axis_extent_async(ctx, cc[c].d_xyz, cc[c].n, sa.d_flt + 8, sa.d_ints, sa.d_flt + 16);
+    }
+  ctx->stream = main_stream;
+  for (int i = 0; i < FIT_STREAMS; ++i) {
+    cudaEventRecord(ctx->ev_fit_join[i], ctx->fit_streams[i]);
+    cudaStreamWaitEvent(main_stream, ctx->ev_fit_join[i], 0);
+  }
+  if (status != PITT_OK) {
+    pitt::stream_sync(ctx);
+    return status;
+  }
+  PITT_CUDA(ctx, cudaMemcpyAsync(h_stage, d_res, (size_t)nfits * FIT_WORDS * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PITT_CUDA(ctx, pitt::stream_sync(ctx));
+  for (int slot = 0; slot < nfits; ++slot) {
+    const int c = slot / 4, m = slot % 4;
+    const pitt_sac_params& p = *sp[m];
+    const int* I = h_stage + (size_t)slot * FIT_WORDS;
+    const float* F = reinterpret_cast<const float*>(I + 16);
+    const float* A = F + 16;
+    PrimitiveHost& P = ph[slot];
+    if (issued[slot] && I[8] != 0) {
+      // the device-side scan could not decide exactly like the host would: the synchronous path settles it
+      PITT_TRY(primitive_service_impl(ctx, &cc[c], p, &P));
+      PITT_TRY(count_after_zero_drop(ctx, P.sac, &inl[slot]));
+      continue;
+    }
+    memset(&P.sac.info, 0, sizeof(P.sac.info));
+    P.sac.info.best_hypothesis = -1;
+    P.sac.d_inliers = nullptr;
+    P.sac.n_inliers = 0;
+    P.sac.n_coeffs = 0;
+    for (int i = 0; i < 8; ++i) P.sac.coeffs[i] = 0.0f;
+    const bool found = issued[slot] && I[0] >= 0;
+    const int NC = (p.model == PITT_MODEL_PLANE || p.model == PITT_MODEL_SPHERE) ? 4 : 7;
+    if (issued[slot]) {
+      P.sac.info.iterations = I[6];
+      P.sac.info.skipped = I[7];
+    }
+    if (found) {
+      P.sac.info.best_hypothesis = I[0];
+      P.sac.info.best_count = I[1];
+      P.sac.info.n_inliers_model = I[2];
+      P.sac.info.lm_info = I[4];
+      P.sac.info.lm_nfev = I[5];
+      for (int i = 0; i < NC; ++i) { P.sac.info.model_coeffs[i] = F[i]; P.sac.coeffs[i] = F[8 + i]; }
+      P.sac.n_coeffs = NC;
+      P.sac.n_inliers = I[3];
+    }
+    const SacDeviceResult& r = P.sac;
+    P.n_coefficients = r.n_coeffs;
+    for (int i = 0; i < 8; ++i) P.coefficients[i] = i < r.n_coeffs ? r.coeffs[i] : 0.0f;
+    P.centroid[0] = P.centroid[1] = P.centroid[2] = 0.0f;
+    P.centroid_valid = 0;
+    if (p.model == PITT_MODEL_SPHERE) {
+      if (r.n_coeffs > 0) {
+        for (int a = 0; a < 3; ++a) P.centroid[a] = r.coeffs[a];
+        P.centroid_valid = 1;
+      }
+    } else if (p.model == PITT_MODEL_CYLINDER || p.model == PITT_MODEL_CONE) {
+      float height = -1.0f;
+      if (r.n_inliers > 0) {
+        height = A[0];
+        int idx1 = -1;
+        memcpy(&idx1, &A[1], 4);
+        if (p.model == PITT_MODEL_CYLINDER) {
+          if (idx1 >= 0) {
+            for (int a = 0; a < 3; ++a) P.centroid[a] = (A[3 + a] + A[6 + a]) / 2;
+            P.centroid_valid = 1;
+          }
+        } else {
+          for (int a = 0; a < 3; ++a) P.centroid[a] = r.coeffs[a] + 3.0f / 4.0f * height * A[9 + a];
+          P.centroid_valid = 1;
+        }
+      }
+      P.coefficients[r.n_coeffs] = height;  // coefficientVector.push_back(height)
+      P.n_coefficients = r.n_coeffs + 1;
+    }
+    // PCManager::inlierToVectorMsg drops the index VALUE 0 (pc_manager.cpp:108): the ascending list starts with it or not at all
+    inl[slot] = r.n_inliers - ((r.n_inliers > 0 && I[9] == 0) ? 1 : 0);
+  }
+  return PITT_OK;
+}
+
+}  // namespace pitt
+
 using namespace pitt;
 
 extern "C" {
@@ -887,8 +1162,14 @@ int pitt_segment_frame(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_frame_
       const pitt_sac_params* sp[4] = {&fp->sphere, &fp->cylinder, &fp->cone, &fp->plane};
       std::vector<PrimitiveHost> ph((size_t)nc * 4);
       std::vector<int> inl((size_t)nc * 4, 0), st((size_t)nc * 4, PITT_OK);
-      pitt_workers* W = workers_get(ctx);
-      if (W) {
+      pitt_workers* W = g_frame_legacy ? workers_get(ctx) : nullptr;
+      if (!g_frame_legacy) {
+        const int s1 = frame_fits_async(ctx, cc, sp, ph, inl);
+        if (s1 != PITT_OK) {
+          for (auto& v : cc) { v.d_xyz = nullptr; v.d_nrm = nullptr; }
+          return s1;
+        }
+      } else if (W) {
         if (!ctx->ev_fan) PITT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fan, cudaEventDisableTiming));
         PITT_CUDA(ctx, cudaEventRecord(ctx->ev_fan, ctx->stream));
         std::vector<std::function<void(pitt_ctx*)>> tasks;

@@ -10,6 +10,7 @@
 
 #include "cluster.cuh"
 #include "grid.cuh"
+#include "mgrid.cuh"
 
 namespace pitt {
 
@@ -110,6 +111,181 @@ __global__ void cc_label_kernel(const int* __restrict__ parent, const int* __res
 __global__ void fill_i32_kernel(int* p, int n, int v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The same extraction with every data-dependent size kept on the device (the clusterize() path of a frame): the grid is the
+// block-Morton grid of knn.cu with fine cells a hair wider than the tolerance, the components come from the same lock-free
+// union-find, and the PCL ordering (size descending, ties by smallest index), the size filter, the per-cluster ordered index
+// lists, the cluster clouds and the centroid sums are all produced by kernels. The host reads ONE block at the end.
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CC_WARPS * 32)
+cc_union_mg_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, const float4* __restrict__ sorted, float r2,
+                   int* __restrict__ parent) {
+  __shared__ int s_rb[CC_WARPS][32], s_pre[CC_WARPS][32];
+  const MGrid g = *G;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.x * CC_WARPS + warp;
+  if (t >= g.n_finite) return;
+  const float4 q = sorted[t];
+  const int qi = __float_as_int(q.w);
+  const int cx = mg_coord(q.x, g.mnx, g.inv_hf, g.dx), cy = mg_coord(q.y, g.mny, g.inv_hf, g.dy), cz = mg_coord(q.z, g.mnz, g.inv_hf, g.dz);
+  // the 27 surrounding fine cells (cells are at least tol wide; h is a hair above tol so that float rounding of the cell
+  // assignment cannot put a neighbour two cells away): one range per lane, walked as one flat list
+  int jb = 0, len = 0;
+  if (lane < 27) {
+    const int x = cx + (lane % 3) - 1, y = cy + ((lane / 3) % 3) - 1, z = cz + (lane / 9) - 1;
+    if (x >= 0 && y >= 0 && z >= 0 && x < g.dx && y < g.dy && z < g.dz) {
+      const int idx = mg_index(g, x, y, z);
+      jb = start[idx];
+      len = start[idx + 1] - jb;
+    }
+  }
+  int incl = len;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  const int mtot = __shfl_sync(0xffffffffu, incl, 31);
+  s_rb[warp][lane] = jb;
+  s_pre[warp][lane] = incl - len;
+  __syncwarp();
+  int rq = uf_find(parent, qi);
+  for (int fi = lane; fi < mtot; fi += 32) {
+    int r = 0;
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1)
+      if (s_pre[warp][r + s] <= fi) r += s;
+    const float4 p = sorted[s_rb[warp][r] + (fi - s_pre[warp][r])];
+    const int pi = __float_as_int(p.w);
+    if (pi >= qi) continue;  // each edge once
+    const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
+    const float d = (ddx * ddx + ddy * ddy) + ddz * ddz;
+    if (d < r2) {
+      const int rp = uf_find(parent, pi);
+      if (rp != rq) {
+        uf_union(parent, rq, rp);
+        rq = uf_find(parent, qi);
+      }
+    }
+  }
+}
+__global__ void cc_flatten_mg_kernel(const MGrid* __restrict__ G, const float4* __restrict__ sorted, int* __restrict__ parent,
+                                     int* __restrict__ size) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= G->n_finite) return;
+  const int i = __float_as_int(sorted[t].w);
+  const int r = uf_find(parent, i);
+  parent[i] = r;
+  atomicAdd(&size[r], 1);
+}
+// head: [0] clusters kept (nc), [1] roots that passed the size filter (> CC_MAXC: overflow, the caller takes the host path),
+// [2 .. 2+CC_MAXC) sizes in PCL order, then offsets [CC_MAXC + 1]
+__global__ void __launch_bounds__(CC_MAXC)
+cc_rank_dev_kernel(const int* __restrict__ n_roots, const int2* __restrict__ roots, int* __restrict__ rank_of, int* __restrict__ head) {
+  __shared__ int s_size[CC_MAXC], s_root[CC_MAXC], s_sorted[CC_MAXC];
+  const int R = *n_roots;
+  if (R > CC_MAXC) {
+    if (threadIdx.x == 0) { head[0] = 0; head[1] = R; }
+    return;
+  }
+  const int t = threadIdx.x;
+  if (t < R) { s_root[t] = roots[t].x; s_size[t] = roots[t].y; }
+  __syncthreads();
+  if (t < R) {
+    // PCL order: size descending; equal sizes by smallest point index (the root)
+    int rank = 0;
+    for (int j = 0; j < R; ++j)
+      rank += (s_size[j] > s_size[t] || (s_size[j] == s_size[t] && s_root[j] < s_root[t])) ? 1 : 0;
+    rank_of[s_root[t]] = rank;
+    s_sorted[rank] = s_size[t];
+  }
+  __syncthreads();
+  if (t == 0) {
+    head[0] = R;
+    head[1] = R;
+    int off = 0;
+    for (int c = 0; c < R; ++c) {
+      head[2 + c] = s_sorted[c];
+      head[2 + CC_MAXC + c] = off;
+      off += s_sorted[c];
+    }
+    head[2 + CC_MAXC + R] = off;
+  }
+}
+// one CTA per cluster: ordered (ascending index) compaction of its points -> index list + cluster cloud
+__global__ void __launch_bounds__(1024)
+cc_compact_dev_kernel(const float4* __restrict__ xyz, const int* __restrict__ labels, int n, const int* __restrict__ head,
+                      int* __restrict__ idx_out, float4* __restrict__ pts_out) {
+  __shared__ int s_w[32];
+  __shared__ int s_base, s_tile;
+  const int c = blockIdx.x;
+  if (c >= head[0]) return;
+  const int off = head[2 + CC_MAXC + c];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int tile = 0; tile < n; tile += 1024) {
+    const int i = tile + threadIdx.x;
+    const bool in = (i < n) && labels[i] == c;
+    const unsigned m = __ballot_sync(0xffffffffu, in);
+    if (lane == 0) s_w[warp] = __popc(m);
+    __syncthreads();
+    if (warp == 0) {
+      const int v = s_w[lane];
+      int incl = v;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      s_w[lane] = incl - v;
+      if (lane == 31) s_tile = incl;
+    }
+    __syncthreads();
+    const int base = s_base;
+    if (in) {
+      const int pos = off + base + s_w[warp] + __popc(m & ((1u << lane) - 1u));
+      idx_out[pos] = i;
+      pts_out[pos] = xyz[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_base = base + s_tile;
+    __syncthreads();
+  }
+}
+
+int euclidean_clusters_dev(pitt_ctx* ctx, const float4* d_xyz, int n, double tolerance, int min_size, int max_size, ClustersOnDevice* out) {
+  const float r2 = (float)(tolerance * tolerance);
+  MGridBuf mg;
+  PITT_TRY(mgrid_build(ctx, d_xyz, n, (float)tolerance * 1.001f + 1e-7f, &mg));
+  int* d_parent = nullptr;
+  int* d_size = nullptr;
+  int* d_rank = nullptr;
+  int* d_nroots = nullptr;
+  int2* d_roots = nullptr;
+  PITT_TRY(arena_alloc(ctx, (size_t)n, &d_parent));
+  PITT_TRY(arena_alloc(ctx, (size_t)n, &d_size));
+  PITT_TRY(arena_alloc(ctx, (size_t)n, &d_rank));
+  PITT_TRY(arena_alloc(ctx, 1, &d_nroots));
+  PITT_TRY(arena_alloc(ctx, (size_t)n, &d_roots));
+  PITT_TRY(arena_alloc(ctx, (size_t)n, &out->d_labels));
+  PITT_TRY(arena_alloc(ctx, (size_t)n, &out->d_idx));
+  PITT_TRY(arena_alloc(ctx, (size_t)n, &out->d_points));
+  PITT_TRY(arena_alloc(ctx, (size_t)CC_HEAD_INTS, &out->d_head));
+  cc_init_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_parent, d_size, n);
+  fill_i32_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_rank, n, -1);
+  PITT_CUDA(ctx, cudaMemsetAsync(d_nroots, 0, sizeof(int), ctx->stream));
+  PITT_CUDA(ctx, cudaMemsetAsync(out->d_head, 0, CC_HEAD_INTS * sizeof(int), ctx->stream));
+  cc_union_mg_kernel<<<cdiv(n, CC_WARPS), CC_WARPS * 32, 0, ctx->stream>>>(mg.d_G, mg.d_start, mg.d_sorted, r2, d_parent);
+  cc_flatten_mg_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(mg.d_G, mg.d_sorted, d_parent, d_size);
+  cc_roots_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_parent, d_size, n, std::max(min_size, 1), max_size, d_nroots, d_roots, n);
+  cc_rank_dev_kernel<<<1, CC_MAXC, 0, ctx->stream>>>(d_nroots, d_roots, d_rank, out->d_head);
+  cc_label_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_parent, d_size, d_rank, n, out->d_labels);
+  cc_compact_dev_kernel<<<CC_MAXC, 1024, 0, ctx->stream>>>(d_xyz, out->d_labels, n, out->d_head, out->d_idx, out->d_points);
+  ctx->launches += 8;
+  PITT_CUDA(ctx, cudaGetLastError());
+  return PITT_OK;
 }
 
 int euclidean_clusters_impl(pitt_ctx* ctx, const float4* d_xyz, int n, double tolerance, int min_size, int max_size,

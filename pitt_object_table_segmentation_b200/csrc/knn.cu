@@ -11,6 +11,7 @@
 #include <algorithm>
 
 #include "grid.cuh"
+#include "mgrid.cuh"
 #include "pitt_math.cuh"
 
 namespace pitt {
@@ -229,31 +230,8 @@ __global__ void fill_knn_kernel(int* idx, float* sq, size_t n) {
 // k > KNN_FAST_KMAX. Measured on B200 (307 200-point frame, k = 50): build 0.05 ms, fast 0.78 ms, wide 0.23 ms
 // (profiles/r02_knn_ncu.md); the round-1 heap kernel took 1.01 ms after a 0.15 ms build with two host round trips.
 // =====================================================================================================================
-constexpr int MG_CAP_CELLS = 1 << 22;  // dense table: at most 4 M fine cells (16 MB of int)
-constexpr int MG_CAP_BLOCKS = MG_CAP_CELLS >> 9;
-constexpr int MG_MAXLVL = 3;
 constexpr int KNN_FAST_KMAX = 56;      // 64-key buffer: k plus the contents of one 1/8-octave bucket
 constexpr int KNN_FAST_TPB = 128;
-
-struct MGrid {
-  float mnx, mny, mnz, hf, inv_hf;
-  int dx, dy, dz;     // fine cells per axis (multiples of 8)
-  int nbx, nby, nbz;  // blocks per axis
-  int ncells, nblocks;
-  int n_finite;
-};
-
-__device__ __forceinline__ int mg_spread3(int v) { return (v & 1) | ((v & 2) << 2) | ((v & 4) << 4); }
-__device__ __forceinline__ int mg_index(const MGrid& g, int cx, int cy, int cz) {
-  const int blk = ((cz >> 3) * g.nby + (cy >> 3)) * g.nbx + (cx >> 3);
-  return (blk << 9) | mg_spread3(cx & 7) | (mg_spread3(cy & 7) << 1) | (mg_spread3(cz & 7) << 2);
-}
-__device__ __forceinline__ int mg_f2ord(float f) {
-  int i = __float_as_int(f);
-  return i >= 0 ? i : i ^ 0x7fffffff;
-}
-__device__ __forceinline__ float mg_ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
-__device__ __forceinline__ bool mg_finite3(float4 p) { return isfinite(p.x) && isfinite(p.y) && isfinite(p.z); }
 
 // scratch ints: [0..2] min, [3..5] max (ordered ints), [6] finite points, [7] fallback queue length
 __global__ void mg_init_kernel(int* __restrict__ bb) {
@@ -299,7 +277,7 @@ __global__ void __launch_bounds__(256) mg_bbox_kernel(const float4* __restrict__
 }
 // geometry on the device: fine cell size from the mean surface density (about c_avg points per fine cell if the cloud were a
 // uniform sheet over the two largest extents), enlarged until the table fits; one thread
-__global__ void mg_geom_kernel(const int* __restrict__ bb, float c_avg, MGrid* __restrict__ G) {
+__global__ void mg_geom_kernel(const int* __restrict__ bb, float c_avg, float h_fixed, MGrid* __restrict__ G) {
   MGrid g;
   g.n_finite = bb[6];
   if (g.n_finite <= 0) {
@@ -318,6 +296,7 @@ __global__ void mg_geom_kernel(const int* __restrict__ bb, float c_avg, MGrid* _
   const float area = fmaxf(emax * emid, emax * emax * 1e-6f);
   float h = sqrtf(c_avg * area / (float)g.n_finite);
   h = fmaxf(h, emax * 1e-5f);
+  if (h_fixed > 0.0f) h = h_fixed;
   int d[3], nb[3];
   for (int it = 0; it < 200; ++it) {
     const float inv = 1.0f / h;
@@ -344,10 +323,6 @@ __global__ void mg_geom_kernel(const int* __restrict__ bb, float c_avg, MGrid* _
   g.nblocks = nb[0] * nb[1] * nb[2];
   g.ncells = g.nblocks << 9;
   *G = g;
-}
-__device__ __forceinline__ int mg_coord(float v, float mn, float inv_h, int dim) {
-  const int c = (int)floorf((v - mn) * inv_h);
-  return min(max(c, 0), dim - 1);
 }
 __global__ void __launch_bounds__(256) mg_zero_kernel(const MGrid* __restrict__ G, int4* __restrict__ cnt4) {
   const int nc4 = (G->ncells >> 2) + 1;
@@ -864,17 +839,10 @@ static int knn_smem_opt_in(pitt_ctx* ctx) {
   return PITT_OK;
 }
 
-struct MGridBuf {
-  MGrid* d_G;
-  int* d_start;
-  float4* d_sorted;
-  int* d_scr;      // [0..5] bounding box, [6] finite points, [7] ring-search queue length, [8..] 64-bit diagnostics
-  int* d_fb_list;
-};
 // Builds the multi-level grid of d_xyz[0..n) on ctx->stream; nothing here waits for the device. The two dense tables live
 // in the context (allocated once, reused by every call: calls of one context are ordered on its stream), the n-sized arrays
 // in the per-call arena.
-static int mgrid_build(pitt_ctx* ctx, const float4* d_xyz, int n, MGridBuf* out) {
+int mgrid_build(pitt_ctx* ctx, const float4* d_xyz, int n, float h_fixed, MGridBuf* out) {
   if (!ctx->mg_tables) {
     const size_t bytes = (size_t)(2 * (MG_CAP_CELLS + 4) + 2 * MG_CAP_BLOCKS) * sizeof(int) + 256;
     PITT_CUDA(ctx, cudaMalloc(&ctx->mg_tables, bytes));
@@ -894,7 +862,7 @@ static int mgrid_build(pitt_ctx* ctx, const float4* d_xyz, int n, MGridBuf* out)
   const int pb = std::max(1, std::min(cdiv(n, 2048), ctx->sm_count * 2));
   mg_init_kernel<<<1, 32, 0, ctx->stream>>>(d_scr);
   mg_bbox_kernel<<<pb, 256, 0, ctx->stream>>>(d_xyz, n, d_scr);
-  mg_geom_kernel<<<1, 1, 0, ctx->stream>>>(d_scr, knn_c_avg(), d_G);
+  mg_geom_kernel<<<1, 1, 0, ctx->stream>>>(d_scr, knn_c_avg(), h_fixed, d_G);
   mg_zero_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_G, reinterpret_cast<int4*>(d_cnt));
   mg_hist_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_xyz, n, d_G, d_cnt, d_cellid);
   mg_blocksum_kernel<<<MG_CAP_BLOCKS / 8, 256, 0, ctx->stream>>>(d_G, d_cnt, d_bsum);
@@ -913,7 +881,7 @@ static int mgrid_build(pitt_ctx* ctx, const float4* d_xyz, int n, MGridBuf* out)
 template <int MODE>
 static int knn_large(pitt_ctx* ctx, const float4* d_xyz, int n, int k, const float vp[3], int* d_idx, float* d_sq, float4* d_nrm) {
   MGridBuf mg;
-  PITT_TRY(mgrid_build(ctx, d_xyz, n, &mg));
+  PITT_TRY(mgrid_build(ctx, d_xyz, n, 0.0f, &mg));
   PITT_TRY(knn_smem_opt_in(ctx));
   const int need = knn_need(k);
   if (k <= KNN_FAST_KMAX && n < (1 << 28)) {

@@ -471,6 +471,192 @@ struct SupportDev {
   const float4* d_on;        // on-support cloud (points of the original cloud, original order)
 };
 
+static int stage_reserve(pitt_ctx* ctx, size_t bytes);
+
+// ---- device-side halves of one findSupports trip (no host round trip between them)
+__global__ void gather_points_dev_kernel(const float4* __restrict__ src, const int* __restrict__ idx, const int* __restrict__ m,
+                                         float4* __restrict__ dst, float* __restrict__ px, float* __restrict__ py) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < *m) {
+    const float4 p = src[idx[i]];
+    dst[i] = p;
+    px[i] = p.x;  // running-maximum scan inputs of getPointOnPlane
+    py[i] = p.y;
+  }
+}
+// isHorizontalPlane (supports…:161-179) on the device + the label of this trip: out[0] = horizontal, out[1] = level
+__global__ void support_decide_kernel(const float* __restrict__ co, SupportCfg c, int idxMapLayer, int* __restrict__ out) {
+  float div = sqrtf(co[0] * co[0] + co[1] * co[1] + co[2] * co[2]);
+  float nx = co[0] / div, ny = co[1] / div, nz = co[2] / div;
+  float crossX = ny * c.axis[2] - nz * c.axis[1];
+  float crossY = nz * c.axis[0] - nx * c.axis[2];
+  float crossZ = nx * c.axis[1] - ny * c.axis[0];
+  const bool h = ((crossX > c.minVar) && (crossX < c.maxVar)) && ((crossY > c.minVar) && (crossY < c.maxVar)) &&
+                 ((crossZ > c.minVar) && (crossZ < c.maxVar));
+  out[0] = h ? 1 : 0;
+  out[1] = h ? idxMapLayer : -1;
+}
+__global__ void idxmap_classify_dev_kernel(const int* __restrict__ prev, int n0, const int* __restrict__ flag, int n_flag,
+                                           const int* __restrict__ decide, int* __restrict__ is_else) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n0) return;
+  const int level = decide[1];
+  int v = prev ? prev[p] : p;  // first trip: the identity map
+  int e;
+  if (v > level && v < 0) e = 0;
+  else if (v >= 0 && v < n_flag && flag[v]) e = 0;
+  else e = 1;
+  is_else[p] = e;
+}
+__global__ void idxmap_write_dev_kernel(const int* __restrict__ prev, int n0, const int* __restrict__ flag, int n_flag,
+                                        const int* __restrict__ decide, const int* __restrict__ else_pos, int* __restrict__ out) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n0) return;
+  const int level = decide[1];
+  int v = prev ? prev[p] : p;
+  if (v > level && v < 0) out[p] = v;
+  else if (v >= 0 && v < n_flag && flag[v]) out[p] = level;
+  else out[p] = else_pos[p];
+}
+__global__ void __launch_bounds__(1024)
+bbox_quirk_dev_kernel(const float4* __restrict__ pts, const int* __restrict__ m_ptr, const int* __restrict__ decide,
+                      const float* __restrict__ pmax_x, const float* __restrict__ pmax_y, double* __restrict__ partial) {
+  __shared__ double s[5][32];
+  if (!decide[0]) return;  // not a horizontal plane: no getPointOnPlane
+  const int m = *m_ptr;
+  double xMax = -INFINITY, xMin = INFINITY, yMax = -INFINITY, yMin = INFINITY, zs = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    float4 p = pts[i];
+    if (p.x > pmax_x[i]) xMax = fmax(xMax, (double)p.x);
+    else if ((double)p.x < xMin) xMin = (double)p.x;
+    if (p.y > pmax_y[i]) yMax = fmax(yMax, (double)p.y);
+    else if ((double)p.y < yMin) yMin = (double)p.y;
+    zs += (double)p.z;
+  }
+  double v[5] = {xMax, xMin, yMax, yMin, zs};
+  for (int o = 16; o > 0; o >>= 1) {
+    v[0] = fmax(v[0], __shfl_down_sync(0xffffffffu, v[0], o));
+    v[1] = fmin(v[1], __shfl_down_sync(0xffffffffu, v[1], o));
+    v[2] = fmax(v[2], __shfl_down_sync(0xffffffffu, v[2], o));
+    v[3] = fmin(v[3], __shfl_down_sync(0xffffffffu, v[3], o));
+    v[4] += __shfl_down_sync(0xffffffffu, v[4], o);
+  }
+  if ((threadIdx.x & 31) == 0)
+    for (int k = 0; k < 5; ++k) s[k][threadIdx.x >> 5] = v[k];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double r[5] = {-INFINITY, INFINITY, -INFINITY, INFINITY, 0.0};
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      r[0] = fmax(r[0], s[0][w]); r[1] = fmin(r[1], s[1][w]);
+      r[2] = fmax(r[2], s[2][w]); r[3] = fmin(r[3], s[3][w]);
+      r[4] += s[4][w];
+    }
+    for (int k = 0; k < 5; ++k) partial[blockIdx.x * 5 + k] = r[k];
+  }
+}
+// folds the blocks and applies the offsets (supports…:222-228): out = xMin, xMax, yMin, yMax, zMed
+__global__ void bbox_quirk_final_dev_kernel(const double* __restrict__ partial, int blocks, const int* __restrict__ m_ptr,
+                                            const int* __restrict__ decide, SupportCfg c, double* __restrict__ out) {
+  if (threadIdx.x != 0 || !decide[0]) return;
+  double r[5] = {-INFINITY, INFINITY, -INFINITY, INFINITY, 0.0};
+  for (int b = 0; b < blocks; ++b) {
+    r[0] = fmax(r[0], partial[b * 5 + 0]); r[1] = fmin(r[1], partial[b * 5 + 1]);
+    r[2] = fmax(r[2], partial[b * 5 + 2]); r[3] = fmin(r[3], partial[b * 5 + 3]);
+    r[4] += partial[b * 5 + 4];
+  }
+  double xMax = r[0], xMin = r[1], yMax = r[2], yMin = r[3], zMed = r[4];
+  xMax -= c.offset[0];
+  xMin += c.offset[0];
+  yMax -= c.offset[1];
+  yMin += c.offset[1];
+  zMed = zMed / *m_ptr + c.offset[2];
+  out[0] = xMin; out[1] = xMax; out[2] = yMin; out[3] = yMax; out[4] = zMed;
+}
+__global__ void on_plane_flag_dev_kernel(const float4* __restrict__ orig, const int* __restrict__ map, int n0, const int* __restrict__ decide,
+                                         const double* __restrict__ bb, int* __restrict__ flag, int* __restrict__ keep) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n0) return;
+  bool k = false;
+  if (decide[0]) {
+    const int level = decide[1];
+    const double xMin = bb[0], xMax = bb[1], yMin = bb[2], yMax = bb[3], zMed = bb[4];
+    float4 p = orig[i];
+    k = (map[i] != level) && ((double)p.x > xMin && (double)p.x < xMax && (double)p.z > zMed && (double)p.y > yMin && (double)p.y < yMax);
+  }
+  flag[i] = k ? 1 : 0;
+  keep[i] = k ? 1 : 0;
+}
+
+struct TripDev {        // device outputs of the second half of a trip
+  int* d_decide;        // [0] horizontal, [1] level, [2] points on the support
+  int* d_new_map;
+  float4* d_support;
+  float4* d_rest;
+  float4* d_on;
+};
+// removePlaneInliner + createNewIdxMap + getPointOnPlane of one trip from device-resident inliers (d_inl, *d_n_inl ascending
+// indices into the trip's cloud of ni points) and coefficients; every size that depends on the RANSAC result stays on the device
+static int supports_trip_second_half(pitt_ctx* ctx, const pitt_cloud* cloud, const float4* d_iter, int ni, const int* d_prev_map,
+                                     const int* d_inl, const int* d_n_inl, const float* d_co, const SupportCfg& c, int idxMapLayer,
+                                     TripDev* T) {
+  const int n0 = cloud->n;
+  int* d_flag = nullptr;
+  int* d_keep = nullptr;
+  float* d_px = nullptr;
+  float* d_py = nullptr;
+  int* d_else = nullptr;
+  double* d_part = nullptr;
+  double* d_bb = nullptr;
+  int* d_onflag = nullptr;
+  int* d_onkeep = nullptr;
+  PITT_TRY(arena_alloc(ctx, 4, &T->d_decide));
+  PITT_TRY(arena_alloc(ctx, (size_t)ni, &d_flag));
+  PITT_TRY(arena_alloc(ctx, (size_t)ni, &d_keep));
+  PITT_TRY(arena_alloc(ctx, (size_t)ni, &T->d_support));
+  PITT_TRY(arena_alloc(ctx, (size_t)ni, &T->d_rest));
+  PITT_TRY(arena_alloc(ctx, (size_t)ni, &d_px));
+  PITT_TRY(arena_alloc(ctx, (size_t)ni, &d_py));
+  PITT_TRY(arena_alloc(ctx, (size_t)n0, &d_else));
+  PITT_TRY(arena_alloc(ctx, (size_t)n0, &T->d_new_map));
+  PITT_TRY(arena_alloc(ctx, (size_t)BBOX_BLOCKS * 5, &d_part));
+  PITT_TRY(arena_alloc(ctx, 8, &d_bb));
+  PITT_TRY(arena_alloc(ctx, (size_t)n0, &d_onflag));
+  PITT_TRY(arena_alloc(ctx, (size_t)n0 + 1, &d_onkeep));
+  PITT_TRY(arena_alloc(ctx, (size_t)n0, &T->d_on));
+  PITT_CUDA(ctx, cudaMemsetAsync(d_flag, 0, (size_t)ni * sizeof(int), ctx->stream));
+  set_flags_kernel<<<cdiv(ni, 256), 256, 0, ctx->stream>>>(d_inl, d_n_inl, d_flag);
+  gather_points_dev_kernel<<<cdiv(ni, 256), 256, 0, ctx->stream>>>(d_iter, d_inl, d_n_inl, T->d_support, d_px, d_py);
+  invert_flags_kernel<<<cdiv(ni, 256), 256, 0, ctx->stream>>>(d_flag, ni, d_keep);
+  ctx->launches += 3;
+  PITT_TRY(device_exclusive_scan(ctx, d_keep, ni, nullptr));
+  scatter_rest_kernel<<<cdiv(ni, 256), 256, 0, ctx->stream>>>(d_iter, d_flag, d_keep, ni, T->d_rest);
+  support_decide_kernel<<<1, 1, 0, ctx->stream>>>(d_co, c, idxMapLayer, T->d_decide);
+  idxmap_classify_dev_kernel<<<cdiv(n0, 256), 256, 0, ctx->stream>>>(d_prev_map, n0, d_flag, ni, T->d_decide, d_else);
+  ctx->launches += 3;
+  PITT_TRY(device_exclusive_scan(ctx, d_else, n0, nullptr));
+  idxmap_write_dev_kernel<<<cdiv(n0, 256), 256, 0, ctx->stream>>>(d_prev_map, n0, d_flag, ni, T->d_decide, d_else, T->d_new_map);
+  ctx->launches++;
+  // getPointOnPlane (only does anything when the plane is horizontal: the kernels check the flag themselves). The running
+  // maxima are scanned over ni entries; the tail beyond the inlier count never reaches an entry that is read.
+  PITT_TRY(device_exclusive_max_scan(ctx, d_px, ni));
+  PITT_TRY(device_exclusive_max_scan(ctx, d_py, ni));
+  const int bb_blocks = std::max(1, std::min(BBOX_BLOCKS, cdiv(ni, 4096)));
+  bbox_quirk_dev_kernel<<<bb_blocks, 1024, 0, ctx->stream>>>(T->d_support, d_n_inl, T->d_decide, d_px, d_py, d_part);
+  bbox_quirk_final_dev_kernel<<<1, 32, 0, ctx->stream>>>(d_part, bb_blocks, d_n_inl, T->d_decide, c, d_bb);
+  on_plane_flag_dev_kernel<<<cdiv(n0, 256), 256, 0, ctx->stream>>>(cloud->d_xyz, T->d_new_map, n0, T->d_decide, d_bb, d_onflag, d_onkeep);
+  ctx->launches += 3;
+  PITT_TRY(device_exclusive_scan(ctx, d_onkeep, n0, T->d_decide + 2));
+  compact_points_kernel<<<cdiv(n0, 256), 256, 0, ctx->stream>>>(cloud->d_xyz, d_onflag, d_onkeep, n0, T->d_on, nullptr);
+  ctx->launches++;
+  PITT_CUDA(ctx, cudaGetLastError());
+  return PITT_OK;
+}
+
+// findSupports (supports…:241-361): ONE host synchronisation per trip. The plane RANSAC of a trip (sample table, estimate,
+// score, PCL stop rule, refinement, final inliers) and the whole second half of the trip are enqueued back to back; the host then
+// reads one small block (inlier count, coefficients, horizontal flag, points on the support, scan flags) and decides whether the
+// loop goes on. The second half of the LAST trip is wasted work (the loop always ends with a trip whose plane is rejected), on a
+// cloud that has shrunk to the objects by then.
 static int find_supports_impl(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_support_params& params, SupportCfg* cfg_out,
                               std::vector<SupportDev>* out, int* loop_trips) {
   const SupportCfg c = resolve_support(params);
@@ -490,128 +676,86 @@ static int find_supports_impl(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt
   iter.d_xyz = cloud->d_xyz;
   iter.h_valid = false;
   const int* d_prev_map = nullptr;  // nullptr = identity (first trip)
-  int idxMapLayer = -2, cnt = 0;
+  int idxMapLayer = -2;
   const int k = params.normals_k > 0 ? params.normals_k : 50;
+  const size_t stage_words = (size_t)(std::max(c.maxIter, 0) + 1) * 3 + 64;
   for (;;) {
     const int ni = iter.n;
-    SacDeviceResult r;
-    {
-      TraceScope ts(ctx, "supports: plane RANSAC");
-      PITT_TRY(sac_segment_impl(ctx, &iter, sp, &r));
-    }
+    // ---- first half: seg.segment() of the trip's cloud, enqueued
+    PITT_TRY(stage_reserve(ctx, stage_words * 4));
+    int* h_stage = reinterpret_cast<int*>(ctx->h_stage);
+    SacAsync sa;
+    sa.d_ints = nullptr;
+    sa.d_flt = nullptr;
+    bool issued = false;
+    PITT_TRY(sac_segment_async(ctx, &iter, sp, h_stage + 64, &sa, &issued));
     (*loop_trips)++;
-    TraceScope ts_rest(ctx, "supports: rest of the trip");
-    const int n_inl = r.n_inliers;
+    if (!issued) break;  // no solution possible (fewer points than the sample size): n_inl == 0
+    // the size test of the reference comes AFTER its RANSAC call and needs nothing from it: no second half for a trip it rejects
+    const bool cloud_too_small = (float)ni < (float)n0 * c.minCloudPct;
+    TripDev T;
+    memset(&T, 0, sizeof(T));
+    if (!cloud_too_small)
+      PITT_TRY(supports_trip_second_half(ctx, cloud, iter.d_xyz, ni, d_prev_map, sa.d_inl, sa.d_ints + 3, sa.d_flt + 8, c, idxMapLayer, &T));
+    PITT_CUDA(ctx, cudaMemcpyAsync(h_stage, sa.d_ints, 16 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PITT_CUDA(ctx, cudaMemcpyAsync(h_stage + 16, sa.d_flt, 16 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!cloud_too_small) PITT_CUDA(ctx, cudaMemcpyAsync(h_stage + 32, T.d_decide, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PITT_CUDA(ctx, pitt::stream_sync(ctx));
+    int n_inl = 0;
+    float co[4] = {0.f, 0.f, 0.f, 0.f};
+    bool horizontal = false;
+    int n_on = 0;
+    if (h_stage[8] != 0) {
+      // the device-side stop rule raised a flag: repeat the trip's RANSAC on the synchronous path and its second half from that
+      SacDeviceResult r;
+      PITT_TRY(sac_segment_impl(ctx, &iter, sp, &r));
+      n_inl = r.n_inliers;
+      if (n_inl > 0 && !cloud_too_small) {
+        int* d_n = nullptr;
+        float* d_co = nullptr;
+        PITT_TRY(arena_alloc(ctx, 1, &d_n));
+        PITT_TRY(arena_alloc(ctx, 8, &d_co));
+        h_stage[40] = n_inl;
+        memcpy(h_stage + 44, r.coeffs, 4 * sizeof(float));
+        PITT_CUDA(ctx, cudaMemcpyAsync(d_n, h_stage + 40, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        PITT_CUDA(ctx, cudaMemcpyAsync(d_co, h_stage + 44, 4 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        PITT_TRY(supports_trip_second_half(ctx, cloud, iter.d_xyz, ni, d_prev_map, r.d_inliers, d_n, d_co, c, idxMapLayer, &T));
+        PITT_CUDA(ctx, cudaMemcpyAsync(h_stage + 32, T.d_decide, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        PITT_CUDA(ctx, pitt::stream_sync(ctx));
+      }
+      for (int i = 0; i < 4; ++i) co[i] = r.coeffs[i];
+    } else if (h_stage[0] >= 0) {
+      n_inl = h_stage[3];
+      memcpy(co, h_stage + 16 + 8, 4 * sizeof(float));
+    }
     if (n_inl == 0) break;
-    else if ((float)ni < (float)n0 * c.minCloudPct) break;
+    else if (cloud_too_small) break;
     else if ((float)n_inl < (float)n0 * c.minPlanePct) break;
-    // removePlaneInliner: positive -> support cloud (gather, inliers are ascending), negative in place
-    int* d_flag = nullptr;
-    int* d_keep = nullptr;
-    int* d_n = nullptr;
-    float4* d_support = nullptr;
-    float4* d_rest = nullptr;
-    PITT_TRY(arena_alloc(ctx, (size_t)ni, &d_flag));
-    PITT_TRY(arena_alloc(ctx, (size_t)ni, &d_keep));
-    PITT_TRY(arena_alloc(ctx, 1, &d_n));
-    PITT_TRY(arena_alloc(ctx, (size_t)n_inl, &d_support));
-    PITT_TRY(arena_alloc(ctx, (size_t)std::max(ni - n_inl, 1), &d_rest));
-    PITT_CUDA(ctx, cudaMemsetAsync(d_flag, 0, (size_t)ni * sizeof(int), ctx->stream));
-    PITT_CUDA(ctx, cudaMemcpyAsync(d_n, &r.n_inliers, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    set_flags_kernel<<<cdiv(n_inl, 256), 256, 0, ctx->stream>>>(r.d_inliers, d_n, d_flag);
-    gather_points_kernel<<<cdiv(n_inl, 256), 256, 0, ctx->stream>>>(iter.d_xyz, r.d_inliers, n_inl, d_support);
-    invert_flags_kernel<<<cdiv(ni, 256), 256, 0, ctx->stream>>>(d_flag, ni, d_keep);
-    ctx->launches += 3;
-    PITT_TRY(device_exclusive_scan(ctx, d_keep, ni, nullptr));
-    scatter_rest_kernel<<<cdiv(ni, 256), 256, 0, ctx->stream>>>(iter.d_xyz, d_flag, d_keep, ni, d_rest);
-    ctx->launches++;
+    horizontal = h_stage[32] != 0;
+    n_on = h_stage[34];
     if (params.compute_discarded_normals) {
       // supports…:297,300 — results are never used by the reference; offered for cost fidelity only
       const float vp[3] = {0.f, 0.f, 0.f};
       float4* d_scratch = nullptr;
       PITT_TRY(arena_alloc(ctx, (size_t)std::max(ni, 1), &d_scratch));
-      PITT_TRY(estimate_normals_impl(ctx, d_rest, ni - n_inl, k, vp, d_scratch));
-      PITT_TRY(estimate_normals_impl(ctx, d_support, n_inl, k, vp, d_scratch));
+      PITT_TRY(estimate_normals_impl(ctx, T.d_rest, ni - n_inl, k, vp, d_scratch));
+      PITT_TRY(estimate_normals_impl(ctx, T.d_support, n_inl, k, vp, d_scratch));
     }
-    const bool horizontal = is_horizontal_plane(r.coeffs, c);
-    const int level = horizontal ? idxMapLayer : -1;
-    // createNewIdxMap
-    int* d_prev = nullptr;
-    if (!d_prev_map) {
-      PITT_TRY(arena_alloc(ctx, (size_t)n0, &d_prev));
-      iota_kernel<<<cdiv(n0, 256), 256, 0, ctx->stream>>>(d_prev, n0);
-      ctx->launches++;
-      d_prev_map = d_prev;
-    }
-    int* d_else = nullptr;
-    int* d_new = nullptr;
-    PITT_TRY(arena_alloc(ctx, (size_t)n0, &d_else));
-    PITT_TRY(arena_alloc(ctx, (size_t)n0, &d_new));
-    idxmap_classify_kernel<<<cdiv(n0, 256), 256, 0, ctx->stream>>>(d_prev_map, n0, d_flag, ni, level, d_else);
-    ctx->launches++;
-    PITT_TRY(device_exclusive_scan(ctx, d_else, n0, nullptr));
-    idxmap_write_kernel<<<cdiv(n0, 256), 256, 0, ctx->stream>>>(d_prev_map, n0, d_flag, ni, level, d_else, d_new);
-    ctx->launches++;
     if (horizontal) {
-      // getPointOnPlane
-      float* d_px = nullptr;
-      float* d_py = nullptr;
-      double* d_bb = nullptr;
-      PITT_TRY(arena_alloc(ctx, (size_t)n_inl, &d_px));
-      PITT_TRY(arena_alloc(ctx, (size_t)n_inl, &d_py));
-      PITT_TRY(arena_alloc(ctx, 8, &d_bb));
-      copy_axis_kernel<<<cdiv(n_inl, 256), 256, 0, ctx->stream>>>(d_support, n_inl, 0, d_px);
-      copy_axis_kernel<<<cdiv(n_inl, 256), 256, 0, ctx->stream>>>(d_support, n_inl, 1, d_py);
-      ctx->launches += 2;
-      PITT_TRY(device_exclusive_max_scan(ctx, d_px, n_inl));
-      PITT_TRY(device_exclusive_max_scan(ctx, d_py, n_inl));
-      double* d_part = nullptr;
-      PITT_TRY(arena_alloc(ctx, (size_t)BBOX_BLOCKS * 5, &d_part));
-      const int bb_blocks = std::max(1, std::min(BBOX_BLOCKS, cdiv(n_inl, 4096)));
-      bbox_quirk_kernel<<<bb_blocks, 1024, 0, ctx->stream>>>(d_support, n_inl, d_px, d_py, d_part);
-      bbox_quirk_final_kernel<<<1, 32, 0, ctx->stream>>>(d_part, bb_blocks, d_bb);
-      ctx->launches += 2;
-      double bb[5];
-      PITT_CUDA(ctx, cudaMemcpyAsync(bb, d_bb, sizeof(bb), cudaMemcpyDeviceToHost, ctx->stream));
-      PITT_CUDA(ctx, pitt::stream_sync(ctx));
-      double xMax = bb[0], xMin = bb[1], yMax = bb[2], yMin = bb[3], zMed = bb[4];
-      xMax -= c.offset[0];
-      xMin += c.offset[0];
-      yMax -= c.offset[1];
-      yMin += c.offset[1];
-      zMed = zMed / n_inl + c.offset[2];
-      int* d_onkeep = nullptr;
-      int* d_ontotal = nullptr;
-      PITT_TRY(arena_alloc(ctx, (size_t)n0 + 1, &d_onkeep));
-      PITT_TRY(arena_alloc(ctx, 1, &d_ontotal));
-      int* d_onflag = nullptr;
-      PITT_TRY(arena_alloc(ctx, (size_t)n0, &d_onflag));
-      on_plane_flag_kernel<<<cdiv(n0, 256), 256, 0, ctx->stream>>>(cloud->d_xyz, d_new, n0, level, xMin, xMax, yMin, yMax, zMed, d_onflag);
-      ctx->launches++;
-      PITT_CUDA(ctx, cudaMemcpyAsync(d_onkeep, d_onflag, (size_t)n0 * sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
-      PITT_TRY(device_exclusive_scan(ctx, d_onkeep, n0, d_ontotal));
-      int n_on = 0;
-      PITT_CUDA(ctx, cudaMemcpyAsync(&n_on, d_ontotal, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-      PITT_CUDA(ctx, pitt::stream_sync(ctx));
-      float4* d_on = nullptr;
-      PITT_TRY(arena_alloc(ctx, (size_t)std::max(n_on, 1), &d_on));
-      compact_points_kernel<<<cdiv(n0, 256), 256, 0, ctx->stream>>>(cloud->d_xyz, d_onflag, d_onkeep, n0, d_on, nullptr);
-      ctx->launches++;
       SupportDev S;
-      for (int i = 0; i < 4; ++i) S.co[i] = r.coeffs[i];
+      for (int i = 0; i < 4; ++i) S.co[i] = co[i];
       S.n_support = n_inl;
       S.n_on = n_on;
-      S.d_map = d_new;
-      S.d_support = d_support;
-      S.d_on = d_on;
+      S.d_map = T.d_new_map;
+      S.d_support = T.d_support;
+      S.d_on = T.d_on;
       out->push_back(S);
     }
-    d_prev_map = d_new;
-    iter.d_xyz = d_rest;
+    d_prev_map = T.d_new_map;
+    iter.d_xyz = T.d_rest;
     iter.n = ni - n_inl;
     iter.h_valid = false;
     iter.h_xyz.clear();
-    cnt++;
     idxMapLayer--;
     if (iter.n <= 0) {
       // the reference would call RANSAC on an empty cloud, get no inliers and stop
@@ -619,7 +763,6 @@ static int find_supports_impl(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt
       break;
     }
   }
-  (void)cnt;
   PITT_CUDA(ctx, cudaGetLastError());
   return PITT_OK;
 }
@@ -632,7 +775,7 @@ struct ClustersDev {
   std::vector<float> centroid;// 3 per cluster (sum/(n+1))
   const float4* d_points = nullptr;  // cluster clouds, contiguous in `offsets` order (device)
 };
-static int cluster_service_impl(pitt_ctx* ctx, const float4* d_xyz, int n, const pitt_cluster_params& p, ClustersDev* out) {
+static int cluster_service_host_impl(pitt_ctx* ctx, const float4* d_xyz, int n, const pitt_cluster_params& p, ClustersDev* out) {
   out->sizes.clear();
   out->offsets.assign(1, 0);
   out->indices.clear();
@@ -681,6 +824,76 @@ static int cluster_service_impl(pitt_ctx* ctx, const float4* d_xyz, int n, const
     for (int a = 0; a < 3; ++a) out->centroid[3 * c + a] = sums[3 * c + a] / cntp1;
   }
   out->d_points = d_pts;
+  return PITT_OK;
+}
+
+__global__ void __launch_bounds__(256)
+cluster_centroid_dev_kernel(const float4* __restrict__ pts, const int* __restrict__ head, float* __restrict__ out /*[c][3]*/) {
+  __shared__ double s[3][8];
+  const int c = blockIdx.x;
+  if (c >= head[0]) return;
+  const int b = head[2 + CC_MAXC + c], e = head[2 + CC_MAXC + c + 1];
+  double sx = 0, sy = 0, sz = 0;
+  for (int i = b + threadIdx.x; i < e; i += blockDim.x) {
+    float4 p = pts[i];  // the cluster clouds lie back to back in index order
+    sx += (double)p.x; sy += (double)p.y; sz += (double)p.z;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    sx += __shfl_down_sync(0xffffffffu, sx, o);
+    sy += __shfl_down_sync(0xffffffffu, sy, o);
+    sz += __shfl_down_sync(0xffffffffu, sz, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s[0][threadIdx.x >> 5] = sx; s[1][threadIdx.x >> 5] = sy; s[2][threadIdx.x >> 5] = sz; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t[3] = {0, 0, 0};
+    for (int w = 0; w < 8; ++w) { t[0] += s[0][w]; t[1] += s[1][w]; t[2] += s[2][w]; }
+    out[3 * c] = (float)t[0]; out[3 * c + 1] = (float)t[1]; out[3 * c + 2] = (float)t[2];
+  }
+}
+// clusterize (cluster…:38-108) with ONE host synchronisation: components, PCL ordering, index lists, cluster clouds and centroid
+// sums are made on the device (cluster.cu: euclidean_clusters_dev); the host reads the cluster count, the sizes and the sums.
+// want_indices: also fetch the index lists (the service response needs them, the frame path does not). More than CC_MAXC
+// clusters (min_rate below 1/128): the host-ordered path.
+static int cluster_service_impl(pitt_ctx* ctx, const float4* d_xyz, int n, const pitt_cluster_params& p, ClustersDev* out,
+                                bool want_indices = true) {
+  out->sizes.clear();
+  out->offsets.assign(1, 0);
+  out->indices.clear();
+  out->centroid.clear();
+  out->d_points = nullptr;
+  if (!(n >= p.min_input_size) || n <= 0) return PITT_OK;
+  const int min_sz = (int)round((double)n * p.min_rate);
+  const int max_sz = (int)round((double)n * p.max_rate);
+  ClustersOnDevice cd;
+  PITT_TRY(euclidean_clusters_dev(ctx, d_xyz, n, p.tolerance, min_sz, max_sz, &cd));
+  float* d_cen = nullptr;
+  PITT_TRY(arena_alloc(ctx, (size_t)CC_MAXC * 3, &d_cen));
+  cluster_centroid_dev_kernel<<<CC_MAXC, 256, 0, ctx->stream>>>(cd.d_points, cd.d_head, d_cen);
+  ctx->launches++;
+  PITT_TRY(stage_reserve(ctx, (size_t)(CC_HEAD_INTS + CC_MAXC * 3) * 4));
+  int* h_head = reinterpret_cast<int*>(ctx->h_stage);
+  float* h_cen = reinterpret_cast<float*>(h_head + CC_HEAD_INTS);
+  PITT_CUDA(ctx, cudaMemcpyAsync(h_head, cd.d_head, CC_HEAD_INTS * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PITT_CUDA(ctx, cudaMemcpyAsync(h_cen, d_cen, (size_t)CC_MAXC * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  PITT_CUDA(ctx, pitt::stream_sync(ctx));
+  if (h_head[1] > CC_MAXC) return cluster_service_host_impl(ctx, d_xyz, n, p, out);
+  const int nc = h_head[0];
+  if (nc == 0) return PITT_OK;
+  out->sizes.assign(h_head + 2, h_head + 2 + nc);
+  out->offsets.assign(h_head + 2 + CC_MAXC, h_head + 2 + CC_MAXC + nc + 1);
+  out->centroid.resize((size_t)nc * 3);
+  for (int c = 0; c < nc; ++c) {
+    const int cntp1 = 1 + out->sizes[c];  // `int cnt = 1; ... cnt++` (cluster…:78,91)
+    for (int a = 0; a < 3; ++a) out->centroid[3 * c + a] = h_cen[3 * c + a] / cntp1;
+  }
+  out->d_points = cd.d_points;
+  if (want_indices) {
+    const int total = out->offsets[nc];
+    out->indices.resize(total);
+    PITT_CUDA(ctx, cudaMemcpyAsync(out->indices.data(), cd.d_idx, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    PITT_CUDA(ctx, pitt::stream_sync(ctx));
+  }
   return PITT_OK;
 }
 
@@ -1145,7 +1358,7 @@ int pitt_segment_frame(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_frame_
         res->on_support_sizes[s] = S.n_on;
       }
       ClustersDev cd;
-      PITT_TRY(cluster_service_impl(ctx, S.d_on, S.n_on, fp->cluster, &cd));
+      PITT_TRY(cluster_service_impl(ctx, S.d_on, S.n_on, fp->cluster, &cd, false));
       const int nc = (int)cd.sizes.size();
       if (nc == 0) continue;
       // cluster normals (ransac_segmentation.cpp:233) on this ctx's stream, then the 4 fits per cluster

@@ -476,9 +476,10 @@ __device__ __forceinline__ int mg_pick_level(const int* __restrict__ start, int 
   return lvl;
 }
 
-// visits the points of the 27 level-l cells around (X, Y, Z): f(point, valid). Four loads are in flight per lane (indices
-// clamped to the range, the surplus masked), so the L1 / L2 latency of a lane's private candidate stream overlaps with the
-// arithmetic of the previous four.
+// visits the points of the 27 level-l cells around (X, Y, Z): f(point). Inside a cell the points are taken four at a time with
+// the next four already requested (two register sets used alternately, no index clamping, no per-point validity), so the L1 / L2
+// latency of a lane's private candidate stream overlaps with the arithmetic of the previous four; the last one to three points
+// of a cell follow one by one.
 template <typename F>
 __device__ __forceinline__ void mg_for_block27(const MGrid& g, const int* __restrict__ start, const float4* __restrict__ sorted, int X,
                                                int Y, int Z, int l, F f) {
@@ -493,21 +494,31 @@ __device__ __forceinline__ void mg_for_block27(const MGrid& g, const int* __rest
         const int x = X + a;
         if (x < 0 || x >= nx) continue;
         const int idx = mg_index(g, x << l, y << l, z << l);
-        const int jb = __ldg(start + idx), je = __ldg(start + idx + span);
-        if (jb >= je) continue;
-        const int last = je - 1;
-        float4 c0 = __ldg(sorted + jb), c1 = __ldg(sorted + min(jb + 1, last)), c2 = __ldg(sorted + min(jb + 2, last)),
-               c3 = __ldg(sorted + min(jb + 3, last));
-        for (int j = jb; j < je; j += 4) {
-          // the next four are requested before the current four are consumed
-          const float4 n0 = __ldg(sorted + min(j + 4, last)), n1 = __ldg(sorted + min(j + 5, last)),
-                       n2 = __ldg(sorted + min(j + 6, last)), n3 = __ldg(sorted + min(j + 7, last));
-          f(c0, true);
-          f(c1, j + 1 < je);
-          f(c2, j + 2 < je);
-          f(c3, j + 3 < je);
-          c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        const int jb = __ldg(start + idx), cnt = __ldg(start + idx + span) - jb;
+        const float4* p = sorted + jb;
+        int grp = cnt >> 2;
+        if (grp) {
+          float4 a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2), a3 = __ldg(p + 3);
+          p += 4;
+          --grp;  // groups still to be requested
+          while (grp >= 2) {
+            const float4 b0 = __ldg(p), b1 = __ldg(p + 1), b2 = __ldg(p + 2), b3 = __ldg(p + 3);
+            f(a0); f(a1); f(a2); f(a3);
+            a0 = __ldg(p + 4); a1 = __ldg(p + 5); a2 = __ldg(p + 6); a3 = __ldg(p + 7);
+            p += 8;
+            f(b0); f(b1); f(b2); f(b3);
+            grp -= 2;
+          }
+          if (grp == 1) {
+            const float4 b0 = __ldg(p), b1 = __ldg(p + 1), b2 = __ldg(p + 2), b3 = __ldg(p + 3);
+            p += 4;
+            f(a0); f(a1); f(a2); f(a3);
+            f(b0); f(b1); f(b2); f(b3);
+          } else {
+            f(a0); f(a1); f(a2); f(a3);
+          }
         }
+        for (int r = 0; r < (cnt & 3); ++r) f(__ldg(p + r));
       }
     }
   }
@@ -533,24 +544,26 @@ __device__ __forceinline__ int mg_block27_count(const MGrid& g, const int* __res
   return tot;
 }
 
-constexpr int KF_MCAP = 1536;  // queries with more points than this in their 27 cells go to the warp-per-query kernel
 
-template <int MODE>  // 0: neighbour lists, 1: normals
-__global__ void __launch_bounds__(KNN_FAST_TPB, 3)
-knn_fast_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, const float4* __restrict__ sorted,
-                const float4* __restrict__ xyz, int k, int need, float vpx, float vpy, float vpz, int* __restrict__ out_idx,
-                float* __restrict__ out_sq, float4* __restrict__ out_nrm, int* __restrict__ fb_count, int* __restrict__ fb_list,
-                unsigned long long* __restrict__ dbg) {
-  extern __shared__ __align__(16) unsigned long long knn_keys[];  // [warps][66][32]
+// Fast path, first kernel: level choice, pass 1 (histogram -> threshold), pass 2 (the <= 64 candidates below the threshold as
+// 64-bit keys). Few registers and 4 KB of shared memory per warp, so an SM holds many warps and the latency of the lane-private
+// candidate streams is hidden by switching warps. The keys go to global memory laid out [slot][query] (coalesced: consecutive
+// lanes are consecutive queries); ncol[query] = their number, or -1 when the query was handed to the warp-per-query kernel.
+__global__ void __launch_bounds__(KNN_FAST_TPB)
+knn_collect_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, const float4* __restrict__ sorted, int t_base, int t_count,
+                   int k, int need, int mcap, unsigned long long* __restrict__ keys, int* __restrict__ ncol, int* __restrict__ fb_count,
+                   int* __restrict__ fb_list, unsigned long long* __restrict__ dbg) {
+  __shared__ unsigned s_hist[KNN_FAST_TPB / 32][33][32];
   const MGrid g = *G;
-  const int t = blockIdx.x * KNN_FAST_TPB + threadIdx.x;
-  if (t >= g.n_finite) return;
+  const int tl = blockIdx.x * KNN_FAST_TPB + threadIdx.x;  // query within this chunk
+  const int t = t_base + tl;
+  if (tl >= t_count) return;
+  if (t >= g.n_finite) {  // beyond the finite points of the grid: nothing to sort either
+    ncol[tl] = -1;
+    return;
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // key slot s of this thread: kcol[s * 32] (slot 64 takes the rejected candidates: no branch around the store);
-  // histogram bucket b: hcol[b * 32] (bucket 32 takes the candidates outside the window); the histogram aliases the key slots
-  // of the same warp, it is dead before the first key is written (__syncwarp in between)
-  unsigned long long* kcol = knn_keys + (size_t)warp * 66 * 32 + lane;
-  unsigned* hcol = reinterpret_cast<unsigned*>(knn_keys + (size_t)warp * 66 * 32) + lane;
+  unsigned* hcol = &s_hist[warp][0][lane];  // bucket b of this thread: hcol[b * 32]
   const float4 q = __ldg(sorted + t);
   const int cx = mg_coord(q.x, g.mnx, g.inv_hf, g.dx), cy = mg_coord(q.y, g.mny, g.inv_hf, g.dy), cz = mg_coord(q.z, g.mnz, g.inv_hf, g.dz);
   const int lvl = mg_pick_level(start, mg_index(g, cx, cy, cz), need);
@@ -566,22 +579,22 @@ knn_fast_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, cons
   const int mtot = mg_block27_count(g, start, X, Y, Z, lvl);
   if (btop < (40u << 20)) {
     hand_over = lvl;
-  } else if (mtot > KF_MCAP) {
+  } else if (mtot > mcap) {
     hand_over = max(lvl - 1, 0);  // far more points around than the level choice expected (a density step): try finer cells first
   } else {
 #pragma unroll
     for (int b = 0; b < 33; ++b) hcol[b * 32] = 0u;
-    mg_for_block27(g, start, sorted, X, Y, Z, lvl, [&](const float4 p, bool valid) {
+    // bucket qq = (btop - bits(d2)) >> 20 counts DOWN from the top of the window (31 = everything further below, 32 = outside)
+    mg_for_block27(g, start, sorted, X, Y, Z, lvl, [&](const float4 p) {
       const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
-      const unsigned db = __float_as_uint((ddx * ddx + ddy * ddy) + ddz * ddz);
-      const unsigned qq = min((btop - db) >> 20, 31u);
-      const unsigned bucket = (valid && db <= btop) ? 31u - qq : 32u;
-      hcol[bucket * 32] += 1u;
+      const int dd = (int)btop - __float_as_int((ddx * ddx + ddy * ddy) + ddz * ddz);  // both are bit patterns of floats >= 0
+      const int qq = dd < 0 ? 32 : min(dd >> 20, 31);
+      hcol[qq * 32] += 1u;
     });
-    int cum = 0, bsel = -1, cat = 0;
+    int cum = 0, bsel = -1, cat = 0;  // bsel in the ascending numbering: bucket b = 31 - qq
 #pragma unroll
     for (int b = 0; b < 32; ++b) {
-      cum += (int)hcol[b * 32];
+      cum += (int)hcol[(31 - b) * 32];
       if (bsel < 0 && cum >= k) { bsel = b; cat = cum; }
     }
     if (dbg) {  // diagnostics (pitt_debug_knn_stats)
@@ -596,57 +609,76 @@ knn_fast_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, cons
     else tsel = btop - ((unsigned)(31 - bsel) << 20);
   }
   if (hand_over >= 0) {
-    if (dbg && mtot > KF_MCAP) atomicAdd(&dbg[9], 1ull);
+    if (dbg && mtot > mcap) atomicAdd(&dbg[9], 1ull);
     const int pos = atomicAdd(fb_count, 1);
     fb_list[pos] = t | (hand_over << 28);
+    ncol[tl] = -1;
+    return;
   }
-  __syncwarp();  // the histogram columns are dead: the key columns may be written
-  if (hand_over < 0) {
-    int c = 0;
-    mg_for_block27(g, start, sorted, X, Y, Z, lvl, [&](const float4 p, bool valid) {
-      const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
-      const unsigned db = __float_as_uint((ddx * ddx + ddy * ddy) + ddz * ddz);
-      const bool in = valid && db <= tsel;
-      kcol[(in ? c : 64) * 32] = ((unsigned long long)db << 32) | (unsigned long long)(unsigned)__float_as_int(p.w);
-      c += in ? 1 : 0;
-    });
-    unsigned long long key[64];
+  unsigned long long* kq = keys + tl;  // slot s of this query: kq[s * t_count_padded]
+  const size_t stride = (size_t)((t_count + 31) & ~31);
+  int c = 0;
+  mg_for_block27(g, start, sorted, X, Y, Z, lvl, [&](const float4 p) {
+    const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
+    const unsigned db = __float_as_uint((ddx * ddx + ddy * ddy) + ddz * ddz);
+    if (db <= tsel) {
+      kq[(size_t)c * stride] = ((unsigned long long)db << 32) | (unsigned long long)(unsigned)__float_as_int(p.w);
+      ++c;
+    }
+  });
+  ncol[tl] = c;
+}
+
+// Fast path, second kernel: the 64 keys of a query sorted in REGISTERS (Batcher's odd-even merge network, compile-time indices),
+// then the first k in order: neighbour lists, or the sequential float covariance + eigen33 + flip of computeFeature.
+template <int MODE>  // 0: neighbour lists, 1: normals
+__global__ void __launch_bounds__(KNN_FAST_TPB, 3)
+knn_sort_kernel(const float4* __restrict__ sorted, const float4* __restrict__ xyz, int t_base, int t_count, int k,
+                const unsigned long long* __restrict__ keys, const int* __restrict__ ncol, float vpx, float vpy, float vpz,
+                int* __restrict__ out_idx, float* __restrict__ out_sq, float4* __restrict__ out_nrm) {
+  const int tl = blockIdx.x * KNN_FAST_TPB + threadIdx.x;
+  if (tl >= t_count) return;
+  const int c = ncol[tl];
+  if (c < 0) return;  // handed over
+  const size_t stride = (size_t)((t_count + 31) & ~31);
+  const unsigned long long* kq = keys + tl;
+  unsigned long long key[64];
 #pragma unroll
-    for (int s = 0; s < 64; ++s) key[s] = (s < c) ? kcol[s * 32] : ~0ull;
+  for (int s = 0; s < 64; ++s) key[s] = (s < c) ? __ldg(kq + (size_t)s * stride) : ~0ull;
 #include "knn_sort64.inc"
-    const int qi = __float_as_int(q.w);
-    if (MODE == 0) {
+  const float4 q = __ldg(sorted + t_base + tl);
+  const int qi = __float_as_int(q.w);
+  if (MODE == 0) {
 #pragma unroll
-      for (int s = 0; s < KNN_FAST_KMAX; ++s) {
-        if (s < k) {
-          out_idx[(size_t)qi * k + s] = (int)(unsigned)(key[s] & 0xffffffffull);
-          if (out_sq) out_sq[(size_t)qi * k + s] = __uint_as_float((unsigned)(key[s] >> 32));
-        }
+    for (int s = 0; s < KNN_FAST_KMAX; ++s) {
+      if (s < k) {
+        out_idx[(size_t)qi * k + s] = (int)(unsigned)(key[s] & 0xffffffffull);
+        if (out_sq) out_sq[(size_t)qi * k + s] = __uint_as_float((unsigned)(key[s] >> 32));
       }
-    } else {
-      // computeMeanAndCovarianceMatrix: float accumulators in neighbour order (k >= 3 on this path: the cloud has > 4096 points)
-      float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    }
+  } else {
+    // computeMeanAndCovarianceMatrix: float accumulators in neighbour order (k >= 3 on this path: the cloud has > 4096 points)
+    float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int s = 0; s < KNN_FAST_KMAX; ++s) {
-        if (s < k) {
-          const float4 p = __ldg(xyz + (int)(unsigned)(key[s] & 0xffffffffull));
-          accu[0] += p.x * p.x; accu[1] += p.x * p.y; accu[2] += p.x * p.z;
-          accu[3] += p.y * p.y; accu[4] += p.y * p.z; accu[5] += p.z * p.z;
-          accu[6] += p.x; accu[7] += p.y; accu[8] += p.z;
-        }
+    for (int s = 0; s < KNN_FAST_KMAX; ++s) {
+      if (s < k) {
+        const float4 p = __ldg(xyz + (int)(unsigned)(key[s] & 0xffffffffull));
+        accu[0] += p.x * p.x; accu[1] += p.x * p.y; accu[2] += p.x * p.z;
+        accu[3] += p.y * p.y; accu[4] += p.y * p.z; accu[5] += p.z * p.z;
+        accu[6] += p.x; accu[7] += p.y; accu[8] += p.z;
       }
-      if (k >= 3) {
-        float cov[9], cen[3], ev, evec[3];
-        cov_from_accu(accu, (float)k, cov, cen);
-        eigen33(cov, ev, evec);
-        float nx = evec[0], ny = evec[1], nz = evec[2];
-        const float eig_sum = cov[0] + cov[4] + cov[8];
-        const float curv = (eig_sum != 0.0f) ? fabsf(ev / eig_sum) : 0.0f;
-        const float vx = vpx - q.x, vy = vpy - q.y, vz = vpz - q.z;
-        const float cos_theta = (vx * nx + vy * ny + vz * nz);
-        if (cos_theta < 0.0f) { nx = -nx; ny = -ny; nz = -nz; }
-        out_nrm[qi] = make_float4(nx, ny, nz, curv);
-      }
+    }
+    if (k >= 3) {
+      float cov[9], cen[3], ev, evec[3];
+      cov_from_accu(accu, (float)k, cov, cen);
+      eigen33(cov, ev, evec);
+      float nx = evec[0], ny = evec[1], nz = evec[2];
+      const float eig_sum = cov[0] + cov[4] + cov[8];
+      const float curv = (eig_sum != 0.0f) ? fabsf(ev / eig_sum) : 0.0f;
+      const float vx = vpx - q.x, vy = vpy - q.y, vz = vpz - q.z;
+      const float cos_theta = (vx * nx + vy * ny + vz * nz);
+      if (cos_theta < 0.0f) { nx = -nx; ny = -ny; nz = -nz; }
+      out_nrm[qi] = make_float4(nx, ny, nz, curv);
     }
   }
 }
@@ -825,19 +857,9 @@ static float knn_env(const char* name, float dflt) {
 }
 // tuning knobs (measured on B200, 307 200-point frame, k = 50; the environment variables are for experiments only)
 static float knn_c_avg() { static float v = knn_env("PITT_KNN_CAVG", 2.5f); return v; }             // mean points per fine cell
+// queries with more points than this in their 27 cells go to the warp-per-query kernel
+static int knn_mcap() { static float v = knn_env("PITT_KNN_MCAP", 1536.0f); return (int)v; }
 static int knn_need(int k) { static float f = knn_env("PITT_KNN_NEED", 2.0f); return std::max(8, (int)ceilf(f * (float)k)); }  // points in the parent cell
-
-constexpr size_t KNN_FAST_SMEM = (size_t)(KNN_FAST_TPB / 32) * 66 * 32 * sizeof(unsigned long long);
-// the fast kernel needs more than 48 KB of dynamic shared memory: opt in once per device
-static int knn_smem_opt_in(pitt_ctx* ctx) {
-  static bool done[64] = {false};
-  const int dev = ctx->device & 63;
-  if (done[dev]) return PITT_OK;
-  PITT_CUDA(ctx, cudaFuncSetAttribute(knn_fast_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KNN_FAST_SMEM));
-  PITT_CUDA(ctx, cudaFuncSetAttribute(knn_fast_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KNN_FAST_SMEM));
-  done[dev] = true;
-  return PITT_OK;
-}
 
 // Builds the multi-level grid of d_xyz[0..n) on ctx->stream; nothing here waits for the device. The two dense tables live
 // in the context (allocated once, reused by every call: calls of one context are ordered on its stream), the n-sized arrays
@@ -882,17 +904,29 @@ template <int MODE>
 static int knn_large(pitt_ctx* ctx, const float4* d_xyz, int n, int k, const float vp[3], int* d_idx, float* d_sq, float4* d_nrm) {
   MGridBuf mg;
   PITT_TRY(mgrid_build(ctx, d_xyz, n, 0.0f, &mg));
-  PITT_TRY(knn_smem_opt_in(ctx));
   const int need = knn_need(k);
   if (k <= KNN_FAST_KMAX && n < (1 << 28)) {
-    knn_fast_kernel<MODE><<<cdiv(n, KNN_FAST_TPB), KNN_FAST_TPB, KNN_FAST_SMEM, ctx->stream>>>(
-        mg.d_G, mg.d_start, mg.d_sorted, d_xyz, k, need, vp[0], vp[1], vp[2], d_idx, d_sq, d_nrm, mg.d_scr + 7, mg.d_fb_list,
-        g_knn_stats ? reinterpret_cast<unsigned long long*>(mg.d_scr + 8) : nullptr);
+    // the collected keys take 512 B per query: clouds of more than a million points go through in chunks of queries
+    const int chunk = std::min(n, 1 << 20);
+    const size_t stride = (size_t)((chunk + 31) & ~31);
+    unsigned long long* d_keys = nullptr;
+    int* d_ncol = nullptr;
+    PITT_TRY(arena_alloc(ctx, stride * 64, &d_keys));
+    PITT_TRY(arena_alloc(ctx, (size_t)chunk, &d_ncol));
+    unsigned long long* dbg = g_knn_stats ? reinterpret_cast<unsigned long long*>(mg.d_scr + 8) : nullptr;
+    for (int t0 = 0; t0 < n; t0 += chunk) {
+      const int tc = std::min(chunk, n - t0);
+      knn_collect_kernel<<<cdiv(tc, KNN_FAST_TPB), KNN_FAST_TPB, 0, ctx->stream>>>(mg.d_G, mg.d_start, mg.d_sorted, t0, tc, k, need, knn_mcap(), d_keys,
+                                                                                 d_ncol, mg.d_scr + 7, mg.d_fb_list, dbg);
+      knn_sort_kernel<MODE><<<cdiv(tc, KNN_FAST_TPB), KNN_FAST_TPB, 0, ctx->stream>>>(mg.d_sorted, d_xyz, t0, tc, k, d_keys, d_ncol, vp[0],
+                                                                                     vp[1], vp[2], d_idx, d_sq, d_nrm);
+      ctx->launches += 2;
+    }
     // the queries the fast path handed over, a warp each (their number is only known on the device: CTAs beyond it return at
     // once; a few per cent of the points at most, so a quarter of the worst case is launched and the rest, if any, follows)
     knn_wide_kernel<MODE><<<std::min(cdiv(n, WS_WARPS), ctx->sm_count * 8), WS_WARPS * 32, 0, ctx->stream>>>(
         mg.d_G, mg.d_start, mg.d_sorted, d_xyz, n, k, need, vp[0], vp[1], vp[2], d_idx, d_sq, d_nrm, mg.d_scr + 7, mg.d_fb_list);
-    ctx->launches += 2;
+    ctx->launches++;
   } else {
     knn_wide_kernel<MODE><<<std::min(cdiv(n, WS_WARPS), ctx->sm_count * 8), WS_WARPS * 32, 0, ctx->stream>>>(
         mg.d_G, mg.d_start, mg.d_sorted, d_xyz, n, k, need, vp[0], vp[1], vp[2], d_idx, d_sq, d_nrm, nullptr, nullptr);

@@ -19,5 +19,8 @@ struct ClustersOnDevice {
   float4* d_points;
 };
 int euclidean_clusters_dev(pitt_ctx* ctx, const float4* d_xyz, int n, double tolerance, int min_size, int max_size, ClustersOnDevice* out);
+constexpr int KNN_BRUTE_MAX = 4096;  // below this size the all-pairs kernel beats grid + search
+int estimate_normals_segmented(pitt_ctx* ctx, const float4* d_xyz, int n_total, const int* d_seg_off, const int* d_n_seg, int k,
+                               const float vp[3], float4* d_nrm);
 int estimate_normals_impl(pitt_ctx* ctx, const float4* d_xyz, int n, int k, const float vp[3], float4* d_nrm);
 }  // namespace pitt

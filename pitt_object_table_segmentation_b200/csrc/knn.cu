@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <algorithm>
 
+#include "cluster.cuh"
 #include "grid.cuh"
 #include "mgrid.cuh"
 #include "pitt_math.cuh"
@@ -17,7 +18,6 @@
 namespace pitt {
 
 constexpr int KNN_KMAX = 64;
-constexpr int KNN_BRUTE_MAX = 4096;  // below this size the all-pairs kernel beats grid + ring search
 
 __device__ __forceinline__ bool cand_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
 
@@ -74,15 +74,29 @@ __device__ __forceinline__ void ws_sort128(float (&kd)[4], int (&ki)[4], int lan
   }
 }
 
-template <int MODE>
+// SEG: the cloud is a sequence of independent segments (the cluster clouds of a support, back to back): seg_off[0..*n_seg] are
+// their offsets on the device, every query searches its own segment only. One launch then serves all clusters of a frame.
+template <int MODE, bool SEG>
 __global__ void __launch_bounds__(WS_WARPS * 32)
 knn_brute_kernel(const float4* __restrict__ xyz, int n, int k, float vpx, float vpy, float vpz, int* __restrict__ out_idx,
-                 float* __restrict__ out_sq, float4* __restrict__ out_nrm) {
+                 float* __restrict__ out_sq, float4* __restrict__ out_nrm, const int* __restrict__ seg_off, const int* __restrict__ n_seg) {
   __shared__ float s_bd[WS_WARPS][64];
   __shared__ int s_bi[WS_WARPS][64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qi = blockIdx.x * WS_WARPS + warp;  // one warp per query
   if (qi >= n) return;
+  int sb = 0, se = n;  // the query's segment [sb, se)
+  if (SEG) {
+    const int ns = *n_seg;
+    if (qi >= seg_off[ns]) return;
+    int sidx = 0;
+    for (int base = 0; base < ns; base += 32) {
+      const bool below = (base + lane < ns) && seg_off[base + lane + 1] <= qi;
+      sidx += __popc(__ballot_sync(0xffffffffu, below));
+    }
+    sb = seg_off[sidx];
+    se = seg_off[sidx + 1];
+  }
   const float4 q = __ldg(xyz + qi);
   if (!(isfinite(q.x) && isfinite(q.y) && isfinite(q.z))) return;  // outputs stay NaN / -1
   float kd[4];
@@ -110,16 +124,16 @@ knn_brute_kernel(const float4* __restrict__ xyz, int n, int k, float vpx, float 
   // Candidate chunks of 32 are visited outwards from the query's own index: in organised
   // (scan-ordered) clouds index neighbours are spatial neighbours, so the admission threshold is
   // tight after the first few chunks and almost everything else is rejected by one compare.
-  const int n_chunks = (n + 31) >> 5;
-  const int c0 = qi >> 5;
+  const int n_chunks = ((se - sb) + 31) >> 5;
+  const int c0 = (qi - sb) >> 5;
   for (int step = 0; step < 2 * n_chunks; ++step) {
     const int off = (step + 1) >> 1;
     const int c = (step & 1) ? c0 - off : c0 + off;  // c0, c0-1, c0+1, c0-2, ...
     if (step == 0 ? false : (c == c0)) continue;
     if (c < 0 || c >= n_chunks) continue;
-    const int pi = (c << 5) + lane;
+    const int pi = sb + (c << 5) + lane;
     float d = CUDART_INF_F;
-    if (pi < n) {
+    if (pi < se) {
       const float4 p = __ldg(xyz + pi);
       const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
       d = (ddx * ddx + ddy * ddy) + ddz * ddz;
@@ -164,8 +178,8 @@ knn_brute_kernel(const float4* __restrict__ xyz, int n, int k, float vpx, float 
   // computeMeanAndCovarianceMatrix: sequential float accumulation in neighbour order. Every lane
   // runs the same sequence on broadcast neighbours (identical result), lane 0 stores it.
   float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const float4 p0 = (ki[0] < n) ? __ldg(xyz + ki[0]) : make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 p1 = (ki[1] < n) ? __ldg(xyz + ki[1]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 p0 = (ki[0] < se) ? __ldg(xyz + ki[0]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 p1 = (ki[1] < se) ? __ldg(xyz + ki[1]) : make_float4(0.f, 0.f, 0.f, 0.f);
   for (int t = 0; t < size; ++t) {
     const float4 src = (t < 32) ? p0 : p1;
     const float px = __shfl_sync(0xffffffffu, src.x, t & 31), py = __shfl_sync(0xffffffffu, src.y, t & 31),
@@ -937,6 +951,21 @@ static int knn_large(pitt_ctx* ctx, const float4* d_xyz, int n, int k, const flo
   return PITT_OK;
 }
 
+// normals of several small clouds lying back to back in d_xyz[0..n_total) (the cluster clouds of a support; every segment at most
+// KNN_BRUTE_MAX points, the caller checks): ONE launch, every query searches its own segment. d_seg_off[0..*d_n_seg] on the device.
+int estimate_normals_segmented(pitt_ctx* ctx, const float4* d_xyz, int n_total, const int* d_seg_off, const int* d_n_seg, int k,
+                               const float vp[3], float4* d_nrm) {
+  if (n_total <= 0) return PITT_OK;
+  if (k < 1 || k > KNN_KMAX) return fail(ctx, PITT_ERR_INVALID, "k must be in [1, 64]");
+  const float nan = nanf("");
+  fill_f4_kernel<<<cdiv(n_total, 256), 256, 0, ctx->stream>>>(d_nrm, n_total, make_float4(nan, nan, nan, nan));
+  knn_brute_kernel<1, true><<<cdiv(n_total, WS_WARPS), WS_WARPS * 32, 0, ctx->stream>>>(d_xyz, n_total, k, vp[0], vp[1], vp[2], nullptr, nullptr,
+                                                                                         d_nrm, d_seg_off, d_n_seg);
+  ctx->launches += 2;
+  PITT_CUDA(ctx, cudaGetLastError());
+  return PITT_OK;
+}
+
 int estimate_normals_impl(pitt_ctx* ctx, const float4* d_xyz, int n, int k, const float vp[3], float4* d_nrm) {
   if (n <= 0) return PITT_OK;
   if (k < 1 || k > KNN_KMAX) return fail(ctx, PITT_ERR_INVALID, "k must be in [1, 64]");
@@ -944,7 +973,8 @@ int estimate_normals_impl(pitt_ctx* ctx, const float4* d_xyz, int n, int k, cons
   fill_f4_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_nrm, n, make_float4(nan, nan, nan, nan));
   ctx->launches++;
   if (n <= KNN_BRUTE_MAX) {
-    knn_brute_kernel<1><<<cdiv(n, WS_WARPS), WS_WARPS * 32, 0, ctx->stream>>>(d_xyz, n, k, vp[0], vp[1], vp[2], nullptr, nullptr, d_nrm);
+    knn_brute_kernel<1, false><<<cdiv(n, WS_WARPS), WS_WARPS * 32, 0, ctx->stream>>>(d_xyz, n, k, vp[0], vp[1], vp[2], nullptr, nullptr, d_nrm,
+                                                                                          nullptr, nullptr);
     ctx->launches++;
     PITT_CUDA(ctx, cudaGetLastError());
     return PITT_OK;
@@ -988,7 +1018,8 @@ int pitt_knn(pitt_ctx* ctx, const pitt_cloud* c, int k, int32_t* out_idx, float*
     fill_knn_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, ctx->stream>>>(d_idx, d_sq, tot);
     ctx->launches++;
     if (n <= KNN_BRUTE_MAX) {
-      knn_brute_kernel<0><<<cdiv(n, WS_WARPS), WS_WARPS * 32, 0, ctx->stream>>>(c->d_xyz, n, k, 0.f, 0.f, 0.f, d_idx, d_sq, nullptr);
+      knn_brute_kernel<0, false><<<cdiv(n, WS_WARPS), WS_WARPS * 32, 0, ctx->stream>>>(c->d_xyz, n, k, 0.f, 0.f, 0.f, d_idx, d_sq, nullptr, nullptr,
+                                                                                          nullptr);
       ctx->launches++;
     } else {
       const float vp[3] = {0.f, 0.f, 0.f};

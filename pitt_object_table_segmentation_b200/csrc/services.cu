@@ -774,6 +774,7 @@ struct ClustersDev {
   std::vector<int> indices;   // host copy, ascending per cluster
   std::vector<float> centroid;// 3 per cluster (sum/(n+1))
   const float4* d_points = nullptr;  // cluster clouds, contiguous in `offsets` order (device)
+  const int* d_head = nullptr;       // device copy of {nc, ., sizes, offsets} (device-side clustering only)
 };
 static int cluster_service_host_impl(pitt_ctx* ctx, const float4* d_xyz, int n, const pitt_cluster_params& p, ClustersDev* out) {
   out->sizes.clear();
@@ -862,6 +863,7 @@ static int cluster_service_impl(pitt_ctx* ctx, const float4* d_xyz, int n, const
   out->indices.clear();
   out->centroid.clear();
   out->d_points = nullptr;
+  out->d_head = nullptr;
   if (!(n >= p.min_input_size) || n <= 0) return PITT_OK;
   const int min_sz = (int)round((double)n * p.min_rate);
   const int max_sz = (int)round((double)n * p.max_rate);
@@ -888,6 +890,7 @@ static int cluster_service_impl(pitt_ctx* ctx, const float4* d_xyz, int n, const
     for (int a = 0; a < 3; ++a) out->centroid[3 * c + a] = h_cen[3 * c + a] / cntp1;
   }
   out->d_points = cd.d_points;
+  out->d_head = cd.d_head;
   if (want_indices) {
     const int total = out->offsets[nc];
     out->indices.resize(total);
@@ -1363,12 +1366,19 @@ int pitt_segment_frame(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_frame_
       if (nc == 0) continue;
       // cluster normals (ransac_segmentation.cpp:233) on this ctx's stream, then the 4 fits per cluster
       std::vector<pitt_cloud> cc(nc);  // non-owning views of the cluster clouds
+      const int total = cd.offsets[nc];
+      float4* d_cn_all = nullptr;
+      PITT_TRY(arena_alloc(ctx, (size_t)std::max(total, 1), &d_cn_all));
+      bool all_small = cd.d_head != nullptr;
+      for (int c = 0; c < nc; ++c) all_small = all_small && cd.sizes[c] <= KNN_BRUTE_MAX;
+      // the clusters' normals in ONE launch (every query searches its own cluster), unless a cluster is large enough for the grid
+      if (all_small)
+        PITT_TRY(estimate_normals_segmented(ctx, cd.d_points, total, cd.d_head + 2 + CC_MAXC, cd.d_head, fp->normals_k, fp->viewpoint, d_cn_all));
       for (int c = 0; c < nc; ++c) {
         cc[c].n = cd.sizes[c];
         cc[c].d_xyz = const_cast<float4*>(cd.d_points) + cd.offsets[c];
-        float4* d_cn = nullptr;
-        PITT_TRY(arena_alloc(ctx, (size_t)cc[c].n, &d_cn));
-        PITT_TRY(estimate_normals_impl(ctx, cc[c].d_xyz, cc[c].n, fp->normals_k, fp->viewpoint, d_cn));
+        float4* d_cn = d_cn_all + cd.offsets[c];
+        if (!all_small) PITT_TRY(estimate_normals_impl(ctx, cc[c].d_xyz, cc[c].n, fp->normals_k, fp->viewpoint, d_cn));
         cc[c].d_nrm = d_cn;
         cc[c].has_normals = true;
       }

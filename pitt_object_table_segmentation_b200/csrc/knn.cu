@@ -439,16 +439,29 @@ __global__ void __launch_bounds__(256) mg_blockscan_kernel(const MGrid* __restri
     dst[j] = q;
   }
 }
+// seg_off != nullptr: the cloud is a sequence of segments (seg_off[0..*n_seg], on the device); a point carries its segment in
+// the top 8 bits of the index word (n < 2^24), the searches then ignore candidates of other segments
 __global__ void __launch_bounds__(256) mg_scatter_kernel(const float4* __restrict__ xyz, int n, const int* __restrict__ cellid,
                                                          const int* __restrict__ start, int* __restrict__ cnt,
-                                                         float4* __restrict__ sorted) {
+                                                         float4* __restrict__ sorted, const int* __restrict__ seg_off,
+                                                         const int* __restrict__ n_seg) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int cell = cellid[i];
   if (cell < 0) return;
   const float4 p = __ldg(xyz + i);
+  int w = i;
+  if (seg_off) {
+    int lo = 0, hi = *n_seg;  // segment s: seg_off[s] <= i < seg_off[s + 1]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (seg_off[mid] <= i) lo = mid;
+      else hi = mid;
+    }
+    w = i | (lo << 24);
+  }
   const int pos = start[cell] + atomicSub(&cnt[cell], 1) - 1;  // the histogram counts down to zero: no second table
-  sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+  sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float(w));
 }
 
 // ---- per-query geometry at level l
@@ -563,6 +576,7 @@ __device__ __forceinline__ int mg_block27_count(const MGrid& g, const int* __res
 // 64-bit keys). Few registers and 4 KB of shared memory per warp, so an SM holds many warps and the latency of the lane-private
 // candidate streams is hidden by switching warps. The keys go to global memory laid out [slot][query] (coalesced: consecutive
 // lanes are consecutive queries); ncol[query] = their number, or -1 when the query was handed to the warp-per-query kernel.
+template <bool SEG>
 __global__ void __launch_bounds__(KNN_FAST_TPB)
 knn_collect_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, const float4* __restrict__ sorted, int t_base, int t_count,
                    int k, int need, int mcap, unsigned long long* __restrict__ keys, int* __restrict__ ncol, int* __restrict__ fb_count,
@@ -579,30 +593,39 @@ knn_collect_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, c
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned* hcol = &s_hist[warp][0][lane];  // bucket b of this thread: hcol[b * 32]
   const float4 q = __ldg(sorted + t);
+  const unsigned qw = __float_as_uint(q.w);
   const int cx = mg_coord(q.x, g.mnx, g.inv_hf, g.dx), cy = mg_coord(q.y, g.mny, g.inv_hf, g.dy), cz = mg_coord(q.z, g.mnz, g.inv_hf, g.dz);
-  const int lvl = mg_pick_level(start, mg_index(g, cx, cy, cz), need);
-  const int X = cx >> lvl, Y = cy >> lvl, Z = cz >> lvl;
-  // one attempt at this level; whatever does not fit (too many points around, fewer than k inside the guaranteed radius, more
-  // than 64 candidates below the bucket edge) is handed to the warp-per-query kernel with a level hint
+  int lvl = mg_pick_level(start, mg_index(g, cx, cy, cz), need);
+  // one attempt at this level (two when the 27 cells hold far more points than the level choice expected, i.e. at a density
+  // step: finer cells first); whatever does not fit (fewer than k inside the guaranteed radius, more than 64 candidates below
+  // the bucket edge) is handed to the warp-per-query kernel with a level hint
   int hand_over = -1;
   unsigned tsel = 0;
-  const float bound = mg_bound(g, q, X, Y, Z, lvl, 1);
-  const float hl = g.hf * (float)(1 << lvl);
-  const float top = (bound > 0.0f) ? fminf(bound * bound, 27.5f * hl * hl) : 0.0f;  // cube = whole grid: its diagonal
-  const unsigned btop = __float_as_uint(top);
-  const int mtot = mg_block27_count(g, start, X, Y, Z, lvl);
-  if (btop < (40u << 20)) {
-    hand_over = lvl;
-  } else if (mtot > mcap) {
-    hand_over = max(lvl - 1, 0);  // far more points around than the level choice expected (a density step): try finer cells first
-  } else {
+  int X, Y, Z, mtot;
+  for (int attempt = 0;; ++attempt) {
+    X = cx >> lvl; Y = cy >> lvl; Z = cz >> lvl;
+    const float bound = mg_bound(g, q, X, Y, Z, lvl, 1);
+    const float hl = g.hf * (float)(1 << lvl);
+    const float top = (bound > 0.0f) ? fminf(bound * bound, 27.5f * hl * hl) : 0.0f;  // cube = whole grid: its diagonal
+    const unsigned btop = __float_as_uint(top);
+    mtot = mg_block27_count(g, start, X, Y, Z, lvl);
+    if (btop < (40u << 20)) {
+      hand_over = lvl;
+      break;
+    }
+    if (mtot > mcap) {
+      if (attempt == 0 && lvl > 0) { --lvl; continue; }
+      hand_over = lvl;
+      break;
+    }
 #pragma unroll
     for (int b = 0; b < 33; ++b) hcol[b * 32] = 0u;
     // bucket qq = (btop - bits(d2)) >> 20 counts DOWN from the top of the window (31 = everything further below, 32 = outside)
     mg_for_block27(g, start, sorted, X, Y, Z, lvl, [&](const float4 p) {
       const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
       const int dd = (int)btop - __float_as_int((ddx * ddx + ddy * ddy) + ddz * ddz);  // both are bit patterns of floats >= 0
-      const int qq = dd < 0 ? 32 : min(dd >> 20, 31);
+      int qq = dd < 0 ? 32 : min(dd >> 20, 31);
+      if (SEG && ((__float_as_uint(p.w) ^ qw) >> 24)) qq = 32;  // a point of another segment does not exist for this query
       hcol[qq * 32] += 1u;
     });
     int cum = 0, bsel = -1, cat = 0;  // bsel in the ascending numbering: bucket b = 31 - qq
@@ -621,6 +644,7 @@ knn_collect_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, c
     if (bsel < 0) hand_over = lvl + 1;        // fewer than k points inside the guaranteed radius: a cube twice as wide
     else if (cat > 64) hand_over = lvl;       // the k-th neighbour lies far below the window, or > 64 candidates in one bucket
     else tsel = btop - ((unsigned)(31 - bsel) << 20);
+    break;
   }
   if (hand_over >= 0) {
     if (dbg && mtot > mcap) atomicAdd(&dbg[9], 1ull);
@@ -635,7 +659,7 @@ knn_collect_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, c
   mg_for_block27(g, start, sorted, X, Y, Z, lvl, [&](const float4 p) {
     const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
     const unsigned db = __float_as_uint((ddx * ddx + ddy * ddy) + ddz * ddz);
-    if (db <= tsel) {
+    if (db <= tsel && !(SEG && ((__float_as_uint(p.w) ^ qw) >> 24))) {
       kq[(size_t)c * stride] = ((unsigned long long)db << 32) | (unsigned long long)(unsigned)__float_as_int(p.w);
       ++c;
     }
@@ -645,7 +669,7 @@ knn_collect_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, c
 
 // Fast path, second kernel: the 64 keys of a query sorted in REGISTERS (Batcher's odd-even merge network, compile-time indices),
 // then the first k in order: neighbour lists, or the sequential float covariance + eigen33 + flip of computeFeature.
-template <int MODE>  // 0: neighbour lists, 1: normals
+template <int MODE, bool SEG>  // 0: neighbour lists, 1: normals
 __global__ void __launch_bounds__(KNN_FAST_TPB, 3)
 knn_sort_kernel(const float4* __restrict__ sorted, const float4* __restrict__ xyz, int t_base, int t_count, int k,
                 const unsigned long long* __restrict__ keys, const int* __restrict__ ncol, float vpx, float vpy, float vpz,
@@ -661,12 +685,13 @@ knn_sort_kernel(const float4* __restrict__ sorted, const float4* __restrict__ xy
   for (int s = 0; s < 64; ++s) key[s] = (s < c) ? __ldg(kq + (size_t)s * stride) : ~0ull;
 #include "knn_sort64.inc"
   const float4 q = __ldg(sorted + t_base + tl);
-  const int qi = __float_as_int(q.w);
+  const unsigned IDX = SEG ? 0x00ffffffu : 0xffffffffu;  // the segment lives in the top 8 bits of the index word
+  const int qi = (int)(__float_as_uint(q.w) & IDX);
   if (MODE == 0) {
 #pragma unroll
     for (int s = 0; s < KNN_FAST_KMAX; ++s) {
       if (s < k) {
-        out_idx[(size_t)qi * k + s] = (int)(unsigned)(key[s] & 0xffffffffull);
+        out_idx[(size_t)qi * k + s] = (int)((unsigned)(key[s] & 0xffffffffull) & IDX);
         if (out_sq) out_sq[(size_t)qi * k + s] = __uint_as_float((unsigned)(key[s] >> 32));
       }
     }
@@ -676,7 +701,7 @@ knn_sort_kernel(const float4* __restrict__ sorted, const float4* __restrict__ xy
 #pragma unroll
     for (int s = 0; s < KNN_FAST_KMAX; ++s) {
       if (s < k) {
-        const float4 p = __ldg(xyz + (int)(unsigned)(key[s] & 0xffffffffull));
+        const float4 p = __ldg(xyz + (int)((unsigned)(key[s] & 0xffffffffull) & IDX));
         accu[0] += p.x * p.x; accu[1] += p.x * p.y; accu[2] += p.x * p.z;
         accu[3] += p.y * p.y; accu[4] += p.y * p.z; accu[5] += p.z * p.z;
         accu[6] += p.x; accu[7] += p.y; accu[8] += p.z;
@@ -703,7 +728,7 @@ knn_sort_kernel(const float4* __restrict__ sorted, const float4* __restrict__ xy
 // its level; if the k-th best found there is not closer than the guaranteed radius, the level goes up; above MG_MAXLVL the
 // whole point array is the candidate set, which always ends the search. Serves the queries the fast kernel hands over (list,
 // *n_list on the device) and, with list == nullptr, every point (k > KNN_FAST_KMAX).
-template <int MODE>
+template <int MODE, bool SEG>
 __global__ void __launch_bounds__(WS_WARPS * 32)
 knn_wide_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, const float4* __restrict__ sorted,
                 const float4* __restrict__ xyz, int n_xyz, int k, int need, float vpx, float vpy, float vpz, int* __restrict__ out_idx,
@@ -724,7 +749,9 @@ knn_wide_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, cons
     l = (e >> 28) & 7;
   }
   const float4 q = __ldg(sorted + t);
-  const int qi = __float_as_int(q.w);
+  const unsigned IDX = SEG ? 0x00ffffffu : 0xffffffffu;  // the segment lives in the top 8 bits of the index word
+  const unsigned qw = __float_as_uint(q.w);
+  const int qi = (int)(qw & IDX);
   const int cx = mg_coord(q.x, g.mnx, g.inv_hf, g.dx), cy = mg_coord(q.y, g.mny, g.inv_hf, g.dy), cz = mg_coord(q.z, g.mnz, g.inv_hf, g.dz);
   if (l < 0) l = mg_pick_level(start, mg_index(g, cx, cy, cz), need);
   const int want = min(k, g.n_finite);
@@ -794,6 +821,7 @@ knn_wide_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, cons
           const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
           d = (ddx * ddx + ddy * ddy) + ddz * ddz;
           pi = __float_as_int(p.w);
+          if (SEG && ((__float_as_uint(p.w) ^ qw) >> 24)) d = CUDART_INF_F;  // another segment: not a candidate
         }
         const bool pass = (d < CUDART_INF_F) && cand_less(d, pi, thr_d, thr_i);
         const unsigned mask = __ballot_sync(0xffffffffu, pass);
@@ -831,15 +859,16 @@ knn_wide_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, cons
     for (int tt = lane; tt < k; tt += 32) {
       const float dd_ = (tt < 32) ? kd[0] : kd[1];
       const int ii_ = (tt < 32) ? ki[0] : ki[1];
-      out_idx[(size_t)qi * k + tt] = tt < size ? ii_ : -1;
+      out_idx[(size_t)qi * k + tt] = tt < size ? (int)((unsigned)ii_ & IDX) : -1;
       if (out_sq) out_sq[(size_t)qi * k + tt] = tt < size ? dd_ : CUDART_INF_F;
     }
     continue;
   }
   if (size < 3) continue;
   float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const float4 p0 = (ki[0] >= 0 && ki[0] < n_xyz) ? __ldg(xyz + ki[0]) : make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 p1 = (ki[1] >= 0 && ki[1] < n_xyz) ? __ldg(xyz + ki[1]) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int i0 = (ki[0] == 0x7fffffff) ? -1 : (int)((unsigned)ki[0] & IDX), i1 = (ki[1] == 0x7fffffff) ? -1 : (int)((unsigned)ki[1] & IDX);
+  const float4 p0 = (i0 >= 0 && i0 < n_xyz) ? __ldg(xyz + i0) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 p1 = (i1 >= 0 && i1 < n_xyz) ? __ldg(xyz + i1) : make_float4(0.f, 0.f, 0.f, 0.f);
   for (int tt = 0; tt < size; ++tt) {
     const float4 src = (tt < 32) ? p0 : p1;
     const float px = __shfl_sync(0xffffffffu, src.x, tt & 31), py = __shfl_sync(0xffffffffu, src.y, tt & 31),
@@ -873,12 +902,13 @@ static float knn_env(const char* name, float dflt) {
 static float knn_c_avg() { static float v = knn_env("PITT_KNN_CAVG", 2.5f); return v; }             // mean points per fine cell
 // queries with more points than this in their 27 cells go to the warp-per-query kernel
 static int knn_mcap() { static float v = knn_env("PITT_KNN_MCAP", 1536.0f); return (int)v; }
+static int knn_seg_grid_min() { static float v = knn_env("PITT_KNN_SEG_MIN", 1500.0f); return (int)v; }
 static int knn_need(int k) { static float f = knn_env("PITT_KNN_NEED", 2.0f); return std::max(8, (int)ceilf(f * (float)k)); }  // points in the parent cell
 
 // Builds the multi-level grid of d_xyz[0..n) on ctx->stream; nothing here waits for the device. The two dense tables live
 // in the context (allocated once, reused by every call: calls of one context are ordered on its stream), the n-sized arrays
 // in the per-call arena.
-int mgrid_build(pitt_ctx* ctx, const float4* d_xyz, int n, float h_fixed, MGridBuf* out) {
+int mgrid_build(pitt_ctx* ctx, const float4* d_xyz, int n, float h_fixed, MGridBuf* out, const int* d_seg_off, const int* d_n_seg) {
   if (!ctx->mg_tables) {
     const size_t bytes = (size_t)(2 * (MG_CAP_CELLS + 4) + 2 * MG_CAP_BLOCKS) * sizeof(int) + 256;
     PITT_CUDA(ctx, cudaMalloc(&ctx->mg_tables, bytes));
@@ -904,7 +934,7 @@ int mgrid_build(pitt_ctx* ctx, const float4* d_xyz, int n, float h_fixed, MGridB
   mg_blocksum_kernel<<<MG_CAP_BLOCKS / 8, 256, 0, ctx->stream>>>(d_G, d_cnt, d_bsum);
   mg_top_kernel<<<1, 1024, 0, ctx->stream>>>(d_G, d_bsum, d_bbase, d_start);
   mg_blockscan_kernel<<<MG_CAP_BLOCKS / 8, 256, 0, ctx->stream>>>(d_G, d_cnt, d_bbase, d_start);
-  mg_scatter_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_xyz, n, d_cellid, d_start, d_cnt, out->d_sorted);
+  mg_scatter_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_xyz, n, d_cellid, d_start, d_cnt, out->d_sorted, d_seg_off, d_n_seg);
   ctx->launches += 9;
   PITT_CUDA(ctx, cudaGetLastError());
   out->d_G = d_G;
@@ -914,12 +944,14 @@ int mgrid_build(pitt_ctx* ctx, const float4* d_xyz, int n, float h_fixed, MGridB
 }
 
 // exact k-NN of every point of a large cloud; MODE 0 writes the neighbour lists, MODE 1 the normals
-template <int MODE>
-static int knn_large(pitt_ctx* ctx, const float4* d_xyz, int n, int k, const float vp[3], int* d_idx, float* d_sq, float4* d_nrm) {
+template <int MODE, bool SEG>
+static int knn_large(pitt_ctx* ctx, const float4* d_xyz, int n, int k, const float vp[3], int* d_idx, float* d_sq, float4* d_nrm,
+                     const int* d_seg_off = nullptr, const int* d_n_seg = nullptr) {
   MGridBuf mg;
-  PITT_TRY(mgrid_build(ctx, d_xyz, n, 0.0f, &mg));
+  PITT_TRY(mgrid_build(ctx, d_xyz, n, 0.0f, &mg, d_seg_off, d_n_seg));
   const int need = knn_need(k);
-  if (k <= KNN_FAST_KMAX && n < (1 << 28)) {
+  const int wide_grid = std::min(cdiv(n, WS_WARPS), ctx->sm_count * 8);
+  if (k <= KNN_FAST_KMAX && n < (1 << 24)) {
     // the collected keys take 512 B per query: clouds of more than a million points go through in chunks of queries
     const int chunk = std::min(n, 1 << 20);
     const size_t stride = (size_t)((chunk + 31) & ~31);
@@ -930,38 +962,43 @@ static int knn_large(pitt_ctx* ctx, const float4* d_xyz, int n, int k, const flo
     unsigned long long* dbg = g_knn_stats ? reinterpret_cast<unsigned long long*>(mg.d_scr + 8) : nullptr;
     for (int t0 = 0; t0 < n; t0 += chunk) {
       const int tc = std::min(chunk, n - t0);
-      knn_collect_kernel<<<cdiv(tc, KNN_FAST_TPB), KNN_FAST_TPB, 0, ctx->stream>>>(mg.d_G, mg.d_start, mg.d_sorted, t0, tc, k, need, knn_mcap(), d_keys,
-                                                                                 d_ncol, mg.d_scr + 7, mg.d_fb_list, dbg);
-      knn_sort_kernel<MODE><<<cdiv(tc, KNN_FAST_TPB), KNN_FAST_TPB, 0, ctx->stream>>>(mg.d_sorted, d_xyz, t0, tc, k, d_keys, d_ncol, vp[0],
-                                                                                     vp[1], vp[2], d_idx, d_sq, d_nrm);
+      knn_collect_kernel<SEG><<<cdiv(tc, KNN_FAST_TPB), KNN_FAST_TPB, 0, ctx->stream>>>(mg.d_G, mg.d_start, mg.d_sorted, t0, tc, k, need,
+                                                                                      knn_mcap(), d_keys, d_ncol, mg.d_scr + 7,
+                                                                                      mg.d_fb_list, dbg);
+      knn_sort_kernel<MODE, SEG><<<cdiv(tc, KNN_FAST_TPB), KNN_FAST_TPB, 0, ctx->stream>>>(mg.d_sorted, d_xyz, t0, tc, k, d_keys, d_ncol,
+                                                                                          vp[0], vp[1], vp[2], d_idx, d_sq, d_nrm);
       ctx->launches += 2;
     }
-    // the queries the fast path handed over, a warp each (their number is only known on the device: CTAs beyond it return at
-    // once; a few per cent of the points at most, so a quarter of the worst case is launched and the rest, if any, follows)
-    knn_wide_kernel<MODE><<<std::min(cdiv(n, WS_WARPS), ctx->sm_count * 8), WS_WARPS * 32, 0, ctx->stream>>>(
-        mg.d_G, mg.d_start, mg.d_sorted, d_xyz, n, k, need, vp[0], vp[1], vp[2], d_idx, d_sq, d_nrm, mg.d_scr + 7, mg.d_fb_list);
+    // the queries the fast path handed over, a warp each (their number is only known on the device: a fixed grid strides over them)
+    knn_wide_kernel<MODE, SEG><<<wide_grid, WS_WARPS * 32, 0, ctx->stream>>>(mg.d_G, mg.d_start, mg.d_sorted, d_xyz, n, k, need, vp[0], vp[1],
+                                                                             vp[2], d_idx, d_sq, d_nrm, mg.d_scr + 7, mg.d_fb_list);
     ctx->launches++;
   } else {
-    knn_wide_kernel<MODE><<<std::min(cdiv(n, WS_WARPS), ctx->sm_count * 8), WS_WARPS * 32, 0, ctx->stream>>>(
-        mg.d_G, mg.d_start, mg.d_sorted, d_xyz, n, k, need, vp[0], vp[1], vp[2], d_idx, d_sq, d_nrm, nullptr, nullptr);
+    if (SEG) return fail(ctx, PITT_ERR_INVALID, "segmented k-NN: k <= 56 and fewer than 2^24 points");
+    knn_wide_kernel<MODE, false><<<wide_grid, WS_WARPS * 32, 0, ctx->stream>>>(mg.d_G, mg.d_start, mg.d_sorted, d_xyz, n, k, need, vp[0], vp[1],
+                                                                               vp[2], d_idx, d_sq, d_nrm, nullptr, nullptr);
     ctx->launches++;
   }
   PITT_CUDA(ctx, cudaGetLastError());
-  ctx->knn_scr = mg.d_scr;  // diagnostics: pitt_debug_knn_stats reads [6] (finite points) and [7] (ring-search queries)
+  ctx->knn_scr = mg.d_scr;  // diagnostics: pitt_debug_knn_stats
   return PITT_OK;
 }
 
-// normals of several small clouds lying back to back in d_xyz[0..n_total) (the cluster clouds of a support; every segment at most
-// KNN_BRUTE_MAX points, the caller checks): ONE launch, every query searches its own segment. d_seg_off[0..*d_n_seg] on the device.
 int estimate_normals_segmented(pitt_ctx* ctx, const float4* d_xyz, int n_total, const int* d_seg_off, const int* d_n_seg, int k,
                                const float vp[3], float4* d_nrm) {
   if (n_total <= 0) return PITT_OK;
   if (k < 1 || k > KNN_KMAX) return fail(ctx, PITT_ERR_INVALID, "k must be in [1, 64]");
   const float nan = nanf("");
   fill_f4_kernel<<<cdiv(n_total, 256), 256, 0, ctx->stream>>>(d_nrm, n_total, make_float4(nan, nan, nan, nan));
+  ctx->launches++;
+  if (n_total >= knn_seg_grid_min() && k <= KNN_FAST_KMAX && n_total < (1 << 24)) {
+    // enough points for the grid to pay: ONE multi-level grid over all segments, every point tagged with its segment, the
+    // searches ignore candidates of other segments (6042 cluster points of a frame: 113 us all-pairs -> see profiles/)
+    return knn_large<1, true>(ctx, d_xyz, n_total, k, vp, nullptr, nullptr, d_nrm, d_seg_off, d_n_seg);
+  }
   knn_brute_kernel<1, true><<<cdiv(n_total, WS_WARPS), WS_WARPS * 32, 0, ctx->stream>>>(d_xyz, n_total, k, vp[0], vp[1], vp[2], nullptr, nullptr,
                                                                                          d_nrm, d_seg_off, d_n_seg);
-  ctx->launches += 2;
+  ctx->launches++;
   PITT_CUDA(ctx, cudaGetLastError());
   return PITT_OK;
 }
@@ -979,7 +1016,7 @@ int estimate_normals_impl(pitt_ctx* ctx, const float4* d_xyz, int n, int k, cons
     PITT_CUDA(ctx, cudaGetLastError());
     return PITT_OK;
   }
-  return knn_large<1>(ctx, d_xyz, n, k, vp, nullptr, nullptr, d_nrm);
+  return knn_large<1, false>(ctx, d_xyz, n, k, vp, nullptr, nullptr, d_nrm);
 }
 
 }  // namespace pitt
@@ -1023,7 +1060,7 @@ int pitt_knn(pitt_ctx* ctx, const pitt_cloud* c, int k, int32_t* out_idx, float*
       ctx->launches++;
     } else {
       const float vp[3] = {0.f, 0.f, 0.f};
-      PITT_TRY(knn_large<0>(ctx, c->d_xyz, n, k, vp, d_idx, d_sq, nullptr));
+      PITT_TRY((knn_large<0, false>(ctx, c->d_xyz, n, k, vp, d_idx, d_sq, nullptr)));
     }
     PITT_CUDA(ctx, cudaMemcpyAsync(out_idx, d_idx, tot * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     if (out_sqdist) PITT_CUDA(ctx, cudaMemcpyAsync(out_sqdist, d_sq, tot * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));

@@ -45,6 +45,9 @@ struct MGridBuf {
 // Builds the grid of d_xyz[0..n) on ctx->stream; nothing waits for the device. h_fixed > 0: fine cells of exactly that size
 // (enlarged only if the table would not fit) — the clusterer needs cells at least as wide as its tolerance; otherwise the cell
 // size follows the mean surface density (c_avg points per fine cell).
-int mgrid_build(pitt_ctx* ctx, const float4* d_xyz, int n, float h_fixed, MGridBuf* out);
+// d_seg_off (nullable, with *d_n_seg on the device): segment offsets; points then carry their segment in the top 8 bits of the
+// index word (n < 2^24).
+int mgrid_build(pitt_ctx* ctx, const float4* d_xyz, int n, float h_fixed, MGridBuf* out, const int* d_seg_off = nullptr,
+                const int* d_n_seg = nullptr);
 
 }  // namespace pitt

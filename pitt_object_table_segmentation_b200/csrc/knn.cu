@@ -577,7 +577,7 @@ __device__ __forceinline__ int mg_block27_count(const MGrid& g, const int* __res
 // candidate streams is hidden by switching warps. The keys go to global memory laid out [slot][query] (coalesced: consecutive
 // lanes are consecutive queries); ncol[query] = their number, or -1 when the query was handed to the warp-per-query kernel.
 template <bool SEG>
-__global__ void __launch_bounds__(KNN_FAST_TPB)
+__global__ void __launch_bounds__(KNN_FAST_TPB, 8)
 knn_collect_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, const float4* __restrict__ sorted, int t_base, int t_count,
                    int k, int need, int mcap, unsigned long long* __restrict__ keys, int* __restrict__ ncol, int* __restrict__ fb_count,
                    int* __restrict__ fb_list, unsigned long long* __restrict__ dbg) {
@@ -602,6 +602,7 @@ knn_collect_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, c
   int hand_over = -1;
   unsigned tsel = 0;
   int X, Y, Z, mtot;
+  int dir = 0;  // -1: the level has been lowered (too many points around), +1: raised (fewer than k inside the guaranteed radius)
   for (int attempt = 0;; ++attempt) {
     X = cx >> lvl; Y = cy >> lvl; Z = cz >> lvl;
     const float bound = mg_bound(g, q, X, Y, Z, lvl, 1);
@@ -609,12 +610,12 @@ knn_collect_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, c
     const float top = (bound > 0.0f) ? fminf(bound * bound, 27.5f * hl * hl) : 0.0f;  // cube = whole grid: its diagonal
     const unsigned btop = __float_as_uint(top);
     mtot = mg_block27_count(g, start, X, Y, Z, lvl);
-    if (btop < (40u << 20)) {
+    if (btop < (40u << 20) || attempt == 3) {
       hand_over = lvl;
       break;
     }
     if (mtot > mcap) {
-      if (attempt == 0 && lvl > 0) { --lvl; continue; }
+      if (dir <= 0 && lvl > 0) { --lvl; dir = -1; continue; }
       hand_over = lvl;
       break;
     }
@@ -641,9 +642,15 @@ knn_collect_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, c
       if (bsel < 0) atomicAdd(&dbg[7], 1ull);
       atomicMax(&dbg[8], (unsigned long long)mtot);
     }
-    if (bsel < 0) hand_over = lvl + 1;        // fewer than k points inside the guaranteed radius: a cube twice as wide
-    else if (cat > 64) hand_over = lvl;       // the k-th neighbour lies far below the window, or > 64 candidates in one bucket
-    else tsel = btop - ((unsigned)(31 - bsel) << 20);
+    if (bsel < 0) {
+      // fewer than k points inside the guaranteed radius: a cube twice as wide
+      if (dir >= 0 && lvl < MG_MAXLVL) { ++lvl; dir = 1; continue; }
+      hand_over = min(lvl + 1, MG_MAXLVL + 1);
+    } else if (cat > 64) {
+      hand_over = lvl;  // the k-th neighbour lies far below the window, or > 64 candidates in one bucket
+    } else {
+      tsel = btop - ((unsigned)(31 - bsel) << 20);
+    }
     break;
   }
   if (hand_over >= 0) {
@@ -901,9 +908,9 @@ static float knn_env(const char* name, float dflt) {
 // tuning knobs (measured on B200, 307 200-point frame, k = 50; the environment variables are for experiments only)
 static float knn_c_avg() { static float v = knn_env("PITT_KNN_CAVG", 2.5f); return v; }             // mean points per fine cell
 // queries with more points than this in their 27 cells go to the warp-per-query kernel
-static int knn_mcap() { static float v = knn_env("PITT_KNN_MCAP", 1536.0f); return (int)v; }
+static int knn_mcap() { static float v = knn_env("PITT_KNN_MCAP", 768.0f); return (int)v; }  // measured 1536 / 768 / 512: 379 / 318 / 291 us collect, but 512 floods the wide kernel
 static int knn_seg_grid_min() { static float v = knn_env("PITT_KNN_SEG_MIN", 1500.0f); return (int)v; }
-static int knn_need(int k) { static float f = knn_env("PITT_KNN_NEED", 2.0f); return std::max(8, (int)ceilf(f * (float)k)); }  // points in the parent cell
+static int knn_need(int k) { static float f = knn_env("PITT_KNN_NEED", 1.2f); return std::max(8, (int)ceilf(f * (float)k)); }  // points in the parent cell
 
 // Builds the multi-level grid of d_xyz[0..n) on ctx->stream; nothing here waits for the device. The two dense tables live
 // in the context (allocated once, reused by every call: calls of one context are ordered on its stream), the n-sized arrays

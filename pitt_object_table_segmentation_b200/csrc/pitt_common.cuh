@@ -60,6 +60,7 @@ struct pitt_ctx {
   cudaEvent_t ev_fit_fork = nullptr;
   void* h_stage = nullptr;
   size_t h_stage_bytes = 0;
+  const int* skip_flag = nullptr;  // sac.cu: device word read by the estimate / score kernels launched while it is set (non-zero: return)
   void* mg_tables = nullptr;  // knn.cu: the two dense cell tables of the multi-level grid (allocated on first use)
   int* knn_scr = nullptr;     // knn.cu: scratch of the last large-cloud k-NN (diagnostics, arena memory)
   void* h_pin2 = nullptr;  // pinned block for the gathered sample points (h_pin holds the sample indices at that time)

@@ -23,9 +23,9 @@ namespace pitt {
 template <int MODEL>
 __global__ void estimate_kernel(const float4* __restrict__ xyz, const float4* __restrict__ nrm,
                                 const int* __restrict__ samples, int H, Limits L, ScoreParams sp, HypRec* __restrict__ recs,
-                                float* __restrict__ coeffs8, uint8_t* __restrict__ flags) {
+                                float* __restrict__ coeffs8, uint8_t* __restrict__ flags, const int* __restrict__ skip) {
   int h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= H) return;
+  if (h >= H || (skip && *skip)) return;  // skip: the stop rule has already ended the loop inside an earlier batch
   constexpr int S = (MODEL == PITT_MODEL_PLANE) ? 3 : (MODEL == PITT_MODEL_SPHERE) ? 4 : (MODEL == PITT_MODEL_CYLINDER) ? 2 : 3;
   int s[4];
 #pragma unroll
@@ -68,8 +68,9 @@ __global__ void prep_rec_kernel(const float* __restrict__ coeffs, Limits L, Scor
 template <int MODEL, int P, int TPB>
 __global__ void __launch_bounds__(TPB)
 score_kernel(const float4* __restrict__ xyz, const float4* __restrict__ nrm, int n, const HypRec* __restrict__ recs,
-             int H, int hyp_chunk, int pts_per_cta, ScoreParams sp, int* __restrict__ counts) {
+             int H, int hyp_chunk, int pts_per_cta, ScoreParams sp, int* __restrict__ counts, const int* __restrict__ skip) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (skip && *skip) return;
   HypRec* s_rec = reinterpret_cast<HypRec*>(smem_raw);
   int* s_cnt = reinterpret_cast<int*>(smem_raw + (size_t)hyp_chunk * sizeof(HypRec));
   constexpr bool NEED_N = (MODEL == PITT_MODEL_CYLINDER || MODEL == PITT_MODEL_CONE);
@@ -131,9 +132,10 @@ score_kernel(const float4* __restrict__ xyz, const float4* __restrict__ nrm, int
 template <int MODEL, int P, int TPB>
 __global__ void __launch_bounds__(TPB)
 score2_kernel(const float4* __restrict__ xyz, const float4* __restrict__ nrm, int n, const HypRec* __restrict__ recs,
-              int H, int hyp_chunk, int pts_per_cta, ScoreParams sp, int* __restrict__ counts) {
+              int H, int hyp_chunk, int pts_per_cta, ScoreParams sp, int* __restrict__ counts, const int* __restrict__ skip) {
   constexpr int QCAP = 32 * P + 32;  // at most 31 left over + 32 * P pushed per hypothesis
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (skip && *skip) return;
   HypRec* s_rec = reinterpret_cast<HypRec*>(smem_raw);
   int* s_cnt = reinterpret_cast<int*>(smem_raw + (size_t)hyp_chunk * sizeof(HypRec));
   int2* s_q = reinterpret_cast<int2*>(smem_raw + (size_t)hyp_chunk * (sizeof(HypRec) + sizeof(int)) + 8 - ((size_t)hyp_chunk * 4) % 8);
@@ -1071,7 +1073,8 @@ ScoreParams score_params_for(const pitt_sac_params& p, const Limits& L) {
 template <int MODEL>
 static int launch_estimate(pitt_ctx* ctx, const pitt_cloud* c, const int* d_samples, int H, const Limits& L, const ScoreParams& sp,
                            HypRec* d_recs, float* d_coeffs8, uint8_t* d_flags) {
-  estimate_kernel<MODEL><<<cdiv(H, 128), 128, 0, ctx->stream>>>(c->d_xyz, c->d_nrm, d_samples, H, L, sp, d_recs, d_coeffs8, d_flags);
+  estimate_kernel<MODEL><<<cdiv(H, 128), 128, 0, ctx->stream>>>(c->d_xyz, c->d_nrm, d_samples, H, L, sp, d_recs, d_coeffs8, d_flags,
+                                                                  ctx->skip_flag);
   PITT_LAUNCH_CHECK(ctx, "estimate_kernel");
   return PITT_OK;
 }
@@ -1118,10 +1121,12 @@ static int launch_score_generic(pitt_ctx* ctx, const pitt_cloud* c, const HypRec
   dim3 grid(pblocks, n_chunks);
   if constexpr (TWO_TIER) {
     smem += 8 + (size_t)(TPB / 32) * (32 * P + 32) * sizeof(int2);  // per-warp queues of undecided evaluations
-    score2_kernel<MODEL, P, TPB><<<grid, TPB, smem, ctx->stream>>>(c->d_xyz, c->d_nrm, n, d_recs, H, hyp_chunk, pts_per_cta, sp, d_counts);
+    score2_kernel<MODEL, P, TPB><<<grid, TPB, smem, ctx->stream>>>(c->d_xyz, c->d_nrm, n, d_recs, H, hyp_chunk, pts_per_cta, sp, d_counts,
+                                                                   ctx->skip_flag);
     PITT_LAUNCH_CHECK(ctx, "score2_kernel");
   } else {
-    score_kernel<MODEL, P, TPB><<<grid, TPB, smem, ctx->stream>>>(c->d_xyz, c->d_nrm, n, d_recs, H, hyp_chunk, pts_per_cta, sp, d_counts);
+    score_kernel<MODEL, P, TPB><<<grid, TPB, smem, ctx->stream>>>(c->d_xyz, c->d_nrm, n, d_recs, H, hyp_chunk, pts_per_cta, sp, d_counts,
+                                                                  ctx->skip_flag);
     PITT_LAUNCH_CHECK(ctx, "score_kernel");
   }
   return PITT_OK;
@@ -1168,7 +1173,7 @@ static int launch_score_plane_packed(pitt_ctx* ctx, const pitt_cloud* c, const H
   // large jobs: dot products on the tensor cores (plane_tc.cu); the FFMA filter (mode 2) is the CUDA-core alternative
   const bool tensor = (g_plane_mode == 3) || (g_plane_mode == 0 && (double)n * (double)H >= 134217728.0);
   const bool filter = (g_plane_mode == 2);
-  const int* d_skip = nullptr;  // device flag: non-zero = a fast kernel did the work, the exact kernel returns at once
+  const int* d_skip = ctx->skip_flag;  // device flag: non-zero = a fast kernel did the work (or the stop rule has ended the loop), the exact kernel returns at once
   if (d_ready && !tensor) return fail(ctx, PITT_ERR_STATE, "streaming scoring needs the tensor path");
   if (tensor) PITT_TRY(launch_score_plane_tc(ctx, c, d_recs, H, sp, d_counts, &d_skip, d_extra, n_extra, d_ready, ready_pts));
   if (d_ready) PITT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_all, 0));  // the exact kernel (fallback) reads the whole cloud
@@ -1877,8 +1882,9 @@ constexpr int SCAN_FLAG_NEED_MORE = 1, SCAN_FLAG_AMBIGUOUS = 2, SCAN_FLAG_BAD_SA
 __global__ void __launch_bounds__(256)
 ransac_scan_kernel(const int* __restrict__ counts, const uint8_t* __restrict__ flags, int H, int n, int S, int max_iterations,
                    double log_probability, int speculative_plane, const float* __restrict__ coeffs8, int* __restrict__ ints,
-                   float* __restrict__ model_out) {
+                   float* __restrict__ model_out, const int* __restrict__ skip, int final_batch) {
   extern __shared__ __align__(16) unsigned char scan_smem[];
+  if (skip && *skip) return;  // an earlier batch has already ended the loop
   int* s_cnt = reinterpret_cast<int*>(scan_smem);
   uint8_t* s_flag = reinterpret_cast<uint8_t*>(s_cnt + H);
   for (int i = threadIdx.x; i < H; i += blockDim.x) { s_cnt[i] = counts[i]; s_flag[i] = flags[i]; }
@@ -1910,11 +1916,13 @@ ransac_scan_kernel(const int* __restrict__ counts, const uint8_t* __restrict__ f
     ++iterations;
     if (iterations > max_iterations) break;
   }
+  if ((fl & SCAN_FLAG_NEED_MORE) && !final_batch) return;  // the loop runs on into the next batch: ints[10] stays 0
   ints[0] = best_pos;
   ints[1] = best_pos >= 0 ? best : 0;
   ints[6] = iterations;
   ints[7] = skipped;
   ints[8] = fl;
+  ints[10] = 1;  // done: the kernels of the following batch return at once
   for (int i = 0; i < 8; ++i) model_out[i] = best_pos >= 0 ? coeffs8[(size_t)best_pos * 8 + i] : 0.0f;
 }
 // ALL_H: the winner kernel's {index, count} plus the bookkeeping of the block above
@@ -1990,10 +1998,15 @@ int sac_segment_async(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params&
   PITT_TRY(arena_alloc(ctx, (size_t)H * 8, &d_coeffs8));
   PITT_TRY(arena_alloc(ctx, (size_t)H, &d_flags));
   PITT_TRY(arena_alloc(ctx, (size_t)H, &d_counts));
-  PITT_TRY(sac_estimate(ctx, c, model, d_samples, H, L, sp, d_recs, d_coeffs8, d_flags));
-  PITT_TRY(sac_score(ctx, c, model, d_recs, H, sp, d_counts));
   int* d_ints = out->d_ints;
   float* d_flt = out->d_flt;
+  // PCL's adaptive stop usually ends the loop after a few dozen hypotheses: the first SCAN_BATCH of the stream are estimated,
+  // scored and scanned first; the kernels of the remainder read the "done" word the scan leaves behind and return at once
+  // (results do not depend on the batching: the scan always runs in stream order from the first hypothesis)
+  constexpr int SCAN_BATCH = 256;
+  const int H1 = (!all_h && H > SCAN_BATCH + SCAN_BATCH / 2) ? SCAN_BATCH : H;
+  PITT_TRY(sac_estimate(ctx, c, model, d_samples, H1, L, sp, d_recs, d_coeffs8, d_flags));
+  PITT_TRY(sac_score(ctx, c, model, d_recs, H1, sp, d_counts));
   if (all_h) {
     PITT_TRY(sac_winner(ctx, d_counts, d_flags, H, d_coeffs8, d_ints, d_flt));
     all_h_info_kernel<<<1, 1, 0, ctx->stream>>>(H, d_ints);
@@ -2006,9 +2019,20 @@ int sac_segment_async(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params&
       PITT_CUDA(ctx, cudaFuncSetAttribute(ransac_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       opt_in[ctx->device & 63] = true;
     }
-    ransac_scan_kernel<<<1, 256, smem, ctx->stream>>>(d_counts, d_flags, H, n, S, p.max_iterations, log(1.0 - p.probability),
-                                                      speculative ? 1 : 0, d_coeffs8, d_ints, d_flt);
+    const double log_p = log(1.0 - p.probability);
+    ransac_scan_kernel<<<1, 256, (size_t)H1 * 5 + 16, ctx->stream>>>(d_counts, d_flags, H1, n, S, p.max_iterations, log_p, speculative ? 1 : 0,
+                                                                    d_coeffs8, d_ints, d_flt, nullptr, H1 == H ? 1 : 0);
     PITT_LAUNCH_CHECK(ctx, "ransac_scan_kernel");
+    if (H1 < H) {
+      ctx->skip_flag = d_ints + 10;
+      int st = sac_estimate(ctx, c, model, d_samples + (size_t)H1 * S, H - H1, L, sp, d_recs + H1, d_coeffs8 + (size_t)H1 * 8, d_flags + H1);
+      if (st == PITT_OK) st = sac_score(ctx, c, model, d_recs + H1, H - H1, sp, d_counts + H1);
+      ctx->skip_flag = nullptr;
+      PITT_TRY(st);
+      ransac_scan_kernel<<<1, 256, smem, ctx->stream>>>(d_counts, d_flags, H, n, S, p.max_iterations, log_p, speculative ? 1 : 0, d_coeffs8,
+                                                        d_ints, d_flt, d_ints + 10, 1);
+      PITT_LAUNCH_CHECK(ctx, "ransac_scan_kernel");
+    }
   }
   PITT_TRY(sac_finish(ctx, c, p, L, sp, d_flt, d_flt + 8, d_ints + 2, d_ints + 3, d_ints + 4, out->d_inl));
   first_inlier_kernel<<<1, 1, 0, ctx->stream>>>(out->d_inl, d_ints + 3, d_ints + 9);

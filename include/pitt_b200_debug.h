@@ -27,9 +27,10 @@ void pitt_debug_force_generic_plane(int on);
 void pitt_debug_score_mode(int mode);
 /* 1: small selections take the four-launch path instead of select_small_kernel */
 void pitt_debug_select_no_fuse(int v);
-/* 1: pitt_segment_frame takes the round-1 path (one synchronous seg.segment() per primitive fit) instead of the asynchronous
- * fit chains; results are identical (tests/test_gpu_services.py) */
-void pitt_debug_frame_mode(int legacy);
+/* primitive fits of pitt_segment_frame: 0 = batched per model (every launch serves all clusters of a support), 1 = the round-1
+ * path (one synchronous seg.segment() per fit), 2 = one asynchronous chain per fit; results are identical
+ * (tests/test_gpu_services.py) */
+void pitt_debug_frame_mode(int mode);
 /* rows from which Levenberg-Marquardt runs on a thread-block cluster */
 void pitt_debug_lm_cluster_min(int rows);
 /* pitt_sac_segment_host: k equal chunks (1..8), 0 = by cloud size */

@@ -437,8 +437,13 @@ extern __shared__ __align__(16) float lm_dyn_smem[];
 template <int MODEL, int CL, bool SMEM>
 __global__ void __launch_bounds__(LM_TPB)
 lm_kernel(const float4* __restrict__ xyz, const int* __restrict__ idx, const int* __restrict__ n_idx_ptr, int m_cap,
-          const float* __restrict__ model_in, float* __restrict__ work, float* __restrict__ refined, int* __restrict__ info_out) {
+          const float* __restrict__ model_in, float* __restrict__ work, float* __restrict__ refined, int* __restrict__ info_out,
+          const FitDesc* __restrict__ D = nullptr) {
   __shared__ LmShared S;
+  if (D) {  // batched (one CTA per problem, shared-memory variant only): problem blockIdx.x
+    const FitDesc d = D[blockIdx.x];
+    xyz = d.xyz; idx = d.inl; n_idx_ptr = d.ints + 2; model_in = d.flt; refined = d.flt + 8; info_out = d.ints + 4;
+  }
   constexpr int n = (MODEL == PITT_MODEL_SPHERE) ? 4 : 7;
   const int m = min(*n_idx_ptr, m_cap);
   float* fjac = SMEM ? lm_dyn_smem : work;
@@ -747,7 +752,38 @@ static cudaError_t lm_launch(pitt_ctx* ctx, bool cluster, const float4* xyz, con
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, lm_kernel<MODEL, LM_CLUSTER, false>, xyz, d_idx, d_n_idx, m_cap, d_model, d_work, d_refined, d_lm_info);
+  return cudaLaunchKernelEx(&cfg, lm_kernel<MODEL, LM_CLUSTER, false>, xyz, d_idx, d_n_idx, m_cap, d_model, d_work, d_refined, d_lm_info,
+                            (const FitDesc*)nullptr);
+}
+
+// one CTA per problem of a batch (rows <= LM_SMEM_ROWS each: the object clusters of a frame), work arrays in shared memory
+template <int MODEL>
+static cudaError_t lm_launch_batch(pitt_ctx* ctx, const FitDesc* d_desc, int nprob, int m_cap) {
+  constexpr int n = (MODEL == PITT_MODEL_SPHERE) ? 4 : 7;
+  static bool attr_set[64] = {false};
+  if (!attr_set[ctx->device & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(lm_kernel<MODEL, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (n + 3) * LM_SMEM_ROWS * (int)sizeof(float));
+    if (e != cudaSuccess) return e;
+    attr_set[ctx->device & 63] = true;
+  }
+  const size_t smem = (size_t)(n + 3) * m_cap * sizeof(float);
+  lm_kernel<MODEL, 1, true><<<nprob, LM_TPB, smem, ctx->stream>>>(nullptr, nullptr, nullptr, m_cap, nullptr, nullptr, nullptr, nullptr, d_desc);
+  return cudaGetLastError();
+}
+int lm_refine_batch(pitt_ctx* ctx, int model, const FitDesc* d_desc, int nprob, int m_cap) {
+  if (m_cap > LM_SMEM_ROWS) return fail(ctx, PITT_ERR_INVALID, "lm_refine_batch: problems of at most 4096 rows");
+  m_cap = std::max(m_cap, 1);
+  cudaError_t e;
+  switch (model) {
+    case PITT_MODEL_SPHERE: e = lm_launch_batch<PITT_MODEL_SPHERE>(ctx, d_desc, nprob, m_cap); break;
+    case PITT_MODEL_CYLINDER: e = lm_launch_batch<PITT_MODEL_CYLINDER>(ctx, d_desc, nprob, m_cap); break;
+    case PITT_MODEL_CONE: e = lm_launch_batch<PITT_MODEL_CONE>(ctx, d_desc, nprob, m_cap); break;
+    default: return fail(ctx, PITT_ERR_INVALID, "lm_refine_batch: model has no LM refinement");
+  }
+  ctx->launches++;
+  if (e != cudaSuccess) return fail(ctx, PITT_ERR_CUDA, "lm_kernel launch (batch)", e);
+  return PITT_OK;
 }
 
 int g_lm_cluster_min = LM_CLUSTER_MIN;  // test hook: rows from which the cluster path is used

@@ -793,7 +793,10 @@ void pitt_debug_force_generic_plane(int on) { g_force_generic_plane = on; }
 void pitt_debug_plane_mode(int mode) { g_plane_mode = mode; }
 void pitt_debug_score_mode(int mode) { g_score_mode = mode; }
 void pitt_debug_select_no_fuse(int v) { g_select_no_fuse = v; }
-void pitt_debug_frame_mode(int legacy) { g_frame_legacy = legacy; }
+void pitt_debug_frame_mode(int mode) {
+  g_frame_legacy = (mode == 1);
+  g_frame_no_batch = (mode == 2);
+}
 void pitt_debug_lm_cluster_min(int rows) { g_lm_cluster_min = rows; }
 void pitt_debug_plane_filter_stats(int enable, uint64_t* out2) {
   g_plane_filter_collect_stats = enable;

@@ -23,8 +23,20 @@ namespace pitt {
 template <int MODEL>
 __global__ void estimate_kernel(const float4* __restrict__ xyz, const float4* __restrict__ nrm,
                                 const int* __restrict__ samples, int H, Limits L, ScoreParams sp, HypRec* __restrict__ recs,
-                                float* __restrict__ coeffs8, uint8_t* __restrict__ flags, const int* __restrict__ skip) {
+                                float* __restrict__ coeffs8, uint8_t* __restrict__ flags, const int* __restrict__ skip,
+                                const FitDesc* __restrict__ D = nullptr, int hoff = 0) {
   int h = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int SB = (MODEL == PITT_MODEL_PLANE) ? 3 : (MODEL == PITT_MODEL_SPHERE) ? 4 : (MODEL == PITT_MODEL_CYLINDER) ? 2 : 3;
+  if (D) {  // batched: problem blockIdx.y, hypotheses [hoff, hoff + H) of its stream
+    const FitDesc d = D[blockIdx.y];
+    xyz = d.xyz; nrm = d.nrm;
+    samples = d.samples + (size_t)hoff * SB;
+    H = min(H, d.H - hoff);
+    recs = d.recs + hoff;
+    coeffs8 = d.coeffs8 + (size_t)hoff * 8;
+    flags = d.flags + hoff;
+    skip = hoff > 0 ? d.ints + 10 : nullptr;
+  }
   if (h >= H || (skip && *skip)) return;  // skip: the stop rule has already ended the loop inside an earlier batch
   constexpr int S = (MODEL == PITT_MODEL_PLANE) ? 3 : (MODEL == PITT_MODEL_SPHERE) ? 4 : (MODEL == PITT_MODEL_CYLINDER) ? 2 : 3;
   int s[4];
@@ -51,7 +63,12 @@ __global__ void estimate_kernel(const float4* __restrict__ xyz, const float4* __
 
 // coefficients (device, 8 floats) -> one scoring record (isModelValid applied)
 template <int MODEL>
-__global__ void prep_rec_kernel(const float* __restrict__ coeffs, Limits L, ScoreParams sp, HypRec* __restrict__ rec) {
+__global__ void prep_rec_kernel(const float* __restrict__ coeffs, Limits L, ScoreParams sp, HypRec* __restrict__ rec,
+                                const FitDesc* __restrict__ D = nullptr) {
+  if (D) {  // batched: problem blockIdx.x, the winner's record goes to recs[0] (the hypotheses are not needed any more)
+    coeffs = D[blockIdx.x].flt;
+    rec = D[blockIdx.x].recs;
+  }
   float mc[8];
   for (int i = 0; i < 8; ++i) mc[i] = coeffs[i];
   bool valid = model_valid<MODEL>(L, mc);
@@ -68,14 +85,25 @@ __global__ void prep_rec_kernel(const float* __restrict__ coeffs, Limits L, Scor
 template <int MODEL, int P, int TPB>
 __global__ void __launch_bounds__(TPB)
 score_kernel(const float4* __restrict__ xyz, const float4* __restrict__ nrm, int n, const HypRec* __restrict__ recs,
-             int H, int hyp_chunk, int pts_per_cta, ScoreParams sp, int* __restrict__ counts, const int* __restrict__ skip) {
+             int H, int hyp_chunk, int pts_per_cta, ScoreParams sp, int* __restrict__ counts, const int* __restrict__ skip,
+             const FitDesc* __restrict__ D = nullptr, int hoff = 0) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (D) {  // batched: problem blockIdx.z
+    const FitDesc d = D[blockIdx.z];
+    xyz = d.xyz; nrm = d.nrm; n = d.n;
+    recs = d.recs + hoff;
+    H = min(H, d.H - hoff);
+    counts = d.counts + hoff;
+    skip = hoff > 0 ? d.ints + 10 : nullptr;
+    if (H <= 0) return;
+  }
   if (skip && *skip) return;
   HypRec* s_rec = reinterpret_cast<HypRec*>(smem_raw);
   int* s_cnt = reinterpret_cast<int*>(smem_raw + (size_t)hyp_chunk * sizeof(HypRec));
   constexpr bool NEED_N = (MODEL == PITT_MODEL_CYLINDER || MODEL == PITT_MODEL_CONE);
   const int h0 = blockIdx.y * hyp_chunk;
   const int hc = min(hyp_chunk, H - h0);
+  if (hc <= 0) return;
   // stage the hypothesis chunk (16 B per thread per step, coalesced)
   {
     const float4* src = reinterpret_cast<const float4*>(recs + h0);
@@ -132,15 +160,26 @@ score_kernel(const float4* __restrict__ xyz, const float4* __restrict__ nrm, int
 template <int MODEL, int P, int TPB>
 __global__ void __launch_bounds__(TPB)
 score2_kernel(const float4* __restrict__ xyz, const float4* __restrict__ nrm, int n, const HypRec* __restrict__ recs,
-              int H, int hyp_chunk, int pts_per_cta, ScoreParams sp, int* __restrict__ counts, const int* __restrict__ skip) {
+              int H, int hyp_chunk, int pts_per_cta, ScoreParams sp, int* __restrict__ counts, const int* __restrict__ skip,
+              const FitDesc* __restrict__ D = nullptr, int hoff = 0) {
   constexpr int QCAP = 32 * P + 32;  // at most 31 left over + 32 * P pushed per hypothesis
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  if (D) {  // batched: problem blockIdx.z
+    const FitDesc d = D[blockIdx.z];
+    xyz = d.xyz; nrm = d.nrm; n = d.n;
+    recs = d.recs + hoff;
+    H = min(H, d.H - hoff);
+    counts = d.counts + hoff;
+    skip = hoff > 0 ? d.ints + 10 : nullptr;
+    if (H <= 0) return;
+  }
   if (skip && *skip) return;
   HypRec* s_rec = reinterpret_cast<HypRec*>(smem_raw);
   int* s_cnt = reinterpret_cast<int*>(smem_raw + (size_t)hyp_chunk * sizeof(HypRec));
   int2* s_q = reinterpret_cast<int2*>(smem_raw + (size_t)hyp_chunk * (sizeof(HypRec) + sizeof(int)) + 8 - ((size_t)hyp_chunk * 4) % 8);
   const int h0 = blockIdx.y * hyp_chunk;
   const int hc = min(hyp_chunk, H - h0);
+  if (hc <= 0) return;
   {
     const float4* src = reinterpret_cast<const float4*>(recs + h0);
     float4* dst = reinterpret_cast<float4*>(s_rec);
@@ -867,8 +906,16 @@ constexpr int SEL_SMALL_MAX = 16384;
 template <int MODEL>
 __global__ void __launch_bounds__(SEL_SMALL_TPB)
 select_small_kernel(const float4* __restrict__ xyz, const float4* __restrict__ nrm, int n, const float* __restrict__ coeffs, Limits L,
-                    ScoreParams sp, int* __restrict__ out, int* __restrict__ total) {
+                    ScoreParams sp, int* __restrict__ out, int* __restrict__ total, const FitDesc* __restrict__ D = nullptr,
+                    int refined = 0) {
   constexpr bool NEED_N = (MODEL == PITT_MODEL_CYLINDER || MODEL == PITT_MODEL_CONE);
+  if (D) {  // batched: problem blockIdx.x; refined = 0: inliers of the winner (count -> ints[2]), 1: of the refined model (-> ints[3])
+    const FitDesc d = D[blockIdx.x];
+    xyz = d.xyz; nrm = d.nrm; n = d.n;
+    coeffs = refined ? d.flt + 8 : d.flt;
+    out = d.inl;
+    total = d.ints + (refined ? 3 : 2);
+  }
   __shared__ HypRec s_rec;
   __shared__ int s_w[SEL_SMALL_TPB / 32];
   __shared__ int s_base, s_tile_total;
@@ -920,13 +967,16 @@ select_small_kernel(const float4* __restrict__ xyz, const float4* __restrict__ n
 // The nine sums are accumulated in double by a fixed-shape tree (deterministic) and rounded once
 // to float — the oracle defines them as exact sums rounded once (oracle/orc_math.h DD).
 // =====================================================================================
-constexpr int REF_TPB = 256;
-constexpr int REF_BLOCKS = 296;
 __global__ void __launch_bounds__(REF_TPB)
 plane_sums_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict__ rec, const int* __restrict__ idx,
-                  const int* __restrict__ n_idx, ScoreParams sp, double* __restrict__ partial /*[blocks][10]*/) {
+                  const int* __restrict__ n_idx, ScoreParams sp, double* __restrict__ partial /*[blocks][10]*/,
+                  const FitDesc* __restrict__ D = nullptr) {
   // two modes: idx != nullptr sums the listed points; otherwise the predicate of *rec decides
   __shared__ double s_red[REF_TPB / 32][10];
+  if (D) {  // batched: problem blockIdx.y, predicate mode with the record prep_rec_kernel left in recs[0]
+    const FitDesc d = D[blockIdx.y];
+    xyz = d.xyz; n = d.n; rec = d.recs; idx = nullptr; n_idx = nullptr; partial = d.partial;
+  }
   RecRegs<PITT_MODEL_PLANE> r;
   if (rec) r.load(rec);
   double a[10];
@@ -956,8 +1006,13 @@ plane_sums_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restric
   }
 }
 __global__ void plane_refine_final_kernel(const double* __restrict__ partial, int blocks, const float* __restrict__ model,
-                                          float* __restrict__ refined, int* __restrict__ n_model_inliers) {
+                                          float* __restrict__ refined, int* __restrict__ n_model_inliers,
+                                          const FitDesc* __restrict__ D = nullptr) {
   __shared__ double s[10];
+  if (D) {  // batched: problem blockIdx.x
+    const FitDesc d = D[blockIdx.x];
+    partial = d.partial; model = d.flt; refined = d.flt + 8; n_model_inliers = d.ints + 2;
+  }
   __shared__ double s_part[REF_BLOCKS * 10];
   // all threads fetch the partial sums at once (one L2 round trip instead of `blocks` dependent ones); the additions keep
   // their order (block 0, 1, 2, ...), so the sums are bit-identical to the sequential loop
@@ -1882,8 +1937,17 @@ constexpr int SCAN_FLAG_NEED_MORE = 1, SCAN_FLAG_AMBIGUOUS = 2, SCAN_FLAG_BAD_SA
 __global__ void __launch_bounds__(256)
 ransac_scan_kernel(const int* __restrict__ counts, const uint8_t* __restrict__ flags, int H, int n, int S, int max_iterations,
                    double log_probability, int speculative_plane, const float* __restrict__ coeffs8, int* __restrict__ ints,
-                   float* __restrict__ model_out, const int* __restrict__ skip, int final_batch) {
+                   float* __restrict__ model_out, const int* __restrict__ skip, int final_batch,
+                   const FitDesc* __restrict__ D = nullptr) {
   extern __shared__ __align__(16) unsigned char scan_smem[];
+  if (D) {  // batched: problem blockIdx.x scans the first min(H, d.H) hypotheses of its stream
+    const FitDesc d = D[blockIdx.x];
+    counts = d.counts; flags = d.flags; coeffs8 = d.coeffs8; ints = d.ints; model_out = d.flt; n = d.n;
+    final_batch = (H >= d.H) ? 1 : 0;
+    H = min(H, d.H);
+    skip = skip ? d.ints + 10 : nullptr;
+    if (H <= 0) return;
+  }
   if (skip && *skip) return;  // an earlier batch has already ended the loop
   int* s_cnt = reinterpret_cast<int*>(scan_smem);
   uint8_t* s_flag = reinterpret_cast<uint8_t*>(s_cnt + H);
@@ -1931,7 +1995,11 @@ __global__ void all_h_info_kernel(int H, int* __restrict__ ints) {
   ints[7] = 0;
   ints[8] = 0;
 }
-__global__ void first_inlier_kernel(const int* __restrict__ inl, const int* __restrict__ n_final, int* __restrict__ out) {
+__global__ void first_inlier_kernel(const int* __restrict__ inl, const int* __restrict__ n_final, int* __restrict__ out,
+                                    const FitDesc* __restrict__ D = nullptr) {
+  if (D) {  // batched: problem blockIdx.x
+    inl = D[blockIdx.x].inl; n_final = D[blockIdx.x].ints + 3; out = D[blockIdx.x].ints + 9;
+  }
   *out = (*n_final > 0) ? inl[0] : -1;
 }
 
@@ -2040,6 +2108,112 @@ int sac_segment_async(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params&
   out->H = H;
   *issued = true;
   return PITT_OK;
+}
+
+
+// ------------------------------------------------------------------ a batch of seg.segment() calls in one set of launches
+template <int MODEL>
+static int fit_batch_estimate_score(pitt_ctx* ctx, const FitDesc* d_desc, int nprob, int n_max, int h0, int hc, const Limits& L,
+                                    const ScoreParams& sp) {
+  estimate_kernel<MODEL><<<dim3(cdiv(hc, 128), nprob), 128, 0, ctx->stream>>>(nullptr, nullptr, nullptr, hc, L, sp, nullptr, nullptr, nullptr,
+                                                                            nullptr, d_desc, h0);
+  PITT_LAUNCH_CHECK(ctx, "estimate_kernel (batch)");
+  // the configuration of launch_score_generic for the largest problem of the batch; smaller ones leave their surplus CTAs idle
+  constexpr int TPB = 256;
+  constexpr bool TWO = (MODEL == PITT_MODEL_CYLINDER || MODEL == PITT_MODEL_CONE);
+  constexpr int P = TWO ? 1 : 8;
+  const int tile = TPB * P;
+  const int tiles = cdiv(n_max, tile);
+  const int want_ctas = std::max(1, ctx->sm_count * 4 / nprob);
+  int hyp_chunk = hc < 512 ? hc : 512;
+  if (tiles * cdiv(hc, hyp_chunk) < want_ctas) {
+    const int chunks_wanted = cdiv(want_ctas, tiles);
+    hyp_chunk = std::max(16, cdiv(hc, chunks_wanted));
+    if (hyp_chunk > 512) hyp_chunk = 512;
+    if (hyp_chunk > hc) hyp_chunk = hc;
+  }
+  const int n_chunks = cdiv(hc, hyp_chunk);
+  int pblocks = std::max(1, (ctx->sm_count * 8 / nprob) / n_chunks);
+  if (pblocks > tiles) pblocks = tiles;
+  const int pts_per_cta = cdiv(tiles, pblocks) * tile;
+  pblocks = cdiv(n_max, pts_per_cta);
+  size_t smem = (size_t)hyp_chunk * (sizeof(HypRec) + sizeof(int));
+  const dim3 grid(pblocks, n_chunks, nprob);
+  if constexpr (TWO) {
+    smem += 8 + (size_t)(TPB / 32) * (32 * P + 32) * sizeof(int2);
+    score2_kernel<MODEL, P, TPB><<<grid, TPB, smem, ctx->stream>>>(nullptr, nullptr, 0, nullptr, hc, hyp_chunk, pts_per_cta, sp, nullptr, nullptr,
+                                                                   d_desc, h0);
+  } else {
+    score_kernel<MODEL, P, TPB><<<grid, TPB, smem, ctx->stream>>>(nullptr, nullptr, 0, nullptr, hc, hyp_chunk, pts_per_cta, sp, nullptr, nullptr,
+                                                                  d_desc, h0);
+  }
+  PITT_LAUNCH_CHECK(ctx, "score kernel (batch)");
+  return PITT_OK;
+}
+template <int MODEL>
+static int fit_batch_model(pitt_ctx* ctx, const pitt_sac_params& p, const FitDesc* d_desc, int nprob, int n_max, int H_max,
+                           bool speculative_plane) {
+  const Limits L = limits_for(p);
+  const ScoreParams sp = score_params_for(p, L);
+  constexpr int S = (MODEL == PITT_MODEL_PLANE) ? 3 : (MODEL == PITT_MODEL_SPHERE) ? 4 : (MODEL == PITT_MODEL_CYLINDER) ? 2 : 3;
+  constexpr int SCAN_BATCH = 256;
+  const int H1 = H_max > SCAN_BATCH + SCAN_BATCH / 2 ? SCAN_BATCH : H_max;
+  const double log_p = log(1.0 - p.probability);
+  if ((size_t)H_max * 5 + 16 > 48 * 1024) return fail(ctx, PITT_ERR_INVALID, "sac_fit_batch_async: too many hypotheses");
+  PITT_TRY((fit_batch_estimate_score<MODEL>(ctx, d_desc, nprob, n_max, 0, H1, L, sp)));
+  ransac_scan_kernel<<<nprob, 256, (size_t)H1 * 5 + 16, ctx->stream>>>(nullptr, nullptr, H1, 0, S, p.max_iterations, log_p, speculative_plane ? 1 : 0,
+                                                                      nullptr, nullptr, nullptr, nullptr, 0, d_desc);
+  PITT_LAUNCH_CHECK(ctx, "ransac_scan_kernel (batch)");
+  if (H1 < H_max) {
+    PITT_TRY((fit_batch_estimate_score<MODEL>(ctx, d_desc, nprob, n_max, H1, H_max - H1, L, sp)));
+    ransac_scan_kernel<<<nprob, 256, (size_t)H_max * 5 + 16, ctx->stream>>>(nullptr, nullptr, H_max, 0, S, p.max_iterations, log_p,
+                                                                           speculative_plane ? 1 : 0, nullptr, nullptr, nullptr,
+                                                                           reinterpret_cast<const int*>(d_desc), 1, d_desc);
+    PITT_LAUNCH_CHECK(ctx, "ransac_scan_kernel (batch)");
+  }
+  // refinement of the winners + final inliers (SACSegmentation::segment after computeModel), all problems per launch
+  if (MODEL == PITT_MODEL_PLANE) {
+    if (p.optimize) {
+      prep_rec_kernel<PITT_MODEL_PLANE><<<nprob, 1, 0, ctx->stream>>>(nullptr, L, sp, nullptr, d_desc);
+      PITT_LAUNCH_CHECK(ctx, "prep_rec_kernel (batch)");
+      plane_sums_kernel<<<dim3(REF_BLOCKS, nprob), REF_TPB, 0, ctx->stream>>>(nullptr, 0, nullptr, nullptr, nullptr, sp, nullptr, d_desc);
+      PITT_LAUNCH_CHECK(ctx, "plane_sums_kernel (batch)");
+      plane_refine_final_kernel<<<nprob, 256, 0, ctx->stream>>>(nullptr, REF_BLOCKS, nullptr, nullptr, nullptr, d_desc);
+      PITT_LAUNCH_CHECK(ctx, "plane_refine_final_kernel (batch)");
+      select_small_kernel<MODEL><<<nprob, SEL_SMALL_TPB, 0, ctx->stream>>>(nullptr, nullptr, 0, nullptr, L, sp, nullptr, nullptr, d_desc, 1);
+      PITT_LAUNCH_CHECK(ctx, "select_small_kernel (batch)");
+    } else {
+      return fail(ctx, PITT_ERR_INVALID, "sac_fit_batch_async: optimize = 0 takes the per-fit path");
+    }
+  } else {
+    if (!p.optimize) return fail(ctx, PITT_ERR_INVALID, "sac_fit_batch_async: optimize = 0 takes the per-fit path");
+    select_small_kernel<MODEL><<<nprob, SEL_SMALL_TPB, 0, ctx->stream>>>(nullptr, nullptr, 0, nullptr, L, sp, nullptr, nullptr, d_desc, 0);
+    PITT_LAUNCH_CHECK(ctx, "select_small_kernel (batch)");
+    PITT_TRY(lm_refine_batch(ctx, MODEL, d_desc, nprob, n_max));
+    select_small_kernel<MODEL><<<nprob, SEL_SMALL_TPB, 0, ctx->stream>>>(nullptr, nullptr, 0, nullptr, L, sp, nullptr, nullptr, d_desc, 1);
+    PITT_LAUNCH_CHECK(ctx, "select_small_kernel (batch)");
+  }
+  first_inlier_kernel<<<nprob, 1, 0, ctx->stream>>>(nullptr, nullptr, nullptr, d_desc);
+  PITT_LAUNCH_CHECK(ctx, "first_inlier_kernel (batch)");
+  return PITT_OK;
+}
+int sac_fit_batch_async(pitt_ctx* ctx, const pitt_sac_params& p, const FitDesc* h_desc, const FitDesc* d_desc, int nprob, bool speculative_plane) {
+  if (nprob <= 0) return PITT_OK;
+  if (p.stop != PITT_STOP_PCL_ADAPTIVE) return fail(ctx, PITT_ERR_INVALID, "sac_fit_batch_async: PCL adaptive stop only");
+  int n_max = 1, H_max = 0;
+  for (int i = 0; i < nprob; ++i) {
+    n_max = std::max(n_max, h_desc[i].n);
+    H_max = std::max(H_max, h_desc[i].H);
+  }
+  if (n_max > SEL_SMALL_MAX || n_max > 4096) return fail(ctx, PITT_ERR_INVALID, "sac_fit_batch_async: problems of at most 4096 points");
+  if (H_max <= 0) return PITT_OK;
+  switch (p.model) {
+    case PITT_MODEL_PLANE: return fit_batch_model<PITT_MODEL_PLANE>(ctx, p, d_desc, nprob, n_max, H_max, speculative_plane);
+    case PITT_MODEL_SPHERE: return fit_batch_model<PITT_MODEL_SPHERE>(ctx, p, d_desc, nprob, n_max, H_max, false);
+    case PITT_MODEL_CYLINDER: return fit_batch_model<PITT_MODEL_CYLINDER>(ctx, p, d_desc, nprob, n_max, H_max, false);
+    case PITT_MODEL_CONE: return fit_batch_model<PITT_MODEL_CONE>(ctx, p, d_desc, nprob, n_max, H_max, false);
+    default: return fail(ctx, PITT_ERR_INVALID, "bad model");
+  }
 }
 
 }  // namespace pitt

@@ -5,6 +5,9 @@
 
 namespace pitt {
 
+constexpr int REF_TPB = 256;     // plane refinement: fixed reduction shape (the partial sums of a problem take REF_BLOCKS x 10 doubles)
+constexpr int REF_BLOCKS = 296;
+
 struct SacDeviceResult {
   pitt_sac_info info;
   float coeffs[8];
@@ -55,6 +58,11 @@ struct SacAsync {
   int H;         // hypotheses scored
 };
 int sac_segment_async(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& p, int* h_stage, SacAsync* out, bool* issued);
+// The same for a batch of problems that share the model and its parameters (the clusters of a support): every launch serves all
+// of them (problem = a grid dimension, pointers and sizes from d_desc). h_desc: the host copy of the descriptors (n, H filled in).
+// Every problem must have at most 4096 points and the PCL adaptive stop.
+int sac_fit_batch_async(pitt_ctx* ctx, const pitt_sac_params& p, const FitDesc* h_desc, const FitDesc* d_desc, int nprob, bool speculative_plane);
+int lm_refine_batch(pitt_ctx* ctx, int model, const FitDesc* d_desc, int nprob, int m_cap);
 int fp32_peak(pitt_ctx* ctx, int kind, double* tflops);
 
 extern int g_force_generic_plane;
@@ -63,6 +71,7 @@ bool plane_job_takes_tensor_path(int n, int H);
 extern int g_score_mode;
 extern int g_select_no_fuse;
 extern int g_frame_legacy;
+extern int g_frame_no_batch;
 extern int g_lm_cluster_min;
 extern unsigned long long g_plane_filter_stats[2];
 extern int g_plane_filter_collect_stats;

@@ -37,6 +37,26 @@ struct Limits {
   float ax, ay, az;
 };
 
+// One problem of a batched fit (the primitive fits of a frame: problem = cluster, one batch per model). The kernels of sac.cu /
+// lm.cu / services.cu take a nullable descriptor array; with it, block z (or y, or x: the first free grid dimension) works on
+// problem blockIdx.{z,y,x} and reads its pointers and sizes here instead of from the kernel arguments.
+struct FitDesc {
+  const float4* xyz;
+  const float4* nrm;
+  const int* samples;  // [H][S]
+  HypRec* recs;        // [H]; recs[0] is reused as the winner's record after the scan
+  float* coeffs8;      // [H][8]
+  unsigned char* flags;  // [H]
+  int* counts;         // [H]
+  int* ints;           // 16 ints, see sac_segment_async
+  float* flt;          // model[8], refined[8], axis extent[16]
+  int* inl;            // [n]
+  double* partial;     // plane refinement partial sums
+  float4* proj;        // axis extent: projections
+  void* bb;            // axis extent: per-block best pairs
+  int n, H;
+};
+
 struct ScoreParams {
   double thr;    // distance threshold (double, as PCL compares)
   float thr_up;  // smallest float >= thr:  (double)f < thr  <=>  f < thr_up

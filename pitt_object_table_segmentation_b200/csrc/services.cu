@@ -320,7 +320,11 @@ __device__ __forceinline__ void axis_frame_dev(const float* co, AxisFrame& f, fl
 }
 __device__ __forceinline__ bool axis_gate(const int* ints) { return ints[0] >= 0 && ints[3] > 0; }
 __global__ void axis_project_dev_kernel(const float4* __restrict__ pts, int n, const float* __restrict__ co, const int* __restrict__ ints,
-                                        float4* __restrict__ proj) {
+                                        float4* __restrict__ proj, const FitDesc* __restrict__ D = nullptr) {
+  if (D) {  // batched: problem blockIdx.y
+    const FitDesc d = D[blockIdx.y];
+    pts = d.xyz; n = d.n; co = d.flt + 8; ints = d.ints; proj = d.proj;
+  }
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || !axis_gate(ints)) return;
   AxisFrame f;
@@ -332,7 +336,12 @@ __global__ void axis_project_dev_kernel(const float4* __restrict__ pts, int n, c
   proj[i] = make_float4(f.a1x + G * f.dx, f.a1y + G * f.dy, f.a1z + G * f.dz, 0.0f);
 }
 __global__ void __launch_bounds__(AP_TPB)
-axis_pairs_dev_kernel(const float4* __restrict__ proj, int n, const int* __restrict__ ints, PairBest* __restrict__ block_best) {
+axis_pairs_dev_kernel(const float4* __restrict__ proj, int n, const int* __restrict__ ints, PairBest* __restrict__ block_best,
+                      const FitDesc* __restrict__ D = nullptr) {
+  if (D) {  // batched: problem blockIdx.z
+    const FitDesc d = D[blockIdx.z];
+    proj = d.proj; n = d.n; ints = d.ints; block_best = reinterpret_cast<PairBest*>(d.bb);
+  }
   if (!axis_gate(ints)) return;
   __shared__ float4 s_j[AP_TPB];
   __shared__ PairBest s_red[AP_TPB / 32];
@@ -375,8 +384,12 @@ axis_pairs_dev_kernel(const float4* __restrict__ proj, int n, const int* __restr
 // out: [0] height, [1] idx1, [2] idx2 (int bits), [3..5] p1, [6..8] p2, [9..11] normalised axis direction
 __global__ void __launch_bounds__(1024) axis_pairs_final_dev_kernel(const PairBest* __restrict__ bb, int nb, const float4* __restrict__ proj,
                                                                     const float* __restrict__ co, const int* __restrict__ ints,
-                                                                    float* __restrict__ out) {
+                                                                    float* __restrict__ out, const FitDesc* __restrict__ D = nullptr) {
   __shared__ PairBest s_red[32];
+  if (D) {  // batched: problem blockIdx.x
+    const FitDesc d = D[blockIdx.x];
+    bb = reinterpret_cast<const PairBest*>(d.bb); proj = d.proj; co = d.flt + 8; ints = d.ints; out = d.flt + 16;
+  }
   if (!axis_gate(ints)) {
     if (threadIdx.x == 0) { out[0] = -1.0f; out[1] = __int_as_float(-1); out[2] = __int_as_float(-1); }
     return;
@@ -1051,6 +1064,7 @@ static void workers_run(pitt_workers* W, std::vector<std::function<void(pitt_ctx
 namespace pitt {
 
 int g_frame_legacy = 0;  // test hook (pitt_debug_frame_mode): 1 = the round-1 frame path (one synchronous seg.segment() per fit)
+int g_frame_no_batch = 0;  // test hook (pitt_debug_frame_mode 2): asynchronous chains per fit instead of per model batch
 
 constexpr int FIT_WORDS = 48;  // result block of one fit: 16 ints (sac_segment_async) + model[8] + refined[8] + axis extent[16]
 constexpr int FIT_STREAMS = 4;
@@ -1064,6 +1078,75 @@ static int stage_reserve(pitt_ctx* ctx, size_t bytes) {
   const size_t want = bytes + bytes / 2 + 4096;
   PITT_CUDA(ctx, cudaMallocHost(&ctx->h_stage, want));
   ctx->h_stage_bytes = want;
+  return PITT_OK;
+}
+
+// one fit's result block (see sac_segment_async) -> the service response fields the frame needs; a block whose scan raised a flag
+// is settled by the synchronous path
+static int decode_fit(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_sac_params& p, bool issued, const int* I, PrimitiveHost* Pp,
+                      int* inl_out) {
+  PrimitiveHost& P = *Pp;
+  const float* F = reinterpret_cast<const float*>(I + 16);
+  const float* A = F + 16;
+    if (issued && I[8] != 0) {
+      // the device-side scan could not decide exactly like the host would: the synchronous path settles it
+      PITT_TRY(primitive_service_impl(ctx, cloud, p, &P));
+      PITT_TRY(count_after_zero_drop(ctx, P.sac, inl_out));
+      return PITT_OK;
+    }
+    memset(&P.sac.info, 0, sizeof(P.sac.info));
+    P.sac.info.best_hypothesis = -1;
+    P.sac.d_inliers = nullptr;
+    P.sac.n_inliers = 0;
+    P.sac.n_coeffs = 0;
+    for (int i = 0; i < 8; ++i) P.sac.coeffs[i] = 0.0f;
+    const bool found = issued && I[0] >= 0;
+    const int NC = (p.model == PITT_MODEL_PLANE || p.model == PITT_MODEL_SPHERE) ? 4 : 7;
+    if (issued) {
+      P.sac.info.iterations = I[6];
+      P.sac.info.skipped = I[7];
+    }
+    if (found) {
+      P.sac.info.best_hypothesis = I[0];
+      P.sac.info.best_count = I[1];
+      P.sac.info.n_inliers_model = I[2];
+      P.sac.info.lm_info = I[4];
+      P.sac.info.lm_nfev = I[5];
+      for (int i = 0; i < NC; ++i) { P.sac.info.model_coeffs[i] = F[i]; P.sac.coeffs[i] = F[8 + i]; }
+      P.sac.n_coeffs = NC;
+      P.sac.n_inliers = I[3];
+    }
+    const SacDeviceResult& r = P.sac;
+    P.n_coefficients = r.n_coeffs;
+    for (int i = 0; i < 8; ++i) P.coefficients[i] = i < r.n_coeffs ? r.coeffs[i] : 0.0f;
+    P.centroid[0] = P.centroid[1] = P.centroid[2] = 0.0f;
+    P.centroid_valid = 0;
+    if (p.model == PITT_MODEL_SPHERE) {
+      if (r.n_coeffs > 0) {
+        for (int a = 0; a < 3; ++a) P.centroid[a] = r.coeffs[a];
+        P.centroid_valid = 1;
+      }
+    } else if (p.model == PITT_MODEL_CYLINDER || p.model == PITT_MODEL_CONE) {
+      float height = -1.0f;
+      if (r.n_inliers > 0) {
+        height = A[0];
+        int idx1 = -1;
+        memcpy(&idx1, &A[1], 4);
+        if (p.model == PITT_MODEL_CYLINDER) {
+          if (idx1 >= 0) {
+            for (int a = 0; a < 3; ++a) P.centroid[a] = (A[3 + a] + A[6 + a]) / 2;
+            P.centroid_valid = 1;
+          }
+        } else {
+          for (int a = 0; a < 3; ++a) P.centroid[a] = r.coeffs[a] + 3.0f / 4.0f * height * A[9 + a];
+          P.centroid_valid = 1;
+        }
+      }
+      P.coefficients[r.n_coeffs] = height;  // coefficientVector.push_back(height)
+      P.n_coefficients = r.n_coeffs + 1;
+    }
+    // PCManager::inlierToVectorMsg drops the index VALUE 0 (pc_manager.cpp:108): the ascending list starts with it or not at all
+    *inl_out = r.n_inliers - ((r.n_inliers > 0 && I[9] == 0) ? 1 : 0);
   return PITT_OK;
 }
 
@@ -1127,73 +1210,135 @@ static int frame_fits_async(pitt_ctx* ctx, std::vector<pitt_cloud>& cc, const pi
   }
   PITT_CUDA(ctx, cudaMemcpyAsync(h_stage, d_res, (size_t)nfits * FIT_WORDS * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   PITT_CUDA(ctx, pitt::stream_sync(ctx));
-  for (int slot = 0; slot < nfits; ++slot) {
-    const int c = slot / 4, m = slot % 4;
+  for (int slot = 0; slot < nfits; ++slot)
+    PITT_TRY(decode_fit(ctx, &cc[slot / 4], *sp[slot % 4], issued[slot] != 0, h_stage + (size_t)slot * FIT_WORDS, &ph[slot], &inl[slot]));
+  return PITT_OK;
+}
+
+// The same fits with every launch serving ALL clusters of the support (problem = a grid dimension, pointers and sizes from a
+// descriptor array on the device): four model chains of about ten launches each instead of about fifteen launches per fit.
+// Requires the reference's own configuration (PCL sample stream, adaptive stop, refinement on) and clusters of at most 4096
+// points; anything else takes frame_fits_async.
+static bool fits_can_batch(const std::vector<pitt_cloud>& cc, const pitt_sac_params* const sp[4]) {
+  for (const auto& c : cc)
+    if (c.n > 4096 || c.n < 1) return false;
+  for (int m = 0; m < 4; ++m) {
     const pitt_sac_params& p = *sp[m];
-    const int* I = h_stage + (size_t)slot * FIT_WORDS;
-    const float* F = reinterpret_cast<const float*>(I + 16);
-    const float* A = F + 16;
-    PrimitiveHost& P = ph[slot];
-    if (issued[slot] && I[8] != 0) {
-      // the device-side scan could not decide exactly like the host would: the synchronous path settles it
-      PITT_TRY(primitive_service_impl(ctx, &cc[c], p, &P));
-      PITT_TRY(count_after_zero_drop(ctx, P.sac, &inl[slot]));
-      continue;
-    }
-    memset(&P.sac.info, 0, sizeof(P.sac.info));
-    P.sac.info.best_hypothesis = -1;
-    P.sac.d_inliers = nullptr;
-    P.sac.n_inliers = 0;
-    P.sac.n_coeffs = 0;
-    for (int i = 0; i < 8; ++i) P.sac.coeffs[i] = 0.0f;
-    const bool found = issued[slot] && I[0] >= 0;
-    const int NC = (p.model == PITT_MODEL_PLANE || p.model == PITT_MODEL_SPHERE) ? 4 : 7;
-    if (issued[slot]) {
-      P.sac.info.iterations = I[6];
-      P.sac.info.skipped = I[7];
-    }
-    if (found) {
-      P.sac.info.best_hypothesis = I[0];
-      P.sac.info.best_count = I[1];
-      P.sac.info.n_inliers_model = I[2];
-      P.sac.info.lm_info = I[4];
-      P.sac.info.lm_nfev = I[5];
-      for (int i = 0; i < NC; ++i) { P.sac.info.model_coeffs[i] = F[i]; P.sac.coeffs[i] = F[8 + i]; }
-      P.sac.n_coeffs = NC;
-      P.sac.n_inliers = I[3];
-    }
-    const SacDeviceResult& r = P.sac;
-    P.n_coefficients = r.n_coeffs;
-    for (int i = 0; i < 8; ++i) P.coefficients[i] = i < r.n_coeffs ? r.coeffs[i] : 0.0f;
-    P.centroid[0] = P.centroid[1] = P.centroid[2] = 0.0f;
-    P.centroid_valid = 0;
-    if (p.model == PITT_MODEL_SPHERE) {
-      if (r.n_coeffs > 0) {
-        for (int a = 0; a < 3; ++a) P.centroid[a] = r.coeffs[a];
-        P.centroid_valid = 1;
-      }
-    } else if (p.model == PITT_MODEL_CYLINDER || p.model == PITT_MODEL_CONE) {
-      float height = -1.0f;
-      if (r.n_inliers > 0) {
-        height = A[0];
-        int idx1 = -1;
-        memcpy(&idx1, &A[1], 4);
-        if (p.model == PITT_MODEL_CYLINDER) {
-          if (idx1 >= 0) {
-            for (int a = 0; a < 3; ++a) P.centroid[a] = (A[3 + a] + A[6 + a]) / 2;
-            P.centroid_valid = 1;
-          }
-        } else {
-          for (int a = 0; a < 3; ++a) P.centroid[a] = r.coeffs[a] + 3.0f / 4.0f * height * A[9 + a];
-          P.centroid_valid = 1;
+    if (p.sampler != PITT_SAMPLER_PCL_MT19937 || p.stop != PITT_STOP_PCL_ADAPTIVE || !p.optimize || p.max_iterations < 1 ||
+        p.max_iterations > 8000)
+      return false;
+  }
+  return sp[0]->model == PITT_MODEL_SPHERE && sp[1]->model == PITT_MODEL_CYLINDER && sp[2]->model == PITT_MODEL_CONE &&
+         sp[3]->model == PITT_MODEL_PLANE;
+}
+static int frame_fits_batched(pitt_ctx* ctx, std::vector<pitt_cloud>& cc, const pitt_sac_params* const sp[4], std::vector<PrimitiveHost>& ph,
+                              std::vector<int>& inl) {
+  const int nc = (int)cc.size(), nfits = nc * 4;
+  if (nfits == 0) return PITT_OK;
+  const int Sm[4] = {4, 2, 3, 3};  // sample sizes of sphere, cylinder, cone, plane
+  int n_max = 1;
+  for (const auto& c : cc) n_max = std::max(n_max, c.n);
+  // pinned staging: result blocks | descriptors (grouped by model) | sample tables
+  const size_t res_words = (size_t)nfits * FIT_WORDS;
+  const size_t desc_words = ((size_t)nfits * sizeof(FitDesc) + 3) / 4;
+  size_t sample_words = 0;
+  for (int m = 0; m < 4; ++m) sample_words += (size_t)nc * ((size_t)(sp[m]->max_iterations + 1) * Sm[m]);
+  PITT_TRY(stage_reserve(ctx, (res_words + desc_words + sample_words + 64) * 4));
+  int* h_stage = reinterpret_cast<int*>(ctx->h_stage);
+  FitDesc* h_desc = reinterpret_cast<FitDesc*>(h_stage + ((res_words + 3) & ~(size_t)3));
+  int* h_samples = reinterpret_cast<int*>(h_desc + nfits);
+  int* d_res = nullptr;
+  FitDesc* d_desc = nullptr;
+  int* d_samples = nullptr;
+  int* d_counts_all = nullptr;
+  PITT_TRY(arena_alloc(ctx, res_words, &d_res));
+  PITT_TRY(arena_alloc(ctx, (size_t)nfits, &d_desc));
+  PITT_TRY(arena_alloc(ctx, sample_words + 4, &d_samples));
+  size_t count_words = 0;
+  for (int m = 0; m < 4; ++m) count_words += (size_t)nc * (sp[m]->max_iterations + 1);
+  PITT_TRY(arena_alloc(ctx, count_words + 4, &d_counts_all));
+  const int nt = cdiv(n_max, AP_TPB);
+  std::vector<char> issued((size_t)nfits, 0);
+  size_t soff = 0, coff = 0;
+  for (int m = 0; m < 4; ++m)
+    for (int c = 0; c < nc; ++c) {
+      const int slot = c * 4 + m;           // result / response order (cluster major)
+      FitDesc& d = h_desc[m * nc + c];      // launch order (model major)
+      memset(&d, 0, sizeof(d));
+      const int n = cc[c].n, S = Sm[m], Hcap = sp[m]->max_iterations + 1;
+      d.xyz = cc[c].d_xyz;
+      d.nrm = cc[c].d_nrm;
+      d.n = n;
+      d.ints = d_res + (size_t)slot * FIT_WORDS;
+      d.flt = reinterpret_cast<float*>(d.ints + 16);
+      d.samples = d_samples + soff;
+      d.counts = d_counts_all + coff;
+      int have = 0;
+      if (n >= S) {
+        PclSampleStream stream(n, sp[m]->model, nullptr);  // plane: speculative draws, the scan flags a collinear triple
+        for (int h = 0; h < Hcap; ++h) {
+          if (!stream.next(h_samples + soff + (size_t)h * S)) break;
+          ++have;
         }
       }
-      P.coefficients[r.n_coeffs] = height;  // coefficientVector.push_back(height)
-      P.n_coefficients = r.n_coeffs + 1;
+      d.H = have;
+      issued[slot] = have > 0 ? 1 : 0;
+      soff += (size_t)Hcap * S;
+      coff += (size_t)Hcap;
+      PITT_TRY(arena_alloc(ctx, (size_t)Hcap, &d.recs));
+      PITT_TRY(arena_alloc(ctx, (size_t)Hcap * 8, &d.coeffs8));
+      PITT_TRY(arena_alloc(ctx, (size_t)Hcap, &d.flags));
+      PITT_TRY(arena_alloc(ctx, (size_t)n, &d.inl));
+      if (sp[m]->model == PITT_MODEL_PLANE) PITT_TRY(arena_alloc(ctx, (size_t)REF_BLOCKS * 10, &d.partial));
+      if (sp[m]->model == PITT_MODEL_CYLINDER || sp[m]->model == PITT_MODEL_CONE) {
+        PairBest* bb = nullptr;
+        PITT_TRY(arena_alloc(ctx, (size_t)n, &d.proj));
+        PITT_TRY(arena_alloc(ctx, (size_t)nt * nt, &bb));
+        d.bb = bb;
+      }
     }
-    // PCManager::inlierToVectorMsg drops the index VALUE 0 (pc_manager.cpp:108): the ascending list starts with it or not at all
-    inl[slot] = r.n_inliers - ((r.n_inliers > 0 && I[9] == 0) ? 1 : 0);
+  PITT_CUDA(ctx, cudaMemsetAsync(d_res, 0, res_words * sizeof(int), ctx->stream));
+  PITT_CUDA(ctx, cudaMemsetAsync(d_counts_all, 0, count_words * sizeof(int), ctx->stream));
+  PITT_CUDA(ctx, cudaMemcpyAsync(d_desc, h_desc, (size_t)nfits * sizeof(FitDesc), cudaMemcpyHostToDevice, ctx->stream));
+  PITT_CUDA(ctx, cudaMemcpyAsync(d_samples, h_samples, sample_words * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  if (!ctx->fit_streams[0]) {
+    for (int i = 0; i < FIT_STREAMS; ++i) {
+      PITT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->fit_streams[i], cudaStreamNonBlocking));
+      PITT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fit_join[i], cudaEventDisableTiming));
+    }
+    PITT_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fit_fork, cudaEventDisableTiming));
   }
+  PITT_CUDA(ctx, cudaEventRecord(ctx->ev_fit_fork, ctx->stream));
+  for (int i = 0; i < FIT_STREAMS; ++i) PITT_CUDA(ctx, cudaStreamWaitEvent(ctx->fit_streams[i], ctx->ev_fit_fork, 0));
+  cudaStream_t main_stream = ctx->stream;
+  int status = PITT_OK;
+  const int order[4] = {1, 2, 0, 3};  // longest chains first (cylinder, cone, sphere, plane)
+  for (int oi = 0; oi < 4 && status == PITT_OK; ++oi) {
+    const int m = order[oi];
+    ctx->stream = ctx->fit_streams[oi % FIT_STREAMS];
+    status = sac_fit_batch_async(ctx, *sp[m], h_desc + m * nc, d_desc + m * nc, nc, sp[m]->model == PITT_MODEL_PLANE);
+    if (status == PITT_OK && (sp[m]->model == PITT_MODEL_CYLINDER || sp[m]->model == PITT_MODEL_CONE)) {
+      const FitDesc* dd = d_desc + m * nc;
+      axis_project_dev_kernel<<<dim3(cdiv(n_max, 256), nc), 256, 0, ctx->stream>>>(nullptr, 0, nullptr, nullptr, nullptr, dd);
+      axis_pairs_dev_kernel<<<dim3(nt, nt, nc), AP_TPB, 0, ctx->stream>>>(nullptr, 0, nullptr, nullptr, dd);
+      axis_pairs_final_dev_kernel<<<nc, 1024, 0, ctx->stream>>>(nullptr, nt * nt, nullptr, nullptr, nullptr, nullptr, dd);
+      ctx->launches += 3;
+      if (cudaGetLastError() != cudaSuccess) status = fail(ctx, PITT_ERR_CUDA, "axis extent kernels (batch)");
+    }
+  }
+  ctx->stream = main_stream;
+  for (int i = 0; i < FIT_STREAMS; ++i) {
+    cudaEventRecord(ctx->ev_fit_join[i], ctx->fit_streams[i]);
+    cudaStreamWaitEvent(main_stream, ctx->ev_fit_join[i], 0);
+  }
+  if (status != PITT_OK) {
+    pitt::stream_sync(ctx);
+    return status;
+  }
+  PITT_CUDA(ctx, cudaMemcpyAsync(h_stage, d_res, res_words * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PITT_CUDA(ctx, pitt::stream_sync(ctx));
+  for (int slot = 0; slot < nfits; ++slot)
+    PITT_TRY(decode_fit(ctx, &cc[slot / 4], *sp[slot % 4], issued[slot] != 0, h_stage + (size_t)slot * FIT_WORDS, &ph[slot], &inl[slot]));
   return PITT_OK;
 }
 
@@ -1387,7 +1532,8 @@ int pitt_segment_frame(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_frame_
       std::vector<int> inl((size_t)nc * 4, 0), st((size_t)nc * 4, PITT_OK);
       pitt_workers* W = g_frame_legacy ? workers_get(ctx) : nullptr;
       if (!g_frame_legacy) {
-        const int s1 = frame_fits_async(ctx, cc, sp, ph, inl);
+        const int s1 = (fits_can_batch(cc, sp) && !g_frame_no_batch) ? frame_fits_batched(ctx, cc, sp, ph, inl)
+                                                                   : frame_fits_async(ctx, cc, sp, ph, inl);
         if (s1 != PITT_OK) {
           for (auto& v : cc) { v.d_xyz = nullptr; v.d_nrm = nullptr; }
           return s1;

@@ -212,19 +212,22 @@ def test_segment_frame_is_independent_of_worker_count(oracle, workers):
             assert _eq_f(g["est_centroid"], wv["est_centroid"])
 
 
-def test_segment_frame_async_fit_chains_equal_the_synchronous_path(ctx, oracle):
-    """the primitive fits of a frame run as asynchronous chains (device-side PCL stop rule, one result copy); the round-1 path
-    with one synchronous seg.segment() per fit must give the same TrackedShapes, and both equal the oracle's"""
-    xyz = scenes.tabletop_frame(seed=21, width=320, height=240, random_poses=True)
+@pytest.mark.parametrize("seed,w,h", [(21, 320, 240), (22, 400, 300)])
+def test_segment_frame_fit_paths_agree(ctx, oracle, seed, w, h):
+    """the primitive fits of a frame run batched per model (every launch serves all clusters, device-side PCL stop rule, one
+    result copy); one asynchronous chain per fit (mode 2) and the round-1 path with one synchronous seg.segment() per fit
+    (mode 1) must give the same TrackedShapes, and all equal the oracle's"""
+    xyz = scenes.tabletop_frame(seed=seed, width=w, height=h, random_poses=True)
     cloud = ctx.stage(xyz)
-    got = ctx.segment_frame(cloud)
-    ctx.lib.pitt_debug_frame_mode(1)
-    try:
-        legacy = ctx.segment_frame(cloud)
-    finally:
-        ctx.lib.pitt_debug_frame_mode(0)
+    results = [ctx.segment_frame(cloud)]
+    for mode in (1, 2):
+        ctx.lib.pitt_debug_frame_mode(mode)
+        try:
+            results.append(ctx.segment_frame(cloud))
+        finally:
+            ctx.lib.pitt_debug_frame_mode(0)
     want = oracle.segment_frame(xyz, oracle.default_frame_params())
-    for res in (got, legacy):
+    for res in results:
         assert (res["n_supports"], res["n_clusters"]) == (want["n_supports"], want["n_clusters"])
         assert len(res["shapes"]) == len(want["shapes"]) == 3
         for g, wv in zip(res["shapes"], want["shapes"]):

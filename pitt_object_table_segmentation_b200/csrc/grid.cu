@@ -168,6 +168,87 @@ __global__ void __launch_bounds__(SCAN_TPB) scan_add_kernel(typename Op::T* __re
     if (base + j < n) data[base + j] = Op::apply(off, data[base + j]);
 }
 
+// ---- the same scan in ONE launch for consumers that can add the chunk offset themselves: every CTA scans its chunk of
+// SCAN_CHUNK elements in place (exclusive, relative to the chunk) and publishes the chunk total; the last CTA to finish (atomic
+// ticket) turns the totals into exclusive chunk offsets. Element i of the full scan = Op(chunk_off[i / SCAN_CHUNK], data[i]).
+template <typename Op>
+__global__ void __launch_bounds__(SCAN_TPB) scan_chunks_kernel(typename Op::T* __restrict__ data, int n, typename Op::T* __restrict__ chunk_off,
+                                                               unsigned* __restrict__ ticket, typename Op::T* __restrict__ total) {
+  typedef typename Op::T T;
+  __shared__ T s_w[SCAN_TPB / 32];
+  __shared__ bool s_last;
+  const int base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_IPT;
+  T v[SCAN_IPT], sum = Op::identity();
+#pragma unroll
+  for (int j = 0; j < SCAN_IPT; ++j) {
+    v[j] = (base + j < n) ? data[base + j] : Op::identity();
+    sum = Op::apply(sum, v[j]);
+  }
+  T incl = warp_incl_scan<Op>(sum);
+  if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  T run = Op::identity();
+  for (int w = 0; w < (threadIdx.x >> 5); ++w) run = Op::apply(run, s_w[w]);
+  T lane_excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  if ((threadIdx.x & 31) != 0) run = Op::apply(run, lane_excl);
+#pragma unroll
+  for (int j = 0; j < SCAN_IPT; ++j) {
+    if (base + j < n) data[base + j] = run;
+    run = Op::apply(run, v[j]);
+  }
+  if (threadIdx.x == SCAN_TPB - 1) {
+    chunk_off[blockIdx.x] = run;  // chunk total for now
+    __threadfence();
+    s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // the last CTA: exclusive scan of the gridDim.x chunk totals (serial over strips of SCAN_TPB)
+  __shared__ T s_carry;
+  if (threadIdx.x == 0) s_carry = Op::identity();
+  __syncthreads();
+  const int nb = gridDim.x;
+  for (int b0 = 0; b0 < nb; b0 += SCAN_TPB) {
+    const int i = b0 + threadIdx.x;
+    T x = (i < nb) ? __ldcg(chunk_off + i) : Op::identity();
+    T in2 = warp_incl_scan<Op>(x);
+    if ((threadIdx.x & 31) == 31) s_w[threadIdx.x >> 5] = in2;
+    __syncthreads();
+    T excl = s_carry;
+    for (int w = 0; w < (threadIdx.x >> 5); ++w) excl = Op::apply(excl, s_w[w]);
+    T le = __shfl_up_sync(0xffffffffu, in2, 1);
+    if ((threadIdx.x & 31) != 0) excl = Op::apply(excl, le);
+    if (i < nb) chunk_off[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == SCAN_TPB - 1) s_carry = Op::apply(excl, x);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (total) *total = s_carry;
+    *ticket = 0u;  // ready for the next scan that uses this ticket
+  }
+}
+template <typename Op>
+static int device_scan_chunks_impl(pitt_ctx* ctx, typename Op::T* d_data, int n, typename Op::T** d_chunk_off, unsigned* d_ticket,
+                                   typename Op::T* d_total) {
+  typedef typename Op::T T;
+  const int nb = std::max(1, cdiv(n, SCAN_CHUNK));
+  T* d_off = nullptr;
+  PITT_TRY(arena_alloc(ctx, (size_t)nb + 1, &d_off));
+  *d_chunk_off = d_off;
+  scan_chunks_kernel<Op><<<nb, SCAN_TPB, 0, ctx->stream>>>(d_data, n, d_off, d_ticket, d_total);
+  ctx->launches++;
+  PITT_CUDA(ctx, cudaGetLastError());
+  return PITT_OK;
+}
+int device_scan_chunks(pitt_ctx* ctx, int* d_data, int n, int** d_chunk_off, unsigned* d_ticket, int* d_total) {
+  return device_scan_chunks_impl<OpSumI>(ctx, d_data, n, d_chunk_off, d_ticket, d_total);
+}
+int device_max_scan_chunks(pitt_ctx* ctx, float* d_data, int n, float** d_chunk_off, unsigned* d_ticket) {
+  return device_scan_chunks_impl<OpMaxF>(ctx, d_data, n, d_chunk_off, d_ticket, nullptr);
+}
+
 template <typename Op>
 static int device_scan_impl(pitt_ctx* ctx, typename Op::T* d_data, int n, typename Op::T* d_total) {
   typedef typename Op::T T;

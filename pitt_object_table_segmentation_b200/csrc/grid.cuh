@@ -40,4 +40,11 @@ int device_exclusive_scan(pitt_ctx* ctx, int* d_data, int n, int* d_total);
 // exclusive prefix maximum of n floats in place (element 0 becomes -inf)
 int device_exclusive_max_scan(pitt_ctx* ctx, float* d_data, int n);
 
+// One-launch variants: the data is scanned in place per chunk of SCAN_CHUNK elements (exclusive, chunk relative) and *d_chunk_off
+// (arena) receives the exclusive chunk offsets; element i of the full scan is chunk_off[i >> SCAN_CHUNK_LOG2] (+ or max) data[i].
+// d_ticket: a zero-initialised device word (left at zero again).
+constexpr int SCAN_CHUNK_LOG2 = 11;
+int device_scan_chunks(pitt_ctx* ctx, int* d_data, int n, int** d_chunk_off, unsigned* d_ticket, int* d_total);
+int device_max_scan_chunks(pitt_ctx* ctx, float* d_data, int n, float** d_chunk_off, unsigned* d_ticket);
+
 }  // namespace pitt

@@ -45,10 +45,11 @@ __global__ void invert_flags_kernel(const int* __restrict__ flag, int n, int* __
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) keep[i] = flag[i] ? 0 : 1;
 }
+// boff (nullable): pos is a chunk-relative scan, boff its chunk offsets (device_scan_chunks)
 __global__ void scatter_rest_kernel(const float4* __restrict__ src, const int* __restrict__ flag, const int* __restrict__ pos,
-                                    int n, float4* __restrict__ dst) {
+                                    int n, float4* __restrict__ dst, const int* __restrict__ boff = nullptr) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && !flag[i]) dst[pos[i]] = src[i];
+  if (i < n && !flag[i]) dst[pos[i] + (boff ? boff[i >> SCAN_CHUNK_LOG2] : 0)] = src[i];
 }
 // createNewIdxMap (supports…:139-157), pass 1: classify. cat: 0 propagate, 1 level, 2 running counter
 __global__ void idxmap_classify_kernel(const int* __restrict__ prev, int n0, const int* __restrict__ flag, int n_flag,
@@ -135,11 +136,12 @@ __global__ void on_plane_flag_kernel(const float4* __restrict__ orig, const int*
   keep[i] = k ? 1 : 0;
 }
 __global__ void compact_points_kernel(const float4* __restrict__ src, const int* __restrict__ keep, const int* __restrict__ pos,
-                                      int n, float4* __restrict__ dst, int* __restrict__ dst_idx) {
+                                      int n, float4* __restrict__ dst, int* __restrict__ dst_idx, const int* __restrict__ boff = nullptr) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n && keep[i]) {
-    dst[pos[i]] = src[i];
-    if (dst_idx) dst_idx[pos[i]] = i;
+    const int q = pos[i] + (boff ? boff[i >> SCAN_CHUNK_LOG2] : 0);
+    dst[q] = src[i];
+    if (dst_idx) dst_idx[q] = i;
   }
 }
 
@@ -522,27 +524,30 @@ __global__ void idxmap_classify_dev_kernel(const int* __restrict__ prev, int n0,
   is_else[p] = e;
 }
 __global__ void idxmap_write_dev_kernel(const int* __restrict__ prev, int n0, const int* __restrict__ flag, int n_flag,
-                                        const int* __restrict__ decide, const int* __restrict__ else_pos, int* __restrict__ out) {
+                                        const int* __restrict__ decide, const int* __restrict__ else_pos, const int* __restrict__ boff,
+                                        int* __restrict__ out) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n0) return;
   const int level = decide[1];
   int v = prev ? prev[p] : p;
   if (v > level && v < 0) out[p] = v;
   else if (v >= 0 && v < n_flag && flag[v]) out[p] = level;
-  else out[p] = else_pos[p];
+  else out[p] = else_pos[p] + boff[p >> SCAN_CHUNK_LOG2];
 }
 __global__ void __launch_bounds__(1024)
 bbox_quirk_dev_kernel(const float4* __restrict__ pts, const int* __restrict__ m_ptr, const int* __restrict__ decide,
-                      const float* __restrict__ pmax_x, const float* __restrict__ pmax_y, double* __restrict__ partial) {
+                      const float* __restrict__ pmax_x, const float* __restrict__ pmax_y, const float* __restrict__ boff_x,
+                      const float* __restrict__ boff_y, double* __restrict__ partial) {
   __shared__ double s[5][32];
   if (!decide[0]) return;  // not a horizontal plane: no getPointOnPlane
   const int m = *m_ptr;
   double xMax = -INFINITY, xMin = INFINITY, yMax = -INFINITY, yMin = INFINITY, zs = 0.0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
     float4 p = pts[i];
-    if (p.x > pmax_x[i]) xMax = fmax(xMax, (double)p.x);
+    const float rmx = fmaxf(pmax_x[i], boff_x[i >> SCAN_CHUNK_LOG2]), rmy = fmaxf(pmax_y[i], boff_y[i >> SCAN_CHUNK_LOG2]);  // running maxima
+    if (p.x > rmx) xMax = fmax(xMax, (double)p.x);
     else if ((double)p.x < xMin) xMin = (double)p.x;
-    if (p.y > pmax_y[i]) yMax = fmax(yMax, (double)p.y);
+    if (p.y > rmy) yMax = fmax(yMax, (double)p.y);
     else if ((double)p.y < yMin) yMin = (double)p.y;
     zs += (double)p.z;
   }
@@ -636,30 +641,39 @@ static int supports_trip_second_half(pitt_ctx* ctx, const pitt_cloud* cloud, con
   PITT_TRY(arena_alloc(ctx, (size_t)n0, &d_onflag));
   PITT_TRY(arena_alloc(ctx, (size_t)n0 + 1, &d_onkeep));
   PITT_TRY(arena_alloc(ctx, (size_t)n0, &T->d_on));
+  unsigned* d_tickets = nullptr;
+  int* boff_keep = nullptr;
+  int* boff_else = nullptr;
+  int* boff_on = nullptr;
+  float* boff_x = nullptr;
+  float* boff_y = nullptr;
+  PITT_TRY(arena_alloc(ctx, 8, &d_tickets));
+  PITT_CUDA(ctx, cudaMemsetAsync(d_tickets, 0, 8 * sizeof(unsigned), ctx->stream));
   PITT_CUDA(ctx, cudaMemsetAsync(d_flag, 0, (size_t)ni * sizeof(int), ctx->stream));
   set_flags_kernel<<<cdiv(ni, 256), 256, 0, ctx->stream>>>(d_inl, d_n_inl, d_flag);
   gather_points_dev_kernel<<<cdiv(ni, 256), 256, 0, ctx->stream>>>(d_iter, d_inl, d_n_inl, T->d_support, d_px, d_py);
   invert_flags_kernel<<<cdiv(ni, 256), 256, 0, ctx->stream>>>(d_flag, ni, d_keep);
   ctx->launches += 3;
-  PITT_TRY(device_exclusive_scan(ctx, d_keep, ni, nullptr));
-  scatter_rest_kernel<<<cdiv(ni, 256), 256, 0, ctx->stream>>>(d_iter, d_flag, d_keep, ni, T->d_rest);
+  // every prefix scan is one launch (chunk-relative scan + chunk offsets by the last CTA); the consumers add the chunk offset
+  PITT_TRY(device_scan_chunks(ctx, d_keep, ni, &boff_keep, d_tickets + 0, nullptr));
+  scatter_rest_kernel<<<cdiv(ni, 256), 256, 0, ctx->stream>>>(d_iter, d_flag, d_keep, ni, T->d_rest, boff_keep);
   support_decide_kernel<<<1, 1, 0, ctx->stream>>>(d_co, c, idxMapLayer, T->d_decide);
   idxmap_classify_dev_kernel<<<cdiv(n0, 256), 256, 0, ctx->stream>>>(d_prev_map, n0, d_flag, ni, T->d_decide, d_else);
   ctx->launches += 3;
-  PITT_TRY(device_exclusive_scan(ctx, d_else, n0, nullptr));
-  idxmap_write_dev_kernel<<<cdiv(n0, 256), 256, 0, ctx->stream>>>(d_prev_map, n0, d_flag, ni, T->d_decide, d_else, T->d_new_map);
+  PITT_TRY(device_scan_chunks(ctx, d_else, n0, &boff_else, d_tickets + 1, nullptr));
+  idxmap_write_dev_kernel<<<cdiv(n0, 256), 256, 0, ctx->stream>>>(d_prev_map, n0, d_flag, ni, T->d_decide, d_else, boff_else, T->d_new_map);
   ctx->launches++;
   // getPointOnPlane (only does anything when the plane is horizontal: the kernels check the flag themselves). The running
   // maxima are scanned over ni entries; the tail beyond the inlier count never reaches an entry that is read.
-  PITT_TRY(device_exclusive_max_scan(ctx, d_px, ni));
-  PITT_TRY(device_exclusive_max_scan(ctx, d_py, ni));
+  PITT_TRY(device_max_scan_chunks(ctx, d_px, ni, &boff_x, d_tickets + 2));
+  PITT_TRY(device_max_scan_chunks(ctx, d_py, ni, &boff_y, d_tickets + 3));
   const int bb_blocks = std::max(1, std::min(BBOX_BLOCKS, cdiv(ni, 4096)));
-  bbox_quirk_dev_kernel<<<bb_blocks, 1024, 0, ctx->stream>>>(T->d_support, d_n_inl, T->d_decide, d_px, d_py, d_part);
+  bbox_quirk_dev_kernel<<<bb_blocks, 1024, 0, ctx->stream>>>(T->d_support, d_n_inl, T->d_decide, d_px, d_py, boff_x, boff_y, d_part);
   bbox_quirk_final_dev_kernel<<<1, 32, 0, ctx->stream>>>(d_part, bb_blocks, d_n_inl, T->d_decide, c, d_bb);
   on_plane_flag_dev_kernel<<<cdiv(n0, 256), 256, 0, ctx->stream>>>(cloud->d_xyz, T->d_new_map, n0, T->d_decide, d_bb, d_onflag, d_onkeep);
   ctx->launches += 3;
-  PITT_TRY(device_exclusive_scan(ctx, d_onkeep, n0, T->d_decide + 2));
-  compact_points_kernel<<<cdiv(n0, 256), 256, 0, ctx->stream>>>(cloud->d_xyz, d_onflag, d_onkeep, n0, T->d_on, nullptr);
+  PITT_TRY(device_scan_chunks(ctx, d_onkeep, n0, &boff_on, d_tickets + 4, T->d_decide + 2));
+  compact_points_kernel<<<cdiv(n0, 256), 256, 0, ctx->stream>>>(cloud->d_xyz, d_onflag, d_onkeep, n0, T->d_on, nullptr, boff_on);
   ctx->launches++;
   PITT_CUDA(ctx, cudaGetLastError());
   return PITT_OK;

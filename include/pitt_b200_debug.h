@@ -52,6 +52,11 @@ void pitt_debug_plane_tc_nwq(int v);
 void pitt_debug_plane_tc_time_kernel(pitt_ctx* ctx, int enable);
 double pitt_debug_plane_tc_kernel_ms(pitt_ctx* ctx);
 
+/* the device's Philox-4x32-10 (the PHILOX sampler's generator): one raw block for a counter (4 words) and a key (2 words);
+ * checked against the Random123 known-answer vectors */
+int pitt_debug_philox(pitt_ctx* ctx, const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4);
+/* the minimal sample sets the PHILOX sampler draws for hypotheses 0..H-1 of batch stream_id on a cloud of n points (H x S) */
+int pitt_debug_philox_samples(pitt_ctx* ctx, int H, int S, int n, uint32_t stream_id, int32_t* out);
 /* enable = collect diagnostics in the large-cloud k-NN calls that follow (process wide); out16 (nullable) = those of the last
  * call of ctx: [0] finite points, [1] queries that took the general ring search, [2..5] fast-path attempts at level 0..3,
  * [6] candidates inside the guaranteed radius, [7] / [8] attempts with > 64 candidates below the threshold (first / later

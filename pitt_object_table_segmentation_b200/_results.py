@@ -100,4 +100,5 @@ class FrameBuffers:
         return {"n_supports": r.n_supports, "n_clusters": r.n_clusters, "shapes": shapes,
                 "support_coefficients": np.array(r.support_coefficients[: 4 * ns], np.float32).reshape(ns, 4),
                 "support_sizes": list(r.support_sizes[:ns]), "on_support_sizes": list(r.on_support_sizes[:ns]),
-                "device_ms": r.device_ms}
+                "device_ms": r.device_ms,
+                "debug_words": [int(np.float32(v).view(np.uint32)) for v in r.support_coefficients[16:24]]}

@@ -24,6 +24,17 @@ __device__ __forceinline__ int uf_find(int* parent, int x) {
   }
   return x;
 }
+// read-only find: used once the unions are complete. (Writing the root back into parent[] there would race with the path halving
+// of other threads' finds: a stale grandparent written after the root left parent[i] pointing at a non-root, the point then lost
+// its label although it had been counted - about one frame in 3000.)
+__device__ __forceinline__ int uf_find_ro(const int* parent, int x) {
+  int p = __ldcg(parent + x);
+  while (p != x) {
+    x = p;
+    p = __ldcg(parent + x);
+  }
+  return x;
+}
 __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
   for (;;) {
     a = uf_find(parent, a);
@@ -36,9 +47,9 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
   }
 }
 
-__global__ void cc_init_kernel(int* parent, int* size, int n) {
+__global__ void cc_init_kernel(int* parent, int* size, int* root, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) { parent[i] = i; size[i] = 0; }
+  if (i < n) { parent[i] = i; size[i] = 0; root[i] = i; }
 }
 // One WARP per query point: the 32 lanes stride over the candidates of the 27 surrounding cells. A dense
 // object cluster has hundreds of neighbours within the tolerance per point and only a few thousand points
@@ -79,12 +90,12 @@ __global__ void __launch_bounds__(CC_WARPS * 32) cc_union_kernel(GridDev g, floa
       }
     }
 }
-__global__ void cc_flatten_kernel(GridDev g, int* __restrict__ parent, int* __restrict__ size) {
+__global__ void cc_flatten_kernel(GridDev g, const int* __restrict__ parent, int* __restrict__ size, int* __restrict__ root) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= g.n) return;
   const int i = __float_as_int(g.sorted[t].w);
-  const int r = uf_find(parent, i);
-  parent[i] = r;
+  const int r = uf_find_ro(parent, i);
+  root[i] = r;
   atomicAdd(&size[r], 1);
 }
 __global__ void cc_roots_kernel(const int* __restrict__ parent, const int* __restrict__ size, int n, int min_size,
@@ -101,11 +112,11 @@ __global__ void cc_rank_kernel(const int2* __restrict__ ranked, int k, int* __re
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < k) rank_of[ranked[i].x] = i;
 }
-__global__ void cc_label_kernel(const int* __restrict__ parent, const int* __restrict__ size, const int* __restrict__ rank_of,
+__global__ void cc_label_kernel(const int* __restrict__ root, const int* __restrict__ size, const int* __restrict__ rank_of,
                                 int n, int* __restrict__ labels) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  int r = parent[i];
+  int r = root[i];
   labels[i] = (size[r] > 0) ? rank_of[r] : -1;  // size 0: point never entered the grid (non-finite)
 }
 __global__ void fill_i32_kernel(int* p, int n, int v) {
@@ -119,10 +130,17 @@ __global__ void fill_i32_kernel(int* p, int n, int v) {
 // union-find, and the PCL ordering (size descending, ties by smallest index), the size filter, the per-cluster ordered index
 // lists, the cluster clouds and the centroid sums are all produced by kernels. The host reads ONE block at the end.
 // ---------------------------------------------------------------------------------------------------------------------
+// Grid cells of 0.57 tol: the diagonal of a cell is below the tolerance, so ALL points of a cell are mutually connected and one
+// union with the cell's first point stands for the whole clique; a point's other neighbours lie within +-2 cells, and for each of
+// those 124 cells ONE edge is enough (the cell is a single component): the cell is skipped outright when it already shares the
+// point's root, otherwise its points are tried until one is within the tolerance. A warp serves one point, its lanes take the
+// cells. A dense object has hundreds of points within the tolerance of each point; this visits a few dozen of them. The
+// components are exactly those of the radius graph (every edge used is a radius edge, every radius edge joins two cells that
+// end up connected).
+constexpr float CC_CELL_FACTOR = 0.57f;  // cell size / tolerance: sqrt(3) * 0.57 = 0.987 < 1, 2 * 0.57 = 1.14 > 1
 __global__ void __launch_bounds__(CC_WARPS * 32)
 cc_union_mg_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, const float4* __restrict__ sorted, float r2,
                    int* __restrict__ parent) {
-  __shared__ int s_rb[CC_WARPS][32], s_pre[CC_WARPS][32];
   const MGrid g = *G;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * CC_WARPS + warp;
@@ -130,62 +148,54 @@ cc_union_mg_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, c
   const float4 q = sorted[t];
   const int qi = __float_as_int(q.w);
   const int cx = mg_coord(q.x, g.mnx, g.inv_hf, g.dx), cy = mg_coord(q.y, g.mny, g.inv_hf, g.dy), cz = mg_coord(q.z, g.mnz, g.inv_hf, g.dz);
-  // the 27 surrounding fine cells (cells are at least tol wide; h is a hair above tol so that float rounding of the cell
-  // assignment cannot put a neighbour two cells away): one range per lane, walked as one flat list
-  int jb = 0, len = 0;
-  if (lane < 27) {
-    const int x = cx + (lane % 3) - 1, y = cy + ((lane / 3) % 3) - 1, z = cz + (lane / 9) - 1;
-    if (x >= 0 && y >= 0 && z >= 0 && x < g.dx && y < g.dy && z < g.dz) {
-      const int idx = mg_index(g, x, y, z);
-      jb = start[idx];
-      len = start[idx + 1] - jb;
-    }
-  }
-  int incl = len;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int y = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += y;
-  }
-  const int mtot = __shfl_sync(0xffffffffu, incl, 31);
-  s_rb[warp][lane] = jb;
-  s_pre[warp][lane] = incl - len;
-  __syncwarp();
   int rq = uf_find(parent, qi);
-  for (int fi = lane; fi < mtot; fi += 32) {
-    int r = 0;
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1)
-      if (s_pre[warp][r + s] <= fi) r += s;
-    const float4 p = sorted[s_rb[warp][r] + (fi - s_pre[warp][r])];
-    const int pi = __float_as_int(p.w);
-    if (pi >= qi) continue;  // each edge once
-    const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
-    const float d = (ddx * ddx + ddy * ddy) + ddz * ddz;
-    if (d < r2) {
-      const int rp = uf_find(parent, pi);
-      if (rp != rq) {
-        uf_union(parent, rq, rp);
+  for (int ci = lane; ci < 125; ci += 32) {
+    const int x = cx + (ci % 5) - 2, y = cy + ((ci / 5) % 5) - 2, z = cz + (ci / 25) - 2;
+    if (x < 0 || y < 0 || z < 0 || x >= g.dx || y >= g.dy || z >= g.dz) continue;
+    const int idx = mg_index(g, x, y, z);
+    const int jb = start[idx], je = start[idx + 1];
+    if (jb == je) continue;
+    const int pf = __float_as_int(sorted[jb].w);
+    if (ci == 62) {  // the point's own cell: a clique
+      if (pf != qi) {
+        uf_union(parent, rq, uf_find(parent, pf));
         rq = uf_find(parent, qi);
+      }
+      continue;
+    }
+    rq = uf_find(parent, qi);
+    if (uf_find(parent, pf) == rq) continue;  // that cell is already in this point's component
+    for (int j = jb; j < je; ++j) {
+      const float4 p = sorted[j];
+      const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
+      const float d = (ddx * ddx + ddy * ddy) + ddz * ddz;
+      if (d < r2) {
+        uf_union(parent, rq, uf_find(parent, __float_as_int(p.w)));
+        rq = uf_find(parent, qi);
+        break;
       }
     }
   }
 }
-__global__ void cc_flatten_mg_kernel(const MGrid* __restrict__ G, const float4* __restrict__ sorted, int* __restrict__ parent,
-                                     int* __restrict__ size) {
+__global__ void cc_flatten_mg_kernel(const MGrid* __restrict__ G, const float4* __restrict__ sorted, const int* __restrict__ parent,
+                                     int* __restrict__ size, int* __restrict__ root) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= G->n_finite) return;
   const int i = __float_as_int(sorted[t].w);
-  const int r = uf_find(parent, i);
-  parent[i] = r;
+  const int r = uf_find_ro(parent, i);
+  root[i] = r;
   atomicAdd(&size[r], 1);
 }
 // head: [0] clusters kept (nc), [1] roots that passed the size filter (> CC_MAXC: overflow, the caller takes the host path),
 // [2 .. 2+CC_MAXC) sizes in PCL order, then offsets [CC_MAXC + 1]
 __global__ void __launch_bounds__(CC_MAXC)
-cc_rank_dev_kernel(const int* __restrict__ n_roots, const int2* __restrict__ roots, int* __restrict__ rank_of, int* __restrict__ head) {
+cc_rank_dev_kernel(const int* __restrict__ n_roots, const int2* __restrict__ roots, int* __restrict__ rank_of, int* __restrict__ head,
+                   const MGrid* __restrict__ G, float h_req) {
   __shared__ int s_size[CC_MAXC], s_root[CC_MAXC], s_sorted[CC_MAXC];
-  const int R = *n_roots;
+  int R = *n_roots;
+  // the cell table did not fit at the requested cell size and the cells were enlarged: the clique argument of cc_union_mg_kernel
+  // does not hold, the caller must take the host-ordered path (reported like an overflow of the cluster table)
+  if (G->hf > h_req * 1.0001f) R = CC_MAXC + 1;
   if (R > CC_MAXC) {
     if (threadIdx.x == 0) { head[0] = 0; head[1] = R; }
     return;
@@ -258,14 +268,16 @@ cc_compact_dev_kernel(const float4* __restrict__ xyz, const int* __restrict__ la
 int euclidean_clusters_dev(pitt_ctx* ctx, const float4* d_xyz, int n, double tolerance, int min_size, int max_size, ClustersOnDevice* out) {
   const float r2 = (float)(tolerance * tolerance);
   MGridBuf mg;
-  PITT_TRY(mgrid_build(ctx, d_xyz, n, (float)tolerance * 1.001f + 1e-7f, &mg));
+  PITT_TRY(mgrid_build(ctx, d_xyz, n, (float)tolerance * CC_CELL_FACTOR, &mg));
   int* d_parent = nullptr;
   int* d_size = nullptr;
   int* d_rank = nullptr;
   int* d_nroots = nullptr;
   int2* d_roots = nullptr;
+  int* d_root = nullptr;
   PITT_TRY(arena_alloc(ctx, (size_t)n, &d_parent));
   PITT_TRY(arena_alloc(ctx, (size_t)n, &d_size));
+  PITT_TRY(arena_alloc(ctx, (size_t)n, &d_root));
   PITT_TRY(arena_alloc(ctx, (size_t)n, &d_rank));
   PITT_TRY(arena_alloc(ctx, 1, &d_nroots));
   PITT_TRY(arena_alloc(ctx, (size_t)n, &d_roots));
@@ -273,15 +285,15 @@ int euclidean_clusters_dev(pitt_ctx* ctx, const float4* d_xyz, int n, double tol
   PITT_TRY(arena_alloc(ctx, (size_t)n, &out->d_idx));
   PITT_TRY(arena_alloc(ctx, (size_t)n, &out->d_points));
   PITT_TRY(arena_alloc(ctx, (size_t)CC_HEAD_INTS, &out->d_head));
-  cc_init_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_parent, d_size, n);
+  cc_init_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_parent, d_size, d_root, n);
   fill_i32_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_rank, n, -1);
   PITT_CUDA(ctx, cudaMemsetAsync(d_nroots, 0, sizeof(int), ctx->stream));
   PITT_CUDA(ctx, cudaMemsetAsync(out->d_head, 0, CC_HEAD_INTS * sizeof(int), ctx->stream));
   cc_union_mg_kernel<<<cdiv(n, CC_WARPS), CC_WARPS * 32, 0, ctx->stream>>>(mg.d_G, mg.d_start, mg.d_sorted, r2, d_parent);
-  cc_flatten_mg_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(mg.d_G, mg.d_sorted, d_parent, d_size);
+  cc_flatten_mg_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(mg.d_G, mg.d_sorted, d_parent, d_size, d_root);
   cc_roots_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_parent, d_size, n, std::max(min_size, 1), max_size, d_nroots, d_roots, n);
-  cc_rank_dev_kernel<<<1, CC_MAXC, 0, ctx->stream>>>(d_nroots, d_roots, d_rank, out->d_head);
-  cc_label_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_parent, d_size, d_rank, n, out->d_labels);
+  cc_rank_dev_kernel<<<1, CC_MAXC, 0, ctx->stream>>>(d_nroots, d_roots, d_rank, out->d_head, mg.d_G, (float)tolerance * CC_CELL_FACTOR);
+  cc_label_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_root, d_size, d_rank, n, out->d_labels);
   cc_compact_dev_kernel<<<CC_MAXC, 1024, 0, ctx->stream>>>(d_xyz, out->d_labels, n, out->d_head, out->d_idx, out->d_points);
   ctx->launches += 8;
   PITT_CUDA(ctx, cudaGetLastError());
@@ -303,12 +315,14 @@ int euclidean_clusters_impl(pitt_ctx* ctx, const float4* d_xyz, int n, double to
   int* d_nroots = nullptr;
   int2* d_roots = nullptr;
   const int cap = n;
+  int* d_root = nullptr;
+  PITT_TRY(arena_alloc(ctx, (size_t)n, &d_root));
   PITT_TRY(arena_alloc(ctx, (size_t)n, &d_parent));
   PITT_TRY(arena_alloc(ctx, (size_t)n, &d_size));
   PITT_TRY(arena_alloc(ctx, (size_t)n, &d_rank));
   PITT_TRY(arena_alloc(ctx, 1, &d_nroots));
   PITT_TRY(arena_alloc(ctx, (size_t)cap, &d_roots));
-  cc_init_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_parent, d_size, n);
+  cc_init_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_parent, d_size, d_root, n);
   fill_i32_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_rank, n, -1);
   PITT_CUDA(ctx, cudaMemsetAsync(d_nroots, 0, sizeof(int), ctx->stream));
   ctx->launches += 2;
@@ -316,7 +330,7 @@ int euclidean_clusters_impl(pitt_ctx* ctx, const float4* d_xyz, int n, double to
   std::vector<int2> roots;
   if (g.n > 0) {
     cc_union_kernel<<<cdiv(g.n, CC_WARPS), CC_WARPS * 32, 0, ctx->stream>>>(g, r2, d_parent);
-    cc_flatten_kernel<<<cdiv(g.n, 256), 256, 0, ctx->stream>>>(g, d_parent, d_size);
+    cc_flatten_kernel<<<cdiv(g.n, 256), 256, 0, ctx->stream>>>(g, d_parent, d_size, d_root);
     cc_roots_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_parent, d_size, n, std::max(min_size, 1), max_size, d_nroots, d_roots, cap);
     ctx->launches += 3;
     PITT_CUDA(ctx, cudaMemcpyAsync(&h_nroots, d_nroots, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -333,7 +347,7 @@ int euclidean_clusters_impl(pitt_ctx* ctx, const float4* d_xyz, int n, double to
       ctx->launches++;
     }
   }
-  cc_label_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_parent, d_size, d_rank, n, d_labels);
+  cc_label_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_root, d_size, d_rank, n, d_labels);
   ctx->launches++;
   PITT_CUDA(ctx, cudaGetLastError());
   if (sizes_out)

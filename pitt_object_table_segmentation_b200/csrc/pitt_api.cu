@@ -837,5 +837,26 @@ double pitt_debug_plane_tc_kernel_ms(pitt_ctx* ctx) {
   return (double)ms;
 }
 void pitt_debug_plane_tc_nwq(int v) { g_plane_tc_nwq = v; }
+/* the device's Philox-4x32-10: one raw block for a given counter (4 words) and key (2 words) */
+int pitt_debug_philox(pitt_ctx* ctx, const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4) {
+  if (!ctx || !ctr4 || !key2 || !out4) return PITT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  arena_reset(ctx);
+  uint32_t ck[6] = {ctr4[0], ctr4[1], ctr4[2], ctr4[3], key2[0], key2[1]};
+  return sac_philox_raw(ctx, ck, out4);
+}
+/* the minimal sample sets the PHILOX sampler draws for hypotheses 0..H-1 of batch `stream_id` on a cloud of n points (S indices
+ * each, written to the host array out) */
+int pitt_debug_philox_samples(pitt_ctx* ctx, int H, int S, int n, uint32_t stream_id, int32_t* out) {
+  if (!ctx || !out || H <= 0 || S < 1 || S > 4 || n < S) return PITT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  arena_reset(ctx);
+  int* d = nullptr;
+  PITT_TRY(arena_alloc(ctx, (size_t)H * S, &d));
+  PITT_TRY(sac_philox_samples(ctx, d, H, S, n, stream_id));
+  PITT_CUDA(ctx, cudaMemcpyAsync(out, d, (size_t)H * S * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PITT_CUDA(ctx, pitt::stream_sync(ctx));
+  return PITT_OK;
+}
 
 }  // extern "C"

@@ -1595,6 +1595,26 @@ __global__ void philox_samples_kernel(int* __restrict__ samples, int H, int S, i
   }
   for (int i = 0; i < S; ++i) samples[(size_t)h * S + i] = s[i];
 }
+// raw Philox-4x32-10 block (known-answer tests: the Random123 vectors, tests/test_gpu_plane.py)
+__global__ void philox_raw_kernel(const uint32_t* __restrict__ ctr_key /*4 + 2*/, uint32_t* __restrict__ out4) {
+  uint32_t c0 = ctr_key[0], c1 = ctr_key[1], c2 = ctr_key[2], c3 = ctr_key[3], k0 = ctr_key[4], k1 = ctr_key[5];
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c0, c1, c2, c3, k0, k1);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out4[0] = c0; out4[1] = c1; out4[2] = c2; out4[3] = c3;
+}
+int sac_philox_raw(pitt_ctx* ctx, const uint32_t* h_ctr_key6, uint32_t* h_out4) {
+  uint32_t* d = nullptr;
+  PITT_TRY(arena_alloc(ctx, 16, &d));
+  PITT_CUDA(ctx, cudaMemcpyAsync(d, h_ctr_key6, 6 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  philox_raw_kernel<<<1, 1, 0, ctx->stream>>>(d, d + 8);
+  ctx->launches++;
+  PITT_CUDA(ctx, cudaMemcpyAsync(h_out4, d + 8, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  PITT_CUDA(ctx, pitt::stream_sync(ctx));
+  return PITT_OK;
+}
 int sac_philox_samples(pitt_ctx* ctx, int* d_samples, int H, int S, int n, uint32_t stream_id) {
   philox_samples_kernel<<<cdiv(H, 256), 256, 0, ctx->stream>>>(d_samples, H, S, n, ctx->seed, stream_id);
   PITT_LAUNCH_CHECK(ctx, "philox_samples_kernel");

@@ -47,6 +47,7 @@ int plane_refine(pitt_ctx* ctx, const pitt_cloud* c, const float* d_model, const
 int lm_refine(pitt_ctx* ctx, const pitt_cloud* c, int model, const float* d_model, const int* d_idx, const int* d_n_idx,
               int n_idx_host, float* d_refined, int* d_lm_info);
 int sac_philox_samples(pitt_ctx* ctx, int* d_samples, int H, int S, int n, uint32_t stream_id);
+int sac_philox_raw(pitt_ctx* ctx, const uint32_t* h_ctr_key6, uint32_t* h_out4);
 int sac_finish_from_winner(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& p, const int* d_samples_all, int H_all,
                            const int* d_best, SacDeviceResult* out);
 int sac_segment_impl(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& p, SacDeviceResult* out);

@@ -802,6 +802,8 @@ struct ClustersDev {
   std::vector<float> centroid;// 3 per cluster (sum/(n+1))
   const float4* d_points = nullptr;  // cluster clouds, contiguous in `offsets` order (device)
   const int* d_head = nullptr;       // device copy of {nc, ., sizes, offsets} (device-side clustering only)
+  const int* d_labels = nullptr;     // debugging aid
+  const int* d_idx = nullptr;
 };
 static int cluster_service_host_impl(pitt_ctx* ctx, const float4* d_xyz, int n, const pitt_cluster_params& p, ClustersDev* out) {
   out->sizes.clear();
@@ -894,6 +896,11 @@ static int cluster_service_impl(pitt_ctx* ctx, const float4* d_xyz, int n, const
   if (!(n >= p.min_input_size) || n <= 0) return PITT_OK;
   const int min_sz = (int)round((double)n * p.min_rate);
   const int max_sz = (int)round((double)n * p.max_rate);
+  {
+    static int host_path = -1;  // PITT_DEBUG_CC_HOST=1: the host-ordered clustering (debugging aid)
+    if (host_path < 0) { const char* v = getenv("PITT_DEBUG_CC_HOST"); host_path = (v && v[0] == '1') ? 1 : 0; }
+    if (host_path) return cluster_service_host_impl(ctx, d_xyz, n, p, out);
+  }
   ClustersOnDevice cd;
   PITT_TRY(euclidean_clusters_dev(ctx, d_xyz, n, p.tolerance, min_sz, max_sz, &cd));
   float* d_cen = nullptr;
@@ -918,6 +925,8 @@ static int cluster_service_impl(pitt_ctx* ctx, const float4* d_xyz, int n, const
   }
   out->d_points = cd.d_points;
   out->d_head = cd.d_head;
+  out->d_labels = cd.d_labels;
+  out->d_idx = cd.d_idx;
   if (want_indices) {
     const int total = out->offsets[nc];
     out->indices.resize(total);
@@ -1486,6 +1495,24 @@ int pitt_select_primitive(int64_t plane_inl, int64_t sphere_inl, int64_t cylinde
   return select_primitive_rule(plane_inl, sphere_inl, cylinder_inl, cone_inl, prio);
 }
 
+// PITT_DEBUG_HASH=1 (development aid): FNV-1a hashes of the intermediate stages of a frame are stored, as bit patterns, in the
+// unused tail of support_coefficients (entries 16..): [16] cloud, [17] on-support cloud, [18] cluster clouds, [19] cluster normals
+static bool dbg_hash_on() {
+  static int e = -1;
+  if (e < 0) { const char* v = getenv("PITT_DEBUG_HASH"); e = (v && v[0] == '1') ? 1 : 0; }
+  return e == 1;
+}
+static unsigned dbg_hash_device(pitt_ctx* ctx, const void* d, size_t bytes) {
+  std::vector<unsigned char> h(bytes);
+  if (bytes) {
+    cudaMemcpyAsync(h.data(), d, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    pitt::stream_sync(ctx);
+  }
+  unsigned v = 2166136261u;
+  for (unsigned char b : h) { v ^= b; v *= 16777619u; }
+  return v;
+}
+
 int pitt_segment_frame(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_frame_params* fp, pitt_frame_result* res) {
   if (!ctx) return PITT_ERR_CUDA;
   if (!cloud || !fp || !res) return fail(ctx, PITT_ERR_INVALID, "pitt_segment_frame arguments");
@@ -1520,6 +1547,12 @@ int pitt_segment_frame(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_frame_
         res->on_support_sizes[s] = S.n_on;
       }
       ClustersDev cd;
+      if (dbg_hash_on() && s == 0) {
+        unsigned hv = dbg_hash_device(ctx, cloud->d_xyz, (size_t)n * 16);
+        memcpy(&res->support_coefficients[16], &hv, 4);
+        hv = dbg_hash_device(ctx, S.d_on, (size_t)S.n_on * 16);
+        memcpy(&res->support_coefficients[17], &hv, 4);
+      }
       PITT_TRY(cluster_service_impl(ctx, S.d_on, S.n_on, fp->cluster, &cd, false));
       const int nc = (int)cd.sizes.size();
       if (nc == 0) continue;
@@ -1540,6 +1573,20 @@ int pitt_segment_frame(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_frame_
         if (!all_small) PITT_TRY(estimate_normals_impl(ctx, cc[c].d_xyz, cc[c].n, fp->normals_k, fp->viewpoint, d_cn));
         cc[c].d_nrm = d_cn;
         cc[c].has_normals = true;
+      }
+      if (dbg_hash_on() && s == 0) {
+        unsigned hv = dbg_hash_device(ctx, cd.d_points, (size_t)total * 16);
+        memcpy(&res->support_coefficients[18], &hv, 4);
+        hv = dbg_hash_device(ctx, d_cn_all, (size_t)total * 16);
+        memcpy(&res->support_coefficients[19], &hv, 4);
+        if (cd.d_labels) {
+          hv = dbg_hash_device(ctx, cd.d_labels, (size_t)S.n_on * 4);
+          memcpy(&res->support_coefficients[20], &hv, 4);
+          hv = dbg_hash_device(ctx, cd.d_idx, (size_t)total * 4);
+          memcpy(&res->support_coefficients[21], &hv, 4);
+          hv = dbg_hash_device(ctx, cd.d_head, (size_t)CC_HEAD_INTS * 4);
+          memcpy(&res->support_coefficients[22], &hv, 4);
+        }
       }
       const pitt_sac_params* sp[4] = {&fp->sphere, &fp->cylinder, &fp->cone, &fp->plane};
       std::vector<PrimitiveHost> ph((size_t)nc * 4);

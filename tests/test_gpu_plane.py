@@ -371,3 +371,20 @@ def test_segment_host_single_launch_bounds_check(ctx, oracle, spoil):
     c_cpu, _, _ = oracle.sac_score(xyz, None, p, samples[:40])
     c_gpu, _, _ = ctx.sac_score(cloud, p, samples[:40])
     assert np.array_equal(c_cpu, c_gpu)
+
+
+def test_philox_device_known_answers_and_sample_sets(ctx):
+    """the PHILOX sampler's generator on the device against the Random123 known-answer vectors (Philox-4x32-10), and the sample
+    sets it draws against the Python restatement of the derivation (csrc/sac.cu::philox_samples_kernel)"""
+    import ctypes as C
+    from pitt_object_table_segmentation_b200 import philox
+    u32x4, u32x2 = C.c_uint32 * 4, C.c_uint32 * 2
+    for ctr, key, want in philox.KAT:
+        out = u32x4()
+        assert ctx.lib.pitt_debug_philox(ctx.handle, u32x4(*ctr), u32x2(*key), out) == 0
+        assert tuple(out) == want
+    for S, n, stream in ((3, 1000, 1), (4, 37, 2), (2, 5, 7)):
+        H = 500
+        got = np.zeros((H, S), np.int32)
+        assert ctx.lib.pitt_debug_philox_samples(ctx.handle, H, S, n, stream, got.ctypes.data_as(A.i32p)) == 0
+        assert np.array_equal(got, philox.sample_sets(H, S, n, seed=12345, stream_id=stream))

@@ -578,3 +578,14 @@ def test_bench_reference_arm_c2_workload():
     assert d["impl"] == "reference" and d["metric"] == "RANSAC hypothesis-point evals/s" and d["unit"] == "evals/s"
     assert d["value"] > 1e7 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_philox_restatement_matches_the_random123_known_answers():
+    """the Python restatement of Philox-4x32-10 that checks the device sampler (tests/test_gpu_plane.py) reproduces the three
+    known-answer vectors of Random123, and its sample sets are valid minimal samples"""
+    from pitt_object_table_segmentation_b200 import philox
+    for ctr, key, want in philox.KAT:
+        assert philox.philox4x32_10(ctr, key) == want
+    s = philox.sample_sets(200, 4, 37, seed=12345, stream_id=1)
+    assert s.min() >= 0 and s.max() < 37
+    assert all(len(set(row)) == 4 for row in s.tolist())

@@ -83,7 +83,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("PITT_BENCH_CLOCK_MS", "100")],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -388,7 +388,7 @@ def arm_frames(env, args, pkg):
     frames = [p.numpy() for p in pinned]
     gen_s = time.perf_counter() - t0
     fctxs = [pkg.Context(env.local_rank, seed=12345) for _ in range(n_ctx)]
-    oversubscribed = env.world * n_ctx > (os.cpu_count() or 1)  # more host threads than cores: waits sleep instead of spinning
+    oversubscribed = env.world * n_ctx > len(os.sched_getaffinity(0))  # more host threads than cores: waits sleep instead of spinning
     for c in fctxs:
         c.set_workers(args.frame_workers)
         c.set_blocking_sync(oversubscribed)
@@ -413,7 +413,9 @@ def arm_frames(env, args, pkg):
     for _ in range(args.warmup):
         step_resident()
     l0 = launches()
+    cpu0 = time.process_time()  # user + system time of every thread of this process
     ms_step, wall = env.timed_steps(step_resident, args.steps, 0)
+    cpu_s = time.process_time() - cpu0
     n_launch = launches() - l0
     clk = clocks.stop()
     clk["note"] = "sampled every 100 ms over the timed region of the headline (resident) arm"
@@ -447,7 +449,8 @@ def arm_frames(env, args, pkg):
                 "h2d_bytes_per_step": int(sum(f.nbytes for f in frames)),
                 "d2h_bytes_per_step": int(sum(C.sizeof(b.res) + r["n_clusters"] * C.sizeof(b.shapes[0]) for b, r in zip(bufs, out["res_e2e"])))},
         "parity": parity, "contexts_per_gpu": n_ctx, "workers_per_context": args.frame_workers,
-        "blocking_sync": bool(oversubscribed), "host_cores": os.cpu_count(), "frames_per_gpu_per_step": per_gpu,
+        "blocking_sync": bool(oversubscribed), "host_cores": len(os.sched_getaffinity(0)),
+        "host_cpu_ms_per_frame": 1e3 * cpu_s / float(max(1, args.steps * per_gpu)), "frames_per_gpu_per_step": per_gpu,
         "distinct_frames": per_gpu * env.world, "points_per_frame": int(frames[0].shape[0]),
         "shape_tags_of_this_rank": shapes_hist, "frame_generation_s": gen_s,
         "launches_per_frame": n_launch / float(max(1, args.steps * per_gpu)),

@@ -102,3 +102,27 @@ class FrameBuffers:
                 "support_sizes": list(r.support_sizes[:ns]), "on_support_sizes": list(r.on_support_sizes[:ns]),
                 "device_ms": r.device_ms,
                 "debug_words": [int(np.float32(v).view(np.uint32)) for v in r.support_coefficients[16:24]]}
+
+
+class FrameResults:
+    """The responses of a batched call: a read-only sequence over the caller-owned result structs the C ABI has filled. The
+    dict view of a frame (FrameBuffers.to_python) is built when the frame is first looked at, not for all frames up front."""
+
+    def __init__(self, bufs):
+        self._bufs = list(bufs)
+        self._views = [None] * len(self._bufs)
+
+    def __len__(self):
+        return len(self._bufs)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if self._views[i] is None:
+            self._views[i] = self._bufs[i].to_python()
+        return self._views[i]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))

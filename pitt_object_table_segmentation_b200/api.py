@@ -528,11 +528,9 @@ def segment_clouds_batched(contexts, clouds, params=None, shapes_cap=64, bufs=No
     st = lib.pitt_segment_clouds_batched(ctxs, len(contexts), handles, n, C.byref(params), res)
     if st != A.PITT_OK:
         raise PittError(f"pitt_segment_clouds_batched status {st}")
-    out = []
     for i, b in enumerate(bufs):
         b.res = res[i]
-        out.append(b.to_python())
-    return out
+    return R.FrameResults(bufs)
 
 
 def segment_frames_batched(contexts, frames, params=None, shapes_cap=64, prefilter=None):
@@ -554,8 +552,6 @@ def segment_frames_batched(contexts, frames, params=None, shapes_cap=64, prefilt
                                              C.byref(prefilter) if prefilter is not None else None, C.byref(params), res)
     if st != A.PITT_OK:
         raise PittError(f"pitt_segment_frames_batched status {st}")
-    out = []
     for i, b in enumerate(bufs):
         b.res = res[i]
-        out.append(b.to_python())
-    return out
+    return R.FrameResults(bufs)

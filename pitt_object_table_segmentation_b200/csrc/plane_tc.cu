@@ -591,12 +591,17 @@ plane_tc_kernel(const float4* __restrict__ xyz, int n, const HypRec* __restrict_
           if (lane == 0) {
             // flags come up in copy order: the one of the chunk's last point covers a chunk that straddles two regions
             const int* f = ready + (min(base + TC_CHUNK, n) - 1) / ready_pts;
-            int v, spins = 0;
+            // The wait is bounded by wall clock (2 s on %globaltimer), and once any warp has timed out (seen[3]) nobody waits
+            // again: the run is void, the remaining chunks only have to drain.
+            int v;
+            unsigned long long t0 = 0ull, t;
             for (;;) {
               asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-              if (v) break;
+              if (v || *reinterpret_cast<volatile unsigned*>(seen + 3)) break;
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+              if (t0 == 0ull) t0 = t;
+              else if (t - t0 > 2000000000ull) { atomicExch(seen + 3, 1u); break; }
               __nanosleep(200);
-              if (++spins > (1 << 23)) { atomicExch(seen + 3, 1u); break; }
             }
           }
           __syncwarp();

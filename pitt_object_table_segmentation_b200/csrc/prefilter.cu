@@ -6,13 +6,11 @@
 // VoxelGrid = voxel keys -> stable radix sort of (key, point index) -> segment heads -> one thread per
 // voxel accumulates its points in ascending point index (float, like PCL) -> centroids in ascending voxel
 // index (PCL's output order). The deep filter and the transform are fused into one ordered compaction.
-// The sort is cub::DeviceRadixSort (CUDA toolkit); everything else is hand written.
+// The sort is the hand-written stable LSD radix sort below (rs_*: per-tile digit histogram -> one-launch scan -> ranked scatter).
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
 #include <limits>
-
-#include <cub/device/device_radix_sort.cuh>
 
 #include "grid.cuh"
 #include "pitt_common.cuh"
@@ -31,13 +29,14 @@ struct VoxGeom {
   float inv0, inv1, inv2;
   int min0, min1, min2;
   int mul1, mul2;
+  unsigned sentinel;  // key of a non-finite point: one past the largest voxel index
 };
 __global__ void __launch_bounds__(256) voxel_key_kernel(const float4* __restrict__ xyz, int n, VoxGeom g, unsigned* __restrict__ key,
                                                         int* __restrict__ idx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float4 p = __ldg(xyz + i);
-  unsigned k = 0xffffffffu;  // non-finite points sort to the end and are cut off
+  unsigned k = g.sentinel;  // non-finite points sort to the end and are cut off
   if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
     // static_cast<int> (floor (x * inverse_leaf_size_[0]) - static_cast<float> (min_b_[0]))
     const int i0 = (int)(floorf(p.x * g.inv0) - (float)g.min0);
@@ -48,6 +47,111 @@ __global__ void __launch_bounds__(256) voxel_key_kernel(const float4* __restrict
   key[i] = k;
   idx[i] = i;
 }
+// ---------------------------------------------------------------- stable LSD radix sort of (key, value) pairs
+// A pass sorts by `bits` (<= 9) key bits: tiles of 2048 pairs, warp w of a tile owns the contiguous pairs [256 w, 256 w + 256)
+// and walks them in 8 rounds of 32, so "warp, round, lane" is ascending input position and equal digits keep their order.
+//   rs_hist_kernel     digit histogram of every tile -> hist[digit][tile]
+//   device_scan_chunks exclusive scan of hist in that (digit-major) order = where each tile's run of a digit starts
+//   rs_scatter_kernel  rank of a pair among the tile's equal digits (match_any inside the warp + running per-warp counters in
+//                      shared memory + a prefix over the 8 warps) -> output position
+constexpr int RS_TPB = 256, RS_TILE = 2048, RS_MAXB = 512;
+__global__ void __launch_bounds__(RS_TPB) rs_hist_kernel(const unsigned* __restrict__ key, int n, int shift, int bits, int ntiles,
+                                                         int* __restrict__ hist) {
+  __shared__ int cnt[RS_MAXB];
+  const int NB = 1 << bits;
+  for (int d = threadIdx.x; d < NB; d += RS_TPB) cnt[d] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * RS_TILE;
+#pragma unroll
+  for (int r = 0; r < RS_TILE / RS_TPB; ++r) {
+    const int i = base + r * RS_TPB + threadIdx.x;
+    if (i < n) atomicAdd(&cnt[(__ldg(key + i) >> shift) & (NB - 1)], 1);
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < NB; d += RS_TPB) hist[(size_t)d * ntiles + blockIdx.x] = cnt[d];
+}
+__global__ void __launch_bounds__(RS_TPB) rs_scatter_kernel(const unsigned* __restrict__ key_in, const int* __restrict__ val_in, int n,
+                                                            int shift, int bits, int ntiles, const int* __restrict__ off,
+                                                            const int* __restrict__ chunk_off, unsigned* __restrict__ key_out,
+                                                            int* __restrict__ val_out) {
+  __shared__ int cnt[8][RS_MAXB];  // running count of digit d in warp w, then the warp's start inside the tile's run of d
+  __shared__ int goff[RS_MAXB];    // start of the tile's run of digit d in the output
+  const int NB = 1 << bits;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 8 * RS_MAXB; i += RS_TPB) (&cnt[0][0])[i] = 0;
+  for (int d = threadIdx.x; d < NB; d += RS_TPB) {
+    const size_t j = (size_t)d * ntiles + blockIdx.x;
+    goff[d] = off[j] + chunk_off[j >> SCAN_CHUNK_LOG2];
+  }
+  __syncthreads();
+  const int base = blockIdx.x * RS_TILE + w * 256;
+  unsigned k[8];
+  int v[8], rank[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int i = base + r * 32 + lane;
+    const bool valid = i < n;
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    rank[r] = 0;
+    if (valid) {
+      k[r] = __ldg(key_in + i);
+      v[r] = __ldg(val_in + i);
+      const int d = (k[r] >> shift) & (NB - 1);
+      const unsigned m = __match_any_sync(act, d);
+      const int before = __popc(m & ((1u << lane) - 1u));
+      const int prior = cnt[w][d];
+      __syncwarp(act);
+      if (before == 0) cnt[w][d] = prior + __popc(m);
+      __syncwarp(act);
+      rank[r] = prior + before;
+    }
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < NB; d += RS_TPB) {
+    int run = 0;
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) {
+      const int c = cnt[ww][d];
+      cnt[ww][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int i = base + r * 32 + lane;
+    if (i < n) {
+      const int d = (k[r] >> shift) & (NB - 1);
+      const int pos = goff[d] + cnt[w][d] + rank[r];
+      key_out[pos] = k[r];
+      val_out[pos] = v[r];
+    }
+  }
+}
+// sorts by key bits [0, end_bit); the result is in (*key_a, *val_a) on return (the pointers are swapped per pass)
+static int radix_sort_pairs(pitt_ctx* ctx, unsigned** key_a, int** val_a, unsigned** key_b, int** val_b, int n, int end_bit) {
+  const int passes = (end_bit + 8) / 9;  // <= 9 bits per pass
+  const int ntiles = cdiv(n, RS_TILE);
+  int* d_hist = nullptr;
+  unsigned* d_ticket = nullptr;
+  PITT_TRY(arena_alloc(ctx, (size_t)RS_MAXB * ntiles, &d_hist));
+  PITT_TRY(arena_alloc(ctx, 1, &d_ticket));
+  PITT_CUDA(ctx, cudaMemsetAsync(d_ticket, 0, sizeof(unsigned), ctx->stream));
+  int shift = 0;
+  for (int p = 0; p < passes; ++p) {
+    const int bits = (end_bit - shift + (passes - p) - 1) / (passes - p);
+    rs_hist_kernel<<<ntiles, RS_TPB, 0, ctx->stream>>>(*key_a, n, shift, bits, ntiles, d_hist);
+    int* d_chunk_off = nullptr;
+    PITT_TRY(device_scan_chunks(ctx, d_hist, (1 << bits) * ntiles, &d_chunk_off, d_ticket, nullptr));
+    rs_scatter_kernel<<<ntiles, RS_TPB, 0, ctx->stream>>>(*key_a, *val_a, n, shift, bits, ntiles, d_hist, d_chunk_off, *key_b, *val_b);
+    ctx->launches += 2;
+    std::swap(*key_a, *key_b);
+    std::swap(*val_a, *val_b);
+    shift += bits;
+  }
+  return PITT_OK;
+}
+
 __global__ void __launch_bounds__(256) voxel_heads_kernel(const unsigned* __restrict__ key_sorted, int m, int* __restrict__ head) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
@@ -220,23 +324,16 @@ static int prefilter_impl(pitt_ctx* ctx, const float4* d_in, int n, const pitt_p
         PITT_TRY(arena_alloc(ctx, (size_t)n, &d_head));
         PITT_TRY(arena_alloc(ctx, 1, &d_total));
         PITT_TRY(arena_alloc(ctx, (size_t)n_finite, &d_vox));
+        // stable sort on the voxel key only: equal keys keep ascending point index; only the bits a key can have are sorted
+        const int64_t max_key = (int64_t)div_b[0] * div_b[1] * div_b[2];  // <= INT32_MAX (checked above)
+        g.sentinel = (unsigned)max_key;
+        int end_bit = 1;
+        while (end_bit < 32 && ((int64_t)1 << end_bit) <= max_key) ++end_bit;
         voxel_key_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_in, n, g, d_key, d_idx);
         ctx->launches++;
-        // stable LSD radix sort on the voxel key only: equal keys keep ascending point index
-        int end_bit = 32;
-        {
-          const int64_t max_key = (int64_t)div_b[0] * div_b[1] * div_b[2];
-          if (n_finite == n) {  // no 0xffffffff sentinels: only the bits a key can have
-            end_bit = 1;
-            while (end_bit < 32 && ((int64_t)1 << end_bit) < max_key) ++end_bit;
-          }
-        }
-        size_t tmp_bytes = 0;
-        PITT_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_key, d_key2, d_idx, d_idx2, n, 0, end_bit, ctx->stream));
-        unsigned char* d_tmp = nullptr;
-        PITT_TRY(arena_alloc(ctx, tmp_bytes + 16, &d_tmp));
-        PITT_CUDA(ctx, cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_key, d_key2, d_idx, d_idx2, n, 0, end_bit, ctx->stream));
-        ctx->launches += 4;  // cub: histogram + onesweep passes
+        PITT_TRY(radix_sort_pairs(ctx, &d_key, &d_idx, &d_key2, &d_idx2, n, end_bit));
+        std::swap(d_key, d_key2);  // the code below reads the sorted pairs from d_key2 / d_idx2
+        std::swap(d_idx, d_idx2);
         const int m = n_finite;  // the finite points come first
         voxel_heads_kernel<<<cdiv(m, 256), 256, 0, ctx->stream>>>(d_key2, m, d_head);
         ctx->launches++;

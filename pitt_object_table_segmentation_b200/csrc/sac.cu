@@ -1519,23 +1519,55 @@ struct Mt19937 {
   }
 };
 
+// The shuffled index array of drawIndexSample is kept sparse: positions 0..3 (touched by every draw) in a small array, the
+// other touched positions in an open-addressing table (a frame draws 13 streams of 1001 minimal sets: a node-based map cost
+// 2 ms of host time per frame, more than every launch of the frame together).
 struct PclSampleStream::Impl {
   Mt19937 mt{12345u};
-  std::unordered_map<int, int> moved;
   int n = 0;
-  int get(int i) const {
-    auto it = moved.find(i);
-    return it == moved.end() ? i : it->second;
+  int front[4] = {0, 1, 2, 3};
+  std::vector<int> keys, vals;
+  int log2_slots = 13, used = 0;
+  Impl() : keys((size_t)1 << 13, -1), vals((size_t)1 << 13, 0) {}
+  size_t probe(const std::vector<int>& k, int key, int lg) const {
+    size_t h = (size_t)(((uint32_t)key * 0x9E3779B1u) >> (32 - lg));
+    const size_t mask = ((size_t)1 << lg) - 1;
+    while (k[h] != -1 && k[h] != key) h = (h + 1) & mask;
+    return h;
+  }
+  void grow() {
+    const int lg = log2_slots + 1;
+    std::vector<int> k2((size_t)1 << lg, -1), v2((size_t)1 << lg, 0);
+    for (size_t i = 0; i < keys.size(); ++i)
+      if (keys[i] != -1) {
+        const size_t h = probe(k2, keys[i], lg);
+        k2[h] = keys[i];
+        v2[h] = vals[i];
+      }
+    keys.swap(k2);
+    vals.swap(v2);
+    log2_slots = lg;
+  }
+  // the entry of position pos (an untouched position holds its own index)
+  int* at(int pos) {
+    if (pos < 4) return &front[pos];
+    if ((size_t)used * 2 >= keys.size()) grow();
+    const size_t h = probe(keys, pos, log2_slots);
+    if (keys[h] == -1) {
+      keys[h] = pos;
+      vals[h] = pos;
+      ++used;
+    }
+    return &vals[h];
   }
   void draw(int S, int* out) {
     for (int i = 0; i < S; ++i) {
       uint32_t r = mt.next() >> 1;  // uniform_int<>(0, INT_MAX) over a 32-bit engine
       int j = i + (int)(r % (uint32_t)(n - i));
-      int a = get(i), b = get(j);
-      moved[i] = b;
-      moved[j] = a;
+      int* pj = at(j);
+      std::swap(front[i], *pj);
     }
-    for (int i = 0; i < S; ++i) out[i] = get(i);
+    for (int i = 0; i < S; ++i) out[i] = front[i];
   }
 };
 PclSampleStream::PclSampleStream(int n, int model, const float* h_xyz4) : impl_(new Impl), model_(model), h_xyz_(h_xyz4) {
@@ -1806,7 +1838,9 @@ int sac_segment_impl(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& 
   std::vector<uint8_t> h_flags;
   int winner = -1, winner_count = 0;
 
-  for (int round = 0; round < 64; ++round) {
+  // Every scanned hypothesis advances PCL's iteration or skip counter and both are bounded (max_iterations, 10 x that), so
+  // the scan reports done after finitely many batches; the sample sources run dry on their own (replay_count).
+  for (int round = 0;; ++round) {
     const int H = batch;
     PITT_TRY(arena_alloc(ctx, (size_t)H * S, &d_samples));
     PITT_TRY(arena_alloc(ctx, (size_t)H, &d_recs));
@@ -1822,7 +1856,12 @@ int sac_segment_impl(pitt_ctx* ctx, const pitt_cloud* c, const pitt_sac_params& 
         if (!p.replay_samples) return fail(ctx, PITT_ERR_INVALID, "replay_samples is null");
         H_have = std::min(H, p.replay_count - H_total);
         if (H_have <= 0) break;
-        memcpy(h_samples.data(), p.replay_samples + (size_t)H_total * S, (size_t)H_have * S * sizeof(int));
+        const int* src = p.replay_samples + (size_t)H_total * S;
+        for (size_t i = 0; i < (size_t)H_have * S; ++i) {
+          // they index the cloud on the device and, in the streaming stage, the caller's host buffer
+          if (src[i] < 0 || src[i] >= n) return fail(ctx, PITT_ERR_INVALID, "sample index out of range");
+          h_samples[i] = src[i];
+        }
       } else {
         H_have = 0;
         for (int h = 0; h < H; ++h) {

@@ -62,6 +62,9 @@ int pitt_debug_philox_samples(pitt_ctx* ctx, int H, int S, int n, uint32_t strea
  * [6] candidates inside the guaranteed radius, [7] / [8] attempts with > 64 candidates below the threshold (first / later
  * bucket), [9] attempts with < k candidates inside the guaranteed radius, [10] most candidates of one attempt */
 int pitt_debug_knn_stats(pitt_ctx* ctx, int enable, int64_t* out16);
+/* enable != 0: record {start ns, end ns, SM, candidates of the histogram passes, histogram passes, hand-overs} of every CTA of
+ * the following knn_collect_kernel launches (whole-cloud normals); out (nullable, 6 * cap words): the record of the last launch. Returns the number of CTAs copied. (knn.cu) */
+int pitt_debug_knn_timeline(pitt_ctx* ctx, int enable, uint64_t* out, int cap);
 
 #ifdef __cplusplus
 }

@@ -32,7 +32,7 @@ DEBUG_SYMBOLS = [
     "pitt_debug_plane_mode", "pitt_debug_force_generic_plane", "pitt_debug_score_mode", "pitt_debug_select_no_fuse",
     "pitt_debug_lm_cluster_min", "pitt_debug_stream_chunks", "pitt_debug_plane_filter_stats", "pitt_debug_plane_tc_stats",
     "pitt_debug_plane_tc_cta_cycles", "pitt_debug_plane_tc_dump", "pitt_debug_plane_tc_acc_ulps", "pitt_debug_plane_tc_variant",
-    "pitt_debug_plane_tc_nwq", "pitt_debug_plane_tc_time_kernel", "pitt_debug_plane_tc_kernel_ms", "pitt_debug_knn_stats", "pitt_debug_frame_mode", "pitt_debug_philox", "pitt_debug_philox_samples",
+    "pitt_debug_plane_tc_nwq", "pitt_debug_plane_tc_time_kernel", "pitt_debug_plane_tc_kernel_ms", "pitt_debug_knn_stats", "pitt_debug_knn_timeline", "pitt_debug_frame_mode", "pitt_debug_philox", "pitt_debug_philox_samples",
 ]
 
 
@@ -143,6 +143,7 @@ def load_library():
     lib.pitt_debug_plane_tc_time_kernel.argtypes = [vp, C.c_int]
     lib.pitt_debug_plane_tc_time_kernel.restype = None
     lib.pitt_debug_knn_stats.argtypes = [vp, C.c_int, C.POINTER(C.c_int64)]
+    lib.pitt_debug_knn_timeline.argtypes = [vp, C.c_int, C.POINTER(C.c_uint64), C.c_int]
     u32p = C.POINTER(C.c_uint32)
     lib.pitt_debug_philox.argtypes = [vp, u32p, u32p, u32p]
     lib.pitt_debug_philox_samples.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_uint32, A.i32p]

@@ -481,12 +481,19 @@ __device__ __forceinline__ float mg_bound(const MGrid& g, float4 q, int X, int Y
   return b;
 }
 
-#define CE(i, j)                                       \
-  {                                                    \
-    const unsigned long long a_ = key[i], b_ = key[j]; \
-    const bool s_ = b_ < a_;                           \
-    key[i] = s_ ? b_ : a_;                             \
-    key[j] = s_ ? a_ : b_;                             \
+// One 64-bit compare feeds both selects (written in C, the compiler turns the pair into min + max with a compare each: 8
+// instructions per exchange instead of 6, and the unrolled network is bound by instruction fetch).
+#define CE(i, j)                                                                                              \
+  {                                                                                                           \
+    unsigned long long lo_, hi_;                                                                              \
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 al, ah, bl, bh, xl, xh, yl, yh;\n\t"                                  \
+        "mov.b64 {al, ah}, %2;\n\tmov.b64 {bl, bh}, %3;\n\tsetp.lt.u64 p, %3, %2;\n\t"                        \
+        "selp.b32 xl, bl, al, p;\n\tselp.b32 xh, bh, ah, p;\n\tselp.b32 yl, al, bl, p;\n\tselp.b32 yh, ah, bh, p;\n\t" \
+        "mov.b64 %0, {xl, xh};\n\tmov.b64 %1, {yl, yh};\n\t}"                                                \
+        : "=l"(lo_), "=l"(hi_)                                                                                \
+        : "l"(key[i]), "l"(key[j]));                                                                          \
+    key[i] = lo_;                                                                                             \
+    key[j] = hi_;                                                                                             \
   }
 
 // finest level l such that the query's ancestor cell one level up holds at least `need` points (monotone in l), MG_MAXLVL if
@@ -577,11 +584,11 @@ __device__ __forceinline__ int mg_block27_count(const MGrid& g, const int* __res
 // candidate streams is hidden by switching warps. The keys go to global memory laid out [slot][query] (coalesced: consecutive
 // lanes are consecutive queries); ncol[query] = their number, or -1 when the query was handed to the warp-per-query kernel.
 template <bool SEG>
-__global__ void __launch_bounds__(KNN_FAST_TPB, 8)
-knn_collect_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, const float4* __restrict__ sorted, int t_base, int t_count,
-                   int k, int need, int mcap, unsigned long long* __restrict__ keys, int* __restrict__ ncol, int* __restrict__ fb_count,
-                   int* __restrict__ fb_list, unsigned long long* __restrict__ dbg) {
-  __shared__ unsigned s_hist[KNN_FAST_TPB / 32][33][32];
+__device__ __forceinline__ void
+knn_collect_body(const MGrid* __restrict__ G, const int* __restrict__ start, const float4* __restrict__ sorted, int t_base, int t_count,
+                 int k, int need, int mcap, unsigned long long* __restrict__ keys, int* __restrict__ ncol, int* __restrict__ fb_count,
+                 int* __restrict__ fb_list, unsigned long long* __restrict__ dbg, unsigned (*s_hist)[33][32],
+                 unsigned long long* __restrict__ tline, int retry_up) {
   const MGrid g = *G;
   const int tl = blockIdx.x * KNN_FAST_TPB + threadIdx.x;  // query within this chunk
   const int t = t_base + tl;
@@ -635,6 +642,10 @@ knn_collect_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, c
       cum += (int)hcol[(31 - b) * 32];
       if (bsel < 0 && cum >= k) { bsel = b; cat = cum; }
     }
+    if (tline) {  // [3] candidates of histogram passes, [4] histogram passes, [5] hand-overs (pitt_debug_knn_timeline)
+      atomicAdd(tline + 6 * blockIdx.x + 3, (unsigned long long)mtot);
+      atomicAdd(tline + 6 * blockIdx.x + 4, 1ull);
+    }
     if (dbg) {  // diagnostics (pitt_debug_knn_stats)
       atomicAdd(&dbg[lvl], 1ull);
       atomicAdd(&dbg[4], (unsigned long long)cum);
@@ -644,7 +655,7 @@ knn_collect_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, c
     }
     if (bsel < 0) {
       // fewer than k points inside the guaranteed radius: a cube twice as wide
-      if (dir >= 0 && lvl < MG_MAXLVL) { ++lvl; dir = 1; continue; }
+      if (retry_up && dir >= 0 && lvl < MG_MAXLVL) { ++lvl; dir = 1; continue; }
       hand_over = min(lvl + 1, MG_MAXLVL + 1);
     } else if (cat > 64) {
       hand_over = lvl;  // the k-th neighbour lies far below the window, or > 64 candidates in one bucket
@@ -655,6 +666,7 @@ knn_collect_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, c
   }
   if (hand_over >= 0) {
     if (dbg && mtot > mcap) atomicAdd(&dbg[9], 1ull);
+    if (tline) atomicAdd(tline + 6 * blockIdx.x + 5, 1ull);
     const int pos = atomicAdd(fb_count, 1);
     fb_list[pos] = t | (hand_over << 28);
     ncol[tl] = -1;
@@ -674,14 +686,41 @@ knn_collect_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, c
   ncol[tl] = c;
 }
 
+__device__ __forceinline__ unsigned long long knn_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// tline (pitt_debug_knn_timeline, else null): per CTA {first start, last end} in ns of %globaltimer and the SM it ran on
+template <bool SEG>
+__global__ void __launch_bounds__(KNN_FAST_TPB, 8)
+knn_collect_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, const float4* __restrict__ sorted, int t_base, int t_count,
+                   int k, int need, int mcap, unsigned long long* __restrict__ keys, int* __restrict__ ncol, int* __restrict__ fb_count,
+                   int* __restrict__ fb_list, unsigned long long* __restrict__ dbg, unsigned long long* __restrict__ tline, int retry_up) {
+  __shared__ unsigned s_hist[KNN_FAST_TPB / 32][33][32];
+  unsigned long long t0 = 0ull;
+  if (tline) t0 = knn_globaltimer();
+  knn_collect_body<SEG>(G, start, sorted, t_base, t_count, k, need, mcap, keys, ncol, fb_count, fb_list, dbg, s_hist, tline, retry_up);
+  if (tline) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) atomicMax(tline + 6 * blockIdx.x + 1, knn_globaltimer());
+    if (threadIdx.x == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      tline[6 * blockIdx.x] = t0;
+      tline[6 * blockIdx.x + 2] = smid;
+    }
+  }
+}
+
 // Fast path, second kernel: the 64 keys of a query sorted in REGISTERS (Batcher's odd-even merge network, compile-time indices),
 // then the first k in order: neighbour lists, or the sequential float covariance + eigen33 + flip of computeFeature.
 template <int MODE, bool SEG>  // 0: neighbour lists, 1: normals
-__global__ void __launch_bounds__(KNN_FAST_TPB, 3)
-knn_sort_kernel(const float4* __restrict__ sorted, const float4* __restrict__ xyz, int t_base, int t_count, int k,
-                const unsigned long long* __restrict__ keys, const int* __restrict__ ncol, float vpx, float vpy, float vpz,
-                int* __restrict__ out_idx, float* __restrict__ out_sq, float4* __restrict__ out_nrm) {
-  const int tl = blockIdx.x * KNN_FAST_TPB + threadIdx.x;
+__device__ __forceinline__ void
+knn_sort_body(const float4* __restrict__ sorted, const float4* __restrict__ xyz, int t_base, int t_count, int k,
+              const unsigned long long* __restrict__ keys, const int* __restrict__ ncol, float vpx, float vpy, float vpz,
+              int* __restrict__ out_idx, float* __restrict__ out_sq, float4* __restrict__ out_nrm, int vblock) {
+  const int tl = vblock * KNN_FAST_TPB + threadIdx.x;
   if (tl >= t_count) return;
   const int c = ncol[tl];
   if (c < 0) return;  // handed over
@@ -735,20 +774,27 @@ knn_sort_kernel(const float4* __restrict__ sorted, const float4* __restrict__ xy
 // its level; if the k-th best found there is not closer than the guaranteed radius, the level goes up; above MG_MAXLVL the
 // whole point array is the candidate set, which always ends the search. Serves the queries the fast kernel hands over (list,
 // *n_list on the device) and, with list == nullptr, every point (k > KNN_FAST_KMAX).
-template <int MODE, bool SEG>
-__global__ void __launch_bounds__(WS_WARPS * 32)
-knn_wide_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, const float4* __restrict__ sorted,
-                const float4* __restrict__ xyz, int n_xyz, int k, int need, float vpx, float vpy, float vpz, int* __restrict__ out_idx,
-                float* __restrict__ out_sq, float4* __restrict__ out_nrm, const int* __restrict__ n_list, const int* __restrict__ list) {
-  __shared__ float s_bd[WS_WARPS][64];
-  __shared__ int s_bi[WS_WARPS][64];
-  __shared__ int s_rb[WS_WARPS][32], s_pre[WS_WARPS][32];
+struct KnnWideSmem {  // per warp
+  float bd[64];
+  int bi[64];
+  int rb[32], pre[32];
+};
+template <int MODE, bool SEG, int NW>  // NW warps per CTA; vblock of vgrid CTAs take this role
+__device__ __forceinline__ void
+knn_wide_body(const MGrid* __restrict__ G, const int* __restrict__ start, const float4* __restrict__ sorted,
+              const float4* __restrict__ xyz, int n_xyz, int k, int need, float vpx, float vpy, float vpz, int* __restrict__ out_idx,
+              float* __restrict__ out_sq, float4* __restrict__ out_nrm, const int* __restrict__ n_list, const int* __restrict__ list,
+              KnnWideSmem* __restrict__ sm_all, int vblock, int vgrid) {
   const MGrid g = *G;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* const s_bd_w = sm_all[warp].bd;
+  int* const s_bi_w = sm_all[warp].bi;
+  int* const s_rb_w = sm_all[warp].rb;
+  int* const s_pre_w = sm_all[warp].pre;
   const int nq = list ? *n_list : g.n_finite;
   // a fixed grid of warps strides over the queries (launching a CTA per 8 potential queries, almost all of them empty, costs
   // more than the search itself)
-  for (int slot = blockIdx.x * WS_WARPS + warp; slot < nq; slot += gridDim.x * WS_WARPS) {
+  for (int slot = vblock * NW + warp; slot < nq; slot += vgrid * NW) {
   int t = slot, l = -1;
   if (list) {
     const int e = list[slot];
@@ -767,10 +813,10 @@ knn_wide_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, cons
   float thr_d;
   int thr_i, count;
   auto flush = [&]() {
-    kd[2] = (lane < count) ? s_bd[warp][lane] : CUDART_INF_F;
-    ki[2] = (lane < count) ? s_bi[warp][lane] : 0x7fffffff;
-    kd[3] = (lane + 32 < count) ? s_bd[warp][lane + 32] : CUDART_INF_F;
-    ki[3] = (lane + 32 < count) ? s_bi[warp][lane + 32] : 0x7fffffff;
+    kd[2] = (lane < count) ? s_bd_w[lane] : CUDART_INF_F;
+    ki[2] = (lane < count) ? s_bi_w[lane] : 0x7fffffff;
+    kd[3] = (lane + 32 < count) ? s_bd_w[lane + 32] : CUDART_INF_F;
+    ki[3] = (lane + 32 < count) ? s_bi_w[lane + 32] : 0x7fffffff;
     __syncwarp();
     ws_sort128(kd, ki, lane);
     count = 0;
@@ -812,8 +858,8 @@ knn_wide_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, cons
       const int mtot = __shfl_sync(0xffffffffu, incl, 31);
       if (mtot == 0) continue;
       __syncwarp();
-      s_rb[warp][lane] = jb;
-      s_pre[warp][lane] = incl - len;
+      s_rb_w[lane] = jb;
+      s_pre_w[lane] = incl - len;
       __syncwarp();
       for (int base = 0; base < mtot; base += 32) {
         const int fi = base + lane;
@@ -823,8 +869,8 @@ knn_wide_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, cons
           int r = 0;
 #pragma unroll
           for (int s = 16; s > 0; s >>= 1)
-            if (s_pre[warp][r + s] <= fi) r += s;
-          const float4 p = __ldg(sorted + s_rb[warp][r] + (fi - s_pre[warp][r]));
+            if (s_pre_w[r + s] <= fi) r += s;
+          const float4 p = __ldg(sorted + s_rb_w[r] + (fi - s_pre_w[r]));
           const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
           d = (ddx * ddx + ddy * ddy) + ddz * ddz;
           pi = __float_as_int(p.w);
@@ -842,8 +888,8 @@ knn_wide_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, cons
           }
           if (pass2) {
             const int pos = count + __popc(mask2 & ((1u << lane) - 1u));
-            s_bd[warp][pos] = d;
-            s_bi[warp][pos] = pi;
+            s_bd_w[pos] = d;
+            s_bi_w[pos] = pi;
           }
           count += __popc(mask2);
           __syncwarp();
@@ -898,6 +944,42 @@ knn_wide_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, cons
   }  // queries of this warp
 }
 
+
+template <int MODE, bool SEG>
+__global__ void __launch_bounds__(KNN_FAST_TPB, 3)
+knn_sort_kernel(const float4* __restrict__ sorted, const float4* __restrict__ xyz, int t_base, int t_count, int k,
+                const unsigned long long* __restrict__ keys, const int* __restrict__ ncol, float vpx, float vpy, float vpz,
+                int* __restrict__ out_idx, float* __restrict__ out_sq, float4* __restrict__ out_nrm) {
+  knn_sort_body<MODE, SEG>(sorted, xyz, t_base, t_count, k, keys, ncol, vpx, vpy, vpz, out_idx, out_sq, out_nrm, blockIdx.x);
+}
+template <int MODE, bool SEG>
+__global__ void __launch_bounds__(WS_WARPS * 32)
+knn_wide_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, const float4* __restrict__ sorted,
+                const float4* __restrict__ xyz, int n_xyz, int k, int need, float vpx, float vpy, float vpz, int* __restrict__ out_idx,
+                float* __restrict__ out_sq, float4* __restrict__ out_nrm, const int* __restrict__ n_list, const int* __restrict__ list) {
+  __shared__ KnnWideSmem sm[WS_WARPS];
+  knn_wide_body<MODE, SEG, WS_WARPS>(G, start, sorted, xyz, n_xyz, k, need, vpx, vpy, vpz, out_idx, out_sq, out_nrm, n_list, list, sm,
+                                     blockIdx.x, gridDim.x);
+}
+// Second kernel of the fast path when the cloud is one chunk: the first `wide_ctas` CTAs serve the handed-over queries a warp each
+// (few, long searches: they start first and run beside the sorting CTAs instead of after them), the others sort.
+template <int MODE, bool SEG>
+__global__ void __launch_bounds__(KNN_FAST_TPB, 3)
+knn_finish_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, const float4* __restrict__ sorted,
+                  const float4* __restrict__ xyz, int n_xyz, int t_count, int k, int need, const unsigned long long* __restrict__ keys,
+                  const int* __restrict__ ncol, float vpx, float vpy, float vpz, int* __restrict__ out_idx, float* __restrict__ out_sq,
+                  float4* __restrict__ out_nrm, const int* __restrict__ n_list, const int* __restrict__ list, int wide_ctas) {
+  __shared__ KnnWideSmem sm[KNN_FAST_TPB / 32];
+  if ((int)blockIdx.x < wide_ctas)
+    knn_wide_body<MODE, SEG, KNN_FAST_TPB / 32>(G, start, sorted, xyz, n_xyz, k, need, vpx, vpy, vpz, out_idx, out_sq, out_nrm, n_list,
+                                                list, sm, blockIdx.x, wide_ctas);
+  else
+    knn_sort_body<MODE, SEG>(sorted, xyz, 0, t_count, k, keys, ncol, vpx, vpy, vpz, out_idx, out_sq, out_nrm, blockIdx.x - wide_ctas);
+}
+
+constexpr int KNN_TIMELINE_MAX = 8192;
+unsigned long long* g_knn_timeline = nullptr;  // pitt_debug_knn_timeline: device buffer of 3 words per CTA of knn_collect_kernel
+int g_knn_timeline_ctas = 0;
 int g_knn_stats = 0;  // pitt_debug_knn_stats(ctx, out, enable): collect the diagnostics of knn_fast_kernel
 static float knn_env(const char* name, float dflt) {
   const char* v = getenv(name);
@@ -909,6 +991,9 @@ static float knn_env(const char* name, float dflt) {
 static float knn_c_avg() { static float v = knn_env("PITT_KNN_CAVG", 2.5f); return v; }             // mean points per fine cell
 // queries with more points than this in their 27 cells go to the warp-per-query kernel
 static int knn_mcap() { static float v = knn_env("PITT_KNN_MCAP", 768.0f); return (int)v; }  // measured 1536 / 768 / 512: 379 / 318 / 291 us collect, but 512 floods the wide kernel
+// a query with fewer than k points inside the guaranteed radius: 1 = its lane repeats the search one level up (the other 31 lanes
+// of the warp wait: 0.7 % of the queries make a fifth of the warps twice as long), 0.4 = it joins the hand-over list (measured: the warp-per-query searches cost more than the waiting, 1182 against 1520 frames/s)
+static int knn_retry_up() { static float v = knn_env("PITT_KNN_RETRY", 1.0f); return v > 0.5f ? 1 : 0; }
 static int knn_seg_grid_min() { static float v = knn_env("PITT_KNN_SEG_MIN", 1500.0f); return (int)v; }
 static int knn_need(int k) { static float f = knn_env("PITT_KNN_NEED", 1.2f); return std::max(8, (int)ceilf(f * (float)k)); }  // points in the parent cell
 
@@ -967,19 +1052,36 @@ static int knn_large(pitt_ctx* ctx, const float4* d_xyz, int n, int k, const flo
     PITT_TRY(arena_alloc(ctx, stride * 64, &d_keys));
     PITT_TRY(arena_alloc(ctx, (size_t)chunk, &d_ncol));
     unsigned long long* dbg = g_knn_stats ? reinterpret_cast<unsigned long long*>(mg.d_scr + 8) : nullptr;
-    for (int t0 = 0; t0 < n; t0 += chunk) {
-      const int tc = std::min(chunk, n - t0);
-      knn_collect_kernel<SEG><<<cdiv(tc, KNN_FAST_TPB), KNN_FAST_TPB, 0, ctx->stream>>>(mg.d_G, mg.d_start, mg.d_sorted, t0, tc, k, need,
-                                                                                      knn_mcap(), d_keys, d_ncol, mg.d_scr + 7,
-                                                                                      mg.d_fb_list, dbg);
-      knn_sort_kernel<MODE, SEG><<<cdiv(tc, KNN_FAST_TPB), KNN_FAST_TPB, 0, ctx->stream>>>(mg.d_sorted, d_xyz, t0, tc, k, d_keys, d_ncol,
-                                                                                          vp[0], vp[1], vp[2], d_idx, d_sq, d_nrm);
-      ctx->launches += 2;
+    unsigned long long* tline = nullptr;
+    if (g_knn_timeline && !SEG && cdiv(chunk, KNN_FAST_TPB) <= KNN_TIMELINE_MAX) {
+      tline = g_knn_timeline;
+      g_knn_timeline_ctas = cdiv(chunk, KNN_FAST_TPB);
+      PITT_CUDA(ctx, cudaMemsetAsync(tline, 0, (size_t)6 * KNN_TIMELINE_MAX * sizeof(unsigned long long), ctx->stream));
     }
-    // the queries the fast path handed over, a warp each (their number is only known on the device: a fixed grid strides over them)
-    knn_wide_kernel<MODE, SEG><<<wide_grid, WS_WARPS * 32, 0, ctx->stream>>>(mg.d_G, mg.d_start, mg.d_sorted, d_xyz, n, k, need, vp[0], vp[1],
-                                                                             vp[2], d_idx, d_sq, d_nrm, mg.d_scr + 7, mg.d_fb_list);
-    ctx->launches++;
+    if (n <= chunk) {
+      const int wide_ctas = std::min(cdiv(n, KNN_FAST_TPB / 32), ctx->sm_count * 2);
+      knn_collect_kernel<SEG><<<cdiv(n, KNN_FAST_TPB), KNN_FAST_TPB, 0, ctx->stream>>>(mg.d_G, mg.d_start, mg.d_sorted, 0, n, k, need,
+                                                                                     knn_mcap(), d_keys, d_ncol, mg.d_scr + 7,
+                                                                                     mg.d_fb_list, dbg, tline, knn_retry_up());
+      knn_finish_kernel<MODE, SEG><<<wide_ctas + cdiv(n, KNN_FAST_TPB), KNN_FAST_TPB, 0, ctx->stream>>>(
+          mg.d_G, mg.d_start, mg.d_sorted, d_xyz, n, n, k, need, d_keys, d_ncol, vp[0], vp[1], vp[2], d_idx, d_sq, d_nrm, mg.d_scr + 7,
+          mg.d_fb_list, wide_ctas);
+      ctx->launches += 2;
+    } else {
+      for (int t0 = 0; t0 < n; t0 += chunk) {
+        const int tc = std::min(chunk, n - t0);
+        knn_collect_kernel<SEG><<<cdiv(tc, KNN_FAST_TPB), KNN_FAST_TPB, 0, ctx->stream>>>(mg.d_G, mg.d_start, mg.d_sorted, t0, tc, k, need,
+                                                                                        knn_mcap(), d_keys, d_ncol, mg.d_scr + 7,
+                                                                                        mg.d_fb_list, dbg, tline, knn_retry_up());
+        knn_sort_kernel<MODE, SEG><<<cdiv(tc, KNN_FAST_TPB), KNN_FAST_TPB, 0, ctx->stream>>>(mg.d_sorted, d_xyz, t0, tc, k, d_keys, d_ncol,
+                                                                                            vp[0], vp[1], vp[2], d_idx, d_sq, d_nrm);
+        ctx->launches += 2;
+      }
+      // the queries the fast path handed over, a warp each (their number is only known on the device: a fixed grid strides over them)
+      knn_wide_kernel<MODE, SEG><<<wide_grid, WS_WARPS * 32, 0, ctx->stream>>>(mg.d_G, mg.d_start, mg.d_sorted, d_xyz, n, k, need, vp[0],
+                                                                               vp[1], vp[2], d_idx, d_sq, d_nrm, mg.d_scr + 7, mg.d_fb_list);
+      ctx->launches++;
+    }
   } else {
     if (SEG) return fail(ctx, PITT_ERR_INVALID, "segmented k-NN: k <= 56 and fewer than 2^24 points");
     knn_wide_kernel<MODE, false><<<wide_grid, WS_WARPS * 32, 0, ctx->stream>>>(mg.d_G, mg.d_start, mg.d_sorted, d_xyz, n, k, need, vp[0], vp[1],
@@ -1096,6 +1198,28 @@ int pitt_debug_knn_stats(pitt_ctx* ctx, int enable, int64_t* out16) {
   const unsigned long long* d = reinterpret_cast<const unsigned long long*>(h + 8);
   for (int i = 0; i < 9; ++i) out16[2 + i] = (int64_t)d[i];
   return PITT_OK;
+}
+
+/* measurement hook (include/pitt_b200_debug.h): enable != 0 arms the recording for the following large-cloud k-NN calls of the
+ * process (one context at a time); out (nullable, 6 * cap words) receives {start ns, end ns, SM, candidates of the histogram passes, histogram passes, hand-overs} of every CTA of the last
+ * knn_collect_kernel<unsegmented> launch. Returns the number of CTAs recorded, or a negative status. */
+int pitt_debug_knn_timeline(pitt_ctx* ctx, int enable, uint64_t* out, int cap) {
+  if (!ctx) return PITT_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  if (enable && !g_knn_timeline) {
+    if (cudaMalloc((void**)&g_knn_timeline, (size_t)6 * KNN_TIMELINE_MAX * sizeof(unsigned long long)) != cudaSuccess) return PITT_ERR_CUDA;
+  }
+  int n = 0;
+  if (out && g_knn_timeline) {
+    n = std::min(cap, g_knn_timeline_ctas);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) return PITT_ERR_CUDA;
+    if (cudaMemcpy(out, g_knn_timeline, (size_t)6 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return PITT_ERR_CUDA;
+  }
+  if (!enable && g_knn_timeline) {
+    cudaFree(g_knn_timeline);
+    g_knn_timeline = nullptr;
+  }
+  return n;
 }
 
 }  // extern "C"

@@ -1522,21 +1522,46 @@ struct Mt19937 {
 // The shuffled index array of drawIndexSample is kept sparse: positions 0..3 (touched by every draw) in a small array, the
 // other touched positions in an open-addressing table (a frame draws 13 streams of 1001 minimal sets: a node-based map cost
 // 2 ms of host time per frame, more than every launch of the frame together).
+// every stream starts from boost::mt19937(12345): the first draws of the engine are the same for all of them and are kept in
+// a table built once per process (>> 1: uniform_int<>(0, INT_MAX) over a 32-bit engine)
+constexpr int MT_TABLE = 16384;
+static const uint32_t* mt_table() {
+  static const std::vector<uint32_t> t = [] {
+    std::vector<uint32_t> v(MT_TABLE);
+    Mt19937 mt(12345u);
+    for (int i = 0; i < MT_TABLE; ++i) v[i] = mt.next() >> 1;
+    return v;
+  }();
+  return t.data();
+}
 struct PclSampleStream::Impl {
-  Mt19937 mt{12345u};
+  const uint32_t* table = mt_table();
+  int drawn = 0;
+  Mt19937* mt = nullptr;  // only a stream that outruns the table runs its own engine
+  ~Impl() { delete mt; }
+  uint32_t next_r() {
+    if (drawn < MT_TABLE) return table[drawn++];
+    if (!mt) {
+      mt = new Mt19937(12345u);
+      for (int i = 0; i < MT_TABLE; ++i) mt->next();
+    }
+    ++drawn;
+    return mt->next() >> 1;
+  }
   int n = 0;
   int front[4] = {0, 1, 2, 3};
-  std::vector<int> keys, vals;
+  static constexpr int DENSE_MAX = 1 << 16;
+  std::vector<int> dense, keys, vals;
   int log2_slots = 13, used = 0;
-  Impl() : keys((size_t)1 << 13, -1), vals((size_t)1 << 13, 0) {}
+
   size_t probe(const std::vector<int>& k, int key, int lg) const {
     size_t h = (size_t)(((uint32_t)key * 0x9E3779B1u) >> (32 - lg));
     const size_t mask = ((size_t)1 << lg) - 1;
     while (k[h] != -1 && k[h] != key) h = (h + 1) & mask;
     return h;
   }
-  void grow() {
-    const int lg = log2_slots + 1;
+  void grow_table() {
+    const int lg = keys.empty() ? 13 : log2_slots + 1;
     std::vector<int> k2((size_t)1 << lg, -1), v2((size_t)1 << lg, 0);
     for (size_t i = 0; i < keys.size(); ++i)
       if (keys[i] != -1) {
@@ -1551,7 +1576,14 @@ struct PclSampleStream::Impl {
   // the entry of position pos (an untouched position holds its own index)
   int* at(int pos) {
     if (pos < 4) return &front[pos];
-    if ((size_t)used * 2 >= keys.size()) grow();
+    if (n <= DENSE_MAX) {  // a cluster: the plain array
+      if (dense.empty()) {
+        dense.resize((size_t)n);
+        for (int i = 0; i < n; ++i) dense[i] = i;
+      }
+      return &dense[pos];
+    }
+    if ((size_t)used * 2 >= keys.size()) grow_table();
     const size_t h = probe(keys, pos, log2_slots);
     if (keys[h] == -1) {
       keys[h] = pos;
@@ -1562,8 +1594,8 @@ struct PclSampleStream::Impl {
   }
   void draw(int S, int* out) {
     for (int i = 0; i < S; ++i) {
-      uint32_t r = mt.next() >> 1;  // uniform_int<>(0, INT_MAX) over a 32-bit engine
-      int j = i + (int)(r % (uint32_t)(n - i));
+      const uint32_t r = next_r();
+      const int j = i + (int)(r % (uint32_t)(n - i));
       int* pj = at(j);
       std::swap(front[i], *pj);
     }

@@ -1,6 +1,6 @@
 """Aggregates an ncu launch list (--metrics gpu__time_duration.sum,launch__grid_size,sm__cycles_active.avg,sm__cycles_elapsed.avg
 --csv) by kernel: launches, device time, device time weighted by the fraction of cycles the SMs were active (what a kernel costs
-when other streams fill the gaps). usage: launch_table.py file.csv [rows]"""
+when other streams fill the gaps). usage: launch_table.py file.csv [rows] [last N launches only]"""
 import collections
 import csv
 import sys
@@ -12,6 +12,9 @@ data = collections.OrderedDict()
 for r in rows[1:]:
     d = data.setdefault(r[ii], {'name': r[ki]})
     d[r[mi]] = float(r[vi].replace(',', ''))
+if len(sys.argv) > 3:
+    keep = list(data.keys())[-int(sys.argv[3]):]
+    data = collections.OrderedDict((k, data[k]) for k in keep)
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
 tot = totw = 0.0
 for d in data.values():

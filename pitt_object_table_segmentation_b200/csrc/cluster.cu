@@ -138,9 +138,14 @@ __global__ void fill_i32_kernel(int* p, int n, int v) {
 // components are exactly those of the radius graph (every edge used is a radius edge, every radius edge joins two cells that
 // end up connected).
 constexpr float CC_CELL_FACTOR = 0.57f;  // cell size / tolerance: sqrt(3) * 0.57 = 0.987 < 1, 2 * 0.57 = 1.14 > 1
+// Two launches: phase 0 takes the 27 cells at offsets -1..1 (neighbouring cells of a surface are almost always connected and
+// the witness is found after a few points), phase 1 the 98 cells of the outer shell, where most pairs are NOT within the
+// tolerance: by then the components are nearly final and a single find per cell skips them (run in one launch, every warp
+// starts from the unmerged state and scans those cells in full: 86 us instead of 2 x 15 on the objects of a tabletop frame).
+// Cells whose box is out of reach of the point are skipped without a look at their points.
 __global__ void __launch_bounds__(CC_WARPS * 32)
 cc_union_mg_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, const float4* __restrict__ sorted, float r2,
-                   int* __restrict__ parent) {
+                   int* __restrict__ parent, int phase) {
   const MGrid g = *G;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * CC_WARPS + warp;
@@ -150,7 +155,10 @@ cc_union_mg_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, c
   const int cx = mg_coord(q.x, g.mnx, g.inv_hf, g.dx), cy = mg_coord(q.y, g.mny, g.inv_hf, g.dy), cz = mg_coord(q.z, g.mnz, g.inv_hf, g.dz);
   int rq = uf_find(parent, qi);
   for (int ci = lane; ci < 125; ci += 32) {
-    const int x = cx + (ci % 5) - 2, y = cy + ((ci / 5) % 5) - 2, z = cz + (ci / 25) - 2;
+    const int ox = (ci % 5) - 2, oy = ((ci / 5) % 5) - 2, oz = (ci / 25) - 2;
+    const bool inner = (ox >= -1 && ox <= 1 && oy >= -1 && oy <= 1 && oz >= -1 && oz <= 1);
+    if (inner != (phase == 0)) continue;
+    const int x = cx + ox, y = cy + oy, z = cz + oz;
     if (x < 0 || y < 0 || z < 0 || x >= g.dx || y >= g.dy || z >= g.dz) continue;
     const int idx = mg_index(g, x, y, z);
     const int jb = start[idx], je = start[idx + 1];
@@ -162,6 +170,13 @@ cc_union_mg_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, c
         rq = uf_find(parent, qi);
       }
       continue;
+    }
+    if (!inner) {
+      // squared distance from the point to the cell's box, shrunk by a relative margin so that rounding can only keep a cell
+      const float lx = g.mnx + (float)x * g.hf, ly = g.mny + (float)y * g.hf, lz = g.mnz + (float)z * g.hf;
+      const float ex = fmaxf(fmaxf(lx - q.x, q.x - (lx + g.hf)), 0.0f), ey = fmaxf(fmaxf(ly - q.y, q.y - (ly + g.hf)), 0.0f),
+                  ez = fmaxf(fmaxf(lz - q.z, q.z - (lz + g.hf)), 0.0f);
+      if (((ex * ex + ey * ey) + ez * ez) * 0.98f > r2) continue;
     }
     rq = uf_find(parent, qi);
     if (uf_find(parent, pf) == rq) continue;  // that cell is already in this point's component
@@ -289,13 +304,14 @@ int euclidean_clusters_dev(pitt_ctx* ctx, const float4* d_xyz, int n, double tol
   fill_i32_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_rank, n, -1);
   PITT_CUDA(ctx, cudaMemsetAsync(d_nroots, 0, sizeof(int), ctx->stream));
   PITT_CUDA(ctx, cudaMemsetAsync(out->d_head, 0, CC_HEAD_INTS * sizeof(int), ctx->stream));
-  cc_union_mg_kernel<<<cdiv(n, CC_WARPS), CC_WARPS * 32, 0, ctx->stream>>>(mg.d_G, mg.d_start, mg.d_sorted, r2, d_parent);
+  cc_union_mg_kernel<<<cdiv(n, CC_WARPS), CC_WARPS * 32, 0, ctx->stream>>>(mg.d_G, mg.d_start, mg.d_sorted, r2, d_parent, 0);
+  cc_union_mg_kernel<<<cdiv(n, CC_WARPS), CC_WARPS * 32, 0, ctx->stream>>>(mg.d_G, mg.d_start, mg.d_sorted, r2, d_parent, 1);
   cc_flatten_mg_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(mg.d_G, mg.d_sorted, d_parent, d_size, d_root);
   cc_roots_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_parent, d_size, n, std::max(min_size, 1), max_size, d_nroots, d_roots, n);
   cc_rank_dev_kernel<<<1, CC_MAXC, 0, ctx->stream>>>(d_nroots, d_roots, d_rank, out->d_head, mg.d_G, (float)tolerance * CC_CELL_FACTOR);
   cc_label_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d_root, d_size, d_rank, n, out->d_labels);
   cc_compact_dev_kernel<<<CC_MAXC, 1024, 0, ctx->stream>>>(d_xyz, out->d_labels, n, out->d_head, out->d_idx, out->d_points);
-  ctx->launches += 8;
+  ctx->launches += 9;
   PITT_CUDA(ctx, cudaGetLastError());
   return PITT_OK;
 }

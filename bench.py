@@ -476,10 +476,12 @@ def arm_frames(env, args, pkg):
         raws_np = make_frames(seeds[: min(len(seeds), 64)], raw=True)
         raw_pinned = [torch.from_numpy(f).pin_memory() for f in raws_np]
         raws = [p.numpy() for p in raw_pinned]
-        pkg.segment_frames_batched(fctxs, raws, prefilter=pf)
+        for _ in range(max(3, args.warmup)):  # the arenas / pools of every context grow to their steady size during the first calls
+            pkg.segment_frames_batched(fctxs, raws, prefilter=pf)
+        torch.cuda.synchronize()
         env.barrier()
         t0 = time.perf_counter()
-        reps = 2
+        reps = 4
         for _ in range(reps):
             res_f = pkg.segment_frames_batched(fctxs, raws, prefilter=pf)
         torch.cuda.synchronize()

@@ -481,19 +481,14 @@ __device__ __forceinline__ float mg_bound(const MGrid& g, float4 q, int X, int Y
   return b;
 }
 
-// One 64-bit compare feeds both selects (written in C, the compiler turns the pair into min + max with a compare each: 8
-// instructions per exchange instead of 6, and the unrolled network is bound by instruction fetch).
-#define CE(i, j)                                                                                              \
-  {                                                                                                           \
-    unsigned long long lo_, hi_;                                                                              \
-    asm("{\n\t.reg .pred p;\n\t.reg .b32 al, ah, bl, bh, xl, xh, yl, yh;\n\t"                                  \
-        "mov.b64 {al, ah}, %2;\n\tmov.b64 {bl, bh}, %3;\n\tsetp.lt.u64 p, %3, %2;\n\t"                        \
-        "selp.b32 xl, bl, al, p;\n\tselp.b32 xh, bh, ah, p;\n\tselp.b32 yl, al, bl, p;\n\tselp.b32 yh, ah, bh, p;\n\t" \
-        "mov.b64 %0, {xl, xh};\n\tmov.b64 %1, {yl, yh};\n\t}"                                                \
-        : "=l"(lo_), "=l"(hi_)                                                                                \
-        : "l"(key[i]), "l"(key[j]));                                                                          \
-    key[i] = lo_;                                                                                             \
-    key[j] = hi_;                                                                                             \
+// Compare-exchange of the sorting network on 32-bit words: one min and one max (two ALU instructions; the first version sorted
+// the 64-bit (distance, index) keys with a 64-bit compare and four selects, six instructions and twice the registers).
+#define CE(i, j)                               \
+  {                                            \
+    const unsigned lo_ = min(key[i], key[j]);  \
+    const unsigned hi_ = max(key[i], key[j]);  \
+    key[i] = lo_;                              \
+    key[j] = hi_;                              \
   }
 
 // finest level l such that the query's ancestor cell one level up holds at least `need` points (monotone in l), MG_MAXLVL if
@@ -510,72 +505,92 @@ __device__ __forceinline__ int mg_pick_level(const int* __restrict__ start, int 
   return lvl;
 }
 
-// visits the points of the 27 level-l cells around (X, Y, Z): f(point). Inside a cell the points are taken four at a time with
-// the next four already requested (two register sets used alternately, no index clamping, no per-point validity), so the L1 / L2
-// latency of a lane's private candidate stream overlaps with the arithmetic of the previous four; the last one to three points
-// of a cell follow one by one.
-template <typename F>
-__device__ __forceinline__ void mg_for_block27(const MGrid& g, const int* __restrict__ start, const float4* __restrict__ sorted, int X,
-                                               int Y, int Z, int l, F f) {
+// The 27 level-l cells around (X, Y, Z), looked up ONCE per attempt: the range of every NON-EMPTY cell goes to the thread's
+// column of a shared-memory list as one word (first point << 10 | number of points; the fast path is limited to clouds of
+// <= 2^22 points and to attempts with <= mcap < 1024 candidates). Returns the number of points; ncell = non-empty cells (only
+// the first KNN_CELLS_MAX are listed: a query with more of them is handed over).
+// The block / Morton terms of z and y are hoisted out of the inner loops by hand (the compiler re-derived the whole index per
+// cell: ~45 instructions and two dependent loads per cell in each of the three loops that walked the cells; now the two passes
+// over the candidates read one shared-memory word per cell).
+constexpr int KNN_CELLS_MAX = 21;  // 33 histogram rows + 21 cell rows of 128 B per warp: eight CTAs per SM
+__device__ __forceinline__ int mg_block27_pack(const MGrid& g, const int* __restrict__ start, int X, int Y, int Z, int l,
+                                               unsigned* __restrict__ ccol, int& ncell) {
   const int nx = g.dx >> l, ny = g.dy >> l, nz = g.dz >> l, span = 1 << (3 * l);
+  int tot = 0, nc = 0;
   for (int c = -1; c <= 1; ++c) {
-    const int z = Z + c;
-    if (z < 0 || z >= nz) continue;
+    const int z = Z + c, fz = z << l;
+    const bool vz = (unsigned)z < (unsigned)nz;
+    const int zb = (fz >> 3) * g.nby, zm = mg_spread3(fz & 7) << 2;
     for (int b = -1; b <= 1; ++b) {
-      const int y = Y + b;
-      if (y < 0 || y >= ny) continue;
+      const int y = Y + b, fy = y << l;
+      const bool vy = vz && (unsigned)y < (unsigned)ny;
+      const int yb = (zb + (fy >> 3)) * g.nbx, ym = zm | (mg_spread3(fy & 7) << 1);
+#pragma unroll
       for (int a = -1; a <= 1; ++a) {
-        const int x = X + a;
-        if (x < 0 || x >= nx) continue;
-        const int idx = mg_index(g, x << l, y << l, z << l);
-        const int jb = __ldg(start + idx), cnt = __ldg(start + idx + span) - jb;
-        const float4* p = sorted + jb;
-        int grp = cnt >> 2;
-        if (grp) {
-          float4 a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2), a3 = __ldg(p + 3);
-          p += 4;
-          --grp;  // groups still to be requested
-          while (grp >= 2) {
-            const float4 b0 = __ldg(p), b1 = __ldg(p + 1), b2 = __ldg(p + 2), b3 = __ldg(p + 3);
-            f(a0); f(a1); f(a2); f(a3);
-            a0 = __ldg(p + 4); a1 = __ldg(p + 5); a2 = __ldg(p + 6); a3 = __ldg(p + 7);
-            p += 8;
-            f(b0); f(b1); f(b2); f(b3);
-            grp -= 2;
-          }
-          if (grp == 1) {
-            const float4 b0 = __ldg(p), b1 = __ldg(p + 1), b2 = __ldg(p + 2), b3 = __ldg(p + 3);
-            p += 4;
-            f(a0); f(a1); f(a2); f(a3);
-            f(b0); f(b1); f(b2); f(b3);
-          } else {
-            f(a0); f(a1); f(a2); f(a3);
+        const int x = X + a, fx = x << l;
+        if (vy && (unsigned)x < (unsigned)nx) {
+          const int idx = ((yb + (fx >> 3)) << 9) | ym | mg_spread3(fx & 7);
+          const int jb = __ldg(start + idx), cnt = __ldg(start + idx + span) - jb;
+          if (cnt > 0) {
+            tot += cnt;
+            if (nc < KNN_CELLS_MAX) ccol[nc * 32] = ((unsigned)jb << 10) | (unsigned)min(cnt, 1023);
+            ++nc;
           }
         }
-        for (int r = 0; r < (cnt & 3); ++r) f(__ldg(p + r));
       }
     }
   }
-}
-// number of points in those 27 cells
-__device__ __forceinline__ int mg_block27_count(const MGrid& g, const int* __restrict__ start, int X, int Y, int Z, int l) {
-  const int nx = g.dx >> l, ny = g.dy >> l, nz = g.dz >> l, span = 1 << (3 * l);
-  int tot = 0;
-  for (int c = -1; c <= 1; ++c) {
-    const int z = Z + c;
-    if (z < 0 || z >= nz) continue;
-    for (int b = -1; b <= 1; ++b) {
-      const int y = Y + b;
-      if (y < 0 || y >= ny) continue;
-      for (int a = -1; a <= 1; ++a) {
-        const int x = X + a;
-        if (x < 0 || x >= nx) continue;
-        const int idx = mg_index(g, x << l, y << l, z << l);
-        tot += __ldg(start + idx + span) - __ldg(start + idx);
-      }
-    }
-  }
+  ncell = nc;
   return tot;
+}
+// visits the points of those cells: f(point). Inside a cell the points are taken four at a time with the next four already
+// requested (two register sets used alternately, no index clamping, no per-point validity), so the L1 / L2 latency of a lane's
+// private candidate stream overlaps with the arithmetic of the previous four; the last one to three points of a cell follow
+// one by one.
+template <typename F>
+__device__ __forceinline__ void mg_for_cells27(const float4* __restrict__ sorted, const unsigned* __restrict__ ccol, int ncell, F f) {
+  for (int ci = 0; ci < ncell; ++ci) {
+    const unsigned w = ccol[ci * 32];
+    const int cnt = (int)(w & 1023u);
+    const float4* p = sorted + (w >> 10);
+    int grp = cnt >> 2;
+    // the one to three points beyond the last whole group are requested together with the first group and handled first
+    // (taken one by one after the groups, each of them exposed a full load latency: 12 % of the long-scoreboard stalls)
+    const int rem = cnt & 3;
+    const float4* pt = p + (cnt - rem);
+    float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0, t2 = t0;
+    if (rem > 0) t0 = __ldg(pt);
+    if (rem > 1) t1 = __ldg(pt + 1);
+    if (rem > 2) t2 = __ldg(pt + 2);
+    if (grp) {
+      float4 a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2), a3 = __ldg(p + 3);
+      p += 4;
+      --grp;  // groups still to be requested
+      if (rem > 0) f(t0);
+      if (rem > 1) f(t1);
+      if (rem > 2) f(t2);
+      while (grp >= 2) {
+        const float4 b0 = __ldg(p), b1 = __ldg(p + 1), b2 = __ldg(p + 2), b3 = __ldg(p + 3);
+        f(a0); f(a1); f(a2); f(a3);
+        a0 = __ldg(p + 4); a1 = __ldg(p + 5); a2 = __ldg(p + 6); a3 = __ldg(p + 7);
+        p += 8;
+        f(b0); f(b1); f(b2); f(b3);
+        grp -= 2;
+      }
+      if (grp == 1) {
+        const float4 b0 = __ldg(p), b1 = __ldg(p + 1), b2 = __ldg(p + 2), b3 = __ldg(p + 3);
+        p += 4;
+        f(a0); f(a1); f(a2); f(a3);
+        f(b0); f(b1); f(b2); f(b3);
+      } else {
+        f(a0); f(a1); f(a2); f(a3);
+      }
+    } else {
+      if (rem > 0) f(t0);
+      if (rem > 1) f(t1);
+      if (rem > 2) f(t2);
+    }
+  }
 }
 
 
@@ -587,7 +602,7 @@ template <bool SEG>
 __device__ __forceinline__ void
 knn_collect_body(const MGrid* __restrict__ G, const int* __restrict__ start, const float4* __restrict__ sorted, int t_base, int t_count,
                  int k, int need, int mcap, unsigned long long* __restrict__ keys, int* __restrict__ ncol, int* __restrict__ fb_count,
-                 int* __restrict__ fb_list, unsigned long long* __restrict__ dbg, unsigned (*s_hist)[33][32],
+                 int* __restrict__ fb_list, unsigned long long* __restrict__ dbg, unsigned (*s_hist)[33][32], unsigned (*s_cell)[KNN_CELLS_MAX][32],
                  unsigned long long* __restrict__ tline, int retry_up) {
   const MGrid g = *G;
   const int tl = blockIdx.x * KNN_FAST_TPB + threadIdx.x;  // query within this chunk
@@ -598,7 +613,8 @@ knn_collect_body(const MGrid* __restrict__ G, const int* __restrict__ start, con
     return;
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned* hcol = &s_hist[warp][0][lane];  // bucket b of this thread: hcol[b * 32]
+  unsigned* hcol = &s_hist[warp][1][lane];  // row r of this thread's histogram: hcol[r * 32], r = -1 (outside the window) .. 31
+  unsigned* ccol = &s_cell[warp][0][lane];  // cell c of this thread's 27: ccol[c * 32]
   const float4 q = __ldg(sorted + t);
   const unsigned qw = __float_as_uint(q.w);
   const int cx = mg_coord(q.x, g.mnx, g.inv_hf, g.dx), cy = mg_coord(q.y, g.mny, g.inv_hf, g.dy), cz = mg_coord(q.z, g.mnz, g.inv_hf, g.dz);
@@ -608,7 +624,7 @@ knn_collect_body(const MGrid* __restrict__ G, const int* __restrict__ start, con
   // the bucket edge) is handed to the warp-per-query kernel with a level hint
   int hand_over = -1;
   unsigned tsel = 0;
-  int X, Y, Z, mtot;
+  int X, Y, Z, mtot, ncell = 0;
   int dir = 0;  // -1: the level has been lowered (too many points around), +1: raised (fewer than k inside the guaranteed radius)
   for (int attempt = 0;; ++attempt) {
     X = cx >> lvl; Y = cy >> lvl; Z = cz >> lvl;
@@ -616,7 +632,7 @@ knn_collect_body(const MGrid* __restrict__ G, const int* __restrict__ start, con
     const float hl = g.hf * (float)(1 << lvl);
     const float top = (bound > 0.0f) ? fminf(bound * bound, 27.5f * hl * hl) : 0.0f;  // cube = whole grid: its diagonal
     const unsigned btop = __float_as_uint(top);
-    mtot = mg_block27_count(g, start, X, Y, Z, lvl);
+    mtot = mg_block27_pack(g, start, X, Y, Z, lvl, ccol, ncell);
     if (btop < (40u << 20) || attempt == 3) {
       hand_over = lvl;
       break;
@@ -626,14 +642,20 @@ knn_collect_body(const MGrid* __restrict__ G, const int* __restrict__ start, con
       hand_over = lvl;
       break;
     }
+    if (ncell > KNN_CELLS_MAX) {  // more non-empty cells than the list holds (a volume rather than a surface)
+      hand_over = lvl;
+      break;
+    }
 #pragma unroll
-    for (int b = 0; b < 33; ++b) hcol[b * 32] = 0u;
-    // bucket qq = (btop - bits(d2)) >> 20 counts DOWN from the top of the window (31 = everything further below, 32 = outside)
-    mg_for_block27(g, start, sorted, X, Y, Z, lvl, [&](const float4 p) {
+    for (int b = 0; b < 32; ++b) hcol[b * 32] = 0u;
+    // bucket qq = (btop - bits(d2)) >> 20 counts DOWN from the top of the window (31 = everything further below); a point
+    // outside the window has a negative difference and lands in row -1, which nobody reads (shift, clamp, clamp, address:
+    // no compare + select)
+    mg_for_cells27(sorted, ccol, ncell, [&](const float4 p) {
       const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
       const int dd = (int)btop - __float_as_int((ddx * ddx + ddy * ddy) + ddz * ddz);  // both are bit patterns of floats >= 0
-      int qq = dd < 0 ? 32 : min(dd >> 20, 31);
-      if (SEG && ((__float_as_uint(p.w) ^ qw) >> 24)) qq = 32;  // a point of another segment does not exist for this query
+      int qq = max(min(dd >> 20, 31), -1);
+      if (SEG && ((__float_as_uint(p.w) ^ qw) >> 24)) qq = -1;  // a point of another segment does not exist for this query
       hcol[qq * 32] += 1u;
     });
     int cum = 0, bsel = -1, cat = 0;  // bsel in the ascending numbering: bucket b = 31 - qq
@@ -675,7 +697,7 @@ knn_collect_body(const MGrid* __restrict__ G, const int* __restrict__ start, con
   unsigned long long* kq = keys + tl;  // slot s of this query: kq[s * t_count_padded]
   const size_t stride = (size_t)((t_count + 31) & ~31);
   int c = 0;
-  mg_for_block27(g, start, sorted, X, Y, Z, lvl, [&](const float4 p) {
+  mg_for_cells27(sorted, ccol, ncell, [&](const float4 p) {
     const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
     const unsigned db = __float_as_uint((ddx * ddx + ddy * ddy) + ddz * ddz);
     if (db <= tsel && !(SEG && ((__float_as_uint(p.w) ^ qw) >> 24))) {
@@ -697,10 +719,11 @@ __global__ void __launch_bounds__(KNN_FAST_TPB, 8)
 knn_collect_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, const float4* __restrict__ sorted, int t_base, int t_count,
                    int k, int need, int mcap, unsigned long long* __restrict__ keys, int* __restrict__ ncol, int* __restrict__ fb_count,
                    int* __restrict__ fb_list, unsigned long long* __restrict__ dbg, unsigned long long* __restrict__ tline, int retry_up) {
-  __shared__ unsigned s_hist[KNN_FAST_TPB / 32][33][32];
+  __shared__ unsigned s_hist[KNN_FAST_TPB / 32][33][32];  // row 0: points outside the histogram window, rows 1..32: the buckets
+  __shared__ unsigned s_cell[KNN_FAST_TPB / 32][KNN_CELLS_MAX][32];  // the non-empty cells of every thread's current attempt
   unsigned long long t0 = 0ull;
   if (tline) t0 = knn_globaltimer();
-  knn_collect_body<SEG>(G, start, sorted, t_base, t_count, k, need, mcap, keys, ncol, fb_count, fb_list, dbg, s_hist, tline, retry_up);
+  knn_collect_body<SEG>(G, start, sorted, t_base, t_count, k, need, mcap, keys, ncol, fb_count, fb_list, dbg, s_hist, s_cell, tline, retry_up);
   if (tline) {
     __syncwarp();
     if ((threadIdx.x & 31) == 0) atomicMax(tline + 6 * blockIdx.x + 1, knn_globaltimer());
@@ -713,49 +736,131 @@ knn_collect_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, c
   }
 }
 
-// Fast path, second kernel: the 64 keys of a query sorted in REGISTERS (Batcher's odd-even merge network, compile-time indices),
-// then the first k in order: neighbour lists, or the sequential float covariance + eigen33 + flip of computeFeature.
-template <int MODE, bool SEG>  // 0: neighbour lists, 1: normals
+// Fast path, second kernel: the <= 64 candidates of a query sorted in REGISTERS (Batcher's odd-even merge network, compile-time
+// indices), then the first k in order: neighbour lists, or the sequential float covariance + eigen33 + flip of computeFeature.
+//
+// What is sorted is ONE 32-bit word per candidate: the bit pattern of d2 (a non-negative float: unsigned order == numeric order)
+// with its low 6 bits replaced by the candidate's slot number. Two candidates whose d2 differ above those 6 bits are ordered
+// exactly as the 64-bit (d2, index) keys would order them. Candidates that agree in the upper 26 bits ("ambiguous": closer than
+// 64 ulps, about 1 % of the queries of a frame have such a pair) end up ADJACENT after the sort, in slot order; a bubble pass
+// over the adjacent pairs compares their true 64-bit keys (fetched from the key array by slot) and swaps where needed, repeated
+// until nothing moves, which sorts every ambiguous group exactly. The result is the order of the 64-bit keys, bit for bit
+// (tie rule of the oracle: distance, then index), at a third of the compare-exchange instructions and half the registers.
+// Empty slots get distinct pad words above every real one (bit 31 set).
+template <int MODE, bool SEG, int KC>  // MODE 0: neighbour lists, 1: normals; KC > 0: k is this compile-time constant
 __device__ __forceinline__ void
 knn_sort_body(const float4* __restrict__ sorted, const float4* __restrict__ xyz, int t_base, int t_count, int k,
               const unsigned long long* __restrict__ keys, const int* __restrict__ ncol, float vpx, float vpy, float vpz,
-              int* __restrict__ out_idx, float* __restrict__ out_sq, float4* __restrict__ out_nrm, int vblock) {
+              int* __restrict__ out_idx, float* __restrict__ out_sq, float4* __restrict__ out_nrm, int vblock,
+              unsigned* __restrict__ s_idx /*MODE 1: [64][KNN_FAST_TPB] words of dynamic shared memory*/) {
   const int tl = vblock * KNN_FAST_TPB + threadIdx.x;
   if (tl >= t_count) return;
   const int c = ncol[tl];
   if (c < 0) return;  // handed over
   const size_t stride = (size_t)((t_count + 31) & ~31);
   const unsigned long long* kq = keys + tl;
-  unsigned long long key[64];
+  unsigned key[64];
+  // The keys stream in coalesced (consecutive lanes = consecutive queries). The index words wait in shared memory, one column
+  // per thread laid out [slot][thread] (any slot of 32 lanes = 32 banks), and are read back BY SLOT after the sort: fetching
+  // them from the key array by slot instead put two dependent gathers (key array in DRAM, then the point) behind every
+  // neighbour and left the kernel waiting on memory (long-scoreboard stalls 2.3 -> 6.3 per issue, measured).
+  // All 64 slots are requested whatever c is (slots >= c hold stale words of the arena, masked below): loads behind a
+  // per-slot predicate were issued a few at a time and every group paid a DRAM round trip (62 % of the kernel's long-scoreboard
+  // stalls sat on the first use of a key). The whole column is pulled into L2 first, then read in batches of 16.
+  unsigned* icol = s_idx + threadIdx.x;
 #pragma unroll
-  for (int s = 0; s < 64; ++s) key[s] = (s < c) ? __ldg(kq + (size_t)s * stride) : ~0ull;
+  for (int s = 0; s < 64; ++s) asm volatile("prefetch.global.L2 [%0];" ::"l"(kq + (size_t)s * stride));
+#pragma unroll
+  for (int b = 0; b < 64; b += 16) {
+    unsigned long long kv[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) kv[j] = __ldg(kq + (size_t)(b + j) * stride);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int s = b + j;
+      key[s] = (s < c) ? (((unsigned)(kv[j] >> 32) & ~63u) | (unsigned)s) : (0x80000000u | ((unsigned)s << 6));
+      if (MODE == 1) icol[s * KNN_FAST_TPB] = (unsigned)(kv[j] & 0xffffffffull);
+    }
+  }
 #include "knn_sort64.inc"
+  {
+    // smallest xor of adjacent words: < 64 <=> some adjacent pair agrees in the upper 26 bits
+    unsigned mx = 0xffffffffu;
+#pragma unroll
+    for (int s = 0; s < 63; ++s) mx = min(mx, key[s] ^ key[s + 1]);
+    if (mx < 64u) {  // rare: resolve the ambiguous groups with the true keys
+      bool again;
+      do {
+        again = false;
+#pragma unroll
+        for (int s = 0; s < 63; ++s) {
+          if ((key[s] ^ key[s + 1]) < 64u) {
+            const unsigned long long a = __ldg(kq + (size_t)(key[s] & 63u) * stride), b = __ldg(kq + (size_t)(key[s + 1] & 63u) * stride);
+            if (b < a) {
+              const unsigned t_ = key[s];
+              key[s] = key[s + 1];
+              key[s + 1] = t_;
+              again = true;
+            }
+          }
+        }
+      } while (again);
+    }
+  }
   const float4 q = __ldg(sorted + t_base + tl);
   const unsigned IDX = SEG ? 0x00ffffffu : 0xffffffffu;  // the segment lives in the top 8 bits of the index word
   const int qi = (int)(__float_as_uint(q.w) & IDX);
+  const int kk = KC > 0 ? KC : k;
   if (MODE == 0) {
 #pragma unroll
     for (int s = 0; s < KNN_FAST_KMAX; ++s) {
-      if (s < k) {
-        out_idx[(size_t)qi * k + s] = (int)((unsigned)(key[s] & 0xffffffffull) & IDX);
-        if (out_sq) out_sq[(size_t)qi * k + s] = __uint_as_float((unsigned)(key[s] >> 32));
+      if (s < kk) {
+        const unsigned long long tk = __ldg(kq + (size_t)(key[s] & 63u) * stride);
+        out_idx[(size_t)qi * kk + s] = (int)((unsigned)(tk & 0xffffffffull) & IDX);
+        if (out_sq) out_sq[(size_t)qi * kk + s] = __uint_as_float((unsigned)(tk >> 32));
       }
     }
   } else {
     // computeMeanAndCovarianceMatrix: float accumulators in neighbour order (k >= 3 on this path: the cloud has > 4096 points)
     float accu[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (KC > 0) {
+      // k known at compile time (the reference's k = 50): no branch between the gathers, so the loads of a batch are all in
+      // flight before the first accumulation waits for one (with a runtime k every neighbour's load sat behind its own branch
+      // and the L2 latency of 50 dependent gathers was exposed: 18 % of the kernel's stall samples). Same order of additions.
+      constexpr int NB = 10;
 #pragma unroll
-    for (int s = 0; s < KNN_FAST_KMAX; ++s) {
-      if (s < k) {
-        const float4 p = __ldg(xyz + (int)((unsigned)(key[s] & 0xffffffffull) & IDX));
-        accu[0] += p.x * p.x; accu[1] += p.x * p.y; accu[2] += p.x * p.z;
-        accu[3] += p.y * p.y; accu[4] += p.y * p.z; accu[5] += p.z * p.z;
-        accu[6] += p.x; accu[7] += p.y; accu[8] += p.z;
+      for (int b = 0; b < KC; b += NB) {
+        unsigned ix[NB];
+        float4 p[NB];
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+          if (b + j < KC) ix[j] = icol[(key[b + j] & 63u) * KNN_FAST_TPB] & IDX;
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+          if (b + j < KC) p[j] = __ldg(xyz + (int)ix[j]);
+#pragma unroll
+        for (int j = 0; j < NB; ++j)
+          if (b + j < KC) {
+            accu[0] += p[j].x * p[j].x; accu[1] += p[j].x * p[j].y; accu[2] += p[j].x * p[j].z;
+            accu[3] += p[j].y * p[j].y; accu[4] += p[j].y * p[j].z; accu[5] += p[j].z * p[j].z;
+            accu[6] += p[j].x; accu[7] += p[j].y; accu[8] += p[j].z;
+          }
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < KNN_FAST_KMAX; ++s) {
+        if (s < kk) {
+          const unsigned ix = icol[(key[s] & 63u) * KNN_FAST_TPB] & IDX;
+          const float4 p = __ldg(xyz + (int)ix);
+          accu[0] += p.x * p.x; accu[1] += p.x * p.y; accu[2] += p.x * p.z;
+          accu[3] += p.y * p.y; accu[4] += p.y * p.z; accu[5] += p.z * p.z;
+          accu[6] += p.x; accu[7] += p.y; accu[8] += p.z;
+        }
       }
     }
-    if (k >= 3) {
+    if (kk >= 3) {
       float cov[9], cen[3], ev, evec[3];
-      cov_from_accu(accu, (float)k, cov, cen);
+      cov_from_accu(accu, (float)kk, cov, cen);
       eigen33(cov, ev, evec);
       float nx = evec[0], ny = evec[1], nz = evec[2];
       const float eig_sum = cov[0] + cov[4] + cov[8];
@@ -946,11 +1051,12 @@ knn_wide_body(const MGrid* __restrict__ G, const int* __restrict__ start, const 
 
 
 template <int MODE, bool SEG>
-__global__ void __launch_bounds__(KNN_FAST_TPB, 3)
+__global__ void __launch_bounds__(KNN_FAST_TPB, 5)
 knn_sort_kernel(const float4* __restrict__ sorted, const float4* __restrict__ xyz, int t_base, int t_count, int k,
                 const unsigned long long* __restrict__ keys, const int* __restrict__ ncol, float vpx, float vpy, float vpz,
                 int* __restrict__ out_idx, float* __restrict__ out_sq, float4* __restrict__ out_nrm) {
-  knn_sort_body<MODE, SEG>(sorted, xyz, t_base, t_count, k, keys, ncol, vpx, vpy, vpz, out_idx, out_sq, out_nrm, blockIdx.x);
+  extern __shared__ unsigned s_dyn_idx[];
+  knn_sort_body<MODE, SEG, 0>(sorted, xyz, t_base, t_count, k, keys, ncol, vpx, vpy, vpz, out_idx, out_sq, out_nrm, blockIdx.x, s_dyn_idx);
 }
 template <int MODE, bool SEG>
 __global__ void __launch_bounds__(WS_WARPS * 32)
@@ -963,18 +1069,20 @@ knn_wide_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, cons
 }
 // Second kernel of the fast path when the cloud is one chunk: the first `wide_ctas` CTAs serve the handed-over queries a warp each
 // (few, long searches: they start first and run beside the sorting CTAs instead of after them), the others sort.
-template <int MODE, bool SEG>
-__global__ void __launch_bounds__(KNN_FAST_TPB, 3)
+template <int MODE, bool SEG, int KC>
+__global__ void __launch_bounds__(KNN_FAST_TPB, 5)
 knn_finish_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, const float4* __restrict__ sorted,
                   const float4* __restrict__ xyz, int n_xyz, int t_count, int k, int need, const unsigned long long* __restrict__ keys,
                   const int* __restrict__ ncol, float vpx, float vpy, float vpz, int* __restrict__ out_idx, float* __restrict__ out_sq,
                   float4* __restrict__ out_nrm, const int* __restrict__ n_list, const int* __restrict__ list, int wide_ctas) {
   __shared__ KnnWideSmem sm[KNN_FAST_TPB / 32];
+  extern __shared__ unsigned s_dyn_idx[];
   if ((int)blockIdx.x < wide_ctas)
     knn_wide_body<MODE, SEG, KNN_FAST_TPB / 32>(G, start, sorted, xyz, n_xyz, k, need, vpx, vpy, vpz, out_idx, out_sq, out_nrm, n_list,
                                                 list, sm, blockIdx.x, wide_ctas);
   else
-    knn_sort_body<MODE, SEG>(sorted, xyz, 0, t_count, k, keys, ncol, vpx, vpy, vpz, out_idx, out_sq, out_nrm, blockIdx.x - wide_ctas);
+    knn_sort_body<MODE, SEG, KC>(sorted, xyz, 0, t_count, KC > 0 ? KC : k, keys, ncol, vpx, vpy, vpz, out_idx, out_sq, out_nrm,
+                                 blockIdx.x - wide_ctas, s_dyn_idx);
 }
 
 constexpr int KNN_TIMELINE_MAX = 8192;
@@ -990,10 +1098,12 @@ static float knn_env(const char* name, float dflt) {
 // tuning knobs (measured on B200, 307 200-point frame, k = 50; the environment variables are for experiments only)
 static float knn_c_avg() { static float v = knn_env("PITT_KNN_CAVG", 2.5f); return v; }             // mean points per fine cell
 // queries with more points than this in their 27 cells go to the warp-per-query kernel
-static int knn_mcap() { static float v = knn_env("PITT_KNN_MCAP", 768.0f); return (int)v; }  // measured 1536 / 768 / 512: 379 / 318 / 291 us collect, but 512 floods the wide kernel
+static int knn_mcap() { static float v = knn_env("PITT_KNN_MCAP", 768.0f); return std::min((int)v, 1023); }  // < 1024: the packed cell words  // measured 1536 / 768 / 512: 379 / 318 / 291 us collect, but 512 floods the wide kernel
 // a query with fewer than k points inside the guaranteed radius: 1 = its lane repeats the search one level up (the other 31 lanes
 // of the warp wait: 0.7 % of the queries make a fifth of the warps twice as long), 0.4 = it joins the hand-over list (measured: the warp-per-query searches cost more than the waiting, 1182 against 1520 frames/s)
 static int knn_retry_up() { static float v = knn_env("PITT_KNN_RETRY", 1.0f); return v > 0.5f ? 1 : 0; }
+// CTAs per SM that serve the handed-over queries inside the finishing launch
+static int knn_wide_mult() { static float v = knn_env("PITT_KNN_WIDE", 2.0f); return std::max(1, (int)v); }
 static int knn_seg_grid_min() { static float v = knn_env("PITT_KNN_SEG_MIN", 1500.0f); return (int)v; }
 static int knn_need(int k) { static float f = knn_env("PITT_KNN_NEED", 1.2f); return std::max(8, (int)ceilf(f * (float)k)); }  // points in the parent cell
 
@@ -1035,6 +1145,9 @@ int mgrid_build(pitt_ctx* ctx, const float4* d_xyz, int n, float h_fixed, MGridB
   return PITT_OK;
 }
 
+// dynamic shared memory of the sorting kernels: the index words of MODE 1, [64][KNN_FAST_TPB]
+static size_t knn_sort_smem(int mode) { return mode == 1 ? (size_t)64 * KNN_FAST_TPB * sizeof(unsigned) : 0; }
+
 // exact k-NN of every point of a large cloud; MODE 0 writes the neighbour lists, MODE 1 the normals
 template <int MODE, bool SEG>
 static int knn_large(pitt_ctx* ctx, const float4* d_xyz, int n, int k, const float vp[3], int* d_idx, float* d_sq, float4* d_nrm,
@@ -1043,7 +1156,7 @@ static int knn_large(pitt_ctx* ctx, const float4* d_xyz, int n, int k, const flo
   PITT_TRY(mgrid_build(ctx, d_xyz, n, 0.0f, &mg, d_seg_off, d_n_seg));
   const int need = knn_need(k);
   const int wide_grid = std::min(cdiv(n, WS_WARPS), ctx->sm_count * 8);
-  if (k <= KNN_FAST_KMAX && n < (1 << 24)) {
+  if (k <= KNN_FAST_KMAX && n <= (1 << 22)) {  // the packed cell words hold 22 bits of point offset
     // the collected keys take 512 B per query: clouds of more than a million points go through in chunks of queries
     const int chunk = std::min(n, 1 << 20);
     const size_t stride = (size_t)((chunk + 31) & ~31);
@@ -1059,11 +1172,12 @@ static int knn_large(pitt_ctx* ctx, const float4* d_xyz, int n, int k, const flo
       PITT_CUDA(ctx, cudaMemsetAsync(tline, 0, (size_t)6 * KNN_TIMELINE_MAX * sizeof(unsigned long long), ctx->stream));
     }
     if (n <= chunk) {
-      const int wide_ctas = std::min(cdiv(n, KNN_FAST_TPB / 32), ctx->sm_count * 2);
+      const int wide_ctas = std::min(cdiv(n, KNN_FAST_TPB / 32), ctx->sm_count * knn_wide_mult());
       knn_collect_kernel<SEG><<<cdiv(n, KNN_FAST_TPB), KNN_FAST_TPB, 0, ctx->stream>>>(mg.d_G, mg.d_start, mg.d_sorted, 0, n, k, need,
                                                                                      knn_mcap(), d_keys, d_ncol, mg.d_scr + 7,
                                                                                      mg.d_fb_list, dbg, tline, knn_retry_up());
-      knn_finish_kernel<MODE, SEG><<<wide_ctas + cdiv(n, KNN_FAST_TPB), KNN_FAST_TPB, 0, ctx->stream>>>(
+      auto finish = (MODE == 1 && k == 50) ? knn_finish_kernel<MODE, SEG, (MODE == 1 ? 50 : 0)> : knn_finish_kernel<MODE, SEG, 0>;
+      finish<<<wide_ctas + cdiv(n, KNN_FAST_TPB), KNN_FAST_TPB, knn_sort_smem(MODE), ctx->stream>>>(
           mg.d_G, mg.d_start, mg.d_sorted, d_xyz, n, n, k, need, d_keys, d_ncol, vp[0], vp[1], vp[2], d_idx, d_sq, d_nrm, mg.d_scr + 7,
           mg.d_fb_list, wide_ctas);
       ctx->launches += 2;
@@ -1073,7 +1187,7 @@ static int knn_large(pitt_ctx* ctx, const float4* d_xyz, int n, int k, const flo
         knn_collect_kernel<SEG><<<cdiv(tc, KNN_FAST_TPB), KNN_FAST_TPB, 0, ctx->stream>>>(mg.d_G, mg.d_start, mg.d_sorted, t0, tc, k, need,
                                                                                         knn_mcap(), d_keys, d_ncol, mg.d_scr + 7,
                                                                                         mg.d_fb_list, dbg, tline, knn_retry_up());
-        knn_sort_kernel<MODE, SEG><<<cdiv(tc, KNN_FAST_TPB), KNN_FAST_TPB, 0, ctx->stream>>>(mg.d_sorted, d_xyz, t0, tc, k, d_keys, d_ncol,
+        knn_sort_kernel<MODE, SEG><<<cdiv(tc, KNN_FAST_TPB), KNN_FAST_TPB, knn_sort_smem(MODE), ctx->stream>>>(mg.d_sorted, d_xyz, t0, tc, k, d_keys, d_ncol,
                                                                                             vp[0], vp[1], vp[2], d_idx, d_sq, d_nrm);
         ctx->launches += 2;
       }
@@ -1100,7 +1214,7 @@ int estimate_normals_segmented(pitt_ctx* ctx, const float4* d_xyz, int n_total, 
   const float nan = nanf("");
   fill_f4_kernel<<<cdiv(n_total, 256), 256, 0, ctx->stream>>>(d_nrm, n_total, make_float4(nan, nan, nan, nan));
   ctx->launches++;
-  if (n_total >= knn_seg_grid_min() && k <= KNN_FAST_KMAX && n_total < (1 << 24)) {
+  if (n_total >= knn_seg_grid_min() && k <= KNN_FAST_KMAX && n_total <= (1 << 22)) {
     // enough points for the grid to pay: ONE multi-level grid over all segments, every point tagged with its segment, the
     // searches ignore candidates of other segments (6042 cluster points of a frame: 113 us all-pairs -> see profiles/)
     return knn_large<1, true>(ctx, d_xyz, n_total, k, vp, nullptr, nullptr, d_nrm, d_seg_off, d_n_seg);

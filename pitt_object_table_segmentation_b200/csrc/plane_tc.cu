@@ -13,7 +13,7 @@
 //       (i, j) != (3, 3), and d1 + d2 + d3 (27 of the 32 K slots); every product is exact (8 x 8 bits)
 //       and what is dropped, a3 x3, is below 2^-27 m, m = |a x| + |b y| + |c z| + |d|; the only real
 //       error is the tensor core's FP32 accumulation, bounded by TC_ACC_ULPS u m (u = 2^-24;
-//       measured, profiles/r01_plane_tc_numerics.md),
+//       measured, profiles/r02_plane_tc_numerics.md),
 //   (3) hypotheses are pre-scaled by a power of two sigma, so the accumulator holds s~ = sigma s and
 //       u = sat(C - |s~|), C = fl(sigma thr + 1/2), is exactly 1 for a certain inlier, exactly 0 for a
 //       certain outlier and fractional inside the window | |s~| - sigma thr | < 1/2, which sigma makes

@@ -455,6 +455,35 @@ def arm_frames(env, args, pkg):
         "shape_tags_of_this_rank": shapes_hist, "frame_generation_s": gen_s,
         "launches_per_frame": n_launch / float(max(1, args.steps * per_gpu)),
     }
+    # ---- the dominant kernel group of the frame path, timed alone: whole-cloud normals (grid build + knn_collect_kernel +
+    # knn_finish_kernel) on distinct resident frames (629 MB of clouds in rotation: nothing is warm in L2), CUDA events
+    # recorded by the library on the context's stream
+    nctx = stager  # the context that owns the resident clouds (the normals are attached to them from its pool)
+    nsub = clouds[: min(len(clouds), 64)]
+    for cl in nsub:  # first round: the normal arrays are attached to the clouds (allocation), the arena grows
+        nctx.estimate_normals_device(cl, 50)
+    nms = []
+    for cl in nsub:  # second round, timed: 64 x 4.9 MB of clouds + 157 MB of keys per call went through L2 since this cloud's turn
+        nctx.estimate_normals_device(cl, 50)
+        nms.append(nctx.last_device_ms)
+    normals_ms = float(np.median(nms))
+    n_pts = int(frames[0].shape[0])
+    alg_bytes = n_pts * 32  # 16 B per point in, 16 B per normal out
+    info["normals"] = {
+        "ms": normals_ms, "points": n_pts, "k": 50,
+        "share_of_gpu_time_per_frame": normals_ms / (1e3 * env.world / value) if value > 0 else None,
+        "queries_per_s": n_pts / (normals_ms * 1e-3),
+        "note": "whole-cloud NormalEstimation (pc_manager.cpp:68-78) alone on one stream; under the 16-context frame stream its "
+                "launches overlap with other frames' work",
+        "roofline": {"bound": "hbm", "kernel": "knn_collect_kernel + knn_finish_kernel (+ 9 grid-build launches)",
+                     "achieved": alg_bytes / (normals_ms * 1e-3) / 1e9, "peak": MEASURED.get("hbm_gbs"), "unit": "GB/s",
+                     "frac": ((alg_bytes / (normals_ms * 1e-3) / 1e9) / MEASURED["hbm_gbs"]) if MEASURED.get("hbm_gbs") else None,
+                     "traffic": 306.0e6, "algorithmic_bytes_per_launch": alg_bytes,
+                     "traffic_note": "dram__bytes_read+write of the two kernels from profiles/r02_knn_ncu.md (the 157 MB key "
+                                     "array is written by the first kernel and read by the second)",
+                     "note": "an exact 50-nearest-neighbour search is not a bandwidth problem: 15 000 executed thread "
+                             "instructions per query (about 480 candidate distances, twice), issue- and latency-bound; "
+                             "the HBM fraction is reported because SURVEY 8d files the kernel under HBM/L2"}}
     # ---- single-frame latency: one context, the fits of a frame fanned out to 4 helper streams
     lctx = pkg.Context(env.local_rank, seed=12345)
     lctx.set_workers(4)

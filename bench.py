@@ -471,10 +471,10 @@ def arm_frames(env, args, pkg):
     alg_bytes = n_pts * 32  # 16 B per point in, 16 B per normal out
     info["normals"] = {
         "ms": normals_ms, "points": n_pts, "k": 50,
-        "share_of_gpu_time_per_frame": normals_ms / (1e3 * env.world / value) if value > 0 else None,
+        "frame_stream_ms_per_frame_per_gpu": (1e3 * env.world / value) if value > 0 else None,
         "queries_per_s": n_pts / (normals_ms * 1e-3),
-        "note": "whole-cloud NormalEstimation (pc_manager.cpp:68-78) alone on one stream; under the 16-context frame stream its "
-                "launches overlap with other frames' work",
+        "note": "whole-cloud NormalEstimation (pc_manager.cpp:68-78) alone on one stream (latency-bound there: about as long as a "
+                "whole frame costs inside the 16-context stream, where other frames' kernels fill its stalls)",
         "roofline": {"bound": "hbm", "kernel": "knn_collect_kernel + knn_finish_kernel (+ 9 grid-build launches)",
                      "achieved": alg_bytes / (normals_ms * 1e-3) / 1e9, "peak": MEASURED.get("hbm_gbs"), "unit": "GB/s",
                      "frac": ((alg_bytes / (normals_ms * 1e-3) / 1e9) / MEASURED["hbm_gbs"]) if MEASURED.get("hbm_gbs") else None,

@@ -413,7 +413,9 @@ int pitt_segment_frame(pitt_ctx* ctx, const pitt_cloud* cloud, const pitt_frame_
 /* C4: a stream of frames. Thread t of n_ctx host threads drives ctxs[t] (one stream each; the
  * contexts may sit on one GPU or on several) over frames t, t+n_ctx, ...: stage from the host
  * pointer (frames[i], n_points[i], stride_bytes), pitt_segment_frame, release. results[i] must
- * have its shapes buffer set. Returns the first non-OK status. */
+ * have its shapes buffer set. Returns the first non-OK status. The frame buffers are borrowed until the
+ * call returns: with stride_bytes == 16 (pinned memory recommended) the copy of a context's next frame is
+ * queued on a second stream while its current frame is segmented. */
 int pitt_segment_frames_batched(pitt_ctx* const* ctxs, int n_ctx, const void* const* frames, const int* n_points,
                                 int stride_bytes, int n_frames, const pitt_frame_params* params,
                                 pitt_frame_result* results);

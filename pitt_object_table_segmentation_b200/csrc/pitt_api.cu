@@ -91,6 +91,8 @@ void pitt_destroy(pitt_ctx* ctx) {
   for (cudaEvent_t e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
   if (ctx->ev_copy_gate) cudaEventDestroy(ctx->ev_copy_gate);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->h2d_stream) { cudaStreamSynchronize(ctx->h2d_stream); cudaStreamDestroy(ctx->h2d_stream); }
+  for (cudaEvent_t e : ctx->ev_h2d) if (e) cudaEventDestroy(e);
   if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);
   if (ctx->ev_k0) { cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1); }
   cudaEventDestroy(ctx->ev0);

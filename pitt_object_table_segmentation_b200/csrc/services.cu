@@ -1681,7 +1681,65 @@ int pitt_segment_raw_frames_batched(pitt_ctx* const* ctxs, int n_ctx, const void
   if (n_frames < 0 || (n_frames > 0 && (!frames || !n_points || !results)) || !params)
     return fail(ctxs[0], PITT_ERR_INVALID, "pitt_segment_frames_batched arguments");
   std::atomic<int> first_error(PITT_OK);
+  auto note = [&](int st) {
+    if (st != PITT_OK) {
+      int expected = PITT_OK;
+      first_error.compare_exchange_strong(expected, st);
+    }
+  };
+  // World-frame clouds in the HBM layout (point_step 16, no pre-filter): a context's frames are double-buffered. The copy of
+  // its next frame is queued on the context's copy stream before the current frame is segmented, so the 4.9 MB transfer and
+  // the wait for it (pitt_stage_cloud synchronises: the caller's buffer is only borrowed for that call; here it is borrowed for
+  // the whole batched call) disappear behind the previous frame's kernels.
+  auto worker_prefetch = [&](int t) {
+    pitt_ctx* ctx = ctxs[t];
+    cudaSetDevice(ctx->device);
+    if (!ctx->h2d_stream) {
+      if (cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ctx->ev_h2d[0], cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&ctx->ev_h2d[1], cudaEventDisableTiming) != cudaSuccess) {
+        note(fail(ctx, PITT_ERR_CUDA, "copy stream of the frame stream"));
+        return;
+      }
+    }
+    auto issue = [&](int i, int slot, pitt_cloud** out) -> int {
+      pitt_cloud* c = new pitt_cloud();
+      c->n = n_points[i];
+      if (c->n < 0 || (c->n > 0 && !frames[i])) { delete c; return fail(ctx, PITT_ERR_INVALID, "pitt_segment_frames_batched: frame pointer / size"); }
+      if (c->n > 0) {
+        if (pool_alloc(ctx, (size_t)c->n * sizeof(float4), (void**)&c->d_xyz) != PITT_OK) { delete c; return PITT_ERR_CUDA; }
+        cudaError_t e = cudaMemcpyAsync(c->d_xyz, frames[i], (size_t)c->n * 16, cudaMemcpyHostToDevice, ctx->h2d_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_h2d[slot], ctx->h2d_stream);
+        if (e != cudaSuccess) { pool_free(ctx, c->d_xyz, (size_t)c->n * sizeof(float4)); delete c; return fail(ctx, PITT_ERR_CUDA, "cudaMemcpyAsync(H2D frame)", e); }
+      }
+      *out = c;
+      return PITT_OK;
+    };
+    pitt_cloud* cur = nullptr;
+    int slot = 0;
+    int st = t < n_frames ? issue(t, slot, &cur) : PITT_OK;
+    note(st);
+    for (int i = t; i < n_frames && st == PITT_OK; i += n_ctx) {
+      pitt_cloud* next = nullptr;
+      int st_next = PITT_OK;
+      if (i + n_ctx < n_frames) st_next = issue(i + n_ctx, slot ^ 1, &next);
+      if (cur->n > 0 && cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[slot], 0) != cudaSuccess) st = fail(ctx, PITT_ERR_CUDA, "wait for the frame copy");
+      if (st == PITT_OK) st = pitt_segment_frame(ctx, cur, params, &results[i]);
+      if (st != PITT_OK) cudaStreamSynchronize(ctx->h2d_stream);
+      pitt_release_cloud(ctx, cur);
+      cur = next;
+      slot ^= 1;
+      note(st);
+      if (st == PITT_OK) { st = st_next; note(st); }
+    }
+    if (cur) {
+      cudaStreamSynchronize(ctx->h2d_stream);
+      pitt_release_cloud(ctx, cur);
+    }
+  };
+  const bool prefetch = !prefilter && stride_bytes == 16;
   auto worker = [&](int t) {
+    if (prefetch) { worker_prefetch(t); return; }
     pitt_ctx* ctx = ctxs[t];
     for (int i = t; i < n_frames; i += n_ctx) {
       pitt_cloud* c = nullptr;

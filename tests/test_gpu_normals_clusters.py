@@ -35,6 +35,26 @@ def test_knn_with_exact_ties_and_duplicates(ctx, oracle):
     assert np.array_equal(gi, ci) and np.array_equal(gs, cs)
 
 
+@pytest.mark.parametrize("jitter", [0.0, 1e-9])
+def test_knn_grid_path_with_ties_and_near_ties(ctx, oracle, jitter):
+    # Large enough for the multi-level grid path (> 4096 points). A lattice gives many EXACTLY equal distances per query
+    # (index order decides); with a 1e-9 jitter the same distances differ by a few ulps: both cases land in the
+    # "ambiguous" groups of the 32-bit sort (upper 26 bits of d2 equal), which are ordered by their true 64-bit keys.
+    g = np.stack(np.meshgrid(np.arange(96), np.arange(96), np.arange(2), indexing="ij"), -1).reshape(-1, 3)
+    rng = np.random.default_rng(11)
+    xyz = np.ones((len(g), 4), np.float32)
+    xyz[:, :3] = (g * 0.01 + rng.uniform(-jitter, jitter, g.shape)).astype(np.float32)
+    cloud = ctx.stage(xyz)
+    for k in (20, 50):
+        gi, gs = ctx.knn(cloud, k)
+        ci, cs = oracle.knn(xyz, k)
+        assert np.array_equal(gs, cs)
+        assert np.array_equal(gi, ci)
+    got = ctx.estimate_normals(cloud, 50, (0.0, 0.0, 1.0))
+    want = oracle.estimate_normals(xyz, 50, (0.0, 0.0, 1.0))
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
 def test_knn_small_clouds(ctx, oracle):
     for n in (1, 2, 5, 49):
         xyz = _frame(5)[:n]

@@ -1061,7 +1061,8 @@ knn_sort_kernel(const float4* __restrict__ sorted, const float4* __restrict__ xy
                 const unsigned long long* __restrict__ keys, const int* __restrict__ ncol, float vpx, float vpy, float vpz,
                 int* __restrict__ out_idx, float* __restrict__ out_sq, float4* __restrict__ out_nrm) {
   extern __shared__ unsigned s_dyn_idx[];
-  knn_sort_body<MODE, SEG, 0>(sorted, xyz, t_base, t_count, k, keys, ncol, vpx, vpy, vpz, out_idx, out_sq, out_nrm, blockIdx.x, s_dyn_idx);
+  knn_sort_body<MODE, SEG, 0>(sorted, xyz, t_base, t_count, k, keys, ncol, vpx, vpy, vpz, out_idx, out_sq, out_nrm,
+                              (int)gridDim.x - 1 - (int)blockIdx.x, s_dyn_idx);
 }
 template <int MODE, bool SEG>
 __global__ void __launch_bounds__(WS_WARPS * 32)
@@ -1087,7 +1088,9 @@ knn_finish_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, co
                                                 list, sm, blockIdx.x, wide_ctas);
   else
     knn_sort_body<MODE, SEG, KC>(sorted, xyz, 0, t_count, KC > 0 ? KC : k, keys, ncol, vpx, vpy, vpz, out_idx, out_sq, out_nrm,
-                                 blockIdx.x - wide_ctas, s_dyn_idx);
+                                 // last-written keys first: the collect kernel left the tail of the 157 MB key array in L2 and
+                                 // its head in DRAM; walking it backwards the sorting CTAs start on the resident part
+                                 (int)gridDim.x - 1 - (int)blockIdx.x, s_dyn_idx);
 }
 
 constexpr int KNN_TIMELINE_MAX = 8192;

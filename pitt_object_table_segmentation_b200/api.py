@@ -57,7 +57,9 @@ def torch_allgather_callback(group=None):
         try:
             world = dist.get_world_size(group)
             # the counts are produced on the context's stream: make it torch's current stream for the collective
-            with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+            # (ctypes hands a NULL void* over as None: a context created on the legacy default stream)
+            ts = torch.cuda.ExternalStream(int(stream)) if stream else torch.cuda.default_stream()
+            with torch.cuda.stream(ts):
                 send = torch.as_tensor(_DevArray(d_send, count), device="cuda")
                 recv = torch.as_tensor(_DevArray(d_recv, count * world), device="cuda")
                 dist.all_gather_into_tensor(recv, send, group=group)

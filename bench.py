@@ -489,16 +489,21 @@ def arm_frames(env, args, pkg):
                              "the HBM fraction is reported because SURVEY 8d files the kernel under HBM/L2"}}
     # ---- single-frame latency: one context, the fits of a frame fanned out to 4 helper streams
     lctx = pkg.Context(env.local_rank, seed=12345)
-    lctx.set_workers(4)
-    lat = []
-    for i in range(8):
-        t1 = time.perf_counter()
-        cl = lctx.stage_host_ptr(pinned[i % len(pinned)].data_ptr(), 16, int(pinned[i % len(pinned)].shape[0]))
-        lctx.segment_frame(cl)
-        cl.release()
-        lat.append((time.perf_counter() - t1) * 1e3)
-    info["frame_latency_ms"] = float(np.median(lat[2:]))
-    info["frame_latency_note"] = "one frame at a time: stage (H2D) + segment_frame + results, 1 context + 4 helper streams"
+    lctx.set_workers(0)
+    lat, lat_dev = [], []
+    for rnd in range(2):  # first round: the context's arena and pools grow to the sizes these frames need
+        for i in range(8):
+            t1 = time.perf_counter()
+            cl = lctx.stage_host_ptr(pinned[i % len(pinned)].data_ptr(), 16, int(pinned[i % len(pinned)].shape[0]))
+            fr1 = lctx.segment_frame(cl)
+            cl.release()
+            if rnd == 1:
+                lat.append((time.perf_counter() - t1) * 1e3)
+                lat_dev.append(float(fr1["device_ms"]))
+    info["frame_latency_ms"] = float(np.median(lat))
+    info["frame_latency_device_ms"] = float(np.median(lat_dev))
+    info["frame_latency_note"] = ("one frame at a time on one context: stage (H2D from pinned memory) + segment_frame + results, wall "
+                                  "clock; device_ms = the segment_frame part between two CUDA events")
     lctx.close()
 
     # ---- faithful variant (BASELINE configs[0] as the reference runs it): the raw camera-frame message through fromROSMsg + 1 cm

@@ -191,6 +191,37 @@ def test_segment_frames_batched_matches_single(ctx, oracle):
         c.close()
 
 
+def test_segment_frames_batched_ragged_empty_and_short_streams(oracle):
+    """the double-buffered frame stream (next frame's copy under the current frame's kernels) on a ragged stream: frames of
+    different sizes, an empty frame, a frame below the 30-point guard of depthAcquisition (obj_segmentation.cpp:251), more
+    contexts than frames, and no frames at all"""
+    big = scenes.tabletop_frame(seed=21, width=200, height=150, random_poses=True)
+    small = scenes.tabletop_frame(seed=22, width=120, height=90, random_poses=True)
+    frames = [big, np.zeros((0, 4), np.float32), small, big[:25].copy(), small[::2].copy(), big]
+    fp = oracle.default_frame_params()
+    want = [oracle.segment_frame(f, fp) if len(f) else None for f in frames]
+    for n_ctx in (1, 2, 8):
+        ctxs = [pkg.Context(0, seed=12345) for _ in range(n_ctx)]
+        try:
+            for _ in range(2):  # second pass: buffers come back from the contexts' pools
+                got = pkg.segment_frames_batched(ctxs, frames)
+                assert len(got) == len(frames)
+                for f, g, w in zip(frames, got, want):
+                    if len(f) <= 30:
+                        assert g["n_supports"] == 0 and g["n_clusters"] == 0 and g["shapes"] == []
+                        continue
+                    assert (g["n_supports"], g["n_clusters"], g["support_sizes"], g["on_support_sizes"]) == \
+                           (w["n_supports"], w["n_clusters"], w["support_sizes"], w["on_support_sizes"])
+                    assert _eq_f(g["support_coefficients"], w["support_coefficients"])
+                    for a, b in zip(g["shapes"], w["shapes"]):
+                        assert (a["tag"], a["n_points"], a["inliers"]) == (b["tag"], b["n_points"], b["inliers"])
+                        assert _eq_f(a["coefficients"], b["coefficients"]) and _eq_f(a["pc_centroid"], b["pc_centroid"])
+            assert len(pkg.segment_frames_batched(ctxs, [])) == 0
+        finally:
+            for c in ctxs:
+                c.close()
+
+
 @pytest.mark.parametrize("workers", [0, 1, 3, 12])
 def test_segment_frame_is_independent_of_worker_count(oracle, workers):
     """the primitive fits of a frame fan out to helper streams/threads; results must not depend on that"""

@@ -599,6 +599,22 @@ __device__ __forceinline__ void mg_for_cells27(const float4* __restrict__ sorted
 }
 
 
+// Squared distance in the oracle's operation order, (dx*dx + dy*dy) + dz*dz with every operation rounded on its own, with
+// the x and y lanes on the packed FP32 instructions of sm_100 (FADD2, FMUL2: two issue slots less per candidate). nqxy holds
+// (-q.x, -q.y): p + (-q) == -(q - p) bit for bit and the square does not see the sign.
+__device__ __forceinline__ unsigned long long knn_pack2(float lo, float hi) {
+  return ((unsigned long long)__float_as_uint(hi) << 32) | (unsigned long long)__float_as_uint(lo);
+}
+__device__ __forceinline__ float knn_d2(unsigned long long nqxy, float qz, const float4 p) {
+  unsigned long long d, sq;
+  const unsigned long long pxy = knn_pack2(p.x, p.y);
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pxy), "l"(nqxy));
+  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(sq) : "l"(d));
+  const float sx = __uint_as_float((unsigned)(sq & 0xffffffffull)), sy = __uint_as_float((unsigned)(sq >> 32));
+  const float ddz = qz - p.z;
+  return (sx + sy) + ddz * ddz;
+}
+
 // Fast path, first kernel: level choice, pass 1 (histogram -> threshold), pass 2 (the <= 64 candidates below the threshold as
 // 64-bit keys). Few registers and 4 KB of shared memory per warp, so an SM holds many warps and the latency of the lane-private
 // candidate streams is hidden by switching warps. The keys go to global memory laid out [slot][query] (coalesced: consecutive
@@ -622,6 +638,7 @@ knn_collect_body(const MGrid* __restrict__ G, const int* __restrict__ start, con
   unsigned* ccol = &s_cell[warp][0][lane];  // cell c of this thread's 27: ccol[c * 32]
   const float4 q = __ldg(sorted + t);
   const unsigned qw = __float_as_uint(q.w);
+  const unsigned long long nqxy = knn_pack2(-q.x, -q.y);
   const int cx = mg_coord(q.x, g.mnx, g.inv_hf, g.dx), cy = mg_coord(q.y, g.mny, g.inv_hf, g.dy), cz = mg_coord(q.z, g.mnz, g.inv_hf, g.dz);
   int lvl = mg_pick_level(start, mg_index(g, cx, cy, cz), need);
   // one attempt at this level (two when the 27 cells hold far more points than the level choice expected, i.e. at a density
@@ -657,11 +674,10 @@ knn_collect_body(const MGrid* __restrict__ G, const int* __restrict__ start, con
     // outside the window has a negative difference and lands in row -1, which nobody reads (shift, clamp, clamp, address:
     // no compare + select)
     mg_for_cells27(sorted, ccol, ncell, [&](const float4 p) {
-      const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
-      const int dd = (int)btop - __float_as_int((ddx * ddx + ddy * ddy) + ddz * ddz);  // both are bit patterns of floats >= 0
+      const int dd = (int)btop - __float_as_int(knn_d2(nqxy, q.z, p));  // both are bit patterns of floats >= 0
       int qq = max(min(dd >> 20, 31), -1);
       if (SEG && ((__float_as_uint(p.w) ^ qw) >> 24)) qq = -1;  // a point of another segment does not exist for this query
-      hcol[qq * 32] += 1u;
+      atomicAdd(&hcol[qq * 32], 1u);  // the thread's own column: one shared-memory atomic instead of load + add + store
     });
     int cum = 0, bsel = -1, cat = 0;  // bsel in the ascending numbering: bucket b = 31 - qq
 #pragma unroll
@@ -703,8 +719,7 @@ knn_collect_body(const MGrid* __restrict__ G, const int* __restrict__ start, con
   const size_t stride = (size_t)((t_count + 31) & ~31);
   int c = 0;
   mg_for_cells27(sorted, ccol, ncell, [&](const float4 p) {
-    const float ddx = q.x - p.x, ddy = q.y - p.y, ddz = q.z - p.z;
-    const unsigned db = __float_as_uint((ddx * ddx + ddy * ddy) + ddz * ddz);
+    const unsigned db = __float_as_uint(knn_d2(nqxy, q.z, p));
     if (db <= tsel && !(SEG && ((__float_as_uint(p.w) ^ qw) >> 24))) {
       kq[(size_t)c * stride] = ((unsigned long long)db << 32) | (unsigned long long)(unsigned)__float_as_int(p.w);
       ++c;

@@ -1071,7 +1071,7 @@ knn_wide_body(const MGrid* __restrict__ G, const int* __restrict__ start, const 
 
 
 template <int MODE, bool SEG>
-__global__ void __launch_bounds__(KNN_FAST_TPB, 5)
+__global__ void __launch_bounds__(KNN_FAST_TPB, 6)
 knn_sort_kernel(const float4* __restrict__ sorted, const float4* __restrict__ xyz, int t_base, int t_count, int k,
                 const unsigned long long* __restrict__ keys, const int* __restrict__ ncol, float vpx, float vpy, float vpz,
                 int* __restrict__ out_idx, float* __restrict__ out_sq, float4* __restrict__ out_nrm) {
@@ -1091,7 +1091,7 @@ knn_wide_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, cons
 // Second kernel of the fast path when the cloud is one chunk: the first `wide_ctas` CTAs serve the handed-over queries a warp each
 // (few, long searches: they start first and run beside the sorting CTAs instead of after them), the others sort.
 template <int MODE, bool SEG, int KC>
-__global__ void __launch_bounds__(KNN_FAST_TPB, 5)
+__global__ void __launch_bounds__(KNN_FAST_TPB, 6)
 knn_finish_kernel(const MGrid* __restrict__ G, const int* __restrict__ start, const float4* __restrict__ sorted,
                   const float4* __restrict__ xyz, int n_xyz, int t_count, int k, int need, const unsigned long long* __restrict__ keys,
                   const int* __restrict__ ncol, float vpx, float vpy, float vpz, int* __restrict__ out_idx, float* __restrict__ out_sq,

@@ -225,24 +225,27 @@ __global__ void fill_knn_kernel(int* idx, float* sq, size_t n) {
 // Everything is built on the device from device-resident geometry (no host round trip): bounding box -> geometry -> cell
 // histogram -> block totals -> scan of the block totals -> per-block scan -> scatter (the histogram counts back down to zero).
 //
-// knn_fast_kernel: one thread per query, 32 consecutive queries of the Morton-sorted array per warp (spatial neighbours:
-// their loops have the same shape, 31 of 32 lanes active on the frame). A query picks the finest level whose PARENT cell holds
-// >= `need` points and looks at the 3 x 3 x 3 cells around it at that level:
-//   pass 1  histogram of the squared distances (32 buckets of 1/8 octave below the distance to the faces of the 27-cell block,
-//           inside which every point closer than that is guaranteed to lie) -> the bucket edge T at which the cumulative count
-//           reaches k; usable when T exists and at most 64 candidates lie below it
-//   pass 2  the <= 64 candidates with d2 <= T go to the thread's column of a shared-memory buffer as 64-bit keys
-//           (bits(d2) << 32 | index): unsigned order == (distance, index) order, the tie rule of the oracle
-//   sort    64 keys in REGISTERS with Batcher's odd-even merge network (543 compare-exchanges, compile-time indices)
-//   finish  the first k keys in order: neighbour lists, or the sequential float covariance + eigen33 + flip of
-//           NormalEstimation::computeFeature, bit-identical to the warp-cooperative kernels.
-// No heap, no data-dependent sift loops, branch-free inner loops (rejected candidates go to a spare bucket / key slot), four
-// loads in flight per lane.
-// knn_wide_kernel: the general exact search, one warp per query (ballot compaction + register bitonic top-64 like the
+// Fast path, two kernels (one thread per query, 32 consecutive queries of the Morton-sorted array per warp: neighbouring
+// queries walk the same cells in step, so a candidate load is one broadcast for the warp):
+//   knn_collect_kernel  a query picks the finest level whose PARENT cell holds >= `need` points and takes the 3 x 3 x 3 cells
+//           around it at that level (their non-empty ranges looked up once into a shared-memory list);
+//           pass 1: histogram of the squared distances (32 buckets of 1/8 octave below the distance to the faces of the
+//           27-cell block, inside which every point closer than that is guaranteed to lie) -> the bucket edge T at which the
+//           cumulative count reaches k; usable when T exists and at most 64 candidates lie below it;
+//           pass 2: the <= 64 candidates with d2 <= T go to global memory as 64-bit keys (bits(d2) << 32 | index: unsigned
+//           order == (distance, index) order, the tie rule of the oracle), laid out [slot][query]. Few registers (64), 8 CTAs per
+//           SM: the latency of the candidate streams is hidden by switching warps.
+//   knn_finish_kernel   sorts a query's candidates in REGISTERS with Batcher's odd-even merge network (543 compare-exchanges,
+//           compile-time indices) on one 32-bit word per candidate (see knn_sort_body), then the first k in order: neighbour
+//           lists, or the sequential float covariance + eigen33 + flip of NormalEstimation::computeFeature,
+//           bit-identical to the warp-cooperative kernels. Its first CTAs serve the handed-over queries (below).
+// No heap, no data-dependent sift loops, branch-free inner loops (rejected candidates go to a spare histogram row).
+// knn_wide_body: the general exact search, one warp per query (ballot compaction + register bitonic top-64 like the
 // all-pairs kernel), over the 27 cells at rising levels and then over growing cubes of the coarsest cells, for the queries the
-// fast path hands over (0.4 % of the frame: sparse corners, density steps, > 64 candidates in one bucket, duplicates) and for
-// k > KNN_FAST_KMAX. Measured on B200 (307 200-point frame, k = 50): build 0.05 ms, fast 0.78 ms, wide 0.23 ms
-// (profiles/r02_knn_ncu.md); the round-1 heap kernel took 1.01 ms after a 0.15 ms build with two host round trips.
+// fast path hands over (96 of the 307 200 of a frame: sparse corners, density steps, > 64 candidates in one bucket,
+// duplicates) and for k > KNN_FAST_KMAX. Measured on B200 (307 200-point frame, k = 50, profiles/r02_knn_ncu.md): build
+// 0.05 ms, whole normal estimation 0.59-0.61 ms alone on the GPU (134 M + 38 M warp instructions in the two kernels); the
+// round-1 heap kernel took 1.01 ms after a 0.15 ms build with two host round trips.
 // =====================================================================================================================
 constexpr int KNN_FAST_KMAX = 56;      // 64-key buffer: k plus the contents of one 1/8-octave bucket
 constexpr int KNN_FAST_TPB = 128;

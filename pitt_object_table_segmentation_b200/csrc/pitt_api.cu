@@ -91,6 +91,9 @@ void pitt_destroy(pitt_ctx* ctx) {
   for (cudaEvent_t e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
   if (ctx->ev_copy_gate) cudaEventDestroy(ctx->ev_copy_gate);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+  if (ctx->ev_aux_fork) cudaEventDestroy(ctx->ev_aux_fork);
+  if (ctx->ev_aux_join) cudaEventDestroy(ctx->ev_aux_join);
   if (ctx->h2d_stream) { cudaStreamSynchronize(ctx->h2d_stream); cudaStreamDestroy(ctx->h2d_stream); }
   for (cudaEvent_t e : ctx->ev_h2d) if (e) cudaEventDestroy(e);
   if (ctx->ev_block) cudaEventDestroy(ctx->ev_block);

@@ -63,6 +63,9 @@ struct pitt_ctx {
   const int* skip_flag = nullptr;  // sac.cu: device word read by the estimate / score kernels launched while it is set (non-zero: return)
   void* mg_tables = nullptr;  // knn.cu: the two dense cell tables of the multi-level grid (allocated on first use)
   int* knn_scr = nullptr;     // knn.cu: scratch of the last large-cloud k-NN (diagnostics, arena memory)
+  // services.cu, pitt_segment_frame: the whole-cloud normals (which findSupports never reads) run on this stream beside the supports loop
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_aux_fork = nullptr, ev_aux_join = nullptr;
   // services.cu, batched frame streams: the next frame's host -> device copy runs on this stream while the current frame is segmented
   cudaStream_t h2d_stream = nullptr;
   cudaEvent_t ev_h2d[2] = {};

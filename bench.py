@@ -925,6 +925,9 @@ def main():
                         clocks=fr["clocks"], e2e=fr["e2e"], gpu_launches=fr["launches"], parity_checked=fr["parity"],
                         frames={k: v for k, v in fr.items() if k not in ("clocks", "e2e", "parity", "cpu_baseline")},
                         wall_s_timed_region=fr["wall_s"])
+            # the frame path's own dominant kernel group (whole-cloud normals) beside the RANSAC scoring roofline
+            if "normals" in fr:
+                line["roofline_frame"] = dict(fr["normals"]["roofline"], kernel_ms=fr["normals"]["ms"])
             if ransac:
                 line["roofline"] = ransac["roofline"]
                 line["ransac"] = {k: v for k, v in ransac.items() if k != "roofline"}
